@@ -1,0 +1,102 @@
+// Entropy-code front end: parses histogram sets (ANS alias tables / prefix
+// code LUTs, context maps, hybrid-uint configs, LZ77 params) into flat tables
+// that both the host-side symbol reader (used for headers, trees, LF and
+// HF-metadata streams) and the device kernels consume unchanged.
+//
+// Reference: jxl/src/entropy_coding/{decode,ans,huffman,hybrid_uint,context_map}.rs
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "bitreader.h"
+
+namespace jxg {
+
+// hybrid_uint.rs:11-16, packed for the device as
+//   split_exponent | msb_in_token << 8 | lsb_in_token << 16
+struct HybridUint {
+  uint32_t split_exponent = 0, msb = 0, lsb = 0;
+  uint32_t split_token() const { return 1u << split_exponent; }
+  uint32_t packed() const { return split_exponent | (msb << 8) | (lsb << 16); }
+  static HybridUint decode(uint32_t log_alpha_size, BitReader& br);
+  // hybrid_uint.rs:87-102
+  inline uint32_t read(uint32_t token, BitReader& br) const {
+    if (token < split_token()) return token;
+    uint32_t bits_in_token = lsb + msb;
+    uint32_t nbits = (split_exponent - bits_in_token + ((token - split_token()) >> bits_in_token)) & 31;
+    uint32_t low = token & ((1u << lsb) - 1);
+    uint32_t token_nolow = token >> lsb;
+    uint32_t bits = uint32_t(br.read(nbits));
+    uint32_t hi = (token_nolow & ((1u << msb) - 1)) | (1u << msb);
+    return (((hi << nbits) | bits) << lsb) | low;
+  }
+};
+
+// ans.rs:31-39 — 8-byte alias-table bucket, same field order and widths.
+struct AnsBucket {
+  uint8_t alias_symbol;
+  uint8_t alias_cutoff;
+  uint16_t dist;
+  uint16_t alias_offset;
+  uint16_t alias_dist_xor;
+};
+static_assert(sizeof(AnsBucket) == 8, "bucket must be 8 bytes");
+
+// huffman.rs:18-21, packed as bits | value << 16.
+using HuffEntry = uint32_t;
+
+struct EntropyCode {
+  // decode.rs:36-45
+  bool lz77_enabled = false;
+  uint32_t lz77_min_symbol = 0, lz77_min_length = 0;
+  HybridUint lz77_length_uint;
+  uint32_t lz_dist_cluster = 0;
+
+  bool use_prefix = false;
+  uint32_t log_alpha_size = 0;
+  std::vector<uint8_t> context_map;  // context -> cluster
+  uint32_t num_clusters = 0;
+  std::vector<HybridUint> uint_configs;  // per cluster
+  // ANS: num_clusters << log_alpha_size buckets.
+  std::vector<AnsBucket> ans_buckets;
+  // Prefix: per-cluster LUT (>= 256 root entries + 2nd level), concatenated.
+  std::vector<HuffEntry> huff_entries;
+  std::vector<uint32_t> huff_offset;  // per cluster, into huff_entries
+  std::vector<int32_t> single_symbol;  // per cluster, -1 if none
+
+  // decode.rs:487-545
+  static EntropyCode decode(size_t num_contexts, BitReader& br, bool allow_lz77);
+  bool is_rle() const;
+};
+
+constexpr uint32_t kAnsChecksum = 0x130000;  // ans.rs:425
+constexpr uint32_t kAnsLogSumProbs = 12;
+
+// decode.rs:177-405 (host copy; the device kernel has its own).
+class SymbolReader {
+ public:
+  SymbolReader(const EntropyCode& code, BitReader& br, size_t dist_multiplier);
+  uint32_t read_unsigned(BitReader& br, size_t ctx) { return read_clustered(br, code_.context_map[ctx]); }
+  int32_t read_signed(BitReader& br, size_t ctx) { return unpack_signed(read_unsigned(br, ctx)); }
+  uint32_t read_clustered(BitReader& br, uint32_t cluster);
+  // decode.rs:400: latched errors, over-read, final ANS state.
+  void check_final_state(BitReader& br) const;
+
+ private:
+  inline uint32_t read_token(BitReader& br, uint32_t cluster);
+  const EntropyCode& code_;
+  uint32_t state_ = kAnsChecksum;
+  // LZ77 (decode.rs:73-147)
+  std::vector<uint32_t> window_;
+  uint32_t dist_multiplier_ = 0, num_to_copy_ = 0, copy_pos_ = 0, num_decoded_ = 0;
+  bool err_lz77_repeat_ = false, err_overflow_ = false;
+};
+
+// context_map.rs:43
+std::vector<uint8_t> decode_context_map(size_t num_contexts, BitReader& br);
+
+// headers/permutation.rs:27-160 (Lehmer-coded permutation)
+std::vector<uint32_t> decode_permutation(uint32_t size, uint32_t skip, const EntropyCode& code, BitReader& br,
+                                         SymbolReader& reader);
+
+}  // namespace jxg

@@ -1,0 +1,449 @@
+// See frame.h.
+#include "frame.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "quant.h"
+
+namespace jxg {
+
+namespace {
+
+// Re-packs the bits of `data` starting at bit `bit_pos` into a fresh byte
+// vector (only needed for single-section frames, frame_info.rs:414-450, where
+// the HF group follows HfGlobal without byte alignment).
+std::vector<uint8_t> repack_bits(const uint8_t* data, size_t size, size_t bit_pos) {
+  std::vector<uint8_t> out;
+  size_t byte = bit_pos / 8, sh = bit_pos % 8;
+  if (sh == 0) return std::vector<uint8_t>(data + std::min(byte, size), data + size);
+  for (size_t i = byte; i < size; i++) {
+    uint32_t lo = data[i] >> sh;
+    uint32_t hi = i + 1 < size ? uint32_t(data[i + 1]) << (8 - sh) : 0;
+    out.push_back(uint8_t(lo | hi));
+  }
+  return out;
+}
+
+// frame/decode.rs:307-427
+void decode_lf_global(FrameState& fs, BitReader& br) {
+  const FrameHeader& h = fs.header;
+  if (h.has_patches()) fail("patches are outside the hot-path scope", kErrUnsupported);
+  if (h.has_splines()) fail("splines are outside the hot-path scope", kErrUnsupported);
+  if (h.has_noise())
+    for (int i = 0; i < 8; i++) br.read(10);  // features/noise.rs:14 (parsed, not rendered)
+  // LfQuantFactors (quantizer.rs:28-52)
+  if (!br.read_bool()) {
+    for (float& q : fs.lf_quant) {
+      q = read_f16(br) / 128.0f;
+      if (q < 1e-8f) fail("LF quant factor too small");
+    }
+  }
+  // QuantizerParams (quantizer.rs:60-77)
+  switch (br.read(2)) {
+    case 0: fs.global_scale = uint32_t(br.read(11)) + 1; break;
+    case 1: fs.global_scale = uint32_t(br.read(11)) + 2049; break;
+    case 2: fs.global_scale = uint32_t(br.read(12)) + 4097; break;
+    default: fs.global_scale = uint32_t(br.read(16)) + 8193;
+  }
+  switch (br.read(2)) {
+    case 0: fs.quant_lf = 16; break;
+    case 1: fs.quant_lf = uint32_t(br.read(5)) + 1; break;
+    case 2: fs.quant_lf = uint32_t(br.read(8)) + 1; break;
+    default: fs.quant_lf = uint32_t(br.read(16)) + 1;
+  }
+  // BlockContextMap (block_context_map.rs:61-126)
+  if (br.read_bool()) {
+    static const uint8_t kDefault[39] = {0, 1, 2, 2, 3,  3,  4,  5,  6,  6,  6,  6,  6,  7, 8, 9, 9, 10, 11, 12,
+                                         13, 14, 14, 14, 14, 14, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14};
+    fs.block_ctx_map.assign(kDefault, kDefault + 39);
+    fs.num_lf_contexts = 1;
+    fs.num_block_contexts = 15;
+  } else {
+    fs.num_lf_contexts = 1;
+    for (auto& thr : fs.lf_thresholds) {
+      size_t n = size_t(br.read(4));
+      thr.resize(n);
+      for (auto& v : thr) {
+        uint64_t u;
+        switch (br.read(2)) {
+          case 0: u = br.read(4); break;
+          case 1: u = br.read(8) + 16; break;
+          case 2: u = br.read(16) + 272; break;
+          default: u = br.read(32) + 65808;
+        }
+        v = unpack_signed(uint32_t(u));
+      }
+      fs.num_lf_contexts *= uint32_t(n + 1);
+    }
+    size_t nq = size_t(br.read(4));
+    fs.qf_thresholds.resize(nq);
+    for (auto& v : fs.qf_thresholds) {
+      switch (br.read(2)) {
+        case 0: v = uint32_t(br.read(2)); break;
+        case 1: v = uint32_t(br.read(3)) + 4; break;
+        case 2: v = uint32_t(br.read(5)) + 12; break;
+        default: v = uint32_t(br.read(8)) + 44;
+      }
+      v += 1;
+    }
+    if (fs.num_lf_contexts * (nq + 1) > 64) fail("block context map too big");
+    fs.block_ctx_map = decode_context_map(3 * kNumOrders * fs.num_lf_contexts * (nq + 1), br);
+    fs.num_block_contexts = uint32_t(*std::max_element(fs.block_ctx_map.begin(), fs.block_ctx_map.end())) + 1;
+    if (fs.num_block_contexts > 16) fail("too many block contexts");
+  }
+  // ColorCorrelationParams (color_correlation_map.rs:43-75)
+  if (!br.read_bool()) {
+    switch (br.read(2)) {
+      case 0: fs.color_factor = 84; break;
+      case 1: fs.color_factor = 256; break;
+      case 2: fs.color_factor = uint32_t(br.read(8)) + 2; break;
+      default: fs.color_factor = uint32_t(br.read(16)) + 258;
+    }
+    fs.base_correlation_x = read_f16(br);
+    fs.base_correlation_b = read_f16(br);
+    if (fs.base_correlation_x > 4.0f || fs.base_correlation_b > 4.0f) fail("base colour correlation out of range");
+    fs.ytox_lf = int32_t(br.read(8)) - 128;
+    fs.ytob_lf = int32_t(br.read(8)) - 128;
+  }
+  // global MA tree (frame/decode.rs:380-391)
+  if (br.read_bool()) {
+    size_t limit = std::min<size_t>(1024 + size_t(h.width) * h.height * 3 / 16, size_t(1) << 22);
+    fs.global_tree = ModularTree::read(br, limit);
+    fs.has_global_tree = true;
+  }
+  // FullModularImage::read: zero channels for VarDCT without extra channels (modular/mod.rs:303-321).
+  br.check();
+}
+
+// modular/mod.rs:837-1080
+void decode_lf_group(FrameState& fs, uint32_t g, BitReader& br) {
+  const FrameHeader& h = fs.header;
+  const uint32_t gd = h.group_dim();  // LF group = group_dim blocks
+  uint32_t gx = g % h.xsize_lf_groups(), gy = g / h.xsize_lf_groups();
+  uint32_t x0 = gx * gd, y0 = gy * gd;
+  uint32_t w = std::min(gd, fs.xb - x0), hh = std::min(gd, fs.yb - y0);
+  const ModularTree* gt = fs.has_global_tree ? &fs.global_tree : nullptr;
+  // ---- LF coefficients (decode_vardct_lf) ----
+  uint32_t extra_precision = uint32_t(br.read(2));
+  float mul = 1.0f / float(1u << extra_precision);
+  {
+    std::vector<ModularChannel> ch;
+    for (int c = 0; c < 3; c++) ch.emplace_back(w, hh);
+    decode_modular_subbitstream(ch, 1 + g, gt, br);
+    // dequant_lf (444): channel 0 = Y, 1 = X, 2 = B
+    float inv_quant_lf = 65536.0f / (float(fs.global_scale) * float(fs.quant_lf));
+    float fac_x = fs.lf_quant[0] * inv_quant_lf * mul;
+    float fac_y = fs.lf_quant[1] * inv_quant_lf * mul;
+    float fac_b = fs.lf_quant[2] * inv_quant_lf * mul;
+    float cfl_x = fs.base_correlation_x + float(fs.ytox_lf) / float(fs.color_factor);
+    float cfl_b = fs.base_correlation_b + float(fs.ytob_lf) / float(fs.color_factor);
+    for (uint32_t y = 0; y < hh; y++) {
+      const int32_t *qy = ch[0].row(y), *qx = ch[1].row(y), *qb = ch[2].row(y);
+      size_t o = size_t(y0 + y) * fs.xb + x0;
+      for (uint32_t x = 0; x < w; x++) {
+        float in_x = float(qx[x]) * fac_x, in_y = float(qy[x]) * fac_y, in_b = float(qb[x]) * fac_b;
+        fs.lf[1][o + x] = in_y;
+        fs.lf[0][o + x] = in_y * cfl_x + in_x;
+        fs.lf[2][o + x] = in_y * cfl_b + in_b;
+      }
+      if (fs.num_lf_contexts > 1) {
+        for (uint32_t x = 0; x < w; x++) {
+          auto bucket = [](const std::vector<int32_t>& thr, int32_t v) {
+            uint32_t n = 0;
+            for (int32_t t : thr) n += v > t;
+            return n;
+          };
+          uint32_t b = bucket(fs.lf_thresholds[0], qx[x]);
+          b = b * uint32_t(fs.lf_thresholds[2].size() + 1) + bucket(fs.lf_thresholds[2], qb[x]);
+          b = b * uint32_t(fs.lf_thresholds[1].size() + 1) + bucket(fs.lf_thresholds[1], qy[x]);
+          fs.quant_lf_map[o + x] = uint8_t(b);
+        }
+      }
+    }
+  }
+  // ModularLF stream: no channels in a VarDCT frame without extra channels.
+  // ---- HF metadata (decode_hf_metadata) ----
+  {
+    uint32_t count = uint32_t(br.read(ceil_log2(uint64_t(w) * hh))) + 1;
+    uint32_t cw = (w + 7) / 8, chh = (hh + 7) / 8;
+    std::vector<ModularChannel> ch;
+    ch.emplace_back(cw, chh, 3, 3);
+    ch.emplace_back(cw, chh, 3, 3);
+    ch.emplace_back(count, 2);
+    ch.emplace_back(w, hh);
+    size_t stream_id = 1 + 2 * size_t(h.num_lf_groups()) + g;
+    decode_modular_subbitstream(ch, stream_id, gt, br);
+    uint32_t cxb = (fs.xb + 7) / 8;
+    for (uint32_t y = 0; y < chh; y++)
+      for (uint32_t x = 0; x < cw; x++) {
+        size_t o = size_t(y0 / 8 + y) * cxb + x0 / 8 + x;
+        fs.ytox_map[o] = int8_t(std::clamp(ch[0].row(y)[x], -128, 127));
+        fs.ytob_map[o] = int8_t(std::clamp(ch[1].row(y)[x], -128, 127));
+      }
+    uint32_t num = 0;
+    for (uint32_t y = 0; y < hh; y++) {
+      for (uint32_t x = 0; x < w; x++) {
+        size_t o = size_t(y0 + y) * fs.xb + x0 + x;
+        int32_t epf = ch[3].row(y)[x];
+        if (epf < 0 || epf > 7) fail("invalid EPF sharpness value");
+        fs.epf_map[o] = uint8_t(epf);
+        if (fs.transform_map[o] != 27) continue;  // already covered by an earlier varblock
+        if (num >= count) fail("invalid VarDCT transform map");
+        int32_t raw_transform = ch[2].row(0)[num];
+        int32_t raw_quant = 1 + std::clamp(ch[2].row(1)[num], 0, 255);
+        if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
+        uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
+        uint32_t ngx = (x / 32 + 1) * 32, ngy = (y / 32 + 1) * 32;
+        if (x + cx > std::min(w, ngx) || y + cy > std::min(hh, ngy)) fail("HF block out of bounds");
+        num++;
+        for (uint32_t iy = 0; iy < cy; iy++)
+          for (uint32_t ix = 0; ix < cx; ix++) {
+            size_t oo = size_t(y0 + y + iy) * fs.xb + x0 + x + ix;
+            fs.transform_map[oo] = uint8_t(raw_transform) | ((ix == 0 && iy == 0) ? 128 : 0);
+            fs.raw_quant_map[oo] = raw_quant;
+          }
+      }
+    }
+  }
+  br.check();
+}
+
+// frame/decode.rs:506-566
+void decode_hf_global(FrameState& fs, BitReader& br) {
+  const FrameHeader& h = fs.header;
+  const ModularTree* gt = fs.has_global_tree ? &fs.global_tree : nullptr;
+  if (!br.read_bool()) {  // DequantMatrices::decode, quant_weights.rs:1088-1120
+    for (int i = 0; i < kNumQuantTables; i++) {
+      QuantEncoding e = read_quant_encoding(i, br, h, gt);
+      if (e.mode != QuantEncoding::kLibrary) fs.custom_dequant[i] = compute_dequant_table(e, i);
+    }
+  }
+  fs.num_histograms = uint32_t(br.read(ceil_log2(h.num_groups()))) + 1;
+  fs.passes.resize(h.passes.num_passes);
+  for (uint32_t p = 0; p < h.passes.num_passes; p++) {
+    PassState& ps = fs.passes[p];
+    uint32_t used_orders;
+    switch (br.read(2)) {
+      case 0: used_orders = 0x5f; break;
+      case 1: used_orders = 0x13; break;
+      case 2: used_orders = 0; break;
+      default: used_orders = uint32_t(br.read(kNumOrders));
+    }
+    if (used_orders) {  // coeff_order.rs:122-152
+      ps.custom_orders = true;
+      std::vector<std::vector<uint32_t>> orders(3 * kNumOrders);
+      for (int o = 0; o < 3 * kNumOrders; o++) orders[o] = natural_coeff_order(o / 3);
+      EntropyCode code = EntropyCode::decode(8, br, true);
+      SymbolReader reader(code, br, 0);
+      for (int ord = 0; ord < kNumOrders; ord++) {
+        if (!(used_orders & (1u << ord))) continue;
+        int t = kOrderTransform[ord];
+        uint32_t num_blocks = uint32_t(kCoveredBlocksX[t]) * kCoveredBlocksY[t];
+        for (int c = 0; c < 3; c++) {
+          std::vector<uint32_t> perm = decode_permutation(num_blocks * 64, num_blocks, code, br, reader);
+          std::vector<uint32_t>& o = orders[3 * ord + c];
+          std::vector<uint32_t> tmp(o.size());
+          for (size_t i = 0; i < o.size(); i++) tmp[i] = o[perm[i]];  // Permutation::compose
+          o = std::move(tmp);
+        }
+      }
+      reader.check_final_state(br);
+      for (int o = 0; o < 3 * kNumOrders; o++) {
+        ps.coeff_order_offset[o] = uint32_t(ps.coeff_order.size());
+        ps.coeff_order.insert(ps.coeff_order.end(), orders[o].begin(), orders[o].end());
+      }
+    }
+    size_t num_contexts = size_t(fs.num_histograms) * fs.num_ac_contexts();
+    ps.code = EntropyCode::decode(num_contexts, br, true);
+    // frame/decode.rs:536-538: pad so that zero-density contexts never index past the map.
+    ps.code.context_map.resize(ps.code.context_map.size() + 16, 0);
+    for (auto& u : ps.code.uint_configs) ps.uint_configs_packed.push_back(u.packed());
+  }
+  br.check();
+}
+
+// frame/adaptive_lf_smoothing.rs:44-125
+void adaptive_lf_smoothing(FrameState& fs) {
+  const size_t xs = fs.xb, ys = fs.yb;
+  if (xs <= 2 || ys <= 2) return;
+  float inv_quant_lf = (65536.0f / float(fs.global_scale)) / float(fs.quant_lf);
+  float lf_factors[3] = {inv_quant_lf * fs.lf_quant[0], inv_quant_lf * fs.lf_quant[1], inv_quant_lf * fs.lf_quant[2]};
+  const float kSide = 0.20345139757231578f, kCorner = 0.0334829185968739f;
+  const float kCenter = 1.0f - 4.0f * (kSide + kCorner);
+  std::vector<float> out[3] = {fs.lf[0], fs.lf[1], fs.lf[2]};
+  for (size_t y = 1; y + 1 < ys; y++) {
+    for (size_t x = 1; x + 1 < xs; x++) {
+      float gap = 0.5f, mc[3], sm[3];
+      for (int c = 0; c < 3; c++) {
+        const float* t = &fs.lf[c][(y - 1) * xs];
+        const float* m = &fs.lf[c][y * xs];
+        const float* b = &fs.lf[c][(y + 1) * xs];
+        float corner = t[x - 1] + t[x + 1] + b[x - 1] + b[x + 1];
+        float side = m[x - 1] + m[x + 1] + t[x] + b[x];
+        mc[c] = m[x];
+        sm[c] = corner * kCorner + side * kSide + mc[c] * kCenter;
+        gap = std::max(gap, std::fabs((mc[c] - sm[c]) / lf_factors[c]));
+      }
+      float factor = std::max(3.0f - 4.0f * gap, 0.0f);
+      for (int c = 0; c < 3; c++) out[c][y * xs + x] = (sm[c] - mc[c]) * factor + mc[c];
+    }
+  }
+  for (int c = 0; c < 3; c++) fs.lf[c] = std::move(out[c]);
+}
+
+}  // namespace
+
+std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) {
+  auto fsp = std::make_unique<FrameState>();
+  FrameState& fs = *fsp;
+  fs.codestream = extract_codestream(data, size);
+  BitReader br(fs.codestream.data(), fs.codestream.size());
+  fs.file = read_file_header(br);
+  if (fs.file.have_preview) fail("preview frames are outside the hot-path scope", kErrUnsupported);
+  fs.header = read_frame_header(br, fs.file);
+  FrameHeader& h = fs.header;
+  if (h.encoding != 0) fail("not a VarDCT frame (Modular frames use the Modular path)", kErrUnsupported);
+  if (h.frame_type != 0) fail("only regular frames are in scope", kErrUnsupported);
+  if (!fs.file.xyb_encoded || h.do_ycbcr) fail("non-XYB VarDCT (JPEG recompression) is outside the scope", kErrUnsupported);
+  if (h.num_extra_channels) fail("extra channels are outside the hot-path scope", kErrUnsupported);
+  if (h.upsampling != 1) fail("upsampling is outside the hot-path scope", kErrUnsupported);
+  if (h.has_lf_frame()) fail("LF frames are outside the hot-path scope", kErrUnsupported);
+  if (h.have_crop || h.blending.mode != 0) fail("cropped/blended frames are outside the hot-path scope", kErrUnsupported);
+  fs.toc = read_toc(br, h.num_toc_entries());
+  fs.sections_base = br.byte_pos();
+  const uint8_t* base = fs.codestream.data() + fs.sections_base;
+  size_t avail = fs.codestream.size() - fs.sections_base;
+  for (size_t i = 0; i < fs.toc.offsets.size(); i++)
+    if (fs.toc.offsets[i] + fs.toc.lengths[i] > avail) fail("truncated file: section beyond end", kErrOutOfBounds);
+
+  fs.xb = h.xsize_blocks();
+  fs.yb = h.ysize_blocks();
+  size_t nb = size_t(fs.xb) * fs.yb;
+  for (auto& p : fs.lf) p.assign(nb, 0.0f);
+  fs.transform_map.assign(nb, 27);
+  fs.raw_quant_map.assign(nb, 0);
+  fs.epf_map.assign(nb, 0);
+  fs.quant_lf_map.assign(nb, 0);
+  size_t ncm = size_t((fs.xb + 7) / 8) * ((fs.yb + 7) / 8);
+  fs.ytox_map.assign(ncm, 0);
+  fs.ytob_map.assign(ncm, 0);
+
+  const uint32_t num_groups = h.num_groups(), num_passes = h.passes.num_passes;
+  fs.hf_off.assign(size_t(num_groups) * num_passes, 0);
+  fs.hf_len.assign(size_t(num_groups) * num_passes, 0);
+
+  if (fs.toc.offsets.size() == 1) {
+    BitReader sbr(base + fs.toc.offsets[0], fs.toc.lengths[0]);
+    decode_lf_global(fs, sbr);
+    decode_lf_group(fs, 0, sbr);
+    decode_hf_global(fs, sbr);
+    // The single HF group follows without alignment: re-pack it byte aligned at the end of the codestream buffer.
+    std::vector<uint8_t> packed = repack_bits(base + fs.toc.offsets[0], fs.toc.lengths[0], sbr.total_bits_read());
+    fs.hf_off[0] = fs.codestream.size();
+    fs.hf_len[0] = uint32_t(packed.size());
+    fs.codestream.insert(fs.codestream.end(), packed.begin(), packed.end());
+  } else {
+    {
+      BitReader sbr(base + fs.toc.offsets[0], fs.toc.lengths[0]);
+      decode_lf_global(fs, sbr);
+    }
+    for (uint32_t g = 0; g < h.num_lf_groups(); g++) {
+      BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
+      decode_lf_group(fs, g, sbr);
+    }
+    {
+      size_t s = 1 + h.num_lf_groups();
+      BitReader sbr(base + fs.toc.offsets[s], fs.toc.lengths[s]);
+      decode_hf_global(fs, sbr);
+    }
+    for (uint32_t p = 0; p < num_passes; p++)
+      for (uint32_t g = 0; g < num_groups; g++) {
+        size_t s = 2 + h.num_lf_groups() + size_t(num_groups) * p + g;
+        fs.hf_off[size_t(p) * num_groups + g] = fs.sections_base + fs.toc.offsets[s];
+        fs.hf_len[size_t(p) * num_groups + g] = fs.toc.lengths[s];
+      }
+  }
+  for (uint8_t t : fs.transform_map)
+    if (t == 27) fail("VarDCT transform map has uncovered blocks");
+  if (h.adaptive_lf_smoothing()) adaptive_lf_smoothing(fs);
+  return fsp;
+}
+
+void FrameState::fill_desc(JxgFrameDesc* d, uint32_t output_format) {
+  memset(d, 0, sizeof(*d));
+  d->abi_version = JXG_ABI_VERSION;
+  d->width = header.xsize();
+  d->height = header.ysize();
+  d->global_scale = global_scale;
+  d->x_qm_scale = header.x_qm_scale;
+  d->b_qm_scale = header.b_qm_scale;
+  memcpy(d->quant_biases, file.opsin.quant_biases, sizeof(d->quant_biases));
+  d->base_correlation_x = base_correlation_x;
+  d->base_correlation_b = base_correlation_b;
+  d->color_factor = color_factor;
+  d->num_qf_thresholds = uint32_t(qf_thresholds.size());
+  for (size_t i = 0; i < qf_thresholds.size(); i++) d->qf_thresholds[i] = qf_thresholds[i];
+  d->num_lf_contexts = num_lf_contexts;
+  d->num_block_contexts = num_block_contexts;
+  d->block_ctx_map_len = uint32_t(block_ctx_map.size());
+  d->block_ctx_map = block_ctx_map.data();
+  d->num_histograms = num_histograms;
+  d->num_passes = uint32_t(passes.size());
+  pass_descs.assign(passes.size(), JxgPassDesc{});
+  for (size_t p = 0; p < passes.size(); p++) {
+    PassState& ps = passes[p];
+    JxgPassDesc& pd = pass_descs[p];
+    pd.shift = p < header.passes.shift.size() ? header.passes.shift[p] : 0;
+    pd.use_prefix = ps.code.use_prefix;
+    pd.log_alpha_size = ps.code.log_alpha_size;
+    pd.num_clusters = ps.code.num_clusters;
+    pd.num_contexts = uint32_t(ps.code.context_map.size());
+    pd.lz77_enabled = ps.code.lz77_enabled;
+    pd.lz77_min_symbol = ps.code.lz77_min_symbol;
+    pd.lz77_min_length = ps.code.lz77_min_length;
+    pd.lz77_length_uint = ps.code.lz77_length_uint.packed();
+    pd.lz_dist_cluster = ps.code.lz_dist_cluster;
+    pd.context_map = ps.code.context_map.data();
+    pd.uint_configs = ps.uint_configs_packed.data();
+    pd.ans_buckets = reinterpret_cast<const uint64_t*>(ps.code.ans_buckets.data());
+    pd.huff_entries = ps.code.huff_entries.data();
+    pd.huff_offset = ps.code.huff_offset.data();
+    pd.huff_entries_len = uint32_t(ps.code.huff_entries.size());
+    if (ps.custom_orders) {
+      pd.coeff_order = ps.coeff_order.data();
+      memcpy(pd.coeff_order_offset, ps.coeff_order_offset, sizeof(pd.coeff_order_offset));
+      pd.coeff_order_len = uint32_t(ps.coeff_order.size());
+    }
+  }
+  d->passes = pass_descs.data();
+  for (int i = 0; i < kNumQuantTables; i++) d->dequant_tables[i] = custom_dequant[i].empty() ? nullptr : custom_dequant[i].data();
+  for (int c = 0; c < 3; c++) d->lf[c] = lf[c].data();
+  d->transform_map = transform_map.data();
+  d->raw_quant_map = raw_quant_map.data();
+  d->epf_map = epf_map.data();
+  d->quant_lf = quant_lf_map.data();
+  d->ytox_map = ytox_map.data();
+  d->ytob_map = ytob_map.data();
+  const RestorationFilter& rf = header.rf;
+  d->gab = rf.gab;
+  memcpy(d->gab_w1, rf.gab_w1, sizeof(d->gab_w1));
+  memcpy(d->gab_w2, rf.gab_w2, sizeof(d->gab_w2));
+  d->epf_iters = rf.epf_iters;
+  memcpy(d->epf_sharp_lut, rf.epf_sharp_lut, sizeof(d->epf_sharp_lut));
+  memcpy(d->epf_channel_scale, rf.epf_channel_scale, sizeof(d->epf_channel_scale));
+  d->epf_quant_mul = rf.epf_quant_mul;
+  d->epf_pass0_sigma_scale = rf.epf_pass0_sigma_scale;
+  d->epf_pass2_sigma_scale = rf.epf_pass2_sigma_scale;
+  d->epf_border_sad_mul = rf.epf_border_sad_mul;
+  memcpy(d->opsin_inverse_matrix, file.opsin.inverse_matrix, sizeof(d->opsin_inverse_matrix));
+  memcpy(d->opsin_biases, file.opsin.opsin_biases, sizeof(d->opsin_biases));
+  d->intensity_target = file.intensity_target;
+  d->output_format = output_format;
+  // api/inner/codestream_parser/image_info.rs:204-237: integer outputs get the
+  // image's transfer function (sRGB here), f32 output stays linear.
+  d->output_tf = (output_format == JXG_FORMAT_RGB_F32 || output_format == JXG_FORMAT_XYB_F32_PLANAR) ? JXG_TF_LINEAR : JXG_TF_SRGB;
+}
+
+}  // namespace jxg

@@ -1,0 +1,87 @@
+// Host front-end of one VarDCT frame: everything jxl-rs does *before* the hot
+// path (jxl/src/frame/decode.rs:307-566): LfGlobal, LfGroups (LF image + HF
+// metadata through the Modular decoder), HfGlobal (dequant matrices,
+// coefficient orders, per-pass histograms), LF finalisation (adaptive
+// smoothing). Produces the flat frame state behind JxgFrameDesc.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "../../../include/jxg.h"
+#include "entropy.h"
+#include "headers.h"
+#include "modular.h"
+
+namespace jxg {
+
+constexpr int kNumQuantTables = 17;
+constexpr int kNumOrders = 13;
+
+// quant_weights.rs: library tables (computed once, shared) and custom tables.
+const std::vector<float>& library_dequant_table(int idx);
+extern const uint8_t kQuantTableRows[kNumQuantTables];  // REQUIRED_SIZE_X (rows, in blocks)
+extern const uint8_t kQuantTableCols[kNumQuantTables];  // REQUIRED_SIZE_Y (cols, in blocks)
+int quant_table_for_transform(int transform);           // QuantTable::for_strategy
+
+// transform_map.rs
+extern const uint8_t kCoveredBlocksX[27], kCoveredBlocksY[27], kBlockShapeId[27];
+// coeff_order.rs:66
+std::vector<uint32_t> natural_coeff_order(int order_idx);
+extern const uint8_t kOrderTransform[kNumOrders];  // TRANSFORM_TYPE_LUT
+
+struct PassState {
+  EntropyCode code;            // context map padded by 16 (frame/decode.rs:536-538)
+  bool custom_orders = false;
+  std::vector<uint32_t> coeff_order;  // 39 concatenated orders if custom_orders
+  uint32_t coeff_order_offset[39] = {0};
+  std::vector<uint32_t> uint_configs_packed;
+};
+
+struct FrameState {
+  FileHeader file;
+  FrameHeader header;
+  Toc toc;
+  std::vector<uint8_t> codestream;  // owns the bytes
+  size_t sections_base = 0;         // byte offset of section 0 in codestream
+
+  // LfGlobal
+  float lf_quant[3] = {1.0f / 4096.0f, 1.0f / 512.0f, 1.0f / 256.0f};
+  uint32_t global_scale = 0, quant_lf = 0;
+  std::vector<int32_t> lf_thresholds[3];
+  std::vector<uint32_t> qf_thresholds;
+  std::vector<uint8_t> block_ctx_map;
+  uint32_t num_lf_contexts = 1, num_block_contexts = 15;
+  uint32_t color_factor = 84;
+  float base_correlation_x = 0.0f, base_correlation_b = 1.0f;
+  int32_t ytox_lf = 0, ytob_lf = 0;
+  bool has_global_tree = false;
+  ModularTree global_tree;
+
+  // planes (xb x yb)
+  uint32_t xb = 0, yb = 0;
+  std::vector<float> lf[3];
+  std::vector<uint8_t> transform_map, epf_map, quant_lf_map;
+  std::vector<int32_t> raw_quant_map;
+  std::vector<int8_t> ytox_map, ytob_map;
+
+  // HfGlobal
+  std::vector<float> custom_dequant[kNumQuantTables];  // empty = library
+  uint32_t num_histograms = 1;
+  std::vector<PassState> passes;
+  std::vector<JxgPassDesc> pass_descs;
+
+  // Section table for the HF groups (pass-major), offsets into codestream.
+  std::vector<uint64_t> hf_off;
+  std::vector<uint32_t> hf_len;
+
+  size_t num_ac_contexts() const { return size_t(num_block_contexts) * (37 + 458); }
+  void fill_desc(JxgFrameDesc* d, uint32_t output_format);
+};
+
+// Parses a complete file up to (not including) the HF groups of its first
+// displayed VarDCT frame. Throws jxg::Error.
+std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size);
+
+}  // namespace jxg

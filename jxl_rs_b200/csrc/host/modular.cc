@@ -1,0 +1,666 @@
+// See modular.h.
+#include "modular.h"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace jxg {
+
+namespace {
+
+struct U32D {
+  uint32_t bits, off;
+};
+inline uint32_t u2s(BitReader& br, U32D a, U32D b, U32D c, U32D d) {
+  const U32D ds[4] = {a, b, c, d};
+  const U32D& s = ds[br.read(2)];
+  return uint32_t(br.read(s.bits)) + s.off;
+}
+constexpr U32D V(uint32_t v) { return U32D{0, v}; }
+constexpr U32D B(uint32_t n, uint32_t off = 0) { return U32D{n, off}; }
+
+inline int32_t wadd(int32_t a, int32_t b) { return int32_t(uint32_t(a) + uint32_t(b)); }
+inline int32_t wsub(int32_t a, int32_t b) { return int32_t(uint32_t(a) - uint32_t(b)); }
+inline int32_t wabs(int32_t a) { return a < 0 ? int32_t(0u - uint32_t(a)) : a; }
+
+enum Predictor : uint32_t {
+  kZero = 0, kWest, kNorth, kAvgWN, kSelect, kGradient, kWeighted, kNorthEast, kNorthWest, kWestWest, kAvgWNW,
+  kAvgNNW, kAvgNNE, kAvgAll, kNumPredictors
+};
+
+// predict.rs:137-143
+inline int64_t clamped_gradient(int64_t left, int64_t top, int64_t topleft) {
+  int64_t mn = std::min(left, top), mx = std::max(left, top);
+  int64_t grad = left + top - topleft;
+  int64_t g = topleft < mn ? mx : grad;
+  return topleft > mx ? mn : g;
+}
+
+struct Neigh {
+  int32_t left, top, toptop, topleft, topright, leftleft, toprightright;
+};
+
+// predict.rs:64-103 (get_rows)
+inline Neigh get_neigh(const int32_t* row, const int32_t* top_row, const int32_t* toptop_row, size_t x, size_t y,
+                       size_t w) {
+  Neigh n;
+  n.left = x > 0 ? row[x - 1] : (y > 0 ? top_row[0] : 0);
+  n.top = y > 0 ? top_row[x] : n.left;
+  n.topleft = (x > 0 && y > 0) ? top_row[x - 1] : n.left;
+  n.topright = (x + 1 < w && y > 0) ? top_row[x + 1] : n.top;
+  n.leftleft = x > 1 ? row[x - 2] : n.left;
+  n.toptop = y > 1 ? toptop_row[x] : n.top;
+  n.toprightright = (x + 2 < w && y > 0) ? top_row[x + 2] : n.topright;
+  return n;
+}
+
+// predict.rs:148-194
+inline int64_t predict_one(uint32_t p, const Neigh& n, int64_t wp_pred) {
+  int64_t left = n.left, top = n.top, topleft = n.topleft, topright = n.topright;
+  switch (p) {
+    case kZero: return 0;
+    case kWest: return left;
+    case kNorth: return top;
+    case kSelect: {
+      int64_t pp = left + top - topleft;
+      return std::llabs(pp - left) < std::llabs(pp - top) ? left : top;
+    }
+    case kGradient: return clamped_gradient(left, top, topleft);
+    case kWeighted: return wp_pred;
+    case kWestWest: return n.leftleft;
+    case kNorthEast: return topright;
+    case kNorthWest: return topleft;
+    case kAvgWN: return (top + left) / 2;
+    case kAvgWNW: return (left + topleft) / 2;
+    case kAvgNNW: return (top + topleft) / 2;
+    case kAvgNNE: return (top + topright) / 2;
+    case kAvgAll:
+      return (6 * top - 2 * int64_t(n.toptop) + 7 * left + int64_t(n.leftleft) + int64_t(n.toprightright) +
+              3 * topright + 8) / 16;
+  }
+  return 0;
+}
+
+const uint32_t kDivLookup[64] = {
+    16777216, 8388608, 5592405, 4194304, 3355443, 2796202, 2396745, 2097152, 1864135, 1677721, 1525201,
+    1398101,  1290555, 1198372, 1118481, 1048576, 986895,  932067,  883011,  838860,  798915,  762600,
+    729444,   699050,  671088,  645277,  621378,  599186,  578524,  559240,  541200,  524288,  508400,
+    493447,   479349,  466033,  453438,  441505,  430185,  419430,  409200,  399457,  390167,  381300,
+    372827,   364722,  356962,  349525,  342392,  335544,  328965,  322638,  316551,  310689,  305040,
+    299593,   294337,  289262,  284359,  279620,  275036,  270600,  266305,  262144,
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Weighted predictor
+// ---------------------------------------------------------------------------
+
+WpState::WpState(const WeightedHeader& h, size_t xs) : xsize(xs), hdr(h) {
+  size_t n = (xs + 1) * 2;
+  pred_errors.assign(n * 4, 0);
+  error.assign(n, 0);
+}
+
+void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t topright, int32_t topleft,
+                      int32_t toptop, int64_t& pred_out, int32_t& prop_out) {
+  size_t cur_row = (y & 1) ? 0 : xsize + 1, prev_row = (y & 1) ? xsize + 1 : 0;
+  size_t pos_ne = x + 1 < xsize ? x + 1 : x;
+  size_t pos_nw = x > 0 ? x - 1 : 0;
+  const uint32_t* en = &pred_errors[(prev_row + x) * 4];
+  const uint32_t* ene = &pred_errors[(prev_row + pos_ne) * 4];
+  const uint32_t* enw = &pred_errors[(prev_row + pos_nw) * 4];
+  uint32_t wv[4];
+  for (int i = 0; i < 4; i++) {
+    uint32_t err = en[i] + ene[i] + enw[i];
+    uint32_t l2 = floor_log2(uint64_t(err) + 1);
+    uint32_t shift = l2 > 5 ? l2 - 5 : 0;
+    uint32_t div = kDivLookup[err >> shift];
+    wv[i] = 4u + ((hdr.w[i] * div) >> shift);
+  }
+  int64_t te_w = error[cur_row + x];
+  int64_t te_n = error[prev_row + 1 + x];
+  int64_t te_nw = error[prev_row + 1 + pos_nw];
+  int64_t sum_wn = te_n + te_w;
+  int64_t te_ne = error[prev_row + 1 + pos_ne];
+  int64_t p = te_w;
+  if (std::llabs(te_n) > std::llabs(p)) p = te_n;
+  if (std::llabs(te_nw) > std::llabs(p)) p = te_nw;
+  if (std::llabs(te_ne) > std::llabs(p)) p = te_ne;
+  int64_t n = int64_t(top) << 3, w = int64_t(left) << 3, ne = int64_t(topright) << 3, nw = int64_t(topleft) << 3,
+          nn = int64_t(toptop) << 3;
+  int64_t p0 = w + ne - n;
+  int64_t p1 = n - (((sum_wn + te_ne) * int64_t(hdr.p1c)) >> 5);
+  int64_t p2 = w - (((sum_wn + te_nw) * int64_t(hdr.p2c)) >> 5);
+  int64_t p3 = n - ((te_nw * int64_t(hdr.p3ca) + te_n * int64_t(hdr.p3cb) + te_ne * int64_t(hdr.p3cc) +
+                     (nn - n) * int64_t(hdr.p3cd) + (nw - w) * int64_t(hdr.p3ce)) >> 5);
+  uint32_t log_weight = floor_log2(uint64_t(wv[0]) + wv[1] + wv[2] + wv[3]);
+  int64_t w0 = int64_t(wv[0]) >> (log_weight - 4), w1 = int64_t(wv[1]) >> (log_weight - 4),
+          w2 = int64_t(wv[2]) >> (log_weight - 4), w3 = int64_t(wv[3]) >> (log_weight - 4);
+  int64_t weight_sum = w0 + w1 + w2 + w3;
+  int64_t sum = (weight_sum >> 1) - 1 + w0 * p0 + w1 * p1 + w2 * p2 + w3 * p3;
+  int64_t pr = (sum * int64_t(kDivLookup[weight_sum - 1])) >> 24;
+  if (((te_n ^ te_w) | (te_n ^ te_nw)) <= 0) {
+    int64_t mx = std::max(w, std::max(ne, n)), mn = std::min(w, std::min(ne, n));
+    pr = std::max(mn, std::min(mx, pr));
+  }
+  prediction[0] = p0;
+  prediction[1] = p1;
+  prediction[2] = p2;
+  prediction[3] = p3;
+  pred = pr;
+  pred_out = (pr + 3) >> 3;
+  prop_out = int32_t(p);
+}
+
+void WpState::update(int32_t val, size_t x, size_t y) {
+  size_t cur_row = (y & 1) ? 0 : xsize + 1, prev_row = (y & 1) ? xsize + 1 : 0;
+  int64_t v = int64_t(val) << 3;
+  error[cur_row + x + 1] = int32_t(pred - v);
+  uint32_t* cur = &pred_errors[(cur_row + x) * 4];
+  uint32_t* prev = &pred_errors[(prev_row + x + 1) * 4];
+  for (int i = 0; i < 4; i++) {
+    uint32_t e = uint32_t((std::llabs(prediction[i] - v) + 3) >> 3);
+    cur[i] = e;
+    prev[i] += e;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Headers / tree
+// ---------------------------------------------------------------------------
+
+GroupHeader GroupHeader::read(BitReader& br) {
+  GroupHeader g;
+  g.use_global_tree = br.read_bool();
+  if (!br.read_bool()) {  // WeightedHeader all_default
+    WeightedHeader& w = g.wp;
+    w.p1c = uint32_t(br.read(5));
+    w.p2c = uint32_t(br.read(5));
+    w.p3ca = uint32_t(br.read(5));
+    w.p3cb = uint32_t(br.read(5));
+    w.p3cc = uint32_t(br.read(5));
+    w.p3cd = uint32_t(br.read(5));
+    w.p3ce = uint32_t(br.read(5));
+    for (auto& x : w.w) x = uint32_t(br.read(4));
+  }
+  uint32_t nt = u2s(br, V(0), V(1), B(4, 2), B(8, 18));
+  g.transforms.resize(nt);
+  for (auto& t : g.transforms) {
+    t.id = uint32_t(br.read(2));
+    if (t.id == 3) fail("invalid modular transform");
+    if (t.id == 0 || t.id == 1) t.begin_channel = u2s(br, B(3), B(6, 8), B(10, 72), B(13, 1096));
+    if (t.id == 0) {
+      t.rct_type = u2s(br, V(6), B(2), B(4, 2), B(6, 10));
+      if (t.rct_type >= 42) fail("invalid RCT type");
+    }
+    if (t.id == 1) {
+      t.num_channels = u2s(br, V(1), V(3), V(4), B(13, 1));
+      t.num_colors = u2s(br, B(8), B(10, 256), B(12, 1280), B(16, 5376));
+      t.num_deltas = u2s(br, V(0), B(8, 1), B(10, 257), B(16, 1281));
+      t.predictor_id = uint32_t(br.read(4));
+      if (t.predictor_id >= kNumPredictors) fail("invalid predictor");
+    }
+    if (t.id == 2) {
+      uint32_t ns = u2s(br, V(0), B(4, 1), B(6, 9), B(8, 41));
+      t.squeezes.resize(ns);
+      for (auto& s : t.squeezes) {
+        s.horizontal = br.read_bool();
+        s.in_place = br.read_bool();
+        s.begin_channel = u2s(br, B(3), B(6, 8), B(10, 72), B(13, 1096));
+        s.num_channels = u2s(br, V(1), V(2), V(3), B(4, 4));
+      }
+    }
+  }
+  br.check();
+  return g;
+}
+
+ModularTree ModularTree::read(BitReader& br, size_t size_limit) {
+  // tree.rs:284-358; contexts: 0 splitval, 1 property, 2 predictor, 3 offset, 4 mul_log, 5 mul_bits
+  ModularTree t;
+  EntropyCode tc = EntropyCode::decode(6, br, true);
+  SymbolReader r(tc, br, 0);
+  size_t to_decode = 1;
+  uint32_t leaf_id = 0, max_property = 0;
+  while (to_decode > 0) {
+    if (t.nodes.size() > size_limit) fail("MA tree too large");
+    to_decode--;
+    uint32_t property = r.read_unsigned(br, 1);
+    if (property > 0) {
+      property -= 1;
+      if (property > 255) fail("invalid MA tree property");
+      max_property = std::max(max_property, property);
+      int32_t splitval = r.read_signed(br, 0);
+      uint32_t left = uint32_t(t.nodes.size() + to_decode + 1);
+      t.nodes.push_back(TreeNode{int32_t(property), splitval, left, left + 1, 0});
+      to_decode += 2;
+      if (property == 15) t.uses_wp = true;
+    } else {
+      uint32_t predictor = r.read_unsigned(br, 2);
+      if (predictor >= kNumPredictors) fail("invalid predictor");
+      int32_t offset = r.read_signed(br, 3);
+      uint32_t mul_log = r.read_unsigned(br, 4);
+      if (mul_log >= 31) fail("MA tree multiplier too large");
+      uint32_t mul_bits = r.read_unsigned(br, 5);
+      uint64_t mul = (uint64_t(mul_bits) + 1) << mul_log;
+      if (mul > 0xffffffffull) fail("MA tree multiplier too large");
+      t.nodes.push_back(TreeNode{-1, offset, predictor, uint32_t(mul), leaf_id++});
+      if (predictor == kWeighted) t.uses_wp = true;
+    }
+    br.check();
+  }
+  r.check_final_state(br);
+  t.num_properties = max_property + 1;
+  t.code = EntropyCode::decode((t.nodes.size() + 1) / 2, br, true);
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// Channel decode (decode/channel.rs FullTree path; the reference's specialised
+// trees are performance variants of the same semantics)
+// ---------------------------------------------------------------------------
+
+static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_t stream_id, const GroupHeader& header,
+                           const ModularTree& tree, SymbolReader& reader, BitReader& br) {
+  ModularChannel& ch = *chans[ci];
+  const size_t w = ch.w, h = ch.h;
+  size_t num_ref_props = tree.num_properties > 16 ? ((tree.num_properties - 16 + 3) / 4) * 4 : 0;
+  std::vector<int32_t> refs(num_ref_props * w, 0);
+  int32_t props[16 + 256] = {0};
+  props[0] = int32_t(ci);
+  props[1] = int32_t(stream_id);
+  const bool use_wp = tree.uses_wp;
+  WpState wp(header.wp, use_wp ? w : 0);
+  const TreeNode* nodes = tree.nodes.data();
+  // Fast path: a single-leaf tree.
+  for (size_t y = 0; y < h; y++) {
+    int32_t* row = ch.row(uint32_t(y));
+    const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+    const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+    if (num_ref_props) {  // decode/common.rs:42-83
+      std::fill(refs.begin(), refs.end(), 0);
+      size_t offset = 0;
+      for (size_t i = 0; i < ci && offset < num_ref_props; i++) {
+        const ModularChannel& rc = *chans[ci - i - 1];
+        if (rc.w != ch.w || rc.h != ch.h || rc.hshift != ch.hshift || rc.vshift != ch.vshift) continue;
+        const int32_t* rrow = rc.row(uint32_t(y));
+        const int32_t* rprev = rc.row(uint32_t(y > 0 ? y - 1 : 0));
+        for (size_t x = 0; x < w; x++) {
+          int32_t* rp = &refs[x * num_ref_props + offset];
+          int32_t v = rrow[x];
+          rp[0] = wabs(v);
+          rp[1] = v;
+          int32_t vleft = x > 0 ? rrow[x - 1] : 0;
+          int32_t vtop = y > 0 ? rprev[x] : vleft;
+          int32_t vtopleft = (x > 0 && y > 0) ? rprev[x - 1] : vleft;
+          int64_t vpred = clamped_gradient(vleft, vtop, vtopleft);
+          int64_t d = int64_t(v) - vpred;
+          rp[2] = int32_t(d < 0 ? -d : d);
+          rp[3] = int32_t(d);
+        }
+        offset += 4;
+      }
+    }
+    props[9] = 0;
+    props[2] = int32_t(y);
+    for (size_t x = 0; x < w; x++) {
+      Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
+      // tree.rs:189-240
+      props[3] = int32_t(x);
+      props[4] = wabs(n.top);
+      props[5] = wabs(n.left);
+      props[6] = n.top;
+      props[7] = n.left;
+      props[8] = wsub(n.left, props[9]);
+      props[9] = wsub(wadd(n.left, n.top), n.topleft);
+      props[10] = wsub(n.left, n.topleft);
+      props[11] = wsub(n.topleft, n.top);
+      props[12] = wsub(n.top, n.topright);
+      props[13] = wsub(n.top, n.toptop);
+      props[14] = wsub(n.left, n.leftleft);
+      int64_t wp_pred = 0;
+      int32_t wp_prop = 0;
+      if (use_wp) wp.predict(x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
+      props[15] = wp_prop;
+      for (size_t i = 0; i < num_ref_props; i++) props[16 + i] = refs[x * num_ref_props + i];
+      const TreeNode* nd = nodes;
+      while (nd->property >= 0) nd = nodes + (props[nd->property] > nd->val ? nd->left : nd->right);
+      int64_t guess = predict_one(nd->left, n, wp_pred) + int64_t(nd->val);
+      int32_t dec = reader.read_signed(br, nd->ctx);
+      int32_t val = int32_t(guess + int64_t(nd->right) * int64_t(dec));  // decode/common.rs:85
+      if (use_wp) wp.update(val, x, y);
+      row[x] = val;
+    }
+  }
+  br.check();
+}
+
+void decode_modular_channels(std::vector<ModularChannel*>& channels, size_t stream_id, const GroupHeader& header,
+                             const ModularTree& tree, BitReader& br) {
+  size_t image_width = 0;
+  for (auto* c : channels) image_width = std::max<size_t>(image_width, c->w);
+  SymbolReader reader(tree.code, br, image_width);
+  for (size_t i = 0; i < channels.size(); i++) {
+    if (channels[i]->w == 0 || channels[i]->h == 0) continue;
+    decode_channel(channels, i, stream_id, header, tree, reader, br);
+  }
+  reader.check_final_state(br);
+}
+
+// ---------------------------------------------------------------------------
+// Transforms
+// ---------------------------------------------------------------------------
+
+// squeeze.rs:39-105
+static std::vector<SqueezeParams> default_squeeze(const std::vector<ModularChannel>& ch, uint32_t nb_meta) {
+  std::vector<SqueezeParams> params;
+  size_t first = nb_meta;
+  uint32_t w = ch[first].w, h = ch[first].h;
+  size_t nc = ch.size() - first;
+  if (nc > 2 && ch[first + 1].w == w && ch[first + 1].h == h) {
+    SqueezeParams sp{true, false, uint32_t(first + 1), 2};
+    if (w > 1) params.push_back(sp);
+    if (h > 1) {
+      sp.horizontal = false;
+      params.push_back(sp);
+    }
+  }
+  const uint32_t kMax = 8;
+  SqueezeParams sp{false, true, uint32_t(first), uint32_t(nc)};
+  if (w <= h && h > kMax) {
+    sp.horizontal = false;
+    params.push_back(sp);
+    h = (h + 1) / 2;
+  }
+  while (w > kMax || h > kMax) {
+    if (w > kMax) {
+      sp.horizontal = true;
+      params.push_back(sp);
+      w = (w + 1) / 2;
+    }
+    if (h > kMax) {
+      sp.horizontal = false;
+      params.push_back(sp);
+      h = (h + 1) / 2;
+    }
+  }
+  return params;
+}
+
+void meta_apply_transforms(std::vector<ModularChannel>& ch, uint32_t& nb_meta, GroupHeader& header) {
+  for (auto& t : header.transforms) {
+    if (t.id == 0) {  // RCT: channel list unchanged (meta_apply.rs RCT arm checks equal sizes)
+      if (t.begin_channel + 3 > ch.size()) fail("RCT channel range");
+      for (int i = 1; i < 3; i++)
+        if (ch[t.begin_channel + i].w != ch[t.begin_channel].w || ch[t.begin_channel + i].h != ch[t.begin_channel].h)
+          fail("RCT on channels of different size");
+    } else if (t.id == 1) {  // palette, meta_apply.rs:181-230
+      size_t b = t.begin_channel, n = t.num_channels;
+      if (b + n > ch.size()) fail("palette channel range");
+      for (size_t i = 1; i < n; i++)
+        if (ch[b + i].w != ch[b].w || ch[b + i].h != ch[b].h) fail("palette on channels of different size");
+      if (b < nb_meta) {
+        if (b + n > nb_meta) fail("palette mixes meta and non-meta channels");
+        nb_meta += 2 - uint32_t(n);
+      } else {
+        nb_meta += 1;
+      }
+      ch.erase(ch.begin() + b + 1, ch.begin() + b + n);
+      ch.insert(ch.begin(), ModularChannel(t.num_colors + t.num_deltas, uint32_t(n), -1, -1));
+    } else {  // squeeze, meta_apply.rs squeeze arm / squeeze.rs:17-37
+      if (t.squeezes.empty()) t.squeezes = default_squeeze(ch, nb_meta);
+      for (const auto& s : t.squeezes) {
+        size_t b = s.begin_channel, e = b + s.num_channels;
+        if (e > ch.size() || s.num_channels == 0) fail("squeeze channel range");
+        bool meta_b = b < nb_meta, meta_e = (e - 1) < nb_meta;
+        if (meta_b != meta_e) fail("squeeze mixes meta and non-meta channels");
+        if (meta_b && !s.in_place) fail("meta squeeze must be in place");
+        if (meta_b) nb_meta += s.num_channels;
+        size_t offset = s.in_place ? e : ch.size();
+        for (size_t c = b; c < e; c++) {
+          ModularChannel& in = ch[c];
+          ModularChannel res;
+          if (s.horizontal) {
+            uint32_t w = in.w;
+            in.w = (w + 1) / 2;
+            if (in.hshift >= 0) in.hshift++;
+            res = ModularChannel(w - in.w, in.h, in.hshift, in.vshift);
+          } else {
+            uint32_t h = in.h;
+            in.h = (h + 1) / 2;
+            if (in.vshift >= 0) in.vshift++;
+            res = ModularChannel(in.w, h - in.h, in.hshift, in.vshift);
+          }
+          in.data.assign(size_t(in.w) * in.h, 0);
+          ch.insert(ch.begin() + offset + (c - b), std::move(res));
+        }
+      }
+    }
+  }
+}
+
+// squeeze.rs:144-170 (scalar definition)
+static inline int64_t smooth_tendency(int64_t b, int64_t a, int64_t n) {
+  int64_t diff = 0;
+  if (b >= a && a >= n) {
+    diff = (4 * b - 3 * n - a + 6) / 12;
+    if (diff - (diff & 1) > 2 * (b - a)) diff = 2 * (b - a) + 1;
+    if (diff + (diff & 1) > 2 * (a - n)) diff = 2 * (a - n);
+  } else if (b <= a && a <= n) {
+    diff = (4 * b - 3 * n - a - 6) / 12;
+    if (diff + (diff & 1) < 2 * (b - a)) diff = 2 * (b - a) - 1;
+    if (diff - (diff & 1) < 2 * (a - n)) diff = 2 * (a - n);
+  }
+  return diff;
+}
+
+static void inv_hsqueeze(const ModularChannel& avg, const ModularChannel& res, ModularChannel& out) {
+  out = ModularChannel(avg.w + res.w, avg.h, avg.hshift > 0 ? avg.hshift - 1 : avg.hshift, avg.vshift);
+  for (uint32_t y = 0; y < out.h; y++) {
+    const int32_t* a = avg.row(y);
+    const int32_t* r = res.w ? res.row(y) : nullptr;
+    int32_t* o = out.row(y);
+    for (uint32_t x = 0; x < res.w; x++) {
+      int64_t av = a[x];
+      int64_t next_avg = x + 1 < avg.w ? a[x + 1] : av;
+      int64_t left = x ? o[2 * x - 1] : av;
+      int64_t diff = int64_t(r[x]) + smooth_tendency(left, av, next_avg);
+      int64_t A = av + diff / 2;
+      o[2 * x] = int32_t(A);
+      o[2 * x + 1] = int32_t(A - diff);
+    }
+    if (out.w & 1) o[out.w - 1] = a[avg.w - 1];
+  }
+}
+
+static void inv_vsqueeze(const ModularChannel& avg, const ModularChannel& res, ModularChannel& out) {
+  out = ModularChannel(avg.w, avg.h + res.h, avg.hshift, avg.vshift > 0 ? avg.vshift - 1 : avg.vshift);
+  for (uint32_t y = 0; y < res.h; y++) {
+    const int32_t* a = avg.row(y);
+    const int32_t* an = y + 1 < avg.h ? avg.row(y + 1) : a;
+    const int32_t* r = res.row(y);
+    int32_t* o0 = out.row(2 * y);
+    int32_t* o1 = out.row(2 * y + 1);
+    const int32_t* op = y ? out.row(2 * y - 1) : a;
+    for (uint32_t x = 0; x < out.w; x++) {
+      int64_t av = a[x];
+      int64_t diff = int64_t(r[x]) + smooth_tendency(op[x], av, an[x]);
+      int64_t A = av + diff / 2;
+      o0[x] = int32_t(A);
+      o1[x] = int32_t(A - diff);
+    }
+  }
+  if (out.h & 1) std::copy(avg.row(avg.h - 1), avg.row(avg.h - 1) + avg.w, out.row(out.h - 1));
+}
+
+// rct.rs:9-40 + do_rct_step permutation
+static void inv_rct(std::vector<ModularChannel>& ch, size_t b, uint32_t rct_type) {
+  uint32_t perm = rct_type / 7, op = rct_type % 7;
+  ModularChannel &c0 = ch[b], &c1 = ch[b + 1], &c2 = ch[b + 2];
+  size_t n = c0.data.size();
+  int32_t *p0 = c0.data.data(), *p1 = c1.data.data(), *p2 = c2.data.data();
+  for (size_t i = 0; i < n; i++) {
+    int32_t v0 = p0[i], v1 = p1[i], v2 = p2[i];
+    switch (op) {
+      case 1: v2 = wadd(v2, v0); break;
+      case 2: v1 = wadd(v1, v0); break;
+      case 3: v1 = wadd(v1, v0); v2 = wadd(v2, v0); break;
+      case 4: v1 = wadd(v1, wadd(v0, v2) >> 1); break;
+      case 5: v2 = wadd(v0, v2); v1 = wadd(v1, wadd(v0, v2) >> 1); break;
+      case 6: {
+        int32_t y = v0, co = v1, cg = v2;
+        y = wsub(y, cg >> 1);
+        int32_t g = wadd(cg, y);
+        y = wsub(y, co >> 1);
+        int32_t r = wadd(y, co);
+        v0 = r; v1 = g; v2 = y;
+        break;
+      }
+      default: break;
+    }
+    p0[i] = v0; p1[i] = v1; p2[i] = v2;
+  }
+  // out[perm % 3] = first, out[(perm + 1 + perm / 3) % 3] = second, out[(perm + 2 - perm / 3) % 3] = third
+  std::vector<int32_t> d[3] = {std::move(c0.data), std::move(c1.data), std::move(c2.data)};
+  ch[b + perm % 3].data = std::move(d[0]);
+  ch[b + (perm + 1 + perm / 3) % 3].data = std::move(d[1]);
+  ch[b + (perm + 2 - perm / 3) % 3].data = std::move(d[2]);
+}
+
+// palette.rs:17-138
+static int32_t palette_value(const ModularChannel& pal, int64_t index, size_t c, size_t palette_size,
+                             size_t bit_depth) {
+  static const int16_t kDelta[72][3] = {
+      {0, 0, 0},       {4, 4, 4},       {11, 0, 0},      {0, 0, -13},     {0, -12, 0},     {-10, -10, -10},
+      {-18, -18, -18}, {-27, -27, -27}, {-18, -18, 0},   {0, 0, -32},     {-32, 0, 0},     {-37, -37, -37},
+      {0, -32, -32},   {24, 24, 45},    {50, 50, 50},    {-45, -24, -24}, {-24, -45, -45}, {0, -24, -24},
+      {-34, -34, 0},   {-24, 0, -24},   {-45, -45, -24}, {64, 64, 64},    {-32, 0, -32},   {0, -32, 0},
+      {-32, 0, 32},    {-24, -45, -24}, {45, 24, 45},    {24, -24, -45},  {-45, -24, 24},  {80, 80, 80},
+      {64, 0, 0},      {0, 0, -64},     {0, -64, -64},   {-24, -24, 45},  {96, 96, 96},    {64, 64, 0},
+      {45, -24, -24},  {34, -34, 0},    {112, 112, 112}, {24, -45, -45},  {45, 45, -24},   {0, -32, 32},
+      {24, -24, 45},   {0, 96, 96},     {45, -24, 24},   {24, -45, -24},  {-24, -45, 24},  {0, -64, 0},
+      {96, 0, 0},      {128, 128, 128}, {64, 0, 64},     {144, 144, 144}, {96, 96, 0},     {-36, -36, 36},
+      {45, -24, -45},  {45, -45, -24},  {0, 0, -96},     {0, 128, 128},   {0, 96, 0},      {45, 24, -45},
+      {-128, 0, 0},    {24, -45, 24},   {-45, 24, -45},  {64, 0, -64},    {64, -64, -64},  {96, 0, 96},
+      {45, -45, 24},   {24, 45, -45},   {64, 64, -64},   {128, 128, 0},   {0, 0, -128},    {-24, 45, -45},
+  };
+  if (index < 0) {
+    if (c >= 3) return 0;
+    size_t idx = size_t(-(index + 1));
+    idx %= 1 + 2 * (72 - 1);
+    int32_t result = kDelta[(idx + 1) >> 1][c] * ((idx & 1) ? 1 : -1);
+    if (bit_depth > 8) result *= 1 << (bit_depth - 8);
+    return result;
+  }
+  size_t idx = size_t(index);
+  auto scale = [&](size_t value) { return int32_t((value * ((size_t(1) << bit_depth) - 1)) >> 2); };
+  if (palette_size <= idx && idx < palette_size + 64) {
+    if (c >= 3) return 0;
+    idx -= palette_size;
+    idx >>= c * 2;
+    return scale(idx % 4) + (1 << std::max<int>(0, int(bit_depth) - 3));
+  } else if (palette_size + 64 <= idx) {
+    if (c >= 3) return 0;
+    idx -= palette_size + 64;
+    if (c == 1) idx /= 5;
+    if (c == 2) idx /= 25;
+    return scale(idx % 5);
+  }
+  return pal.row(uint32_t(c))[idx];
+}
+
+static void inv_palette(std::vector<ModularChannel>& ch, const ModularTransform& t, const WeightedHeader& wph,
+                        uint32_t bit_depth_in) {
+  // channel 0 is the palette, channel begin+1 the index channel.
+  size_t b = t.begin_channel + 1, n = t.num_channels;
+  ModularChannel pal = std::move(ch[0]);
+  ModularChannel index = std::move(ch[b]);
+  size_t bit_depth = std::min<uint32_t>(bit_depth_in, 24);
+  std::vector<ModularChannel> outs;
+  size_t w = index.w, h = index.h;
+  for (size_t c = 0; c < n; c++) {
+    ModularChannel out(index.w, index.h, index.hshift, index.vshift);
+    if (w == 0) {
+    } else if (t.num_deltas == 0 && t.predictor_id == kZero) {
+      for (size_t y = 0; y < h; y++)
+        for (size_t x = 0; x < w; x++)
+          out.row(uint32_t(y))[x] = palette_value(pal, index.row(uint32_t(y))[x], c, t.num_colors, bit_depth);
+    } else {
+      bool weighted = t.predictor_id == kWeighted;
+      WpState wp(wph, weighted ? w : 0);
+      for (size_t y = 0; y < h; y++) {
+        int32_t* row = out.row(uint32_t(y));
+        const int32_t* top_row = y > 0 ? out.row(uint32_t(y - 1)) : row;
+        const int32_t* toptop_row = y > 1 ? out.row(uint32_t(y - 2)) : top_row;
+        for (size_t x = 0; x < w; x++) {
+          int32_t idx = index.row(uint32_t(y))[x];
+          int32_t entry = palette_value(pal, idx, c, t.num_colors + t.num_deltas, bit_depth);
+          Neigh nb = get_neigh(row, top_row, toptop_row, x, y, w);
+          int64_t wp_pred = 0;
+          int32_t wp_prop;
+          if (weighted) wp.predict(x, y, nb.top, nb.left, nb.topright, nb.topleft, nb.toptop, wp_pred, wp_prop);
+          int32_t val = entry;
+          if (idx < int32_t(t.num_deltas)) val = int32_t(predict_one(t.predictor_id, nb, wp_pred) + entry);
+          row[x] = val;
+          if (weighted) wp.update(val, x, y);
+        }
+      }
+    }
+    outs.push_back(std::move(out));
+  }
+  ch.erase(ch.begin() + b);
+  for (size_t c = 0; c < n; c++) ch.insert(ch.begin() + b + c, std::move(outs[c]));
+  ch.erase(ch.begin());
+}
+
+void undo_transforms(std::vector<ModularChannel>& ch, const GroupHeader& header, uint32_t bit_depth) {
+  for (size_t ti = header.transforms.size(); ti-- > 0;) {
+    const ModularTransform& t = header.transforms[ti];
+    if (t.id == 0) {
+      inv_rct(ch, t.begin_channel, t.rct_type);
+    } else if (t.id == 1) {
+      inv_palette(ch, t, header.wp, bit_depth);
+    } else {
+      for (size_t si = t.squeezes.size(); si-- > 0;) {
+        const SqueezeParams& s = t.squeezes[si];
+        size_t b = s.begin_channel, e = b + s.num_channels;
+        size_t offset = s.in_place ? e : ch.size() - s.num_channels;
+        for (size_t c = b; c < e; c++) {
+          ModularChannel out;
+          if (s.horizontal) inv_hsqueeze(ch[c], ch[offset + (c - b)], out);
+          else inv_vsqueeze(ch[c], ch[offset + (c - b)], out);
+          ch[c] = std::move(out);
+        }
+        ch.erase(ch.begin() + offset, ch.begin() + offset + s.num_channels);
+      }
+    }
+  }
+}
+
+void decode_modular_subbitstream(std::vector<ModularChannel>& channels, size_t stream_id,
+                                 const ModularTree* global_tree, BitReader& br) {
+  bool empty = true;
+  for (auto& c : channels)
+    if (c.w && c.h) empty = false;
+  if (empty) return;
+  GroupHeader header = GroupHeader::read(br);
+  uint32_t nb_meta = 0;
+  meta_apply_transforms(channels, nb_meta, header);
+  ModularTree local;
+  const ModularTree* tree = global_tree;
+  if (!header.use_global_tree) {
+    size_t samples = 0;
+    for (auto& c : channels) samples += size_t(c.w) * c.h;
+    local = ModularTree::read(br, std::min<size_t>(1024 + samples, 1u << 20));
+    tree = &local;
+  } else if (!global_tree) {
+    fail("no global MA tree");
+  }
+  std::vector<ModularChannel*> ptrs;
+  for (auto& c : channels) ptrs.push_back(&c);
+  decode_modular_channels(ptrs, stream_id, header, *tree, br);
+  undo_transforms(channels, header, 8);
+}
+
+}  // namespace jxg

@@ -1,0 +1,65 @@
+/*
+ * oracle.h — CPU restatement of the jxl-rs VarDCT per-group hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load it, and only as the checker / CPU baseline.
+ * The product path (libjxgpu.so) never links or calls it.
+ *
+ * Parity status: "parity pinned on integers, unpinned on pixels" — the
+ * reference (Rust) cannot be built in this container (no cargo), and the tree
+ * holds no decoded-pixel goldens for VarDCT files. The oracle is pinned by
+ *   (1) the reference's own known-answer tests restated in tests/ (ANS
+ *       histograms, Huffman, natural coefficient orders, dequant tables,
+ *       IDCT/reinterpreting-DCT vs f64 definitions with the reference's
+ *       tolerances, Gaborish checkerboard, XYB primaries, sRGB TF, weighted
+ *       predictor golden), and
+ *   (2) self-verification on the reference's real .jxl fixtures: every ANS
+ *       stream must end in state 0x130000, every block must consume exactly
+ *       its non-zero count, no section may be over-read.
+ */
+#ifndef JXO_ORACLE_H_
+#define JXO_ORACLE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../include/jxg.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Optional taps; any pointer may be NULL. */
+typedef struct JxoTaps {
+  int32_t* coeffs;      /* [num_groups][3][65536] i32, decode order (group.rs:53-55)        */
+  float* xyb_idct;      /* [3][yb*8][xb*8] planes after dequant+IDCT                        */
+  float* xyb_filtered;  /* [3][height][width] planes after Gaborish+EPF                     */
+} JxoTaps;
+
+/* Full hot path for one frame (decode_vardct_group for every group, then the
+ * render stages with SimpleRenderPipeline semantics). Output layout follows
+ * desc->output_format. Returns 0 or a JXG_ERR_* code; *bad_group is set on
+ * entropy errors. */
+int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const uint64_t* sec_off,
+                     const uint32_t* sec_len, uint32_t n_sections, void* out, size_t out_row_stride,
+                     const JxoTaps* taps, int num_threads, uint32_t* bad_group);
+
+/* Host front-end + oracle: decode a whole file. */
+int jxo_decode_file(const uint8_t* data, size_t size, uint32_t output_format, void* out, size_t out_row_stride,
+                    const JxoTaps* taps, int num_threads);
+int jxo_file_info(const uint8_t* data, size_t size, JxgImageInfo* info);
+const char* jxo_last_error(void);
+
+/* Unit-test hooks into the restated primitives. */
+void jxo_idct2d(int rows, int cols, float* block);                  /* in place, layouts as transform.rs */
+void jxo_reinterpreting_dct2d(int rows, int cols, const float* in, float* out, int out_stride);
+void jxo_transform_to_pixels(int transform, const float* lf, float* coeffs_in_pixels_out);
+void jxo_gaborish(int w, int h, const float* in, float* out, float w1, float w2);
+void jxo_xyb_to_linear(int n, float* x, float* y, float* b, const float* opsin_matrix, const float* opsin_biases,
+                       float intensity_target);
+void jxo_linear_to_srgb(int n, float* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
