@@ -162,6 +162,10 @@ void jxg_batch_end(void* batch);
 int jxg_batch_read_coeffs(void* batch, uint32_t f, int32_t* out, size_t out_len);
 int jxg_batch_read_xyb(void* batch, uint32_t f, int stage, float* out, size_t out_len);
 
+/* Debug/parity: 0 = run everything (default), 1 = stop after the entropy kernel,
+ * 2 = stop after dequant+IDCT (planes readable with stage 0). */
+int jxg_batch_set_debug_stop(void* batch, int stage);
+
 /* Counters for bench.py (kernels launched by the last run, bytes moved). */
 int jxg_batch_stats(void* batch, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes,
                     float* last_device_ms);
@@ -182,6 +186,10 @@ void jxg_parsed_free(void* parsed);
 /* Adds a parsed frame to a batch with the given output. */
 int jxg_batch_add_parsed(void* batch, void* parsed, uint32_t output_format, void* out, size_t out_row_stride,
                          int out_is_device);
+/* Exposes the parsed frame as the (desc, sections) tuple jxg_batch_add_frame takes;
+ * pointers stay valid until jxg_parsed_free. */
+int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, const uint8_t** hf_bytes,
+                    const uint64_t** sec_off, const uint32_t** sec_len, uint32_t* n_sections);
 const char* jxg_last_error(void);
 
 #ifdef __cplusplus

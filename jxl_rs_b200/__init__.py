@@ -1,0 +1,7 @@
+"""jxl_rs_b200 — B200 (sm_100a) VarDCT decode hot path behind the jxl-rs decoder seam.
+
+Only the pieces the path needs live here: `csrc/` (CUDA kernels, C ABI, host
+front-end) and the host-side mirror of the reference's decoder interface.
+"""
+from .abi import JxgError, library_path, load_library  # noqa: F401
+from .decoder import Batch, JxgContext, JxlPixelFormat, ParsedFrame, decode_files  # noqa: F401

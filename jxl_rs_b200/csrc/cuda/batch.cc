@@ -1,0 +1,557 @@
+// C ABI of libjxgpu.so (include/jxg.h): context + batch management around the
+// sm_100a kernels. There is NO CPU fallback: without a CUDA device jxg_init
+// fails with JXG_ERR_NO_DEVICE and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/jxg.h"
+#include "../host/frame.h"
+#include "device_types.h"
+#include "launch.h"
+
+using namespace jxgpu;
+
+namespace {
+
+thread_local std::string g_error;
+int set_error(int code, const std::string& what) {
+  g_error = what;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return set_error(JXG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) return set_error(JXG_ERR_CUDA, "cudaMalloc of " + std::to_string(want) + " bytes failed");
+    cap = want;
+    return 0;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+// Growable pinned host arena: the batch blob is assembled directly in pinned
+// memory so that the upload is one cudaMemcpyAsync.
+struct PinnedArena {
+  uint8_t* p = nullptr;
+  size_t size = 0, cap = 0;
+  ~PinnedArena() {
+    if (p) cudaFreeHost(p);
+  }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t ncap = std::max(want, cap * 2);
+    ncap = std::max<size_t>(ncap, 1 << 20);
+    uint8_t* np = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&np), ncap, cudaHostAllocDefault) != cudaSuccess) return false;
+    if (p) {
+      memcpy(np, p, size);
+      cudaFreeHost(p);
+    }
+    p = np;
+    cap = ncap;
+    return true;
+  }
+  // returns offset; pads with zeros up to `align`, appends `bytes` (+ `tail_zero` zero bytes)
+  int64_t append(const void* src, size_t bytes, size_t align = 16, size_t tail_zero = 0) {
+    size_t off = (size + align - 1) / align * align;
+    size_t end = off + bytes + tail_zero;
+    if (!reserve(end)) return -1;
+    memset(p + size, 0, off - size);
+    if (bytes) memcpy(p + off, src, bytes);
+    if (tail_zero) memset(p + off + bytes, 0, tail_zero);
+    size = end;
+    return int64_t(off);
+  }
+};
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf dequant_default, dequant_default_off, natural_orders, natural_order_off;
+};
+
+struct FrameOut {
+  void* user_ptr;
+  size_t row_stride, rows, bytes;
+  bool is_device;
+  size_t dev_off;  // offset in d_out when !is_device
+};
+
+struct Batch {
+  Context* ctx;
+  PinnedArena blob;
+  std::vector<FrameDev> frames;
+  std::vector<SectionDev> sections;
+  std::vector<StreamDev> streams;
+  std::vector<uint64_t> nz_base;
+  std::vector<uint32_t> tile_prefix{0};
+  std::vector<FrameOut> outs;
+  uint64_t total_groups = 0, total_blocks = 0, total_plane_floats = 0, nz_bytes = 0, out_bytes = 0;
+  uint32_t max_epf = 0;
+  bool any_gab = false;
+  int debug_stop = 0;
+  // device
+  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_coeffs, d_block_off, d_nz, d_planes_a,
+      d_planes_b, d_status, d_out;
+  bool uploaded = false;
+  const float* final_planes = nullptr;
+  std::vector<int32_t> status_host;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  float last_ms = 0;
+};
+
+template <typename T>
+int upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s, uint64_t* counter) {
+  if (int r = b.ensure(std::max<size_t>(v.size() * sizeof(T), 16))) return r;
+  if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  if (counter) *counter += v.size() * sizeof(T);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jxg_last_error(void) { return g_error.c_str(); }
+
+int jxg_init(int device, void** out_ctx) {
+  if (!out_ctx) return JXG_ERR_ARGUMENT;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return set_error(JXG_ERR_NO_DEVICE, "no CUDA device: libjxgpu has no CPU fallback");
+  if (device < 0 || device >= n) return set_error(JXG_ERR_ARGUMENT, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  auto ctx = std::make_unique<Context>();
+  ctx->device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // constant tables
+  std::vector<float> wc(9 * 128, 0.0f), rs(6 * 32, 0.0f);
+  for (int l = 1; l <= 8; l++) {
+    int nn = 1 << l;
+    for (int i = 0; i < nn / 2; i++) wc[l * 128 + i] = float(1.0 / (2.0 * std::cos((i + 0.5) * M_PI / nn)));
+  }
+  for (int l = 0; l <= 5; l++) {
+    int nn = 1 << l;
+    for (int i = 0; i < nn; i++) {
+      double s = std::cos(i / (16.0 * nn) * M_PI) * std::cos(i / (8.0 * nn) * M_PI) * std::cos(i / (4.0 * nn) * M_PI) * nn;
+      rs[l * 32 + i] = float(std::round(1e6 / s) / 1e6);  // 6-decimal literals of the generated reference code
+    }
+  }
+  CUDA_TRY(upload_constants(wc.data(), rs.data()));
+  CUDA_TRY(configure_kernels());
+  // library dequant tables and natural coefficient orders
+  std::vector<float> dq;
+  std::vector<uint32_t> dq_off(17);
+  for (int i = 0; i < 17; i++) {
+    const std::vector<float>& t = jxg::library_dequant_table(i);
+    dq_off[i] = uint32_t(dq.size());
+    dq.insert(dq.end(), t.begin(), t.end());
+  }
+  std::vector<uint32_t> no, no_off(13);
+  for (int i = 0; i < 13; i++) {
+    std::vector<uint32_t> o = jxg::natural_coeff_order(i);
+    no_off[i] = uint32_t(no.size());
+    no.insert(no.end(), o.begin(), o.end());
+  }
+  if (int r = upload(ctx->dequant_default, dq, ctx->stream, nullptr)) return r;
+  if (int r = upload(ctx->dequant_default_off, dq_off, ctx->stream, nullptr)) return r;
+  if (int r = upload(ctx->natural_orders, no, ctx->stream, nullptr)) return r;
+  if (int r = upload(ctx->natural_order_off, no_off, ctx->stream, nullptr)) return r;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *out_ctx = ctx.release();
+  return JXG_OK;
+}
+
+void jxg_shutdown(void* c) {
+  Context* ctx = static_cast<Context*>(c);
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int jxg_batch_begin(void* c, uint32_t n_frames_hint, void** out_batch) {
+  if (!c || !out_batch) return JXG_ERR_ARGUMENT;
+  auto b = std::make_unique<Batch>();
+  b->ctx = static_cast<Context*>(c);
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  b->frames.reserve(n_frames_hint);
+  CUDA_TRY(cudaEventCreate(&b->ev0));
+  CUDA_TRY(cudaEventCreate(&b->ev1));
+  *out_batch = b.release();
+  return JXG_OK;
+}
+
+void jxg_batch_end(void* bp) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  delete b;
+}
+
+int jxg_batch_set_debug_stop(void* bp, int stage) {
+  static_cast<Batch*>(bp)->debug_stop = stage;
+  return JXG_OK;
+}
+
+int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes, const uint64_t* sec_off,
+                        const uint32_t* sec_len, uint32_t n_sections, void* out, size_t out_row_stride,
+                        int out_is_device) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || !d || !hf_bytes || !sec_off || !sec_len || !out) return JXG_ERR_ARGUMENT;
+  if (d->abi_version != JXG_ABI_VERSION) return set_error(JXG_ERR_ARGUMENT, "ABI version mismatch");
+  if (b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch already submitted");
+  if (d->num_passes == 0 || d->num_passes > kMaxPasses) return set_error(JXG_ERR_ARGUMENT, "bad num_passes");
+  FrameDev F;
+  memset(&F, 0, sizeof(F));
+  F.width = d->width;
+  F.height = d->height;
+  F.xb = (d->width + 7) / 8;
+  F.yb = (d->height + 7) / 8;
+  F.xg = (d->width + 255) / 256;
+  F.yg = (d->height + 255) / 256;
+  F.num_groups = F.xg * F.yg;
+  F.num_passes = d->num_passes;
+  if (n_sections != F.num_groups * F.num_passes) return set_error(JXG_ERR_ARGUMENT, "n_sections != groups * passes");
+  F.plane_stride = F.xb * 8;
+  F.plane_rows = F.yb * 8;
+  F.cxb = (F.xb + 7) / 8;
+  const size_t nb = size_t(F.xb) * F.yb, ncm = size_t(F.cxb) * ((F.yb + 7) / 8);
+  size_t bpp = d->output_format == JXG_FORMAT_RGB_U8 ? 3 : d->output_format == JXG_FORMAT_RGBA_U8 ? 4 : d->output_format == JXG_FORMAT_RGB_F32 ? 12 : 4;
+  if (out_row_stride < size_t(F.width) * bpp) return set_error(JXG_ERR_INVALID_OUTPUT, "output row stride too small");
+  F.num_histograms = d->num_histograms;
+  F.num_block_contexts = d->num_block_contexts;
+  F.num_lf_contexts = d->num_lf_contexts;
+  F.num_qf_thresholds = d->num_qf_thresholds;
+  if (F.num_qf_thresholds > 15) return set_error(JXG_ERR_ARGUMENT, "too many qf thresholds");
+  memcpy(F.qf_thresholds, d->qf_thresholds, sizeof(F.qf_thresholds));
+#define APPEND(dst, src, bytes, align)                                         \
+  do {                                                                         \
+    int64_t o__ = b->blob.append(src, bytes, align);                           \
+    if (o__ < 0) return set_error(JXG_ERR_CUDA, "pinned staging allocation failed"); \
+    dst = uint64_t(o__);                                                       \
+  } while (0)
+  APPEND(F.block_ctx_map_off, d->block_ctx_map, d->block_ctx_map_len, 16);
+  for (uint32_t p = 0; p < d->num_passes; p++) {
+    const JxgPassDesc& s = d->passes[p];
+    PassDev& P = F.passes[p];
+    if (s.lz77_enabled)
+      return set_error(JXG_ERR_UNSUPPORTED, "LZ77 in HF coefficient streams is not implemented on the device path");
+    P.shift = s.shift;
+    P.use_prefix = s.use_prefix;
+    P.log_alpha_size = s.log_alpha_size;
+    P.num_clusters = s.num_clusters;
+    P.custom_orders = s.coeff_order != nullptr;
+    APPEND(P.context_map_off, s.context_map, s.num_contexts, 16);
+    APPEND(P.uint_configs_off, s.uint_configs, size_t(s.num_clusters) * 4, 16);
+    if (s.use_prefix) {
+      APPEND(P.huff_off, s.huff_entries, size_t(s.huff_entries_len) * 4, 16);
+      APPEND(P.huff_offset_off, s.huff_offset, size_t(s.num_clusters) * 4, 16);
+    } else {
+      APPEND(P.ans_off, s.ans_buckets, (size_t(s.num_clusters) << s.log_alpha_size) * 8, 16);
+    }
+    if (P.custom_orders) {
+      APPEND(P.order_off, s.coeff_order, size_t(s.coeff_order_len) * 4, 16);
+      memcpy(P.order_offset, s.coeff_order_offset, sizeof(P.order_offset));
+    }
+  }
+  F.inv_global_scale = 65536.0f / float(d->global_scale);
+  F.x_dm = std::pow(1.0f / 1.25f, float(d->x_qm_scale) - 2.0f);  // group.rs:395-396
+  F.b_dm = std::pow(1.0f / 1.25f, float(d->b_qm_scale) - 2.0f);
+  memcpy(F.quant_biases, d->quant_biases, sizeof(F.quant_biases));
+  F.base_correlation_x = d->base_correlation_x;
+  F.base_correlation_b = d->base_correlation_b;
+  F.color_factor = d->color_factor;
+  for (int i = 0; i < 17; i++) {
+    F.dequant_off[i] = -1;
+    if (d->dequant_tables[i]) {
+      size_t n = 3 * 64 * size_t(jxg::kQuantTableRows[i]) * jxg::kQuantTableCols[i];
+      uint64_t o;
+      APPEND(o, d->dequant_tables[i], n * 4, 16);
+      F.dequant_off[i] = int64_t(o);
+    }
+  }
+  for (int c = 0; c < 3; c++) APPEND(F.lf_off[c], d->lf[c], nb * 4, 16);
+  APPEND(F.transform_off, d->transform_map, nb, 16);
+  APPEND(F.raw_quant_off, d->raw_quant_map, nb * 4, 16);
+  APPEND(F.epf_off, d->epf_map, nb, 16);
+  APPEND(F.quant_lf_off, d->quant_lf, nb, 16);
+  APPEND(F.ytox_off, d->ytox_map, ncm, 16);
+  APPEND(F.ytob_off, d->ytob_map, ncm, 16);
+  F.section_base = uint32_t(b->sections.size());
+  for (uint32_t s = 0; s < n_sections; s++) {
+    SectionDev sd;
+    uint64_t o;
+    // 8-byte aligned copy followed by >= 8 zero bytes: the device bit reader
+    // refills with aligned 32-bit words and may look one word past the end.
+    int64_t oo = b->blob.append(hf_bytes + sec_off[s], sec_len[s], 8, 8);
+    if (oo < 0) return set_error(JXG_ERR_CUDA, "pinned staging allocation failed");
+    o = uint64_t(oo);
+    sd.off = o;
+    sd.len = sec_len[s];
+    sd.pad = 0;
+    b->sections.push_back(sd);
+  }
+#undef APPEND
+  F.first_stream = uint32_t(b->streams.size());
+  for (uint32_t g = 0; g < F.num_groups; g++) {
+    b->streams.push_back(StreamDev{uint32_t(b->frames.size()), g});
+    b->nz_base.push_back(b->nz_bytes);
+    b->nz_bytes += size_t(F.num_passes) * 3072;
+  }
+  F.coeff_group_base = b->total_groups;
+  b->total_groups += F.num_groups;
+  F.block_base = b->total_blocks;
+  b->total_blocks += nb;
+  F.plane_size = size_t(F.plane_stride) * F.plane_rows;
+  F.plane_base = b->total_plane_floats;
+  b->total_plane_floats += 3 * F.plane_size;
+  F.out_row_stride = out_row_stride;
+  size_t rows = d->output_format == JXG_FORMAT_XYB_F32_PLANAR ? size_t(F.height) * 3 : F.height;
+  FrameOut fo{out, out_row_stride, rows, rows * out_row_stride, out_is_device != 0, 0};
+  if (!fo.is_device) {
+    fo.dev_off = (b->out_bytes + 255) / 256 * 256;
+    b->out_bytes = fo.dev_off + fo.bytes;
+  }
+  b->outs.push_back(fo);
+  F.gab = d->gab;
+  for (int c = 0; c < 3; c++) {  // gaborish.rs:20-27
+    float total = 1.0f + d->gab_w1[c] * 4.0f + d->gab_w2[c] * 4.0f;
+    F.gab_k0[c] = 1.0f / total;
+    F.gab_k1[c] = d->gab_w1[c] / total;
+    F.gab_k2[c] = d->gab_w2[c] / total;
+  }
+  F.epf_iters = d->epf_iters;
+  memcpy(F.epf_sharp_lut, d->epf_sharp_lut, sizeof(F.epf_sharp_lut));
+  memcpy(F.epf_channel_scale, d->epf_channel_scale, sizeof(F.epf_channel_scale));
+  F.epf_quant_mul = d->epf_quant_mul;
+  F.epf_pass0_sigma_scale = d->epf_pass0_sigma_scale;
+  F.epf_pass2_sigma_scale = d->epf_pass2_sigma_scale;
+  F.epf_border_sad_mul = d->epf_border_sad_mul;
+  F.quant_scale = 1.0f / F.inv_global_scale;
+  memcpy(F.opsin, d->opsin_inverse_matrix, sizeof(F.opsin));
+  F.intensity_scale = 255.0f / d->intensity_target;
+  for (int i = 0; i < 3; i++) {  // xyb.rs:147-160
+    F.bias_cbrt[i] = std::cbrt(d->opsin_biases[i]);
+    F.scaled_bias[i] = d->opsin_biases[i] * F.intensity_scale;
+  }
+  F.output_tf = d->output_tf;
+  F.output_format = d->output_format;
+  b->max_epf = std::max(b->max_epf, d->epf_iters);
+  b->any_gab = b->any_gab || d->gab;
+  uint32_t tiles = ((F.width + 31) / 32) * ((F.height + 7) / 8);
+  b->tile_prefix.push_back(b->tile_prefix.back() + tiles);
+  b->frames.push_back(F);
+  return JXG_OK;
+}
+
+static int launch(Batch* b, cudaStream_t s) {
+  BatchDev B;
+  memset(&B, 0, sizeof(B));
+  B.blob = static_cast<const uint8_t*>(b->d_blob.p);
+  B.frames = static_cast<const FrameDev*>(b->d_frames.p);
+  B.sections = static_cast<const SectionDev*>(b->d_sections.p);
+  B.streams = static_cast<const StreamDev*>(b->d_streams.p);
+  B.num_frames = uint32_t(b->frames.size());
+  B.num_streams = uint32_t(b->streams.size());
+  B.coeffs = static_cast<int32_t*>(b->d_coeffs.p);
+  B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
+  B.nz = static_cast<uint8_t*>(b->d_nz.p);
+  B.nz_base = static_cast<uint64_t*>(b->d_nz_base.p);
+  B.planes_a = static_cast<float*>(b->d_planes_a.p);
+  B.planes_b = static_cast<float*>(b->d_planes_b.p);
+  B.status = static_cast<int32_t*>(b->d_status.p);
+  B.dequant_default = static_cast<const float*>(b->ctx->dequant_default.p);
+  B.dequant_default_off = static_cast<const uint32_t*>(b->ctx->dequant_default_off.p);
+  B.natural_orders = static_cast<const uint32_t*>(b->ctx->natural_orders.p);
+  B.natural_order_off = static_cast<const uint32_t*>(b->ctx->natural_order_off.p);
+  size_t coeff_bytes = size_t(b->total_groups) * 3 * kGroupCoeffs * 4;
+  b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
+                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int copy_out(Batch* b, cudaStream_t s) {
+  for (size_t f = 0; f < b->outs.size(); f++) {
+    const FrameOut& fo = b->outs[f];
+    if (fo.is_device) continue;
+    CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.bytes, cudaMemcpyDeviceToHost, s));
+    b->d2h += fo.bytes;
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int jxg_batch_run(void* bp, void* cuda_stream) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || b->frames.empty()) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  b->h2d = b->d2h = 0;
+  // device allocations
+  if (int r = b->d_blob.ensure(b->blob.size)) return r;
+  if (int r = b->d_coeffs.ensure(size_t(b->total_groups) * 3 * kGroupCoeffs * 4)) return r;
+  if (int r = b->d_block_off.ensure(b->total_blocks * 4)) return r;
+  if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
+  if (int r = b->d_planes_a.ensure(b->total_plane_floats * 4)) return r;
+  if (int r = b->d_planes_b.ensure(b->total_plane_floats * 4)) return r;
+  if (int r = b->d_status.ensure(b->streams.size() * 4)) return r;
+  if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
+  for (size_t f = 0; f < b->frames.size(); f++)
+    b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
+  b->status_host.assign(b->streams.size(), 0);
+  CUDA_TRY(cudaEventRecord(b->ev0, s));
+  CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
+  b->h2d += b->blob.size;
+  if (int r = upload(b->d_frames, b->frames, s, &b->h2d)) return r;
+  if (int r = upload(b->d_sections, b->sections, s, &b->h2d)) return r;
+  if (int r = upload(b->d_streams, b->streams, s, &b->h2d)) return r;
+  if (int r = upload(b->d_nz_base, b->nz_base, s, &b->h2d)) return r;
+  if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
+  b->uploaded = true;
+  if (int r = launch(b, s)) return r;
+  if (int r = copy_out(b, s)) return r;
+  CUDA_TRY(cudaEventRecord(b->ev1, s));
+  return JXG_OK;
+}
+
+int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || !b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch was never submitted");
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  CUDA_TRY(cudaEventRecord(b->ev0, s));
+  if (int r = launch(b, s)) return r;
+  CUDA_TRY(cudaEventRecord(b->ev1, s));
+  CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
+  return JXG_OK;
+}
+
+int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_group) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  CUDA_TRY(cudaEventSynchronize(b->ev1));
+  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  CUDA_TRY(cudaGetLastError());
+  cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
+  for (size_t i = 0; i < b->status_host.size(); i++)
+    if (b->status_host[i] != 0) {
+      if (first_bad_frame) *first_bad_frame = b->streams[i].frame;
+      if (first_bad_group) *first_bad_group = b->streams[i].group;
+      return set_error(b->status_host[i], "entropy decode failed in frame " + std::to_string(b->streams[i].frame) +
+                                              " group " + std::to_string(b->streams[i].group));
+    }
+  return JXG_OK;
+}
+
+int jxg_batch_stats(void* bp, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, float* last_device_ms) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b) return JXG_ERR_ARGUMENT;
+  if (kernel_launches) *kernel_launches = b->launches;
+  if (h2d_bytes) *h2d_bytes = b->h2d;
+  if (d2h_bytes) *d2h_bytes = b->d2h;
+  if (last_device_ms) *last_device_ms = b->last_ms;
+  return JXG_OK;
+}
+
+int jxg_batch_read_coeffs(void* bp, uint32_t f, int32_t* out, size_t out_len) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || f >= b->frames.size() || !b->uploaded) return JXG_ERR_ARGUMENT;
+  const FrameDev& F = b->frames[f];
+  size_t n = size_t(F.num_groups) * 3 * kGroupCoeffs;
+  if (out_len < n) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  CUDA_TRY(cudaMemcpy(out, static_cast<int32_t*>(b->d_coeffs.p) + F.coeff_group_base * 3 * kGroupCoeffs, n * 4, cudaMemcpyDeviceToHost));
+  return JXG_OK;
+}
+
+int jxg_batch_read_xyb(void* bp, uint32_t f, int stage, float* out, size_t out_len) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || f >= b->frames.size() || !b->uploaded) return JXG_ERR_ARGUMENT;
+  const FrameDev& F = b->frames[f];
+  size_t n = 3 * F.plane_size;
+  if (out_len < n) return JXG_ERR_ARGUMENT;
+  const float* src = stage == 0 ? static_cast<const float*>(b->d_planes_a.p) : b->final_planes;
+  if (!src) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  CUDA_TRY(cudaMemcpy(out, src + F.plane_base, n * 4, cudaMemcpyDeviceToHost));
+  return JXG_OK;
+}
+
+// ---------------- host front-end convenience ----------------
+
+int jxg_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info) {
+  if (!data || !parsed) return JXG_ERR_ARGUMENT;
+  try {
+    std::unique_ptr<jxg::FrameState> fs = jxg::parse_vardct_file(data, size);
+    if (info) {
+      info->width = fs->header.xsize();
+      info->height = fs->header.ysize();
+      info->num_groups = fs->header.num_groups();
+      info->num_passes = fs->header.passes.num_passes;
+      info->encoding = 0;
+      info->hf_bytes = 0;
+      for (uint32_t l : fs->hf_len) info->hf_bytes += l;
+    }
+    *parsed = fs.release();
+    return JXG_OK;
+  } catch (jxg::Error& e) {
+    return set_error(e.code, e.what());
+  } catch (std::exception& e) {
+    return set_error(JXG_ERR_BITSTREAM, e.what());
+  }
+}
+
+void jxg_parsed_free(void* parsed) { delete static_cast<jxg::FrameState*>(parsed); }
+
+int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, const uint8_t** hf_bytes,
+                    const uint64_t** sec_off, const uint32_t** sec_len, uint32_t* n_sections) {
+  jxg::FrameState* fs = static_cast<jxg::FrameState*>(parsed);
+  if (!fs || !desc) return JXG_ERR_ARGUMENT;
+  fs->fill_desc(desc, output_format);
+  if (hf_bytes) *hf_bytes = fs->codestream.data();
+  if (sec_off) *sec_off = fs->hf_off.data();
+  if (sec_len) *sec_len = fs->hf_len.data();
+  if (n_sections) *n_sections = uint32_t(fs->hf_off.size());
+  return JXG_OK;
+}
+
+int jxg_batch_add_parsed(void* batch, void* parsed, uint32_t output_format, void* out, size_t out_row_stride,
+                         int out_is_device) {
+  jxg::FrameState* fs = static_cast<jxg::FrameState*>(parsed);
+  if (!fs) return JXG_ERR_ARGUMENT;
+  JxgFrameDesc d;
+  fs->fill_desc(&d, output_format);
+  return jxg_batch_add_frame(batch, &d, fs->codestream.data(), fs->hf_off.data(), fs->hf_len.data(),
+                             uint32_t(fs->hf_off.size()), out, out_row_stride, out_is_device);
+}
+
+}  // extern "C"

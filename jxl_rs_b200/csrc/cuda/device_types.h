@@ -1,0 +1,95 @@
+// Device-visible layout of a decode batch. One "blob" (uploaded with a single
+// H2D copy from pinned staging) carries every per-frame table and plane the
+// kernels read; FrameDev holds byte offsets into it. Large intermediates
+// (coefficients, XYB planes) live in separate device-only allocations.
+#pragma once
+#include <stdint.h>
+
+namespace jxgpu {
+
+constexpr int kMaxPasses = 11;
+constexpr uint32_t kGroupCoeffs = 65536;  // per channel per group (group.rs:53-55)
+
+struct PassDev {
+  uint32_t shift, use_prefix, log_alpha_size, num_clusters;
+  uint32_t lz77_enabled, lz77_min_symbol, lz77_min_length, lz77_length_uint, lz_dist_cluster;
+  uint32_t custom_orders;
+  uint64_t context_map_off;   // u8[]
+  uint64_t uint_configs_off;  // u32[num_clusters]
+  uint64_t ans_off;           // u64[num_clusters << log_alpha_size]
+  uint64_t huff_off;          // u32[] entries
+  uint64_t huff_offset_off;   // u32[num_clusters]
+  uint64_t order_off;         // u32[] custom orders
+  uint32_t order_offset[39];
+};
+
+struct FrameDev {
+  uint32_t width, height, xb, yb, xg, yg, num_groups, num_passes;
+  uint32_t plane_stride, plane_rows;     // padded XYB plane geometry (xb*8, yb*8)
+  uint32_t cxb;                          // ceil(xb/8): CfL map stride
+  // entropy / contexts
+  uint32_t num_histograms, num_block_contexts, num_lf_contexts, num_qf_thresholds;
+  uint32_t qf_thresholds[15];
+  uint64_t block_ctx_map_off;
+  PassDev passes[kMaxPasses];
+  // dequant
+  float inv_global_scale, x_dm, b_dm;
+  float quant_biases[4];
+  float base_correlation_x, base_correlation_b, inv_color_factor_unused;
+  uint32_t color_factor;
+  int64_t dequant_off[17];  // byte offset into blob, or -1 = library default table
+  // planes in the blob
+  uint64_t lf_off[3];  // f32 xb*yb
+  uint64_t transform_off, raw_quant_off, epf_off, quant_lf_off, ytox_off, ytob_off;
+  // HF sections: index of this frame's first section in the batch section table
+  uint32_t section_base;
+  uint32_t first_stream;      // index of group 0 in the batch stream list
+  // device-only buffers (element offsets)
+  uint64_t coeff_group_base;  // group index base into coeffs
+  uint64_t block_base;        // block index base into block_off
+  uint64_t plane_base;        // float index base into plane sets (per channel: + c * plane_size)
+  uint64_t plane_size;        // plane_stride * plane_rows
+  uint64_t out_off;           // byte offset into device output buffer (or absolute pointer if out_is_ptr)
+  uint64_t out_row_stride;
+  void* out_ptr;              // device pointer for this frame's output
+  // filters / colour
+  uint32_t gab, epf_iters;
+  float gab_k0[3], gab_k1[3], gab_k2[3];  // normalised weights (gaborish.rs:20-27)
+  float epf_sharp_lut[8], epf_channel_scale[3];
+  float epf_quant_mul, epf_pass0_sigma_scale, epf_pass2_sigma_scale, epf_border_sad_mul;
+  float quant_scale;  // 1 / inv_global_scale (features/epf.rs:55)
+  float opsin[9], bias_cbrt[3], scaled_bias[3], intensity_scale;
+  uint32_t output_tf, output_format;
+};
+
+struct SectionDev {
+  uint64_t off;  // byte offset in blob (8-byte aligned, zero padded)
+  uint32_t len;
+  uint32_t pad;
+};
+
+struct StreamDev {  // one (frame, group) unit of entropy-decode work
+  uint32_t frame, group;
+};
+
+struct BatchDev {
+  const uint8_t* blob;
+  const FrameDev* frames;
+  const SectionDev* sections;
+  const StreamDev* streams;
+  uint32_t num_frames, num_streams;
+  int32_t* coeffs;      // [groups][3][65536]
+  uint32_t* block_off;  // per 8x8 block: coefficient offset of the varblock starting there
+  uint8_t* nz;          // [streams][passes][3][1024]
+  uint64_t* nz_base;    // per stream offset into nz (bytes)
+  float* planes_a;
+  float* planes_b;
+  int32_t* status;      // per stream
+  // context-wide tables
+  const float* dequant_default;       // 17 tables concatenated
+  const uint32_t* dequant_default_off;  // [17] float offsets
+  const uint32_t* natural_orders;     // 13 orders concatenated
+  const uint32_t* natural_order_off;  // [13]
+};
+
+}  // namespace jxgpu

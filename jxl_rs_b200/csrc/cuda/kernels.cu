@@ -1,0 +1,1179 @@
+// sm_100a kernels of the VarDCT hot path (first correct version).
+//
+//   k_entropy   K1  one warp per (frame, group) stream: ANS / prefix decode of the
+//                   AC coefficients with the JPEG XL context model
+//                   (jxl/src/frame/group.rs:454-578, entropy_coding/*.rs)
+//   k_dequant_idct K2 one CTA per group: dequant + chroma-from-luma + LLF + inverse
+//                   variable-block DCT (group.rs:100-250, jxl_transforms/src/transform.rs)
+//   k_gaborish  K3  3x3 smoothing (render/stages/gaborish.rs)
+//   k_epf       K4  edge-preserving filter passes 0/1/2 (render/stages/epf/*.rs)
+//   k_xyb_store K5  XYB -> linear -> sRGB -> u8/f32 interleaved store
+//                   (render/stages/{xyb,from_linear,convert}.rs, color/tf.rs)
+//
+// No tensor cores: there is no dense contraction on this path; everything is
+// HBM / latency bound integer and f32 work.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/jxg.h"
+#include "device_types.h"
+
+namespace jxgpu {
+
+__constant__ float c_wc[9][128];       // 1 / (2 cos((i + 0.5) pi / n)), n = 2^l
+__constant__ float c_rdct_scale[6][32];  // reinterpreting-DCT output scales (6 decimals)
+__constant__ uint8_t c_cov_x[27] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
+__constant__ uint8_t c_cov_y[27] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
+__constant__ uint8_t c_shape[27] = {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12};
+__constant__ uint8_t c_qtable[27] = {0, 1, 2, 3, 4, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10, 10, 11, 12, 12, 13, 14, 14, 15, 16, 16};
+// block_context_map.rs:20-31
+__constant__ uint16_t c_freq_ctx[64] = {0xBAD, 0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 15, 16, 16, 17, 17,
+                                        18,    18, 19, 19, 20, 20, 21, 21, 22, 22, 23, 23, 23, 23, 24, 24, 24, 24, 25, 25, 25, 25,
+                                        26,    26, 26, 26, 27, 27, 27, 27, 28, 28, 28, 28, 29, 29, 29, 29, 30, 30, 30, 30};
+__constant__ uint16_t c_nz_ctx[64] = {0xBAD, 0,   31,  62,  62,  93,  93,  93,  93,  123, 123, 123, 123, 152, 152, 152,
+                                      152,   152, 152, 152, 152, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180,
+                                      180,   206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206,
+                                      206,   206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
+__constant__ float c_afv[256] = {
+#include "afv_basis.inc"
+};
+__constant__ float c_dither[1024] = {
+#include "dither_table.inc"
+};
+
+// ===========================================================================
+// K1: entropy decode
+// ===========================================================================
+
+// bit_reader.rs:15-219 restated for 32-bit word refills from an 8-byte aligned,
+// zero-padded section copy. Reads past the end return zeros (optimistic reads);
+// over-read is detected at the end (check_for_error, :109).
+struct DevBr {
+  const uint32_t* words;
+  uint32_t nwords, wpos;
+  uint64_t buf;
+  uint32_t bits, total;
+  __device__ __forceinline__ void init(const uint8_t* p, uint32_t len) {
+    words = reinterpret_cast<const uint32_t*>(p);
+    nwords = (len + 3) >> 2;
+    wpos = 0;
+    buf = 0;
+    bits = 0;
+    total = 0;
+  }
+  __device__ __forceinline__ void ensure(uint32_t n) {
+    if (bits < n) {
+      uint32_t w = wpos < nwords ? __ldg(words + wpos) : 0u;
+      wpos++;
+      buf |= uint64_t(w) << bits;
+      bits += 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t peek(uint32_t n) {  // n <= 32
+    ensure(n);
+    return uint32_t(buf & ((1ull << n) - 1ull));
+  }
+  __device__ __forceinline__ void consume(uint32_t n) {
+    buf >>= n;
+    bits -= n;
+    total += n;
+  }
+  __device__ __forceinline__ uint32_t read(uint32_t n) {
+    uint32_t v = peek(n);
+    consume(n);
+    return v;
+  }
+};
+
+struct PassState {
+  DevBr br;
+  uint32_t ans_state;
+  uint32_t hist_idx;
+};
+
+// hybrid_uint.rs:87-102
+__device__ __forceinline__ uint32_t hybrid_uint(uint32_t cfg, uint32_t token, DevBr& br) {
+  uint32_t split_exponent = cfg & 0xff, msb = (cfg >> 8) & 0xff, lsb = (cfg >> 16) & 0xff;
+  uint32_t split_token = 1u << split_exponent;
+  if (token < split_token) return token;
+  uint32_t bits_in_token = lsb + msb;
+  uint32_t nbits = (split_exponent - bits_in_token + ((token - split_token) >> bits_in_token)) & 31;
+  uint32_t low = token & ((1u << lsb) - 1);
+  uint32_t token_nolow = token >> lsb;
+  uint32_t bits = br.read(nbits);
+  uint32_t hi = (token_nolow & ((1u << msb) - 1)) | (1u << msb);
+  return (((hi << nbits) | bits) << lsb) | low;
+}
+
+struct PassTables {
+  const uint8_t* context_map;
+  const uint32_t* uint_configs;
+  const uint2* ans;  // 8-byte buckets
+  const uint32_t* huff;
+  const uint32_t* huff_offset;
+  uint32_t use_prefix, log_alpha_size;
+};
+
+// ans.rs:356-393 / huffman.rs:446-457
+__device__ __forceinline__ uint32_t read_token(const PassTables& T, PassState& s, uint32_t cluster) {
+  if (T.use_prefix) {
+    const uint32_t* t = T.huff + __ldg(T.huff_offset + cluster);
+    uint32_t pos = s.br.peek(8);
+    uint32_t e = __ldg(t + pos);
+    uint32_t n_bits = e & 0xff;
+    if (n_bits > 8) {
+      s.br.consume(8);
+      n_bits -= 8;
+      pos += e >> 16;
+      pos += s.br.peek(n_bits);
+      e = __ldg(t + pos);
+    }
+    s.br.consume(e & 0xff);
+    return e >> 16;
+  }
+  const uint32_t log_bucket = 12 - T.log_alpha_size;
+  uint32_t idx = s.ans_state & 0xfff;
+  uint32_t i = idx >> log_bucket;
+  uint32_t pos = idx & ((1u << log_bucket) - 1);
+  uint2 b = __ldg(T.ans + ((size_t(cluster) << T.log_alpha_size) + i));
+  uint32_t alias_symbol = b.x & 0xff, alias_cutoff = (b.x >> 8) & 0xff, dist = b.x >> 16;
+  uint32_t alias_offset = b.y & 0xffff, alias_dist_xor = b.y >> 16;
+  bool alias = pos >= alias_cutoff;
+  uint32_t offset = (alias ? alias_offset : 0u) + pos;
+  dist ^= alias ? alias_dist_xor : 0u;
+  uint32_t symbol = alias ? alias_symbol : i;
+  uint32_t next = (s.ans_state >> 12) * dist + offset;
+  if (next < (1u << 16)) {
+    next = (next << 16) | s.br.peek(16);
+    s.br.consume(16);
+  }
+  s.ans_state = next;
+  return symbol;
+}
+
+__device__ __forceinline__ uint32_t read_symbol(const PassTables& T, PassState& s, uint32_t ctx) {
+  uint32_t cluster = __ldg(T.context_map + ctx);
+  uint32_t tok = read_token(T, s, cluster);
+  return hybrid_uint(__ldg(T.uint_configs + cluster), tok, s.br);
+}
+
+__device__ __forceinline__ int32_t unpack_signed(uint32_t u) { return int32_t((u >> 1) ^ (((~u) & 1u) - 1u)); }
+
+struct BlockInfo {
+  uint32_t bx, by, cx, cy, shape, raw_quant, quant_lf, num_blocks, num_coeffs, log_num_blocks;
+};
+
+// One varblock, one pass: the three channels in Y, X, B order (group.rs:509-577).
+__device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameDev& F, const PassDev& P,
+                                                 const PassTables& T, PassState& s, uint32_t pass, const BlockInfo& bi,
+                                                 uint8_t* nz_pass /* [3][1024] */, int32_t* group_coeffs,
+                                                 uint32_t coeffs_offset) {
+  const uint32_t num_ac_contexts = F.num_block_contexts * (37 + 458);
+  const uint32_t context_offset = s.hist_idx * num_ac_contexts;
+  const uint8_t* bcm = B.blob + F.block_ctx_map_off;
+#pragma unroll 1
+  for (int ci = 0; ci < 3; ci++) {
+    const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
+    uint8_t* nz = nz_pass + c * 1024;
+    uint32_t predicted;
+    if (bi.bx == 0) predicted = bi.by == 0 ? 32u : nz[(bi.by - 1) * 32];
+    else if (bi.by == 0) predicted = nz[bi.bx - 1];
+    else predicted = (uint32_t(nz[(bi.by - 1) * 32 + bi.bx]) + uint32_t(nz[bi.by * 32 + bi.bx - 1]) + 1u) >> 1;
+    uint32_t qf_idx = 0;
+    for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += bi.raw_quant > F.qf_thresholds[i];
+    uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u;
+    idx = idx * 13 + bi.shape;
+    idx = idx * (F.num_qf_thresholds + 1) + qf_idx;
+    idx = idx * F.num_lf_contexts + bi.quant_lf;
+    uint32_t block_context = __ldg(bcm + idx);
+    uint32_t nzc = predicted < 8 ? predicted : (predicted < 64 ? 4 + predicted / 2 : 36);
+    uint32_t nonzeros = read_symbol(T, s, nzc * F.num_block_contexts + block_context + context_offset);
+    if (nonzeros + bi.num_blocks > bi.num_coeffs) return JXG_ERR_INVALID_NUM_NONZEROS;
+    uint8_t nzv = uint8_t((nonzeros + bi.num_blocks - 1) >> bi.log_num_blocks);
+    for (uint32_t iy = 0; iy < bi.cy; iy++)
+      for (uint32_t ix = 0; ix < bi.cx; ix++) nz[(bi.by + iy) * 32 + bi.bx + ix] = nzv;
+    const uint32_t histo_offset = F.num_block_contexts * 37 + 458 * block_context + context_offset;
+    uint32_t prev = nonzeros > bi.num_coeffs / 16 ? 0u : 1u;
+    const uint32_t* order = P.custom_orders
+                                ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[bi.shape * 3 + c]
+                                : B.natural_orders + B.natural_order_off[bi.shape];
+    int32_t* cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+    const uint32_t lnb = bi.log_num_blocks, rnd = bi.num_blocks - 1;
+#pragma unroll 1
+    for (uint32_t k = bi.num_blocks; k < bi.num_coeffs && nonzeros != 0; k++) {
+      uint32_t ctx = histo_offset + (uint32_t(c_nz_ctx[((nonzeros + rnd) >> lnb) & 63]) + uint32_t(c_freq_ctx[(k >> lnb) & 63])) * 2 + prev;
+      uint32_t u = read_symbol(T, s, ctx);
+      int32_t coeff = int32_t(uint32_t(unpack_signed(u)) << P.shift);
+      prev = coeff != 0;
+      nonzeros -= prev;
+      if (coeff != 0) {
+        uint32_t pos = __ldg(order + k);
+        if (pass == 0) cur[pos] = coeff;
+        else cur[pos] += coeff;
+      }
+    }
+    if (nonzeros != 0) return JXG_ERR_RESIDUAL_NONZEROS;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ PassTables make_tables(const BatchDev& B, const PassDev& P) {
+  PassTables T;
+  T.context_map = B.blob + P.context_map_off;
+  T.uint_configs = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
+  T.ans = reinterpret_cast<const uint2*>(B.blob + P.ans_off);
+  T.huff = reinterpret_cast<const uint32_t*>(B.blob + P.huff_off);
+  T.huff_offset = reinterpret_cast<const uint32_t*>(B.blob + P.huff_offset_off);
+  T.use_prefix = P.use_prefix;
+  T.log_alpha_size = P.log_alpha_size;
+  return T;
+}
+
+__device__ __forceinline__ int init_pass(const BatchDev& B, const FrameDev& F, uint32_t pass, uint32_t g, PassState& s) {
+  const SectionDev sec = B.sections[F.section_base + pass * F.num_groups + g];
+  s.br.init(B.blob + sec.off, sec.len);
+  uint32_t nb = 0;
+  while ((1u << nb) < F.num_histograms) nb++;
+  s.hist_idx = s.br.read(nb);  // group.rs:333-341
+  if (s.hist_idx >= F.num_histograms) return JXG_ERR_INVALID_HISTOGRAM_INDEX;
+  s.ans_state = 0x130000u;
+  if (!F.passes[pass].use_prefix) s.ans_state = s.br.read(32);  // ans.rs:431
+  return 0;
+}
+
+__device__ __forceinline__ int finish_pass(const BatchDev& B, const FrameDev& F, uint32_t pass, uint32_t g, const PassState& s) {
+  const SectionDev sec = B.sections[F.section_base + pass * F.num_groups + g];
+  if (s.br.total > sec.len * 8u) return JXG_ERR_OUT_OF_BOUNDS;                          // bit_reader.rs:109
+  if (!F.passes[pass].use_prefix && s.ans_state != 0x130000u) return JXG_ERR_ANS_CHECKSUM;  // ans.rs:441
+  return 0;
+}
+
+constexpr int kEntropyWarps = 4;
+
+__global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B) {
+  const uint32_t stream = blockIdx.x * kEntropyWarps + (threadIdx.x >> 5);
+  if (stream >= B.num_streams || (threadIdx.x & 31) != 0) return;
+  const StreamDev sd = B.streams[stream];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t gx = g % F.xg, gy = g / F.xg;
+  const uint32_t bx0 = gx * 32, by0 = gy * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
+  int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  uint8_t* nz = B.nz + B.nz_base[stream];
+  const uint8_t* tmap = B.blob + F.transform_off;
+  const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
+  const uint8_t* qlf = B.blob + F.quant_lf_off;
+  uint32_t* block_off = B.block_off + F.block_base;
+  const uint32_t np = F.num_passes;
+  int err = 0;
+  uint32_t coeffs_offset = 0;
+
+  if (np == 1) {
+    PassState s;
+    err = init_pass(B, F, 0, g, s);
+    const PassTables T = make_tables(B, F.passes[0]);
+    for (uint32_t by = 0; by < gh && !err; by++) {
+      for (uint32_t bx = 0; bx < gw && !err; bx++) {
+        const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+        uint32_t raw_t = tmap[bidx];
+        if (raw_t < 128) continue;
+        uint32_t t = raw_t & 127;
+        if (t >= 27) { err = JXG_ERR_INVALID_TRANSFORM; break; }
+        BlockInfo bi;
+        bi.bx = bx; bi.by = by; bi.cx = c_cov_x[t]; bi.cy = c_cov_y[t]; bi.shape = c_shape[t];
+        bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
+        bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
+        bi.log_num_blocks = 31 - __clz(bi.num_blocks);
+        block_off[bidx] = coeffs_offset;
+        err = decode_block_pass(B, F, F.passes[0], T, s, 0, bi, nz, group_coeffs, coeffs_offset);
+        coeffs_offset += bi.num_coeffs;
+      }
+    }
+    if (!err) err = finish_pass(B, F, 0, g, s);
+  } else {
+    PassState st[kMaxPasses];
+    for (uint32_t p = 0; p < np && !err; p++) err = init_pass(B, F, p, g, st[p]);
+    for (uint32_t by = 0; by < gh && !err; by++) {
+      for (uint32_t bx = 0; bx < gw && !err; bx++) {
+        const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+        uint32_t raw_t = tmap[bidx];
+        if (raw_t < 128) continue;
+        uint32_t t = raw_t & 127;
+        if (t >= 27) { err = JXG_ERR_INVALID_TRANSFORM; break; }
+        BlockInfo bi;
+        bi.bx = bx; bi.by = by; bi.cx = c_cov_x[t]; bi.cy = c_cov_y[t]; bi.shape = c_shape[t];
+        bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
+        bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
+        bi.log_num_blocks = 31 - __clz(bi.num_blocks);
+        block_off[bidx] = coeffs_offset;
+        for (uint32_t p = 0; p < np && !err; p++) {
+          PassState s = st[p];
+          const PassTables T = make_tables(B, F.passes[p]);
+          err = decode_block_pass(B, F, F.passes[p], T, s, p, bi, nz + p * 3072, group_coeffs, coeffs_offset);
+          st[p] = s;
+        }
+        coeffs_offset += bi.num_coeffs;
+      }
+    }
+    for (uint32_t p = 0; p < np && !err; p++) err = finish_pass(B, F, p, g, st[p]);
+  }
+  B.status[stream] = err;
+}
+
+// ===========================================================================
+// K2: dequant + CfL + LLF + inverse DCT
+// ===========================================================================
+
+template <int N>
+struct Log2 {
+  static constexpr int v = 1 + Log2<N / 2>::v;
+};
+template <>
+struct Log2<1> {
+  static constexpr int v = 0;
+};
+
+// gen_idct.py:112-127 / idct_large.rs:251-310: even/odd split recursion.
+template <int N>
+__device__ __forceinline__ void idct1d(float* v) {
+  if constexpr (N == 1) {
+    return;
+  } else if constexpr (N == 2) {
+    float a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  } else {
+    constexpr int H = N / 2;
+    float first[H], second[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      first[i] = v[2 * i];
+      second[i] = v[2 * i + 1];
+    }
+    idct1d<H>(first);
+#pragma unroll
+    for (int i = H - 1; i >= 1; i--) second[i] += second[i - 1];
+    second[0] *= 1.41421356237309504880f;
+    idct1d<H>(second);
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      float mul = c_wc[Log2<N>::v][i];
+      v[i] = fmaf(second[i], mul, first[i]);
+      v[N - 1 - i] = fmaf(-second[i], mul, first[i]);
+    }
+  }
+}
+
+// Large sizes: same recursion, arrays in local memory, loops not unrolled.
+template <int N>
+__device__ __noinline__ void idct1d_large(float* v) {
+  if constexpr (N <= 32) {
+    idct1d<N>(v);
+  } else {
+    constexpr int H = N / 2;
+    float first[H], second[H];
+#pragma unroll 1
+    for (int i = 0; i < H; i++) {
+      first[i] = v[2 * i];
+      second[i] = v[2 * i + 1];
+    }
+    idct1d_large<H>(first);
+#pragma unroll 1
+    for (int i = H - 1; i >= 1; i--) second[i] += second[i - 1];
+    second[0] *= 1.41421356237309504880f;
+    idct1d_large<H>(second);
+#pragma unroll 1
+    for (int i = 0; i < H; i++) {
+      float mul = c_wc[Log2<N>::v][i];
+      v[i] = fmaf(second[i], mul, first[i]);
+      v[N - 1 - i] = fmaf(-second[i], mul, first[i]);
+    }
+  }
+}
+
+// gen_reinterpreting_dct.py:47-136
+template <int N>
+__device__ __forceinline__ void rdct1d_rec(float* v) {
+  if constexpr (N == 1) {
+    return;
+  } else if constexpr (N == 2) {
+    float a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  } else {
+    constexpr int H = N / 2;
+    float first[H], second[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      first[i] = v[i] + v[N - 1 - i];
+      second[i] = v[i] - v[N - 1 - i];
+    }
+    rdct1d_rec<H>(first);
+#pragma unroll
+    for (int i = 0; i < H; i++) second[i] *= c_wc[Log2<N>::v][i];
+    rdct1d_rec<H>(second);
+    second[0] = fmaf(second[0], 1.41421356237309504880f, second[1]);
+#pragma unroll
+    for (int i = 1; i + 1 < H; i++) second[i] = second[i] + second[i + 1];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      v[2 * i] = first[i];
+      v[2 * i + 1] = second[i];
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void rdct1d(float* v) {
+  if constexpr (N > 1) {
+    rdct1d_rec<N>(v);
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] *= c_rdct_scale[Log2<N>::v][i];
+  }
+}
+__device__ __noinline__ void rdct1d_dyn(float* v, int n) {
+  switch (n) {
+    case 2: rdct1d<2>(v); break;
+    case 4: rdct1d<4>(v); break;
+    case 8: rdct1d<8>(v); break;
+    case 16: rdct1d<16>(v); break;
+    case 32: rdct1d<32>(v); break;
+    default: break;
+  }
+}
+
+// LLF of one channel: cy x cx LF samples -> coefficients (tests.rs:154-180).
+// Serial (tiny); `put(vf, hf, value)` stores into the caller's layout.
+template <typename Put>
+__device__ __forceinline__ void llf_small(const float* lf, uint32_t lf_stride, int cy, int cx, Put put) {
+  float tmp[16];  // cy, cx <= 4
+  float line[4];
+  for (int y = 0; y < cy; y++) {
+    for (int x = 0; x < cx; x++) line[x] = lf[y * lf_stride + x];
+    if (cx == 2) rdct1d<2>(line);
+    else if (cx == 4) rdct1d<4>(line);
+    for (int x = 0; x < cx; x++) tmp[y * 4 + x] = line[x];
+  }
+  for (int hf = 0; hf < cx; hf++) {
+    for (int y = 0; y < cy; y++) line[y] = tmp[y * 4 + hf];
+    if (cy == 2) rdct1d<2>(line);
+    else if (cy == 4) rdct1d<4>(line);
+    for (int vf = 0; vf < cy; vf++) put(vf, hf, line[vf]);
+  }
+}
+
+// group.rs:85-96
+__device__ __forceinline__ float adjust_quant_bias(int32_t q, float bias_c, float bias3) {
+  float qf = float(q);
+  return (q > -2 && q < 2) ? qf * bias_c : qf - bias3 / qf;
+}
+
+struct DequantCtx {
+  const int32_t* qx;
+  const int32_t* qy;
+  const int32_t* qb;
+  const float* mat;
+  uint32_t num_coeffs;
+  float sx, sy, sb, x_cc, b_cc, bias0, bias1, bias2, bias3;
+  __device__ __forceinline__ void get(uint32_t k, float& vx, float& vy, float& vb) const {
+    float dy = adjust_quant_bias(qy[k], bias1, bias3) * (__ldg(mat + num_coeffs + k) * sy);
+    float dxc = adjust_quant_bias(qx[k], bias0, bias3) * (__ldg(mat + k) * sx);
+    float dbc = adjust_quant_bias(qb[k], bias2, bias3) * (__ldg(mat + 2 * num_coeffs + k) * sb);
+    vy = dy;
+    vx = fmaf(x_cc, dy, dxc);
+    vb = fmaf(b_cc, dy, dbc);
+  }
+};
+
+// ---- special 8x8 transforms, one lane per channel, serial (transform.rs:306-661) ----
+__device__ __forceinline__ void idct2d_4x4(float* b) {  // [hf][vf] layout, in place -> [y][x]
+  float t[16], line[4];
+  for (int vf = 0; vf < 4; vf++) {
+    for (int hf = 0; hf < 4; hf++) line[hf] = b[hf * 4 + vf];
+    idct1d<4>(line);
+    for (int x = 0; x < 4; x++) t[vf * 4 + x] = line[x];
+  }
+  for (int x = 0; x < 4; x++) {
+    for (int vf = 0; vf < 4; vf++) line[vf] = t[vf * 4 + x];
+    idct1d<4>(line);
+    for (int y = 0; y < 4; y++) b[y * 4 + x] = line[y];
+  }
+}
+__device__ __forceinline__ void idct2d_4x8(float* b) {  // 4 rows x 8 cols, [vf][hf] -> [y][x]
+  float t[32], l8[8], l4[4];
+  for (int vf = 0; vf < 4; vf++) {
+    for (int hf = 0; hf < 8; hf++) l8[hf] = b[vf * 8 + hf];
+    idct1d<8>(l8);
+    for (int x = 0; x < 8; x++) t[vf * 8 + x] = l8[x];
+  }
+  for (int x = 0; x < 8; x++) {
+    for (int vf = 0; vf < 4; vf++) l4[vf] = t[vf * 8 + x];
+    idct1d<4>(l4);
+    for (int y = 0; y < 4; y++) b[y * 8 + x] = l4[y];
+  }
+}
+__device__ __forceinline__ void idct2d_8x4(float* b) {  // 8 rows x 4 cols, stored [hf][vf] stride 8 -> [y][x] stride 4
+  float t[32], l8[8], l4[4];
+  for (int vf = 0; vf < 8; vf++) {
+    for (int hf = 0; hf < 4; hf++) l4[hf] = b[hf * 8 + vf];
+    idct1d<4>(l4);
+    for (int x = 0; x < 4; x++) t[vf * 4 + x] = l4[x];
+  }
+  for (int x = 0; x < 4; x++) {
+    for (int vf = 0; vf < 8; vf++) l8[vf] = t[vf * 4 + x];
+    idct1d<8>(l8);
+    for (int y = 0; y < 8; y++) b[y * 4 + x] = l8[y];
+  }
+}
+
+__device__ __noinline__ void special_transform(int t, const float* co, float* px) {
+  if (t == 1) {  // IDENTITY
+    float b00 = co[0], b01 = co[1], b10 = co[8], b11 = co[9];
+    float dcs[4] = {b00 + b01 + b10 + b11, b00 + b01 - b10 - b11, b00 - b01 + b10 - b11, b00 - b01 - b10 + b11};
+    for (int y = 0; y < 2; y++)
+      for (int x = 0; x < 2; x++) {
+        float residual_sum = 0.0f;
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 4; ix++) {
+            if (ix == 0 && iy == 0) continue;
+            residual_sum += co[(y + iy * 2) * 8 + x + ix * 2];
+          }
+        float center = dcs[y * 2 + x] - residual_sum * (1.0f / 16.0f);
+        px[(4 * y + 1) * 8 + 4 * x + 1] = center;
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 4; ix++) {
+            if (ix == 1 && iy == 1) continue;
+            px[(y * 4 + iy) * 8 + x * 4 + ix] = co[(y + iy * 2) * 8 + x + ix * 2] + center;
+          }
+        px[y * 4 * 8 + x * 4] = co[(y + 2) * 8 + x + 2] + center;
+      }
+  } else if (t == 2) {  // DCT2X2
+    float tmp[64];
+    auto top = [](int s, const float* in, float* out) {
+      int n = s / 2;
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) {
+          float c00 = in[y * 8 + x], c01 = in[y * 8 + n + x], c10 = in[(y + n) * 8 + x], c11 = in[(y + n) * 8 + n + x];
+          out[y * 2 * 8 + x * 2] = c00 + c01 + c10 + c11;
+          out[y * 2 * 8 + x * 2 + 1] = c00 + c01 - c10 - c11;
+          out[(y * 2 + 1) * 8 + x * 2] = c00 - c01 + c10 - c11;
+          out[(y * 2 + 1) * 8 + x * 2 + 1] = c00 - c01 - c10 + c11;
+        }
+    };
+    for (int i = 0; i < 64; i++) {
+      tmp[i] = co[i];
+      px[i] = co[i];
+    }
+    top(2, tmp, px);
+    top(4, px, tmp);
+    top(8, tmp, px);
+  } else if (t == 3) {  // DCT4X4
+    float b00 = co[0], b01 = co[1], b10 = co[8], b11 = co[9];
+    float dcs[4] = {b00 + b01 + b10 + b11, b00 + b01 - b10 - b11, b00 - b01 + b10 - b11, b00 - b01 - b10 + b11};
+    for (int y = 0; y < 2; y++)
+      for (int x = 0; x < 2; x++) {
+        float block[16];
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 4; ix++) block[iy * 4 + ix] = co[(y + iy * 2) * 8 + x + ix * 2];
+        block[0] = dcs[y * 2 + x];
+        idct2d_4x4(block);
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 4; ix++) px[(y * 4 + iy) * 8 + x * 4 + ix] = block[iy * 4 + ix];
+      }
+  } else if (t == 12 || t == 13) {  // DCT4X8 / DCT8X4
+    float dcs[2] = {co[0] + co[8], co[0] - co[8]};
+    for (int h = 0; h < 2; h++) {
+      float block[32];
+      for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 8; ix++) block[iy * 8 + ix] = (ix == 0 && iy == 0) ? dcs[h] : co[(h + iy * 2) * 8 + ix];
+      if (t == 13) {
+        idct2d_8x4(block);
+        for (int iy = 0; iy < 8; iy++)
+          for (int ix = 0; ix < 4; ix++) px[iy * 8 + h * 4 + ix] = block[iy * 4 + ix];
+      } else {
+        idct2d_4x8(block);
+        for (int iy = 0; iy < 4; iy++)
+          for (int ix = 0; ix < 8; ix++) px[(h * 4 + iy) * 8 + ix] = block[iy * 8 + ix];
+      }
+    }
+  } else {  // AFV0..3
+    int kind = t - 14;
+    int afv_x = kind & 1, afv_y = kind / 2;
+    float b00 = co[0], b01 = co[1], b10 = co[8];
+    float dcs[3] = {(b00 + b10 + b01) * 4.0f, b00 + b10 - b01, b00 - b10};
+    float coeff[16], block[32];
+    for (int iy = 0; iy < 4; iy++)
+      for (int ix = 0; ix < 4; ix++) coeff[iy * 4 + ix] = (ix == 0 && iy == 0) ? dcs[0] : co[iy * 2 * 8 + ix * 2];
+    for (int i = 0; i < 16; i++) {
+      float p = 0.0f;
+      for (int j = 0; j < 16; j++) p += coeff[j] * c_afv[j * 16 + i];
+      block[i] = p;
+    }
+    for (int iy = 0; iy < 4; iy++) {
+      int by = afv_y ? 3 - iy : iy;
+      for (int ix = 0; ix < 4; ix++) {
+        int bx = afv_x ? 3 - ix : ix;
+        px[(iy + afv_y * 4) * 8 + afv_x * 4 + ix] = block[by * 4 + bx];
+      }
+    }
+    for (int iy = 0; iy < 4; iy++)
+      for (int ix = 0; ix < 4; ix++) block[iy * 4 + ix] = (ix == 0 && iy == 0) ? dcs[1] : co[iy * 2 * 8 + ix * 2 + 1];
+    idct2d_4x4(block);
+    for (int iy = 0; iy < 4; iy++)
+      for (int ix = 0; ix < 4; ix++) px[(iy + afv_y * 4) * 8 + (1 - afv_x) * 4 + ix] = block[iy * 4 + ix];
+    for (int iy = 0; iy < 4; iy++)
+      for (int ix = 0; ix < 8; ix++) block[iy * 8 + ix] = (ix == 0 && iy == 0) ? dcs[2] : co[(1 + iy * 2) * 8 + ix];
+    idct2d_4x8(block);
+    for (int iy = 0; iy < 4; iy++)
+      for (int ix = 0; ix < 8; ix++) px[(iy + (1 - afv_y) * 4) * 8 + ix] = block[iy * 8 + ix];
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void warp_row_pass(float* ch, int lane_row, int stride) {
+  float v[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = ch[lane_row * stride + i];
+  idct1d<N>(v);
+#pragma unroll
+  for (int i = 0; i < N; i++) ch[lane_row * stride + i] = v[i];
+}
+template <int N>
+__device__ __forceinline__ void warp_col_pass(float* ch, int lane_col, int stride) {
+  float v[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = ch[i * stride + lane_col];
+  idct1d<N>(v);
+#pragma unroll
+  for (int i = 0; i < N; i++) ch[i * stride + lane_col] = v[i];
+}
+
+constexpr int kIdctWarps = 8;
+constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
+
+// Global in-place 1-D passes for varblocks with a dimension >= 64.
+template <int N>
+__device__ __noinline__ void big_line_pass(float* base, size_t elem_stride) {
+  float v[N];
+#pragma unroll 1
+  for (int i = 0; i < N; i++) v[i] = base[i * elem_stride];
+  idct1d_large<N>(v);
+#pragma unroll 1
+  for (int i = 0; i < N; i++) base[i * elem_stride] = v[i];
+}
+__device__ __forceinline__ void big_line_dispatch(int n, float* base, size_t elem_stride) {
+  switch (n) {
+    case 32: big_line_pass<32>(base, elem_stride); break;
+    case 64: big_line_pass<64>(base, elem_stride); break;
+    case 128: big_line_pass<128>(base, elem_stride); break;
+    case 256: big_line_pass<256>(base, elem_stride); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev B) {
+  extern __shared__ float smem[];
+  __shared__ uint32_t s_next;
+  __shared__ uint32_t s_nbig;
+  __shared__ uint16_t s_big[64];
+  const uint32_t stream = blockIdx.x;
+  if (B.status[stream] != 0) return;
+  const StreamDev sd = B.streams[stream];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t gx = g % F.xg, gy = g / F.xg;
+  const uint32_t bx0 = gx * 32, by0 = gy * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
+  const int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  const uint8_t* tmap = B.blob + F.transform_off;
+  const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
+  const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
+  const int8_t* ytob = reinterpret_cast<const int8_t*>(B.blob + F.ytob_off);
+  const uint32_t* block_off = B.block_off + F.block_base;
+  float* planes[3] = {B.planes_a + F.plane_base, B.planes_a + F.plane_base + F.plane_size,
+                      B.planes_a + F.plane_base + 2 * F.plane_size};
+  const float* lfp[3] = {reinterpret_cast<const float*>(B.blob + F.lf_off[0]),
+                         reinterpret_cast<const float*>(B.blob + F.lf_off[1]),
+                         reinterpret_cast<const float*>(B.blob + F.lf_off[2])};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wbuf = smem + warp * 3 * kWarpBuf;
+  if (threadIdx.x == 0) {
+    s_next = 0;
+    s_nbig = 0;
+  }
+  __syncthreads();
+
+  auto setup = [&](uint32_t bx, uint32_t by, int t, DequantCtx& dq) {
+    const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+    const uint32_t off = block_off[bidx];
+    const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
+    dq.num_coeffs = cx * cy * 64;
+    dq.qx = group_coeffs + off;
+    dq.qy = group_coeffs + kGroupCoeffs + off;
+    dq.qb = group_coeffs + 2 * kGroupCoeffs + off;
+    int qt = c_qtable[t];
+    dq.mat = F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt])
+                                    : B.dequant_default + B.dequant_default_off[qt];
+    const size_t cidx = size_t((by0 + by) >> 3) * F.cxb + ((bx0 + bx) >> 3);
+    dq.x_cc = F.base_correlation_x + float(ytox[cidx]) / float(F.color_factor);
+    dq.b_cc = F.base_correlation_b + float(ytob[cidx]) / float(F.color_factor);
+    dq.sy = F.inv_global_scale / float(rq[bidx]);
+    dq.sx = dq.sy * F.x_dm;
+    dq.sb = dq.sy * F.b_dm;
+    dq.bias0 = F.quant_biases[0];
+    dq.bias1 = F.quant_biases[1];
+    dq.bias2 = F.quant_biases[2];
+    dq.bias3 = F.quant_biases[3];
+  };
+
+  // ---- warp path: each warp grabs the next block position of the group ----
+  for (;;) {
+    uint32_t pos = 0;
+    if (lane == 0) pos = atomicAdd(&s_next, 1u);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (pos >= gw * gh) break;
+    const uint32_t bx = pos % gw, by = pos / gw;
+    const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+    const uint32_t raw_t = tmap[bidx];
+    if (raw_t < 128) continue;
+    const int t = raw_t & 127;
+    const int cx = c_cov_x[t], cy = c_cov_y[t];
+    if (cx > 4 || cy > 4) {  // big varblock: handled cooperatively below
+      if (lane == 0) {
+        uint32_t i = atomicAdd(&s_nbig, 1u);
+        if (i < 64) s_big[i] = uint16_t(pos);
+      }
+      continue;
+    }
+    DequantCtx dq;
+    setup(bx, by, t, dq);
+    const int R = 8 * cy, C = 8 * cx;
+    const bool is_dct = (t == 0) || (t >= 4 && t <= 11);
+    float* ch0 = wbuf;
+    float* ch1 = wbuf + kWarpBuf;
+    float* ch2 = wbuf + 2 * kWarpBuf;
+    const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
+    if (is_dct) {
+      const int stride = C + 1;
+      const bool wide = R < C;
+      for (uint32_t k = lane; k < dq.num_coeffs; k += 32) {
+        float vx, vy, vb;
+        dq.get(k, vx, vy, vb);
+        int vf = wide ? int(k) / C : int(k) % R;
+        int hf = wide ? int(k) % C : int(k) / R;
+        ch0[vf * stride + hf] = vx;
+        ch1[vf * stride + hf] = vy;
+        ch2[vf * stride + hf] = vb;
+      }
+      __syncwarp();
+      if (lane < 3) {  // LLF (group.rs:227-236, transform.rs:387-...)
+        float* ch = wbuf + lane * kWarpBuf;
+        const float* lf = lfp[lane] + size_t(by0 + by) * F.xb + bx0 + bx;
+        if (cx == 1 && cy == 1) ch[0] = lf[0];
+        else llf_small(lf, F.xb, cy, cx, [&](int vf, int hf, float v) { ch[vf * stride + hf] = v; });
+      }
+      __syncwarp();
+      for (int r = lane; r < 3 * R; r += 32) {
+        float* ch = wbuf + (r / R) * kWarpBuf;
+        int row = r % R;
+        if (C == 8) warp_row_pass<8>(ch, row, stride);
+        else if (C == 16) warp_row_pass<16>(ch, row, stride);
+        else warp_row_pass<32>(ch, row, stride);
+      }
+      __syncwarp();
+      for (int r = lane; r < 3 * C; r += 32) {
+        float* ch = wbuf + (r / C) * kWarpBuf;
+        int col = r % C;
+        if (R == 8) warp_col_pass<8>(ch, col, stride);
+        else if (R == 16) warp_col_pass<16>(ch, col, stride);
+        else warp_col_pass<32>(ch, col, stride);
+      }
+      __syncwarp();
+      for (int c = 0; c < 3; c++) {
+        const float* ch = wbuf + c * kWarpBuf;
+        for (int i = lane; i < R * C; i += 32) {
+          int y = i / C, x = i % C;
+          planes[c][px0 + size_t(y) * F.plane_stride + x] = ch[y * stride + x];
+        }
+      }
+    } else {
+      // special transforms work on the storage layout (64 coefficients, stride 8)
+      for (uint32_t k = lane; k < 64; k += 32) {
+        float vx, vy, vb;
+        dq.get(k, vx, vy, vb);
+        ch0[k] = vx;
+        ch1[k] = vy;
+        ch2[k] = vb;
+      }
+      __syncwarp();
+      if (lane < 3) {
+        float* ch = wbuf + lane * kWarpBuf;
+        ch[0] = lfp[lane][size_t(by0 + by) * F.xb + bx0 + bx];
+        float co[64];
+        for (int i = 0; i < 64; i++) co[i] = ch[i];
+        special_transform(t, co, ch + 64);
+      }
+      __syncwarp();
+      for (int c = 0; c < 3; c++) {
+        const float* ch = wbuf + c * kWarpBuf + 64;
+        for (int i = lane; i < 64; i += 32) planes[c][px0 + size_t(i >> 3) * F.plane_stride + (i & 7)] = ch[i];
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- big varblocks (a dimension >= 64): CTA-cooperative, in place in HBM ----
+  const uint32_t nbig = min(s_nbig, 64u);
+  for (uint32_t bi = 0; bi < nbig; bi++) {
+    const uint32_t pos = s_big[bi];
+    const uint32_t bx = pos % gw, by = pos / gw;
+    const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+    const int t = tmap[bidx] & 127;
+    const int cx = c_cov_x[t], cy = c_cov_y[t];
+    const int R = 8 * cy, C = 8 * cx;
+    DequantCtx dq;
+    setup(bx, by, t, dq);
+    const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
+    const bool wide = R < C;
+    for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
+      float vx, vy, vb;
+      dq.get(k, vx, vy, vb);
+      int vf = wide ? int(k) / C : int(k) % R;
+      int hf = wide ? int(k) % C : int(k) / R;
+      size_t o = px0 + size_t(vf) * F.plane_stride + hf;
+      planes[0][o] = vx;
+      planes[1][o] = vy;
+      planes[2][o] = vb;
+    }
+    __syncthreads();
+    // LLF: rows then columns of the cy x cx LF samples, staged in shared memory.
+    float* llf = smem;  // 3 * 32 * 33
+    for (int r = threadIdx.x; r < 3 * cy; r += blockDim.x) {
+      int c = r / cy, y = r % cy;
+      float line[32];
+      const float* lf = lfp[c] + size_t(by0 + by + y) * F.xb + bx0 + bx;
+      for (int x = 0; x < cx; x++) line[x] = lf[x];
+      rdct1d_dyn(line, cx);
+      for (int x = 0; x < cx; x++) llf[c * kWarpBuf + y * 33 + x] = line[x];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < 3 * cx; r += blockDim.x) {
+      int c = r / cx, hf = r % cx;
+      float line[32];
+      for (int y = 0; y < cy; y++) line[y] = llf[c * kWarpBuf + y * 33 + hf];
+      rdct1d_dyn(line, cy);
+      for (int vf = 0; vf < cy; vf++) planes[c][px0 + size_t(vf) * F.plane_stride + hf] = line[vf];
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < 3 * R; r += blockDim.x)
+      big_line_dispatch(C, planes[r / R] + px0 + size_t(r % R) * F.plane_stride, 1);
+    __syncthreads();
+    for (int r = threadIdx.x; r < 3 * C; r += blockDim.x)
+      big_line_dispatch(R, planes[r / C] + px0 + (r % C), F.plane_stride);
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// K3-K5: loop filters and colour
+// ===========================================================================
+
+__device__ __forceinline__ int mirror(int v, int s) {  // util/mirror.rs:8
+  while (v < 0 || v >= s) v = v < 0 ? -v - 1 : 2 * s - v - 1;
+  return v;
+}
+
+struct TileDev {  // 32x8-pixel tiles over all frames of the batch
+  const uint32_t* tile_prefix;  // [num_frames + 1]
+  uint32_t num_frames;
+};
+
+__device__ __forceinline__ bool locate_tile(const BatchDev& B, const TileDev& T, uint32_t tile, uint32_t& f, int& x, int& y) {
+  uint32_t lo = 0, hi = T.num_frames;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (T.tile_prefix[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  f = lo;
+  const FrameDev& F = B.frames[f];
+  uint32_t local = tile - T.tile_prefix[f];
+  uint32_t tiles_x = (F.width + 31) / 32;
+  x = int((local % tiles_x) * 32 + threadIdx.x);
+  y = int((local / tiles_x) * 8 + threadIdx.y);
+  return x < int(F.width) && y < int(F.height);
+}
+
+// gaborish.rs:40-88
+__global__ void __launch_bounds__(256) k_gaborish(const BatchDev B, const TileDev T, const float* src, float* dst) {
+  uint32_t f;
+  int x, y;
+  if (!locate_tile(B, T, blockIdx.x, f, x, y)) return;
+  const FrameDev& F = B.frames[f];
+  const int w = int(F.width), h = int(F.height);
+  const int xl = mirror(x - 1, w), xr = mirror(x + 1, w), yt = mirror(y - 1, h), yb = mirror(y + 1, h);
+  const size_t st = F.plane_stride;
+  if (!F.gab) {  // frame without Gaborish inside a mixed batch: pass through
+#pragma unroll
+    for (int c = 0; c < 3; c++) dst[F.plane_base + c * F.plane_size + y * st + x] = src[F.plane_base + c * F.plane_size + y * st + x];
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float* p = src + F.plane_base + c * F.plane_size;
+    const float *t = p + yt * st, *m = p + y * st, *b = p + yb * st;
+    float sum = m[x] * F.gab_k0[c];
+    sum = fmaf(F.gab_k1[c], t[x] + m[xl] + b[x] + m[xr], sum);
+    sum = fmaf(F.gab_k2[c], t[xl] + t[xr] + b[xl] + b[xr], sum);
+    dst[F.plane_base + c * F.plane_size + y * st + x] = sum;
+  }
+}
+
+// features/epf.rs:54-79
+__device__ __forceinline__ float inv_sigma_at(const BatchDev& B, const FrameDev& F, int x, int y) {
+  const size_t bidx = size_t(y >> 3) * F.xb + (x >> 3);
+  const int32_t raw_quant = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off)[bidx];
+  const uint32_t sharp = (B.blob + F.epf_off)[bidx];
+  const float kInvSigmaNum = -1.1715728752538099024f;
+  float sigma_quant = F.epf_quant_mul / (F.quant_scale * float(raw_quant) * kInvSigmaNum);
+  float sigma = fminf(sigma_quant * F.epf_sharp_lut[sharp], -1e-4f);
+  return 1.0f / sigma;
+}
+
+// epf0.rs / epf1.rs / epf2.rs; STAGE selects the neighbourhood.
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_epf(const BatchDev B, const TileDev T, const float* src, float* dst) {
+  uint32_t f;
+  int x, y;
+  if (!locate_tile(B, T, blockIdx.x, f, x, y)) return;
+  const FrameDev& F = B.frames[f];
+  const bool enabled = STAGE == 0 ? F.epf_iters >= 3 : (STAGE == 1 ? F.epf_iters >= 1 : F.epf_iters >= 2);
+  const int w = int(F.width), h = int(F.height);
+  const size_t st = F.plane_stride;
+  const float* p[3] = {src + F.plane_base, src + F.plane_base + F.plane_size, src + F.plane_base + 2 * F.plane_size};
+  float* q[3] = {dst + F.plane_base, dst + F.plane_base + F.plane_size, dst + F.plane_base + 2 * F.plane_size};
+  auto at = [&](int c, int xx, int yy) { return p[c][size_t(mirror(yy, h)) * st + mirror(xx, w)]; };
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+  const float inv_sigma_px = inv_sigma_at(B, F, x, y);
+  const size_t o = size_t(y) * st + x;
+  if (!enabled || inv_sigma_px < kMinSigma) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) q[c][o] = p[c][o];
+    return;
+  }
+  const float sigma_scale = STAGE == 0 ? F.epf_pass0_sigma_scale : (STAGE == 1 ? 1.0f : F.epf_pass2_sigma_scale);
+  const float sm = sigma_scale * 1.65f, bsm = sm * F.epf_border_sad_mul;
+  const bool border = ((y & 7) == 0 || (y & 7) == 7) || ((x & 7) == 0 || (x & 7) == 7);
+  const float inv_s = inv_sigma_px * (border ? bsm : sm);
+  if (STAGE == 2) {
+    const int off[4][2] = {{0, -1}, {-1, 0}, {1, 0}, {0, 1}};
+    float cc[3] = {p[0][o], p[1][o], p[2][o]};
+    float wacc = 1.0f, acc[3] = {cc[0], cc[1], cc[2]};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float nb[3] = {at(0, x + off[k][0], y + off[k][1]), at(1, x + off[k][0], y + off[k][1]), at(2, x + off[k][0], y + off[k][1])};
+      float sad = fmaf(fabsf(nb[0] - cc[0]), F.epf_channel_scale[0],
+                       fmaf(fabsf(nb[1] - cc[1]), F.epf_channel_scale[1], fabsf(nb[2] - cc[2]) * F.epf_channel_scale[2]));
+      float wt = fmaxf(fmaf(sad, inv_s, 1.0f), 0.0f);
+      wacc += wt;
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[c] = fmaf(wt, nb[c], acc[c]);
+    }
+    float inv_w = 1.0f / wacc;
+#pragma unroll
+    for (int c = 0; c < 3; c++) q[c][o] = acc[c] * inv_w;
+    return;
+  }
+  constexpr int N = STAGE == 0 ? 12 : 4;
+  const int off0[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0}, {1, 0}, {2, 0}, {-1, 1}, {0, 1}, {1, 1}, {0, 2}};
+  const int off1[4][2] = {{0, -1}, {-1, 0}, {1, 0}, {0, 1}};
+  const int plus[5][2] = {{0, -1}, {-1, 0}, {0, 0}, {1, 0}, {0, 1}};
+  float sads[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) sads[k] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    // window of radius 3 (stage 0) / 2 (stage 1) around the pixel
+    constexpr int RAD = STAGE == 0 ? 3 : 2;
+    float win[2 * RAD + 1][2 * RAD + 1];
+#pragma unroll
+    for (int dy = -RAD; dy <= RAD; dy++)
+#pragma unroll
+      for (int dx = -RAD; dx <= RAD; dx++) {
+        if (abs(dx) + abs(dy) <= RAD) win[dy + RAD][dx + RAD] = at(c, x + dx, y + dy);
+      }
+    const float scale = F.epf_channel_scale[c];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const int ox = STAGE == 0 ? off0[k][0] : off1[k][0], oy = STAGE == 0 ? off0[k][1] : off1[k][1];
+      float s = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 5; j++)
+        s += fabsf(win[plus[j][1] + RAD][plus[j][0] + RAD] - win[plus[j][1] + oy + RAD][plus[j][0] + ox + RAD]);
+      sads[k] = fmaf(scale, s, sads[k]);
+    }
+  }
+  float wsum = 1.0f;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    sads[k] = fmaxf(fmaf(sads[k], inv_s, 1.0f), 0.0f);
+    wsum += sads[k];
+  }
+  const float inv_w = 1.0f / wsum;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float v = p[c][o];
+#pragma unroll
+    for (int k = N - 1; k >= 0; k--) {
+      const int ox = STAGE == 0 ? off0[k][0] : off1[k][0], oy = STAGE == 0 ? off0[k][1] : off1[k][1];
+      v = fmaf(at(c, x + ox, y + oy), sads[k], v);
+    }
+    q[c][o] = v * inv_w;
+  }
+}
+
+// color/tf.rs:13-44
+__device__ __forceinline__ float linear_to_srgb(float v) {
+  const float P[5] = {-5.135152395e-4f, 5.287254571e-3f, 3.903842876e-1f, 1.474205315f, 7.352629620e-1f};
+  const float Q[5] = {1.004519624e-2f, 3.036675394e-1f, 1.340816930f, 9.258482155e-1f, 2.424867759e-2f};
+  float a = fabsf(v), r;
+  if (a < 0.0031308f) {
+    r = a * 12.92f;
+  } else {
+    float s = sqrtf(a);
+    float yp = P[4], yq = Q[4];
+#pragma unroll
+    for (int i = 3; i >= 0; i--) {
+      yp = fmaf(yp, s, P[i]);
+      yq = fmaf(yq, s, Q[i]);
+    }
+    r = yp / yq;
+  }
+  return copysignf(r, v);
+}
+
+// xyb.rs:197-241 + from_linear + convert.rs:574-598 + save (interleave)
+__global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileDev T, const float* src) {
+  uint32_t f;
+  int x, y;
+  if (!locate_tile(B, T, blockIdx.x, f, x, y)) return;
+  const FrameDev& F = B.frames[f];
+  const size_t o = size_t(y) * F.plane_stride + x;
+  float vx = src[F.plane_base + o], vy = src[F.plane_base + F.plane_size + o], vb = src[F.plane_base + 2 * F.plane_size + o];
+  uint8_t* row = static_cast<uint8_t*>(F.out_ptr) + size_t(y) * F.out_row_stride;
+  if (F.output_format == JXG_FORMAT_XYB_F32_PLANAR) {
+    uint8_t* base = static_cast<uint8_t*>(F.out_ptr);
+    reinterpret_cast<float*>(base + (size_t(0) * F.height + y) * F.out_row_stride)[x] = vx;
+    reinterpret_cast<float*>(base + (size_t(1) * F.height + y) * F.out_row_stride)[x] = vy;
+    reinterpret_cast<float*>(base + (size_t(2) * F.height + y) * F.out_row_stride)[x] = vb;
+    return;
+  }
+  float l = vy + vx - F.bias_cbrt[0], m = vy - vx - F.bias_cbrt[1], s = vb - F.bias_cbrt[2];
+  float l2 = l * l, m2 = m * m, s2 = s * s;
+  float sl = l * F.intensity_scale, sm = m * F.intensity_scale, ss = s * F.intensity_scale;
+  l = fmaf(l2, sl, F.scaled_bias[0]);
+  m = fmaf(m2, sm, F.scaled_bias[1]);
+  s = fmaf(s2, ss, F.scaled_bias[2]);
+  float v[3];
+  v[0] = fmaf(F.opsin[0], l, fmaf(F.opsin[1], m, F.opsin[2] * s));
+  v[1] = fmaf(F.opsin[3], l, fmaf(F.opsin[4], m, F.opsin[5] * s));
+  v[2] = fmaf(F.opsin[6], l, fmaf(F.opsin[7], m, F.opsin[8] * s));
+  if (F.output_tf == JXG_TF_SRGB) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = linear_to_srgb(v[c]);
+  }
+  if (F.output_format == JXG_FORMAT_RGB_F32) {
+    float* dst = reinterpret_cast<float*>(row) + size_t(x) * 3;
+    dst[0] = v[0];
+    dst[1] = v[1];
+    dst[2] = v[2];
+    return;
+  }
+  uint8_t px[4];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    float d = c_dither[((y + 13 * c) & 31) * 32 + ((x + 23 * c) & 31)];
+    float sc = fminf(fmaxf(v[c] * 255.0f + d, 0.0f), 255.0f);
+    px[c] = uint8_t(__float2int_rn(sc));  // round-to-nearest-even, as the AVX store (jxl_simd avx.rs:609)
+  }
+  if (F.output_format == JXG_FORMAT_RGBA_U8) {
+    px[3] = 255;
+    reinterpret_cast<uchar4*>(row)[x] = make_uchar4(px[0], px[1], px[2], px[3]);
+  } else {
+    row[x * 3 + 0] = px[0];
+    row[x * 3 + 1] = px[1];
+    row[x * 3 + 2] = px[2];
+  }
+}
+
+// ===========================================================================
+// host-callable launch wrappers (used by batch.cc through launch.h)
+// ===========================================================================
+
+}  // namespace jxgpu
+
+#include "launch.h"
+
+namespace jxgpu {
+
+cudaError_t upload_constants(const float* wc, const float* rdct_scale) {
+  cudaError_t e = cudaMemcpyToSymbol(c_wc, wc, sizeof(float) * 9 * 128);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_rdct_scale, rdct_scale, sizeof(float) * 6 * 32);
+}
+
+cudaError_t configure_kernels() {
+  return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(kIdctWarps * 3 * kWarpBuf * sizeof(float)));
+}
+
+int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
+                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop) {
+  int launches = 0;
+  cudaMemsetAsync(B.coeffs, 0, coeff_bytes, stream);
+  k_entropy<<<(B.num_streams + kEntropyWarps - 1) / kEntropyWarps, kEntropyWarps * 32, 0, stream>>>(B);
+  launches++;
+  if (final_planes) *final_planes = B.planes_a;
+  if (debug_stop == 1) return launches;
+  k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
+  launches++;
+  if (debug_stop == 2) return launches;
+  TileDev T{tile_prefix, B.num_frames};
+  dim3 blk(32, 8);
+  const float* cur = B.planes_a;
+  float* nxt = B.planes_b;
+  auto swap = [&] {
+    const float* t = cur;
+    cur = nxt;
+    nxt = const_cast<float*>(t);
+  };
+  // NOTE: all frames of a batch share the filter configuration checked by the
+  // host (batch.cc splits batches otherwise).
+  if (any_gab) {
+    k_gaborish<<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
+    launches++;
+    swap();
+  }
+  if (max_epf_iters >= 3) {
+    k_epf<0><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
+    launches++;
+    swap();
+  }
+  if (max_epf_iters >= 1) {
+    k_epf<1><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
+    launches++;
+    swap();
+  }
+  if (max_epf_iters >= 2) {
+    k_epf<2><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
+    launches++;
+    swap();
+  }
+  k_xyb_store<<<total_tiles, blk, 0, stream>>>(B, T, cur);
+  launches++;
+  if (final_planes) *final_planes = cur;
+  return launches;
+}
+
+}  // namespace jxgpu

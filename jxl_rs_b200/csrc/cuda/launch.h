@@ -1,0 +1,13 @@
+// Host-side entry points into kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace jxgpu {
+cudaError_t upload_constants(const float* wc, const float* rdct_scale);
+cudaError_t configure_kernels();
+// Enqueues the whole K1..K5 pipeline on `stream`; returns the number of kernel launches.
+int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
+                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop);
+}  // namespace jxgpu

@@ -1,0 +1,167 @@
+"""Host-side mirror of the jxl-rs decoder API for the VarDCT hot path.
+
+Reference shape (jxl/src/api/decoder.rs:33-266, data_types.rs:154, image/output_buffer.rs:26):
+    JxlDecoder::process(input, buffers, runner)  ->  pixels in JxlOutputBuffer
+Here a *batch* of frames is decoded per call (one crossing of the host/device
+boundary per batch). PyTorch supplies device memory, pinned host
+memory and streams only; all compute is in libjxgpu.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+
+
+@dataclass
+class JxlPixelFormat:
+    """jxl/src/api/data_types.rs:154 (colour part only)."""
+    color_type: str = "RGB"          # "RGB" | "RGBA"
+    data_format: str = "U8"          # "U8" | "F32"
+
+    def abi_format(self):
+        if self.data_format == "U8":
+            return abi.FORMAT_RGBA_U8 if self.color_type == "RGBA" else abi.FORMAT_RGB_U8
+        if self.data_format == "F32" and self.color_type == "RGB":
+            return abi.FORMAT_RGB_F32
+        raise ValueError(f"unsupported pixel format {self}")
+
+
+class ParsedFrame:
+    """A .jxl file run through the host front-end (headers, TOC, LfGlobal, LF
+    groups, HfGlobal): what a Rust host has in `Frame` when it reaches
+    decode_and_render_hf_groups (frame/render.rs:143)."""
+
+    def __init__(self, data: bytes):
+        self._lib = abi.load_library()
+        self._h = C.c_void_p()
+        self.info = abi.JxgImageInfo()
+        abi.check(self._lib, self._lib.jxg_parse_file(data, len(data), C.byref(self._h), C.byref(self.info)))
+
+    @property
+    def width(self):
+        return self.info.width
+
+    @property
+    def height(self):
+        return self.info.height
+
+    def desc(self, output_format):
+        d = abi.JxgFrameDesc()
+        hf, off, ln, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        abi.check(self._lib, self._lib.jxg_parsed_desc(self._h, output_format, C.byref(d), C.byref(hf), C.byref(off),
+                                                       C.byref(ln), C.byref(n)))
+        return d, hf, off, ln, n.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.jxg_parsed_free(self._h)
+            self._h = C.c_void_p()
+
+
+class JxgContext:
+    """One per GPU / rank (jxg_init)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = abi.load_library()
+        self._h = C.c_void_p()
+        abi.check(self._lib, self._lib.jxg_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h.value:
+            self._lib.jxg_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """jxg_batch_*: frames decoded together by one kernel pipeline."""
+
+    def __init__(self, ctx: JxgContext, n_hint: int = 0):
+        self._lib = ctx._lib
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        abi.check(self._lib, self._lib.jxg_batch_begin(ctx._h, n_hint, C.byref(self._h)))
+        self._keep = []
+        self.frames = []
+
+    def add(self, frame: ParsedFrame, out_ptr: int, row_stride: int, fmt: int, out_is_device: bool):
+        abi.check(self._lib, self._lib.jxg_batch_add_parsed(self._h, frame._h, fmt, C.c_void_p(out_ptr), row_stride,
+                                                            1 if out_is_device else 0))
+        self.frames.append(frame)
+
+    def add_desc(self, desc, hf, off, ln, n, out_ptr, row_stride, out_is_device):
+        abi.check(self._lib, self._lib.jxg_batch_add_frame(self._h, C.byref(desc), hf, off, ln, n, C.c_void_p(out_ptr),
+                                                           row_stride, 1 if out_is_device else 0))
+
+    def set_debug_stop(self, stage: int):
+        self._lib.jxg_batch_set_debug_stop(self._h, stage)
+
+    def run(self, stream_ptr: int = 0):
+        abi.check(self._lib, self._lib.jxg_batch_run(self._h, C.c_void_p(stream_ptr)))
+
+    def rerun_device(self, stream_ptr: int = 0):
+        abi.check(self._lib, self._lib.jxg_batch_rerun_device(self._h, C.c_void_p(stream_ptr)))
+
+    def wait(self):
+        f, g = C.c_uint32(), C.c_uint32()
+        abi.check(self._lib, self._lib.jxg_batch_wait(self._h, C.byref(f), C.byref(g)))
+
+    def stats(self):
+        k, h, d, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        self._lib.jxg_batch_stats(self._h, C.byref(k), C.byref(h), C.byref(d), C.byref(ms))
+        return {"kernel_launches": k.value, "h2d_bytes": h.value, "d2h_bytes": d.value, "device_ms": ms.value}
+
+    def read_coeffs(self, f: int):
+        n = self.frames[f].info.num_groups * 3 * 65536
+        out = np.empty(n, np.int32)
+        abi.check(self._lib, self._lib.jxg_batch_read_coeffs(self._h, f, out.ctypes.data_as(C.c_void_p), n))
+        return out.reshape(self.frames[f].info.num_groups, 3, 65536)
+
+    def read_xyb(self, f: int, stage: int):
+        w, h = self.frames[f].width, self.frames[f].height
+        ps, pr = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        out = np.empty(3 * ps * pr, np.float32)
+        abi.check(self._lib, self._lib.jxg_batch_read_xyb(self._h, f, stage, out.ctypes.data_as(C.c_void_p), out.size))
+        return out.reshape(3, pr, ps)
+
+    def close(self):
+        if self._h.value:
+            self._lib.jxg_batch_end(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixelFormat(), to_host: bool = True):
+    """Decodes a list of .jxl byte strings; returns a list of torch tensors
+    (H x W x C). Host results land in pinned memory (JxlOutputBuffer analogue)."""
+    import torch
+    fmt = pixel_format.abi_format()
+    frames = [ParsedFrame(f) for f in files]
+    batch = Batch(ctx, len(frames))
+    outs = []
+    for fr in frames:
+        ch = 4 if fmt == abi.FORMAT_RGBA_U8 else 3
+        dt = torch.float32 if fmt == abi.FORMAT_RGB_F32 else torch.uint8
+        if to_host:
+            t = torch.empty((fr.height, fr.width, ch), dtype=dt).pin_memory()
+        else:
+            t = torch.empty((fr.height, fr.width, ch), dtype=dt, device=f"cuda:{ctx.device}")
+        outs.append(t)
+        batch.add(fr, t.data_ptr(), fr.width * ch * t.element_size(), fmt, not to_host)
+    batch.run()
+    batch.wait()
+    batch.close()
+    return outs

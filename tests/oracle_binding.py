@@ -1,0 +1,76 @@
+"""ctypes binding of oracle/liboracle.so — the CPU checker (test infrastructure).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jxl_rs_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+class JxoTaps(C.Structure):
+    _fields_ = [("coeffs", C.c_void_p), ("xyb_idct", C.c_void_p), ("xyb_filtered", C.c_void_p)]
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(path)
+    lib.jxo_last_error.restype = C.c_char_p
+    lib.jxo_decode_file.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(JxoTaps), C.c_int]
+    lib.jxo_file_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(abi.JxgImageInfo)]
+    lib.jxo_decode_frame.argtypes = [C.POINTER(abi.JxgFrameDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                     C.c_void_p, C.c_size_t, C.POINTER(JxoTaps), C.c_int, C.POINTER(C.c_uint32)]
+    lib.jxo_idct2d.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.jxo_reinterpreting_dct2d.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.jxo_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    lib.jxo_gaborish.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+    lib.jxo_xyb_to_linear.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+    lib.jxo_linear_to_srgb.argtypes = [C.c_int, C.c_void_p]
+    _LIB = lib
+    return lib
+
+
+def file_info(data: bytes):
+    lib = load()
+    info = abi.JxgImageInfo()
+    r = lib.jxo_file_info(data, len(data), C.byref(info))
+    if r != 0:
+        raise abi.JxgError(r, lib.jxo_last_error().decode())
+    return info
+
+
+def decode_file(data: bytes, fmt=abi.FORMAT_RGB_U8, taps=False, threads=0):
+    """Returns (pixels, taps dict). pixels: HxWx3 u8 / HxWx4 u8 / HxWx3 f32."""
+    lib = load()
+    info = file_info(data)
+    w, h = info.width, info.height
+    if fmt == abi.FORMAT_RGB_F32:
+        out = np.zeros((h, w, 3), np.float32)
+    elif fmt == abi.FORMAT_RGBA_U8:
+        out = np.zeros((h, w, 4), np.uint8)
+    elif fmt == abi.FORMAT_XYB_F32_PLANAR:
+        out = np.zeros((3, h, w), np.float32)
+    else:
+        out = np.zeros((h, w, 3), np.uint8)
+    stride = out.strides[0] if fmt != abi.FORMAT_XYB_F32_PLANAR else out.strides[1]
+    t = None
+    tap_arrays = {}
+    if taps:
+        ps, pr = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        tap_arrays["coeffs"] = np.zeros((info.num_groups, 3, 65536), np.int32)
+        tap_arrays["xyb_idct"] = np.zeros((3, pr, ps), np.float32)
+        tap_arrays["xyb_filtered"] = np.zeros((3, h, w), np.float32)
+        t = JxoTaps(tap_arrays["coeffs"].ctypes.data, tap_arrays["xyb_idct"].ctypes.data, tap_arrays["xyb_filtered"].ctypes.data)
+    r = lib.jxo_decode_file(data, len(data), fmt, out.ctypes.data, stride, C.byref(t) if t else None, threads)
+    if r != 0:
+        raise abi.JxgError(r, lib.jxo_last_error().decode())
+    return out, tap_arrays
