@@ -166,6 +166,11 @@ int jxg_batch_read_xyb(void* batch, uint32_t f, int stage, float* out, size_t ou
  * 2 = stop after dequant+IDCT (planes readable with stage 0). */
 int jxg_batch_set_debug_stop(void* batch, int stage);
 
+/* Per-stage device timing with CUDA events on the launching stream (bench.py roofline):
+ * stages = memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store. */
+int jxg_batch_set_profile(void* batch, int on);
+int jxg_batch_stage_times(void* batch, float* ms, int n);
+
 /* Counters for bench.py (kernels launched by the last run, bytes moved). */
 int jxg_batch_stats(void* batch, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes,
                     float* last_device_ms);

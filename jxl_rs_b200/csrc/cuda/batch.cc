@@ -88,6 +88,13 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   DevBuf dequant_default, dequant_default_off, natural_orders, natural_order_off;
+  // Pools reused by successive batches (one live batch per context): device
+  // intermediates and the pinned staging arena survive jxg_batch_end so that a
+  // steady-state decode loop does no cudaMalloc / cudaHostAlloc.
+  PinnedArena blob;
+  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_coeffs, d_block_off, d_nz, d_planes_a,
+      d_planes_b, d_status, d_out;
+  bool batch_live = false;
 };
 
 struct FrameOut {
@@ -99,7 +106,11 @@ struct FrameOut {
 
 struct Batch {
   Context* ctx;
-  PinnedArena blob;
+  PinnedArena& blob;
+  explicit Batch(Context* c)
+      : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams),
+        d_nz_base(c->d_nz_base), d_tiles(c->d_tiles), d_coeffs(c->d_coeffs), d_block_off(c->d_block_off), d_nz(c->d_nz),
+        d_planes_a(c->d_planes_a), d_planes_b(c->d_planes_b), d_status(c->d_status), d_out(c->d_out) {}
   std::vector<FrameDev> frames;
   std::vector<SectionDev> sections;
   std::vector<StreamDev> streams;
@@ -111,12 +122,14 @@ struct Batch {
   bool any_gab = false;
   int debug_stop = 0;
   // device
-  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_coeffs, d_block_off, d_nz, d_planes_a,
-      d_planes_b, d_status, d_out;
+  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_nz_base, &d_tiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
+      &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
   std::vector<int32_t> status_host;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool profile = false;
+  cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
   uint64_t launches = 0, h2d = 0, d2h = 0;
   float last_ms = 0;
 };
@@ -193,9 +206,12 @@ void jxg_shutdown(void* c) {
 
 int jxg_batch_begin(void* c, uint32_t n_frames_hint, void** out_batch) {
   if (!c || !out_batch) return JXG_ERR_ARGUMENT;
-  auto b = std::make_unique<Batch>();
-  b->ctx = static_cast<Context*>(c);
+  Context* cx = static_cast<Context*>(c);
+  if (cx->batch_live) return set_error(JXG_ERR_ARGUMENT, "one live batch per context: call jxg_batch_end first");
+  auto b = std::make_unique<Batch>(cx);
   CUDA_TRY(cudaSetDevice(b->ctx->device));
+  cx->blob.size = 0;
+  cx->batch_live = true;
   b->frames.reserve(n_frames_hint);
   CUDA_TRY(cudaEventCreate(&b->ev0));
   CUDA_TRY(cudaEventCreate(&b->ev1));
@@ -210,7 +226,32 @@ void jxg_batch_end(void* bp) {
   cudaStreamSynchronize(b->ctx->stream);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  for (auto& e : b->stage_ev)
+    if (e) cudaEventDestroy(e);
+  b->ctx->batch_live = false;
   delete b;
+}
+
+int jxg_batch_set_profile(void* bp, int on) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b) return JXG_ERR_ARGUMENT;
+  if (on && !b->stage_ev[0])
+    for (auto& e : b->stage_ev) CUDA_TRY(cudaEventCreate(&e));
+  b->profile = on != 0;
+  return JXG_OK;
+}
+
+// ms per stage of the last run (memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store); 0 if skipped.
+int jxg_batch_stage_times(void* bp, float* ms, int n) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || !ms || n < kNumStages || !b->profile) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  for (int i = 0; i < kNumStages; i++) {
+    ms[i] = 0.0f;
+    if (cudaEventElapsedTime(&ms[i], b->stage_ev[i], b->stage_ev[i + 1]) != cudaSuccess) ms[i] = 0.0f;
+  }
+  cudaGetLastError();
+  return JXG_OK;
 }
 
 int jxg_batch_set_debug_stop(void* bp, int stage) {
@@ -391,7 +432,8 @@ static int launch(Batch* b, cudaStream_t s) {
   B.natural_order_off = static_cast<const uint32_t*>(b->ctx->natural_order_off.p);
   size_t coeff_bytes = size_t(b->total_groups) * 3 * kGroupCoeffs * 4;
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
-                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop));
+                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop,
+                                         b->profile ? b->stage_ev : nullptr));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -1129,15 +1129,25 @@ cudaError_t configure_kernels() {
 }
 
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
-                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop) {
+                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
+                    cudaEvent_t* ev) {
+  // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
+  // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
+  auto mark = [&](int i) {
+    if (ev) cudaEventRecord(ev[i], stream);
+  };
+  mark(0);
   cudaMemsetAsync(B.coeffs, 0, coeff_bytes, stream);
+  mark(1);
   k_entropy<<<(B.num_streams + kEntropyWarps - 1) / kEntropyWarps, kEntropyWarps * 32, 0, stream>>>(B);
   launches++;
+  mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
   k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
   launches++;
+  mark(3);
   if (debug_stop == 2) return launches;
   TileDev T{tile_prefix, B.num_frames};
   dim3 blk(32, 8);
@@ -1148,30 +1158,33 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
     cur = nxt;
     nxt = const_cast<float*>(t);
   };
-  // NOTE: all frames of a batch share the filter configuration checked by the
-  // host (batch.cc splits batches otherwise).
   if (any_gab) {
     k_gaborish<<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
     launches++;
     swap();
   }
+  mark(4);
   if (max_epf_iters >= 3) {
     k_epf<0><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
     launches++;
     swap();
   }
+  mark(5);
   if (max_epf_iters >= 1) {
     k_epf<1><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
     launches++;
     swap();
   }
+  mark(6);
   if (max_epf_iters >= 2) {
     k_epf<2><<<total_tiles, blk, 0, stream>>>(B, T, cur, nxt);
     launches++;
     swap();
   }
+  mark(7);
   k_xyb_store<<<total_tiles, blk, 0, stream>>>(B, T, cur);
   launches++;
+  mark(8);
   if (final_planes) *final_planes = cur;
   return launches;
 }

@@ -9,5 +9,7 @@ cudaError_t upload_constants(const float* wc, const float* rdct_scale);
 cudaError_t configure_kernels();
 // Enqueues the whole K1..K5 pipeline on `stream`; returns the number of kernel launches.
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
-                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop);
+                    bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
+                    cudaEvent_t* ev);
+constexpr int kNumStages = 8;  // memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store
 }  // namespace jxgpu

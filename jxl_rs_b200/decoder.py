@@ -104,6 +104,16 @@ class Batch:
     def set_debug_stop(self, stage: int):
         self._lib.jxg_batch_set_debug_stop(self._h, stage)
 
+    STAGES = ["memset", "entropy", "dequant_idct", "gaborish", "epf0", "epf1", "epf2", "xyb_store"]
+
+    def set_profile(self, on: bool):
+        abi.check(self._lib, self._lib.jxg_batch_set_profile(self._h, 1 if on else 0))
+
+    def stage_times(self):
+        ms = (C.c_float * 8)()
+        abi.check(self._lib, self._lib.jxg_batch_stage_times(self._h, ms, 8))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
     def run(self, stream_ptr: int = 0):
         abi.check(self._lib, self._lib.jxg_batch_run(self._h, C.c_void_p(stream_ptr)))
 

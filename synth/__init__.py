@@ -1,0 +1,36 @@
+"""Synthetic VarDCT .jxl generator (ctypes binding of synth/libjxlsynth.so). Test-data tooling."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libjxlsynth.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", _HERE])
+        _LIB = C.CDLL(path)
+        _LIB.jxs_encode_synthetic.restype = C.c_int64
+        _LIB.jxs_encode_synthetic.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_float, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_void_p, C.c_size_t]
+        _LIB.jxs_last_error.restype = C.c_char_p
+    return _LIB
+
+
+def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, profile=1) -> bytes:
+    """One synthetic VarDCT frame. profile 0: DCT8x8 only; 1: mixed transforms up to 32x32;
+    2: also 64x64 / 64x32 / 32x64."""
+    lib = _lib()
+    cap = max(1 << 16, width * height * 2)
+    buf = C.create_string_buffer(cap)
+    n = lib.jxs_encode_synthetic(width, height, seed, distance, epf_iters, gab, profile, buf, cap)
+    if n < 0:
+        raise RuntimeError("synthetic encode failed: " + lib.jxs_last_error().decode())
+    if n > cap:
+        buf = C.create_string_buffer(n)
+        n = lib.jxs_encode_synthetic(width, height, seed, distance, epf_iters, gab, profile, buf, n)
+    return buf.raw[:n]
