@@ -92,7 +92,7 @@ struct Context {
   // intermediates and the pinned staging arena survive jxg_batch_end so that a
   // steady-state decode loop does no cudaMalloc / cudaHostAlloc.
   PinnedArena blob;
-  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_coeffs, d_block_off, d_nz, d_planes_a,
+  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
       d_planes_b, d_status, d_out;
   bool batch_live = false;
 };
@@ -109,20 +109,22 @@ struct Batch {
   PinnedArena& blob;
   explicit Batch(Context* c)
       : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams),
-        d_nz_base(c->d_nz_base), d_tiles(c->d_tiles), d_coeffs(c->d_coeffs), d_block_off(c->d_block_off), d_nz(c->d_nz),
+        d_nz_base(c->d_nz_base), d_tiles(c->d_tiles), d_ftiles(c->d_ftiles), d_coeffs(c->d_coeffs), d_block_off(c->d_block_off), d_nz(c->d_nz),
         d_planes_a(c->d_planes_a), d_planes_b(c->d_planes_b), d_status(c->d_status), d_out(c->d_out) {}
   std::vector<FrameDev> frames;
   std::vector<SectionDev> sections;
   std::vector<StreamDev> streams;
   std::vector<uint64_t> nz_base;
   std::vector<uint32_t> tile_prefix{0};
+  std::vector<uint32_t> fused_prefix{0};
   std::vector<FrameOut> outs;
   uint64_t total_groups = 0, total_blocks = 0, total_plane_floats = 0, nz_bytes = 0, out_bytes = 0;
   uint32_t max_epf = 0;
+  uint32_t filter_cfg_mask = 0;  // bit (gab * 4 + min(epf_iters, 3))
   bool any_gab = false;
   int debug_stop = 0;
   // device
-  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_nz_base, &d_tiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
+  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
@@ -404,8 +406,10 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   F.output_format = d->output_format;
   b->max_epf = std::max(b->max_epf, d->epf_iters);
   b->any_gab = b->any_gab || d->gab;
+  b->filter_cfg_mask |= 1u << ((d->gab ? 4 : 0) + std::min<uint32_t>(d->epf_iters, 3));
   uint32_t tiles = ((F.width + 31) / 32) * ((F.height + 7) / 8);
   b->tile_prefix.push_back(b->tile_prefix.back() + tiles);
+  b->fused_prefix.push_back(b->fused_prefix.back() + ((F.width + kFusedTileW - 1) / kFusedTileW) * ((F.height + kFusedTileH - 1) / kFusedTileH));
   b->frames.push_back(F);
   return JXG_OK;
 }
@@ -433,7 +437,8 @@ static int launch(Batch* b, cudaStream_t s) {
   size_t coeff_bytes = size_t(b->total_groups) * 3 * kGroupCoeffs * 4;
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop,
-                                         b->profile ? b->stage_ev : nullptr));
+                                         b->profile ? b->stage_ev : nullptr, static_cast<const uint32_t*>(b->d_ftiles.p),
+                                         b->fused_prefix.back(), b->filter_cfg_mask));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -475,6 +480,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = upload(b->d_streams, b->streams, s, &b->h2d)) return r;
   if (int r = upload(b->d_nz_base, b->nz_base, s, &b->h2d)) return r;
   if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
+  if (int r = upload(b->d_ftiles, b->fused_prefix, s, &b->h2d)) return r;
   b->uploaded = true;
   if (int r = launch(b, s)) return r;
   if (int r = copy_out(b, s)) return r;

@@ -1108,6 +1108,318 @@ __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileD
 }
 
 // ===========================================================================
+// K3+K4+K5 fused: Gaborish -> EPF0 -> EPF1 -> EPF2 -> XYB -> sRGB -> store, one
+// shared-memory tile per CTA, templated on the frame's filter configuration.
+//
+// * Every window cell holds the value of its *mirrored* image pixel, and every
+//   stage evaluates out-of-image cells at the mirrored coordinate, so halo
+//   cells hold exactly what the reference's mirror-padded rows hold
+//   (render/simple_pipeline/run_stage.rs:127-134) and stages chain in the tile.
+// * EPF sums of absolute differences are built from channel-combined difference
+//   maps D_o(c) = sum_ch scale_ch * |I_ch(c) - I_ch(c + o)| shared by all pixels
+//   (epf0.rs:157-168 / epf1.rs:98-101 evaluate the same sums per pixel).
+// * HBM traffic: one read of the IDCT planes (+ halo) and one write of the output.
+// ===========================================================================
+constexpr int kTW = 64, kTH = 32;
+
+struct FusedTiles {
+  const uint32_t* tile_prefix;  // [num_frames + 1], kTW x kTH tiles
+  uint32_t num_frames;
+};
+
+template <bool GAB, int EPF>
+struct FCfg {
+  static constexpr int H = (GAB ? 1 : 0) + (EPF >= 3 ? 3 : 0) + (EPF >= 1 ? 2 : 0) + (EPF >= 2 ? 1 : 0);
+  static constexpr int WW = kTW + 2 * H, WH = kTH + 2 * H, NC = WW * WH;
+  static constexpr int NMAPS = EPF >= 3 ? 6 : (EPF >= 1 ? 2 : 0);
+  static constexpr int SBW = WW / 8 + 2, SBH = WH / 8 + 2;  // sigma blocks covering the window
+  static constexpr size_t kSmemBytes = sizeof(float) * (size_t(6 + NMAPS) * NC + SBW * SBH);
+};
+
+// One EPF stage. src/dst: [3][NC]; maps: [NMAPS][NC]; m = margin of the output region.
+template <int STAGE, int WW, int WH, int H, int SBW>
+__device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, float* dst, float* maps, const float* sig,
+                                          int wx0, int wy0, int sbx0, int sby0, int m) {
+  constexpr int NC = WW * WH;
+  const int w = int(F.width), h = int(F.height);
+  const float s0 = F.epf_channel_scale[0], s1 = F.epf_channel_scale[1], s2 = F.epf_channel_scale[2];
+  constexpr int B = STAGE == 0 ? 3 : (STAGE == 1 ? 2 : 1);  // border of this stage
+  const int mp = m - B;                                       // margin of valid source cells
+  // ---- phase A: difference maps over the source-valid area ----
+  {
+    constexpr int NO = STAGE == 0 ? 6 : 2;
+    const int ox[6] = {1, 0, 2, 0, 1, 1}, oy[6] = {0, 1, 0, 2, 1, -1};  // A=(1,0) C=(0,1) B=(2,0) D=(0,2) E=(1,1) F=(1,-1)
+    const int aw = WW - 2 * mp, ah = WH - 2 * mp;
+    for (int idx = threadIdx.x; idx < aw * ah; idx += blockDim.x) {
+      const int lx = mp + idx % aw, ly = mp + idx / aw;
+      const int o = ly * WW + lx;
+      const float c0 = src[o], c1 = src[NC + o], c2 = src[2 * NC + o];
+#pragma unroll
+      for (int k = 0; k < NO; k++) {
+        const int nx = lx + ox[k], ny = ly + oy[k];
+        if (nx >= WW - mp || ny >= WH - mp || ny < mp) continue;
+        const int on = ny * WW + nx;
+        maps[k * NC + o] = fmaf(fabsf(src[on] - c0), s0, fmaf(fabsf(src[NC + on] - c1), s1, fabsf(src[2 * NC + on] - c2) * s2));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B ----
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+  const float sigma_scale = STAGE == 0 ? F.epf_pass0_sigma_scale : (STAGE == 1 ? 1.0f : F.epf_pass2_sigma_scale);
+  const float sm = sigma_scale * 1.65f, bsm = sm * F.epf_border_sad_mul;
+  constexpr int rw = WW - 2 * (H - (H - 0)) ;  // placeholder to keep constexpr math simple (unused)
+  (void)rw;
+  const int r = H - m;  // halo still needed after this stage
+  const int bw_ = kTW + 2 * r, bh_ = kTH + 2 * r;
+  const float* Dh = maps;            // (1,0)
+  const float* Dv = maps + NC;       // (0,1)
+  for (int idx = threadIdx.x; idx < bw_ * bh_; idx += blockDim.x) {
+    const int lx = m + idx % bw_, ly = m + idx / bw_;
+    const int gx = wx0 + lx, gy = wy0 + ly;
+    if (gx < -r || gx > w - 1 + r || gy < -r || gy > h - 1 + r) continue;  // never needed by a valid output
+    const int mx = mirror(gx, w), my = mirror(gy, h);
+    const int cx = mx - wx0, cy = my - wy0;
+    const int o = cy * WW + cx, od = ly * WW + lx;
+    const float inv_sigma_px = sig[((my >> 3) - sby0) * SBW + ((mx >> 3) - sbx0)];
+    if (inv_sigma_px < kMinSigma) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) dst[c * NC + od] = src[c * NC + o];
+      continue;
+    }
+    const bool border = ((my & 7) == 0 || (my & 7) == 7) || ((mx & 7) == 0 || (mx & 7) == 7);
+    const float inv_s = inv_sigma_px * (border ? bsm : sm);
+    if (STAGE == 2) {
+      // neighbours in the reference's order: up, left, right, down (epf2.rs:83)
+      const float sad[4] = {Dv[o - WW], Dh[o - 1], Dh[o], Dv[o]};
+      const int offs[4] = {-WW, -1, 1, WW};
+      float wacc = 1.0f, acc[3] = {src[o], src[NC + o], src[2 * NC + o]};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float wt = fmaxf(fmaf(sad[k], inv_s, 1.0f), 0.0f);
+        wacc += wt;
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc[c] = fmaf(wt, src[c * NC + o + offs[k]], acc[c]);
+      }
+      float inv_w = 1.0f / wacc;
+#pragma unroll
+      for (int c = 0; c < 3; c++) dst[c * NC + od] = acc[c] * inv_w;
+      continue;
+    }
+    auto plus_sum = [&](const float* M, int base) {
+      return M[base - WW] + M[base - 1] + M[base] + M[base + 1] + M[base + WW];
+    };
+    if (STAGE == 1) {
+      const float sad[4] = {plus_sum(Dv, o - WW), plus_sum(Dh, o - 1), plus_sum(Dh, o), plus_sum(Dv, o)};
+      const int offs[4] = {-WW, -1, 1, WW};
+      float wts[4], wsum = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        wts[k] = fmaxf(fmaf(sad[k], inv_s, 1.0f), 0.0f);
+        wsum += wts[k];
+      }
+      const float inv_w = 1.0f / wsum;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float* p = src + c * NC + o;
+        float v = p[0];
+#pragma unroll
+        for (int k = 3; k >= 0; k--) v = fmaf(p[offs[k]], wts[k], v);
+        dst[c * NC + od] = v * inv_w;
+      }
+      continue;
+    }
+    // STAGE 0: 12 neighbours (epf0.rs:182-195 order)
+    const float* MB = maps + 2 * NC;  // (2,0)
+    const float* MD = maps + 3 * NC;  // (0,2)
+    const float* ME = maps + 4 * NC;  // (1,1)
+    const float* MF = maps + 5 * NC;  // (1,-1)
+    const int offs[12] = {-2 * WW, -WW - 1, -WW, -WW + 1, -2, -1, 1, 2, WW - 1, WW, WW + 1, 2 * WW};
+    const float sad[12] = {
+        plus_sum(MD, o - 2 * WW), plus_sum(ME, o - WW - 1), plus_sum(Dv, o - WW), plus_sum(MF, o),
+        plus_sum(MB, o - 2),      plus_sum(Dh, o - 1),      plus_sum(Dh, o),      plus_sum(MB, o),
+        plus_sum(MF, o + WW - 1), plus_sum(Dv, o),          plus_sum(ME, o),      plus_sum(MD, o)};
+    float wts[12], wsum = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      wts[k] = fmaxf(fmaf(sad[k], inv_s, 1.0f), 0.0f);
+      wsum += wts[k];
+    }
+    const float inv_w = 1.0f / wsum;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float* p = src + c * NC + o;
+      float v = p[0];
+#pragma unroll
+      for (int k = 11; k >= 0; k--) v = fmaf(p[offs[k]], wts[k], v);
+      dst[c * NC + od] = v * inv_w;
+    }
+  }
+  __syncthreads();
+}
+
+template <bool GAB, int EPF>
+__global__ void __launch_bounds__(256) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+  using C = FCfg<GAB, EPF>;
+  constexpr int H = C::H, WW = C::WW, WH = C::WH, NC = C::NC;
+  extern __shared__ float smem[];
+  float* bufA = smem;
+  float* bufB = smem + 3 * NC;
+  float* maps = smem + 6 * NC;
+  float* sig = maps + C::NMAPS * NC;
+  uint32_t lo = 0, hi = T.num_frames;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (T.tile_prefix[mid] <= blockIdx.x) lo = mid;
+    else hi = mid;
+  }
+  const FrameDev& F = B.frames[lo];
+  if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return;  // another instantiation handles this frame
+  const uint32_t local = blockIdx.x - T.tile_prefix[lo];
+  const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
+  const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
+  const int w = int(F.width), h = int(F.height);
+  const int wx0 = x0 - H, wy0 = y0 - H;
+  // ---- load, pre-mirrored; cells farther than H outside the image are never needed ----
+  for (int idx = threadIdx.x; idx < NC; idx += blockDim.x) {
+    const int lx = idx % WW, ly = idx / WW;
+    const int gx = wx0 + lx, gy = wy0 + ly;
+    if (gx > w - 1 + H || gy > h - 1 + H) continue;
+    const size_t so = size_t(mirror(gy, h)) * F.plane_stride + mirror(gx, w);
+#pragma unroll
+    for (int c = 0; c < 3; c++) bufA[c * NC + idx] = src_planes[F.plane_base + c * F.plane_size + so];
+  }
+  const int sbx0 = max(wx0, 0) >> 3, sby0 = max(wy0, 0) >> 3;
+  if (EPF > 0) {  // features/epf.rs:54-79, once per 8x8 block touched by the window
+    for (int idx = threadIdx.x; idx < C::SBW * C::SBH; idx += blockDim.x) {
+      const int bx = sbx0 + idx % C::SBW, by = sby0 + idx / C::SBW;
+      float v = 0.0f;
+      if (bx < int(F.xb) && by < int(F.yb)) {
+        const size_t bidx = size_t(by) * F.xb + bx;
+        const int32_t raw_quant = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off)[bidx];
+        const uint32_t sharp = (B.blob + F.epf_off)[bidx];
+        float sigma_quant = F.epf_quant_mul / (F.quant_scale * float(raw_quant) * -1.1715728752538099024f);
+        v = 1.0f / fminf(sigma_quant * F.epf_sharp_lut[sharp], -1e-4f);
+      }
+      sig[idx] = v;
+    }
+  }
+  __syncthreads();
+  float* cur = bufA;
+  float* nxt = bufB;
+  int m = 0;
+  if (GAB) {  // gaborish.rs:40-88
+    m += 1;
+    const int r = H - m;
+    const int rw = kTW + 2 * r, rh = kTH + 2 * r;
+    for (int idx = threadIdx.x; idx < rw * rh; idx += blockDim.x) {
+      const int lx = m + idx % rw, ly = m + idx / rw;
+      const int gx = wx0 + lx, gy = wy0 + ly;
+      if (gx < -r || gx > w - 1 + r || gy < -r || gy > h - 1 + r) continue;
+      const int o = (mirror(gy, h) - wy0) * WW + (mirror(gx, w) - wx0);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float* p = cur + c * NC + o;
+        float sum = p[0] * F.gab_k0[c];
+        sum = fmaf(F.gab_k1[c], p[-WW] + p[-1] + p[WW] + p[1], sum);
+        sum = fmaf(F.gab_k2[c], p[-WW - 1] + p[-WW + 1] + p[WW - 1] + p[WW + 1], sum);
+        nxt[c * NC + ly * WW + lx] = sum;
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (EPF >= 3) {
+    m += 3;
+    epf_stage<0, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (EPF >= 1) {
+    m += 2;
+    epf_stage<1, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (EPF >= 2) {
+    m += 1;
+    epf_stage<2, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // ---- colour + store of the kTW x kTH core ----
+  const int tw = min(kTW, w - x0), th = min(kTH, h - y0);
+  uint8_t* out_base = static_cast<uint8_t*>(F.out_ptr);
+  if (F.output_format == JXG_FORMAT_XYB_F32_PLANAR) {
+    for (int idx = threadIdx.x; idx < kTW * th; idx += blockDim.x) {
+      const int lx = idx % kTW, ly = idx / kTW;
+      if (lx >= tw) continue;
+      const int o = (H + ly) * WW + H + lx;
+      for (int c = 0; c < 3; c++)
+        reinterpret_cast<float*>(out_base + (size_t(c) * F.height + y0 + ly) * F.out_row_stride)[x0 + lx] = cur[c * NC + o];
+    }
+    return;
+  }
+  uint8_t* stage_u8 = reinterpret_cast<uint8_t*>(nxt);  // free buffer: interleaved output staging (<= 24 KB)
+  const int bpp = F.output_format == JXG_FORMAT_RGB_U8 ? 3 : (F.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 12);
+  for (int idx = threadIdx.x; idx < kTW * th; idx += blockDim.x) {
+    const int lx = idx % kTW, ly = idx / kTW;
+    if (lx >= tw) continue;
+    const int o = (H + ly) * WW + H + lx;
+    const int x = x0 + lx, y = y0 + ly;
+    float vx = cur[o], vy = cur[NC + o], vb = cur[2 * NC + o];
+    float l = vy + vx - F.bias_cbrt[0], mm = vy - vx - F.bias_cbrt[1], s = vb - F.bias_cbrt[2];
+    float l2 = l * l, m2 = mm * mm, s2 = s * s;
+    float sl = l * F.intensity_scale, sm = mm * F.intensity_scale, ss = s * F.intensity_scale;
+    l = fmaf(l2, sl, F.scaled_bias[0]);
+    mm = fmaf(m2, sm, F.scaled_bias[1]);
+    s = fmaf(s2, ss, F.scaled_bias[2]);
+    float v[3];
+    v[0] = fmaf(F.opsin[0], l, fmaf(F.opsin[1], mm, F.opsin[2] * s));
+    v[1] = fmaf(F.opsin[3], l, fmaf(F.opsin[4], mm, F.opsin[5] * s));
+    v[2] = fmaf(F.opsin[6], l, fmaf(F.opsin[7], mm, F.opsin[8] * s));
+    if (F.output_tf == JXG_TF_SRGB) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) v[c] = linear_to_srgb(v[c]);
+    }
+    if (bpp == 12) {
+      float* d = reinterpret_cast<float*>(stage_u8) + (ly * kTW + lx) * 3;
+      d[0] = v[0];
+      d[1] = v[1];
+      d[2] = v[2];
+    } else {
+      uint8_t* d = stage_u8 + (ly * kTW + lx) * bpp;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float dth = c_dither[((y + 13 * c) & 31) * 32 + ((x + 23 * c) & 31)];
+        float sc = fminf(fmaxf(v[c] * 255.0f + dth, 0.0f), 255.0f);
+        d[c] = uint8_t(__float2int_rn(sc));
+      }
+      if (bpp == 4) d[3] = 255;
+    }
+  }
+  __syncthreads();
+  const int row_bytes = tw * bpp;
+  for (int ly = threadIdx.x >> 5; ly < th; ly += (blockDim.x >> 5)) {  // one warp per row
+    uint8_t* dst = out_base + size_t(y0 + ly) * F.out_row_stride + size_t(x0) * bpp;
+    const uint8_t* srow = stage_u8 + ly * kTW * bpp;
+    const int lane = threadIdx.x & 31;
+    if (((reinterpret_cast<uintptr_t>(dst) | uintptr_t(row_bytes)) & 15) == 0) {
+      for (int i = lane; i < row_bytes / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(srow)[i];
+    } else {
+      for (int i = lane; i < row_bytes; i += 32) dst[i] = srow[i];
+    }
+  }
+}
+
+template <bool GAB, int EPF>
+static void launch_filters(const BatchDev& B, const FusedTiles& FT, uint32_t tiles, cudaStream_t stream) {
+  k_filters_store<GAB, EPF><<<tiles, 256, FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
+}
+template <bool GAB, int EPF>
+static cudaError_t configure_filters() {
+  return cudaFuncSetAttribute(k_filters_store<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(FCfg<GAB, EPF>::kSmemBytes));
+}
+
+// ===========================================================================
 // host-callable launch wrappers (used by batch.cc through launch.h)
 // ===========================================================================
 
@@ -1124,13 +1436,22 @@ cudaError_t upload_constants(const float* wc, const float* rdct_scale) {
 }
 
 cudaError_t configure_kernels() {
+  cudaError_t e;
+  if ((e = configure_filters<false, 0>()) != cudaSuccess) return e;
+  if ((e = configure_filters<false, 1>()) != cudaSuccess) return e;
+  if ((e = configure_filters<false, 2>()) != cudaSuccess) return e;
+  if ((e = configure_filters<false, 3>()) != cudaSuccess) return e;
+  if ((e = configure_filters<true, 0>()) != cudaSuccess) return e;
+  if ((e = configure_filters<true, 1>()) != cudaSuccess) return e;
+  if ((e = configure_filters<true, 2>()) != cudaSuccess) return e;
+  if ((e = configure_filters<true, 3>()) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               int(kIdctWarps * 3 * kWarpBuf * sizeof(float)));
 }
 
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
-                    cudaEvent_t* ev) {
+                    cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask) {
   // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
   // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
@@ -1149,6 +1470,31 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   launches++;
   mark(3);
   if (debug_stop == 2) return launches;
+  if (debug_stop != 3) {  // default: fused filter + colour + store kernel
+    FusedTiles FT{fused_prefix, B.num_frames};
+    mark(4);
+    mark(5);
+    mark(6);
+    // one launch per filter configuration present in the batch (CTAs of other frames exit at once)
+    for (int cfg = 0; cfg < 8; cfg++) {
+      if (!(filter_cfg_mask & (1u << cfg))) continue;
+      switch (cfg) {
+        case 0: launch_filters<false, 0>(B, FT, fused_tiles, stream); break;
+        case 1: launch_filters<false, 1>(B, FT, fused_tiles, stream); break;
+        case 2: launch_filters<false, 2>(B, FT, fused_tiles, stream); break;
+        case 3: launch_filters<false, 3>(B, FT, fused_tiles, stream); break;
+        case 4: launch_filters<true, 0>(B, FT, fused_tiles, stream); break;
+        case 5: launch_filters<true, 1>(B, FT, fused_tiles, stream); break;
+        case 6: launch_filters<true, 2>(B, FT, fused_tiles, stream); break;
+        default: launch_filters<true, 3>(B, FT, fused_tiles, stream); break;
+      }
+      launches++;
+    }
+    mark(7);
+    mark(8);
+    if (final_planes) *final_planes = nullptr;
+    return launches;
+  }
   TileDev T{tile_prefix, B.num_frames};
   dim3 blk(32, 8);
   const float* cur = B.planes_a;

@@ -698,19 +698,52 @@ std::vector<uint32_t> decode_permutation(uint32_t size, uint32_t skip, const Ent
     lehmer[idx - skip] = v;
     prev = v;
   }
+  return apply_lehmer(lehmer, skip, size);
+}
+
+std::vector<uint32_t> apply_lehmer(const std::vector<uint32_t>& lehmer, uint32_t skip, uint32_t size) {
   std::vector<uint32_t> perm(size);
   for (uint32_t i = 0; i < size; i++) perm[i] = i;
   // Plain O(n*k) Lehmer decode of the tail [skip, size): element i takes the
   // lehmer[i]-th remaining value (permutation.rs:103-160 does the same with a
   // Fenwick tree).
   std::vector<uint32_t> remaining(perm.begin() + skip, perm.end());
+  uint32_t end = uint32_t(lehmer.size());
   for (uint32_t i = 0; i < end; i++) {
     uint32_t k = lehmer[i];
+    if (k >= remaining.size()) fail("invalid Lehmer code");
     perm[skip + i] = remaining[k];
     remaining.erase(remaining.begin() + k);
   }
   for (size_t i = 0; i < remaining.size(); i++) perm[skip + end + i] = remaining[i];
   return perm;
+}
+
+int32_t EntropyCode::decode_ans_histogram_for_test(BitReader& br, uint32_t log_alpha_size, std::vector<AnsBucket>& out) {
+  out.resize(size_t(1) << log_alpha_size);
+  int32_t s = decode_ans_histogram(br, log_alpha_size, out.data());
+  br.check();
+  return s;
+}
+
+EntropyCode EntropyCode::decode_prefix_codes_for_test(size_t num_clusters, BitReader& br) {
+  EntropyCode c;
+  c.use_prefix = true;
+  c.log_alpha_size = kHuffmanMaxBits;
+  c.num_clusters = uint32_t(num_clusters);
+  c.context_map.assign(num_clusters, 0);
+  for (size_t i = 0; i < num_clusters; i++) c.context_map[i] = uint8_t(i);
+  c.uint_configs.assign(num_clusters, HybridUint{15, 0, 0});
+  c.single_symbol.assign(num_clusters, -1);
+  std::vector<size_t> al(num_clusters);
+  for (auto& a : al) a = decode_varint16(br) + 1;
+  c.huff_offset.resize(num_clusters);
+  for (uint32_t i = 0; i < num_clusters; i++) {
+    std::vector<HE> t = decode_huffman_table(al[i], br);
+    c.huff_offset[i] = uint32_t(c.huff_entries.size());
+    for (const HE& e : t) c.huff_entries.push_back(uint32_t(e.bits) | (uint32_t(e.value) << 16));
+  }
+  return c;
 }
 
 }  // namespace jxg

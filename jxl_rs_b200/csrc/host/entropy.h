@@ -67,6 +67,9 @@ struct EntropyCode {
   // decode.rs:487-545
   static EntropyCode decode(size_t num_contexts, BitReader& br, bool allow_lz77);
   bool is_rle() const;
+  // Pieces of decode(), exposed for the known-answer tests (ans.rs:463-485, huffman.rs:516-527).
+  static int32_t decode_ans_histogram_for_test(BitReader& br, uint32_t log_alpha_size, std::vector<AnsBucket>& out);
+  static EntropyCode decode_prefix_codes_for_test(size_t num_clusters, BitReader& br);
 };
 
 constexpr uint32_t kAnsChecksum = 0x130000;  // ans.rs:425
@@ -96,6 +99,8 @@ class SymbolReader {
 std::vector<uint8_t> decode_context_map(size_t num_contexts, BitReader& br);
 
 // headers/permutation.rs:27-160 (Lehmer-coded permutation)
+// permutation.rs:103-160: applies a Lehmer code to the tail [skip, size) of the identity permutation.
+std::vector<uint32_t> apply_lehmer(const std::vector<uint32_t>& lehmer, uint32_t skip, uint32_t size);
 std::vector<uint32_t> decode_permutation(uint32_t size, uint32_t skip, const EntropyCode& code, BitReader& br,
                                          SymbolReader& reader);
 

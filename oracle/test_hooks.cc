@@ -1,0 +1,136 @@
+// Test hooks (extern "C") into the host front-end primitives and the oracle, used
+// by tests/test_kat_*.py to replay the reference's own known-answer tests.
+// Test infrastructure only — lives in liboracle.so, never in libjxgpu.so.
+#include <cstring>
+#include <vector>
+
+#include "../jxl_rs_b200/csrc/host/frame.h"
+#include "../jxl_rs_b200/csrc/host/quant.h"
+
+using namespace jxg;
+
+extern "C" {
+
+// ans.rs:463-485: parse one ANS histogram; out_dist[i] = probability of symbol i. Returns 0, or -1 on a parse error.
+int jxo_t_ans_histogram(const uint8_t* bytes, size_t len, uint32_t log_alpha, uint16_t* out_dist, int32_t* single) {
+  try {
+    BitReader br(bytes, len);
+    std::vector<AnsBucket> b;
+    int32_t s = EntropyCode::decode_ans_histogram_for_test(br, log_alpha, b);
+    for (size_t i = 0; i < b.size(); i++) out_dist[i] = b[i].dist;
+    if (single) *single = s;
+    return 0;
+  } catch (Error&) {
+    return -1;
+  }
+}
+
+// huffman.rs:516-527: build prefix codes from `hist`, then read `n` symbols from `data` with cluster 0.
+int jxo_t_prefix_read(const uint8_t* hist, size_t hist_len, const uint8_t* data, size_t data_len, uint32_t n, uint32_t* out) {
+  try {
+    BitReader hbr(hist, hist_len);
+    EntropyCode code = EntropyCode::decode_prefix_codes_for_test(1, hbr);
+    BitReader br(data, data_len);
+    SymbolReader r(code, br, 0);
+    for (uint32_t i = 0; i < n; i++) out[i] = r.read_clustered(br, 0);
+    return 0;
+  } catch (Error&) {
+    return -1;
+  }
+}
+
+// Full histogram-set + symbol stream decode (decode.rs:487 + :271): returns values, checks the final state.
+int jxo_t_decode_stream(const uint8_t* bytes, size_t len, uint32_t num_contexts, const uint32_t* ctxs, uint32_t n, uint32_t* out) {
+  try {
+    BitReader br(bytes, len);
+    EntropyCode code = EntropyCode::decode(num_contexts, br, true);
+    SymbolReader r(code, br, 0);
+    for (uint32_t i = 0; i < n; i++) out[i] = r.read_unsigned(br, ctxs[i]);
+    r.check_final_state(br);
+    return 0;
+  } catch (Error&) {
+    return -1;
+  }
+}
+
+int jxo_t_hybrid_decode_config(const uint8_t* bytes, size_t len, uint32_t skip_bits, uint32_t log_alpha, uint32_t token, uint32_t* value) {
+  try {
+    BitReader br(bytes, len);
+    br.skip_bits(skip_bits);
+    HybridUint u = HybridUint::decode(log_alpha, br);
+    *value = u.read(token, br);
+    return 0;
+  } catch (Error&) {
+    return -1;
+  }
+}
+
+uint64_t jxo_t_bitreader(const uint8_t* bytes, size_t len, const uint32_t* nbits, uint32_t n, uint64_t* out) {
+  BitReader br(bytes, len);
+  for (uint32_t i = 0; i < n; i++) out[i] = br.read(nbits[i]);
+  return br.total_bits_read();
+}
+
+uint32_t jxo_t_natural_order(int order_idx, uint32_t* out, size_t cap) {
+  std::vector<uint32_t> o = natural_coeff_order(order_idx);
+  if (o.size() <= cap) memcpy(out, o.data(), o.size() * 4);
+  return uint32_t(o.size());
+}
+
+uint32_t jxo_t_dequant_table(int transform, int c, float* out, size_t cap) {
+  int qt = quant_table_for_transform(transform);
+  const std::vector<float>& t = library_dequant_table(qt);
+  size_t n = t.size() / 3;
+  if (n <= cap) memcpy(out, t.data() + size_t(c) * n, n * 4);
+  return uint32_t(n);
+}
+
+int jxo_t_lehmer(const uint32_t* code, uint32_t n, uint32_t skip, uint32_t size, uint32_t* out) {
+  try {
+    std::vector<uint32_t> p = apply_lehmer(std::vector<uint32_t>(code, code + n), skip, size);
+    memcpy(out, p.data(), p.size() * 4);
+    return 0;
+  } catch (Error&) {
+    return -1;
+  }
+}
+
+// predict.rs:564-593 (predict_and_update_errors golden)
+void jxo_t_wp_golden(int64_t* preds, int32_t* props) {
+  struct Rnd {
+    int64_t out = 1;
+    int64_t next() {
+      out = out * 48271 % 0x7fffffff;
+      return out;
+    }
+  } rng;
+  WeightedHeader h;
+  h.p1c = uint32_t(rng.next() % 32);
+  h.p2c = uint32_t(rng.next() % 32);
+  h.p3ca = uint32_t(rng.next() % 32);
+  h.p3cb = uint32_t(rng.next() % 32);
+  h.p3cc = uint32_t(rng.next() % 32);
+  h.p3cd = uint32_t(rng.next() % 32);
+  h.p3ce = uint32_t(rng.next() % 32);
+  for (auto& w : h.w) w = uint32_t(rng.next() % 16);
+  const size_t xs = 8, ys = 8;
+  WpState st(h, xs);
+  for (int i = 0; i < 4; i++) {
+    size_t x = size_t(rng.next()) % xs, y = size_t(rng.next()) % ys;
+    int32_t top = int32_t(rng.next()) % 256, left = int32_t(rng.next()) % 256, topright = int32_t(rng.next()) % 256,
+            topleft = int32_t(rng.next()) % 256, toptop = int32_t(rng.next()) % 256;
+    st.predict(x, y, top, left, topright, topleft, toptop, preds[i], props[i]);
+    st.update(int32_t(rng.next() % 256), x, y);
+  }
+}
+
+// Modular sub-bitstream decode of `nch` channels of w x h (test for the host modular decoder via synth streams).
+int jxo_t_parse_ok(const uint8_t* data, size_t size) {
+  try {
+    auto fs = parse_vardct_file(data, size);
+    return 0;
+  } catch (Error& e) {
+    return e.code;
+  }
+}
+}
