@@ -92,7 +92,7 @@ struct Context {
   // intermediates and the pinned staging arena survive jxg_batch_end so that a
   // steady-state decode loop does no cudaMalloc / cudaHostAlloc.
   PinnedArena blob;
-  DevBuf d_blob, d_frames, d_sections, d_streams, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
+  DevBuf d_blob, d_frames, d_sections, d_streams, d_streams_lean, d_streams_fast, d_streams_slow, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
       d_planes_b, d_status, d_out;
   bool batch_live = false;
 };
@@ -108,12 +108,13 @@ struct Batch {
   Context* ctx;
   PinnedArena& blob;
   explicit Batch(Context* c)
-      : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams),
+      : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams), d_streams_lean(c->d_streams_lean), d_streams_fast(c->d_streams_fast), d_streams_slow(c->d_streams_slow),
         d_nz_base(c->d_nz_base), d_tiles(c->d_tiles), d_ftiles(c->d_ftiles), d_coeffs(c->d_coeffs), d_block_off(c->d_block_off), d_nz(c->d_nz),
         d_planes_a(c->d_planes_a), d_planes_b(c->d_planes_b), d_status(c->d_status), d_out(c->d_out) {}
   std::vector<FrameDev> frames;
   std::vector<SectionDev> sections;
-  std::vector<StreamDev> streams;
+  std::vector<StreamDev> streams, streams_lean, streams_fast, streams_slow;
+  bool lean_all_420 = true;
   std::vector<uint64_t> nz_base;
   std::vector<uint32_t> tile_prefix{0};
   std::vector<uint32_t> fused_prefix{0};
@@ -124,7 +125,7 @@ struct Batch {
   bool any_gab = false;
   int debug_stop = 0;
   // device
-  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
+  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_streams_lean, &d_streams_fast, &d_streams_slow, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
@@ -360,9 +361,13 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
     b->sections.push_back(sd);
   }
 #undef APPEND
+  if (F.num_passes == 1 && !F.passes[0].use_prefix)
+    for (uint32_t c = 0; c < d->passes[0].num_clusters; c++)
+      if (d->passes[0].uint_configs[c] != (4u | (2u << 8))) b->lean_all_420 = false;
   F.first_stream = uint32_t(b->streams.size());
   for (uint32_t g = 0; g < F.num_groups; g++) {
     b->streams.push_back(StreamDev{uint32_t(b->frames.size()), g});
+    (F.num_passes != 1 ? b->streams_slow : (F.passes[0].use_prefix ? b->streams_fast : b->streams_lean)).push_back(StreamDev{uint32_t(b->frames.size()), g});
     b->nz_base.push_back(b->nz_bytes);
     b->nz_bytes += size_t(F.num_passes) * 3072;
   }
@@ -423,6 +428,12 @@ static int launch(Batch* b, cudaStream_t s) {
   B.streams = static_cast<const StreamDev*>(b->d_streams.p);
   B.num_frames = uint32_t(b->frames.size());
   B.num_streams = uint32_t(b->streams.size());
+  B.streams_lean = static_cast<const StreamDev*>(b->d_streams_lean.p);
+  B.num_lean = uint32_t(b->streams_lean.size());
+  B.streams_fast = static_cast<const StreamDev*>(b->d_streams_fast.p);
+  B.streams_slow = static_cast<const StreamDev*>(b->d_streams_slow.p);
+  B.num_fast = uint32_t(b->streams_fast.size());
+  B.num_slow = uint32_t(b->streams_slow.size());
   B.coeffs = static_cast<int32_t*>(b->d_coeffs.p);
   B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
   B.nz = static_cast<uint8_t*>(b->d_nz.p);
@@ -438,7 +449,7 @@ static int launch(Batch* b, cudaStream_t s) {
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop,
                                          b->profile ? b->stage_ev : nullptr, static_cast<const uint32_t*>(b->d_ftiles.p),
-                                         b->fused_prefix.back(), b->filter_cfg_mask));
+                                         b->fused_prefix.back(), b->filter_cfg_mask, b->lean_all_420));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -461,7 +472,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
   b->h2d = b->d2h = 0;
   // device allocations
-  if (int r = b->d_blob.ensure(b->blob.size)) return r;
+  if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
   if (int r = b->d_coeffs.ensure(size_t(b->total_groups) * 3 * kGroupCoeffs * 4)) return r;
   if (int r = b->d_block_off.ensure(b->total_blocks * 4)) return r;
   if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
@@ -478,6 +489,9 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = upload(b->d_frames, b->frames, s, &b->h2d)) return r;
   if (int r = upload(b->d_sections, b->sections, s, &b->h2d)) return r;
   if (int r = upload(b->d_streams, b->streams, s, &b->h2d)) return r;
+  if (int r = upload(b->d_streams_lean, b->streams_lean, s, &b->h2d)) return r;
+  if (int r = upload(b->d_streams_fast, b->streams_fast, s, &b->h2d)) return r;
+  if (int r = upload(b->d_streams_slow, b->streams_slow, s, &b->h2d)) return r;
   if (int r = upload(b->d_nz_base, b->nz_base, s, &b->h2d)) return r;
   if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
   if (int r = upload(b->d_ftiles, b->fused_prefix, s, &b->h2d)) return r;

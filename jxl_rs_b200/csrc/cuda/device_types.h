@@ -76,8 +76,11 @@ struct BatchDev {
   const uint8_t* blob;
   const FrameDev* frames;
   const SectionDev* sections;
-  const StreamDev* streams;
-  uint32_t num_frames, num_streams;
+  const StreamDev* streams;       // all (frame, group) units, ordered by frame then group
+  const StreamDev* streams_lean;  // single-pass ANS frames: k_entropy_lean
+  const StreamDev* streams_fast;  // single-pass prefix-coded frames: k_entropy_fast
+  const StreamDev* streams_slow;  // multi-pass frames: k_entropy
+  uint32_t num_frames, num_streams, num_lean, num_fast, num_slow;
   int32_t* coeffs;      // [groups][3][65536]
   uint32_t* block_off;  // per 8x8 block: coefficient offset of the varblock starting there
   uint8_t* nz;          // [streams][passes][3][1024]

@@ -14,6 +14,7 @@
 // HBM / latency bound integer and f32 work.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../../include/jxg.h"
 #include "device_types.h"
@@ -251,11 +252,12 @@ __device__ __forceinline__ int finish_pass(const BatchDev& B, const FrameDev& F,
 constexpr int kEntropyWarps = 4;
 
 __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B) {
-  const uint32_t stream = blockIdx.x * kEntropyWarps + (threadIdx.x >> 5);
-  if (stream >= B.num_streams || (threadIdx.x & 31) != 0) return;
-  const StreamDev sd = B.streams[stream];
+  const uint32_t slow_idx = blockIdx.x * kEntropyWarps + (threadIdx.x >> 5);
+  if (slow_idx >= B.num_slow || (threadIdx.x & 31) != 0) return;
+  const StreamDev sd = B.streams_slow[slow_idx];
   const FrameDev& F = B.frames[sd.frame];
   const uint32_t g = sd.group;
+  const uint32_t stream = F.first_stream + g;
   const uint32_t gx = g % F.xg, gy = g / F.xg;
   const uint32_t bx0 = gx * 32, by0 = gy * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
@@ -319,6 +321,483 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
     for (uint32_t p = 0; p < np && !err; p++) err = finish_pass(B, F, p, g, st[p]);
   }
   B.status[stream] = err;
+}
+
+// ---------------------------------------------------------------------------
+// K1 fast path (single-pass frames): S streams per warp, one lane per stream,
+// the decode loop written as a small state machine so that the lanes of a warp
+// stay converged on the common "decode one symbol" body. A stream's symbols are
+// strictly serial (one rANS state, contexts depend on the previous values), so
+// throughput comes from packing independent streams: S is chosen by the host so
+// that the grid is about one resident wave of warps.
+// ---------------------------------------------------------------------------
+struct LaneBr {  // 32-bit window bit reader (bit_reader.rs semantics: zeros past the end, checked at the end)
+  const uint32_t* words;
+  uint32_t nwords, bitpos, ci, lo, hi;
+  __device__ __forceinline__ uint32_t ldw(uint32_t i) const { return i < nwords ? __ldg(words + i) : 0u; }
+  __device__ __forceinline__ void init(const uint8_t* p, uint32_t len) {
+    words = reinterpret_cast<const uint32_t*>(p);
+    nwords = (len + 3) >> 2;
+    bitpos = 0;
+    ci = 0;
+    lo = ldw(0);
+    hi = ldw(1);
+  }
+  __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(lo, hi, bitpos & 31); }
+  __device__ __forceinline__ uint32_t peek(uint32_t n) const {  // n <= 31
+    return peek32() & ((1u << n) - 1u);
+  }
+  __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
+    const uint32_t nb = bitpos + n;
+    if ((nb >> 5) != ci) {
+      ci++;
+      lo = hi;
+      hi = ldw(ci + 1);
+    }
+    bitpos = nb;
+  }
+};
+
+constexpr uint32_t kCfg420 = 4u | (2u << 8) | (0u << 16);  // hybrid_uint.rs:60-65
+
+__device__ __forceinline__ uint32_t lane_hybrid(uint32_t cfg, uint32_t token, LaneBr& br) {
+  if (cfg == kCfg420) {  // hybrid_uint.rs:67-80 (read_config_420)
+    if (token < 16) return token;
+    const uint32_t nbits = ((token >> 2) - 2) & 31;
+    const uint32_t bits = br.peek(nbits);
+    br.skip(nbits);
+    return (((token & 3) | 4) << nbits) | bits;
+  }
+  const uint32_t split_exponent = cfg & 0xff, msb = (cfg >> 8) & 0xff, lsb = (cfg >> 16) & 0xff;
+  const uint32_t split_token = 1u << split_exponent;
+  if (token < split_token) return token;
+  const uint32_t bits_in_token = lsb + msb;
+  const uint32_t nbits = (split_exponent - bits_in_token + ((token - split_token) >> bits_in_token)) & 31;
+  const uint32_t low = token & ((1u << lsb) - 1);
+  const uint32_t token_nolow = token >> lsb;
+  const uint32_t bits = br.peek(nbits);
+  br.skip(nbits);
+  const uint32_t hi = (token_nolow & ((1u << msb) - 1)) | (1u << msb);
+  return (((hi << nbits) | bits) << lsb) | low;
+}
+
+template <int S>
+__global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
+  __shared__ uint16_t s_nz_ctx[64], s_freq_ctx[64];
+  if (threadIdx.x < 64) {
+    s_nz_ctx[threadIdx.x] = c_nz_ctx[threadIdx.x];
+    s_freq_ctx[threadIdx.x] = c_freq_ctx[threadIdx.x];
+  }
+  __syncthreads();
+  const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t sidx = warp * S + lane;
+  bool done = !(lane < S && sidx < B.num_fast);
+  // per-lane stream state (dummy but valid values for idle lanes)
+  const StreamDev sd = done ? StreamDev{0, 0} : B.streams_fast[sidx];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t gsid = F.first_stream + g;
+  const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0), gn = gw * gh;
+  int32_t* const group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  uint8_t* const nz = B.nz + B.nz_base[gsid];
+  const uint8_t* const tmap = B.blob + F.transform_off;
+  const int32_t* const rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
+  const uint8_t* const qlf = B.blob + F.quant_lf_off;
+  const uint8_t* const bcm = B.blob + F.block_ctx_map_off;
+  uint32_t* const block_off = B.block_off + F.block_base;
+  const PassDev& P = F.passes[0];
+  const uint8_t* const ctxmap = B.blob + P.context_map_off;
+  const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
+  const uint2* const ans = reinterpret_cast<const uint2*>(B.blob + P.ans_off);
+  const uint32_t* const huff = reinterpret_cast<const uint32_t*>(B.blob + P.huff_off);
+  const uint32_t* const huff_offset = reinterpret_cast<const uint32_t*>(B.blob + P.huff_offset_off);
+  const bool use_prefix = P.use_prefix != 0;
+  const uint32_t log_alpha = P.log_alpha_size, log_bucket = 12 - P.log_alpha_size, bucket_mask = (1u << (12 - P.log_alpha_size)) - 1;
+  const uint32_t shift = P.shift;
+  const uint32_t nbc = F.num_block_contexts;
+  const uint32_t num_ac_contexts = nbc * (37 + 458);
+  int err = 0;
+  LaneBr br;
+  uint32_t ans_state = 0x130000u, context_offset = 0;
+  if (!done) {
+    const SectionDev sec = B.sections[F.section_base + g];
+    br.init(B.blob + sec.off, sec.len);
+    uint32_t nb = 0;
+    while ((1u << nb) < F.num_histograms) nb++;
+    const uint32_t hist_idx = br.peek(nb);  // group.rs:333-341
+    br.skip(nb);
+    if (hist_idx >= F.num_histograms) {
+      err = JXG_ERR_INVALID_HISTOGRAM_INDEX;
+      done = true;
+      B.status[gsid] = err;
+    }
+    context_offset = hist_idx * num_ac_contexts;
+    if (!use_prefix) {
+      ans_state = br.peek32();
+      br.skip(32);
+    }
+  } else {
+    br.words = nullptr;
+    br.nwords = br.bitpos = br.ci = br.lo = br.hi = 0;
+  }
+  enum { PH_SCAN = 0, PH_NNZ = 1, PH_COEF = 2 };
+  uint32_t phase = PH_SCAN, pos = 0, coeffs_offset = 0;
+  // current block / channel
+  uint32_t bx = 0, by = 0, cx = 1, cy = 1, shape = 0, qf_idx = 0, quant_lf = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
+  uint32_t ci = 0, k = 0, nonzeros = 0, prev = 0, histo_offset = 0;
+  const uint32_t* order = B.natural_orders;
+  int32_t* cur = group_coeffs;
+
+  for (;;) {
+    if (!__any_sync(0xffffffffu, !done)) break;
+    if (!done && phase == PH_SCAN) {
+      uint32_t raw_t = 0;
+      while (pos < gn) {
+        bx = pos % gw;
+        by = pos / gw;
+        raw_t = tmap[size_t(by0 + by) * F.xb + bx0 + bx];
+        if (raw_t >= 128) break;
+        pos++;
+      }
+      if (pos >= gn) {  // stream finished: check_final_state (decode.rs:400)
+        const SectionDev sec = B.sections[F.section_base + g];
+        if (br.bitpos > sec.len * 8u) err = JXG_ERR_OUT_OF_BOUNDS;
+        else if (!use_prefix && ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
+        B.status[gsid] = err;
+        done = true;
+      } else {
+        const uint32_t t = raw_t & 127;
+        if (t >= 27) {
+          B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
+          done = true;
+        } else {
+          const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+          cx = c_cov_x[t];
+          cy = c_cov_y[t];
+          shape = c_shape[t];
+          const uint32_t raw_quant = uint32_t(rq[bidx]);
+          quant_lf = qlf[bidx];
+          qf_idx = 0;
+          for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
+          num_blocks = cx * cy;
+          num_coeffs = num_blocks * 64;
+          lnb = 31 - __clz(num_blocks);
+          block_off[bidx] = coeffs_offset;
+          ci = 0;
+          phase = PH_NNZ;
+        }
+      }
+    }
+    if (done) continue;
+    // ---- one symbol ----
+    uint32_t ctx, block_context = 0;
+    const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);  // Y, X, B
+    if (phase == PH_NNZ) {
+      const uint8_t* nzc_map = nz + c * 1024;
+      uint32_t predicted;
+      if (bx == 0) predicted = by == 0 ? 32u : nzc_map[(by - 1) * 32];
+      else if (by == 0) predicted = nzc_map[bx - 1];
+      else predicted = (uint32_t(nzc_map[(by - 1) * 32 + bx]) + uint32_t(nzc_map[by * 32 + bx - 1]) + 1u) >> 1;
+      uint32_t idx = c < 2 ? uint32_t(c ^ 1) : 2u;
+      idx = idx * 13 + shape;
+      idx = idx * (F.num_qf_thresholds + 1) + qf_idx;
+      idx = idx * F.num_lf_contexts + quant_lf;
+      block_context = __ldg(bcm + idx);
+      const uint32_t nzc = predicted < 8 ? predicted : (predicted < 64 ? 4 + predicted / 2 : 36);
+      ctx = nzc * nbc + block_context + context_offset;
+    } else {
+      ctx = histo_offset + (uint32_t(s_nz_ctx[((nonzeros + num_blocks - 1) >> lnb) & 63]) + uint32_t(s_freq_ctx[(k >> lnb) & 63])) * 2 + prev;
+    }
+    const uint32_t cluster = __ldg(ctxmap + ctx);
+    uint32_t token;
+    if (use_prefix) {  // huffman.rs:446-457
+      const uint32_t* tb = huff + __ldg(huff_offset + cluster);
+      uint32_t p = br.peek(8);
+      uint32_t e = __ldg(tb + p);
+      uint32_t n_bits = e & 0xff;
+      if (n_bits > 8) {
+        br.skip(8);
+        n_bits -= 8;
+        p += e >> 16;
+        p += br.peek(n_bits);
+        e = __ldg(tb + p);
+      }
+      br.skip(e & 0xff);
+      token = e >> 16;
+    } else {  // ans.rs:356-393
+      const uint32_t idx = ans_state & 0xfff;
+      const uint32_t i = idx >> log_bucket, p = idx & bucket_mask;
+      const uint2 b = __ldg(ans + ((cluster << log_alpha) + i));
+      const uint32_t alias_cutoff = (b.x >> 8) & 0xff;
+      const bool alias = p >= alias_cutoff;
+      const uint32_t dist = (b.x >> 16) ^ (alias ? (b.y >> 16) : 0u);
+      const uint32_t offset = p + (alias ? (b.y & 0xffff) : 0u);
+      token = alias ? (b.x & 0xff) : i;
+      uint32_t next = (ans_state >> 12) * dist + offset;
+      if (next < (1u << 16)) {
+        next = (next << 16) | br.peek(16);
+        br.skip(16);
+      }
+      ans_state = next;
+    }
+    const uint32_t value = lane_hybrid(__ldg(ucfg + cluster), token, br);
+    bool next_channel = false;
+    if (phase == PH_NNZ) {
+      nonzeros = value;
+      if (nonzeros + num_blocks > num_coeffs) {
+        B.status[gsid] = JXG_ERR_INVALID_NUM_NONZEROS;
+        done = true;
+        continue;
+      }
+      uint8_t* nzc_map = nz + c * 1024;
+      const uint8_t nzv = uint8_t((nonzeros + num_blocks - 1) >> lnb);
+      for (uint32_t iy = 0; iy < cy; iy++)
+        for (uint32_t ix = 0; ix < cx; ix++) nzc_map[(by + iy) * 32 + bx + ix] = nzv;
+      histo_offset = nbc * 37 + 458 * block_context + context_offset;
+      prev = nonzeros > num_coeffs / 16 ? 0u : 1u;
+      k = num_blocks;
+      order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
+                              : B.natural_orders + B.natural_order_off[shape];
+      cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+      if (nonzeros == 0) next_channel = true;
+      else phase = PH_COEF;
+    } else {
+      const int32_t coeff = int32_t(uint32_t(unpack_signed(value)) << shift);
+      if (coeff != 0) {
+        cur[__ldg(order + k)] = coeff;
+        prev = 1;
+        nonzeros--;
+      } else {
+        prev = 0;
+      }
+      k++;
+      if (nonzeros == 0) next_channel = true;
+      else if (k >= num_coeffs) {
+        B.status[gsid] = JXG_ERR_RESIDUAL_NONZEROS;  // group.rs:574
+        done = true;
+        continue;
+      }
+    }
+    if (next_channel) {
+      ci++;
+      phase = PH_NNZ;
+      if (ci == 3) {
+        coeffs_offset += num_coeffs;
+        pos++;
+        phase = PH_SCAN;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1 lean path: ANS-coded single-pass frames. Same S-streams-per-warp scheme as
+// k_entropy_fast, but the per-symbol step is branch-light and identical for the
+// "number of non-zeros" symbol and the coefficient symbols, so that packed lanes
+// stay converged; only block / channel set-up diverges.
+// Bit window: three consecutive 32-bit words re-read from L1 per symbol (the
+// section copies are 8-byte aligned and zero padded, so reading two words past
+// the end is in bounds); a symbol consumes at most 16 + 31 bits.
+// ---------------------------------------------------------------------------
+template <int S, bool K420>
+__global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
+  __shared__ uint16_t s_nz2[64], s_fr2[64];  // context LUTs, pre-multiplied by 2 (block_context_map.rs:34-46)
+  if (threadIdx.x < 64) {
+    s_nz2[threadIdx.x] = uint16_t(c_nz_ctx[threadIdx.x] * 2);
+    s_fr2[threadIdx.x] = uint16_t(c_freq_ctx[threadIdx.x] * 2);
+  }
+  __syncthreads();
+  const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t sidx = warp * S + lane;
+  bool done = !(lane < S && sidx < B.num_lean);
+  const StreamDev sd = done ? StreamDev{0, 0} : B.streams_lean[sidx];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t gsid = F.first_stream + g;
+  const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0), gn = gw * gh;
+  int32_t* const group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  uint8_t* const nz = B.nz + B.nz_base[gsid];
+  const uint8_t* const tmap = B.blob + F.transform_off + (size_t(by0) * F.xb + bx0);
+  const int32_t* const rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off) + (size_t(by0) * F.xb + bx0);
+  const uint8_t* const qlf = B.blob + F.quant_lf_off + (size_t(by0) * F.xb + bx0);
+  uint32_t* const block_off = B.block_off + F.block_base + (size_t(by0) * F.xb + bx0);
+  const uint32_t xb = F.xb;
+  const PassDev& P = F.passes[0];
+  const uint8_t* const ctxmap = B.blob + P.context_map_off;
+  const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
+  const uint2* const ans = reinterpret_cast<const uint2*>(B.blob + P.ans_off);
+  const uint32_t log_alpha = P.log_alpha_size, log_bucket = 12 - P.log_alpha_size, bucket_mask = (1u << (12 - P.log_alpha_size)) - 1;
+  const uint32_t shift = P.shift;
+  const uint32_t nbc = F.num_block_contexts;
+  const SectionDev sec = B.sections[F.section_base + (done ? 0 : g)];
+  const uint32_t* const words = reinterpret_cast<const uint32_t*>(B.blob + sec.off);
+  uint32_t bitpos = 0, ans_state = 0x130000u, context_offset = 0;
+  if (!done) {
+    uint32_t nb = 0;
+    while ((1u << nb) < F.num_histograms) nb++;
+    const uint32_t hist_idx = nb ? (__ldg(words) & ((1u << nb) - 1u)) : 0u;  // group.rs:333-341 (nb <= 12)
+    bitpos = nb;
+    if (hist_idx >= F.num_histograms) {
+      B.status[gsid] = JXG_ERR_INVALID_HISTOGRAM_INDEX;
+      done = true;
+    }
+    context_offset = hist_idx * nbc * (37 + 458);
+    const uint32_t w0 = __ldg(words + (bitpos >> 5)), w1 = __ldg(words + (bitpos >> 5) + 1);
+    ans_state = __funnelshift_r(w0, w1, bitpos & 31);  // ans.rs:431
+    bitpos += 32;
+  }
+  // lane state
+  uint32_t pos = 0, coeffs_offset = 0;
+  uint32_t bx = 0, by = 0, cxy = 0x0101, shape = 0, qf_lf_idx = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
+  uint32_t ci = 3;          // 3: need a new block
+  bool need_setup = true;   // channel (and maybe block) set-up before the next symbol
+  bool mode_nnz = true;
+  uint32_t ctx_nnz = 0, block_context = 0;
+  uint32_t k = 0, nonzeros = 0, prev = 0, histo_offset = 0;
+  const uint32_t* order = B.natural_orders;
+  int32_t* cur = group_coeffs;
+
+  for (;;) {
+    if (!__any_sync(0xffffffffu, !done)) break;
+    if (!done && need_setup) {
+      // ---------- rare path: next block and/or channel ----------
+      if (ci == 3) {
+        uint32_t raw_t = 0;
+        while (pos < gn) {
+          by = pos / gw;
+          bx = pos - by * gw;
+          raw_t = tmap[by * xb + bx];
+          if (raw_t >= 128) break;
+          pos++;
+        }
+        if (pos >= gn) {  // finished: check_final_state (decode.rs:400)
+          int err = 0;
+          if (bitpos > sec.len * 8u) err = JXG_ERR_OUT_OF_BOUNDS;
+          else if (ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
+          B.status[gsid] = err;
+          done = true;
+        } else if ((raw_t & 127) >= 27) {
+          B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
+          done = true;
+        } else {
+          const uint32_t t = raw_t & 127, bidx = by * xb + bx;
+          const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
+          cxy = cx | (cy << 8);
+          shape = c_shape[t];
+          const uint32_t raw_quant = uint32_t(rq[bidx]);
+          uint32_t qf_idx = 0;
+          for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
+          qf_lf_idx = qf_idx * F.num_lf_contexts + qlf[bidx];
+          num_blocks = cx * cy;
+          num_coeffs = num_blocks * 64;
+          lnb = 31 - __clz(num_blocks);
+          block_off[bidx] = coeffs_offset;
+          ci = 0;
+        }
+      }
+      if (!done) {
+        const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);  // Y, X, B
+        const uint8_t* nzc_map = nz + c * 1024;
+        uint32_t predicted;
+        if (bx == 0) predicted = by == 0 ? 32u : nzc_map[(by - 1) * 32];
+        else if (by == 0) predicted = nzc_map[bx - 1];
+        else predicted = (uint32_t(nzc_map[(by - 1) * 32 + bx]) + uint32_t(nzc_map[by * 32 + bx - 1]) + 1u) >> 1;
+        uint32_t idx = (c < 2 ? uint32_t(c ^ 1) : 2u) * 13 + shape;
+        idx = idx * (F.num_qf_thresholds + 1) * F.num_lf_contexts + qf_lf_idx;
+        block_context = __ldg(B.blob + F.block_ctx_map_off + idx);
+        const uint32_t nzc = predicted < 8 ? predicted : (predicted < 64 ? 4 + predicted / 2 : 36);
+        ctx_nnz = nzc * nbc + block_context + context_offset;
+        mode_nnz = true;
+        need_setup = false;
+      }
+    }
+    if (done) continue;
+    // ---------- common path: one symbol ----------
+    const uint32_t wi = bitpos >> 5;
+    const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1), w2 = __ldg(words + wi + 2);
+    const uint32_t ctx_coef = histo_offset + uint32_t(s_nz2[((nonzeros + num_blocks - 1) >> lnb) & 63]) + uint32_t(s_fr2[(k >> lnb) & 63]) + prev;
+    const uint32_t ctx = mode_nnz ? ctx_nnz : ctx_coef;
+    const uint32_t cluster = __ldg(ctxmap + ctx);
+    // rANS step (ans.rs:356-393)
+    const uint32_t idx12 = ans_state & 0xfff;
+    const uint32_t bi = idx12 >> log_bucket, bp = idx12 & bucket_mask;
+    const uint2 bk = __ldg(ans + ((cluster << log_alpha) + bi));
+    const bool alias = bp >= ((bk.x >> 8) & 0xff);
+    const uint32_t dist = (bk.x >> 16) ^ (alias ? (bk.y >> 16) : 0u);
+    const uint32_t offset = bp + (alias ? (bk.y & 0xffff) : 0u);
+    const uint32_t token = alias ? (bk.x & 0xff) : bi;
+    uint32_t next = (ans_state >> 12) * dist + offset;
+    const uint32_t sh = bitpos & 31;
+    const bool refill = next < (1u << 16);
+    const uint32_t w16 = __funnelshift_r(w0, w1, sh) & 0xffff;
+    ans_state = refill ? ((next << 16) | w16) : next;
+    const uint32_t sh2 = sh + (refill ? 16u : 0u);  // <= 47
+    // hybrid uint (hybrid_uint.rs:87-102), branch free
+    uint32_t split_exponent = 4, msb = 2, lsb = 0;
+    if (!K420) {
+      const uint32_t cfg = __ldg(ucfg + cluster);
+      split_exponent = cfg & 0xff;
+      msb = (cfg >> 8) & 0xff;
+      lsb = (cfg >> 16) & 0xff;
+    }
+    const uint32_t split_token = 1u << split_exponent;
+    const bool direct = token < split_token;
+    const uint32_t bits_in_token = msb + lsb;
+    const uint32_t nbits = direct ? 0u : ((split_exponent - bits_in_token + ((token - split_token) >> bits_in_token)) & 31);
+    const uint32_t win = sh2 < 32 ? __funnelshift_r(w0, w1, sh2) : __funnelshift_r(w1, w2, sh2 - 32);
+    const uint32_t bits = win & ((1u << nbits) - 1u);
+    const uint32_t hi = ((token >> lsb) & ((1u << msb) - 1u)) | (1u << msb);
+    const uint32_t composed = (((hi << nbits) | bits) << lsb) | (token & ((1u << lsb) - 1u));
+    const uint32_t value = direct ? token : composed;
+    bitpos += (refill ? 16u : 0u) + nbits;
+    // ---------- post ----------
+    if (mode_nnz) {
+      const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
+      nonzeros = value;
+      if (nonzeros + num_blocks > num_coeffs) {
+        B.status[gsid] = JXG_ERR_INVALID_NUM_NONZEROS;
+        done = true;
+        continue;
+      }
+      uint8_t* nzc_map = nz + c * 1024;
+      const uint8_t nzv = uint8_t((nonzeros + num_blocks - 1) >> lnb);
+      const uint32_t cx = cxy & 0xff, cy = cxy >> 8;
+      for (uint32_t iy = 0; iy < cy; iy++)
+        for (uint32_t ix = 0; ix < cx; ix++) nzc_map[(by + iy) * 32 + bx + ix] = nzv;
+      histo_offset = nbc * 37 + 458 * block_context + context_offset;
+      prev = nonzeros > num_coeffs / 16 ? 0u : 1u;
+      k = num_blocks;
+      order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
+                              : B.natural_orders + B.natural_order_off[shape];
+      cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+      mode_nnz = false;
+      if (nonzeros == 0) {
+        need_setup = true;
+        if (++ci == 3) {
+          coeffs_offset += num_coeffs;
+          pos++;
+        }
+      }
+    } else {
+      const int32_t coeff = int32_t(uint32_t(unpack_signed(value)) << shift);
+      if (coeff != 0) cur[__ldg(order + k)] = coeff;
+      prev = coeff != 0;
+      nonzeros -= prev;
+      k++;
+      if (nonzeros == 0) {
+        need_setup = true;
+        if (++ci == 3) {
+          coeffs_offset += num_coeffs;
+          pos++;
+        }
+      } else if (k >= num_coeffs) {
+        B.status[gsid] = JXG_ERR_RESIDUAL_NONZEROS;  // group.rs:574
+        done = true;
+      }
+    }
+  }
 }
 
 // ===========================================================================
@@ -1120,7 +1599,7 @@ __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileD
 //   (epf0.rs:157-168 / epf1.rs:98-101 evaluate the same sums per pixel).
 // * HBM traffic: one read of the IDCT planes (+ halo) and one write of the output.
 // ===========================================================================
-constexpr int kTW = 64, kTH = 32;
+constexpr int kTW = 64, kTH = 32, kFilterThreads = 512;
 
 struct FusedTiles {
   const uint32_t* tile_prefix;  // [num_frames + 1], kTW x kTH tiles
@@ -1259,7 +1738,7 @@ __device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, f
 }
 
 template <bool GAB, int EPF>
-__global__ void __launch_bounds__(256) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+__global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
   using C = FCfg<GAB, EPF>;
   constexpr int H = C::H, WW = C::WW, WH = C::WH, NC = C::NC;
   extern __shared__ float smem[];
@@ -1411,7 +1890,7 @@ __global__ void __launch_bounds__(256) k_filters_store(const BatchDev B, const F
 
 template <bool GAB, int EPF>
 static void launch_filters(const BatchDev& B, const FusedTiles& FT, uint32_t tiles, cudaStream_t stream) {
-  k_filters_store<GAB, EPF><<<tiles, 256, FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
+  k_filters_store<GAB, EPF><<<tiles, kFilterThreads, FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
 }
 template <bool GAB, int EPF>
 static cudaError_t configure_filters() {
@@ -1451,7 +1930,8 @@ cudaError_t configure_kernels() {
 
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
-                    cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask) {
+                    cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
+                    bool lean_all_420) {
   // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
   // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
@@ -1461,8 +1941,38 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(0);
   cudaMemsetAsync(B.coeffs, 0, coeff_bytes, stream);
   mark(1);
-  k_entropy<<<(B.num_streams + kEntropyWarps - 1) / kEntropyWarps, kEntropyWarps * 32, 0, stream>>>(B);
-  launches++;
+  if (B.num_lean) {
+    uint32_t per = (B.num_lean + 2367) / 2368;
+    if (const char* e = getenv("JXG_ENTROPY_S")) per = uint32_t(atoi(e));  // experiment knob
+    const uint32_t S = per <= 1 ? 1 : (per <= 2 ? 2 : (per <= 4 ? 4 : 8));
+    const uint32_t grid = (B.num_lean + 4 * S - 1) / (4 * S);
+    if (lean_all_420) {
+      if (S == 1) k_entropy_lean<1, true><<<grid, 128, 0, stream>>>(B);
+      else if (S == 2) k_entropy_lean<2, true><<<grid, 128, 0, stream>>>(B);
+      else if (S == 4) k_entropy_lean<4, true><<<grid, 128, 0, stream>>>(B);
+      else k_entropy_lean<8, true><<<grid, 128, 0, stream>>>(B);
+    } else {
+      if (S == 1) k_entropy_lean<1, false><<<grid, 128, 0, stream>>>(B);
+      else if (S == 2) k_entropy_lean<2, false><<<grid, 128, 0, stream>>>(B);
+      else if (S == 4) k_entropy_lean<4, false><<<grid, 128, 0, stream>>>(B);
+      else k_entropy_lean<8, false><<<grid, 128, 0, stream>>>(B);
+    }
+    launches++;
+  }
+  if (B.num_fast) {
+    // streams per warp: aim at about one resident wave (592 schedulers x ~4 warps)
+    uint32_t per = (B.num_fast + 2367) / 2368;
+    if (const char* e = getenv("JXG_ENTROPY_S")) per = uint32_t(atoi(e));  // experiment knob
+    if (per <= 1) k_entropy_fast<1><<<(B.num_fast + 3) / 4, 128, 0, stream>>>(B);
+    else if (per <= 2) k_entropy_fast<2><<<(B.num_fast + 7) / 8, 128, 0, stream>>>(B);
+    else if (per <= 4) k_entropy_fast<4><<<(B.num_fast + 15) / 16, 128, 0, stream>>>(B);
+    else k_entropy_fast<8><<<(B.num_fast + 31) / 32, 128, 0, stream>>>(B);
+    launches++;
+  }
+  if (B.num_slow) {
+    k_entropy<<<(B.num_slow + kEntropyWarps - 1) / kEntropyWarps, kEntropyWarps * 32, 0, stream>>>(B);
+    launches++;
+  }
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
