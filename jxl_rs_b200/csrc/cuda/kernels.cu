@@ -1127,6 +1127,8 @@ __device__ __forceinline__ void warp_col_pass(float* ch, int lane_col, int strid
   for (int i = 0; i < N; i++) ch[i * stride + lane_col] = v[i];
 }
 
+__device__ __forceinline__ bool is_small_reg_type(int t) { return t == 0 || t == 3 || t == 12 || t == 13; }
+
 constexpr int kIdctWarps = 8;
 constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
 
@@ -1217,6 +1219,7 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     if (raw_t < 128) continue;
     const int t = raw_t & 127;
     const int cx = c_cov_x[t], cy = c_cov_y[t];
+    if (is_small_reg_type(t)) continue;  // handled by k_idct_small
     if (cx > 4 || cy > 4) {  // big varblock: handled cooperatively below
       if (lane == 0) {
         uint32_t i = atomicAdd(&s_nbig, 1u);
@@ -1351,6 +1354,176 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     for (int r = threadIdx.x; r < 3 * C; r += blockDim.x)
       big_line_dispatch(R, planes[r / C] + px0 + (r % C), F.plane_stride);
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2a: register path for the 8x8-footprint transforms DCT8x8, DCT4x4, DCT4x8,
+// DCT8x4 (the bulk of all varblocks). Eight threads own one block: thread i holds
+// storage row i (coefficients k = 8 i .. 8 i + 7) of all three channels in
+// registers; 1-D IDCTs run in registers, 8x8 transposes go through warp shuffles,
+// loads and stores are 16-byte vectors. No shared-memory tile, no barriers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void transpose8(float (&v)[8], uint32_t r, uint32_t gmask) {
+#pragma unroll
+  for (int s = 1; s < 8; s <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j & s) continue;
+      const float send = (r & s) ? v[j] : v[j | s];
+      const float recv = __shfl_xor_sync(gmask, send, s);
+      if (r & s) v[j] = recv;
+      else v[j | s] = recv;
+    }
+  }
+}
+
+constexpr int kSmallThreads = 256;
+
+
+__global__ void __launch_bounds__(kSmallThreads) k_idct_small(const BatchDev B) {
+  __shared__ uint16_t s_list[1024];
+  __shared__ uint32_t s_count;
+  const uint32_t stream = blockIdx.x;
+  if (B.status[stream] != 0) return;
+  const StreamDev sd = B.streams[stream];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
+  const uint8_t* tmap = B.blob + F.transform_off;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  for (uint32_t pos = threadIdx.x; pos < gw * gh; pos += blockDim.x) {
+    const uint32_t by = pos / gw, bx = pos - by * gw;
+    const uint32_t raw_t = tmap[size_t(by0 + by) * F.xb + bx0 + bx];
+    if (raw_t >= 128 && is_small_reg_type(raw_t & 127)) s_list[atomicAdd(&s_count, 1u)] = uint16_t(bx | (by << 5));
+  }
+  __syncthreads();
+  const uint32_t count = s_count;
+  const int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
+  const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
+  const int8_t* ytob = reinterpret_cast<const int8_t*>(B.blob + F.ytob_off);
+  const uint32_t* block_off = B.block_off + F.block_base;
+  const uint32_t r = threadIdx.x & 7;  // storage row owned by this thread
+  const uint32_t gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes that own one block (groups may diverge on the type)
+  const float bias0 = F.quant_biases[0], bias1 = F.quant_biases[1], bias2 = F.quant_biases[2], bias3 = F.quant_biases[3];
+  // all lanes of a warp iterate together (shuffles need full participation); tail blocks are clamped + masked
+  const uint32_t iters = (count + kSmallThreads / 8 - 1) / (kSmallThreads / 8);
+  for (uint32_t it = 0; it < iters; it++) {
+    const uint32_t li = it * (kSmallThreads / 8) + (threadIdx.x >> 3);
+    const bool valid = li < count;
+    const uint32_t e = s_list[valid ? li : 0];
+    const uint32_t bx = e & 31, by = e >> 5;
+    const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+    const int t = tmap[bidx] & 127;
+    const uint32_t off = block_off[bidx] + r * 8;
+    const int qt = c_qtable[t];
+    const float* mat = (F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt])
+                                               : B.dequant_default + B.dequant_default_off[qt]) + r * 8;
+    const size_t cidx = size_t((by0 + by) >> 3) * F.cxb + ((bx0 + bx) >> 3);
+    const float x_cc = F.base_correlation_x + float(ytox[cidx]) / float(F.color_factor);
+    const float b_cc = F.base_correlation_b + float(ytob[cidx]) / float(F.color_factor);
+    const float sy = F.inv_global_scale / float(rq[bidx]), sx = sy * F.x_dm, sb = sy * F.b_dm;
+    float v[3][8];
+    {
+      const int4* qp[3] = {reinterpret_cast<const int4*>(group_coeffs + off), reinterpret_cast<const int4*>(group_coeffs + kGroupCoeffs + off),
+                           reinterpret_cast<const int4*>(group_coeffs + 2 * kGroupCoeffs + off)};
+      int q[3][8];
+      float m[3][8];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int4 a = qp[c][0], b = qp[c][1];
+        q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
+        q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
+        const float4 ma = __ldg(reinterpret_cast<const float4*>(mat + c * 64)), mb = __ldg(reinterpret_cast<const float4*>(mat + c * 64) + 1);
+        m[c][0] = ma.x; m[c][1] = ma.y; m[c][2] = ma.z; m[c][3] = ma.w;
+        m[c][4] = mb.x; m[c][5] = mb.y; m[c][6] = mb.z; m[c][7] = mb.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {  // group.rs:100-133
+        const float dy = adjust_quant_bias(q[1][j], bias1, bias3) * (m[1][j] * sy);
+        const float dxc = adjust_quant_bias(q[0][j], bias0, bias3) * (m[0][j] * sx);
+        const float dbc = adjust_quant_bias(q[2][j], bias2, bias3) * (m[2][j] * sb);
+        v[1][j] = dy;
+        v[0][j] = fmaf(x_cc, dy, dxc);
+        v[2][j] = fmaf(b_cc, dy, dbc);
+      }
+    }
+    const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float (&w)[8] = v[c];
+      const float lf = reinterpret_cast<const float*>(B.blob + F.lf_off[c])[bidx];
+      if (r == 0) w[0] = lf;  // LLF of a 1x1 varblock: coefficient 0 <- LF sample
+      float* plane = (c == 0 ? B.planes_a + F.plane_base : (c == 1 ? B.planes_a + F.plane_base + F.plane_size : B.planes_a + F.plane_base + 2 * F.plane_size)) + px0;
+      if (t == 0) {  // DCT8x8: storage [hf = r][vf]
+        idct1d<8>(w);
+        transpose8(w, r, gmask);
+        idct1d<8>(w);  // thread r = y now holds x = 0..7
+        if (valid) {
+          float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
+          d[0] = make_float4(w[0], w[1], w[2], w[3]);
+          d[1] = make_float4(w[4], w[5], w[6], w[7]);
+        }
+      } else if (t == 12 || t == 13) {
+        // DC pair (transform.rs:617-620): dcs = [c0 + c8, c0 - c8], c0 = row 0 col 0, c8 = row 1 col 0
+        const float c0 = __shfl_sync(gmask, w[0], (threadIdx.x & 24) + 0), c8 = __shfl_sync(gmask, w[0], (threadIdx.x & 24) + 1);
+        if (r == 0) w[0] = c0 + c8;
+        if (r == 1) w[0] = c0 - c8;
+        idct1d<8>(w);       // t=13: over vf -> y; t=12: over hf -> x
+        transpose8(w, r, gmask);   // thread j holds entries i = h + 2 * f (f = hf for 8x4, vf for 4x8)
+        float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};
+        idct1d<4>(a4);
+        idct1d<4>(b4);
+        if (t == 13) {  // DCT8X4: thread y: half 0 -> x 0..3, half 1 -> x 4..7
+          if (valid) {
+            float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
+            d[0] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+            d[1] = make_float4(b4[0], b4[1], b4[2], b4[3]);
+          }
+        } else {  // DCT4X8: thread x holds the column: half 0 -> y 0..3, half 1 -> y 4..7
+          w[0] = a4[0]; w[1] = a4[1]; w[2] = a4[2]; w[3] = a4[3];
+          w[4] = b4[0]; w[5] = b4[1]; w[6] = b4[2]; w[7] = b4[3];
+          transpose8(w, r, gmask);
+          if (valid) {
+            float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
+            d[0] = make_float4(w[0], w[1], w[2], w[3]);
+            d[1] = make_float4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      } else {  // DCT4X4 (transform.rs:579-612): thread i = qy + 2 hf holds j = qx + 2 vf
+        const uint32_t base = threadIdx.x & 24;
+        const float c00 = __shfl_sync(gmask, w[0], base), c01 = __shfl_sync(gmask, w[1], base);
+        const float c10 = __shfl_sync(gmask, w[0], base + 1), c11 = __shfl_sync(gmask, w[1], base + 1);
+        if (r == 0) {
+          w[0] = c00 + c01 + c10 + c11;  // quadrant (0,0)
+          w[1] = c00 + c01 - c10 - c11;  // quadrant (0,1)
+        }
+        if (r == 1) {
+          w[0] = c00 - c01 + c10 - c11;  // quadrant (1,0)
+          w[1] = c00 - c01 - c10 + c11;  // quadrant (1,1)
+        }
+        float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};  // over vf for qx = 0 / 1
+        idct1d<4>(a4);
+        idct1d<4>(b4);
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+          w[2 * y] = a4[y];
+          w[2 * y + 1] = b4[y];
+        }
+        transpose8(w, r, gmask);  // thread j = qx + 2 y holds i = qy + 2 hf
+        float p4[4] = {w[0], w[2], w[4], w[6]}, q4[4] = {w[1], w[3], w[5], w[7]};  // over hf for qy = 0 / 1
+        idct1d<4>(p4);
+        idct1d<4>(q4);
+        if (valid) {
+          const uint32_t qx = r & 1, y = r >> 1;
+          *reinterpret_cast<float4*>(plane + size_t(y) * F.plane_stride + qx * 4) = make_float4(p4[0], p4[1], p4[2], p4[3]);
+          *reinterpret_cast<float4*>(plane + size_t(4 + y) * F.plane_stride + qx * 4) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+        }
+      }
+    }
   }
 }
 
@@ -1976,6 +2149,8 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
+  k_idct_small<<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  launches++;
   k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
   launches++;
   mark(3);
