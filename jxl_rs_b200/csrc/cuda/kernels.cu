@@ -1127,7 +1127,7 @@ __device__ __forceinline__ void warp_col_pass(float* ch, int lane_col, int strid
   for (int i = 0; i < N; i++) ch[i * stride + lane_col] = v[i];
 }
 
-__device__ __forceinline__ bool is_small_reg_type(int t) { return t == 0 || t == 3 || t == 12 || t == 13; }
+__device__ __forceinline__ bool is_small_reg_type(int t) { return (t == 0) || (t >= 3 && t <= 13); }  // k_idct_small
 
 constexpr int kIdctWarps = 8;
 constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
@@ -1380,10 +1380,135 @@ __device__ __forceinline__ void transpose8(float (&v)[8], uint32_t r, uint32_t g
 
 constexpr int kSmallThreads = 256;
 
+template <int N>
+__device__ __forceinline__ void transposeN(float* v, uint32_t r, uint32_t gmask) {
+#pragma unroll
+  for (int s = 1; s < N; s <<= 1) {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      if (j & s) continue;
+      const float send = (r & s) ? v[j] : v[j | s];
+      const float recv = __shfl_xor_sync(gmask, send, s);
+      if (r & s) v[j] = recv;
+      else v[j | s] = recv;
+    }
+  }
+}
 
-__global__ void __launch_bounds__(kSmallThreads) k_idct_small(const BatchDev B) {
+struct RegBlockCtx {
+  const int32_t* coeffs;  // group coefficient base (channel 0) + block offset
+  const float* mat;       // dequant matrix of the block's table (channel 0)
+  float* plane;           // plane set base (channel 0) + pixel offset of the block
+  const float* lf;        // LF plane set base handled by caller
+  size_t plane_size, plane_stride;
+  uint32_t num_coeffs;
+  float sx, sy, sb, x_cc, b_cc, bias0, bias1, bias2, bias3;
+};
+
+// One plain-DCT varblock of min(R,C) = NT storage rows x max(R,C) = L entries, NT threads (lanes r = 0..NT-1 of
+// an aligned lane group). TALL: rows >= cols, storage [hf][vf]; else storage [vf][hf] (tests.rs:123-136).
+template <int NT, int L, bool TALL>
+__device__ __forceinline__ void reg_dct_block(const RegBlockCtx& X, const float* const* lfp, uint32_t lf_stride, uint32_t r,
+                                              uint32_t gmask, bool valid) {
+  constexpr int M = L / NT;
+  constexpr int CY = TALL ? L / 8 : NT / 8, CX = TALL ? NT / 8 : L / 8;  // covered blocks
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) {
+    float w[L];
+    {
+      const int4* qc = reinterpret_cast<const int4*>(X.coeffs + size_t(c) * kGroupCoeffs + r * L);
+      const int4* qy = reinterpret_cast<const int4*>(X.coeffs + kGroupCoeffs + r * L);
+      const float4* mc = reinterpret_cast<const float4*>(X.mat + size_t(c) * X.num_coeffs + r * L);
+      const float4* my = reinterpret_cast<const float4*>(X.mat + X.num_coeffs + r * L);
+      const float sc = c == 0 ? X.sx : (c == 1 ? X.sy : X.sb);
+      const float bc = c == 0 ? X.bias0 : (c == 1 ? X.bias1 : X.bias2);
+      const float cc = c == 0 ? X.x_cc : (c == 1 ? 0.0f : X.b_cc);
+#pragma unroll
+      for (int j4 = 0; j4 < L / 4; j4++) {
+        const int4 q = qc[j4];
+        const float4 m = __ldg(mc + j4);
+        float d0 = adjust_quant_bias(q.x, bc, X.bias3) * (m.x * sc), d1 = adjust_quant_bias(q.y, bc, X.bias3) * (m.y * sc);
+        float d2 = adjust_quant_bias(q.z, bc, X.bias3) * (m.z * sc), d3 = adjust_quant_bias(q.w, bc, X.bias3) * (m.w * sc);
+        if (c != 1) {  // chroma from luma: recompute the dequantised Y coefficient (group.rs:128-130)
+          const int4 y = qy[j4];
+          const float4 n = __ldg(my + j4);
+          d0 = fmaf(cc, adjust_quant_bias(y.x, X.bias1, X.bias3) * (n.x * X.sy), d0);
+          d1 = fmaf(cc, adjust_quant_bias(y.y, X.bias1, X.bias3) * (n.y * X.sy), d1);
+          d2 = fmaf(cc, adjust_quant_bias(y.z, X.bias1, X.bias3) * (n.z * X.sy), d2);
+          d3 = fmaf(cc, adjust_quant_bias(y.w, X.bias1, X.bias3) * (n.w * X.sy), d3);
+        }
+        w[4 * j4] = d0;
+        w[4 * j4 + 1] = d1;
+        w[4 * j4 + 2] = d2;
+        w[4 * j4 + 3] = d3;
+      }
+    }
+    // LLF: rows < (TALL ? CX : CY), entries < (TALL ? CY : CX)
+    if (r < uint32_t(TALL ? CX : CY)) {
+      const float* lf = lfp[c];
+      if (CX == 1 && CY == 1) {
+        w[0] = lf[0];
+      } else {
+        llf_small(lf, lf_stride, CY, CX, [&](int vf, int hf, float val) {
+          const int row = TALL ? hf : vf, ent = TALL ? vf : hf;
+          if (uint32_t(row) == r) {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (e == ent) w[e] = val;
+          }
+        });
+      }
+    }
+    idct1d<L>(w);
+    float* plane = X.plane + size_t(c) * X.plane_size;
+#pragma unroll
+    for (int q = 0; q < M; q++) {
+      float* u = w + q * NT;
+      transposeN<NT>(u, r, gmask);
+      idct1d<NT>(u);
+      if (TALL) {  // thread r holds pixel row y = q NT + r, x = 0..NT-1
+        if (valid) {
+          float4* d = reinterpret_cast<float4*>(plane + size_t(q * NT + r) * X.plane_stride);
+#pragma unroll
+          for (int j4 = 0; j4 < NT / 4; j4++) d[j4] = make_float4(u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3]);
+        }
+      } else {  // thread r holds column x = q NT + r; transpose back to rows
+        transposeN<NT>(u, r, gmask);
+        if (valid) {
+          float4* d = reinterpret_cast<float4*>(plane + size_t(r) * X.plane_stride + q * NT);
+#pragma unroll
+          for (int j4 = 0; j4 < NT / 4; j4++) d[j4] = make_float4(u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3]);
+        }
+      }
+    }
+  }
+}
+
+// types handled in registers: 8x8-footprint {0,3,12,13} and plain DCTs up to 32x32 {4..11}
+__device__ __forceinline__ int reg_class(int t) {  // 0: 8 lanes, 1: 16 lanes, 2: 32 lanes, -1: not handled
+  switch (t) {
+    case 0: case 3: case 12: case 13: case 6: case 7: case 8: case 9: return 0;
+    case 4: case 10: case 11: return 1;
+    case 5: return 2;
+    default: return -1;
+  }
+}
+
+// KIND selects the coefficient-row length handled by this instantiation (register budget): 0: L = 8 (types
+// 0, 3, 12, 13), 1: L = 16 (6, 7, 4), 2: L = 32 (8, 9, 10, 11, 5).
+__device__ __forceinline__ int reg_kind(int t) {
+  switch (t) {
+    case 0: case 3: case 12: case 13: return 0;
+    case 6: case 7: case 4: return 1;
+    case 8: case 9: case 10: case 11: case 5: return 2;
+    default: return -1;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : (KIND == 1 ? 2 : 1)) k_idct_small(const BatchDev B) {
   __shared__ uint16_t s_list[1024];
-  __shared__ uint32_t s_count;
+  __shared__ uint32_t s_cnt[28], s_start[28], s_fill[28];
   const uint32_t stream = blockIdx.x;
   if (B.status[stream] != 0) return;
   const StreamDev sd = B.streams[stream];
@@ -1392,137 +1517,207 @@ __global__ void __launch_bounds__(kSmallThreads) k_idct_small(const BatchDev B) 
   const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
   const uint8_t* tmap = B.blob + F.transform_off;
-  if (threadIdx.x == 0) s_count = 0;
+  if (threadIdx.x < 28) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // counting sort of the group's first-blocks by (lane class, transform type): lanes of a warp mostly share a type
+  for (uint32_t pos = threadIdx.x; pos < gw * gh; pos += blockDim.x) {
+    const uint32_t by = pos / gw, bx = pos - by * gw;
+    const uint32_t raw_t = tmap[size_t(by0 + by) * F.xb + bx0 + bx];
+    if (raw_t >= 128 && reg_kind(raw_t & 127) == KIND) atomicAdd(&s_cnt[raw_t & 127], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int order[12] = {0, 3, 12, 13, 6, 7, 8, 9, 4, 10, 11, 5};
+    uint32_t acc = 0;
+    for (int i = 0; i < 12; i++) {
+      s_start[order[i]] = acc;
+      s_fill[order[i]] = acc;
+      acc += s_cnt[order[i]];
+    }
+  }
   __syncthreads();
   for (uint32_t pos = threadIdx.x; pos < gw * gh; pos += blockDim.x) {
     const uint32_t by = pos / gw, bx = pos - by * gw;
     const uint32_t raw_t = tmap[size_t(by0 + by) * F.xb + bx0 + bx];
-    if (raw_t >= 128 && is_small_reg_type(raw_t & 127)) s_list[atomicAdd(&s_count, 1u)] = uint16_t(bx | (by << 5));
+    if (raw_t >= 128 && reg_kind(raw_t & 127) == KIND) s_list[atomicAdd(&s_fill[raw_t & 127], 1u)] = uint16_t(bx | (by << 5));
   }
   __syncthreads();
-  const uint32_t count = s_count;
+  const uint32_t begin8 = 0, begin16 = s_start[4], begin32 = s_start[5], end_all = s_start[5] + s_cnt[5];
   const int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
   const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
   const int8_t* ytob = reinterpret_cast<const int8_t*>(B.blob + F.ytob_off);
   const uint32_t* block_off = B.block_off + F.block_base;
-  const uint32_t r = threadIdx.x & 7;  // storage row owned by this thread
-  const uint32_t gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes that own one block (groups may diverge on the type)
   const float bias0 = F.quant_biases[0], bias1 = F.quant_biases[1], bias2 = F.quant_biases[2], bias3 = F.quant_biases[3];
-  // all lanes of a warp iterate together (shuffles need full participation); tail blocks are clamped + masked
-  const uint32_t iters = (count + kSmallThreads / 8 - 1) / (kSmallThreads / 8);
-  for (uint32_t it = 0; it < iters; it++) {
-    const uint32_t li = it * (kSmallThreads / 8) + (threadIdx.x >> 3);
-    const bool valid = li < count;
-    const uint32_t e = s_list[valid ? li : 0];
+
+  auto setup_ctx = [&](uint32_t e, RegBlockCtx& X, const float* (&lfp)[3], int& t) {
     const uint32_t bx = e & 31, by = e >> 5;
     const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
-    const int t = tmap[bidx] & 127;
-    const uint32_t off = block_off[bidx] + r * 8;
+    t = tmap[bidx] & 127;
     const int qt = c_qtable[t];
-    const float* mat = (F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt])
-                                               : B.dequant_default + B.dequant_default_off[qt]) + r * 8;
+    X.coeffs = group_coeffs + block_off[bidx];
+    X.mat = F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt]) : B.dequant_default + B.dequant_default_off[qt];
+    X.num_coeffs = uint32_t(c_cov_x[t]) * c_cov_y[t] * 64;
     const size_t cidx = size_t((by0 + by) >> 3) * F.cxb + ((bx0 + bx) >> 3);
-    const float x_cc = F.base_correlation_x + float(ytox[cidx]) / float(F.color_factor);
-    const float b_cc = F.base_correlation_b + float(ytob[cidx]) / float(F.color_factor);
-    const float sy = F.inv_global_scale / float(rq[bidx]), sx = sy * F.x_dm, sb = sy * F.b_dm;
-    float v[3][8];
-    {
-      const int4* qp[3] = {reinterpret_cast<const int4*>(group_coeffs + off), reinterpret_cast<const int4*>(group_coeffs + kGroupCoeffs + off),
-                           reinterpret_cast<const int4*>(group_coeffs + 2 * kGroupCoeffs + off)};
-      int q[3][8];
-      float m[3][8];
+    X.x_cc = F.base_correlation_x + float(ytox[cidx]) / float(F.color_factor);
+    X.b_cc = F.base_correlation_b + float(ytob[cidx]) / float(F.color_factor);
+    X.sy = F.inv_global_scale / float(rq[bidx]);
+    X.sx = X.sy * F.x_dm;
+    X.sb = X.sy * F.b_dm;
+    X.bias0 = bias0; X.bias1 = bias1; X.bias2 = bias2; X.bias3 = bias3;
+    X.plane = B.planes_a + F.plane_base + (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
+    X.plane_size = F.plane_size;
+    X.plane_stride = F.plane_stride;
+    for (int c = 0; c < 3; c++) lfp[c] = reinterpret_cast<const float*>(B.blob + F.lf_off[c]) + bidx;
+  };
+
+  // ---------------- class 0: 8 lanes per block ----------------
+  {
+    const uint32_t r = threadIdx.x & 7;
+    const uint32_t gmask = 0xffu << (threadIdx.x & 24);
+    const uint32_t count = begin16 - begin8;
+    const uint32_t iters = (count + kSmallThreads / 8 - 1) / (kSmallThreads / 8);
+    for (uint32_t it = 0; it < iters; it++) {
+      const uint32_t li = it * (kSmallThreads / 8) + (threadIdx.x >> 3);
+      const bool valid = li < count;
+      RegBlockCtx X;
+      const float* lfp[3];
+      int t;
+      setup_ctx(s_list[begin8 + (valid ? li : 0)], X, lfp, t);
+      if constexpr (KIND == 1) {
+        if (t == 6) reg_dct_block<8, 16, true>(X, lfp, F.xb, r, gmask, valid);
+        else reg_dct_block<8, 16, false>(X, lfp, F.xb, r, gmask, valid);
+      } else if constexpr (KIND == 2) {
+        if (t == 8) reg_dct_block<8, 32, true>(X, lfp, F.xb, r, gmask, valid);
+        else reg_dct_block<8, 32, false>(X, lfp, F.xb, r, gmask, valid);
+      } else if (t == 0) {
+        reg_dct_block<8, 8, true>(X, lfp, F.xb, r, gmask, valid);
+      } else {
+        // DCT4x4 / DCT4x8 / DCT8x4: all three channels at once (64 coefficients each)
+        float v[3][8];
+        {
+          int q[3][8];
+          float m[3][8];
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const int4 a = qp[c][0], b = qp[c][1];
-        q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
-        q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
-        const float4 ma = __ldg(reinterpret_cast<const float4*>(mat + c * 64)), mb = __ldg(reinterpret_cast<const float4*>(mat + c * 64) + 1);
-        m[c][0] = ma.x; m[c][1] = ma.y; m[c][2] = ma.z; m[c][3] = ma.w;
-        m[c][4] = mb.x; m[c][5] = mb.y; m[c][6] = mb.z; m[c][7] = mb.w;
-      }
+          for (int c = 0; c < 3; c++) {
+            const int4* qp = reinterpret_cast<const int4*>(X.coeffs + size_t(c) * kGroupCoeffs + r * 8);
+            const int4 a = qp[0], b = qp[1];
+            q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
+            q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
+            const float4* mp = reinterpret_cast<const float4*>(X.mat + c * 64 + r * 8);
+            const float4 ma = __ldg(mp), mb = __ldg(mp + 1);
+            m[c][0] = ma.x; m[c][1] = ma.y; m[c][2] = ma.z; m[c][3] = ma.w;
+            m[c][4] = mb.x; m[c][5] = mb.y; m[c][6] = mb.z; m[c][7] = mb.w;
+          }
 #pragma unroll
-      for (int j = 0; j < 8; j++) {  // group.rs:100-133
-        const float dy = adjust_quant_bias(q[1][j], bias1, bias3) * (m[1][j] * sy);
-        const float dxc = adjust_quant_bias(q[0][j], bias0, bias3) * (m[0][j] * sx);
-        const float dbc = adjust_quant_bias(q[2][j], bias2, bias3) * (m[2][j] * sb);
-        v[1][j] = dy;
-        v[0][j] = fmaf(x_cc, dy, dxc);
-        v[2][j] = fmaf(b_cc, dy, dbc);
+          for (int j = 0; j < 8; j++) {  // group.rs:100-133
+            const float dy = adjust_quant_bias(q[1][j], bias1, bias3) * (m[1][j] * X.sy);
+            const float dxc = adjust_quant_bias(q[0][j], bias0, bias3) * (m[0][j] * X.sx);
+            const float dbc = adjust_quant_bias(q[2][j], bias2, bias3) * (m[2][j] * X.sb);
+            v[1][j] = dy;
+            v[0][j] = fmaf(X.x_cc, dy, dxc);
+            v[2][j] = fmaf(X.b_cc, dy, dbc);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          float (&w)[8] = v[c];
+          if (r == 0) w[0] = lfp[c][0];
+          float* plane = X.plane + size_t(c) * X.plane_size;
+          const uint32_t base = threadIdx.x & 24;
+          if (t == 12 || t == 13) {
+            // DC pair (transform.rs:617-620): dcs = [c0 + c8, c0 - c8], c0 = row 0 col 0, c8 = row 1 col 0
+            const float c0 = __shfl_sync(gmask, w[0], base), c8 = __shfl_sync(gmask, w[0], base + 1);
+            if (r == 0) w[0] = c0 + c8;
+            if (r == 1) w[0] = c0 - c8;
+            idct1d<8>(w);             // t=13: over vf -> y; t=12: over hf -> x
+            transposeN<8>(w, r, gmask);  // thread j holds entries i = h + 2 f (f = hf for 8x4, vf for 4x8)
+            float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};
+            idct1d<4>(a4);
+            idct1d<4>(b4);
+            if (t == 13) {  // DCT8X4: thread y: half 0 -> x 0..3, half 1 -> x 4..7
+              if (valid) {
+                float4* d = reinterpret_cast<float4*>(plane + size_t(r) * X.plane_stride);
+                d[0] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                d[1] = make_float4(b4[0], b4[1], b4[2], b4[3]);
+              }
+            } else {  // DCT4X8: thread x holds the column: half 0 -> y 0..3, half 1 -> y 4..7
+              w[0] = a4[0]; w[1] = a4[1]; w[2] = a4[2]; w[3] = a4[3];
+              w[4] = b4[0]; w[5] = b4[1]; w[6] = b4[2]; w[7] = b4[3];
+              transposeN<8>(w, r, gmask);
+              if (valid) {
+                float4* d = reinterpret_cast<float4*>(plane + size_t(r) * X.plane_stride);
+                d[0] = make_float4(w[0], w[1], w[2], w[3]);
+                d[1] = make_float4(w[4], w[5], w[6], w[7]);
+              }
+            }
+          } else {  // DCT4X4 (transform.rs:579-612): thread i = qy + 2 hf holds j = qx + 2 vf
+            const float c00 = __shfl_sync(gmask, w[0], base), c01 = __shfl_sync(gmask, w[1], base);
+            const float c10 = __shfl_sync(gmask, w[0], base + 1), c11 = __shfl_sync(gmask, w[1], base + 1);
+            if (r == 0) {
+              w[0] = c00 + c01 + c10 + c11;  // quadrant (0,0)
+              w[1] = c00 + c01 - c10 - c11;  // quadrant (0,1)
+            }
+            if (r == 1) {
+              w[0] = c00 - c01 + c10 - c11;  // quadrant (1,0)
+              w[1] = c00 - c01 - c10 + c11;  // quadrant (1,1)
+            }
+            float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};  // over vf for qx = 0 / 1
+            idct1d<4>(a4);
+            idct1d<4>(b4);
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+              w[2 * y] = a4[y];
+              w[2 * y + 1] = b4[y];
+            }
+            transposeN<8>(w, r, gmask);  // thread j = qx + 2 y holds i = qy + 2 hf
+            float p4[4] = {w[0], w[2], w[4], w[6]}, q4[4] = {w[1], w[3], w[5], w[7]};  // over hf for qy = 0 / 1
+            idct1d<4>(p4);
+            idct1d<4>(q4);
+            if (valid) {
+              const uint32_t qx = r & 1, y = r >> 1;
+              *reinterpret_cast<float4*>(plane + size_t(y) * X.plane_stride + qx * 4) = make_float4(p4[0], p4[1], p4[2], p4[3]);
+              *reinterpret_cast<float4*>(plane + size_t(4 + y) * X.plane_stride + qx * 4) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+            }
+          }
+        }
       }
     }
-    const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      float (&w)[8] = v[c];
-      const float lf = reinterpret_cast<const float*>(B.blob + F.lf_off[c])[bidx];
-      if (r == 0) w[0] = lf;  // LLF of a 1x1 varblock: coefficient 0 <- LF sample
-      float* plane = (c == 0 ? B.planes_a + F.plane_base : (c == 1 ? B.planes_a + F.plane_base + F.plane_size : B.planes_a + F.plane_base + 2 * F.plane_size)) + px0;
-      if (t == 0) {  // DCT8x8: storage [hf = r][vf]
-        idct1d<8>(w);
-        transpose8(w, r, gmask);
-        idct1d<8>(w);  // thread r = y now holds x = 0..7
-        if (valid) {
-          float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
-          d[0] = make_float4(w[0], w[1], w[2], w[3]);
-          d[1] = make_float4(w[4], w[5], w[6], w[7]);
-        }
-      } else if (t == 12 || t == 13) {
-        // DC pair (transform.rs:617-620): dcs = [c0 + c8, c0 - c8], c0 = row 0 col 0, c8 = row 1 col 0
-        const float c0 = __shfl_sync(gmask, w[0], (threadIdx.x & 24) + 0), c8 = __shfl_sync(gmask, w[0], (threadIdx.x & 24) + 1);
-        if (r == 0) w[0] = c0 + c8;
-        if (r == 1) w[0] = c0 - c8;
-        idct1d<8>(w);       // t=13: over vf -> y; t=12: over hf -> x
-        transpose8(w, r, gmask);   // thread j holds entries i = h + 2 * f (f = hf for 8x4, vf for 4x8)
-        float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};
-        idct1d<4>(a4);
-        idct1d<4>(b4);
-        if (t == 13) {  // DCT8X4: thread y: half 0 -> x 0..3, half 1 -> x 4..7
-          if (valid) {
-            float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
-            d[0] = make_float4(a4[0], a4[1], a4[2], a4[3]);
-            d[1] = make_float4(b4[0], b4[1], b4[2], b4[3]);
-          }
-        } else {  // DCT4X8: thread x holds the column: half 0 -> y 0..3, half 1 -> y 4..7
-          w[0] = a4[0]; w[1] = a4[1]; w[2] = a4[2]; w[3] = a4[3];
-          w[4] = b4[0]; w[5] = b4[1]; w[6] = b4[2]; w[7] = b4[3];
-          transpose8(w, r, gmask);
-          if (valid) {
-            float4* d = reinterpret_cast<float4*>(plane + size_t(r) * F.plane_stride);
-            d[0] = make_float4(w[0], w[1], w[2], w[3]);
-            d[1] = make_float4(w[4], w[5], w[6], w[7]);
-          }
-        }
-      } else {  // DCT4X4 (transform.rs:579-612): thread i = qy + 2 hf holds j = qx + 2 vf
-        const uint32_t base = threadIdx.x & 24;
-        const float c00 = __shfl_sync(gmask, w[0], base), c01 = __shfl_sync(gmask, w[1], base);
-        const float c10 = __shfl_sync(gmask, w[0], base + 1), c11 = __shfl_sync(gmask, w[1], base + 1);
-        if (r == 0) {
-          w[0] = c00 + c01 + c10 + c11;  // quadrant (0,0)
-          w[1] = c00 + c01 - c10 - c11;  // quadrant (0,1)
-        }
-        if (r == 1) {
-          w[0] = c00 - c01 + c10 - c11;  // quadrant (1,0)
-          w[1] = c00 - c01 - c10 + c11;  // quadrant (1,1)
-        }
-        float a4[4] = {w[0], w[2], w[4], w[6]}, b4[4] = {w[1], w[3], w[5], w[7]};  // over vf for qx = 0 / 1
-        idct1d<4>(a4);
-        idct1d<4>(b4);
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-          w[2 * y] = a4[y];
-          w[2 * y + 1] = b4[y];
-        }
-        transpose8(w, r, gmask);  // thread j = qx + 2 y holds i = qy + 2 hf
-        float p4[4] = {w[0], w[2], w[4], w[6]}, q4[4] = {w[1], w[3], w[5], w[7]};  // over hf for qy = 0 / 1
-        idct1d<4>(p4);
-        idct1d<4>(q4);
-        if (valid) {
-          const uint32_t qx = r & 1, y = r >> 1;
-          *reinterpret_cast<float4*>(plane + size_t(y) * F.plane_stride + qx * 4) = make_float4(p4[0], p4[1], p4[2], p4[3]);
-          *reinterpret_cast<float4*>(plane + size_t(4 + y) * F.plane_stride + qx * 4) = make_float4(q4[0], q4[1], q4[2], q4[3]);
-        }
+  }
+  // ---------------- class 1: 16 lanes per block ----------------
+  {
+    const uint32_t r = threadIdx.x & 15;
+    const uint32_t gmask = 0xffffu << (threadIdx.x & 16);
+    const uint32_t count = begin32 - begin16;
+    const uint32_t iters = (count + kSmallThreads / 16 - 1) / (kSmallThreads / 16);
+    for (uint32_t it = 0; it < iters; it++) {
+      const uint32_t li = it * (kSmallThreads / 16) + (threadIdx.x >> 4);
+      const bool valid = li < count;
+      RegBlockCtx X;
+      const float* lfp[3];
+      int t;
+      setup_ctx(s_list[begin16 + (valid ? li : 0)], X, lfp, t);
+      if constexpr (KIND == 1) {
+        reg_dct_block<16, 16, true>(X, lfp, F.xb, r, gmask, valid);
+      } else if constexpr (KIND == 2) {
+        if (t == 10) reg_dct_block<16, 32, true>(X, lfp, F.xb, r, gmask, valid);
+        else reg_dct_block<16, 32, false>(X, lfp, F.xb, r, gmask, valid);
       }
+    }
+  }
+  // ---------------- class 2: 32 lanes per block ----------------
+  {
+    const uint32_t r = threadIdx.x & 31;
+    const uint32_t count = end_all - begin32;
+    const uint32_t iters = (count + kSmallThreads / 32 - 1) / (kSmallThreads / 32);
+    for (uint32_t it = 0; it < iters; it++) {
+      const uint32_t li = it * (kSmallThreads / 32) + (threadIdx.x >> 5);
+      const bool valid = li < count;
+      RegBlockCtx X;
+      const float* lfp[3];
+      int t;
+      setup_ctx(s_list[begin32 + (valid ? li : 0)], X, lfp, t);
+      if constexpr (KIND == 2) reg_dct_block<32, 32, true>(X, lfp, F.xb, r, 0xffffffffu, valid);
     }
   }
 }
@@ -2149,8 +2344,10 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
-  k_idct_small<<<B.num_streams, kSmallThreads, 0, stream>>>(B);
-  launches++;
+  k_idct_small<0><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  k_idct_small<1><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  k_idct_small<2><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  launches += 3;
   k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
   launches++;
   mark(3);
