@@ -87,6 +87,9 @@ struct PinnedArena {
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished frame ranges overlaps the filtering of later ranges
+  static constexpr int kMaxRanges = 8;
+  cudaEvent_t range_done[kMaxRanges] = {nullptr}, copy_done = nullptr;
   DevBuf dequant_default, dequant_default_off, natural_orders, natural_order_off;
   // Pools reused by successive batches (one live batch per context): device
   // intermediates and the pinned staging arena survive jxg_batch_end so that a
@@ -161,6 +164,9 @@ int jxg_init(int device, void** out_ctx) {
   auto ctx = std::make_unique<Context>();
   ctx->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : ctx->range_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
   // constant tables
   std::vector<float> wc(9 * 128, 0.0f), rs(6 * 32, 0.0f);
   for (int l = 1; l <= 8; l++) {
@@ -204,6 +210,10 @@ void jxg_shutdown(void* c) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->range_done)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   delete ctx;
 }
 
@@ -419,7 +429,7 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   return JXG_OK;
 }
 
-static int launch(Batch* b, cudaStream_t s) {
+static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   BatchDev B;
   memset(&B, 0, sizeof(B));
   B.blob = static_cast<const uint8_t*>(b->d_blob.p);
@@ -446,21 +456,50 @@ static int launch(Batch* b, cudaStream_t s) {
   B.natural_orders = static_cast<const uint32_t*>(b->ctx->natural_orders.p);
   B.natural_order_off = static_cast<const uint32_t*>(b->ctx->natural_order_off.p);
   size_t coeff_bytes = size_t(b->total_groups) * 3 * kGroupCoeffs * 4;
+  cudaEvent_t* ev = b->profile ? b->stage_ev : nullptr;
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
-                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop,
-                                         b->profile ? b->stage_ev : nullptr, static_cast<const uint32_t*>(b->d_ftiles.p),
-                                         b->fused_prefix.back(), b->filter_cfg_mask, b->lean_all_420));
+                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
+                                         static_cast<const uint32_t*>(b->d_ftiles.p), b->fused_prefix.back(),
+                                         b->filter_cfg_mask, b->lean_all_420));
+  if (b->debug_stop == 0) {
+    // Fused filter + colour + store, launched per range of frames; each finished range is copied to the host
+    // on the copy stream while the next range is being filtered.
+    Context* cx = b->ctx;
+    const uint32_t nf = uint32_t(b->frames.size());
+    const uint32_t nr = copy_to_host ? std::min<uint32_t>(Context::kMaxRanges, nf) : 1;
+    const uint32_t* fp = static_cast<const uint32_t*>(b->d_ftiles.p);
+    if (ev) {
+      for (int i = 4; i <= 6; i++) cudaEventRecord(ev[i], s);
+    }
+    for (uint32_t r = 0; r < nr; r++) {
+      const uint32_t f0 = uint32_t(uint64_t(nf) * r / nr), f1 = uint32_t(uint64_t(nf) * (r + 1) / nr);
+      const uint32_t t0 = b->fused_prefix[f0], t1 = b->fused_prefix[f1];
+      b->launches += uint64_t(launch_filter_range(B, fp, t0, t1 - t0, b->filter_cfg_mask, s));
+      if (copy_to_host) {
+        CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
+        CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->range_done[r], 0));
+        for (uint32_t f = f0; f < f1; f++) {
+          const FrameOut& fo = b->outs[f];
+          if (fo.is_device) continue;
+          CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.bytes, cudaMemcpyDeviceToHost, cx->copy_stream));
+          b->d2h += fo.bytes;
+        }
+      }
+    }
+    if (ev) {
+      cudaEventRecord(ev[7], s);
+      cudaEventRecord(ev[8], s);
+    }
+    if (copy_to_host) {  // the launching stream joins the copy stream so that ev1 / stream sync cover the copies
+      CUDA_TRY(cudaEventRecord(cx->copy_done, cx->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, cx->copy_done, 0));
+    }
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
-static int copy_out(Batch* b, cudaStream_t s) {
-  for (size_t f = 0; f < b->outs.size(); f++) {
-    const FrameOut& fo = b->outs[f];
-    if (fo.is_device) continue;
-    CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.bytes, cudaMemcpyDeviceToHost, s));
-    b->d2h += fo.bytes;
-  }
+static int copy_status(Batch* b, cudaStream_t s) {
   CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
   return 0;
 }
@@ -496,8 +535,8 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
   if (int r = upload(b->d_ftiles, b->fused_prefix, s, &b->h2d)) return r;
   b->uploaded = true;
-  if (int r = launch(b, s)) return r;
-  if (int r = copy_out(b, s)) return r;
+  if (int r = launch(b, s, true)) return r;
+  if (int r = copy_status(b, s)) return r;
   CUDA_TRY(cudaEventRecord(b->ev1, s));
   return JXG_OK;
 }
@@ -508,7 +547,7 @@ int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
   CUDA_TRY(cudaEventRecord(b->ev0, s));
-  if (int r = launch(b, s)) return r;
+  if (int r = launch(b, s, false)) return r;
   CUDA_TRY(cudaEventRecord(b->ev1, s));
   CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
   return JXG_OK;

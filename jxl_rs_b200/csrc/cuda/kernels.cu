@@ -1972,6 +1972,8 @@ constexpr int kTW = 64, kTH = 32, kFilterThreads = 512;
 struct FusedTiles {
   const uint32_t* tile_prefix;  // [num_frames + 1], kTW x kTH tiles
   uint32_t num_frames;
+  uint32_t tile_begin;          // first tile of this launch (frame ranges are launched separately so that the
+                                // D2H copy of finished frames overlaps the filtering of the next ones)
 };
 
 template <bool GAB, int EPF>
@@ -2114,15 +2116,16 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
   float* bufB = smem + 3 * NC;
   float* maps = smem + 6 * NC;
   float* sig = maps + C::NMAPS * NC;
+  const uint32_t tile_id = blockIdx.x + T.tile_begin;
   uint32_t lo = 0, hi = T.num_frames;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
-    if (T.tile_prefix[mid] <= blockIdx.x) lo = mid;
+    if (T.tile_prefix[mid] <= tile_id) lo = mid;
     else hi = mid;
   }
   const FrameDev& F = B.frames[lo];
   if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return;  // another instantiation handles this frame
-  const uint32_t local = blockIdx.x - T.tile_prefix[lo];
+  const uint32_t local = tile_id - T.tile_prefix[lo];
   const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
   const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
   const int w = int(F.width), h = int(F.height);
@@ -2352,28 +2355,7 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   launches++;
   mark(3);
   if (debug_stop == 2) return launches;
-  if (debug_stop != 3) {  // default: fused filter + colour + store kernel
-    FusedTiles FT{fused_prefix, B.num_frames};
-    mark(4);
-    mark(5);
-    mark(6);
-    // one launch per filter configuration present in the batch (CTAs of other frames exit at once)
-    for (int cfg = 0; cfg < 8; cfg++) {
-      if (!(filter_cfg_mask & (1u << cfg))) continue;
-      switch (cfg) {
-        case 0: launch_filters<false, 0>(B, FT, fused_tiles, stream); break;
-        case 1: launch_filters<false, 1>(B, FT, fused_tiles, stream); break;
-        case 2: launch_filters<false, 2>(B, FT, fused_tiles, stream); break;
-        case 3: launch_filters<false, 3>(B, FT, fused_tiles, stream); break;
-        case 4: launch_filters<true, 0>(B, FT, fused_tiles, stream); break;
-        case 5: launch_filters<true, 1>(B, FT, fused_tiles, stream); break;
-        case 6: launch_filters<true, 2>(B, FT, fused_tiles, stream); break;
-        default: launch_filters<true, 3>(B, FT, fused_tiles, stream); break;
-      }
-      launches++;
-    }
-    mark(7);
-    mark(8);
+  if (debug_stop != 3) {  // default: fused filter + colour + store kernel, launched per frame range by the caller
     if (final_planes) *final_planes = nullptr;
     return launches;
   }
@@ -2414,6 +2396,30 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   launches++;
   mark(8);
   if (final_planes) *final_planes = cur;
+  return launches;
+}
+
+// Fused filter/colour/store kernel over tiles [tile_begin, tile_begin + tile_count): one launch per filter
+// configuration present in the batch (CTAs of frames with another configuration exit at once).
+int launch_filter_range(const BatchDev& B, const uint32_t* fused_prefix, uint32_t tile_begin, uint32_t tile_count,
+                        uint32_t filter_cfg_mask, cudaStream_t stream) {
+  int launches = 0;
+  if (!tile_count) return 0;
+  FusedTiles FT{fused_prefix, B.num_frames, tile_begin};
+  for (int cfg = 0; cfg < 8; cfg++) {
+    if (!(filter_cfg_mask & (1u << cfg))) continue;
+    switch (cfg) {
+      case 0: launch_filters<false, 0>(B, FT, tile_count, stream); break;
+      case 1: launch_filters<false, 1>(B, FT, tile_count, stream); break;
+      case 2: launch_filters<false, 2>(B, FT, tile_count, stream); break;
+      case 3: launch_filters<false, 3>(B, FT, tile_count, stream); break;
+      case 4: launch_filters<true, 0>(B, FT, tile_count, stream); break;
+      case 5: launch_filters<true, 1>(B, FT, tile_count, stream); break;
+      case 6: launch_filters<true, 2>(B, FT, tile_count, stream); break;
+      default: launch_filters<true, 3>(B, FT, tile_count, stream); break;
+    }
+    launches++;
+  }
   return launches;
 }
 

@@ -13,5 +13,7 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
                     cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
                     bool lean_all_420);
 constexpr int kFusedTileW = 64, kFusedTileH = 32;
+int launch_filter_range(const BatchDev& B, const uint32_t* fused_prefix, uint32_t tile_begin, uint32_t tile_count,
+                        uint32_t filter_cfg_mask, cudaStream_t stream);
 constexpr int kNumStages = 8;  // memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store
 }  // namespace jxgpu

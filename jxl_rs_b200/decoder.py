@@ -175,3 +175,55 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
     batch.wait()
     batch.close()
     return outs
+
+
+class PipelinedDecoder:
+    """Streaming decode of many batches: `depth` contexts (each with its own CUDA streams, pinned
+    staging arena and device pools) are used round-robin, so that the host front-end work
+    (parse + staging) of batch k+1 overlaps the kernels and the D2H copies of batch k.
+    This is the serving-shaped entry point (many independent images in flight)."""
+
+    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0):
+        import os
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        self.ctxs = [JxgContext(device) for _ in range(depth)]
+        self.depth = depth
+        self.pool = ThreadPoolExecutor(max_workers=workers or min(64, os.cpu_count() or 8))
+        self.inflight = deque()
+        self.k = 0
+        self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0, "kernel_launches": 0}
+
+    def _retire(self):
+        b = self.inflight.popleft()
+        b.wait()
+        self.last_stats = b.stats()
+        b.close()
+
+    def submit(self, files, outs, fmt: int = abi.FORMAT_RGB_U8, out_is_device: bool = False):
+        """files: list of .jxl byte strings; outs: list of (data_ptr, row_stride). Returns once the batch is
+        queued on the device; its outputs are complete after the next-but-one submit() or drain()."""
+        futs = [self.pool.submit(ParsedFrame, f) for f in files]
+        if len(self.inflight) == self.depth:
+            self._retire()
+        ctx = self.ctxs[self.k % self.depth]
+        self.k += 1
+        b = Batch(ctx, len(files))
+        for fut, (ptr, stride) in zip(futs, outs):
+            b.add(fut.result(), ptr, stride, fmt, out_is_device)
+        b.run()
+        self.inflight.append(b)
+
+    def drain(self):
+        while self.inflight:
+            self._retire()
+
+    def decode(self, files, outs, fmt: int = abi.FORMAT_RGB_U8, out_is_device: bool = False):
+        self.submit(files, outs, fmt, out_is_device)
+        self.drain()
+
+    def close(self):
+        self.drain()
+        self.pool.shutdown()
+        for c in self.ctxs:
+            c.close()
