@@ -46,12 +46,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def frame_seeds(n, rank):
+    """Frame i of rank r uses seed 2000 + r*n + i: ranks decode disjoint frames (weak scaling, no collective)."""
+    return [2000 + rank * n + i for i in range(n)]
+
+
 def make_frames(args, rank):
     """Synthetic .jxl byte strings for this rank (outside every timed region)."""
     import synth
     n = args.frames
     uniq = n if args.unique <= 0 else min(args.unique, n)
-    seeds = [2000 + rank * n + i for i in range(uniq)]
+    seeds = frame_seeds(n, rank)[:uniq]
     workers = max(1, min(uniq, (os.cpu_count() or 8)))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         files = list(ex.map(lambda s: synth.encode_synthetic(args.width, args.height, s, args.distance, args.epf, 1, args.profile), seeds))

@@ -132,7 +132,8 @@ struct Batch {
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
-  std::vector<int32_t> status_host;
+  int32_t* status_host = nullptr;  // pinned: a D2H copy into pageable memory would block jxg_batch_run
+  size_t status_cap = 0, status_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
@@ -242,6 +243,7 @@ void jxg_batch_end(void* bp) {
   for (auto& e : b->stage_ev)
     if (e) cudaEventDestroy(e);
   b->ctx->batch_live = false;
+  if (b->status_host) cudaFreeHost(b->status_host);
   delete b;
 }
 
@@ -500,7 +502,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
 }
 
 static int copy_status(Batch* b, cudaStream_t s) {
-  CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(b->status_host, b->d_status.p, b->status_n * 4, cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
@@ -521,7 +523,13 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
   for (size_t f = 0; f < b->frames.size(); f++)
     b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
-  b->status_host.assign(b->streams.size(), 0);
+  b->status_n = b->streams.size();
+  if (b->status_n > b->status_cap) {
+    if (b->status_host) cudaFreeHost(b->status_host);
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&b->status_host), b->status_n * 4, cudaHostAllocDefault));
+    b->status_cap = b->status_n;
+  }
+  memset(b->status_host, 0, b->status_n * 4);
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
   b->h2d += b->blob.size;
@@ -549,7 +557,7 @@ int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   if (int r = launch(b, s, false)) return r;
   CUDA_TRY(cudaEventRecord(b->ev1, s));
-  CUDA_TRY(cudaMemcpyAsync(b->status_host.data(), b->d_status.p, b->status_host.size() * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(b->status_host, b->d_status.p, b->status_n * 4, cudaMemcpyDeviceToHost, s));
   return JXG_OK;
 }
 
@@ -561,7 +569,7 @@ int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_grou
   CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
-  for (size_t i = 0; i < b->status_host.size(); i++)
+  for (size_t i = 0; i < b->status_n; i++)
     if (b->status_host[i] != 0) {
       if (first_bad_frame) *first_bad_frame = b->streams[i].frame;
       if (first_bad_group) *first_bad_group = b->streams[i].group;
