@@ -98,6 +98,10 @@ struct Context {
   DevBuf d_blob, d_frames, d_sections, d_streams, d_streams_lean, d_streams_fast, d_streams_slow, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
       d_planes_b, d_status, d_out;
   bool batch_live = false;
+  // pinned status readback buffer, owned by the context: cudaHostAlloc / cudaFreeHost synchronise the whole
+  // device, so they must not happen per batch when batches of several contexts are in flight
+  int32_t* status_host = nullptr;
+  size_t status_cap = 0;
 };
 
 struct FrameOut {
@@ -132,8 +136,8 @@ struct Batch {
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
-  int32_t* status_host = nullptr;  // pinned: a D2H copy into pageable memory would block jxg_batch_run
-  size_t status_cap = 0, status_n = 0;
+  int32_t* status_host = nullptr;  // pinned (context-owned): a D2H copy into pageable memory would block jxg_batch_run
+  size_t status_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
@@ -215,6 +219,7 @@ void jxg_shutdown(void* c) {
   for (auto& e : ctx->range_done)
     if (e) cudaEventDestroy(e);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->status_host) cudaFreeHost(ctx->status_host);
   delete ctx;
 }
 
@@ -243,7 +248,6 @@ void jxg_batch_end(void* bp) {
   for (auto& e : b->stage_ev)
     if (e) cudaEventDestroy(e);
   b->ctx->batch_live = false;
-  if (b->status_host) cudaFreeHost(b->status_host);
   delete b;
 }
 
@@ -524,11 +528,13 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   for (size_t f = 0; f < b->frames.size(); f++)
     b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
   b->status_n = b->streams.size();
-  if (b->status_n > b->status_cap) {
-    if (b->status_host) cudaFreeHost(b->status_host);
-    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&b->status_host), b->status_n * 4, cudaHostAllocDefault));
-    b->status_cap = b->status_n;
+  if (b->status_n > b->ctx->status_cap) {
+    if (b->ctx->status_host) cudaFreeHost(b->ctx->status_host);
+    size_t cap = std::max<size_t>(b->status_n * 2, 1 << 16);
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&b->ctx->status_host), cap * 4, cudaHostAllocDefault));
+    b->ctx->status_cap = cap;
   }
+  b->status_host = b->ctx->status_host;
   memset(b->status_host, 0, b->status_n * 4);
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
