@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--epf", type=int, default=2)
     ap.add_argument("--unique", type=int, default=0, help="encode only this many distinct frames and repeat them (0 = all distinct)")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
-    ap.add_argument("--inflight", type=int, default=1, help="resident batches alternated by the device-resident loop")
+    ap.add_argument("--inflight", type=int, default=2, help="resident batches alternated by the device-resident loop")
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the pipelined end-to-end decode")
     return ap.parse_args()
 

@@ -162,6 +162,12 @@ void jxg_batch_end(void* batch);
 int jxg_batch_read_coeffs(void* batch, uint32_t f, int32_t* out, size_t out_len);
 int jxg_batch_read_xyb(void* batch, uint32_t f, int stage, float* out, size_t out_len);
 
+/* Opt-in host-side staging speed-up: copies of the large inputs (LF planes, per-block maps, HF sections) into the
+ * pinned staging blob are postponed to jxg_batch_run and spread over `threads` host threads. Every pointer passed to
+ * jxg_batch_add_frame / jxg_batch_add_parsed afterwards must stay valid until jxg_batch_run returns. 0 = immediate
+ * copies (default; the contract a `&[u8]`-borrowing Rust caller gets, frame/render.rs:143). */
+int jxg_batch_set_deferred_copy(void* batch, int threads);
+
 /* Debug/parity: 0 = run everything (default), 1 = stop after the entropy kernel,
  * 2 = stop after dequant+IDCT (planes readable with stage 0). */
 int jxg_batch_set_debug_stop(void* batch, int stage);

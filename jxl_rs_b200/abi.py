@@ -66,7 +66,7 @@ EXPORTS = [
     "jxg_init", "jxg_shutdown", "jxg_batch_begin", "jxg_batch_add_frame", "jxg_batch_run", "jxg_batch_wait",
     "jxg_batch_rerun_device", "jxg_batch_end", "jxg_batch_read_coeffs", "jxg_batch_read_xyb",
     "jxg_batch_set_debug_stop", "jxg_batch_set_profile", "jxg_batch_stage_times", "jxg_batch_stats", "jxg_parse_file", "jxg_parsed_free", "jxg_parsed_desc",
-    "jxg_batch_add_parsed", "jxg_last_error",
+    "jxg_batch_add_parsed", "jxg_batch_set_deferred_copy", "jxg_last_error",
 ]
 
 _LIB = None
@@ -102,6 +102,7 @@ def load_library():
     lib.jxg_batch_read_coeffs.argtypes = [vp, C.c_uint32, vp, C.c_size_t]
     lib.jxg_batch_read_xyb.argtypes = [vp, C.c_uint32, C.c_int, vp, C.c_size_t]
     lib.jxg_batch_set_debug_stop.argtypes = [vp, C.c_int]
+    lib.jxg_batch_set_deferred_copy.argtypes = [vp, C.c_int]
     lib.jxg_batch_set_profile.argtypes = [vp, C.c_int]
     lib.jxg_batch_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.jxg_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

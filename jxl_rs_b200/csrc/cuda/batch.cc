@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -71,16 +73,45 @@ struct PinnedArena {
     cap = ncap;
     return true;
   }
+  // Deferred mode (jxg_batch_set_deferred_copy): large copies are only recorded here and executed by
+  // flush() on several host threads right before the upload; sources must stay valid until then.
+  struct Pending {
+    size_t off;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<Pending> pending;
+  int deferred_threads = 0;
   // returns offset; pads with zeros up to `align`, appends `bytes` (+ `tail_zero` zero bytes)
   int64_t append(const void* src, size_t bytes, size_t align = 16, size_t tail_zero = 0) {
     size_t off = (size + align - 1) / align * align;
     size_t end = off + bytes + tail_zero;
     if (!reserve(end)) return -1;
     memset(p + size, 0, off - size);
-    if (bytes) memcpy(p + off, src, bytes);
+    if (bytes) {
+      if (deferred_threads > 0 && bytes >= 4096) pending.push_back(Pending{off, src, bytes});
+      else memcpy(p + off, src, bytes);
+    }
     if (tail_zero) memset(p + off + bytes, 0, tail_zero);
     size = end;
     return int64_t(off);
+  }
+  void flush() {
+    if (pending.empty()) return;
+    const int nt = std::max(1, std::min<int>(deferred_threads, int(pending.size())));
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+      for (;;) {
+        const size_t i = next.fetch_add(8);
+        if (i >= pending.size()) return;
+        for (size_t j = i; j < std::min(i + 8, pending.size()); j++) memcpy(p + pending[j].off, pending[j].src, pending[j].bytes);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    pending.clear();
   }
 };
 
@@ -95,7 +126,7 @@ struct Context {
   // intermediates and the pinned staging arena survive jxg_batch_end so that a
   // steady-state decode loop does no cudaMalloc / cudaHostAlloc.
   PinnedArena blob;
-  DevBuf d_blob, d_frames, d_sections, d_streams, d_streams_lean, d_streams_fast, d_streams_slow, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
+  DevBuf d_blob, d_frames, d_sections, d_streams, d_streams_lean, d_lean_cta, d_streams_fast, d_streams_slow, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
       d_planes_b, d_status, d_out;
   bool batch_live = false;
   // pinned status readback buffer, owned by the context: cudaHostAlloc / cudaFreeHost synchronise the whole
@@ -115,13 +146,15 @@ struct Batch {
   Context* ctx;
   PinnedArena& blob;
   explicit Batch(Context* c)
-      : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams), d_streams_lean(c->d_streams_lean), d_streams_fast(c->d_streams_fast), d_streams_slow(c->d_streams_slow),
+      : ctx(c), blob(c->blob), d_blob(c->d_blob), d_frames(c->d_frames), d_sections(c->d_sections), d_streams(c->d_streams), d_streams_lean(c->d_streams_lean), d_lean_cta(c->d_lean_cta), d_streams_fast(c->d_streams_fast), d_streams_slow(c->d_streams_slow),
         d_nz_base(c->d_nz_base), d_tiles(c->d_tiles), d_ftiles(c->d_ftiles), d_coeffs(c->d_coeffs), d_block_off(c->d_block_off), d_nz(c->d_nz),
         d_planes_a(c->d_planes_a), d_planes_b(c->d_planes_b), d_status(c->d_status), d_out(c->d_out) {}
   std::vector<FrameDev> frames;
   std::vector<SectionDev> sections;
   std::vector<StreamDev> streams, streams_lean, streams_fast, streams_slow;
   bool lean_all_420 = true;
+  uint32_t lean_S = 1, lean_ctas = 0;  // k_entropy_lean schedule (see schedule_lean)
+  std::vector<uint32_t> lean_cta_first;
   std::vector<uint64_t> nz_base;
   std::vector<uint32_t> tile_prefix{0};
   std::vector<uint32_t> fused_prefix{0};
@@ -132,7 +165,7 @@ struct Batch {
   bool any_gab = false;
   int debug_stop = 0;
   // device
-  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_streams_lean, &d_streams_fast, &d_streams_slow, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
+  DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_streams_lean, &d_lean_cta, &d_streams_fast, &d_streams_slow, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
   const float* final_planes = nullptr;
@@ -230,6 +263,8 @@ int jxg_batch_begin(void* c, uint32_t n_frames_hint, void** out_batch) {
   auto b = std::make_unique<Batch>(cx);
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cx->blob.size = 0;
+  cx->blob.pending.clear();
+  cx->blob.deferred_threads = 0;
   cx->batch_live = true;
   b->frames.reserve(n_frames_hint);
   CUDA_TRY(cudaEventCreate(&b->ev0));
@@ -270,6 +305,17 @@ int jxg_batch_stage_times(void* bp, float* ms, int n) {
     if (cudaEventElapsedTime(&ms[i], b->stage_ev[i], b->stage_ev[i + 1]) != cudaSuccess) ms[i] = 0.0f;
   }
   cudaGetLastError();
+  return JXG_OK;
+}
+
+// Opt-in: copies of large inputs (LF planes, maps, HF sections) into the pinned staging blob are postponed to
+// jxg_batch_run and spread over `threads` host threads. Every pointer handed to jxg_batch_add_frame /
+// jxg_batch_add_parsed must then stay valid until jxg_batch_run returns.
+int jxg_batch_set_deferred_copy(void* bp, int threads) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || threads < 0) return JXG_ERR_ARGUMENT;
+  if (b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch already submitted");
+  b->blob.deferred_threads = threads;
   return JXG_OK;
 }
 
@@ -383,7 +429,7 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   F.first_stream = uint32_t(b->streams.size());
   for (uint32_t g = 0; g < F.num_groups; g++) {
     b->streams.push_back(StreamDev{uint32_t(b->frames.size()), g});
-    (F.num_passes != 1 ? b->streams_slow : (F.passes[0].use_prefix ? b->streams_fast : b->streams_lean)).push_back(StreamDev{uint32_t(b->frames.size()), g});
+    (F.num_passes != 1 ? b->streams_slow : ((F.passes[0].use_prefix || F.passes[0].shift != 0) ? b->streams_fast : b->streams_lean)).push_back(StreamDev{uint32_t(b->frames.size()), g});
     b->nz_base.push_back(b->nz_bytes);
     b->nz_bytes += size_t(F.num_passes) * 3072;
   }
@@ -435,6 +481,50 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   return JXG_OK;
 }
 
+// Schedule of the persistent entropy lanes (k_entropy_lean). A stream's cost is proportional to its section
+// length; each frame's streams are ordered longest first (longest-processing-time rule) and the frame gets about
+// twice the lanes a perfect packing into "longest stream"-sized bins would need, so that every lane ends close to
+// the longest stream while the CTAs of one frame keep that frame's tables in L1.
+static void schedule_lean(Batch* b) {
+  if (b->streams_lean.empty() || b->lean_ctas) return;
+  auto len_of = [&](const StreamDev& sd) { return b->sections[b->frames[sd.frame].section_base + sd.group].len; };
+  std::stable_sort(b->streams_lean.begin(), b->streams_lean.end(), [&](const StreamDev& x, const StreamDev& y) {
+    return x.frame != y.frame ? x.frame < y.frame : len_of(x) > len_of(y);
+  });
+  float mul = 2.0f;
+  if (const char* e = getenv("JXG_ENTROPY_LANES_MUL")) mul = float(atof(e));  // experiment knobs
+  const size_t nf = b->frames.size();
+  std::vector<uint32_t> lanes(nf, 0);
+  for (auto& F : b->frames) F.lean_first = F.lean_count = F.lean_cta_first = F.lean_ctas = 0;
+  uint64_t total_lanes = 0;
+  for (size_t i = 0; i < b->streams_lean.size();) {
+    const uint32_t f = b->streams_lean[i].frame;
+    size_t j = i;
+    uint64_t total = 0;
+    while (j < b->streams_lean.size() && b->streams_lean[j].frame == f) total += len_of(b->streams_lean[j++]) + 64;
+    const uint64_t longest = len_of(b->streams_lean[i]) + 64;
+    b->frames[f].lean_first = uint32_t(i);
+    b->frames[f].lean_count = uint32_t(j - i);
+    lanes[f] = uint32_t(std::min<uint64_t>(j - i, std::max<uint64_t>(1, uint64_t(mul * float(total) / float(longest)))));
+    total_lanes += lanes[f];
+    i = j;
+  }
+  // lanes per warp: keep the grid near one resident wave of 4 warps per scheduler (592 schedulers)
+  uint32_t S = total_lanes <= 2368 ? 1 : (total_lanes <= 2 * 2368 ? 2 : (total_lanes <= 4 * 2368 ? 4 : 8));
+  if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
+  S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
+  b->lean_S = S;
+  b->lean_cta_first.assign(nf, 0);
+  uint32_t ctas = 0;
+  for (size_t f = 0; f < nf; f++) {
+    b->frames[f].lean_cta_first = ctas;
+    b->lean_cta_first[f] = ctas;
+    b->frames[f].lean_ctas = lanes[f] ? (lanes[f] + 4 * S - 1) / (4 * S) : 0;
+    ctas += b->frames[f].lean_ctas;
+  }
+  b->lean_ctas = ctas;
+}
+
 static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   BatchDev B;
   memset(&B, 0, sizeof(B));
@@ -457,6 +547,8 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   B.planes_a = static_cast<float*>(b->d_planes_a.p);
   B.planes_b = static_cast<float*>(b->d_planes_b.p);
   B.status = static_cast<int32_t*>(b->d_status.p);
+  B.queue = reinterpret_cast<uint32_t*>(B.status + b->streams.size());
+  B.lean_cta_first = static_cast<const uint32_t*>(b->d_lean_cta.p);
   B.dequant_default = static_cast<const float*>(b->ctx->dequant_default.p);
   B.dequant_default_off = static_cast<const uint32_t*>(b->ctx->dequant_default_off.p);
   B.natural_orders = static_cast<const uint32_t*>(b->ctx->natural_orders.p);
@@ -466,7 +558,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
                                          static_cast<const uint32_t*>(b->d_ftiles.p), b->fused_prefix.back(),
-                                         b->filter_cfg_mask, b->lean_all_420));
+                                         b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas));
   if (b->debug_stop == 0) {
     // Fused filter + colour + store, launched per range of frames; each finished range is copied to the host
     // on the copy stream while the next range is being filtered.
@@ -516,6 +608,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
   b->h2d = b->d2h = 0;
+  schedule_lean(b);
   // device allocations
   if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
   if (int r = b->d_coeffs.ensure(size_t(b->total_groups) * 3 * kGroupCoeffs * 4)) return r;
@@ -523,7 +616,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
   if (int r = b->d_planes_a.ensure(b->total_plane_floats * 4)) return r;
   if (int r = b->d_planes_b.ensure(b->total_plane_floats * 4)) return r;
-  if (int r = b->d_status.ensure(b->streams.size() * 4)) return r;
+  if (int r = b->d_status.ensure((b->streams.size() + b->frames.size() + 4) * 4)) return r;
   if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
   for (size_t f = 0; f < b->frames.size(); f++)
     b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
@@ -536,12 +629,14 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   }
   b->status_host = b->ctx->status_host;
   memset(b->status_host, 0, b->status_n * 4);
+  b->blob.flush();
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
   b->h2d += b->blob.size;
   if (int r = upload(b->d_frames, b->frames, s, &b->h2d)) return r;
   if (int r = upload(b->d_sections, b->sections, s, &b->h2d)) return r;
   if (int r = upload(b->d_streams, b->streams, s, &b->h2d)) return r;
+  if (int r = upload(b->d_lean_cta, b->lean_cta_first, s, &b->h2d)) return r;
   if (int r = upload(b->d_streams_lean, b->streams_lean, s, &b->h2d)) return r;
   if (int r = upload(b->d_streams_fast, b->streams_fast, s, &b->h2d)) return r;
   if (int r = upload(b->d_streams_slow, b->streams_slow, s, &b->h2d)) return r;

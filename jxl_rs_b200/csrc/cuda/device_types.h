@@ -44,6 +44,8 @@ struct FrameDev {
   // HF sections: index of this frame's first section in the batch section table
   uint32_t section_base;
   uint32_t first_stream;      // index of group 0 in the batch stream list
+  // persistent entropy lanes (k_entropy_lean): this frame's range in streams_lean (longest first) and its CTAs
+  uint32_t lean_first, lean_count, lean_cta_first, lean_ctas;
   // device-only buffers (element offsets)
   uint64_t coeff_group_base;  // group index base into coeffs
   uint64_t block_base;        // block index base into block_off
@@ -88,6 +90,8 @@ struct BatchDev {
   float* planes_a;
   float* planes_b;
   int32_t* status;      // per stream
+  uint32_t* queue;      // [frames] work-queue cursors of the persistent entropy kernel
+  const uint32_t* lean_cta_first;  // [frames] first CTA of each frame in k_entropy_lean's grid
   // context-wide tables
   const float* dequant_default;       // 17 tables concatenated
   const uint32_t* dequant_default_off;  // [17] float offsets

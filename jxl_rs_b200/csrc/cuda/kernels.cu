@@ -592,14 +592,31 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
 }
 
 // ---------------------------------------------------------------------------
-// K1 lean path: ANS-coded single-pass frames. Same S-streams-per-warp scheme as
-// k_entropy_fast, but the per-symbol step is branch-light and identical for the
-// "number of non-zeros" symbol and the coefficient symbols, so that packed lanes
-// stay converged; only block / channel set-up diverges.
-// Bit window: three consecutive 32-bit words re-read from L1 per symbol (the
-// section copies are 8-byte aligned and zero padded, so reading two words past
-// the end is in bounds); a symbol consumes at most 16 + 31 bits.
+// K1 lean path: ANS-coded single-pass frames.
+//  * Persistent lanes: S lanes per warp each own one (frame, group) stream at a time and pull the next one
+//    from a device-wide queue (B.queue) when theirs ends. The host orders the streams longest first, so the
+//    queue is a longest-processing-time schedule: the kernel ends close to max(longest stream, total / lanes)
+//    instead of waiting for whichever warp drew the longest streams.
+//  * The per-symbol step is branch-light and identical for the "number of non-zeros" symbol and the
+//    coefficient symbols, so packed lanes stay converged; only block / channel / stream set-up diverges.
+//  * Short dependent chain per symbol: the cluster of the next coefficient symbol only depends on whether the
+//    current token is zero (value != 0 <=> token != 0), so both candidate context-map entries are fetched
+//    before the token is known; the bit window (5 words) lives in registers and is shifted by selects.
+// Section copies are 8-byte aligned and zero padded; the word index is clamped to the section so that a
+// corrupt stream cannot walk out of the blob (the over-read is reported from bitpos at the end).
 // ---------------------------------------------------------------------------
+// Loads the compiler must not sink below the token computation (it would re-serialise the chain).
+__device__ __forceinline__ uint32_t spec_ld_u8(const uint8_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t spec_ld_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 template <int S, bool K420>
 __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   __shared__ uint16_t s_nz2[64], s_fr2[64];  // context LUTs, pre-multiplied by 2 (block_context_map.rs:34-46)
@@ -608,62 +625,90 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
     s_fr2[threadIdx.x] = uint16_t(c_freq_ctx[threadIdx.x] * 2);
   }
   __syncthreads();
-  const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const uint32_t sidx = warp * S + lane;
-  bool done = !(lane < S && sidx < B.num_lean);
-  const StreamDev sd = done ? StreamDev{0, 0} : B.streams_lean[sidx];
-  const FrameDev& F = B.frames[sd.frame];
-  const uint32_t g = sd.group;
-  const uint32_t gsid = F.first_stream + g;
-  const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
-  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0), gn = gw * gh;
-  int32_t* const group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
-  uint8_t* const nz = B.nz + B.nz_base[gsid];
-  const uint8_t* const tmap = B.blob + F.transform_off + (size_t(by0) * F.xb + bx0);
-  const int32_t* const rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off) + (size_t(by0) * F.xb + bx0);
-  const uint8_t* const qlf = B.blob + F.quant_lf_off + (size_t(by0) * F.xb + bx0);
-  uint32_t* const block_off = B.block_off + F.block_base + (size_t(by0) * F.xb + bx0);
-  const uint32_t xb = F.xb;
+  // CTA -> frame: all lanes of a CTA work on one frame, so its context map and alias tables stay in L1.
+  uint32_t fidx;
+  {
+    uint32_t lo = 0, hi = B.num_frames;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (B.lean_cta_first[mid] <= blockIdx.x) lo = mid;
+      else hi = mid;
+    }
+    fidx = lo;
+  }
+  const FrameDev& F = B.frames[fidx];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane_in_frame = ((blockIdx.x - F.lean_cta_first) * 4 + (threadIdx.x >> 5)) * S + lane;
+  const uint32_t frame_lanes = F.lean_ctas * 4 * S;
+  uint32_t qpos = lane_in_frame;  // position in this frame's (longest first) stream list
+  bool done = !(lane < S && qpos < F.lean_count);
+  // ---- per-frame constants ----
   const PassDev& P = F.passes[0];
   const uint8_t* const ctxmap = B.blob + P.context_map_off;
   const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
   const uint2* const ans = reinterpret_cast<const uint2*>(B.blob + P.ans_off);
   const uint32_t log_alpha = P.log_alpha_size, log_bucket = 12 - P.log_alpha_size, bucket_mask = (1u << (12 - P.log_alpha_size)) - 1;
-  const uint32_t shift = P.shift;
-  const uint32_t nbc = F.num_block_contexts;
-  const SectionDev sec = B.sections[F.section_base + (done ? 0 : g)];
-  const uint32_t* const words = reinterpret_cast<const uint32_t*>(B.blob + sec.off);
+  const uint32_t nbc = F.num_block_contexts, xb = F.xb;
+  // ---- per-stream state (re-initialised by the set-up path when a lane takes a new stream) ----
+  uint32_t g = 0, gsid = 0, goff = 0, gw = 1, gn = 0;
+  int32_t* group_coeffs = B.coeffs;
+  uint8_t* nz = B.nz;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(B.blob);
+  uint32_t sec_bits = 0, wlimit = 0;
   uint32_t bitpos = 0, ans_state = 0x130000u, context_offset = 0;
-  if (!done) {
-    uint32_t nb = 0;
-    while ((1u << nb) < F.num_histograms) nb++;
-    const uint32_t hist_idx = nb ? (__ldg(words) & ((1u << nb) - 1u)) : 0u;  // group.rs:333-341 (nb <= 12)
-    bitpos = nb;
-    if (hist_idx >= F.num_histograms) {
-      B.status[gsid] = JXG_ERR_INVALID_HISTOGRAM_INDEX;
-      done = true;
-    }
-    context_offset = hist_idx * nbc * (37 + 458);
-    const uint32_t w0 = __ldg(words + (bitpos >> 5)), w1 = __ldg(words + (bitpos >> 5) + 1);
-    ans_state = __funnelshift_r(w0, w1, bitpos & 31);  // ans.rs:431
-    bitpos += 32;
-  }
-  // lane state
+  uint32_t wi = 0, w0 = 0, w1 = 0, w2 = 0;
+  // ---- per-block state ----
   uint32_t pos = 0, coeffs_offset = 0;
   uint32_t bx = 0, by = 0, cxy = 0x0101, shape = 0, qf_lf_idx = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
   uint32_t ci = 3;          // 3: need a new block
-  bool need_setup = true;   // channel (and maybe block) set-up before the next symbol
+  bool need_setup = true;   // channel (and maybe block / stream) set-up before the next symbol
+  bool new_stream = true, failed = false;
   bool mode_nnz = true;
-  uint32_t ctx_nnz = 0, block_context = 0;
-  uint32_t k = 0, nonzeros = 0, prev = 0, histo_offset = 0;
+  uint32_t block_context = 0, cluster = 0;
+  uint32_t k = 0, nonzeros = 0, histo_offset = 0;
   const uint32_t* order = B.natural_orders;
   int32_t* cur = group_coeffs;
 
   for (;;) {
     if (!__any_sync(0xffffffffu, !done)) break;
     if (!done && need_setup) {
-      // ---------- rare path: next block and/or channel ----------
-      if (ci == 3) {
+      // ---------- rare path: next stream, block and/or channel ----------
+      while (ci == 3) {
+        if (new_stream) {
+          g = B.streams_lean[F.lean_first + qpos].group;
+          gsid = F.first_stream + g;
+          const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
+          gw = min(32u, F.xb - bx0);
+          gn = gw * min(32u, F.yb - by0);
+          goff = by0 * xb + bx0;
+          group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+          nz = B.nz + B.nz_base[gsid];
+          const SectionDev sec = B.sections[F.section_base + g];
+          words = reinterpret_cast<const uint32_t*>(B.blob + sec.off);
+          sec_bits = sec.len * 8u;
+          wlimit = (sec.len >> 2) + 1;
+          uint32_t nb = 0;
+          while ((1u << nb) < F.num_histograms) nb++;
+          const uint32_t hist_idx = nb ? (__ldg(words) & ((1u << nb) - 1u)) : 0u;  // group.rs:333-341 (nb <= 12)
+          failed = false;
+          pos = 0;
+          coeffs_offset = 0;
+          histo_offset = 0;
+          if (hist_idx >= F.num_histograms) {
+            B.status[gsid] = JXG_ERR_INVALID_HISTOGRAM_INDEX;
+            failed = true;
+            pos = gn;
+          }
+          context_offset = failed ? 0u : hist_idx * nbc * (37 + 458);
+          ans_state = __funnelshift_r(__ldg(words), __ldg(words + 1), nb);  // ans.rs:431
+          bitpos = nb + 32;
+          wi = 1;
+          w0 = __ldg(words + 1);
+          w1 = __ldg(words + 2);
+          w2 = __ldg(words + 3);
+          new_stream = false;
+        }
+        const uint8_t* const tmap = B.blob + F.transform_off + goff;
         uint32_t raw_t = 0;
         while (pos < gn) {
           by = pos / gw;
@@ -672,30 +717,40 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           if (raw_t >= 128) break;
           pos++;
         }
-        if (pos >= gn) {  // finished: check_final_state (decode.rs:400)
-          int err = 0;
-          if (bitpos > sec.len * 8u) err = JXG_ERR_OUT_OF_BOUNDS;
-          else if (ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
-          B.status[gsid] = err;
-          done = true;
-        } else if ((raw_t & 127) >= 27) {
-          B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
-          done = true;
-        } else {
-          const uint32_t t = raw_t & 127, bidx = by * xb + bx;
-          const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
-          cxy = cx | (cy << 8);
-          shape = c_shape[t];
-          const uint32_t raw_quant = uint32_t(rq[bidx]);
-          uint32_t qf_idx = 0;
-          for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
-          qf_lf_idx = qf_idx * F.num_lf_contexts + qlf[bidx];
-          num_blocks = cx * cy;
-          num_coeffs = num_blocks * 64;
-          lnb = 31 - __clz(num_blocks);
-          block_off[bidx] = coeffs_offset;
-          ci = 0;
+        if (pos >= gn) {  // stream finished: check_final_state (decode.rs:400), then take the next one
+          if (!failed) {
+            int err = 0;
+            if (bitpos > sec_bits) err = JXG_ERR_OUT_OF_BOUNDS;
+            else if (ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
+            B.status[gsid] = err;
+          }
+          qpos = atomicAdd(B.queue + fidx, 1u) + frame_lanes;
+          if (qpos >= F.lean_count) {
+            done = true;
+            break;
+          }
+          new_stream = true;
+          continue;
         }
+        if ((raw_t & 127) >= 27) {
+          B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
+          failed = true;
+          pos = gn;
+          continue;
+        }
+        const uint32_t t = raw_t & 127, bidx = by * xb + bx;
+        const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
+        cxy = cx | (cy << 8);
+        shape = c_shape[t];
+        const uint32_t raw_quant = uint32_t(reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off)[goff + bidx]);
+        uint32_t qf_idx = 0;
+        for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
+        qf_lf_idx = qf_idx * F.num_lf_contexts + (B.blob + F.quant_lf_off)[goff + bidx];
+        num_blocks = cx * cy;
+        num_coeffs = num_blocks * 64;
+        lnb = 31 - __clz(num_blocks);
+        (B.block_off + F.block_base)[goff + bidx] = coeffs_offset;
+        ci = 0;
       }
       if (!done) {
         const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);  // Y, X, B
@@ -708,18 +763,20 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
         idx = idx * (F.num_qf_thresholds + 1) * F.num_lf_contexts + qf_lf_idx;
         block_context = __ldg(B.blob + F.block_ctx_map_off + idx);
         const uint32_t nzc = predicted < 8 ? predicted : (predicted < 64 ? 4 + predicted / 2 : 36);
-        ctx_nnz = nzc * nbc + block_context + context_offset;
+        cluster = __ldg(ctxmap + (nzc * nbc + block_context + context_offset));
         mode_nnz = true;
         need_setup = false;
       }
     }
     if (done) continue;
     // ---------- common path: one symbol ----------
-    const uint32_t wi = bitpos >> 5;
-    const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1), w2 = __ldg(words + wi + 2);
-    const uint32_t ctx_coef = histo_offset + uint32_t(s_nz2[((nonzeros + num_blocks - 1) >> lnb) & 63]) + uint32_t(s_fr2[(k >> lnb) & 63]) + prev;
-    const uint32_t ctx = mode_nnz ? ctx_nnz : ctx_coef;
-    const uint32_t cluster = __ldg(ctxmap + ctx);
+    // speculative: clusters of the next coefficient symbol for token == 0 (A) and token != 0 (B)
+    const uint32_t w3 = spec_ld_u32(words + wi + 3), w4 = spec_ld_u32(words + wi + 4);
+    const uint32_t fr_next = s_fr2[((k + 1) >> lnb) & 63];
+    const uint32_t nzq = nonzeros + num_blocks - 1;
+    const uint32_t ctxA = histo_offset + fr_next + uint32_t(s_nz2[(nzq >> lnb) & 63]);
+    const uint32_t ctxB = histo_offset + fr_next + uint32_t(s_nz2[((nzq - 1) >> lnb) & 63]) + 1u;
+    const uint32_t clA = spec_ld_u8(ctxmap + ctxA), clB = spec_ld_u8(ctxmap + ctxB);
     // rANS step (ans.rs:356-393)
     const uint32_t idx12 = ans_state & 0xfff;
     const uint32_t bi = idx12 >> log_bucket, bp = idx12 & bucket_mask;
@@ -728,6 +785,8 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
     const uint32_t dist = (bk.x >> 16) ^ (alias ? (bk.y >> 16) : 0u);
     const uint32_t offset = bp + (alias ? (bk.y & 0xffff) : 0u);
     const uint32_t token = alias ? (bk.x & 0xff) : bi;
+    const uint32_t nonzero = token != 0 ? 1u : 0u;
+    const uint32_t cluster_next = nonzero ? clB : clA;
     uint32_t next = (ans_state >> 12) * dist + offset;
     const uint32_t sh = bitpos & 31;
     const bool refill = next < (1u << 16);
@@ -746,19 +805,33 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
     const bool direct = token < split_token;
     const uint32_t bits_in_token = msb + lsb;
     const uint32_t nbits = direct ? 0u : ((split_exponent - bits_in_token + ((token - split_token) >> bits_in_token)) & 31);
-    const uint32_t win = sh2 < 32 ? __funnelshift_r(w0, w1, sh2) : __funnelshift_r(w1, w2, sh2 - 32);
+    const uint32_t win = sh2 < 32 ? __funnelshift_r(w0, w1, sh2) : __funnelshift_r(w1, w2, sh2);
     const uint32_t bits = win & ((1u << nbits) - 1u);
     const uint32_t hi = ((token >> lsb) & ((1u << msb) - 1u)) | (1u << msb);
     const uint32_t composed = (((hi << nbits) | bits) << lsb) | (token & ((1u << lsb) - 1u));
     const uint32_t value = direct ? token : composed;
     bitpos += (refill ? 16u : 0u) + nbits;
+    {  // advance the register window by 0..2 words
+      const uint32_t nwi = min(bitpos >> 5, wlimit);
+      const uint32_t adv = nwi - wi;
+      wi = nwi;
+      const uint32_t t0 = adv == 0 ? w0 : (adv == 1 ? w1 : w2);
+      const uint32_t t1 = adv == 0 ? w1 : (adv == 1 ? w2 : w3);
+      const uint32_t t2 = adv == 0 ? w2 : (adv == 1 ? w3 : w4);
+      w0 = t0;
+      w1 = t1;
+      w2 = t2;
+    }
     // ---------- post ----------
     if (mode_nnz) {
       const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
       nonzeros = value;
       if (nonzeros + num_blocks > num_coeffs) {
         B.status[gsid] = JXG_ERR_INVALID_NUM_NONZEROS;
-        done = true;
+        failed = true;
+        pos = gn;
+        ci = 3;
+        need_setup = true;
         continue;
       }
       uint8_t* nzc_map = nz + c * 1024;
@@ -767,7 +840,6 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       for (uint32_t iy = 0; iy < cy; iy++)
         for (uint32_t ix = 0; ix < cx; ix++) nzc_map[(by + iy) * 32 + bx + ix] = nzv;
       histo_offset = nbc * 37 + 458 * block_context + context_offset;
-      prev = nonzeros > num_coeffs / 16 ? 0u : 1u;
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
                               : B.natural_orders + B.natural_order_off[shape];
@@ -779,12 +851,15 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           coeffs_offset += num_coeffs;
           pos++;
         }
+      } else {
+        const uint32_t prev = nonzeros > num_coeffs / 16 ? 0u : 1u;
+        cluster = __ldg(ctxmap + (histo_offset + uint32_t(s_nz2[((nonzeros + num_blocks - 1) >> lnb) & 63]) +
+                                  uint32_t(s_fr2[(k >> lnb) & 63]) + prev));
       }
     } else {
-      const int32_t coeff = int32_t(uint32_t(unpack_signed(value)) << shift);
-      if (coeff != 0) cur[__ldg(order + k)] = coeff;
-      prev = coeff != 0;
-      nonzeros -= prev;
+      if (nonzero) cur[__ldg(order + k)] = unpack_signed(value);  // lean streams have shift == 0 (host routing)
+      nonzeros -= nonzero;
+      cluster = cluster_next;
       k++;
       if (nonzeros == 0) {
         need_setup = true;
@@ -794,7 +869,10 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
         }
       } else if (k >= num_coeffs) {
         B.status[gsid] = JXG_ERR_RESIDUAL_NONZEROS;  // group.rs:574
-        done = true;
+        failed = true;
+        pos = gn;
+        ci = 3;
+        need_setup = true;
       }
     }
   }
@@ -1985,29 +2063,46 @@ struct FCfg {
   static constexpr size_t kSmemBytes = sizeof(float) * (size_t(6 + NMAPS) * NC + SBW * SBH);
 };
 
-// One EPF stage. src/dst: [3][NC]; maps: [NMAPS][NC]; m = margin of the output region.
-template <int STAGE, int WW, int WH, int H, int SBW>
+// Cell -> source position. INTERIOR tiles (window fully inside the image) skip every range / mirror computation.
+template <bool INTERIOR, int WW>
+__device__ __forceinline__ bool cell_source(int lx, int ly, int wx0, int wy0, int w, int h, int r, int& o, int& mx, int& my) {
+  if (INTERIOR) {
+    mx = wx0 + lx;
+    my = wy0 + ly;
+    o = ly * WW + lx;
+    return true;
+  }
+  const int gx = wx0 + lx, gy = wy0 + ly;
+  if (gx < -r || gx > w - 1 + r || gy < -r || gy > h - 1 + r) return false;  // never needed by a valid output
+  mx = mirror(gx, w);
+  my = mirror(gy, h);
+  o = (my - wy0) * WW + (mx - wx0);
+  return true;
+}
+
+// One EPF stage. src/dst: [3][NC]; maps: [NMAPS][NC]; M = margin of the output region (compile time).
+template <int STAGE, int WW, int WH, int H, int SBW, int M, bool INTERIOR>
 __device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, float* dst, float* maps, const float* sig,
-                                          int wx0, int wy0, int sbx0, int sby0, int m) {
+                                          int wx0, int wy0, int sbx0, int sby0) {
   constexpr int NC = WW * WH;
   const int w = int(F.width), h = int(F.height);
   const float s0 = F.epf_channel_scale[0], s1 = F.epf_channel_scale[1], s2 = F.epf_channel_scale[2];
   constexpr int B = STAGE == 0 ? 3 : (STAGE == 1 ? 2 : 1);  // border of this stage
-  const int mp = m - B;                                       // margin of valid source cells
+  constexpr int MP = M - B;                                   // margin of valid source cells
   // ---- phase A: difference maps over the source-valid area ----
   {
     constexpr int NO = STAGE == 0 ? 6 : 2;
-    const int ox[6] = {1, 0, 2, 0, 1, 1}, oy[6] = {0, 1, 0, 2, 1, -1};  // A=(1,0) C=(0,1) B=(2,0) D=(0,2) E=(1,1) F=(1,-1)
-    const int aw = WW - 2 * mp, ah = WH - 2 * mp;
+    constexpr int ox[6] = {1, 0, 2, 0, 1, 1}, oy[6] = {0, 1, 0, 2, 1, -1};  // (1,0) (0,1) (2,0) (0,2) (1,1) (1,-1)
+    constexpr int aw = WW - 2 * MP, ah = WH - 2 * MP;
     for (int idx = threadIdx.x; idx < aw * ah; idx += blockDim.x) {
-      const int lx = mp + idx % aw, ly = mp + idx / aw;
+      const int lx = MP + idx % aw, ly = MP + idx / aw;
       const int o = ly * WW + lx;
       const float c0 = src[o], c1 = src[NC + o], c2 = src[2 * NC + o];
 #pragma unroll
       for (int k = 0; k < NO; k++) {
         const int nx = lx + ox[k], ny = ly + oy[k];
-        if (nx >= WW - mp || ny >= WH - mp || ny < mp) continue;
-        const int on = ny * WW + nx;
+        if (nx >= WW - MP || ny >= WH - MP || ny < MP) continue;
+        const int on = o + oy[k] * WW + ox[k];
         maps[k * NC + o] = fmaf(fabsf(src[on] - c0), s0, fmaf(fabsf(src[NC + on] - c1), s1, fabsf(src[2 * NC + on] - c2) * s2));
       }
     }
@@ -2017,26 +2112,22 @@ __device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, f
   const float kMinSigma = -3.90524291751269967465540850526868f;
   const float sigma_scale = STAGE == 0 ? F.epf_pass0_sigma_scale : (STAGE == 1 ? 1.0f : F.epf_pass2_sigma_scale);
   const float sm = sigma_scale * 1.65f, bsm = sm * F.epf_border_sad_mul;
-  constexpr int rw = WW - 2 * (H - (H - 0)) ;  // placeholder to keep constexpr math simple (unused)
-  (void)rw;
-  const int r = H - m;  // halo still needed after this stage
-  const int bw_ = kTW + 2 * r, bh_ = kTH + 2 * r;
-  const float* Dh = maps;            // (1,0)
-  const float* Dv = maps + NC;       // (0,1)
+  constexpr int R = H - M;  // halo still needed after this stage
+  constexpr int bw_ = kTW + 2 * R, bh_ = kTH + 2 * R;
+  const float* Dh = maps;       // (1,0)
+  const float* Dv = maps + NC;  // (0,1)
   for (int idx = threadIdx.x; idx < bw_ * bh_; idx += blockDim.x) {
-    const int lx = m + idx % bw_, ly = m + idx / bw_;
-    const int gx = wx0 + lx, gy = wy0 + ly;
-    if (gx < -r || gx > w - 1 + r || gy < -r || gy > h - 1 + r) continue;  // never needed by a valid output
-    const int mx = mirror(gx, w), my = mirror(gy, h);
-    const int cx = mx - wx0, cy = my - wy0;
-    const int o = cy * WW + cx, od = ly * WW + lx;
+    const int lx = M + idx % bw_, ly = M + idx / bw_;
+    int o, mx, my;
+    if (!cell_source<INTERIOR, WW>(lx, ly, wx0, wy0, w, h, R, o, mx, my)) continue;
+    const int od = ly * WW + lx;
     const float inv_sigma_px = sig[((my >> 3) - sby0) * SBW + ((mx >> 3) - sbx0)];
     if (inv_sigma_px < kMinSigma) {
 #pragma unroll
       for (int c = 0; c < 3; c++) dst[c * NC + od] = src[c * NC + o];
       continue;
     }
-    const bool border = ((my & 7) == 0 || (my & 7) == 7) || ((mx & 7) == 0 || (mx & 7) == 7);
+    const bool border = (((my + 1) & 7) < 2) || (((mx + 1) & 7) < 2);  // x or y == 0 or 7 (mod 8)
     const float inv_s = inv_sigma_px * (border ? bsm : sm);
     if (STAGE == 2) {
       // neighbours in the reference's order: up, left, right, down (epf2.rs:83)
@@ -2055,8 +2146,8 @@ __device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, f
       for (int c = 0; c < 3; c++) dst[c * NC + od] = acc[c] * inv_w;
       continue;
     }
-    auto plus_sum = [&](const float* M, int base) {
-      return M[base - WW] + M[base - 1] + M[base] + M[base + 1] + M[base + WW];
+    auto plus_sum = [&](const float* Mp, int base) {
+      return Mp[base - WW] + Mp[base - 1] + Mp[base] + Mp[base + 1] + Mp[base + WW];
     };
     if (STAGE == 1) {
       const float sad[4] = {plus_sum(Dv, o - WW), plus_sum(Dh, o - 1), plus_sum(Dh, o), plus_sum(Dv, o)};
@@ -2107,35 +2198,27 @@ __device__ __forceinline__ void epf_stage(const FrameDev& F, const float* src, f
   __syncthreads();
 }
 
-template <bool GAB, int EPF>
-__global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+template <bool GAB, int EPF, bool INTERIOR>
+__device__ __forceinline__ void filter_tile(const BatchDev& B, const FrameDev& F, const float* src_planes, float* smem, int x0, int y0) {
   using C = FCfg<GAB, EPF>;
   constexpr int H = C::H, WW = C::WW, WH = C::WH, NC = C::NC;
-  extern __shared__ float smem[];
   float* bufA = smem;
   float* bufB = smem + 3 * NC;
   float* maps = smem + 6 * NC;
   float* sig = maps + C::NMAPS * NC;
-  const uint32_t tile_id = blockIdx.x + T.tile_begin;
-  uint32_t lo = 0, hi = T.num_frames;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (T.tile_prefix[mid] <= tile_id) lo = mid;
-    else hi = mid;
-  }
-  const FrameDev& F = B.frames[lo];
-  if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return;  // another instantiation handles this frame
-  const uint32_t local = tile_id - T.tile_prefix[lo];
-  const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
-  const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
   const int w = int(F.width), h = int(F.height);
   const int wx0 = x0 - H, wy0 = y0 - H;
   // ---- load, pre-mirrored; cells farther than H outside the image are never needed ----
   for (int idx = threadIdx.x; idx < NC; idx += blockDim.x) {
     const int lx = idx % WW, ly = idx / WW;
-    const int gx = wx0 + lx, gy = wy0 + ly;
-    if (gx > w - 1 + H || gy > h - 1 + H) continue;
-    const size_t so = size_t(mirror(gy, h)) * F.plane_stride + mirror(gx, w);
+    size_t so;
+    if (INTERIOR) {
+      so = size_t(wy0 + ly) * F.plane_stride + (wx0 + lx);
+    } else {
+      const int gx = wx0 + lx, gy = wy0 + ly;
+      if (gx > w - 1 + H || gy > h - 1 + H) continue;
+      so = size_t(mirror(gy, h)) * F.plane_stride + mirror(gx, w);
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) bufA[c * NC + idx] = src_planes[F.plane_base + c * F.plane_size + so];
   }
@@ -2157,16 +2240,18 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
   __syncthreads();
   float* cur = bufA;
   float* nxt = bufB;
-  int m = 0;
+  constexpr int M_GAB = GAB ? 1 : 0;
+  constexpr int M_E0 = M_GAB + (EPF >= 3 ? 3 : 0);
+  constexpr int M_E1 = M_E0 + (EPF >= 1 ? 2 : 0);
+  constexpr int M_E2 = M_E1 + (EPF >= 2 ? 1 : 0);
+  static_assert(M_E2 == H, "margins must add up to the halo");
   if (GAB) {  // gaborish.rs:40-88
-    m += 1;
-    const int r = H - m;
-    const int rw = kTW + 2 * r, rh = kTH + 2 * r;
+    constexpr int R = H - M_GAB;
+    constexpr int rw = kTW + 2 * R, rh = kTH + 2 * R;
     for (int idx = threadIdx.x; idx < rw * rh; idx += blockDim.x) {
-      const int lx = m + idx % rw, ly = m + idx / rw;
-      const int gx = wx0 + lx, gy = wy0 + ly;
-      if (gx < -r || gx > w - 1 + r || gy < -r || gy > h - 1 + r) continue;
-      const int o = (mirror(gy, h) - wy0) * WW + (mirror(gx, w) - wx0);
+      const int lx = M_GAB + idx % rw, ly = M_GAB + idx / rw;
+      int o, mx, my;
+      if (!cell_source<INTERIOR, WW>(lx, ly, wx0, wy0, w, h, R, o, mx, my)) continue;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const float* p = cur + c * NC + o;
@@ -2180,18 +2265,15 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
     float* t = cur; cur = nxt; nxt = t;
   }
   if (EPF >= 3) {
-    m += 3;
-    epf_stage<0, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    epf_stage<0, WW, WH, H, C::SBW, M_E0, INTERIOR>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0);
     float* t = cur; cur = nxt; nxt = t;
   }
   if (EPF >= 1) {
-    m += 2;
-    epf_stage<1, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    epf_stage<1, WW, WH, H, C::SBW, M_E1, INTERIOR>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0);
     float* t = cur; cur = nxt; nxt = t;
   }
   if (EPF >= 2) {
-    m += 1;
-    epf_stage<2, WW, WH, H, C::SBW>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0, m);
+    epf_stage<2, WW, WH, H, C::SBW, M_E2, INTERIOR>(F, cur, nxt, maps, sig, wx0, wy0, sbx0, sby0);
     float* t = cur; cur = nxt; nxt = t;
   }
   // ---- colour + store of the kTW x kTH core ----
@@ -2260,6 +2342,27 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
 }
 
 template <bool GAB, int EPF>
+__global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+  using C = FCfg<GAB, EPF>;
+  extern __shared__ float smem[];
+  const uint32_t tile_id = blockIdx.x + T.tile_begin;
+  uint32_t lo = 0, hi = T.num_frames;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (T.tile_prefix[mid] <= tile_id) lo = mid;
+    else hi = mid;
+  }
+  const FrameDev& F = B.frames[lo];
+  if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return;  // another instantiation handles this frame
+  const uint32_t local = tile_id - T.tile_prefix[lo];
+  const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
+  const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
+  const bool interior = x0 - C::H >= 0 && y0 - C::H >= 0 && x0 + kTW + C::H <= int(F.width) && y0 + kTH + C::H <= int(F.height);
+  if (interior) filter_tile<GAB, EPF, true>(B, F, src_planes, smem, x0, y0);
+  else filter_tile<GAB, EPF, false>(B, F, src_planes, smem, x0, y0);
+}
+
+template <bool GAB, int EPF>
 static void launch_filters(const BatchDev& B, const FusedTiles& FT, uint32_t tiles, cudaStream_t stream) {
   k_filters_store<GAB, EPF><<<tiles, kFilterThreads, FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
 }
@@ -2302,7 +2405,7 @@ cudaError_t configure_kernels() {
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
                     cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
-                    bool lean_all_420) {
+                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas) {
   // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
   // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
@@ -2313,10 +2416,9 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   cudaMemsetAsync(B.coeffs, 0, coeff_bytes, stream);
   mark(1);
   if (B.num_lean) {
-    uint32_t per = (B.num_lean + 2367) / 2368;
-    if (const char* e = getenv("JXG_ENTROPY_S")) per = uint32_t(atoi(e));  // experiment knob
-    const uint32_t S = per <= 1 ? 1 : (per <= 2 ? 2 : (per <= 4 ? 4 : 8));
-    const uint32_t grid = (B.num_lean + 4 * S - 1) / (4 * S);
+    // Persistent lanes, scheduled per frame by the host (batch.cc schedule_lean): S lanes per warp, lean_ctas CTAs.
+    cudaMemsetAsync(B.queue, 0, sizeof(uint32_t) * B.num_frames, stream);
+    const uint32_t S = lean_S, grid = lean_ctas;
     if (lean_all_420) {
       if (S == 1) k_entropy_lean<1, true><<<grid, 128, 0, stream>>>(B);
       else if (S == 2) k_entropy_lean<2, true><<<grid, 128, 0, stream>>>(B);

@@ -84,13 +84,17 @@ class JxgContext:
 class Batch:
     """jxg_batch_*: frames decoded together by one kernel pipeline."""
 
-    def __init__(self, ctx: JxgContext, n_hint: int = 0):
+    def __init__(self, ctx: JxgContext, n_hint: int = 0, staging_threads: int = 0):
+        """staging_threads > 0: large input copies are deferred to run() and done by that many host threads
+        (jxg_batch_set_deferred_copy); the ParsedFrames added are kept alive by this object."""
         self._lib = ctx._lib
         self._ctx = ctx
         self._h = C.c_void_p()
         abi.check(self._lib, self._lib.jxg_batch_begin(ctx._h, n_hint, C.byref(self._h)))
         self._keep = []
         self.frames = []
+        if staging_threads > 0:
+            abi.check(self._lib, self._lib.jxg_batch_set_deferred_copy(self._h, staging_threads))
 
     def add(self, frame: ParsedFrame, out_ptr: int, row_stride: int, fmt: int, out_is_device: bool):
         abi.check(self._lib, self._lib.jxg_batch_add_parsed(self._h, frame._h, fmt, C.c_void_p(out_ptr), row_stride,
@@ -178,52 +182,114 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
 
 
 class PipelinedDecoder:
-    """Streaming decode of many batches: `depth` contexts (each with its own CUDA streams, pinned
-    staging arena and device pools) are used round-robin, so that the host front-end work
-    (parse + staging) of batch k+1 overlaps the kernels and the D2H copies of batch k.
+    """Streaming decode of many batches. `submit()` only queues a batch: its files start parsing on the worker
+    pool at once (so parsing of batch k+1.. overlaps everything else) and a dispatcher thread stages each batch
+    (parallel copies into the pinned blob), launches it on one of `depth` contexts (own CUDA streams, staging
+    arena and device pools, used round-robin) and retires the oldest one when all contexts are busy. Host
+    front-end work of batch k+1 therefore overlaps the kernels and the D2H copies of batch k.
     This is the serving-shaped entry point (many independent images in flight)."""
 
-    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0):
+    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0, staging_threads: int = 8, parse_ahead: int = 2):
         import os
+        import queue
+        import threading
         from collections import deque
         from concurrent.futures import ThreadPoolExecutor
         self.ctxs = [JxgContext(device) for _ in range(depth)]
         self.depth = depth
+        self.staging_threads = staging_threads
         self.pool = ThreadPoolExecutor(max_workers=workers or min(64, os.cpu_count() or 8))
         self.inflight = deque()
         self.k = 0
         self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0, "kernel_launches": 0}
+        self._jobs = queue.Queue()
+        self._ahead = threading.Semaphore(depth + parse_ahead)  # bounds parsed-but-not-yet-launched batches
+        self._error = None
+        self.trace = None  # set to [] to record the dispatcher timeline
+        self._thread = threading.Thread(target=self._dispatch, daemon=True)
+        self._thread.start()
 
     def _retire(self):
         b = self.inflight.popleft()
-        b.wait()
-        self.last_stats = b.stats()
-        b.close()
+        try:
+            b.wait()
+            self.last_stats = b.stats()
+        finally:
+            b.close()
+
+    def _launch(self, futs, outs, fmt, out_is_device):
+        import time
+        t0 = time.perf_counter()
+        if len(self.inflight) == self.depth:
+            self._retire()
+        t1 = time.perf_counter()
+        ctx = self.ctxs[self.k % self.depth]
+        self.k += 1
+        b = Batch(ctx, len(futs), self.staging_threads)
+        try:
+            frames = [fut.result() for fut in futs]
+            t2 = time.perf_counter()
+            for fr, (ptr, stride) in zip(frames, outs):
+                b.add(fr, ptr, stride, fmt, out_is_device)
+            t3 = time.perf_counter()
+            b.run()
+        except Exception:
+            b.close()
+            raise
+        self.inflight.append(b)
+        if self.trace is not None:  # host-side timeline of the dispatcher (seconds): start, retire, parse wait, add, run
+            self.trace.append((t0, t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
+
+    def _dispatch(self):
+        while True:
+            job = self._jobs.get()
+            try:
+                if job is None:
+                    return
+                if isinstance(job, tuple) and job[0] == "drain":
+                    try:
+                        while self.inflight:
+                            self._retire()
+                    except Exception as e:  # noqa: BLE001 - reported to the caller of drain()
+                        self._error = self._error or e
+                    job[1].set()
+                    continue
+                try:
+                    if self._error is None:
+                        self._launch(*job)
+                except Exception as e:  # noqa: BLE001
+                    self._error = self._error or e
+                finally:
+                    self._ahead.release()
+            finally:
+                self._jobs.task_done()
 
     def submit(self, files, outs, fmt: int = abi.FORMAT_RGB_U8, out_is_device: bool = False):
         """files: list of .jxl byte strings; outs: list of (data_ptr, row_stride). Returns once the batch is
-        queued on the device; its outputs are complete after the next-but-one submit() or drain()."""
+        queued; its outputs are complete after drain() (or once `depth` later batches have been launched)."""
+        self._ahead.acquire()
         futs = [self.pool.submit(ParsedFrame, f) for f in files]
-        if len(self.inflight) == self.depth:
-            self._retire()
-        ctx = self.ctxs[self.k % self.depth]
-        self.k += 1
-        b = Batch(ctx, len(files))
-        for fut, (ptr, stride) in zip(futs, outs):
-            b.add(fut.result(), ptr, stride, fmt, out_is_device)
-        b.run()
-        self.inflight.append(b)
+        self._jobs.put((futs, list(outs), fmt, out_is_device))
 
     def drain(self):
-        while self.inflight:
-            self._retire()
+        import threading
+        ev = threading.Event()
+        self._jobs.put(("drain", ev))
+        ev.wait()
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
 
     def decode(self, files, outs, fmt: int = abi.FORMAT_RGB_U8, out_is_device: bool = False):
         self.submit(files, outs, fmt, out_is_device)
         self.drain()
 
     def close(self):
-        self.drain()
-        self.pool.shutdown()
-        for c in self.ctxs:
-            c.close()
+        try:
+            self.drain()
+        finally:
+            self._jobs.put(None)
+            self._thread.join()
+            self.pool.shutdown()
+            for c in self.ctxs:
+                c.close()

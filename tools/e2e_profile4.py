@@ -1,0 +1,28 @@
+"""Host-side timeline of PipelinedDecoder on the bench workload. Usage: python tools/e2e_profile4.py [frames] [steps]"""
+import os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench, jxl_rs_b200 as j
+from jxl_rs_b200 import abi
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+args = types.SimpleNamespace(frames=n, unique=0, width=3840, height=2160, distance=0.5, epf=2, profile=1)
+files = bench.make_frames(args, 0)
+host_out = [[torch.empty((2160, 3840, 3), dtype=torch.uint8).pin_memory() for _ in range(n)] for _ in range(2)]
+outs = [[(o.data_ptr(), 3840 * 3) for o in ho] for ho in host_out]
+for st in (8, 16):
+    dec = j.PipelinedDecoder(0, depth=2, staging_threads=st)
+    for i in range(3):
+        dec.submit(files, outs[i % 2])
+    dec.drain()
+    dec.trace = []
+    t0 = time.perf_counter()
+    for i in range(steps):
+        dec.submit(files, outs[i % 2])
+    dec.drain()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"staging_threads={st}: {dt/steps*1e3:.1f} ms/step, {n*3840*2160/1e6*steps/dt:.0f} MP/s")
+    for (ts, ret, pw, add, run) in dec.trace:
+        print(f"  t={1e3*(ts-t0):7.1f}  retire {ret*1e3:6.1f}  parsewait {pw*1e3:6.1f}  add {add*1e3:6.1f}  run {run*1e3:6.1f}")
+    dec.close()
