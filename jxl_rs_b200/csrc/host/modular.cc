@@ -388,7 +388,16 @@ static std::vector<SqueezeParams> default_squeeze(const std::vector<ModularChann
   return params;
 }
 
-void meta_apply_transforms(std::vector<ModularChannel>& ch, uint32_t& nb_meta, GroupHeader& header) {
+void meta_apply_transforms(std::vector<ModularChannel>& ch, uint32_t& nb_meta, GroupHeader& header, bool allocate) {
+  auto make = [&](uint32_t w, uint32_t h, int32_t hs, int32_t vs) {
+    if (allocate) return ModularChannel(w, h, hs, vs);
+    ModularChannel c;
+    c.w = w;
+    c.h = h;
+    c.hshift = hs;
+    c.vshift = vs;
+    return c;
+  };
   for (auto& t : header.transforms) {
     if (t.id == 0) {  // RCT: channel list unchanged (meta_apply.rs RCT arm checks equal sizes)
       if (t.begin_channel + 3 > ch.size()) fail("RCT channel range");
@@ -407,7 +416,7 @@ void meta_apply_transforms(std::vector<ModularChannel>& ch, uint32_t& nb_meta, G
         nb_meta += 1;
       }
       ch.erase(ch.begin() + b + 1, ch.begin() + b + n);
-      ch.insert(ch.begin(), ModularChannel(t.num_colors + t.num_deltas, uint32_t(n), -1, -1));
+      ch.insert(ch.begin(), make(t.num_colors + t.num_deltas, uint32_t(n), -1, -1));
     } else {  // squeeze, meta_apply.rs squeeze arm / squeeze.rs:17-37
       if (t.squeezes.empty()) t.squeezes = default_squeeze(ch, nb_meta);
       for (const auto& s : t.squeezes) {
@@ -425,14 +434,15 @@ void meta_apply_transforms(std::vector<ModularChannel>& ch, uint32_t& nb_meta, G
             uint32_t w = in.w;
             in.w = (w + 1) / 2;
             if (in.hshift >= 0) in.hshift++;
-            res = ModularChannel(w - in.w, in.h, in.hshift, in.vshift);
+            res = make(w - in.w, in.h, in.hshift, in.vshift);
           } else {
             uint32_t h = in.h;
             in.h = (h + 1) / 2;
             if (in.vshift >= 0) in.vshift++;
-            res = ModularChannel(in.w, h - in.h, in.hshift, in.vshift);
+            res = make(in.w, h - in.h, in.hshift, in.vshift);
           }
-          in.data.assign(size_t(in.w) * in.h, 0);
+          if (allocate) in.data.assign(size_t(in.w) * in.h, 0);
+          else in.data.clear();
           ch.insert(ch.begin() + offset + (c - b), std::move(res));
         }
       }

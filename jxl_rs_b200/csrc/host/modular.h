@@ -89,7 +89,9 @@ void decode_modular_subbitstream(std::vector<ModularChannel>& channels, size_t s
                                  const ModularTree* global_tree, BitReader& br);
 
 // Pieces used by the Modular-frame path (global image split over groups).
-void meta_apply_transforms(std::vector<ModularChannel>& channels, uint32_t& nb_meta, GroupHeader& header);
+// allocate = false: only channel shapes are tracked (planes stay empty; Modular-frame front end).
+void meta_apply_transforms(std::vector<ModularChannel>& channels, uint32_t& nb_meta, GroupHeader& header,
+                           bool allocate = true);
 void undo_transforms(std::vector<ModularChannel>& channels, const GroupHeader& header, uint32_t bit_depth);
 void decode_modular_channels(std::vector<ModularChannel*>& channels, size_t stream_id, const GroupHeader& header,
                              const ModularTree& tree, BitReader& br);

@@ -1,0 +1,64 @@
+// CPU checker for Modular frames (BASELINE config 5). TEST INFRASTRUCTURE, like oracle.cc:
+// only tests/, __graft_entry__.smoke() and bench.py's CPU legs may call it.
+//
+// The per-pixel MA-tree decode, the predictors, the weighted predictor and the inverse RCT / palette / Squeeze are
+// the scalar restatement in jxl_rs_b200/csrc/host/modular.cc (decode_channel <- modular/decode/channel.rs:220,
+// tree.rs:189-280, predict.rs:148-527, squeeze.rs:144-195, rct.rs:9-40) that the host front-end already uses for the
+// LF image and the HF metadata of VarDCT frames; here it runs over every ModularHF section and the global inverse
+// transforms (jxg::decode_modular_frame_cpu), followed by ConvertI32ToU8 (render/stages/convert.rs:642). The device
+// path re-implements exactly these pieces as CUDA kernels and never calls this file.
+// Pinning: lossless round trips of the synthetic Modular writer (decoded == source image, bit-exact) and the
+// reference's Modular fixtures decoding with every ANS stream ending in its checksum state.
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "../jxl_rs_b200/csrc/host/modular_frame.h"
+#include "oracle.h"
+
+extern std::string g_jxo_modular_error;
+std::string g_jxo_modular_error;
+
+extern "C" {
+
+const char* jxo_modular_last_error(void) { return g_jxo_modular_error.c_str(); }
+
+int jxo_modular_info(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint32_t* channels,
+                     uint32_t* num_groups) {
+  try {
+    auto ms = jxg::parse_modular_file(data, size);
+    *width = ms->header.xsize();
+    *height = ms->header.ysize();
+    *channels = ms->num_color_channels;
+    *num_groups = ms->header.num_groups();
+    return 0;
+  } catch (jxg::Error& e) {
+    g_jxo_modular_error = e.what();
+    return e.code;
+  }
+}
+
+// out: interleaved RGB u8 (grey is replicated); planes (optional): 3 full-size i32 planes before the u8 conversion.
+int jxo_decode_modular_file(const uint8_t* data, size_t size, uint8_t* out, size_t out_row_stride, int32_t* planes) {
+  try {
+    auto ms = jxg::parse_modular_file(data, size);
+    std::vector<jxg::ModularChannel> ch = jxg::decode_modular_frame_cpu(*ms);
+    const uint32_t w = ms->header.xsize(), h = ms->header.ysize();
+    for (uint32_t c = 0; c < 3; c++) {
+      const jxg::ModularChannel& src = ch[std::min<size_t>(c, ch.size() - 1)];
+      if (src.w != w || src.h != h) throw jxg::Error(jxg::kErrBitstream, "unexpected output channel size");
+      if (planes) memcpy(planes + size_t(c) * w * h, src.data.data(), size_t(w) * h * 4);
+      for (uint32_t y = 0; y < h; y++) {
+        const int32_t* r = src.row(y);
+        uint8_t* o = out + size_t(y) * out_row_stride + c;
+        for (uint32_t x = 0; x < w; x++) o[size_t(x) * 3] = uint8_t(std::min(std::max(r[x], 0), 255));  // convert.rs:675-680
+      }
+    }
+    return 0;
+  } catch (jxg::Error& e) {
+    g_jxo_modular_error = e.what();
+    return e.code;
+  }
+}
+
+}  // extern "C"

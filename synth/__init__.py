@@ -18,6 +18,11 @@ def _lib():
         _LIB.jxs_encode_synthetic.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_float, C.c_uint32, C.c_uint32,
                                               C.c_uint32, C.c_void_p, C.c_size_t]
         _LIB.jxs_last_error.restype = C.c_char_p
+        _LIB.jxs_encode_modular.restype = C.c_int64
+        _LIB.jxs_encode_modular.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.c_size_t]
+        _LIB.jxs_modular_source.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+        _LIB.jxs_modular_last_error.restype = C.c_char_p
     return _LIB
 
 
@@ -33,4 +38,36 @@ def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, prof
     if n > cap:
         buf = C.create_string_buffer(n)
         n = lib.jxs_encode_synthetic(width, height, seed, distance, epf_iters, gab, profile, buf, n)
+    return buf.raw[:n]
+
+
+def modular_source(width, height, seed):
+    """The 8-bit RGB image (H x W x 3 numpy array) the synthetic Modular frame of `seed` encodes losslessly."""
+    import numpy as np
+    lib = _lib()
+    out = np.zeros((height, width, 3), np.uint8)
+    if lib.jxs_modular_source(width, height, seed, out.ctypes.data) != 0:
+        raise RuntimeError("synthetic source failed: " + lib.jxs_modular_last_error().decode())
+    return out
+
+
+def encode_modular(width, height, seed, rct=6, squeeze=0, tree_kind=1, source=None) -> bytes:
+    """One synthetic lossless Modular frame (8-bit RGB, group size 256). rct: 0 or 6 (YCoCg); squeeze: default
+    Squeeze transform on/off; tree_kind: 0 single Gradient leaf, 1 property tree, 2 weighted-predictor tree.
+    source: optional H x W x 3 uint8 array to encode instead of the procedural image."""
+    lib = _lib()
+    src = None
+    if source is not None:
+        import numpy as np
+        source = np.ascontiguousarray(source, dtype=np.uint8)
+        assert source.shape == (height, width, 3)
+        src = source.ctypes.data
+    cap = max(1 << 16, width * height * 4)
+    buf = C.create_string_buffer(cap)
+    n = lib.jxs_encode_modular(width, height, seed, rct, squeeze, tree_kind, src, buf, cap)
+    if n < 0:
+        raise RuntimeError("synthetic Modular encode failed: " + lib.jxs_modular_last_error().decode())
+    if n > cap:
+        buf = C.create_string_buffer(n)
+        n = lib.jxs_encode_modular(width, height, seed, rct, squeeze, tree_kind, src, buf, n)
     return buf.raw[:n]

@@ -776,6 +776,16 @@ std::vector<uint8_t> encode(const Params& p) {
   return bytes;
 }
 
+// 8-bit RGB rendering of the same procedural image (source of the synthetic Modular frames).
+void make_image_u8(uint32_t width, uint32_t height, uint64_t seed, std::vector<uint8_t>& rgb) {
+  Params p{width, height, seed, 1.0f, 0, 0, 0, 0};
+  std::vector<float> img[3];
+  make_image(p, img);
+  rgb.resize(size_t(width) * height * 3);
+  for (size_t i = 0; i < size_t(width) * height; i++)
+    for (int c = 0; c < 3; c++) rgb[i * 3 + c] = uint8_t(std::lround(std::min(1.0f, std::max(0.0f, img[c][i])) * 255.0f));
+}
+
 }  // namespace jxs
 
 extern "C" {

@@ -74,3 +74,35 @@ def decode_file(data: bytes, fmt=abi.FORMAT_RGB_U8, taps=False, threads=0):
     if r != 0:
         raise abi.JxgError(r, lib.jxo_last_error().decode())
     return out, tap_arrays
+
+
+def _load_modular():
+    lib = load()
+    if not getattr(lib, "_modular_ready", False):
+        lib.jxo_modular_last_error.restype = C.c_char_p
+        lib.jxo_modular_info.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_uint32)] * 4
+        lib.jxo_decode_modular_file.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib._modular_ready = True
+    return lib
+
+
+def modular_info(data: bytes):
+    """(width, height, colour channels, groups) of a Modular-encoded file."""
+    lib = _load_modular()
+    v = [C.c_uint32() for _ in range(4)]
+    r = lib.jxo_modular_info(data, len(data), *v)
+    if r != 0:
+        raise abi.JxgError(r, lib.jxo_modular_last_error().decode())
+    return tuple(x.value for x in v)
+
+
+def decode_modular_file(data: bytes, planes=False):
+    """CPU decode of a Modular frame: H x W x 3 u8 (and the 3 i32 planes before the u8 conversion)."""
+    lib = _load_modular()
+    w, h, _, _ = modular_info(data)
+    out = np.zeros((h, w, 3), np.uint8)
+    pl = np.zeros((3, h, w), np.int32) if planes else None
+    r = lib.jxo_decode_modular_file(data, len(data), out.ctypes.data, out.strides[0], pl.ctypes.data if planes else None)
+    if r != 0:
+        raise abi.JxgError(r, lib.jxo_modular_last_error().decode())
+    return (out, pl) if planes else out
