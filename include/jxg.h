@@ -201,6 +201,32 @@ int jxg_batch_add_parsed(void* batch, void* parsed, uint32_t output_format, void
  * pointers stay valid until jxg_parsed_free. */
 int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, const uint8_t** hf_bytes,
                     const uint64_t** sec_off, const uint32_t** sec_len, uint32_t* n_sections);
+
+/* ---- Modular frames (BASELINE config 5) ------------------------------------------------
+ * Seam: FullModularImage::read_stream for ModularHF sections (jxl/src/frame/modular/mod.rs:567,
+ * decode/bitstream.rs:134, decode/channel.rs:220) plus the inverse transforms (transforms/{rct,squeeze}.rs) and
+ * ConvertI32ToU8 (render/stages/convert.rs:642). The host front end (headers, LfGlobal incl. the global MA tree,
+ * section 0, ModularLF streams, group headers / local trees) is jxg_modular_parse_file; a Rust host would hand over
+ * the same state from Frame::decode_lf_global / decode_lf_group (frame/decode.rs:307-497).
+ * Device scope: 8-bit RGB / grey, one pass, global transforms RCT and Squeeze, group-local RCT, ANS or prefix codes,
+ * all 14 predictors incl. the weighted one, properties 0..15. Palette, LZ77 and reference-channel properties return
+ * JXG_ERR_UNSUPPORTED (no CPU fallback). Output: interleaved RGB u8 (grey replicated). */
+int jxg_modular_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info);
+void jxg_modular_parsed_free(void* parsed);
+int jxg_modular_batch_begin(void* ctx, void** batch);
+/* `parsed` must stay alive until jxg_modular_batch_end. */
+int jxg_modular_batch_add(void* batch, void* parsed, void* out, size_t out_row_stride, int out_is_device);
+/* Streams per warp of the decode kernel (1, 2 or 4; default 1). */
+int jxg_modular_batch_set_lanes(void* batch, int lanes_per_warp);
+int jxg_modular_batch_run(void* batch, void* cuda_stream);
+int jxg_modular_batch_wait(void* batch, uint32_t* first_bad_frame, uint32_t* first_bad_group);
+int jxg_modular_batch_rerun_device(void* batch, void* cuda_stream);
+/* Parity tap: final colour planes of frame f (3 x H x W i32, before the u8 conversion). */
+int jxg_modular_batch_read_planes(void* batch, uint32_t f, int32_t* out, size_t out_len);
+/* ms[0]: whole batch on the device, ms[1]: group-stream decode kernel (+ local RCT). */
+int jxg_modular_batch_stats(void* batch, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* kernel_launches, float* ms);
+void jxg_modular_batch_end(void* batch);
+
 const char* jxg_last_error(void);
 
 #ifdef __cplusplus

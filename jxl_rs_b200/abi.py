@@ -67,6 +67,9 @@ EXPORTS = [
     "jxg_batch_rerun_device", "jxg_batch_end", "jxg_batch_read_coeffs", "jxg_batch_read_xyb",
     "jxg_batch_set_debug_stop", "jxg_batch_set_profile", "jxg_batch_stage_times", "jxg_batch_stats", "jxg_parse_file", "jxg_parsed_free", "jxg_parsed_desc",
     "jxg_batch_add_parsed", "jxg_batch_set_deferred_copy", "jxg_last_error",
+    "jxg_modular_parse_file", "jxg_modular_parsed_free", "jxg_modular_batch_begin", "jxg_modular_batch_add",
+    "jxg_modular_batch_set_lanes", "jxg_modular_batch_run", "jxg_modular_batch_wait", "jxg_modular_batch_rerun_device",
+    "jxg_modular_batch_read_planes", "jxg_modular_batch_stats", "jxg_modular_batch_end",
 ]
 
 _LIB = None
@@ -103,6 +106,20 @@ def load_library():
     lib.jxg_batch_read_xyb.argtypes = [vp, C.c_uint32, C.c_int, vp, C.c_size_t]
     lib.jxg_batch_set_debug_stop.argtypes = [vp, C.c_int]
     lib.jxg_batch_set_deferred_copy.argtypes = [vp, C.c_int]
+    lib.jxg_modular_parse_file.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp), C.POINTER(JxgImageInfo)]
+    lib.jxg_modular_parsed_free.argtypes = [vp]
+    lib.jxg_modular_parsed_free.restype = None
+    lib.jxg_modular_batch_begin.argtypes = [vp, C.POINTER(vp)]
+    lib.jxg_modular_batch_add.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    lib.jxg_modular_batch_set_lanes.argtypes = [vp, C.c_int]
+    lib.jxg_modular_batch_run.argtypes = [vp, vp]
+    lib.jxg_modular_batch_wait.argtypes = [vp, u32p, u32p]
+    lib.jxg_modular_batch_rerun_device.argtypes = [vp, vp]
+    lib.jxg_modular_batch_read_planes.argtypes = [vp, C.c_uint32, vp, C.c_size_t]
+    lib.jxg_modular_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_float)]
+    lib.jxg_modular_batch_end.argtypes = [vp]
+    lib.jxg_modular_batch_end.restype = None
     lib.jxg_batch_set_profile.argtypes = [vp, C.c_int]
     lib.jxg_batch_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.jxg_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

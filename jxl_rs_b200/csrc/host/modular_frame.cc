@@ -272,21 +272,4 @@ std::unique_ptr<ModularFrameState> parse_modular_file(const uint8_t* data, size_
   return msp;
 }
 
-std::vector<ModularChannel> decode_modular_frame_cpu(ModularFrameState& ms) {
-  for (ModularGroupStream& st : ms.hf) {
-    if (st.empty) continue;
-    std::vector<ModularChannel> ch = rect_channels(ms, st.rects);
-    BitReader br(ms.codestream.data() + st.sec_off, st.sec_len);
-    br.skip_bits(st.header_bitpos);  // non-zero only in single-section frames
-    decode_modular_subbitstream(ch, size_t(st.stream_id), ms.has_global_tree ? &ms.global_tree : nullptr, br);
-    store_rects(ms, st.rects, ch);
-  }
-  std::vector<ModularChannel> full = ms.coded;
-  for (auto& c : full)
-    if (c.data.empty()) c.data.assign(size_t(c.w) * c.h, 0);
-  undo_transforms(full, ms.global_header, ms.file.bit_depth.bits_per_sample);
-  full.resize(std::min<size_t>(full.size(), ms.num_color_channels));
-  return full;
-}
-
 }  // namespace jxg

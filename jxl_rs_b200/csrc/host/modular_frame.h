@@ -68,8 +68,4 @@ struct ModularFrameState {
 // scope of the device path).
 std::unique_ptr<ModularFrameState> parse_modular_file(const uint8_t* data, size_t size);
 
-// CPU decode of every ModularHF stream + inverse transforms (reference semantics, used by the oracle and the CPU
-// baseline; the product decodes these streams on the GPU). Returns the final colour channels (i32, full size).
-std::vector<ModularChannel> decode_modular_frame_cpu(ModularFrameState& ms);
-
 }  // namespace jxg

@@ -148,7 +148,8 @@ class Batch:
 
     def close(self):
         if self._h.value:
-            self._lib.jxg_batch_end(self._h)
+            if self._ctx._h.value:  # a batch that outlives its context is abandoned, not freed through it
+                self._lib.jxg_batch_end(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -293,3 +294,101 @@ class PipelinedDecoder:
             self.pool.shutdown()
             for c in self.ctxs:
                 c.close()
+
+
+class ModularParsedFrame:
+    """A Modular-encoded .jxl file run through the host front-end (headers, TOC, LfGlobal with the global MA tree,
+    section 0, ModularLF streams, group headers): the state a Rust host holds when it reaches the ModularHF groups."""
+
+    def __init__(self, data: bytes):
+        self._lib = abi.load_library()
+        self._h = C.c_void_p()
+        self.info = abi.JxgImageInfo()
+        abi.check(self._lib, self._lib.jxg_modular_parse_file(data, len(data), C.byref(self._h), C.byref(self.info)))
+
+    @property
+    def width(self):
+        return self.info.width
+
+    @property
+    def height(self):
+        return self.info.height
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.jxg_modular_parsed_free(self._h)
+            self._h = C.c_void_p()
+
+
+class ModularBatch:
+    """jxg_modular_batch_*: Modular frames whose group streams are decoded together on the GPU."""
+
+    def __init__(self, ctx: JxgContext, lanes_per_warp: int = 1):
+        self._lib = ctx._lib
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        abi.check(self._lib, self._lib.jxg_modular_batch_begin(ctx._h, C.byref(self._h)))
+        abi.check(self._lib, self._lib.jxg_modular_batch_set_lanes(self._h, lanes_per_warp))
+        self.frames = []
+
+    def add(self, frame: ModularParsedFrame, out_ptr: int, row_stride: int, out_is_device: bool):
+        abi.check(self._lib, self._lib.jxg_modular_batch_add(self._h, frame._h, C.c_void_p(out_ptr), row_stride,
+                                                             1 if out_is_device else 0))
+        self.frames.append(frame)
+
+    def run(self, stream_ptr: int = 0):
+        abi.check(self._lib, self._lib.jxg_modular_batch_run(self._h, C.c_void_p(stream_ptr)))
+
+    def rerun_device(self, stream_ptr: int = 0):
+        abi.check(self._lib, self._lib.jxg_modular_batch_rerun_device(self._h, C.c_void_p(stream_ptr)))
+
+    def wait(self):
+        bf, bg = C.c_uint32(), C.c_uint32()
+        abi.check(self._lib, self._lib.jxg_modular_batch_wait(self._h, C.byref(bf), C.byref(bg)))
+
+    def stats(self):
+        h2d, d2h, launches = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ms = (C.c_float * 2)()
+        abi.check(self._lib, self._lib.jxg_modular_batch_stats(self._h, C.byref(h2d), C.byref(d2h), C.byref(launches), ms))
+        return {"h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "kernel_launches": launches.value, "device_ms": ms[0],
+                "decode_ms": ms[1]}
+
+    def read_planes(self, f: int):
+        import numpy as np
+        fr = self.frames[f]
+        out = np.zeros((3, fr.height, fr.width), np.int32)
+        abi.check(self._lib, self._lib.jxg_modular_batch_read_planes(self._h, f, out.ctypes.data, out.size))
+        return out
+
+    def close(self):
+        if self._h and self._h.value:
+            if self._ctx._h.value:  # a batch that outlives its context is abandoned, not freed through it
+                self._lib.jxg_modular_batch_end(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_modular_files(ctx: JxgContext, files, to_host: bool = True, lanes_per_warp: int = 1):
+    """Decodes a list of Modular .jxl byte strings on the GPU; returns H x W x 3 uint8 torch tensors."""
+    import torch
+    frames = [ModularParsedFrame(f) for f in files]
+    batch = ModularBatch(ctx, lanes_per_warp)
+    outs = []
+    try:
+        for fr in frames:
+            if to_host:
+                t = torch.empty((fr.height, fr.width, 3), dtype=torch.uint8).pin_memory()
+            else:
+                t = torch.empty((fr.height, fr.width, 3), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+            outs.append(t)
+            batch.add(fr, t.data_ptr(), fr.width * 3, not to_host)
+        batch.run()
+        batch.wait()
+    finally:
+        batch.close()
+    return outs

@@ -5,7 +5,7 @@
 // the scalar restatement in jxl_rs_b200/csrc/host/modular.cc (decode_channel <- modular/decode/channel.rs:220,
 // tree.rs:189-280, predict.rs:148-527, squeeze.rs:144-195, rct.rs:9-40) that the host front-end already uses for the
 // LF image and the HF metadata of VarDCT frames; here it runs over every ModularHF section and the global inverse
-// transforms (jxg::decode_modular_frame_cpu), followed by ConvertI32ToU8 (render/stages/convert.rs:642). The device
+// transforms (decode_modular_frame_cpu below), followed by ConvertI32ToU8 (render/stages/convert.rs:642). The device
 // path re-implements exactly these pieces as CUDA kernels and never calls this file.
 // Pinning: lossless round trips of the synthetic Modular writer (decoded == source image, bit-exact) and the
 // reference's Modular fixtures decoding with every ANS stream ending in its checksum state.
@@ -18,6 +18,36 @@
 
 extern std::string g_jxo_modular_error;
 std::string g_jxo_modular_error;
+
+namespace {
+
+// Every ModularHF section through the scalar sub-bitstream decoder (bitstream.rs:134), results stored at the group
+// rects of the full-size coded channels (mod.rs:150), then the global inverse transforms (mod.rs:820 run_transforms).
+std::vector<jxg::ModularChannel> decode_modular_frame_cpu(jxg::ModularFrameState& ms) {
+  for (jxg::ModularGroupStream& st : ms.hf) {
+    if (st.empty) continue;
+    std::vector<jxg::ModularChannel> ch;
+    for (const jxg::ModularRect& r : st.rects) ch.emplace_back(r.w, r.h, ms.coded[r.chan].hshift, ms.coded[r.chan].vshift);
+    jxg::BitReader br(ms.codestream.data() + st.sec_off, st.sec_len);
+    br.skip_bits(st.header_bitpos);  // non-zero only in single-section frames
+    jxg::decode_modular_subbitstream(ch, size_t(st.stream_id), ms.has_global_tree ? &ms.global_tree : nullptr, br);
+    for (size_t i = 0; i < st.rects.size(); i++) {
+      const jxg::ModularRect& r = st.rects[i];
+      if (!r.w || !r.h) continue;
+      jxg::ModularChannel& dst = ms.coded[r.chan];
+      if (dst.data.empty()) dst.data.assign(size_t(dst.w) * dst.h, 0);
+      for (uint32_t y = 0; y < r.h; y++) memcpy(dst.row(r.y0 + y) + r.x0, ch[i].row(y), size_t(r.w) * 4);
+    }
+  }
+  std::vector<jxg::ModularChannel> full = ms.coded;
+  for (auto& c : full)
+    if (c.data.empty()) c.data.assign(size_t(c.w) * c.h, 0);
+  jxg::undo_transforms(full, ms.global_header, ms.file.bit_depth.bits_per_sample);
+  full.resize(std::min<size_t>(full.size(), ms.num_color_channels));
+  return full;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -42,7 +72,7 @@ int jxo_modular_info(const uint8_t* data, size_t size, uint32_t* width, uint32_t
 int jxo_decode_modular_file(const uint8_t* data, size_t size, uint8_t* out, size_t out_row_stride, int32_t* planes) {
   try {
     auto ms = jxg::parse_modular_file(data, size);
-    std::vector<jxg::ModularChannel> ch = jxg::decode_modular_frame_cpu(*ms);
+    std::vector<jxg::ModularChannel> ch = decode_modular_frame_cpu(*ms);
     const uint32_t w = ms->header.xsize(), h = ms->header.ysize();
     for (uint32_t c = 0; c < 3; c++) {
       const jxg::ModularChannel& src = ch[std::min<size_t>(c, ch.size() - 1)];
