@@ -41,6 +41,11 @@ __constant__ float c_afv[256] = {
 __constant__ float c_dither[1024] = {
 #include "dither_table.inc"
 };
+// Same table in global memory: the vector store path indexes it with per-lane (x, y), which the constant cache
+// would serialise; consecutive lanes read consecutive words here.
+__device__ float g_dither[1024] = {
+#include "dither_table.inc"
+};
 
 // ===========================================================================
 // K1: entropy decode
@@ -2341,6 +2346,291 @@ __device__ __forceinline__ void filter_tile(const BatchDev& B, const FrameDev& F
   }
 }
 
+// ---------------------------------------------------------------------------
+// Vectorised interior path of the default filter configuration (Gaborish + EPF iters 2, halo 4): every thread owns
+// quads of 4 horizontally adjacent cells, loads rows with 16-byte shared-memory accesses, shares the 3-tap sums of
+// the difference maps between the four cells, and converts / stores its four pixels straight from registers.
+// Same arithmetic as the scalar path except for the association of a few float sums and the approximate
+// sqrt / divide of the sRGB curve (<= 3 ulp), both far inside the 1e-3 / 1 LSB parity tolerances.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float linear_to_srgb_fast(float v) {  // color/tf.rs:13-44
+  const float a = fabsf(v);
+  const float s = a * rsqrtf(fmaxf(a, 1e-30f));
+  float yp = 7.352629620e-1f, yq = 2.424867759e-2f;
+  yp = fmaf(yp, s, 1.474205315f);
+  yq = fmaf(yq, s, 9.258482155e-1f);
+  yp = fmaf(yp, s, 3.903842876e-1f);
+  yq = fmaf(yq, s, 1.340816930f);
+  yp = fmaf(yp, s, 5.287254571e-3f);
+  yq = fmaf(yq, s, 3.036675394e-1f);
+  yp = fmaf(yp, s, -5.135152395e-4f);
+  yq = fmaf(yq, s, 1.004519624e-2f);
+  const float r = a < 0.0031308f ? a * 12.92f : __fdividef(yp, yq);
+  return copysignf(r, v);
+}
+
+// EPF difference maps (channel-combined |a - right|, |a - below|) for the rows [r0, r1) of `src`, all quads.
+template <int WW, int NC>
+__device__ __forceinline__ void epf_maps_v4(const float* src, float* maps, int r0, int r1, float s0, float s1, float s2) {
+  constexpr int QW = WW / 4;
+  for (int q = threadIdx.x; q < QW * (r1 - r0); q += blockDim.x) {
+    const int ly = r0 + q / QW, o = ly * WW + (q % QW) * 4;
+    float dh[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      const float* p = src + c * NC + o;
+      const float4 m = ld4(p), d = ld4(p + WW);
+      const float r = p[4];
+      dh[0] = fmaf(fabsf(m.x - m.y), sc, dh[0]);
+      dh[1] = fmaf(fabsf(m.y - m.z), sc, dh[1]);
+      dh[2] = fmaf(fabsf(m.z - m.w), sc, dh[2]);
+      dh[3] = fmaf(fabsf(m.w - r), sc, dh[3]);
+      dv[0] = fmaf(fabsf(m.x - d.x), sc, dv[0]);
+      dv[1] = fmaf(fabsf(m.y - d.y), sc, dv[1]);
+      dv[2] = fmaf(fabsf(m.z - d.z), sc, dv[2]);
+      dv[3] = fmaf(fabsf(m.w - d.w), sc, dv[3]);
+    }
+    st4(maps + o, make_float4(dh[0], dh[1], dh[2], dh[3]));
+    st4(maps + NC + o, make_float4(dv[0], dv[1], dv[2], dv[3]));
+  }
+}
+
+__device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev& F, const float* src_planes, float* smem,
+                                               int x0, int y0) {
+  using C = FCfg<true, 2>;
+  constexpr int H = 4, WW = C::WW, WH = C::WH, NC = C::NC, QW = WW / 4;
+  static_assert(C::H == H && WW == 72 && WH == 40, "vector path is written for the halo-4 configuration");
+  float* bufA = smem;
+  float* bufB = smem + 3 * NC;
+  float* maps = smem + 6 * NC;
+  float* sig = maps + C::NMAPS * NC;
+  const int wx0 = x0 - H, wy0 = y0 - H;
+  // ---- load ----
+  for (int q = threadIdx.x; q < QW * WH; q += blockDim.x) {
+    const int ly = q / QW, o = ly * WW + (q % QW) * 4;
+    const float* g = src_planes + F.plane_base + size_t(wy0 + ly) * F.plane_stride + wx0 + (q % QW) * 4;
+#pragma unroll
+    for (int c = 0; c < 3; c++) st4(bufA + c * NC + o, __ldg(reinterpret_cast<const float4*>(g + c * F.plane_size)));
+  }
+  const int sbx0 = wx0 >> 3, sby0 = wy0 >> 3;
+  for (int idx = threadIdx.x; idx < C::SBW * C::SBH; idx += blockDim.x) {  // features/epf.rs:54-79
+    const int bx = sbx0 + idx % C::SBW, by = sby0 + idx / C::SBW;
+    float v = 0.0f;
+    if (bx < int(F.xb) && by < int(F.yb)) {
+      const size_t bidx = size_t(by) * F.xb + bx;
+      const int32_t raw_quant = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off)[bidx];
+      const uint32_t sharp = (B.blob + F.epf_off)[bidx];
+      const float sigma_quant = F.epf_quant_mul / (F.quant_scale * float(raw_quant) * -1.1715728752538099024f);
+      v = 1.0f / fminf(sigma_quant * F.epf_sharp_lut[sharp], -1e-4f);
+    }
+    sig[idx] = v;
+  }
+  __syncthreads();
+  // ---- Gaborish (gaborish.rs:40-88): rows 1..38, bufA -> bufB ----
+  for (int q = threadIdx.x; q < QW * (WH - 2); q += blockDim.x) {
+    const int ly = 1 + q / QW, o = ly * WW + (q % QW) * 4;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float k0 = F.gab_k0[c], k1 = F.gab_k1[c], k2 = F.gab_k2[c];
+      const float* p = bufA + c * NC + o;
+      const float4 u = ld4(p - WW), m = ld4(p), d = ld4(p + WW);
+      const float ml = p[-1], mr = p[4];
+      const float v0 = p[-WW - 1] + p[WW - 1], v1 = u.x + d.x, v2 = u.y + d.y, v3 = u.z + d.z, v4 = u.w + d.w,
+                  v5 = p[-WW + 4] + p[WW + 4];
+      float4 r;
+      r.x = fmaf(k2, v0 + v2, fmaf(k1, v1 + ml + m.y, m.x * k0));
+      r.y = fmaf(k2, v1 + v3, fmaf(k1, v2 + m.x + m.z, m.y * k0));
+      r.z = fmaf(k2, v2 + v4, fmaf(k1, v3 + m.y + m.w, m.z * k0));
+      r.w = fmaf(k2, v3 + v5, fmaf(k1, v4 + m.z + mr, m.w * k0));
+      st4(bufB + c * NC + o, r);
+    }
+  }
+  __syncthreads();
+  const float cs0 = F.epf_channel_scale[0], cs1 = F.epf_channel_scale[1], cs2 = F.epf_channel_scale[2];
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+  // ---- EPF stage 1 (epf1.rs): maps of bufB rows 1..38, then rows 3..36 -> bufA ----
+  epf_maps_v4<WW, NC>(bufB, maps, 1, WH - 1, cs0, cs1, cs2);
+  __syncthreads();
+  {
+    const float* Dh = maps;
+    const float* Dv = maps + NC;
+    const float sm = 1.65f, bsm = sm * F.epf_border_sad_mul;
+    for (int q = threadIdx.x; q < QW * (WH - 6); q += blockDim.x) {
+      const int ly = 3 + q / QW, lx = (q % QW) * 4, o = ly * WW + lx;
+      const int mx = wx0 + lx, my = wy0 + ly;
+      const float inv_sigma_px = sig[((my >> 3) - sby0) * C::SBW + ((mx >> 3) - sbx0)];
+      if (inv_sigma_px < kMinSigma) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) st4(bufA + c * NC + o, ld4(bufB + c * NC + o));
+        continue;
+      }
+      const bool rowb = ((my + 1) & 7) < 2;
+      const float is_n = inv_sigma_px * (rowb ? bsm : sm), is_b = inv_sigma_px * bsm;
+      const bool lo4 = (mx & 4) == 0;  // quad covers columns 0..3 (border at cell 0) or 4..7 (border at cell 3)
+      const float isg[4] = {lo4 ? is_b : is_n, is_n, is_n, lo4 ? is_n : is_b};
+      // plus-shaped sums of Dh at columns x-1 .. x+3 (left / right SADs of the four cells)
+      float ph[5];
+      {
+        const float* p = Dh + o;
+        const float2 l2 = *reinterpret_cast<const float2*>(p - 2);
+        const float4 m = ld4(p), u = ld4(p - WW), d = ld4(p + WW);
+        const float r = p[4], ul = p[-WW - 1], dl = p[WW - 1];
+        ph[0] = l2.x + l2.y + m.x + ul + dl;
+        ph[1] = l2.y + m.x + m.y + u.x + d.x;
+        ph[2] = m.x + m.y + m.z + u.y + d.y;
+        ph[3] = m.y + m.z + m.w + u.z + d.z;
+        ph[4] = m.z + m.w + r + u.w + d.w;
+      }
+      // plus-shaped sums of Dv at rows y-1 (up SAD) and y (down SAD)
+      float pu[4], pd[4];
+      {
+        const float* p = Dv + o;
+        const float4 a = ld4(p - 2 * WW), b = ld4(p - WW), m = ld4(p), e = ld4(p + WW);
+        const float bl = p[-WW - 1], br = p[-WW + 4], ml = p[-1], mr = p[4];
+        pu[0] = a.x + bl + b.x + b.y + m.x;
+        pu[1] = a.y + b.x + b.y + b.z + m.y;
+        pu[2] = a.z + b.y + b.z + b.w + m.z;
+        pu[3] = a.w + b.z + b.w + br + m.w;
+        pd[0] = b.x + ml + m.x + m.y + e.x;
+        pd[1] = b.y + m.x + m.y + m.z + e.y;
+        pd[2] = b.z + m.y + m.z + m.w + e.z;
+        pd[3] = b.w + m.z + m.w + mr + e.w;
+      }
+      float wu[4], wl[4], wr[4], wd[4], iw[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        wu[i] = fmaxf(fmaf(pu[i], isg[i], 1.0f), 0.0f);
+        wl[i] = fmaxf(fmaf(ph[i], isg[i], 1.0f), 0.0f);
+        wr[i] = fmaxf(fmaf(ph[i + 1], isg[i], 1.0f), 0.0f);
+        wd[i] = fmaxf(fmaf(pd[i], isg[i], 1.0f), 0.0f);
+        iw[i] = 1.0f / (1.0f + wu[i] + wl[i] + wr[i] + wd[i]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float* p = bufB + c * NC + o;
+        const float4 u = ld4(p - WW), m = ld4(p), d = ld4(p + WW);
+        const float ml = p[-1], mr = p[4];
+        float4 r;
+        r.x = fmaf(u.x, wu[0], fmaf(ml, wl[0], fmaf(m.y, wr[0], fmaf(d.x, wd[0], m.x)))) * iw[0];
+        r.y = fmaf(u.y, wu[1], fmaf(m.x, wl[1], fmaf(m.z, wr[1], fmaf(d.y, wd[1], m.y)))) * iw[1];
+        r.z = fmaf(u.z, wu[2], fmaf(m.y, wl[2], fmaf(m.w, wr[2], fmaf(d.z, wd[2], m.z)))) * iw[2];
+        r.w = fmaf(u.w, wu[3], fmaf(m.z, wl[3], fmaf(mr, wr[3], fmaf(d.w, wd[3], m.w)))) * iw[3];
+        st4(bufA + c * NC + o, r);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- EPF stage 2 (epf2.rs) on the 64x32 core + colour + store ----
+  epf_maps_v4<WW, NC>(bufA, maps, 3, WH - 3, cs0, cs1, cs2);
+  __syncthreads();
+  {
+    const float* Dh = maps;
+    const float* Dv = maps + NC;
+    const float sm = F.epf_pass2_sigma_scale * 1.65f, bsm = sm * F.epf_border_sad_mul;
+    const int w = int(F.width);
+    uint8_t* out_base = static_cast<uint8_t*>(F.out_ptr);
+    for (int q = threadIdx.x; q < (kTW / 4) * kTH; q += blockDim.x) {
+      const int ly = H + q / (kTW / 4), lx = H + (q % (kTW / 4)) * 4, o = ly * WW + lx;
+      const int mx = wx0 + lx, my = wy0 + ly;
+      float px[3][4];
+      const float inv_sigma_px = sig[((my >> 3) - sby0) * C::SBW + ((mx >> 3) - sbx0)];
+      if (inv_sigma_px < kMinSigma) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float4 m = ld4(bufA + c * NC + o);
+          px[c][0] = m.x; px[c][1] = m.y; px[c][2] = m.z; px[c][3] = m.w;
+        }
+      } else {
+        const bool rowb = ((my + 1) & 7) < 2;
+        const float is_n = inv_sigma_px * (rowb ? bsm : sm), is_b = inv_sigma_px * bsm;
+        const bool lo4 = (mx & 4) == 0;
+        const float isg[4] = {lo4 ? is_b : is_n, is_n, is_n, lo4 ? is_n : is_b};
+        const float4 su = ld4(Dv + o - WW), sd = ld4(Dv + o), sh = ld4(Dh + o);
+        const float shl = Dh[o - 1];
+        const float sup[4] = {su.x, su.y, su.z, su.w}, sdn[4] = {sd.x, sd.y, sd.z, sd.w};
+        const float shh[5] = {shl, sh.x, sh.y, sh.z, sh.w};
+        float wu[4], wl[4], wr[4], wd[4], iw[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          wu[i] = fmaxf(fmaf(sup[i], isg[i], 1.0f), 0.0f);
+          wl[i] = fmaxf(fmaf(shh[i], isg[i], 1.0f), 0.0f);
+          wr[i] = fmaxf(fmaf(shh[i + 1], isg[i], 1.0f), 0.0f);
+          wd[i] = fmaxf(fmaf(sdn[i], isg[i], 1.0f), 0.0f);
+          iw[i] = 1.0f / (1.0f + wu[i] + wl[i] + wr[i] + wd[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float* p = bufA + c * NC + o;
+          const float4 u = ld4(p - WW), m = ld4(p), d = ld4(p + WW);
+          const float ml = p[-1], mr = p[4];
+          // accumulation order of the reference: up, left, right, down (epf2.rs:83)
+          px[c][0] = fmaf(wd[0], d.x, fmaf(wr[0], m.y, fmaf(wl[0], ml, fmaf(wu[0], u.x, m.x)))) * iw[0];
+          px[c][1] = fmaf(wd[1], d.y, fmaf(wr[1], m.z, fmaf(wl[1], m.x, fmaf(wu[1], u.y, m.y)))) * iw[1];
+          px[c][2] = fmaf(wd[2], d.z, fmaf(wr[2], m.w, fmaf(wl[2], m.y, fmaf(wu[2], u.z, m.z)))) * iw[2];
+          px[c][3] = fmaf(wd[3], d.w, fmaf(wr[3], mr, fmaf(wl[3], m.z, fmaf(wu[3], u.w, m.w)))) * iw[3];
+        }
+      }
+      const int gx = mx, gy = my;
+      if (F.output_format == JXG_FORMAT_XYB_F32_PLANAR) {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          st4(reinterpret_cast<float*>(out_base + (size_t(c) * F.height + gy) * F.out_row_stride) + gx,
+              make_float4(px[c][0], px[c][1], px[c][2], px[c][3]));
+        continue;
+      }
+      float rgb[4][3];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {  // xyb.rs:197-241
+        float l = px[1][i] + px[0][i] - F.bias_cbrt[0], mm = px[1][i] - px[0][i] - F.bias_cbrt[1], s = px[2][i] - F.bias_cbrt[2];
+        const float l2 = l * l, m2 = mm * mm, s2 = s * s;
+        l = fmaf(l2, l * F.intensity_scale, F.scaled_bias[0]);
+        mm = fmaf(m2, mm * F.intensity_scale, F.scaled_bias[1]);
+        s = fmaf(s2, s * F.intensity_scale, F.scaled_bias[2]);
+        rgb[i][0] = fmaf(F.opsin[0], l, fmaf(F.opsin[1], mm, F.opsin[2] * s));
+        rgb[i][1] = fmaf(F.opsin[3], l, fmaf(F.opsin[4], mm, F.opsin[5] * s));
+        rgb[i][2] = fmaf(F.opsin[6], l, fmaf(F.opsin[7], mm, F.opsin[8] * s));
+        if (F.output_tf == JXG_TF_SRGB) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) rgb[i][c] = linear_to_srgb_fast(rgb[i][c]);
+        }
+      }
+      (void)w;
+      if (F.output_format == JXG_FORMAT_RGB_F32) {
+        float* d = reinterpret_cast<float*>(out_base + size_t(gy) * F.out_row_stride) + size_t(gx) * 3;
+        st4(d, make_float4(rgb[0][0], rgb[0][1], rgb[0][2], rgb[1][0]));
+        st4(d + 4, make_float4(rgb[1][1], rgb[1][2], rgb[2][0], rgb[2][1]));
+        st4(d + 8, make_float4(rgb[2][2], rgb[3][0], rgb[3][1], rgb[3][2]));
+        continue;
+      }
+      uint32_t b8[4][3];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {  // convert.rs:574-598 (blue-noise dither)
+          const float dth = g_dither[((gy + 13 * c) & 31) * 32 + ((gx + i + 23 * c) & 31)];
+          b8[i][c] = uint32_t(__float2int_rn(fminf(fmaxf(fmaf(rgb[i][c], 255.0f, dth), 0.0f), 255.0f)));
+        }
+      if (F.output_format == JXG_FORMAT_RGB_U8) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(out_base + size_t(gy) * F.out_row_stride + size_t(gx) * 3);
+        d[0] = b8[0][0] | (b8[0][1] << 8) | (b8[0][2] << 16) | (b8[1][0] << 24);
+        d[1] = b8[1][1] | (b8[1][2] << 8) | (b8[2][0] << 16) | (b8[2][1] << 24);
+        d[2] = b8[2][2] | (b8[3][0] << 8) | (b8[3][1] << 16) | (b8[3][2] << 24);
+      } else {
+        uint4 v;
+        v.x = b8[0][0] | (b8[0][1] << 8) | (b8[0][2] << 16) | 0xff000000u;
+        v.y = b8[1][0] | (b8[1][1] << 8) | (b8[1][2] << 16) | 0xff000000u;
+        v.z = b8[2][0] | (b8[2][1] << 8) | (b8[2][2] << 16) | 0xff000000u;
+        v.w = b8[3][0] | (b8[3][1] << 8) | (b8[3][2] << 16) | 0xff000000u;
+        *reinterpret_cast<uint4*>(out_base + size_t(gy) * F.out_row_stride + size_t(gx) * 4) = v;
+      }
+    }
+  }
+}
+
 template <bool GAB, int EPF>
 __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
   using C = FCfg<GAB, EPF>;
@@ -2358,8 +2648,15 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
   const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
   const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
   const bool interior = x0 - C::H >= 0 && y0 - C::H >= 0 && x0 + kTW + C::H <= int(F.width) && y0 + kTH + C::H <= int(F.height);
-  if (interior) filter_tile<GAB, EPF, true>(B, F, src_planes, smem, x0, y0);
-  else filter_tile<GAB, EPF, false>(B, F, src_planes, smem, x0, y0);
+  if (interior) {
+    // 16-byte accesses need an aligned output row (RGB8: stride and base multiples of 4, f32 / RGBA: of 16)
+    const uintptr_t oa = reinterpret_cast<uintptr_t>(F.out_ptr) | uintptr_t(F.out_row_stride);
+    const bool aligned = F.output_format == JXG_FORMAT_RGB_U8 ? (oa & 3) == 0 : (oa & 15) == 0;
+    if (GAB && EPF == 2 && aligned) filter_tile_v4(B, F, src_planes, smem, x0, y0);
+    else filter_tile<GAB, EPF, true>(B, F, src_planes, smem, x0, y0);
+  } else {
+    filter_tile<GAB, EPF, false>(B, F, src_planes, smem, x0, y0);
+  }
 }
 
 template <bool GAB, int EPF>
