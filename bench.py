@@ -51,13 +51,30 @@ def frame_seeds(n, rank):
     return [2000 + rank * n + i for i in range(n)]
 
 
+def host_cores():
+    """Host threads really available to this process (cgroup CPU quota and affinity included; the GPU boxes of this
+    pool expose 128 logical CPUs but grant 16)."""
+    from jxl_rs_b200.decoder import effective_cpus
+    return effective_cpus()
+
+
+def kernel_traffic(kernel, frames):
+    """ncu dram__bytes_read + dram__bytes_write of the dominant kernel per launch (profiles/r01_traffic.json, taken
+    at 64 frames; scaled linearly to the batch size), or None when no capture exists for that kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        return t["dram_bytes_per_launch"] * frames / t["frames"]
+    except Exception:
+        return None
+
+
 def make_frames(args, rank):
     """Synthetic .jxl byte strings for this rank (outside every timed region)."""
     import synth
     n = args.frames
     uniq = n if args.unique <= 0 else min(args.unique, n)
     seeds = frame_seeds(n, rank)[:uniq]
-    workers = max(1, min(uniq, (os.cpu_count() or 8)))
+    workers = max(1, min(uniq, host_cores()))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         files = list(ex.map(lambda s: synth.encode_synthetic(args.width, args.height, s, args.distance, args.epf, 1, args.profile), seeds))
     return [files[i % uniq] for i in range(n)]
@@ -139,7 +156,7 @@ def run_reference(args, rank, world):
     oracle port of the same path (kind="port") with all host threads, on a bounded sample per step."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     sample = max(1, min(args.cpu_sample_frames, args.frames))
     a2 = argparse.Namespace(**vars(args))
     a2.frames = sample
@@ -200,7 +217,7 @@ def main():
     # Two copies of the batch stay resident on two contexts (own CUDA stream + buffer pools each) and the
     # timed steps alternate between them, so that consecutive steps overlap on the device (entropy decode of
     # one batch is latency-bound and leaves issue slots to the transforms/filters of the other).
-    with ThreadPoolExecutor(max_workers=min(n, os.cpu_count() or 8)) as ex:
+    with ThreadPoolExecutor(max_workers=min(n, host_cores())) as ex:
         frames = list(ex.map(j.ParsedFrame, files))
     depth = max(1, args.inflight)
     ctxs = [ctx] + [j.JxgContext(local_rank) for _ in range(depth - 1)]
@@ -297,7 +314,7 @@ def main():
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
         pipeline_gbs = alg_bytes / (ms_per_step / 1e3) / 1e9
         # CPU baseline on a bounded sample (oracle port, all host threads)
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         sample = max(1, min(args.cpu_sample_frames, n))
         cpu_sec = cpu_decode_batch(files[:sample], cores)
         cpu_v = args.width * args.height * sample / 1e6 / cpu_sec
@@ -314,11 +331,12 @@ def main():
                 "sharding": "frames partitioned by rank, no data-path collective",
                 "stage_ms_single_batch": stage_acc, "single_batch_ms": single_ms, "batches_in_flight": depth,
                 "e2e_pipeline": "whole batches, 2 in flight (host parse/staging of batch k+1 overlaps GPU + D2H of batch k)",
+                "host_cores": cores,
                 "pipeline_alg_gbs": pipeline_gbs,
                 "alg_bytes_per_step": alg_bytes,
             },
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": kernel_traffic(dom, n), "peak_source": peak_src,
                          "kernel_ms": dom_ms},
             "cpu_baseline": {"value": cpu_v, "unit": "MP/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} frames of {args.width}x{args.height}, oracle port, {cpu_sec:.1f} s"},

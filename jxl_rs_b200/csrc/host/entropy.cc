@@ -568,42 +568,7 @@ SymbolReader::SymbolReader(const EntropyCode& code, BitReader& br, size_t dist_m
   if (!code.use_prefix) state_ = uint32_t(br.read(32));  // ans.rs:431
 }
 
-inline uint32_t SymbolReader::read_token(BitReader& br, uint32_t cluster) {
-  if (code_.use_prefix) {  // huffman.rs:446-457
-    const HuffEntry* t = &code_.huff_entries[code_.huff_offset[cluster]];
-    size_t pos = size_t(br.peek(kHuffTableBits));
-    uint32_t n_bits = t[pos] & 0xff;
-    if (n_bits > kHuffTableBits) {
-      br.consume(kHuffTableBits);
-      n_bits -= kHuffTableBits;
-      pos += t[pos] >> 16;
-      pos += size_t(br.peek(n_bits));
-    }
-    HuffEntry e = t[pos];
-    br.consume(e & 0xff);
-    return e >> 16;
-  }
-  // ans.rs:356-393
-  const uint32_t log_bucket = kAnsLogSumProbs - code_.log_alpha_size;
-  uint32_t idx = state_ & 0xfff;
-  uint32_t i = idx >> log_bucket;
-  uint32_t pos = idx & ((1u << log_bucket) - 1);
-  const AnsBucket& b = code_.ans_buckets[(size_t(cluster) << code_.log_alpha_size) + i];
-  bool alias = pos >= b.alias_cutoff;
-  uint32_t offset = (alias ? b.alias_offset : 0) + pos;
-  uint32_t dist = uint32_t(b.dist) ^ (alias ? b.alias_dist_xor : 0);
-  uint32_t symbol = alias ? b.alias_symbol : i;
-  uint32_t next = (state_ >> kAnsLogSumProbs) * dist + offset;
-  if (next < (1u << 16)) {
-    next = (next << 16) | uint32_t(br.peek(16));
-    br.consume(16);
-  }
-  state_ = next;
-  return symbol;
-}
-
-uint32_t SymbolReader::read_clustered(BitReader& br, uint32_t cluster) {
-  if (!code_.lz77_enabled) return code_.uint_configs[cluster].read(read_token(br, cluster), br);
+uint32_t SymbolReader::read_clustered_lz77(BitReader& br, uint32_t cluster) {
   constexpr uint32_t kWindowMask = (1u << 20) - 1;
   auto push = [&](uint32_t v) {
     size_t off = num_decoded_ & kWindowMask;

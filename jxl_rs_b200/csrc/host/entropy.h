@@ -32,6 +32,9 @@ struct HybridUint {
   }
 };
 
+constexpr uint32_t kAnsChecksum = 0x130000;  // ans.rs:425
+constexpr uint32_t kAnsLogSumProbs = 12;
+
 // ans.rs:31-39 — 8-byte alias-table bucket, same field order and widths.
 struct AnsBucket {
   uint8_t alias_symbol;
@@ -72,8 +75,6 @@ struct EntropyCode {
   static EntropyCode decode_prefix_codes_for_test(size_t num_clusters, BitReader& br);
 };
 
-constexpr uint32_t kAnsChecksum = 0x130000;  // ans.rs:425
-constexpr uint32_t kAnsLogSumProbs = 12;
 
 // decode.rs:177-405 (host copy; the device kernel has its own).
 class SymbolReader {
@@ -81,12 +82,49 @@ class SymbolReader {
   SymbolReader(const EntropyCode& code, BitReader& br, size_t dist_multiplier);
   uint32_t read_unsigned(BitReader& br, size_t ctx) { return read_clustered(br, code_.context_map[ctx]); }
   int32_t read_signed(BitReader& br, size_t ctx) { return unpack_signed(read_unsigned(br, ctx)); }
-  uint32_t read_clustered(BitReader& br, uint32_t cluster);
+  inline uint32_t read_clustered(BitReader& br, uint32_t cluster) {
+    if (!code_.lz77_enabled) return code_.uint_configs[cluster].read(read_token(br, cluster), br);
+    return read_clustered_lz77(br, cluster);
+  }
   // decode.rs:400: latched errors, over-read, final ANS state.
   void check_final_state(BitReader& br) const;
 
  private:
-  inline uint32_t read_token(BitReader& br, uint32_t cluster);
+  uint32_t read_clustered_lz77(BitReader& br, uint32_t cluster);
+  // ans.rs:356-393 / huffman.rs:446-457 (in the header so that the per-pixel Modular loops inline it)
+  inline uint32_t read_token(BitReader& br, uint32_t cluster) {
+    if (code_.use_prefix) {
+      constexpr unsigned kRootBits = 8;
+      const HuffEntry* t = &code_.huff_entries[code_.huff_offset[cluster]];
+      size_t pos = size_t(br.peek(kRootBits));
+      uint32_t n_bits = t[pos] & 0xff;
+      if (n_bits > kRootBits) {
+        br.consume(kRootBits);
+        n_bits -= kRootBits;
+        pos += t[pos] >> 16;
+        pos += size_t(br.peek(n_bits));
+      }
+      HuffEntry e = t[pos];
+      br.consume(e & 0xff);
+      return e >> 16;
+    }
+    const uint32_t log_bucket = kAnsLogSumProbs - code_.log_alpha_size;
+    uint32_t idx = state_ & 0xfff;
+    uint32_t i = idx >> log_bucket;
+    uint32_t pos = idx & ((1u << log_bucket) - 1);
+    const AnsBucket& b = code_.ans_buckets[(size_t(cluster) << code_.log_alpha_size) + i];
+    bool alias = pos >= b.alias_cutoff;
+    uint32_t offset = (alias ? b.alias_offset : 0) + pos;
+    uint32_t dist = uint32_t(b.dist) ^ (alias ? b.alias_dist_xor : 0);
+    uint32_t symbol = alias ? b.alias_symbol : i;
+    uint32_t next = (state_ >> kAnsLogSumProbs) * dist + offset;
+    if (next < (1u << 16)) {
+      next = (next << 16) | uint32_t(br.peek(16));
+      br.consume(16);
+    }
+    state_ = next;
+    return symbol;
+  }
   const EntropyCode& code_;
   uint32_t state_ = kAnsChecksum;
   // LZ77 (decode.rs:73-147)

@@ -271,9 +271,89 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
   props[0] = int32_t(ci);
   props[1] = int32_t(stream_id);
   const bool use_wp = tree.uses_wp;
-  WpState wp(header.wp, use_wp ? w : 0);
   const TreeNode* nodes = tree.nodes.data();
-  // Fast path: a single-leaf tree.
+  // ---- specialised walks (same semantics as the generic loop below; the reference keeps a family of these in
+  // decode/specialized_trees.rs). Which properties do the decision nodes look at?
+  uint32_t used_mask = 0;
+  bool wide_props = false;
+  for (const TreeNode& nd : tree.nodes)
+    if (nd.property >= 0) {
+      if (nd.property < 32) used_mask |= 1u << nd.property;
+      if (nd.property >= 16) wide_props = true;
+    }
+  if (!use_wp && !wide_props && (used_mask & ~3u) == 0) {
+    // Only channel / stream id are tested: one leaf for the whole channel.
+    const TreeNode* nd = nodes;
+    while (nd->property >= 0) nd = nodes + (props[nd->property] > nd->val ? nd->left : nd->right);
+    const uint32_t pred = nd->left, ctx = nd->ctx;
+    const int64_t offset = nd->val, mul = nd->right;
+    for (size_t y = 0; y < h; y++) {
+      int32_t* row = ch.row(uint32_t(y));
+      const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+      const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+      if (pred == kGradient) {
+        for (size_t x = 0; x < w; x++) {
+          const int64_t left = x > 0 ? row[x - 1] : (y > 0 ? top_row[0] : 0);
+          const int64_t top = y > 0 ? top_row[x] : left;
+          const int64_t topleft = (x > 0 && y > 0) ? top_row[x - 1] : left;
+          const int64_t guess = clamped_gradient(left, top, topleft) + offset;
+          row[x] = int32_t(guess + mul * int64_t(reader.read_signed(br, ctx)));
+        }
+      } else if (pred == kZero) {
+        for (size_t x = 0; x < w; x++) row[x] = int32_t(offset + mul * int64_t(reader.read_signed(br, ctx)));
+      } else {
+        for (size_t x = 0; x < w; x++) {
+          Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
+          const int64_t guess = predict_one(pred, n, 0) + offset;
+          row[x] = int32_t(guess + mul * int64_t(reader.read_signed(br, ctx)));
+        }
+      }
+    }
+    br.check();
+    return;
+  }
+  if (!use_wp && !wide_props) {
+    // No weighted predictor: evaluate only the properties the walk actually visits.
+    for (size_t y = 0; y < h; y++) {
+      int32_t* row = ch.row(uint32_t(y));
+      const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+      const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+      int32_t prev_p9 = 0;
+      for (size_t x = 0; x < w; x++) {
+        const Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
+        const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
+        const TreeNode* nd = nodes;
+        while (nd->property >= 0) {
+          int32_t v;
+          switch (nd->property) {
+            case 0: v = int32_t(ci); break;
+            case 1: v = int32_t(stream_id); break;
+            case 2: v = int32_t(y); break;
+            case 3: v = int32_t(x); break;
+            case 4: v = wabs(n.top); break;
+            case 5: v = wabs(n.left); break;
+            case 6: v = n.top; break;
+            case 7: v = n.left; break;
+            case 8: v = wsub(n.left, prev_p9); break;
+            case 9: v = p9; break;
+            case 10: v = wsub(n.left, n.topleft); break;
+            case 11: v = wsub(n.topleft, n.top); break;
+            case 12: v = wsub(n.top, n.topright); break;
+            case 13: v = wsub(n.top, n.toptop); break;
+            case 14: v = wsub(n.left, n.leftleft); break;
+            default: v = 0; break;  // property 15 without the weighted predictor is always 0
+          }
+          nd = nodes + (v > nd->val ? nd->left : nd->right);
+        }
+        prev_p9 = p9;
+        const int64_t guess = predict_one(nd->left, n, 0) + int64_t(nd->val);
+        row[x] = int32_t(guess + int64_t(nd->right) * int64_t(reader.read_signed(br, nd->ctx)));
+      }
+    }
+    br.check();
+    return;
+  }
+  WpState wp(header.wp, use_wp ? w : 0);
   for (size_t y = 0; y < h; y++) {
     int32_t* row = ch.row(uint32_t(y));
     const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;

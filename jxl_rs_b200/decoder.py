@@ -182,6 +182,30 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
     return outs
 
 
+def effective_cpus() -> int:
+    """Host threads this process can really run at once: min(cpu_count, affinity mask, cgroup v2/v1 CPU quota)."""
+    import math
+    import os
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, math.ceil(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                n = min(n, max(1, math.ceil(q / p)))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 class PipelinedDecoder:
     """Streaming decode of many batches. `submit()` only queues a batch: its files start parsing on the worker
     pool at once (so parsing of batch k+1.. overlaps everything else) and a dispatcher thread stages each batch
@@ -190,7 +214,7 @@ class PipelinedDecoder:
     front-end work of batch k+1 therefore overlaps the kernels and the D2H copies of batch k.
     This is the serving-shaped entry point (many independent images in flight)."""
 
-    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0, staging_threads: int = 8, parse_ahead: int = 2):
+    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0, staging_threads: int = 4, parse_ahead: int = 2):
         import os
         import queue
         import threading
@@ -199,7 +223,7 @@ class PipelinedDecoder:
         self.ctxs = [JxgContext(device) for _ in range(depth)]
         self.depth = depth
         self.staging_threads = staging_threads
-        self.pool = ThreadPoolExecutor(max_workers=workers or min(64, os.cpu_count() or 8))
+        self.pool = ThreadPoolExecutor(max_workers=workers or min(64, effective_cpus()))
         self.inflight = deque()
         self.k = 0
         self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0, "kernel_launches": 0}
