@@ -48,6 +48,7 @@ struct Batch {
   std::vector<SectionDev> sections;
   std::vector<StreamDev> streams, streams_lean, streams_fast, streams_slow;
   bool lean_all_420 = true;
+  bool lean_ctx_smem = true;  // every lean frame's context map (+64 spill) fits k_entropy_lean's 16 KB staging area
   uint32_t lean_S = 1, lean_ctas = 0;  // k_entropy_lean schedule (see schedule_lean)
   std::vector<uint32_t> lean_cta_first;
   std::vector<uint64_t> nz_base;
@@ -310,6 +311,9 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
     b->sections.push_back(sd);
   }
 #undef APPEND
+  if (F.num_passes == 1 && !F.passes[0].use_prefix && F.passes[0].shift == 0 &&
+      size_t(F.num_histograms) * F.num_block_contexts * 495 + 64 > 16384)
+    b->lean_ctx_smem = false;
   if (F.num_passes == 1 && !F.passes[0].use_prefix)
     for (uint32_t c = 0; c < d->passes[0].num_clusters; c++)
       if (d->passes[0].uint_configs[c] != (4u | (2u << 8))) b->lean_all_420 = false;
@@ -378,31 +382,48 @@ static void schedule_lean(Batch* b) {
   std::stable_sort(b->streams_lean.begin(), b->streams_lean.end(), [&](const StreamDev& x, const StreamDev& y) {
     return x.frame != y.frame ? x.frame < y.frame : len_of(x) > len_of(y);
   });
-  float mul = 2.0f;
+  float mul = 1.6f;
   if (const char* e = getenv("JXG_ENTROPY_LANES_MUL")) mul = float(atof(e));  // experiment knobs
   const size_t nf = b->frames.size();
   std::vector<uint32_t> lanes(nf, 0);
+  std::vector<uint64_t> f_total(nf, 0), f_longest(nf, 1);
   for (auto& F : b->frames) F.lean_first = F.lean_count = F.lean_cta_first = F.lean_ctas = 0;
-  uint64_t total_lanes = 0;
   for (size_t i = 0; i < b->streams_lean.size();) {
     const uint32_t f = b->streams_lean[i].frame;
     size_t j = i;
     uint64_t total = 0;
     while (j < b->streams_lean.size() && b->streams_lean[j].frame == f) total += len_of(b->streams_lean[j++]) + 64;
-    const uint64_t longest = len_of(b->streams_lean[i]) + 64;
     b->frames[f].lean_first = uint32_t(i);
     b->frames[f].lean_count = uint32_t(j - i);
-    lanes[f] = uint32_t(std::min<uint64_t>(j - i, std::max<uint64_t>(1, uint64_t(mul * float(total) / float(longest)))));
-    total_lanes += lanes[f];
+    f_total[f] = total;
+    f_longest[f] = len_of(b->streams_lean[i]) + 64;
     i = j;
   }
-  // lanes per warp: keep the grid near one resident wave of 4 warps per scheduler (592 schedulers)
-  uint32_t S = total_lanes <= 2368 ? 1 : (total_lanes <= 2 * 2368 ? 2 : (total_lanes <= 4 * 2368 ? 4 : 8));
-  if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
-  S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
+  // The kernel keeps 6 CTAs per SM resident (register bound); more CTAs than that would only start after the first
+  // ones end, so the lane multiplier is lowered until the grid fits one resident wave.
+  const uint32_t max_ctas = 148 * 6;
+  uint32_t S = 1, ctas = 0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    uint64_t total_lanes = 0;
+    for (size_t f = 0; f < nf; f++) {
+      lanes[f] = b->frames[f].lean_count
+                     ? uint32_t(std::min<uint64_t>(b->frames[f].lean_count,
+                                                   std::max<uint64_t>(1, uint64_t(mul * float(f_total[f]) / float(f_longest[f])))))
+                     : 0;
+      total_lanes += lanes[f];
+    }
+    // lanes per warp: keep the grid near one resident wave of 3 warps per scheduler
+    S = total_lanes <= 2368 ? 1 : (total_lanes <= 2 * 2368 ? 2 : 4);
+    if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
+    S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
+    ctas = 0;
+    for (size_t f = 0; f < nf; f++) ctas += lanes[f] ? (lanes[f] + 4 * S - 1) / (4 * S) : 0;
+    if (ctas <= max_ctas || mul <= 1.0f) break;
+    mul = std::max(1.0f, mul * float(max_ctas) / float(ctas) * 0.98f);
+  }
   b->lean_S = S;
   b->lean_cta_first.assign(nf, 0);
-  uint32_t ctas = 0;
+  ctas = 0;
   for (size_t f = 0; f < nf; f++) {
     b->frames[f].lean_cta_first = ctas;
     b->lean_cta_first[f] = ctas;
@@ -436,6 +457,8 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   B.status = static_cast<int32_t*>(b->d_status.p);
   B.queue = reinterpret_cast<uint32_t*>(B.status + b->streams.size());
   B.lean_cta_first = static_cast<const uint32_t*>(b->d_lean_cta.p);
+  B.lean_desc = static_cast<uint4*>(b->ctx->d_lean_desc.p);
+  B.lean_nblk = static_cast<uint32_t*>(b->ctx->d_lean_nblk.p);
   B.dequant_default = static_cast<const float*>(b->ctx->dequant_default.p);
   B.dequant_default_off = static_cast<const uint32_t*>(b->ctx->dequant_default_off.p);
   B.natural_orders = static_cast<const uint32_t*>(b->ctx->natural_orders.p);
@@ -445,7 +468,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
                                          static_cast<const uint32_t*>(b->d_ftiles.p), b->fused_prefix.back(),
-                                         b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas));
+                                         b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas, b->lean_ctx_smem));
   if (b->debug_stop == 0) {
     // Fused filter + colour + store, launched per range of frames; each finished range is copied to the host
     // on the copy stream while the next range is being filtered.
@@ -505,6 +528,8 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = b->d_planes_b.ensure(b->total_plane_floats * 4)) return r;
   if (int r = b->d_status.ensure((b->streams.size() + b->frames.size() + 4) * 4)) return r;
   if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
+  if (int r = b->ctx->d_lean_desc.ensure(std::max<size_t>(b->streams_lean.size() * 1024 * 16, 16))) return r;
+  if (int r = b->ctx->d_lean_nblk.ensure(std::max<size_t>(b->streams_lean.size() * 4, 16))) return r;
   for (size_t f = 0; f < b->frames.size(); f++)
     b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
   b->status_n = b->streams.size();

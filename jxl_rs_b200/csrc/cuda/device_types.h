@@ -4,6 +4,7 @@
 // (coefficients, XYB planes) live in separate device-only allocations.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace jxgpu {
 
@@ -92,6 +93,8 @@ struct BatchDev {
   int32_t* status;      // per stream
   uint32_t* queue;      // [frames] work-queue cursors of the persistent entropy kernel
   const uint32_t* lean_cta_first;  // [frames] first CTA of each frame in k_entropy_lean's grid
+  uint4* lean_desc;      // [num_lean][1024] varblock descriptors written by k_block_plan
+  uint32_t* lean_nblk;   // [num_lean] varblocks per stream (0xffffffff: invalid transform id)
   // context-wide tables
   const float* dequant_default;       // 17 tables concatenated
   const uint32_t* dequant_default_off;  // [17] float offsets

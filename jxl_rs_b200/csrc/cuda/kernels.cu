@@ -610,6 +610,77 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
 // Section copies are 8-byte aligned and zero padded; the word index is clamped to the section so that a
 // corrupt stream cannot walk out of the blob (the over-read is reported from bitpos at the end).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// K0: block plan of the lean entropy path. One warp per (frame, group) stream walks the group's 32x32 transform map
+// in raster order and writes, for every varblock, a 16-byte descriptor
+//   x: bx | by << 5 | cx << 10 | cy << 16 | shape << 22 | log2(cx * cy) << 26
+//   y: block contexts of Y, X, B (block_context_map.rs:128-150), one byte each
+//   z: offset of the block's coefficients inside the group (group.rs:455)
+// plus the block count and block_off[] (read by the transform kernels). This is everything the serial decode lanes
+// needed several dependent loads and a scan loop for, computed here fully in parallel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_block_plan(const BatchDev B) {
+  const uint32_t sidx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (sidx >= B.num_lean) return;
+  const StreamDev sd = B.streams_lean[sidx];
+  const FrameDev& F = B.frames[sd.frame];
+  const uint32_t g = sd.group;
+  const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
+  const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
+  const size_t goff = size_t(by0) * F.xb + bx0;
+  const uint8_t* tmap = B.blob + F.transform_off + goff;
+  const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off) + goff;
+  const uint8_t* qlf = B.blob + F.quant_lf_off + goff;
+  const uint8_t* bcm = B.blob + F.block_ctx_map_off;
+  uint32_t* block_off = B.block_off + F.block_base + goff;
+  uint4* desc = B.lean_desc + size_t(sidx) * 1024;
+  uint32_t seq = 0, coeffs_offset = 0;
+  bool bad = false;
+  for (uint32_t by = 0; by < gh; by++) {
+    const uint32_t bidx = by * F.xb + lane;
+    const uint32_t raw_t = lane < gw ? tmap[bidx] : 0u;
+    const bool first = raw_t >= 128;
+    const uint32_t t = raw_t & 127;
+    if (first && t >= 27) bad = true;
+    const uint32_t tt = min(t, 26u);
+    const uint32_t cx = c_cov_x[tt], cy = c_cov_y[tt], nb = first ? cx * cy : 0u;
+    // exclusive prefix sums over the row: number of first blocks and of coefficients
+    const uint32_t mask = __ballot_sync(0xffffffffu, first);
+    const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+    uint32_t incl = nb * 64;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (int(lane) >= d) incl += v;
+    }
+    const uint32_t row_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (first) {
+      const uint32_t off = coeffs_offset + incl - nb * 64;
+      const uint32_t shape = c_shape[tt];
+      const uint32_t raw_quant = uint32_t(rq[bidx]);
+      uint32_t qf_idx = 0;
+      for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
+      const uint32_t qf_lf_idx = qf_idx * F.num_lf_contexts + qlf[bidx];
+      const uint32_t stride = (F.num_qf_thresholds + 1) * F.num_lf_contexts;
+      // channel order of block_context(): index 0 = Y, 1 = X, 2 = B (group.rs:478-480 c < 2 ? c ^ 1 : 2)
+      const uint32_t cy_ctx = bcm[(0 * 13 + shape) * stride + qf_lf_idx];
+      const uint32_t cx_ctx = bcm[(1 * 13 + shape) * stride + qf_lf_idx];
+      const uint32_t cb_ctx = bcm[(2 * 13 + shape) * stride + qf_lf_idx];
+      uint4 d;
+      d.x = lane | (by << 5) | (cx << 10) | (cy << 16) | (shape << 22) | ((31u - __clz(cx * cy)) << 26);
+      d.y = cy_ctx | (cx_ctx << 8) | (cb_ctx << 16);
+      d.z = off;
+      d.w = 0;
+      desc[seq + rank] = d;
+      block_off[bidx] = off;
+    }
+    seq += __popc(mask);
+    coeffs_offset += row_total;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) B.lean_nblk[sidx] = bad ? 0xffffffffu : seq;
+}
+
 // Loads the compiler must not sink below the token computation (it would re-serialise the chain).
 __device__ __forceinline__ uint32_t spec_ld_u8(const uint8_t* p) {
   uint32_t v;
@@ -622,15 +693,38 @@ __device__ __forceinline__ uint32_t spec_ld_u32(const uint32_t* p) {
   return v;
 }
 
-template <int S, bool K420>
+constexpr uint32_t kLeanCtxSmem = 16384;  // context maps up to this size are staged in shared memory
+
+__device__ __forceinline__ uint32_t spec_lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t spec_lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// CTXS: the frame's context map fits the shared-memory staging area (host decision for the whole batch).
+template <int S, bool K420, bool CTXS>
 __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
-  __shared__ uint16_t s_nz2[64], s_fr2[64];  // context LUTs, pre-multiplied by 2 (block_context_map.rs:34-46)
+  // context LUTs, pre-multiplied by 2 (block_context_map.rs:34-46), natural-order table offsets
+  __shared__ uint16_t s_nz2[64], s_fr2[64];
+  __shared__ uint32_t s_order_off[13];
+  // Per-lane non-zero counts: one byte per block column and channel is enough. Varblocks are visited in raster order
+  // of their top-left corner, so the last value written to a column is the count of the block right above the
+  // current row, and (for column bx - 1) of the block to the left — the two neighbours group.rs:489-505 predicts from.
+  __shared__ uint8_t s_nzcol[4 * S][3 * 32];
+  extern __shared__ __align__(16) uint8_t s_ctxmap[];  // the frame's context map (CTXS)
   if (threadIdx.x < 64) {
-    s_nz2[threadIdx.x] = uint16_t(c_nz_ctx[threadIdx.x] * 2);
-    s_fr2[threadIdx.x] = uint16_t(c_freq_ctx[threadIdx.x] * 2);
+    // entry 0 of both tables is the reference's 0xBAD marker: never used by a valid context, but the speculative
+    // look-ups of the per-symbol step may touch it, so it must stay inside the context map
+    s_nz2[threadIdx.x] = threadIdx.x ? uint16_t(c_nz_ctx[threadIdx.x] * 2) : uint16_t(0);
+    s_fr2[threadIdx.x] = threadIdx.x ? uint16_t(c_freq_ctx[threadIdx.x] * 2) : uint16_t(0);
   }
-  __syncthreads();
-  // CTA -> frame: all lanes of a CTA work on one frame, so its context map and alias tables stay in L1.
+  if (threadIdx.x < 13) s_order_off[threadIdx.x] = B.natural_order_off[threadIdx.x];
+  // CTA -> frame: all lanes of a CTA work on one frame, so its context map and alias tables stay close.
   uint32_t fidx;
   {
     uint32_t lo = 0, hi = B.num_frames;
@@ -642,29 +736,40 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
     fidx = lo;
   }
   const FrameDev& F = B.frames[fidx];
+  const PassDev& P = F.passes[0];
+  const uint32_t nbc = F.num_block_contexts;
+  if (CTXS) {
+    const uint32_t num_ctx = F.num_histograms * nbc * (37 + 458);
+    const uint8_t* src = B.blob + P.context_map_off;  // 16-byte aligned in the blob
+    for (uint32_t i = threadIdx.x * 16; i < num_ctx + 64; i += blockDim.x * 16)  // speculative look-ups run a bit past the end
+      *reinterpret_cast<uint4*>(s_ctxmap + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+  }
+  __syncthreads();
+  const uint8_t* const ctxmap_g = B.blob + P.context_map_off;
+  const uint32_t ctxmap_s = uint32_t(__cvta_generic_to_shared(s_ctxmap));
+  const uint32_t nz2_s = uint32_t(__cvta_generic_to_shared(s_nz2)), fr2_s = uint32_t(__cvta_generic_to_shared(s_fr2));
+  auto ctx_cluster = [&](uint32_t ctx) { return CTXS ? spec_lds_u8(ctxmap_s + ctx) : spec_ld_u8(ctxmap_g + ctx); };
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane_in_frame = ((blockIdx.x - F.lean_cta_first) * 4 + (threadIdx.x >> 5)) * S + lane;
   const uint32_t frame_lanes = F.lean_ctas * 4 * S;
   uint32_t qpos = lane_in_frame;  // position in this frame's (longest first) stream list
   bool done = !(lane < S && qpos < F.lean_count);
+  uint8_t* const nz = s_nzcol[(threadIdx.x >> 5) * S + (lane < S ? lane : 0)];
   // ---- per-frame constants ----
-  const PassDev& P = F.passes[0];
-  const uint8_t* const ctxmap = B.blob + P.context_map_off;
   const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
   const uint2* const ans = reinterpret_cast<const uint2*>(B.blob + P.ans_off);
   const uint32_t log_alpha = P.log_alpha_size, log_bucket = 12 - P.log_alpha_size, bucket_mask = (1u << (12 - P.log_alpha_size)) - 1;
-  const uint32_t nbc = F.num_block_contexts, xb = F.xb;
   // ---- per-stream state (re-initialised by the set-up path when a lane takes a new stream) ----
-  uint32_t g = 0, gsid = 0, goff = 0, gw = 1, gn = 0;
+  uint32_t gsid = 0, nblk = 0, bi = 0;
+  const uint4* desc = B.lean_desc;
   int32_t* group_coeffs = B.coeffs;
-  uint8_t* nz = B.nz;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(B.blob);
   uint32_t sec_bits = 0, wlimit = 0;
   uint32_t bitpos = 0, ans_state = 0x130000u, context_offset = 0;
   uint32_t wi = 0, w0 = 0, w1 = 0, w2 = 0;
   // ---- per-block state ----
-  uint32_t pos = 0, coeffs_offset = 0;
-  uint32_t bx = 0, by = 0, cxy = 0x0101, shape = 0, qf_lf_idx = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
+  uint32_t coeffs_offset = 0;
+  uint32_t bx = 0, by = 0, cxy = 0x0101, shape = 0, bctx3 = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
   uint32_t ci = 3;          // 3: need a new block
   bool need_setup = true;   // channel (and maybe block / stream) set-up before the next symbol
   bool new_stream = true, failed = false;
@@ -680,14 +785,13 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       // ---------- rare path: next stream, block and/or channel ----------
       while (ci == 3) {
         if (new_stream) {
-          g = B.streams_lean[F.lean_first + qpos].group;
+          const uint32_t lidx = F.lean_first + qpos;
+          const uint32_t g = B.streams_lean[lidx].group;
           gsid = F.first_stream + g;
-          const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
-          gw = min(32u, F.xb - bx0);
-          gn = gw * min(32u, F.yb - by0);
-          goff = by0 * xb + bx0;
           group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
-          nz = B.nz + B.nz_base[gsid];
+          desc = B.lean_desc + size_t(lidx) * 1024;
+          nblk = B.lean_nblk[lidx];
+          bi = 0;
           const SectionDev sec = B.sections[F.section_base + g];
           words = reinterpret_cast<const uint32_t*>(B.blob + sec.off);
           sec_bits = sec.len * 8u;
@@ -696,13 +800,15 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           while ((1u << nb) < F.num_histograms) nb++;
           const uint32_t hist_idx = nb ? (__ldg(words) & ((1u << nb) - 1u)) : 0u;  // group.rs:333-341 (nb <= 12)
           failed = false;
-          pos = 0;
-          coeffs_offset = 0;
           histo_offset = 0;
-          if (hist_idx >= F.num_histograms) {
+          if (nblk == 0xffffffffu) {
+            B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
+            failed = true;
+            nblk = 0;
+          } else if (hist_idx >= F.num_histograms) {
             B.status[gsid] = JXG_ERR_INVALID_HISTOGRAM_INDEX;
             failed = true;
-            pos = gn;
+            nblk = 0;
           }
           context_offset = failed ? 0u : hist_idx * nbc * (37 + 458);
           ans_state = __funnelshift_r(__ldg(words), __ldg(words + 1), nb);  // ans.rs:431
@@ -713,16 +819,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           w2 = __ldg(words + 3);
           new_stream = false;
         }
-        const uint8_t* const tmap = B.blob + F.transform_off + goff;
-        uint32_t raw_t = 0;
-        while (pos < gn) {
-          by = pos / gw;
-          bx = pos - by * gw;
-          raw_t = tmap[by * xb + bx];
-          if (raw_t >= 128) break;
-          pos++;
-        }
-        if (pos >= gn) {  // stream finished: check_final_state (decode.rs:400), then take the next one
+        if (bi >= nblk) {  // stream finished: check_final_state (decode.rs:400), then take the next one
           if (!failed) {
             int err = 0;
             if (bitpos > sec_bits) err = JXG_ERR_OUT_OF_BOUNDS;
@@ -737,38 +834,30 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           new_stream = true;
           continue;
         }
-        if ((raw_t & 127) >= 27) {
-          B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
-          failed = true;
-          pos = gn;
-          continue;
-        }
-        const uint32_t t = raw_t & 127, bidx = by * xb + bx;
-        const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
+        const uint4 d = __ldg(desc + bi);
+        bi++;
+        bx = d.x & 31;
+        by = (d.x >> 5) & 31;
+        const uint32_t cx = (d.x >> 10) & 63, cy = (d.x >> 16) & 63;
         cxy = cx | (cy << 8);
-        shape = c_shape[t];
-        const uint32_t raw_quant = uint32_t(reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off)[goff + bidx]);
-        uint32_t qf_idx = 0;
-        for (uint32_t i = 0; i < F.num_qf_thresholds; i++) qf_idx += raw_quant > F.qf_thresholds[i];
-        qf_lf_idx = qf_idx * F.num_lf_contexts + (B.blob + F.quant_lf_off)[goff + bidx];
+        shape = (d.x >> 22) & 15;
+        lnb = d.x >> 26;
         num_blocks = cx * cy;
         num_coeffs = num_blocks * 64;
-        lnb = 31 - __clz(num_blocks);
-        (B.block_off + F.block_base)[goff + bidx] = coeffs_offset;
+        bctx3 = d.y;
+        coeffs_offset = d.z;
         ci = 0;
       }
       if (!done) {
         const int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);  // Y, X, B
-        const uint8_t* nzc_map = nz + c * 1024;
+        const uint8_t* nzc_col = nz + c * 32;
         uint32_t predicted;
-        if (bx == 0) predicted = by == 0 ? 32u : nzc_map[(by - 1) * 32];
-        else if (by == 0) predicted = nzc_map[bx - 1];
-        else predicted = (uint32_t(nzc_map[(by - 1) * 32 + bx]) + uint32_t(nzc_map[by * 32 + bx - 1]) + 1u) >> 1;
-        uint32_t idx = (c < 2 ? uint32_t(c ^ 1) : 2u) * 13 + shape;
-        idx = idx * (F.num_qf_thresholds + 1) * F.num_lf_contexts + qf_lf_idx;
-        block_context = __ldg(B.blob + F.block_ctx_map_off + idx);
+        if (bx == 0) predicted = by == 0 ? 32u : nzc_col[0];
+        else if (by == 0) predicted = nzc_col[bx - 1];
+        else predicted = (uint32_t(nzc_col[bx]) + uint32_t(nzc_col[bx - 1]) + 1u) >> 1;
+        block_context = (bctx3 >> (8 * ci)) & 0xff;
         const uint32_t nzc = predicted < 8 ? predicted : (predicted < 64 ? 4 + predicted / 2 : 36);
-        cluster = __ldg(ctxmap + (nzc * nbc + block_context + context_offset));
+        cluster = ctx_cluster(nzc * nbc + block_context + context_offset);
         mode_nnz = true;
         need_setup = false;
       }
@@ -777,19 +866,19 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
     // ---------- common path: one symbol ----------
     // speculative: clusters of the next coefficient symbol for token == 0 (A) and token != 0 (B)
     const uint32_t w3 = spec_ld_u32(words + wi + 3), w4 = spec_ld_u32(words + wi + 4);
-    const uint32_t fr_next = s_fr2[((k + 1) >> lnb) & 63];
+    const uint32_t fr_next = spec_lds_u16(fr2_s + ((((k + 1) >> lnb) & 63) << 1));
     const uint32_t nzq = nonzeros + num_blocks - 1;
-    const uint32_t ctxA = histo_offset + fr_next + uint32_t(s_nz2[(nzq >> lnb) & 63]);
-    const uint32_t ctxB = histo_offset + fr_next + uint32_t(s_nz2[((nzq - 1) >> lnb) & 63]) + 1u;
-    const uint32_t clA = spec_ld_u8(ctxmap + ctxA), clB = spec_ld_u8(ctxmap + ctxB);
+    const uint32_t ctxA = histo_offset + fr_next + spec_lds_u16(nz2_s + (((nzq >> lnb) & 63) << 1));
+    const uint32_t ctxB = histo_offset + fr_next + spec_lds_u16(nz2_s + ((((nzq - 1) >> lnb) & 63) << 1)) + 1u;
+    const uint32_t clA = ctx_cluster(ctxA), clB = ctx_cluster(ctxB);
     // rANS step (ans.rs:356-393)
     const uint32_t idx12 = ans_state & 0xfff;
-    const uint32_t bi = idx12 >> log_bucket, bp = idx12 & bucket_mask;
-    const uint2 bk = __ldg(ans + ((cluster << log_alpha) + bi));
+    const uint32_t bi12 = idx12 >> log_bucket, bp = idx12 & bucket_mask;
+    const uint2 bk = __ldg(ans + ((cluster << log_alpha) + bi12));
     const bool alias = bp >= ((bk.x >> 8) & 0xff);
     const uint32_t dist = (bk.x >> 16) ^ (alias ? (bk.y >> 16) : 0u);
     const uint32_t offset = bp + (alias ? (bk.y & 0xffff) : 0u);
-    const uint32_t token = alias ? (bk.x & 0xff) : bi;
+    const uint32_t token = alias ? (bk.x & 0xff) : bi12;
     const uint32_t nonzero = token != 0 ? 1u : 0u;
     const uint32_t cluster_next = nonzero ? clB : clA;
     uint32_t next = (ans_state >> 12) * dist + offset;
@@ -834,32 +923,28 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       if (nonzeros + num_blocks > num_coeffs) {
         B.status[gsid] = JXG_ERR_INVALID_NUM_NONZEROS;
         failed = true;
-        pos = gn;
+        bi = nblk;
         ci = 3;
         need_setup = true;
         continue;
       }
-      uint8_t* nzc_map = nz + c * 1024;
+      uint8_t* nzc_col = nz + c * 32;
       const uint8_t nzv = uint8_t((nonzeros + num_blocks - 1) >> lnb);
-      const uint32_t cx = cxy & 0xff, cy = cxy >> 8;
-      for (uint32_t iy = 0; iy < cy; iy++)
-        for (uint32_t ix = 0; ix < cx; ix++) nzc_map[(by + iy) * 32 + bx + ix] = nzv;
+      const uint32_t cx = cxy & 0xff;
+      for (uint32_t ix = 0; ix < cx; ix++) nzc_col[bx + ix] = nzv;
       histo_offset = nbc * 37 + 458 * block_context + context_offset;
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
-                              : B.natural_orders + B.natural_order_off[shape];
+                              : B.natural_orders + s_order_off[shape];
       cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
       mode_nnz = false;
       if (nonzeros == 0) {
         need_setup = true;
-        if (++ci == 3) {
-          coeffs_offset += num_coeffs;
-          pos++;
-        }
+        ci++;
       } else {
         const uint32_t prev = nonzeros > num_coeffs / 16 ? 0u : 1u;
-        cluster = __ldg(ctxmap + (histo_offset + uint32_t(s_nz2[((nonzeros + num_blocks - 1) >> lnb) & 63]) +
-                                  uint32_t(s_fr2[(k >> lnb) & 63]) + prev));
+        cluster = ctx_cluster(histo_offset + uint32_t(s_nz2[((nonzeros + num_blocks - 1) >> lnb) & 63]) +
+                              uint32_t(s_fr2[(k >> lnb) & 63]) + prev);
       }
     } else {
       if (nonzero) cur[__ldg(order + k)] = unpack_signed(value);  // lean streams have shift == 0 (host routing)
@@ -868,14 +953,11 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       k++;
       if (nonzeros == 0) {
         need_setup = true;
-        if (++ci == 3) {
-          coeffs_offset += num_coeffs;
-          pos++;
-        }
+        ci++;
       } else if (k >= num_coeffs) {
         B.status[gsid] = JXG_ERR_RESIDUAL_NONZEROS;  // group.rs:574
         failed = true;
-        pos = gn;
+        bi = nblk;
         ci = 3;
         need_setup = true;
       }
@@ -2702,7 +2784,7 @@ cudaError_t configure_kernels() {
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
                     cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
-                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas) {
+                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas, bool lean_ctx_smem) {
   // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
   // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
@@ -2715,18 +2797,27 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   if (B.num_lean) {
     // Persistent lanes, scheduled per frame by the host (batch.cc schedule_lean): S lanes per warp, lean_ctas CTAs.
     cudaMemsetAsync(B.queue, 0, sizeof(uint32_t) * B.num_frames, stream);
+    k_block_plan<<<(B.num_lean + 3) / 4, 128, 0, stream>>>(B);
+    launches++;
     const uint32_t S = lean_S, grid = lean_ctas;
+    const int smem = lean_ctx_smem ? int(kLeanCtxSmem) : 0;
+#define JXG_LEAN(SV, KV, CV) k_entropy_lean<SV, KV, CV><<<grid, 128, smem, stream>>>(B)
+#define JXG_LEAN_S(KV, CV)                                    \
+  do {                                                        \
+    if (S == 1) JXG_LEAN(1, KV, CV);                          \
+    else if (S == 2) JXG_LEAN(2, KV, CV);                     \
+    else if (S == 4) JXG_LEAN(4, KV, CV);                     \
+    else JXG_LEAN(8, KV, CV);                                 \
+  } while (0)
     if (lean_all_420) {
-      if (S == 1) k_entropy_lean<1, true><<<grid, 128, 0, stream>>>(B);
-      else if (S == 2) k_entropy_lean<2, true><<<grid, 128, 0, stream>>>(B);
-      else if (S == 4) k_entropy_lean<4, true><<<grid, 128, 0, stream>>>(B);
-      else k_entropy_lean<8, true><<<grid, 128, 0, stream>>>(B);
+      if (lean_ctx_smem) JXG_LEAN_S(true, true);
+      else JXG_LEAN_S(true, false);
     } else {
-      if (S == 1) k_entropy_lean<1, false><<<grid, 128, 0, stream>>>(B);
-      else if (S == 2) k_entropy_lean<2, false><<<grid, 128, 0, stream>>>(B);
-      else if (S == 4) k_entropy_lean<4, false><<<grid, 128, 0, stream>>>(B);
-      else k_entropy_lean<8, false><<<grid, 128, 0, stream>>>(B);
+      if (lean_ctx_smem) JXG_LEAN_S(false, true);
+      else JXG_LEAN_S(false, false);
     }
+#undef JXG_LEAN_S
+#undef JXG_LEAN
     launches++;
   }
   if (B.num_fast) {

@@ -11,7 +11,7 @@ cudaError_t configure_kernels();
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
                     cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
-                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas);
+                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas, bool lean_ctx_smem);
 constexpr int kFusedTileW = 64, kFusedTileH = 32;
 int launch_filter_range(const BatchDev& B, const uint32_t* fused_prefix, uint32_t tile_begin, uint32_t tile_count,
                         uint32_t filter_cfg_mask, cudaStream_t stream);

@@ -29,15 +29,40 @@ __constant__ uint32_t c_div_lookup[64] = {
 
 struct MBr {  // bit reader over an 8-byte aligned, zero padded section copy (bit_reader.rs semantics)
   const uint32_t* words;
-  uint32_t wlimit;
-  uint64_t bitpos;
-  __device__ __forceinline__ uint32_t peek32() const {
-    const uint32_t wi = min(uint32_t(bitpos >> 5), wlimit);
-    return __funnelshift_r(__ldg(words + wi), __ldg(words + wi + 1), uint32_t(bitpos) & 31);
+  uint32_t wlimit, wi;  // next word to load (clamped: a corrupt stream cannot walk out of the blob)
+  uint64_t buf;         // `avail` valid bits, LSB first
+  uint32_t avail;
+  uint64_t bitpos;      // bits consumed
+  __device__ __forceinline__ void init(const uint32_t* w, uint32_t limit, uint64_t start_bit) {
+    words = w;
+    wlimit = limit;
+    bitpos = start_bit;
+    wi = min(uint32_t(start_bit >> 5), limit);
+    const uint32_t sh = uint32_t(start_bit) & 31;
+    buf = (uint64_t(__ldg(words + wi)) | (uint64_t(__ldg(words + min(wi + 1, limit))) << 32)) >> sh;
+    avail = 64 - sh;
+    wi = min(wi + 2, limit);
+  }
+  __device__ __forceinline__ void refill() {  // keeps >= 32 valid bits
+    if (avail <= 32) {
+      buf |= uint64_t(__ldg(words + wi)) << avail;
+      avail += 32;
+      wi = min(wi + 1, wlimit);
+    }
+  }
+  __device__ __forceinline__ uint32_t peek32() {
+    refill();
+    return uint32_t(buf);
+  }
+  __device__ __forceinline__ void consume(uint32_t n) {  // n <= 32, after a peek32()
+    buf >>= n;
+    avail -= n;
+    bitpos += n;
   }
   __device__ __forceinline__ uint32_t read(uint32_t n) {  // n <= 32
-    const uint32_t v = n == 32 ? peek32() : (peek32() & ((1u << n) - 1u));
-    bitpos += n;
+    const uint32_t w = peek32();
+    const uint32_t v = n == 32 ? w : (w & ((1u << n) - 1u));
+    consume(n);
     return v;
   }
 };
@@ -68,7 +93,7 @@ __device__ __forceinline__ uint32_t m_read_unsigned(MSym& s, uint32_t ctx) {
       pos += (e >> 16) + ((w >> 8) & ((1u << nb) - 1u));
       e = __ldg(t + pos);
     }
-    s.br.bitpos += used + (e & 0xff);
+    s.br.consume(used + (e & 0xff));  // <= 8 + 15 bits
     token = e >> 16;
   } else {  // ans.rs:356-393
     const uint32_t log_bucket = 12 - s.log_alpha;
@@ -196,9 +221,7 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
     const MStreamDev& st = B.streams[B.order[sidx]];
     const MCodeDev& code = B.codes[st.code];
     MSym sym;
-    sym.br.words = reinterpret_cast<const uint32_t*>(B.blob + st.sec_off);
-    sym.br.wlimit = (st.sec_len >> 2) + 1;
-    sym.br.bitpos = st.data_bitpos;
+    sym.br.init(reinterpret_cast<const uint32_t*>(B.blob + st.sec_off), (st.sec_len >> 2) + 1, st.data_bitpos);
     sym.cmap = B.blob + code.cmap_off;
     sym.cfg = reinterpret_cast<const uint32_t*>(B.blob + code.cfg_off);
     sym.ans = reinterpret_cast<const uint2*>(B.blob + code.ans_off);
@@ -209,6 +232,7 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
     sym.ans_state = 0x130000u;
     if (!code.use_prefix) sym.ans_state = sym.br.read(32);  // ans.rs:431
     const int4* const nodes = reinterpret_cast<const int4*>(B.blob + st.tree_off);
+    const int4 root = __ldg(nodes);
     MWp wp;
     const bool use_wp = st.uses_wp != 0;
     if (use_wp) {
@@ -226,6 +250,12 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
       if (rc.w == 0 || rc.h == 0) continue;  // channel numbering stays stable (bitstream.rs:203-206)
       const uint32_t w = rc.w, h = rc.h;
       int32_t* const base = B.planes + rc.base;
+      // Decision nodes on the channel index / stream id are constant for the whole channel: resolve them once.
+      int4 chan_root = root;
+      while (chan_root.x == 0 || chan_root.x == 1) {
+        const int32_t v = chan_root.x == 0 ? int32_t(ci) : int32_t(st.stream_id);
+        chan_root = __ldg(nodes + (v > chan_root.y ? chan_root.z : chan_root.z + 1));
+      }
       if (use_wp) {  // fresh state per channel (channel.rs:236)
         wp.xsize = w;
         wp.perr = reinterpret_cast<uint32_t*>(B.wp_scratch + st.wp_scratch_off);
@@ -238,20 +268,35 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
         const int32_t* const top = y > 0 ? row - rc.stride : row;
         const int32_t* const toptop = y > 1 ? top - rc.stride : top;
         int32_t prev_p9 = 0;
+        int4 row_root = chan_root;  // ... and the ones on y once per row
+        while (row_root.x >= 0 && row_root.x <= 2) {
+          const int32_t v = row_root.x == 0 ? int32_t(ci) : (row_root.x == 1 ? int32_t(st.stream_id) : int32_t(y));
+          row_root = __ldg(nodes + (v > row_root.y ? row_root.z : row_root.z + 1));
+        }
+        // Sliding neighbour window (predict.rs:64-103): the pixels of this row stay in registers (no store -> load
+        // round trip on the dependent chain), the rows above are loaded one pixel ahead of their use.
+        const bool has_top = y > 0, has_tt = y > 1;
+        int32_t v_prev = 0, v_prev2 = 0;                 // row[x-1], row[x-2]
+        int32_t t_prev = 0;                              // top[x-1]
+        int32_t t_cur = has_top ? top[0] : 0;            // top[x]
+        int32_t t_next = (has_top && w > 1) ? top[1] : 0;  // top[x+1]
+        int32_t tt_cur = has_tt ? toptop[0] : 0;         // toptop[x]
+        const int32_t top0 = t_cur;
         for (uint32_t x = 0; x < w; x++) {
-          // predict.rs:64-103
-          const int32_t left = x > 0 ? row[x - 1] : (y > 0 ? top[0] : 0);
-          const int32_t n = y > 0 ? top[x] : left;
-          const int32_t nw = (x > 0 && y > 0) ? top[x - 1] : left;
-          const int32_t ne = (x + 1 < w && y > 0) ? top[x + 1] : n;
-          const int32_t ww = x > 1 ? row[x - 2] : left;
-          const int32_t nn = y > 1 ? toptop[x] : n;
+          const int32_t t_next2 = (has_top && x + 2 < w) ? top[x + 2] : 0;    // used as top[x+1] next iteration
+          const int32_t tt_next = (has_tt && x + 1 < w) ? toptop[x + 1] : 0;  // toptop[x+1]
+          const int32_t left = x > 0 ? v_prev : (has_top ? top0 : 0);
+          const int32_t n = has_top ? t_cur : left;
+          const int32_t nw = (x > 0 && has_top) ? t_prev : left;
+          const int32_t ne = (x + 1 < w && has_top) ? t_next : n;
+          const int32_t ww = x > 1 ? v_prev2 : left;
+          const int32_t nn = has_tt ? tt_cur : n;
           int64_t wp_pred = 0;
           int32_t wp_prop = 0;
           if (use_wp) wp.predict(x, y, n, left, ne, nw, nn, wp_pred, wp_prop);
           const int32_t p9 = wsub(wadd(left, n), nw);
           // tree.rs:189-280 + flat walk (tree.rs:360-390)
-          int4 nd = __ldg(nodes);
+          int4 nd = row_root;
           while (nd.x >= 0) {
             int32_t v;
             switch (nd.x) {
@@ -298,7 +343,7 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
             case 11: guess = (T + TL) / 2; break;
             case 12: guess = (T + TR) / 2; break;
             default: {
-              const int32_t nee = (x + 2 < w && y > 0) ? top[x + 2] : ne;
+              const int32_t nee = (x + 2 < w && has_top) ? t_next2 : ne;
               guess = (6 * T - 2 * int64_t(nn) + 7 * L + int64_t(ww) + int64_t(nee) + 3 * TR + 8) / 16;
             }
           }
@@ -307,6 +352,12 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
           const int32_t val = int32_t(guess + int64_t(uint32_t(nd.w)) * int64_t(dec));  // decode/common.rs:85
           if (use_wp) wp.update(val, x, y);
           row[x] = val;
+          v_prev2 = v_prev;
+          v_prev = val;
+          t_prev = t_cur;
+          t_cur = t_next;
+          t_next = t_next2;
+          tt_cur = tt_next;
         }
       }
     }

@@ -32,8 +32,8 @@ def measure(tag):
     b.close()
     print(tag, {k: round(v, 2) for k, v in best.items() if v > 0.1}, flush=True)
 measure("default")
-for S in (1, 2, 4, 8):
-    for M in (1.0, 1.5, 2.0, 3.0, 100.0):
+for S in (2, 4, 8):
+    for M in (1.0, 1.3, 1.6, 2.0):
         os.environ["JXG_ENTROPY_S"] = str(S)
         os.environ["JXG_ENTROPY_LANES_MUL"] = str(M)
         measure(f"S={S} mul={M}")
