@@ -382,7 +382,7 @@ static void schedule_lean(Batch* b) {
   std::stable_sort(b->streams_lean.begin(), b->streams_lean.end(), [&](const StreamDev& x, const StreamDev& y) {
     return x.frame != y.frame ? x.frame < y.frame : len_of(x) > len_of(y);
   });
-  float mul = 1.6f;
+  float mul = 2.0f;
   if (const char* e = getenv("JXG_ENTROPY_LANES_MUL")) mul = float(atof(e));  // experiment knobs
   const size_t nf = b->frames.size();
   std::vector<uint32_t> lanes(nf, 0);
@@ -468,7 +468,8 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
                                          static_cast<const uint32_t*>(b->d_ftiles.p), b->fused_prefix.back(),
-                                         b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas, b->lean_ctx_smem));
+                                         b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas,
+                                         b->lean_ctx_smem && !(getenv("JXG_LEAN_CTX_SMEM") && atoi(getenv("JXG_LEAN_CTX_SMEM")) == 0)));
   if (b->debug_stop == 0) {
     // Fused filter + colour + store, launched per range of frames; each finished range is copied to the host
     // on the copy stream while the next range is being filtered.

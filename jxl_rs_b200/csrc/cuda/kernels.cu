@@ -1671,7 +1671,7 @@ __device__ __forceinline__ int reg_kind(int t) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : (KIND == 1 ? 2 : 1)) k_idct_small(const BatchDev B) {
+__global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small(const BatchDev B) {
   __shared__ uint16_t s_list[1024];
   __shared__ uint32_t s_cnt[28], s_start[28], s_fill[28];
   const uint32_t stream = blockIdx.x;
