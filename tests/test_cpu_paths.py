@@ -97,3 +97,11 @@ def test_frame_sharding_world_size_2_gloo(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_effective_cpus_is_sane():
+    """Thread-pool sizing honours affinity and cgroup quotas (the GPU boxes show 128 CPUs and grant 16)."""
+    import os
+    from jxl_rs_b200.decoder import effective_cpus
+    n = effective_cpus()
+    assert 1 <= n <= (os.cpu_count() or 1)
