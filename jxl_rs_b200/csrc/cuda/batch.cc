@@ -448,6 +448,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   B.streams_slow = static_cast<const StreamDev*>(b->d_streams_slow.p);
   B.num_fast = uint32_t(b->streams_fast.size());
   B.num_slow = uint32_t(b->streams_slow.size());
+  B.reg_idct32 = (getenv("JXG_REG_IDCT32") && atoi(getenv("JXG_REG_IDCT32"))) ? 1u : 0u;
   B.coeffs = static_cast<int32_t*>(b->d_coeffs.p);
   B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
   B.nz = static_cast<uint8_t*>(b->d_nz.p);

@@ -84,6 +84,7 @@ struct BatchDev {
   const StreamDev* streams_fast;  // single-pass prefix-coded frames: k_entropy_fast
   const StreamDev* streams_slow;  // multi-pass frames: k_entropy
   uint32_t num_frames, num_streams, num_lean, num_fast, num_slow;
+  uint32_t reg_idct32;  // 1: rows of 32 coefficients also go through the register path (experiment knob)
   int32_t* coeffs;      // [groups][3][65536]
   uint32_t* block_off;  // per 8x8 block: coefficient offset of the varblock starting there
   uint8_t* nz;          // [streams][passes][3][1024]

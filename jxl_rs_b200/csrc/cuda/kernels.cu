@@ -1292,7 +1292,13 @@ __device__ __forceinline__ void warp_col_pass(float* ch, int lane_col, int strid
   for (int i = 0; i < N; i++) ch[i * stride + lane_col] = v[i];
 }
 
-__device__ __forceinline__ bool is_small_reg_type(int t) { return (t == 0) || (t >= 3 && t <= 13); }  // k_idct_small
+// Types transformed in registers by k_idct_small: 8x8-footprint transforms and plain DCTs with rows of <= 16
+// coefficients. Rows of 32 (32x8 ... 32x32) unroll into ~300 KB of code and starve on instruction fetch
+// (profiles/r01_ncu_summary.md), so they take the compact shared-memory path of k_dequant_idct unless
+// JXG_REG_IDCT32 is set.
+__device__ __forceinline__ bool is_small_reg_type(int t, bool reg32) {
+  return (t == 0) || (t >= 3 && t <= 13 && (reg32 || !(t == 5 || (t >= 8 && t <= 11))));
+}
 
 constexpr int kIdctWarps = 8;
 constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
@@ -1384,7 +1390,7 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     if (raw_t < 128) continue;
     const int t = raw_t & 127;
     const int cx = c_cov_x[t], cy = c_cov_y[t];
-    if (is_small_reg_type(t)) continue;  // handled by k_idct_small
+    if (is_small_reg_type(t, B.reg_idct32 != 0)) continue;  // handled by k_idct_small
     if (cx > 4 || cy > 4) {  // big varblock: handled cooperatively below
       if (lane == 0) {
         uint32_t i = atomicAdd(&s_nbig, 1u);
@@ -2839,8 +2845,8 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   if (debug_stop == 1) return launches;
   k_idct_small<0><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
   k_idct_small<1><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
-  k_idct_small<2><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
-  launches += 3;
+  if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  launches += B.reg_idct32 ? 3 : 2;
   k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
   launches++;
   mark(3);
