@@ -74,6 +74,15 @@ class BitReader {
 
  private:
   inline void refill() {
+    if (pos_ + 8 <= size_) {  // whole-word refill (little-endian host); bits above bits_ are re-read identically later
+      uint64_t w;
+      memcpy(&w, data_ + pos_, 8);
+      buf_ |= w << bits_;
+      const unsigned nbytes = (63 - bits_) >> 3;
+      pos_ += nbytes;
+      bits_ += nbytes * 8;
+      return;
+    }
     while (bits_ <= 56) {
       uint64_t byte = pos_ < size_ ? data_[pos_] : 0;
       pos_++;

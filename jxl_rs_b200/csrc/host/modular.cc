@@ -285,8 +285,10 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
     // Only channel / stream id are tested: one leaf for the whole channel.
     const TreeNode* nd = nodes;
     while (nd->property >= 0) nd = nodes + (props[nd->property] > nd->val ? nd->left : nd->right);
-    const uint32_t pred = nd->left, ctx = nd->ctx;
+    const uint32_t pred = nd->left;
+    const uint32_t cluster = tree.code.context_map[nd->ctx];  // one leaf -> one cluster for the whole channel
     const int64_t offset = nd->val, mul = nd->right;
+    auto next_signed = [&]() { return int64_t(unpack_signed(reader.read_clustered(br, cluster))); };
     for (size_t y = 0; y < h; y++) {
       int32_t* row = ch.row(uint32_t(y));
       const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
@@ -297,15 +299,15 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
           const int64_t top = y > 0 ? top_row[x] : left;
           const int64_t topleft = (x > 0 && y > 0) ? top_row[x - 1] : left;
           const int64_t guess = clamped_gradient(left, top, topleft) + offset;
-          row[x] = int32_t(guess + mul * int64_t(reader.read_signed(br, ctx)));
+          row[x] = int32_t(guess + mul * next_signed());
         }
       } else if (pred == kZero) {
-        for (size_t x = 0; x < w; x++) row[x] = int32_t(offset + mul * int64_t(reader.read_signed(br, ctx)));
+        for (size_t x = 0; x < w; x++) row[x] = int32_t(offset + mul * next_signed());
       } else {
         for (size_t x = 0; x < w; x++) {
           Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
           const int64_t guess = predict_one(pred, n, 0) + offset;
-          row[x] = int32_t(guess + mul * int64_t(reader.read_signed(br, ctx)));
+          row[x] = int32_t(guess + mul * next_signed());
         }
       }
     }
