@@ -58,6 +58,12 @@ def host_cores():
     return effective_cpus()
 
 
+def rank_cores():
+    """This rank's share of the host threads when several ranks run on the node (one process per GPU)."""
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return max(2, host_cores() // max(1, local_world))
+
+
 def kernel_traffic(kernel, frames):
     """ncu dram__bytes_read + dram__bytes_write of the dominant kernel per launch (profiles/r01_traffic.json, taken
     at 64 frames; scaled linearly to the batch size), or None when no capture exists for that kernel."""
@@ -74,7 +80,7 @@ def make_frames(args, rank):
     n = args.frames
     uniq = n if args.unique <= 0 else min(args.unique, n)
     seeds = frame_seeds(n, rank)[:uniq]
-    workers = max(1, min(uniq, host_cores()))
+    workers = max(1, min(uniq, rank_cores()))
     with ThreadPoolExecutor(max_workers=workers) as ex:
         files = list(ex.map(lambda s: synth.encode_synthetic(args.width, args.height, s, args.distance, args.epf, 1, args.profile), seeds))
     return [files[i % uniq] for i in range(n)]
@@ -217,7 +223,7 @@ def main():
     # Two copies of the batch stay resident on two contexts (own CUDA stream + buffer pools each) and the
     # timed steps alternate between them, so that consecutive steps overlap on the device (entropy decode of
     # one batch is latency-bound and leaves issue slots to the transforms/filters of the other).
-    with ThreadPoolExecutor(max_workers=min(n, host_cores())) as ex:
+    with ThreadPoolExecutor(max_workers=min(n, rank_cores())) as ex:
         frames = list(ex.map(j.ParsedFrame, files))
     depth = max(1, args.inflight)
     ctxs = [ctx] + [j.JxgContext(local_rank) for _ in range(depth - 1)]
@@ -279,7 +285,7 @@ def main():
     outs = [[(o.data_ptr(), fr.width * 3) for o, fr in zip(ho, frames)] for ho in host_out]
     del frames
     ctx.close()
-    dec = j.PipelinedDecoder(local_rank, depth=2)
+    dec = j.PipelinedDecoder(local_rank, depth=2, workers=min(64, rank_cores()), staging_threads=max(2, min(4, rank_cores() // 4)))
     for i in range(max(3, min(args.warmup, 3))):
         dec.submit(files, outs[i % 2], abi.FORMAT_RGB_U8)
     dec.drain()
@@ -331,7 +337,7 @@ def main():
                 "sharding": "frames partitioned by rank, no data-path collective",
                 "stage_ms_single_batch": stage_acc, "single_batch_ms": single_ms, "batches_in_flight": depth,
                 "e2e_pipeline": "whole batches, 2 in flight (host parse/staging of batch k+1 overlaps GPU + D2H of batch k)",
-                "host_cores": cores,
+                "host_cores": cores, "host_cores_per_rank": rank_cores(),
                 "pipeline_alg_gbs": pipeline_gbs,
                 "alg_bytes_per_step": alg_bytes,
             },
