@@ -1273,8 +1273,9 @@ __device__ __noinline__ void special_transform(int t, const float* co, float* px
   }
 }
 
+// noinline: one copy of each IDCT size in the kernel, whatever the number of call sites (instruction-cache footprint)
 template <int N>
-__device__ __forceinline__ void warp_row_pass(float* ch, int lane_row, int stride) {
+__device__ __noinline__ void warp_row_pass(float* ch, int lane_row, int stride) {
   float v[N];
 #pragma unroll
   for (int i = 0; i < N; i++) v[i] = ch[lane_row * stride + i];
@@ -1283,7 +1284,7 @@ __device__ __forceinline__ void warp_row_pass(float* ch, int lane_row, int strid
   for (int i = 0; i < N; i++) ch[lane_row * stride + i] = v[i];
 }
 template <int N>
-__device__ __forceinline__ void warp_col_pass(float* ch, int lane_col, int stride) {
+__device__ __noinline__ void warp_col_pass(float* ch, int lane_col, int stride) {
   float v[N];
 #pragma unroll
   for (int i = 0; i < N; i++) v[i] = ch[i * stride + lane_col];
@@ -1320,6 +1321,48 @@ __device__ __forceinline__ void big_line_dispatch(int n, float* base, size_t ele
     case 128: big_line_pass<128>(base, elem_stride); break;
     case 256: big_line_pass<256>(base, elem_stride); break;
     default: break;
+  }
+}
+
+// Shared-memory warp path of one plain-DCT varblock with compile-time shape (index arithmetic becomes shifts).
+template <int R, int C>
+__device__ __forceinline__ void warp_dct_block(const DequantCtx& dq, float* wbuf, int lane, const float* const* lfp,
+                                               size_t lf_index, uint32_t lf_stride, float* const* planes, size_t px0,
+                                               uint32_t plane_stride) {
+  constexpr int stride = C + 1, cx = C / 8, cy = R / 8;
+  constexpr bool wide = R < C;
+  float* ch0 = wbuf;
+  float* ch1 = wbuf + kWarpBuf;
+  float* ch2 = wbuf + 2 * kWarpBuf;
+#pragma unroll 4
+  for (int k = lane; k < R * C; k += 32) {
+    float vx, vy, vb;
+    dq.get(uint32_t(k), vx, vy, vb);
+    const int vf = wide ? k / C : k % R;
+    const int hf = wide ? k % C : k / R;
+    ch0[vf * stride + hf] = vx;
+    ch1[vf * stride + hf] = vy;
+    ch2[vf * stride + hf] = vb;
+  }
+  __syncwarp();
+  if (lane < 3) {  // LLF (group.rs:227-236)
+    float* ch = wbuf + lane * kWarpBuf;
+    llf_small(lfp[lane] + lf_index, lf_stride, cy, cx, [&](int vf, int hf, float v) { ch[vf * stride + hf] = v; });
+  }
+  __syncwarp();
+  for (int r = lane; r < 3 * R; r += 32) warp_row_pass<C>(wbuf + (r / R) * kWarpBuf, r % R, stride);
+  __syncwarp();
+  for (int r = lane; r < 3 * C; r += 32) warp_col_pass<R>(wbuf + (r / C) * kWarpBuf, r % C, stride);
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float* ch = wbuf + c * kWarpBuf;
+    float* pl = planes[c] + px0;
+#pragma unroll 4
+    for (int i = lane; i < R * C; i += 32) {
+      const int y = i / C, x = i % C;
+      pl[size_t(y) * plane_stride + x] = ch[y * stride + x];
+    }
   }
 }
 
@@ -1406,7 +1449,18 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     float* ch1 = wbuf + kWarpBuf;
     float* ch2 = wbuf + 2 * kWarpBuf;
     const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
-    if (is_dct) {
+    const size_t lf_index = size_t(by0 + by) * F.xb + bx0 + bx;
+    if (is_dct && R == 32 && C == 32) {
+      warp_dct_block<32, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+    } else if (is_dct && R == 32 && C == 16) {
+      warp_dct_block<32, 16>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+    } else if (is_dct && R == 16 && C == 32) {
+      warp_dct_block<16, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+    } else if (is_dct && R == 32 && C == 8) {
+      warp_dct_block<32, 8>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+    } else if (is_dct && R == 8 && C == 32) {
+      warp_dct_block<8, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+    } else if (is_dct) {
       const int stride = C + 1;
       const bool wide = R < C;
       for (uint32_t k = lane; k < dq.num_coeffs; k += 32) {
