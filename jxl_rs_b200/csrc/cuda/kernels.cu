@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
         bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
         bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
         bi.log_num_blocks = 31 - __clz(bi.num_blocks);
+        if (coeffs_offset + bi.num_coeffs > kGroupCoeffs) { err = JXG_ERR_INVALID_TRANSFORM; break; }  // overlapping varblocks
         block_off[bidx] = coeffs_offset;
         err = decode_block_pass(B, F, F.passes[0], T, s, 0, bi, nz, group_coeffs, coeffs_offset);
         coeffs_offset += bi.num_coeffs;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
         bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
         bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
         bi.log_num_blocks = 31 - __clz(bi.num_blocks);
+        if (coeffs_offset + bi.num_coeffs > kGroupCoeffs) { err = JXG_ERR_INVALID_TRANSFORM; break; }  // overlapping varblocks
         block_off[bidx] = coeffs_offset;
         for (uint32_t p = 0; p < np && !err; p++) {
           PassState s = st[p];
@@ -488,9 +490,14 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
           num_blocks = cx * cy;
           num_coeffs = num_blocks * 64;
           lnb = 31 - __clz(num_blocks);
-          block_off[bidx] = coeffs_offset;
-          ci = 0;
-          phase = PH_NNZ;
+          if (coeffs_offset + num_coeffs > kGroupCoeffs) {  // overlapping varblocks: the group's coefficient area would overflow
+            B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
+            done = true;
+          } else {
+            block_off[bidx] = coeffs_offset;
+            ci = 0;
+            phase = PH_NNZ;
+          }
         }
       }
     }
@@ -654,7 +661,8 @@ __global__ void __launch_bounds__(128) k_block_plan(const BatchDev B) {
       if (int(lane) >= d) incl += v;
     }
     const uint32_t row_total = __shfl_sync(0xffffffffu, incl, 31);
-    if (first) {
+    if (first && coeffs_offset + incl > kGroupCoeffs) bad = true;  // overlapping varblocks would overflow the group's area
+    if (first && !bad) {
       const uint32_t off = coeffs_offset + incl - nb * 64;
       const uint32_t shape = c_shape[tt];
       const uint32_t raw_quant = uint32_t(rq[bidx]);

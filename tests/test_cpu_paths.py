@@ -105,3 +105,26 @@ def test_effective_cpus_is_sane():
     from jxl_rs_b200.decoder import effective_cpus
     n = effective_cpus()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_front_end_survives_corrupt_files(golden_dir):
+    """Truncated / bit-flipped / spliced files must come back as an error code (or parse), never crash the process:
+    the host front-end is the part of the product that touches untrusted bytes first."""
+    import ctypes as C
+    import glob
+    from jxl_rs_b200 import abi
+    from tests.fuzz_util import mutants
+    lib = abi.load_library()
+    paths = sorted(glob.glob(os.path.join(golden_dir, "jxl", "*.jxl")))
+    parsed = errors = 0
+    for _, data in mutants(paths, seed=1234, count=160):
+        for parse, free in ((lib.jxg_parse_file, lib.jxg_parsed_free), (lib.jxg_modular_parse_file, lib.jxg_modular_parsed_free)):
+            h, info = C.c_void_p(), abi.JxgImageInfo()
+            r = parse(data, len(data), C.byref(h), C.byref(info))
+            if r == 0:
+                parsed += 1
+                free(h)
+            else:
+                errors += 1
+                assert r in abi.ERRORS, r
+    assert errors > 0 and parsed >= 0

@@ -57,3 +57,45 @@ def test_large_single_image_epf3():
     diff = np.abs(out.numpy().astype(np.int16) - ref.astype(np.int16))
     assert diff.max() <= 1
     assert (diff != 0).mean() < 0.01
+
+
+def test_device_survives_corrupt_streams(golden_dir):
+    """Mutated files that still get through the front-end are decoded on the GPU: every outcome must be a clean result
+    or a JxgError — no CUDA fault — and the context must still decode a good file afterwards."""
+    import glob
+    import os
+    import torch
+    import jxl_rs_b200 as j
+    import synth
+    from tests.fuzz_util import mutants
+    paths = sorted(glob.glob(os.path.join(golden_dir, "jxl", "*.jxl")))
+    ctx = j.JxgContext(0)
+    decoded = failed = 0
+    for _, data in mutants(paths, seed=99, count=220):
+        for parse_cls, modular in ((j.ParsedFrame, False), (j.ModularParsedFrame, True)):
+            try:
+                fr = parse_cls(data)
+            except abi.JxgError:
+                continue
+            if fr.width * fr.height > 40_000_000:
+                continue
+            out = torch.empty((fr.height, fr.width, 3), dtype=torch.uint8).pin_memory()
+            b = j.ModularBatch(ctx) if modular else j.Batch(ctx, 1)
+            try:
+                if modular:
+                    b.add(fr, out.data_ptr(), fr.width * 3, False)
+                else:
+                    b.add(fr, out.data_ptr(), fr.width * 3, abi.FORMAT_RGB_U8, False)
+                b.run()
+                b.wait()
+                decoded += 1
+            except abi.JxgError as e:
+                assert e.code != -20, f"CUDA error on a corrupt stream: {e}"
+                failed += 1
+            finally:
+                b.close()
+    assert decoded + failed > 20
+    good = synth.encode_synthetic(300, 200, 5, 0.7, 2, 1, 1)
+    (o,) = j.decode_files(ctx, [good])
+    assert o.shape == (200, 300, 3)
+    ctx.close()
