@@ -209,7 +209,7 @@ int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, co
  * section 0, ModularLF streams, group headers / local trees) is jxg_modular_parse_file; a Rust host would hand over
  * the same state from Frame::decode_lf_global / decode_lf_group (frame/decode.rs:307-497).
  * Device scope: 8-bit RGB / grey, one pass, global transforms RCT and Squeeze, group-local RCT, ANS or prefix codes,
- * all 14 predictors incl. the weighted one, properties 0..15. Palette, LZ77 and reference-channel properties return
+ * all 14 predictors incl. the weighted one, all properties incl. those of reference channels. Palette and LZ77 return
  * JXG_ERR_UNSUPPORTED (no CPU fallback). Output: interleaved RGB u8 (grey replicated). */
 int jxg_modular_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info);
 void jxg_modular_parsed_free(void* parsed);

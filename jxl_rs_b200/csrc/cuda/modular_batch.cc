@@ -41,6 +41,7 @@ struct ModularBatch {
   std::vector<MRectDev> rects;
   std::vector<MCodeDev> codes;
   std::vector<MRctDev> rcts;
+  std::vector<uint32_t> refs;
   std::vector<std::vector<MJobDev>> levels;  // jobs grouped by plan step index
   std::vector<int> level_kind;
   std::vector<MJobDev> store_jobs;
@@ -52,7 +53,7 @@ struct ModularBatch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_decode = nullptr;
   int32_t* status_host = nullptr;
   // device pools (context-owned buffers are reused where the meaning matches)
-  DevBuf d_streams, d_order, d_rct_streams, d_rects, d_codes, d_rcts, d_jobs, d_wp;
+  DevBuf d_streams, d_order, d_rct_streams, d_rects, d_codes, d_rcts, d_refs, d_jobs, d_wp;
 };
 
 uint64_t blob_append(ModularBatch* b, const void* p, size_t bytes, size_t align = 16, size_t tail = 0) {
@@ -83,8 +84,6 @@ uint32_t add_code(ModularBatch* b, const jxg::EntropyCode& c) {
 }
 
 uint64_t add_tree(ModularBatch* b, const jxg::ModularTree& t) {
-  if (t.num_properties > 16)
-    throw jxg::Error(JXG_ERR_UNSUPPORTED, "MA-tree properties of previous channels (>= 16) are not implemented on the device path");
   std::vector<int32_t> nodes(t.nodes.size() * 4);
   for (size_t i = 0; i < t.nodes.size(); i++) {
     const jxg::TreeNode& n = t.nodes[i];
@@ -172,13 +171,24 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
     d.first_rect = uint32_t(b->rects.size());
     d.num_rects = uint32_t(st.rects.size());
     uint32_t max_w = 0;
-    for (const jxg::ModularRect& r : st.rects) {
+    for (size_t ri = 0; ri < st.rects.size(); ri++) {
+      const jxg::ModularRect& r = st.rects[ri];
       MRectDev rd;
       rd.stride = ms->coded[r.chan].w;
       rd.base = f.buf_off[r.chan] + uint64_t(r.y0) * rd.stride + r.x0;
       rd.w = r.w;
       rd.h = r.h;
       rd.pad = 0;
+      // reference channels: earlier channels of the stream with the same shape, nearest first (common.rs:52-60)
+      rd.ref_first = uint32_t(b->refs.size());
+      if (tree->num_properties > 16)
+        for (size_t k = ri; k-- > 0;) {
+          const jxg::ModularRect& q = st.rects[k];
+          if (q.w == r.w && q.h == r.h && ms->coded[q.chan].hshift == ms->coded[r.chan].hshift &&
+              ms->coded[q.chan].vshift == ms->coded[r.chan].vshift)
+            b->refs.push_back(d.first_rect + uint32_t(k));
+        }
+      rd.ref_count = uint32_t(b->refs.size()) - rd.ref_first;
       b->rects.push_back(rd);
       max_w = std::max(max_w, r.w);
     }
@@ -251,6 +261,7 @@ int launch_all(ModularBatch* b, cudaStream_t s, bool copy_to_host) {
   B.rects = static_cast<const MRectDev*>(b->d_rects.p);
   B.codes = static_cast<const MCodeDev*>(b->d_codes.p);
   B.rcts = static_cast<const MRctDev*>(b->d_rcts.p);
+  B.refs = static_cast<const uint32_t*>(b->d_refs.p);
   B.planes = static_cast<int32_t*>(cx->d_planes_a.p);
   B.wp_scratch = static_cast<uint8_t*>(b->d_wp.p);
   B.status = static_cast<int32_t*>(cx->d_status.p);
@@ -405,6 +416,7 @@ int jxg_modular_batch_run(void* bp, void* cuda_stream) {
   if (int r = upload(b->d_rects, b->rects, s, &b->h2d)) return r;
   if (int r = upload(b->d_codes, b->codes, s, &b->h2d)) return r;
   if (int r = upload(b->d_rcts, b->rcts, s, &b->h2d)) return r;
+  if (int r = upload(b->d_refs, b->refs, s, &b->h2d)) return r;
   if (int r = upload(b->d_jobs, all_jobs, s, &b->h2d)) return r;
   b->uploaded = true;
   if (int r = launch_all(b, s, true)) return r;

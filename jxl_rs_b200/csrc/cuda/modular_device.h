@@ -31,7 +31,9 @@ struct MStreamDev {  // one ModularHF(group) section
 
 struct MRectDev {
   uint64_t base;  // element index of the rect origin in the plane arena
-  uint32_t stride, w, h, pad;
+  uint32_t stride, w, h;
+  uint32_t ref_first;  // into MBatchDev::refs: rects usable as reference channels (same shape, nearest first)
+  uint32_t ref_count, pad;
 };
 
 struct MRctDev {
@@ -53,6 +55,7 @@ struct MBatchDev {
   const MRectDev* rects;
   const MCodeDev* codes;
   const MRctDev* rcts;
+  const uint32_t* refs;  // rect indices, see MRectDev::ref_first
   int32_t* planes;
   uint8_t* wp_scratch;
   int32_t* status;

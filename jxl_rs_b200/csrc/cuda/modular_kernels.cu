@@ -316,7 +316,26 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
               case 13: v = wsub(n, nn); break;
               case 14: v = wsub(left, ww); break;
               case 15: v = wp_prop; break;
-              default: v = 0; break;  // properties >= 16 are rejected by the host for the device path
+              default: {  // properties of previous channels of the same shape (decode/common.rs:40-83)
+                const uint32_t j = uint32_t(nd.x) - 16u, slot = j >> 2;
+                v = 0;
+                if (slot < rc.ref_count) {
+                  const MRectDev rr = B.rects[B.refs[rc.ref_first + slot]];
+                  const int32_t* rrow = B.planes + rr.base + size_t(y) * rr.stride;
+                  const int32_t* rprev = y > 0 ? rrow - rr.stride : rrow;
+                  const int32_t rv = rrow[x];
+                  if ((j & 3) == 0) v = wabs(rv);
+                  else if ((j & 3) == 1) v = rv;
+                  else {
+                    const int32_t vleft = x > 0 ? rrow[x - 1] : 0;
+                    const int32_t vtop = y > 0 ? rprev[x] : vleft;
+                    const int32_t vtl = (x > 0 && y > 0) ? rprev[x - 1] : vleft;
+                    const int64_t d = int64_t(rv) - clamped_gradient(vleft, vtop, vtl);
+                    v = (j & 3) == 2 ? int32_t(d < 0 ? -d : d) : int32_t(d);
+                  }
+                }
+                break;
+              }
             }
             nd = __ldg(nodes + (v > nd.y ? nd.z : nd.z + 1));
           }

@@ -53,7 +53,8 @@ def modular_source(width, height, seed):
 
 def encode_modular(width, height, seed, rct=6, squeeze=0, tree_kind=1, source=None) -> bytes:
     """One synthetic lossless Modular frame (8-bit RGB, group size 256). rct: 0 or 6 (YCoCg); squeeze: default
-    Squeeze transform on/off; tree_kind: 0 single Gradient leaf, 1 property tree, 2 weighted-predictor tree.
+    Squeeze transform on/off; tree_kind: 0 single Gradient leaf, 1 property tree, 2 weighted-predictor tree,
+    3 tree on properties of the previous channel (17, 19).
     source: optional H x W x 3 uint8 array to encode instead of the procedural image."""
     lib = _lib()
     src = None

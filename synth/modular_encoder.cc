@@ -79,6 +79,12 @@ std::vector<MNode> make_tree(uint32_t kind) {
     int lumaA = split(13, 6, a, split(13, -7, b, c));
     int chroma = split(10, 3, e, split(10, -4, f, g));
     root = split(0, 0, chroma, lumaA);
+  } else if (kind == 3) {
+    // properties of the previous channel (decode/common.rs:40-83): 17 = its value, 19 = its gradient residual
+    int a = leaf(5), b = leaf(5), c = leaf(1), e = leaf(5), f = leaf(5), g = leaf(0), h = leaf(5);
+    int luma = split(13, 6, a, split(13, -7, b, c));
+    int chroma = split(19, 4, e, split(19, -5, f, split(17, 100, g, h)));
+    root = split(0, 0, chroma, luma);
   } else {
     // weighted predictor with contexts from its max-error property (15), plus a Gradient branch for channel > 0
     int a = leaf(6), b = leaf(6), c = leaf(6), e = leaf(5), f = leaf(6);
@@ -124,7 +130,13 @@ void tokenize(const std::vector<ModularChannel>& chans, uint64_t stream_id, cons
     const ModularChannel& ch = chans[ci];
     if (!ch.w || !ch.h) continue;
     jxg::WpState wp(wph, uses_wp ? ch.w : 0);
-    int32_t props[16] = {0};
+    int32_t props[16 + 8] = {0};
+    // up to two reference channels (previous channels of the same shape, nearest first), decode/common.rs:40-83
+    const ModularChannel* refs[2] = {nullptr, nullptr};
+    for (size_t i = 0, n = 0; i < ci && n < 2; i++) {
+      const ModularChannel& rc = chans[ci - 1 - i];
+      if (rc.w == ch.w && rc.h == ch.h && rc.hshift == ch.hshift && rc.vshift == ch.vshift) refs[n++] = &rc;
+    }
     props[0] = int32_t(ci);
     props[1] = int32_t(stream_id);
     for (uint32_t y = 0; y < ch.h; y++) {
@@ -156,6 +168,20 @@ void tokenize(const std::vector<ModularChannel>& chans, uint64_t stream_id, cons
         int32_t wp_prop = 0;
         if (uses_wp) wp.predict(x, y, n, left, ne, nw, nn, wp_pred, wp_prop);
         props[15] = wp_prop;
+        for (int ri = 0; ri < 2; ri++) {
+          int32_t* rp = props + 16 + 4 * ri;
+          rp[0] = rp[1] = rp[2] = rp[3] = 0;
+          if (!refs[ri]) continue;
+          const int32_t* rrow = refs[ri]->row(y);
+          const int32_t* rprev = refs[ri]->row(y ? y - 1 : 0);
+          const int32_t v = rrow[x];
+          const int32_t vleft = x ? rrow[x - 1] : 0, vtop = y ? rprev[x] : vleft, vtl = (x && y) ? rprev[x - 1] : vleft;
+          const int64_t d = int64_t(v) - clamped_gradient(vleft, vtop, vtl);
+          rp[0] = wabs(v);
+          rp[1] = v;
+          rp[2] = int32_t(d < 0 ? -d : d);
+          rp[3] = int32_t(d);
+        }
         const MNode* nd = &tree[0];
         while (nd->property >= 0) nd = &tree[props[nd->property] > nd->splitval ? nd->left : nd->right];
         int64_t guess;

@@ -37,7 +37,8 @@ def test_lz77_flower_is_three_copies(golden_dir):
 
 
 @pytest.mark.parametrize("w,h,rct,sq,tk", [(64, 48, 0, 0, 0), (300, 200, 6, 0, 1), (300, 200, 0, 1, 2), (700, 530, 6, 1, 1),
-                                           (257, 513, 6, 1, 2), (1, 1, 0, 0, 0), (9, 1000, 6, 1, 0)])
+                                           (257, 513, 6, 1, 2), (1, 1, 0, 0, 0), (9, 1000, 6, 1, 0), (300, 260, 6, 0, 3),
+                                           (513, 300, 0, 1, 3)])
 def test_lossless_roundtrip(w, h, rct, sq, tk):
     """Writer (forward RCT / Squeeze written from the decoder definitions) -> oracle == source image, bit-exact."""
     import synth

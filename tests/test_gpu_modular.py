@@ -18,6 +18,8 @@ CASES = [
     (513, 300, 4, 0, 1, 0),      # Squeeze, ragged
     (1030, 770, 5, 6, 1, 2),     # RCT + Squeeze + weighted predictor
     (1024, 1024, 6, 6, 1, 1),
+    (700, 530, 7, 6, 0, 3),      # reference-channel properties (17, 19)
+    (513, 300, 8, 0, 1, 3),      # ... with Squeeze (channels of different shapes never reference each other)
 ]
 
 
