@@ -72,6 +72,75 @@ class BitReader {
   // Byte position (only valid on a byte boundary).
   size_t byte_pos() const { return total_ / 8; }
 
+  // Register-resident copy of the reader for the per-pixel Modular loops (the members of a BitReader reached
+  // through a reference are re-loaded and re-stored around every int32 sample store, which puts store-to-load
+  // forwarding on the symbol chain). Same semantics as the member functions above; `commit` writes it back.
+  struct Local {
+    const uint8_t* data;
+    size_t size, pos;
+    uint64_t buf;
+    unsigned bits;
+    // Guarantees >= 56 valid bits (zero bits past the end, like refill()).
+    inline void fill() {
+      if (pos + 8 <= size) {
+        uint64_t w;
+        memcpy(&w, data + pos, 8);
+        buf |= w << bits;
+        const unsigned nbytes = (63 - bits) >> 3;
+        pos += nbytes;
+        bits += nbytes * 8;
+        return;
+      }
+      while (bits <= 56) {
+        uint64_t byte = pos < size ? data[pos] : 0;
+        pos++;
+        buf |= byte << bits;
+        bits += 8;
+      }
+    }
+    // fill() without the end-of-data test; only valid while room() holds for the symbols still to be read.
+    inline void fill_unchecked() {
+      uint64_t w;
+      memcpy(&w, data + pos, 8);
+      buf |= w << bits;
+      const unsigned nbytes = (63 - bits) >> 3;
+      pos += nbytes;
+      bits += nbytes * 8;
+    }
+    // True if `nsym` more symbols of at most 48 bits each can be read with fill_unchecked(): the reader never
+    // holds more than 8 bytes beyond the consumed position, and every load is 8 bytes wide.
+    inline bool room(size_t nsym) const { return pos + nsym * 6 + 16 <= size; }
+    inline uint64_t peek(unsigned n) const { return buf & ((uint64_t(1) << n) - 1); }  // caller keeps bits >= n
+    inline void consume(unsigned n) {
+      buf >>= n;
+      bits -= n;
+    }
+  };
+  // Bits consumed so far == position of the next unread bit (see commit() below for why this holds).
+  size_t bit_pos() const { return pos_ * 8 - bits_; }
+  const uint8_t* data() const { return data_; }
+  size_t size_bytes() const { return size_; }
+  // Repositions the reader at absolute bit `bitpos` of its data (may lie past the end: the over-read is then
+  // reported by check(), like after reading there).
+  void seek_bits(size_t bitpos) {
+    pos_ = bitpos / 8;
+    buf_ = 0;
+    bits_ = 0;
+    total_ = pos_ * 8;
+    read(unsigned(bitpos % 8));
+  }
+
+  // The count of consumed bits is not carried by Local: every byte brought into the window advances pos and bits
+  // together (zero bytes past the end included), so the bits consumed through a Local are the change of
+  // 8 * pos - bits.
+  Local local() const { return Local{data_, size_, pos_, buf_, bits_}; }
+  void commit(const Local& l) {
+    total_ += (l.pos * 8 - l.bits) - (pos_ * 8 - bits_);
+    pos_ = l.pos;
+    buf_ = l.buf;
+    bits_ = l.bits;
+  }
+
  private:
   inline void refill() {
     if (pos_ + 8 <= size_) {  // whole-word refill (little-endian host); bits above bits_ are re-read identically later

@@ -89,6 +89,86 @@ class SymbolReader {
   // decode.rs:400: latched errors, over-read, final ANS state.
   void check_final_state(BitReader& br) const;
 
+  // Register-resident reader for the per-pixel Modular loops (no LZ77): BitReader::Local plus the ANS state.
+  // One fill() per symbol covers the 16 refill bits of the ANS step and the <= 32 extra bits of the hybrid uint
+  // (48 <= 56), so the symbol chain carries no refill branch. Same arithmetic as read_token / HybridUint::read.
+  template <bool kPrefix>
+  struct Local {
+    BitReader::Local br;
+    uint32_t state;
+    const EntropyCode* code;
+    uint32_t log_alpha, log_bucket;
+    inline uint32_t token(uint32_t cluster) {
+      if (kPrefix) {
+        constexpr unsigned kRootBits = 8;
+        const HuffEntry* t = &code->huff_entries[code->huff_offset[cluster]];
+        size_t pos = size_t(br.peek(kRootBits));
+        uint32_t n_bits = t[pos] & 0xff;
+        if (n_bits > kRootBits) {
+          br.consume(kRootBits);
+          n_bits -= kRootBits;
+          pos += t[pos] >> 16;
+          pos += size_t(br.peek(n_bits));
+        }
+        HuffEntry e = t[pos];
+        br.consume(e & 0xff);
+        return e >> 16;
+      }
+      const AnsBucket* buckets = code->ans_buckets.data() + (size_t(cluster) << log_alpha);
+      const uint32_t idx = state & 0xfff;
+      const uint32_t i = idx >> log_bucket;
+      const uint32_t pos = idx & ((1u << log_bucket) - 1);
+      const AnsBucket b = buckets[i];
+      // Mask arithmetic instead of ?: — alias / refill / direct-token are data dependent and the compiler turns
+      // selects into (mispredicted) branches.
+      const uint32_t am = 0u - uint32_t(pos >= b.alias_cutoff);
+      const uint32_t offset = (uint32_t(b.alias_offset) & am) + pos;
+      const uint32_t dist = uint32_t(b.dist) ^ (uint32_t(b.alias_dist_xor) & am);
+      const uint32_t symbol = i ^ ((i ^ uint32_t(b.alias_symbol)) & am);
+      const uint32_t next = (state >> kAnsLogSumProbs) * dist + offset;
+      const uint32_t rm = 0u - uint32_t(next < (1u << 16));
+      const uint32_t sh = 16u & rm;
+      state = (next << sh) | (uint32_t(br.peek(16)) & rm);
+      br.consume(sh);
+      return symbol;
+    }
+    // One whole symbol of `cluster`: fill, token, hybrid-uint extra bits.
+    inline bool room(size_t nsym) const { return br.room(nsym); }
+    template <bool kUnchecked = false>
+    inline uint32_t read_clustered(uint32_t cluster) {
+      if (kUnchecked) br.fill_unchecked();
+      else br.fill();
+      const uint32_t tok = token(cluster);
+      const HybridUint& u = code->uint_configs[cluster];
+      // Branch-free hybrid uint (hybrid_uint.rs:87-102): a direct token takes 0 extra bits and selects itself;
+      // whether a residual is below the split is data dependent and mispredicts on LF-image residuals.
+      const uint32_t dm = 0u - uint32_t(tok >= u.split_token());  // all ones: the token carries extra bits
+      const uint32_t bits_in_token = u.lsb + u.msb;
+      const uint32_t nbits =
+          (u.split_exponent - bits_in_token + ((tok - u.split_token()) >> bits_in_token)) & 31 & dm;
+      const uint32_t low = tok & ((1u << u.lsb) - 1);
+      const uint32_t token_nolow = tok >> u.lsb;
+      const uint32_t bits = uint32_t(br.peek(nbits));
+      br.consume(nbits);
+      const uint32_t hi = (token_nolow & ((1u << u.msb) - 1)) | (1u << u.msb);
+      const uint32_t composed = (((hi << nbits) | bits) << u.lsb) | low;
+      return tok ^ ((tok ^ composed) & dm);
+    }
+  };
+  bool can_localise() const { return !code_.lz77_enabled; }
+  uint32_t ans_state() const { return state_; }
+  void set_ans_state(uint32_t s) { state_ = s; }
+  bool uses_prefix() const { return code_.use_prefix; }
+  template <bool kPrefix>
+  Local<kPrefix> local(const BitReader& br) const {
+    return Local<kPrefix>{br.local(), state_, &code_, code_.log_alpha_size, kAnsLogSumProbs - code_.log_alpha_size};
+  }
+  template <bool kPrefix>
+  void commit(const Local<kPrefix>& l, BitReader& br) {
+    state_ = l.state;
+    br.commit(l.br);
+  }
+
  private:
   uint32_t read_clustered_lz77(BitReader& br, uint32_t cluster);
   // ans.rs:356-393 / huffman.rs:446-457 (in the header so that the per-pixel Modular loops inline it)

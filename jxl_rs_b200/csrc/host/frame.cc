@@ -1,6 +1,8 @@
 // See frame.h.
 #include "frame.h"
 
+#include <immintrin.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -182,28 +184,47 @@ void decode_lf_group(FrameState& fs, uint32_t g, BitReader& br) {
         fs.ytox_map[o] = int8_t(std::clamp(ch[0].row(y)[x], -128, 127));
         fs.ytob_map[o] = int8_t(std::clamp(ch[1].row(y)[x], -128, 127));
       }
-    uint32_t num = 0;
+    // EPF sharpness: one pass per row (range check folded into an OR so that the loop vectorises)
     for (uint32_t y = 0; y < hh; y++) {
+      const int32_t* e = ch[3].row(y);
+      uint8_t* eo = &fs.epf_map[size_t(y0 + y) * fs.xb + x0];
+      int32_t seen = 0;
       for (uint32_t x = 0; x < w; x++) {
-        size_t o = size_t(y0 + y) * fs.xb + x0 + x;
-        int32_t epf = ch[3].row(y)[x];
-        if (epf < 0 || epf > 7) fail("invalid EPF sharpness value");
-        fs.epf_map[o] = uint8_t(epf);
-        if (fs.transform_map[o] != 27) continue;  // already covered by an earlier varblock
+        seen |= e[x];
+        eo[x] = uint8_t(e[x]);
+      }
+      if (seen & ~7) fail("invalid EPF sharpness value");
+    }
+    // Varblocks in raster order at the first uncovered block (modular/mod.rs:1040-1075)
+    uint32_t num = 0;
+    const int32_t *raw_transforms = ch[2].row(0), *raw_quants = ch[2].row(1);
+    for (uint32_t y = 0; y < hh; y++) {
+      uint8_t* tm = &fs.transform_map[size_t(y0 + y) * fs.xb + x0];
+      int32_t* rq = &fs.raw_quant_map[size_t(y0 + y) * fs.xb + x0];
+      const uint32_t ngy = std::min(hh, (y / 32 + 1) * 32);
+      for (uint32_t x = 0; x < w;) {
+        if (tm[x] != 27) {  // already covered by an earlier varblock
+          x++;
+          continue;
+        }
         if (num >= count) fail("invalid VarDCT transform map");
-        int32_t raw_transform = ch[2].row(0)[num];
-        int32_t raw_quant = 1 + std::clamp(ch[2].row(1)[num], 0, 255);
+        const int32_t raw_transform = raw_transforms[num];
+        const int32_t raw_quant = 1 + std::clamp(raw_quants[num], 0, 255);
         if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
-        uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
-        uint32_t ngx = (x / 32 + 1) * 32, ngy = (y / 32 + 1) * 32;
-        if (x + cx > std::min(w, ngx) || y + cy > std::min(hh, ngy)) fail("HF block out of bounds");
+        const uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
+        const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
+        if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
         num++;
-        for (uint32_t iy = 0; iy < cy; iy++)
-          for (uint32_t ix = 0; ix < cx; ix++) {
-            size_t oo = size_t(y0 + y + iy) * fs.xb + x0 + x + ix;
-            fs.transform_map[oo] = uint8_t(raw_transform) | ((ix == 0 && iy == 0) ? 128 : 0);
-            fs.raw_quant_map[oo] = raw_quant;
+        for (uint32_t iy = 0; iy < cy; iy++) {
+          uint8_t* t = tm + size_t(iy) * fs.xb + x;
+          int32_t* q = rq + size_t(iy) * fs.xb + x;
+          for (uint32_t ix = 0; ix < cx; ix++) {  // a block covered earlier is overwritten, like mod.rs:1066-1075
+            t[ix] = uint8_t(raw_transform);
+            q[ix] = raw_quant;
           }
+        }
+        tm[x] |= 128;  // first block of the varblock
+        x += cx;
       }
     }
   }
@@ -264,22 +285,70 @@ void decode_hf_global(FrameState& fs, BitReader& br) {
   br.check();
 }
 
-// frame/adaptive_lf_smoothing.rs:44-125
+}  // namespace
+
+// frame/adaptive_lf_smoothing.rs:44-125. The reference is scalar Rust (no fused multiply-add), so the function is
+// compiled without floating-point contraction and the AVX2 body does, lane by lane, the same operations in the same
+// order as compute_pixel_channel (:20-41): results are bit-identical to the scalar definition.
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
 void adaptive_lf_smoothing(FrameState& fs) {
   const size_t xs = fs.xb, ys = fs.yb;
   if (xs <= 2 || ys <= 2) return;
-  float inv_quant_lf = (65536.0f / float(fs.global_scale)) / float(fs.quant_lf);
-  float lf_factors[3] = {inv_quant_lf * fs.lf_quant[0], inv_quant_lf * fs.lf_quant[1], inv_quant_lf * fs.lf_quant[2]};
+  const float inv_quant_lf = (65536.0f / float(fs.global_scale)) / float(fs.quant_lf);
+  const float lf_factors[3] = {inv_quant_lf * fs.lf_quant[0], inv_quant_lf * fs.lf_quant[1],
+                               inv_quant_lf * fs.lf_quant[2]};
   const float kSide = 0.20345139757231578f, kCorner = 0.0334829185968739f;
   const float kCenter = 1.0f - 4.0f * (kSide + kCorner);
-  std::vector<float> out[3] = {fs.lf[0], fs.lf[1], fs.lf[2]};
+  // In place: row y of the output only needs the original rows y-1, y, y+1, so two saved original rows per channel
+  // (the previous one and the current one) replace the reference's second image; border samples stay unchanged
+  // (:80-85).
+  std::vector<float> saved(6 * xs);
+  float* prev[3];
+  float* cur[3];
+  for (int c = 0; c < 3; c++) {
+    prev[c] = &saved[size_t(2 * c) * xs];
+    cur[c] = &saved[size_t(2 * c + 1) * xs];
+    memcpy(prev[c], &fs.lf[c][0], xs * sizeof(float));
+  }
+  const __m256 vside = _mm256_set1_ps(kSide), vcorner = _mm256_set1_ps(kCorner), vcenter = _mm256_set1_ps(kCenter);
+  const __m256 vabs = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
   for (size_t y = 1; y + 1 < ys; y++) {
-    for (size_t x = 1; x + 1 < xs; x++) {
+    float* outp[3];
+    const float* bot[3];
+    for (int c = 0; c < 3; c++) {
+      outp[c] = &fs.lf[c][y * xs];
+      bot[c] = &fs.lf[c][(y + 1) * xs];
+      memcpy(cur[c], outp[c], xs * sizeof(float));
+    }
+    size_t x = 1;
+    for (; x + 8 <= xs - 1; x += 8) {
+      __m256 gap = _mm256_set1_ps(0.5f), mc[3], sm[3];
+      for (int c = 0; c < 3; c++) {
+        const float* t = prev[c] + x;
+        const float* m = cur[c] + x;
+        const float* b = bot[c] + x;
+        const __m256 corner = _mm256_add_ps(
+            _mm256_add_ps(_mm256_add_ps(_mm256_loadu_ps(t - 1), _mm256_loadu_ps(t + 1)), _mm256_loadu_ps(b - 1)),
+            _mm256_loadu_ps(b + 1));
+        const __m256 side = _mm256_add_ps(
+            _mm256_add_ps(_mm256_add_ps(_mm256_loadu_ps(m - 1), _mm256_loadu_ps(m + 1)), _mm256_loadu_ps(t)),
+            _mm256_loadu_ps(b));
+        mc[c] = _mm256_loadu_ps(m);
+        sm[c] = _mm256_add_ps(_mm256_add_ps(_mm256_mul_ps(corner, vcorner), _mm256_mul_ps(side, vside)),
+                              _mm256_mul_ps(mc[c], vcenter));
+        const __m256 d = _mm256_div_ps(_mm256_sub_ps(mc[c], sm[c]), _mm256_set1_ps(lf_factors[c]));
+        gap = _mm256_max_ps(_mm256_and_ps(d, vabs), gap);  // operand order: keeps gap if d is NaN, like f32::max
+      }
+      const __m256 factor =
+          _mm256_max_ps(_mm256_sub_ps(_mm256_set1_ps(3.0f), _mm256_mul_ps(_mm256_set1_ps(4.0f), gap)), _mm256_setzero_ps());
+      for (int c = 0; c < 3; c++)
+        _mm256_storeu_ps(outp[c] + x, _mm256_add_ps(_mm256_mul_ps(_mm256_sub_ps(sm[c], mc[c]), factor), mc[c]));
+    }
+    for (; x + 1 < xs; x++) {
       float gap = 0.5f, mc[3], sm[3];
       for (int c = 0; c < 3; c++) {
-        const float* t = &fs.lf[c][(y - 1) * xs];
-        const float* m = &fs.lf[c][y * xs];
-        const float* b = &fs.lf[c][(y + 1) * xs];
+        const float *t = prev[c], *m = cur[c], *b = bot[c];
         float corner = t[x - 1] + t[x + 1] + b[x - 1] + b[x + 1];
         float side = m[x - 1] + m[x + 1] + t[x] + b[x];
         mc[c] = m[x];
@@ -287,13 +356,12 @@ void adaptive_lf_smoothing(FrameState& fs) {
         gap = std::max(gap, std::fabs((mc[c] - sm[c]) / lf_factors[c]));
       }
       float factor = std::max(3.0f - 4.0f * gap, 0.0f);
-      for (int c = 0; c < 3; c++) out[c][y * xs + x] = (sm[c] - mc[c]) * factor + mc[c];
+      for (int c = 0; c < 3; c++) outp[c][x] = (sm[c] - mc[c]) * factor + mc[c];
     }
+    for (int c = 0; c < 3; c++) std::swap(prev[c], cur[c]);
   }
-  for (int c = 0; c < 3; c++) fs.lf[c] = std::move(out[c]);
 }
-
-}  // namespace
+#pragma GCC pop_options
 
 std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) {
   auto fsp = std::make_unique<FrameState>();

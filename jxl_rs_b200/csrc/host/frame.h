@@ -80,6 +80,9 @@ struct FrameState {
   void fill_desc(JxgFrameDesc* d, uint32_t output_format);
 };
 
+// frame/adaptive_lf_smoothing.rs:44 on fs.lf (uses xb, yb, global_scale, quant_lf, lf_quant). Exposed for the tests.
+void adaptive_lf_smoothing(FrameState& fs);
+
 // Parses a complete file up to (not including) the HF groups of its first
 // displayed VarDCT frame. Throws jxg::Error.
 std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size);

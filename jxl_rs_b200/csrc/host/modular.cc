@@ -1,8 +1,12 @@
 // See modular.h.
 #include "modular.h"
 
+#include <immintrin.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 namespace jxg {
 
@@ -261,6 +265,215 @@ ModularTree ModularTree::read(BitReader& br, size_t size_limit) {
 // trees are performance variants of the same semantics)
 // ---------------------------------------------------------------------------
 
+// Reader adapters for the specialised walks below: `read_clustered(cluster)` returns one whole symbol.
+struct SlowReader {  // LZ77 streams: the member-state reader
+  SymbolReader* r;
+  BitReader* br;
+  inline bool room(size_t) const { return false; }
+  template <bool kUnchecked = false>
+  inline uint32_t read_clustered(uint32_t cluster) { return r->read_clustered(*br, cluster); }
+};
+
+// Single-cluster ANS reader for big static-leaf channels. The per-symbol loop is bound by instruction issue, not
+// by latency, so everything that is constant for one cluster is tabulated:
+//  * the alias table of the cluster is expanded into a direct 4096-entry table
+//    (symbol | offset << 8 | (freq - 1) << 20, 16 KB): no alias compare / selects (ans.rs:356-393);
+//  * the hybrid-uint configuration becomes a per-token table {number of extra bits, value without them}
+//    (hybrid_uint.rs:87-102): value = base | extra_bits << lsb;
+//  * the bit window is re-loaded from a bit position every symbol (one unaligned 8-byte load gives >= 57 bits,
+//    enough for the 16 refill bits + <= 31 extra bits), so consuming is one addition.
+// Same arithmetic, entry by entry, as SymbolReader::read_token + HybridUint::read.
+struct DirectReader {
+  const uint8_t* data;
+  size_t size;  // bytes
+  size_t bitpos;
+  uint32_t state;
+  const uint32_t* tab;
+  const uint64_t* tok_tab;  // base << 8 | nbits
+  uint32_t lsb;
+  // `nsym` more symbols of <= 47 bits can be read with unchecked 8-byte loads.
+  inline bool room(size_t nsym) const { return (bitpos >> 3) + nsym * 6 + 16 <= size; }
+  template <bool kUnchecked = false>
+  inline uint32_t read_clustered(uint32_t /*cluster*/) {
+    uint64_t w;
+    const size_t byte = bitpos >> 3;
+    if (kUnchecked || byte + 8 <= size) {
+      memcpy(&w, data + byte, 8);
+    } else {  // tail of the section: zero bits past the end (bit_reader.rs:109 reports the over-read afterwards)
+      w = 0;
+      for (size_t i = 0; i < 8 && byte + i < size; i++) w |= uint64_t(data[byte + i]) << (8 * i);
+    }
+    w >>= bitpos & 7;
+    const uint32_t e = tab[state & 0xfff];
+    const uint32_t next = (state >> kAnsLogSumProbs) * ((e >> 20) + 1) + ((e >> 8) & 0xfff);
+    const uint32_t sh = uint32_t(next < (1u << 16)) << 4;
+    state = (next << sh) | uint32_t(_bzhi_u64(w, sh));
+    w >>= sh;
+    const uint64_t t = tok_tab[e & 0xff];
+    const uint32_t nbits = uint32_t(t & 0xff);
+    bitpos += sh + nbits;
+    return uint32_t(t >> 8) | (uint32_t(_bzhi_u64(w, nbits)) << lsb);
+  }
+};
+
+static void build_direct_tables(const EntropyCode& code, uint32_t cluster, uint32_t* tab, uint64_t* tok_tab) {
+  const uint32_t log_bucket = kAnsLogSumProbs - code.log_alpha_size;
+  const AnsBucket* buckets = code.ans_buckets.data() + (size_t(cluster) << code.log_alpha_size);
+  for (uint32_t idx = 0; idx < 4096; idx++) {
+    const uint32_t i = idx >> log_bucket, pos = idx & ((1u << log_bucket) - 1);
+    const AnsBucket& b = buckets[i];
+    const bool alias = pos >= b.alias_cutoff;
+    const uint32_t offset = (alias ? b.alias_offset : 0) + pos;
+    const uint32_t dist = uint32_t(b.dist) ^ (alias ? b.alias_dist_xor : 0);
+    const uint32_t symbol = alias ? b.alias_symbol : i;
+    // build_alias_map guarantees 1 <= dist <= 4096 and offset < dist for every slot.
+    tab[idx] = (symbol & 0xff) | ((offset & 0xfff) << 8) | (((dist - 1) & 0xfff) << 20);
+  }
+  const HybridUint& u = code.uint_configs[cluster];
+  for (uint32_t tok = 0; tok < 256; tok++) {
+    if (tok < u.split_token()) {
+      tok_tab[tok] = uint64_t(tok) << 8;
+      continue;
+    }
+    const uint32_t bits_in_token = u.lsb + u.msb;
+    const uint32_t nbits = (u.split_exponent - bits_in_token + ((tok - u.split_token()) >> bits_in_token)) & 31;
+    const uint32_t low = tok & ((1u << u.lsb) - 1);
+    const uint32_t hi = ((tok >> u.lsb) & ((1u << u.msb) - 1)) | (1u << u.msb);
+    const uint32_t base = ((hi << nbits) << u.lsb) | low;
+    tok_tab[tok] = uint64_t(base) << 8 | nbits;
+  }
+}
+
+// Only channel / stream id are tested by the tree: one leaf (predictor, offset, multiplier, cluster) for the
+// whole channel, so the symbol chain is independent of the sample values.
+template <class R>
+static void decode_static_leaf(ModularChannel& ch, const TreeNode* nd, uint32_t cluster, R& io) {
+  R rd = io;  // a true local (its address never escapes), so the reader state lives in registers
+  const size_t w = ch.w, h = ch.h;
+  const uint32_t pred = nd->left;
+  const int64_t offset = nd->val, mul = nd->right;
+  const uint32_t uoff = uint32_t(offset), umul = uint32_t(mul);
+  // One row of the Gradient predictor, y > 0. `unchecked` rows (all but the last few of a section) refill the bit
+  // window without the end-of-data test, which keeps the byte-wise tail path out of the loop body.
+  // clamped_gradient runs on xmm scalars: its selects depend only on i32 comparisons of left / top / topleft, and
+  // left + top - topleft is exact in wrapping i32 whenever it is the selected value (it then lies between left and
+  // top). That keeps the serial left -> left chain free of (unpredictable) branches and out of the general-purpose
+  // registers the symbol reader needs.
+  auto gradient_row = [&](auto unchecked, int32_t* row, const int32_t* top_row) {
+    constexpr bool kU = decltype(unchecked)::value;
+    __m128i left = _mm_cvtsi32_si128(top_row[0]), topleft = left;  // x = 0: left = topleft = top_row[0]
+    for (size_t x = 0; x < w; x++) {
+      const __m128i top = _mm_cvtsi32_si128(top_row[x]);
+      const uint32_t res = uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
+      const __m128i add = _mm_cvtsi32_si128(int32_t(uoff + umul * res));
+      const __m128i mn = _mm_min_epi32(left, top), mx = _mm_max_epi32(left, top);
+      __m128i g = _mm_sub_epi32(_mm_add_epi32(left, top), topleft);
+      g = _mm_blendv_epi8(g, mx, _mm_cmpgt_epi32(mn, topleft));  // topleft < min -> max
+      g = _mm_blendv_epi8(g, mn, _mm_cmpgt_epi32(topleft, mx));  // topleft > max -> min
+      left = _mm_add_epi32(g, add);
+      row[x] = _mm_cvtsi128_si32(left);
+      topleft = top;
+    }
+  };
+  // One row of a predictor that only looks at the left neighbour (West; also Gradient on the first row, where
+  // top = topleft = left, predict.rs:64-103) or at nothing (Zero).
+  auto west_row = [&](auto unchecked, int32_t* row, uint32_t left, uint32_t keep) {
+    constexpr bool kU = decltype(unchecked)::value;
+    for (size_t x = 0; x < w; x++) {
+      left = (left & keep) + uoff + umul * uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
+      row[x] = int32_t(left);
+    }
+  };
+  auto next_signed = [&]() { return int64_t(unpack_signed(rd.read_clustered(cluster))); };
+  for (size_t y = 0; y < h; y++) {
+    int32_t* row = ch.row(uint32_t(y));
+    const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+    const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+    const bool fast = rd.room(w);
+    if (pred == kZero || pred == kWest || (pred == kGradient && y == 0)) {
+      const uint32_t keep = pred == kZero ? 0u : ~0u;
+      const uint32_t left0 = y > 0 ? uint32_t(top_row[0]) : 0u;  // x = 0: left = top_row[0], or 0 at the origin
+      if (fast) west_row(std::true_type(), row, left0, keep);
+      else west_row(std::false_type(), row, left0, keep);
+    } else if (pred == kGradient) {
+      if (fast) gradient_row(std::true_type(), row, top_row);
+      else gradient_row(std::false_type(), row, top_row);
+    } else {
+      for (size_t x = 0; x < w; x++) {
+        Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
+        const int64_t guess = predict_one(pred, n, 0) + offset;
+        row[x] = int32_t(guess + mul * next_signed());
+      }
+    }
+  }
+  io = rd;
+}
+
+// No weighted predictor, no reference-channel properties: evaluate only the properties the walk visits.
+template <class R>
+static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, const TreeNode* nodes,
+                              const uint8_t* cmap, R& io) {
+  R rd = io;
+  const size_t w = ch.w, h = ch.h;
+  for (size_t y = 0; y < h; y++) {
+    int32_t* row = ch.row(uint32_t(y));
+    const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+    const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+    int32_t prev_p9 = 0;
+    for (size_t x = 0; x < w; x++) {
+      const Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
+      const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
+      const TreeNode* nd = nodes;
+      while (nd->property >= 0) {
+        int32_t v;
+        switch (nd->property) {
+          case 0: v = int32_t(ci); break;
+          case 1: v = int32_t(stream_id); break;
+          case 2: v = int32_t(y); break;
+          case 3: v = int32_t(x); break;
+          case 4: v = wabs(n.top); break;
+          case 5: v = wabs(n.left); break;
+          case 6: v = n.top; break;
+          case 7: v = n.left; break;
+          case 8: v = wsub(n.left, prev_p9); break;
+          case 9: v = p9; break;
+          case 10: v = wsub(n.left, n.topleft); break;
+          case 11: v = wsub(n.topleft, n.top); break;
+          case 12: v = wsub(n.top, n.topright); break;
+          case 13: v = wsub(n.top, n.toptop); break;
+          case 14: v = wsub(n.left, n.leftleft); break;
+          default: v = 0; break;  // property 15 without the weighted predictor is always 0
+        }
+        nd = nodes + (v > nd->val ? nd->left : nd->right);
+      }
+      prev_p9 = p9;
+      const int64_t guess = predict_one(nd->left, n, 0) + int64_t(nd->val);
+      row[x] = int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
+    }
+  }
+  io = rd;
+}
+
+// Runs `f(reader)` with the register-resident reader when the code allows it (no LZ77), else with the member one.
+template <class F>
+static void with_reader(SymbolReader& reader, BitReader& br, F&& f) {
+  if (!reader.can_localise()) {
+    SlowReader s{&reader, &br};
+    f(s);
+  } else if (reader.uses_prefix()) {
+    auto l = reader.local<true>(br);
+    f(l);
+    reader.commit(l, br);
+  } else {
+    auto l = reader.local<false>(br);
+    f(l);
+    reader.commit(l, br);
+  }
+}
+
+static std::atomic<bool> g_force_generic_walk{false};
+void set_force_generic_walk(bool on) { g_force_generic_walk.store(on); }
+
 static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_t stream_id, const GroupHeader& header,
                            const ModularTree& tree, SymbolReader& reader, BitReader& br) {
   ModularChannel& ch = *chans[ci];
@@ -281,77 +494,30 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
       if (nd.property < 32) used_mask |= 1u << nd.property;
       if (nd.property >= 16) wide_props = true;
     }
-  if (!use_wp && !wide_props && (used_mask & ~3u) == 0) {
-    // Only channel / stream id are tested: one leaf for the whole channel.
+  const bool specialise = !g_force_generic_walk.load(std::memory_order_relaxed);
+  if (specialise && !use_wp && !wide_props && (used_mask & ~3u) == 0) {
     const TreeNode* nd = nodes;
     while (nd->property >= 0) nd = nodes + (props[nd->property] > nd->val ? nd->left : nd->right);
-    const uint32_t pred = nd->left;
     const uint32_t cluster = tree.code.context_map[nd->ctx];  // one leaf -> one cluster for the whole channel
-    const int64_t offset = nd->val, mul = nd->right;
-    auto next_signed = [&]() { return int64_t(unpack_signed(reader.read_clustered(br, cluster))); };
-    for (size_t y = 0; y < h; y++) {
-      int32_t* row = ch.row(uint32_t(y));
-      const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
-      const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
-      if (pred == kGradient) {
-        for (size_t x = 0; x < w; x++) {
-          const int64_t left = x > 0 ? row[x - 1] : (y > 0 ? top_row[0] : 0);
-          const int64_t top = y > 0 ? top_row[x] : left;
-          const int64_t topleft = (x > 0 && y > 0) ? top_row[x - 1] : left;
-          const int64_t guess = clamped_gradient(left, top, topleft) + offset;
-          row[x] = int32_t(guess + mul * next_signed());
-        }
-      } else if (pred == kZero) {
-        for (size_t x = 0; x < w; x++) row[x] = int32_t(offset + mul * next_signed());
-      } else {
-        for (size_t x = 0; x < w; x++) {
-          Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
-          const int64_t guess = predict_one(pred, n, 0) + offset;
-          row[x] = int32_t(guess + mul * next_signed());
-        }
-      }
+    if (reader.can_localise() && !reader.uses_prefix() && w * h >= 8192) {
+      // big channel, one ANS cluster: direct table (its 4096-entry build is < 1 % of the channel)
+      uint32_t tab[4096];
+      uint64_t tok_tab[256];
+      build_direct_tables(tree.code, cluster, tab, tok_tab);
+      DirectReader d{br.data(), br.size_bytes(), br.bit_pos(), reader.ans_state(), tab, tok_tab,
+                     tree.code.uint_configs[cluster].lsb};
+      decode_static_leaf(ch, nd, cluster, d);
+      reader.set_ans_state(d.state);
+      br.seek_bits(d.bitpos);
+    } else {
+      with_reader(reader, br, [&](auto& rd) { decode_static_leaf(ch, nd, cluster, rd); });
     }
     br.check();
     return;
   }
-  if (!use_wp && !wide_props) {
-    // No weighted predictor: evaluate only the properties the walk actually visits.
-    for (size_t y = 0; y < h; y++) {
-      int32_t* row = ch.row(uint32_t(y));
-      const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
-      const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
-      int32_t prev_p9 = 0;
-      for (size_t x = 0; x < w; x++) {
-        const Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
-        const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
-        const TreeNode* nd = nodes;
-        while (nd->property >= 0) {
-          int32_t v;
-          switch (nd->property) {
-            case 0: v = int32_t(ci); break;
-            case 1: v = int32_t(stream_id); break;
-            case 2: v = int32_t(y); break;
-            case 3: v = int32_t(x); break;
-            case 4: v = wabs(n.top); break;
-            case 5: v = wabs(n.left); break;
-            case 6: v = n.top; break;
-            case 7: v = n.left; break;
-            case 8: v = wsub(n.left, prev_p9); break;
-            case 9: v = p9; break;
-            case 10: v = wsub(n.left, n.topleft); break;
-            case 11: v = wsub(n.topleft, n.top); break;
-            case 12: v = wsub(n.top, n.topright); break;
-            case 13: v = wsub(n.top, n.toptop); break;
-            case 14: v = wsub(n.left, n.leftleft); break;
-            default: v = 0; break;  // property 15 without the weighted predictor is always 0
-          }
-          nd = nodes + (v > nd->val ? nd->left : nd->right);
-        }
-        prev_p9 = p9;
-        const int64_t guess = predict_one(nd->left, n, 0) + int64_t(nd->val);
-        row[x] = int32_t(guess + int64_t(nd->right) * int64_t(reader.read_signed(br, nd->ctx)));
-      }
-    }
+  if (specialise && !use_wp && !wide_props) {
+    const uint8_t* cmap = tree.code.context_map.data();
+    with_reader(reader, br, [&](auto& rd) { decode_lazy_props(ch, ci, stream_id, nodes, cmap, rd); });
     br.check();
     return;
   }

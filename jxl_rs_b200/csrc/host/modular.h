@@ -95,5 +95,8 @@ void meta_apply_transforms(std::vector<ModularChannel>& channels, uint32_t& nb_m
 void undo_transforms(std::vector<ModularChannel>& channels, const GroupHeader& header, uint32_t bit_depth);
 void decode_modular_channels(std::vector<ModularChannel*>& channels, size_t stream_id, const GroupHeader& header,
                              const ModularTree& tree, BitReader& br);
+// Test hook: route every channel through the generic all-properties loop instead of the specialised walks
+// (static leaf / direct-table ANS / lazy properties), for differential tests of the fast paths.
+void set_force_generic_walk(bool on);
 
 }  // namespace jxg

@@ -133,4 +133,24 @@ int jxo_t_parse_ok(const uint8_t* data, size_t size) {
     return e.code;
   }
 }
+
+// Differential tests of the host front-end's specialised Modular walks: 1 routes every channel through the generic
+// all-properties loop.
+void jxo_t_force_generic_walk(int on) { set_force_generic_walk(on != 0); }
+
+// frame/adaptive_lf_smoothing.rs on caller planes (3 x ys x xs f32, in place), for the known-answer test.
+void jxo_t_adaptive_lf_smoothing(uint32_t xs, uint32_t ys, uint32_t global_scale, uint32_t quant_lf,
+                                 const float* lf_quant, float* planes) {
+  FrameState fs;
+  fs.xb = xs;
+  fs.yb = ys;
+  fs.global_scale = global_scale;
+  fs.quant_lf = quant_lf;
+  for (int c = 0; c < 3; c++) {
+    fs.lf_quant[c] = lf_quant[c];
+    fs.lf[c].assign(planes + size_t(c) * xs * ys, planes + size_t(c + 1) * xs * ys);
+  }
+  adaptive_lf_smoothing(fs);
+  for (int c = 0; c < 3; c++) std::copy(fs.lf[c].begin(), fs.lf[c].end(), planes + size_t(c) * xs * ys);
+}
 }

@@ -128,3 +128,49 @@ def test_front_end_survives_corrupt_files(golden_dir):
                 errors += 1
                 assert r in abi.ERRORS, r
     assert errors > 0 and parsed >= 0
+
+
+@pytest.mark.parametrize("name", REAL + ["green_queen_modular_e3.jxl", "lz77_flower.jxl", "tree_max_property_20.jxl", "grayscale_public_university.jxl"])
+def test_specialised_walks_match_the_generic_loop_on_reference_fixtures(golden_dir, name):
+    """Same differential check on the reference's real files (libjxl trees: property walks, prefix codes, LZ77,
+    weighted predictor), VarDCT front-end and Modular frames."""
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    data = open(os.path.join(golden_dir, "jxl", name), "rb").read()
+    dec = ob.decode_modular_file if name not in REAL else (lambda d: ob.decode_file(d, abi.FORMAT_RGB_U8)[0])
+    try:
+        fast = dec(data)
+        lib.jxo_t_force_generic_walk(1)
+        slow = dec(data)
+    finally:
+        lib.jxo_t_force_generic_walk(0)
+    assert np.array_equal(fast, slow)
+
+
+def test_specialised_modular_walks_match_the_generic_loop():
+    """Host front-end fast paths (static-leaf rows, direct-table ANS reader with unchecked refills, lazy-property
+    walk) against the generic all-properties loop (decode/channel.rs FullTree semantics): same LF image and HF
+    metadata, hence bit-identical coefficients and pixels, on a frame big enough (49 152 blocks, two LF groups wide)
+    that the direct-table reader and the checked tail rows both run."""
+    import synth
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    f = synth.encode_synthetic(2304 + 40, 1024 + 24, 4242, 0.5, 2, 1, 1)
+    try:
+        fast, taps_fast = ob.decode_file(f, abi.FORMAT_RGB_F32, taps=True)
+        lib.jxo_t_force_generic_walk(1)
+        slow, taps_slow = ob.decode_file(f, abi.FORMAT_RGB_F32, taps=True)
+    finally:
+        lib.jxo_t_force_generic_walk(0)
+    assert np.array_equal(taps_fast["coeffs"], taps_slow["coeffs"])
+    assert np.array_equal(fast, slow)
+    # Modular frames: group streams of 65 536 samples per channel through the same walks
+    for tk in (0, 1):
+        m = synth.encode_modular(700, 530, 11, 6, 0, tk)
+        try:
+            a = ob.decode_modular_file(m)
+            lib.jxo_t_force_generic_walk(1)
+            b = ob.decode_modular_file(m)
+        finally:
+            lib.jxo_t_force_generic_walk(0)
+        assert np.array_equal(a, b) and np.array_equal(a, synth.modular_source(700, 530, 11))

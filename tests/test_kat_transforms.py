@@ -117,3 +117,42 @@ def test_srgb_transfer_function(oracle):  # tf.rs:549-585
     neg = np.array([-0.25], np.float32)
     oracle.jxo_linear_to_srgb(1, neg.ctypes.data)
     assert neg[0] < 0
+
+
+@pytest.mark.parametrize("xs,ys", [(3, 3), (10, 4), (37, 21), (480, 270)])
+def test_adaptive_lf_smoothing_matches_the_scalar_definition(oracle, xs, ys):
+    """adaptive_lf_smoothing.rs:20-41,88-117 restated in numpy f32 (unfused multiplies and adds, like the scalar Rust):
+    the host front-end's AVX2 body must agree bit for bit, borders copied unchanged."""
+    import ctypes as C
+    rng = np.random.default_rng(xs * 1000 + ys)
+    lf_quant = np.array([1 / 4096, 1 / 512, 1 / 256], np.float32)
+    gs, qlf = 3072, 16
+    f = np.float32
+    inv = f(f(65536.0) / f(gs)) / f(qlf)
+    fac = [f(inv * lf_quant[c]) for c in range(3)]
+    # quantised LF samples: a smooth ramp (small gaps, factor > 0) with an edge and sparse outliers (factor == 0)
+    yy, xx = np.mgrid[0:ys, 0:xs]
+    q = np.round(0.3 * xx + 0.2 * yy + 6.0 * (yy >= ys // 2)).astype(np.int32)[None] + (rng.random((3, ys, xs)) < 0.05) * 3
+    lf = np.stack([(q[c] * fac[c]).astype(np.float32) for c in range(3)])
+    ws, wc = f(0.20345139757231578), f(0.0334829185968739)
+    wcen = f(f(1.0) - f(4.0) * f(ws + wc))
+    want = lf.copy()
+    gap = np.full((ys - 2, xs - 2), 0.5, np.float32)
+    mc, sm = [], []
+    for c in range(3):
+        p = lf[c]
+        corner = ((p[:-2, :-2] + p[:-2, 2:]) + p[2:, :-2]) + p[2:, 2:]
+        side = ((p[1:-1, :-2] + p[1:-1, 2:]) + p[:-2, 1:-1]) + p[2:, 1:-1]
+        m = p[1:-1, 1:-1]
+        s = (corner * wc + side * ws) + m * wcen
+        mc.append(m)
+        sm.append(s)
+        gap = np.maximum(gap, np.abs((m - s) / fac[c]))
+    factor = np.maximum(f(3.0) - f(4.0) * gap, f(0.0))
+    for c in range(3):
+        want[c, 1:-1, 1:-1] = (sm[c] - mc[c]) * factor + mc[c]
+    got = lf.copy()
+    oracle.jxo_t_adaptive_lf_smoothing(xs, ys, gs, qlf, lf_quant.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p))
+    if xs * ys > 100:
+        assert (factor == 0).any() and (factor > 0).any()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
