@@ -654,7 +654,7 @@ int jxg_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo
   }
 }
 
-void jxg_parsed_free(void* parsed) { delete static_cast<jxg::FrameState*>(parsed); }
+void jxg_parsed_free(void* parsed) { jxg::recycle_frame_state(static_cast<jxg::FrameState*>(parsed)); }
 
 int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, const uint8_t** hf_bytes,
                     const uint64_t** sec_off, const uint32_t** sec_len, uint32_t* n_sections) {

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "quant.h"
 
@@ -363,10 +364,62 @@ void adaptive_lf_smoothing(FrameState& fs) {
 }
 #pragma GCC pop_options
 
+namespace {
+
+// Pool of the large FrameState buffers (see recycle_frame_state in frame.h).
+struct BigBuffers {
+  std::vector<uint8_t> codestream, transform_map, epf_map, quant_lf_map;
+  std::vector<float> lf[3];
+  std::vector<int32_t> raw_quant_map;
+  size_t bytes() const {
+    return codestream.capacity() + transform_map.capacity() + epf_map.capacity() + quant_lf_map.capacity() +
+           4 * (lf[0].capacity() + lf[1].capacity() + lf[2].capacity() + raw_quant_map.capacity());
+  }
+};
+constexpr size_t kPoolMaxEntries = 512, kPoolMaxBytes = size_t(2) << 30;
+std::mutex g_pool_mutex;
+std::vector<BigBuffers> g_pool;
+size_t g_pool_bytes = 0;
+
+void take_buffers(FrameState& fs) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_pool.empty()) return;
+  BigBuffers b = std::move(g_pool.back());
+  g_pool.pop_back();
+  g_pool_bytes -= b.bytes();
+  fs.codestream = std::move(b.codestream);
+  fs.transform_map = std::move(b.transform_map);
+  fs.epf_map = std::move(b.epf_map);
+  fs.quant_lf_map = std::move(b.quant_lf_map);
+  fs.raw_quant_map = std::move(b.raw_quant_map);
+  for (int c = 0; c < 3; c++) fs.lf[c] = std::move(b.lf[c]);
+}
+
+}  // namespace
+
+void recycle_frame_state(FrameState* fs) {
+  if (!fs) return;
+  BigBuffers b;
+  b.codestream = std::move(fs->codestream);
+  b.transform_map = std::move(fs->transform_map);
+  b.epf_map = std::move(fs->epf_map);
+  b.quant_lf_map = std::move(fs->quant_lf_map);
+  b.raw_quant_map = std::move(fs->raw_quant_map);
+  for (int c = 0; c < 3; c++) b.lf[c] = std::move(fs->lf[c]);
+  delete fs;
+  const size_t n = b.bytes();
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_pool.size() < kPoolMaxEntries && g_pool_bytes + n <= kPoolMaxBytes) {
+    g_pool_bytes += n;
+    g_pool.push_back(std::move(b));
+  }  // else: b is freed on return
+}
+
 std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) {
   auto fsp = std::make_unique<FrameState>();
   FrameState& fs = *fsp;
-  fs.codestream = extract_codestream(data, size);
+  take_buffers(fs);
+  extract_codestream(data, size, fs.codestream);
   BitReader br(fs.codestream.data(), fs.codestream.size());
   fs.file = read_file_header(br);
   if (fs.file.have_preview) fail("preview frames are outside the hot-path scope", kErrUnsupported);

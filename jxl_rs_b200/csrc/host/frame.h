@@ -87,4 +87,9 @@ void adaptive_lf_smoothing(FrameState& fs);
 // displayed VarDCT frame. Throws jxg::Error.
 std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size);
 
+// Destroys a FrameState but keeps its large buffers (codestream copy, LF planes, per-block maps; ~4 MB for a 4K
+// frame) in a bounded process-wide pool that parse_vardct_file draws from: a steady-state decode loop then does no
+// large malloc / free, i.e. no mmap, page-fault and munmap (TLB shoot-down) traffic between the parse threads.
+void recycle_frame_state(FrameState* fs);
+
 }  // namespace jxg

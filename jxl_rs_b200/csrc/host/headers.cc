@@ -181,10 +181,19 @@ void read_extensions(BitReader& br) {  // encodings.rs:377-407
 }
 
 std::vector<uint8_t> extract_codestream(const uint8_t* data, size_t size) {
-  if (size >= 2 && data[0] == 0xff && data[1] == 0x0a) return std::vector<uint8_t>(data, data + size);
+  std::vector<uint8_t> out;
+  extract_codestream(data, size, out);
+  return out;
+}
+
+void extract_codestream(const uint8_t* data, size_t size, std::vector<uint8_t>& out) {
+  out.clear();
+  if (size >= 2 && data[0] == 0xff && data[1] == 0x0a) {
+    out.assign(data, data + size);
+    return;
+  }
   static const uint8_t kSig[12] = {0, 0, 0, 0xc, 'J', 'X', 'L', ' ', 0xd, 0xa, 0x87, 0xa};
   if (size < 12 || memcmp(data, kSig, 12) != 0) fail("not a JPEG XL file");
-  std::vector<uint8_t> out;
   size_t pos = 0;
   while (pos + 8 <= size) {
     uint64_t box_size = (uint64_t(data[pos]) << 24) | (uint64_t(data[pos + 1]) << 16) | (uint64_t(data[pos + 2]) << 8) | data[pos + 3];
@@ -207,7 +216,6 @@ std::vector<uint8_t> extract_codestream(const uint8_t* data, size_t size) {
     pos = end;
   }
   if (out.empty()) fail("no codestream box");
-  return out;
 }
 
 FileHeader read_file_header(BitReader& br) {

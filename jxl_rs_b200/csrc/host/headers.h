@@ -157,6 +157,8 @@ struct Toc {
 // codestream (concatenated jxlc / jxlp payloads), or a copy of the input when
 // it already starts with FF 0A.
 std::vector<uint8_t> extract_codestream(const uint8_t* data, size_t size);
+// Same, into a caller-owned vector (its capacity is reused).
+void extract_codestream(const uint8_t* data, size_t size, std::vector<uint8_t>& out);
 
 // Reads signature + SizeHeader + ImageMetadata + CustomTransformData (+ skips
 // an ICC stream if present); leaves `br` positioned before the first frame

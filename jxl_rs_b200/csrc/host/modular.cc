@@ -11,6 +11,42 @@
 namespace jxg {
 
 namespace {
+struct ChannelBufferPool {
+  static constexpr size_t kMaxBuffers = 16, kMinSamples = 4096, kMaxSamples = size_t(4) << 20;
+  std::vector<std::vector<int32_t>> free_list;
+};
+thread_local ChannelBufferPool tl_channel_pool;
+}  // namespace
+
+std::vector<int32_t> take_channel_buffer(size_t n) {
+  auto& fl = tl_channel_pool.free_list;
+  if (n >= ChannelBufferPool::kMinSamples && !fl.empty()) {
+    // best fit among the (few) pooled buffers: the smallest capacity that holds n, else the largest
+    size_t best = 0;
+    for (size_t i = 1; i < fl.size(); i++) {
+      const size_t ci = fl[i].capacity(), cb = fl[best].capacity();
+      if ((ci >= n && (cb < n || ci < cb)) || (ci < n && cb < n && ci > cb)) best = i;
+    }
+    std::vector<int32_t> v = std::move(fl[best]);
+    fl.erase(fl.begin() + best);
+    v.assign(n, 0);
+    return v;
+  }
+  return std::vector<int32_t>(n, 0);
+}
+
+void give_channel_buffer(std::vector<int32_t>&& buf) {
+  const size_t cap = buf.capacity();
+  auto& fl = tl_channel_pool.free_list;
+  if (cap >= ChannelBufferPool::kMinSamples && cap <= ChannelBufferPool::kMaxSamples &&
+      fl.size() < ChannelBufferPool::kMaxBuffers) {
+    fl.push_back(std::move(buf));
+  } else {
+    std::vector<int32_t>().swap(buf);
+  }
+}
+
+namespace {
 
 struct U32D {
   uint32_t bits, off;

@@ -15,13 +15,33 @@
 
 namespace jxg {
 
+// Sample buffers of destroyed channels are kept in a small per-thread pool and handed to new channels: the LF /
+// HF-metadata streams of every frame otherwise allocate and free ~2 MB of i32 planes (mmap + page faults + munmap).
+std::vector<int32_t> take_channel_buffer(size_t n);  // n zero samples
+void give_channel_buffer(std::vector<int32_t>&& buf);
+
 struct ModularChannel {
   uint32_t w = 0, h = 0;
   int32_t hshift = 0, vshift = 0;  // < 0: meta channel
   std::vector<int32_t> data;
   ModularChannel() = default;
   ModularChannel(uint32_t w_, uint32_t h_, int32_t hs = 0, int32_t vs = 0)
-      : w(w_), h(h_), hshift(hs), vshift(vs), data(size_t(w_) * h_, 0) {}
+      : w(w_), h(h_), hshift(hs), vshift(vs), data(take_channel_buffer(size_t(w_) * h_)) {}
+  ModularChannel(const ModularChannel&) = default;
+  ModularChannel(ModularChannel&&) = default;
+  ModularChannel& operator=(const ModularChannel&) = default;
+  ModularChannel& operator=(ModularChannel&& o) {
+    if (this != &o) {
+      give_channel_buffer(std::move(data));
+      w = o.w;
+      h = o.h;
+      hshift = o.hshift;
+      vshift = o.vshift;
+      data = std::move(o.data);
+    }
+    return *this;
+  }
+  ~ModularChannel() { give_channel_buffer(std::move(data)); }
   int32_t* row(uint32_t y) { return data.data() + size_t(y) * w; }
   const int32_t* row(uint32_t y) const { return data.data() + size_t(y) * w; }
 };
