@@ -167,15 +167,11 @@ class BitReader {
   size_t total_ = 0;
 };
 
-inline uint32_t ceil_log2(uint64_t x) {  // util CeilLog2: smallest n with 2^n >= x
-  uint32_t n = 0;
-  while ((uint64_t(1) << n) < x) n++;
-  return n;
+inline uint32_t floor_log2(uint64_t x) {  // 0 for x <= 1
+  return x > 1 ? 63u - uint32_t(__builtin_clzll(x)) : 0u;
 }
-inline uint32_t floor_log2(uint64_t x) {
-  uint32_t n = 0;
-  while (x >>= 1) n++;
-  return n;
+inline uint32_t ceil_log2(uint64_t x) {  // util CeilLog2: smallest n with 2^n >= x
+  return x > 1 ? floor_log2(x - 1) + 1 : 0u;
 }
 // entropy_coding/decode.rs:31
 inline int32_t unpack_signed(uint32_t u) { return int32_t((u >> 1) ^ (((~u) & 1) - 1)); }

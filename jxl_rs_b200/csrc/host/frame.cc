@@ -255,27 +255,32 @@ void decode_hf_global(FrameState& fs, BitReader& br) {
     }
     if (used_orders) {  // coeff_order.rs:122-152
       ps.custom_orders = true;
-      std::vector<std::vector<uint32_t>> orders(3 * kNumOrders);
-      for (int o = 0; o < 3 * kNumOrders; o++) orders[o] = natural_coeff_order(o / 3);
+      // all 39 orders concatenated (the layout the device consumes), natural ones copied from the process-wide
+      // cache, the coded ones composed with their permutation in place
+      size_t total = 0;
+      for (int o = 0; o < 3 * kNumOrders; o++) {
+        ps.coeff_order_offset[o] = uint32_t(total);
+        total += natural_coeff_order_cached(o / 3).size();
+      }
+      ps.coeff_order.resize(total);
+      for (int o = 0; o < 3 * kNumOrders; o++) {
+        const std::vector<uint32_t>& nat = natural_coeff_order_cached(o / 3);
+        memcpy(&ps.coeff_order[ps.coeff_order_offset[o]], nat.data(), nat.size() * sizeof(uint32_t));
+      }
       EntropyCode code = EntropyCode::decode(8, br, true);
       SymbolReader reader(code, br, 0);
       for (int ord = 0; ord < kNumOrders; ord++) {
         if (!(used_orders & (1u << ord))) continue;
         int t = kOrderTransform[ord];
         uint32_t num_blocks = uint32_t(kCoveredBlocksX[t]) * kCoveredBlocksY[t];
+        const std::vector<uint32_t>& nat = natural_coeff_order_cached(ord);
         for (int c = 0; c < 3; c++) {
           std::vector<uint32_t> perm = decode_permutation(num_blocks * 64, num_blocks, code, br, reader);
-          std::vector<uint32_t>& o = orders[3 * ord + c];
-          std::vector<uint32_t> tmp(o.size());
-          for (size_t i = 0; i < o.size(); i++) tmp[i] = o[perm[i]];  // Permutation::compose
-          o = std::move(tmp);
+          uint32_t* o = &ps.coeff_order[ps.coeff_order_offset[3 * ord + c]];
+          for (size_t i = 0; i < nat.size(); i++) o[i] = nat[perm[i]];  // Permutation::compose
         }
       }
       reader.check_final_state(br);
-      for (int o = 0; o < 3 * kNumOrders; o++) {
-        ps.coeff_order_offset[o] = uint32_t(ps.coeff_order.size());
-        ps.coeff_order.insert(ps.coeff_order.end(), orders[o].begin(), orders[o].end());
-      }
     }
     size_t num_contexts = size_t(fs.num_histograms) * fs.num_ac_contexts();
     ps.code = EntropyCode::decode(num_contexts, br, true);

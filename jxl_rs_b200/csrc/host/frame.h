@@ -29,6 +29,7 @@ int quant_table_for_transform(int transform);           // QuantTable::for_strat
 extern const uint8_t kCoveredBlocksX[27], kCoveredBlocksY[27], kBlockShapeId[27];
 // coeff_order.rs:66
 std::vector<uint32_t> natural_coeff_order(int order_idx);
+const std::vector<uint32_t>& natural_coeff_order_cached(int order_idx);  // same, computed once per process
 extern const uint8_t kOrderTransform[kNumOrders];  // TRANSFORM_TYPE_LUT
 
 struct PassState {

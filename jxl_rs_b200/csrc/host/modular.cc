@@ -446,11 +446,12 @@ static void decode_static_leaf(ModularChannel& ch, const TreeNode* nd, uint32_t 
 }
 
 // No weighted predictor, no reference-channel properties: evaluate only the properties the walk visits.
-template <class R>
+template <bool kWp, class R>
 static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, const TreeNode* nodes,
-                              const uint8_t* cmap, R& io) {
+                              const TreeNode* root, const uint8_t* cmap, const WeightedHeader& wph, R& io) {
   R rd = io;
   const size_t w = ch.w, h = ch.h;
+  WpState wp(wph, kWp ? w : 0);
   for (size_t y = 0; y < h; y++) {
     int32_t* row = ch.row(uint32_t(y));
     const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
@@ -459,7 +460,10 @@ static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, c
     for (size_t x = 0; x < w; x++) {
       const Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
       const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
-      const TreeNode* nd = nodes;
+      int64_t wp_pred = 0;
+      int32_t wp_prop = 0;
+      if (kWp) wp.predict(x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
+      const TreeNode* nd = root;
       while (nd->property >= 0) {
         int32_t v;
         switch (nd->property) {
@@ -478,13 +482,16 @@ static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, c
           case 12: v = wsub(n.top, n.topright); break;
           case 13: v = wsub(n.top, n.toptop); break;
           case 14: v = wsub(n.left, n.leftleft); break;
-          default: v = 0; break;  // property 15 without the weighted predictor is always 0
+          default: v = wp_prop; break;  // property 15; 0 without the weighted predictor
         }
         nd = nodes + (v > nd->val ? nd->left : nd->right);
       }
       prev_p9 = p9;
-      const int64_t guess = predict_one(nd->left, n, 0) + int64_t(nd->val);
-      row[x] = int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
+      const int64_t guess = predict_one(nd->left, n, wp_pred) + int64_t(nd->val);
+      const int32_t val =
+          int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
+      if (kWp) wp.update(val, x, y);
+      row[x] = val;
     }
   }
   io = rd;
@@ -522,18 +529,34 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
   const bool use_wp = tree.uses_wp;
   const TreeNode* nodes = tree.nodes.data();
   // ---- specialised walks (same semantics as the generic loop below; the reference keeps a family of these in
-  // decode/specialized_trees.rs). Which properties do the decision nodes look at?
+  // decode/specialized_trees.rs).
+  // Static prefix: nodes that split on the channel index / stream id have one outcome for the whole channel
+  // (libjxl's global trees start with such a chain), so the walk can start below them.
+  const TreeNode* root = nodes;
+  while (root->property == 0 || root->property == 1)
+    root = nodes + (props[root->property] > root->val ? root->left : root->right);
+  // Which properties and predictors does the subtree under `root` use?
   uint32_t used_mask = 0;
-  bool wide_props = false;
-  for (const TreeNode& nd : tree.nodes)
-    if (nd.property >= 0) {
-      if (nd.property < 32) used_mask |= 1u << nd.property;
-      if (nd.property >= 16) wide_props = true;
+  bool wide_props = false, sub_wp = false;
+  {
+    std::vector<const TreeNode*> stack{root};
+    while (!stack.empty()) {
+      const TreeNode* nd = stack.back();
+      stack.pop_back();
+      if (nd->property < 0) {
+        if (nd->left == kWeighted) sub_wp = true;
+        continue;
+      }
+      if (nd->property < 16) used_mask |= 1u << nd->property;
+      else wide_props = true;
+      if (nd->property == 15) sub_wp = true;
+      stack.push_back(nodes + nd->left);
+      stack.push_back(nodes + nd->right);
     }
+  }
   const bool specialise = !g_force_generic_walk.load(std::memory_order_relaxed);
-  if (specialise && !use_wp && !wide_props && (used_mask & ~3u) == 0) {
-    const TreeNode* nd = nodes;
-    while (nd->property >= 0) nd = nodes + (props[nd->property] > nd->val ? nd->left : nd->right);
+  if (specialise && root->property < 0 && !sub_wp) {
+    const TreeNode* nd = root;
     const uint32_t cluster = tree.code.context_map[nd->ctx];  // one leaf -> one cluster for the whole channel
     if (reader.can_localise() && !reader.uses_prefix() && w * h >= 8192) {
       // big channel, one ANS cluster: direct table (its 4096-entry build is < 1 % of the channel)
@@ -551,9 +574,14 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
     br.check();
     return;
   }
-  if (specialise && !use_wp && !wide_props) {
+  if (specialise && !wide_props) {
+    // Properties 0..15 evaluated on demand; the weighted predictor runs only if the subtree uses it (as property
+    // 15 or as a leaf predictor).
     const uint8_t* cmap = tree.code.context_map.data();
-    with_reader(reader, br, [&](auto& rd) { decode_lazy_props(ch, ci, stream_id, nodes, cmap, rd); });
+    with_reader(reader, br, [&](auto& rd) {
+      if (sub_wp) decode_lazy_props<true>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
+      else decode_lazy_props<false>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
+    });
     br.check();
     return;
   }

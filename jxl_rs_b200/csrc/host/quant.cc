@@ -28,6 +28,14 @@ int quant_table_for_transform(int t) {  // quant_weights.rs:311-336
   return lut[t];
 }
 
+const std::vector<uint32_t>& natural_coeff_order_cached(int order_idx) {
+  // computed once per process (the 256x256 order alone is 65 536 entries; frames with custom orders start from all 39)
+  static std::vector<uint32_t> cache[kNumOrders];
+  static std::once_flag once[kNumOrders];
+  std::call_once(once[order_idx], [order_idx] { cache[order_idx] = natural_coeff_order(order_idx); });
+  return cache[order_idx];
+}
+
 std::vector<uint32_t> natural_coeff_order(int order_idx) {  // coeff_order.rs:66-120
   int t = kOrderTransform[order_idx];
   size_t cx = kCoveredBlocksX[t], cy = kCoveredBlocksY[t];
