@@ -94,6 +94,19 @@ inline Neigh get_neigh(const int32_t* row, const int32_t* top_row, const int32_t
   return n;
 }
 
+// get_neigh for 2 <= x < w - 2, y >= 2: every neighbour exists
+inline Neigh get_neigh_interior(const int32_t* row, const int32_t* top_row, const int32_t* toptop_row, size_t x) {
+  Neigh n;
+  n.left = row[x - 1];
+  n.top = top_row[x];
+  n.topleft = top_row[x - 1];
+  n.topright = top_row[x + 1];
+  n.leftleft = row[x - 2];
+  n.toptop = toptop_row[x];
+  n.toprightright = top_row[x + 2];
+  return n;
+}
+
 // predict.rs:148-194
 inline int64_t predict_one(uint32_t p, const Neigh& n, int64_t wp_pred) {
   int64_t left = n.left, top = n.top, topleft = n.topleft, topright = n.topright;
@@ -120,6 +133,9 @@ inline int64_t predict_one(uint32_t p, const Neigh& n, int64_t wp_pred) {
   }
   return 0;
 }
+
+// c ? a : b without a branch
+inline int64_t bsel(bool c, int64_t a, int64_t b) { return b ^ ((a ^ b) & (int64_t(0) - int64_t(c))); }
 
 const uint32_t kDivLookup[64] = {
     16777216, 8388608, 5592405, 4194304, 3355443, 2796202, 2396745, 2097152, 1864135, 1677721, 1525201,
@@ -163,10 +179,12 @@ void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t top
   int64_t te_nw = error[prev_row + 1 + pos_nw];
   int64_t sum_wn = te_n + te_w;
   int64_t te_ne = error[prev_row + 1 + pos_ne];
+  // the property is the neighbouring error of largest magnitude; which one that is depends on the data, so the
+  // selections are written as masks (mispredicted branches otherwise)
   int64_t p = te_w;
-  if (std::llabs(te_n) > std::llabs(p)) p = te_n;
-  if (std::llabs(te_nw) > std::llabs(p)) p = te_nw;
-  if (std::llabs(te_ne) > std::llabs(p)) p = te_ne;
+  p = bsel(std::llabs(te_n) > std::llabs(p), te_n, p);
+  p = bsel(std::llabs(te_nw) > std::llabs(p), te_nw, p);
+  p = bsel(std::llabs(te_ne) > std::llabs(p), te_ne, p);
   int64_t n = int64_t(top) << 3, w = int64_t(left) << 3, ne = int64_t(topright) << 3, nw = int64_t(topleft) << 3,
           nn = int64_t(toptop) << 3;
   int64_t p0 = w + ne - n;
@@ -180,9 +198,12 @@ void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t top
   int64_t weight_sum = w0 + w1 + w2 + w3;
   int64_t sum = (weight_sum >> 1) - 1 + w0 * p0 + w1 * p1 + w2 * p2 + w3 * p3;
   int64_t pr = (sum * int64_t(kDivLookup[weight_sum - 1])) >> 24;
-  if (((te_n ^ te_w) | (te_n ^ te_nw)) <= 0) {
-    int64_t mx = std::max(w, std::max(ne, n)), mn = std::min(w, std::min(ne, n));
-    pr = std::max(mn, std::min(mx, pr));
+  {
+    const int64_t mx = bsel(w > ne, w, ne), mx3 = bsel(mx > n, mx, n);
+    const int64_t mn = bsel(w < ne, w, ne), mn3 = bsel(mn < n, mn, n);
+    const int64_t lo = bsel(mx3 < pr, mx3, pr);          // min(mx, pr)
+    const int64_t clamped = bsel(mn3 > lo, mn3, lo);     // max(mn, min(mx, pr))
+    pr = bsel(((te_n ^ te_w) | (te_n ^ te_nw)) <= 0, clamped, pr);
   }
   prediction[0] = p0;
   prediction[1] = p1;
@@ -497,6 +518,85 @@ static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, c
   io = rd;
 }
 
+// Subtrees whose decision nodes all test the same property p (libjxl's LF trees: only the weighted-predictor
+// property 15) become a table from clamp(value, -1024, 1023) to the leaf, like make_lut in
+// decode/specialized_trees.rs:197-249: one load instead of a chain of data-dependent branches. Returns false if a
+// split value lies outside the range the clamp preserves (or outside the range of its own subtree).
+constexpr int32_t kLutMin = -1024, kLutMax = 1023;
+static bool make_prop_lut(const TreeNode* nodes, const TreeNode* root, std::vector<uint32_t>& lut) {
+  struct Item {
+    int32_t lo, hi;  // values lo .. hi - 1 reach `node`
+    const TreeNode* node;
+  };
+  lut.assign(size_t(kLutMax - kLutMin + 1), 0);
+  std::vector<Item> stack{Item{kLutMin, kLutMax + 1, root}};
+  while (!stack.empty()) {
+    const Item it = stack.back();
+    stack.pop_back();
+    if (it.node->property >= 0) {
+      const int64_t first_left = int64_t(it.node->val) + 1;  // v > val goes left
+      if (first_left >= it.hi || first_left <= it.lo) return false;
+      stack.push_back(Item{int32_t(first_left), it.hi, nodes + it.node->left});
+      stack.push_back(Item{it.lo, int32_t(first_left), nodes + it.node->right});
+    } else {
+      for (int32_t v = it.lo; v < it.hi; v++) lut[size_t(v - kLutMin)] = uint32_t(it.node - nodes);
+    }
+  }
+  return true;
+}
+
+template <bool kWp, class R>
+static void decode_prop_lut(ModularChannel& ch, const TreeNode* nodes, int prop, const uint32_t* lut,
+                            const uint8_t* cmap, const WeightedHeader& wph, R& io) {
+  R rd = io;
+  const size_t w = ch.w, h = ch.h;
+  WpState wp(wph, kWp ? w : 0);
+  for (size_t y = 0; y < h; y++) {
+    int32_t* row = ch.row(uint32_t(y));
+    const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
+    const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
+    int32_t prev_p9 = 0;
+    auto pixel = [&](size_t x, const Neigh& n) {
+      const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
+      int64_t wp_pred = 0;
+      int32_t wp_prop = 0;
+      if (kWp) wp.predict(x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
+      int32_t v;
+      switch (prop) {  // loop invariant
+        case 2: v = int32_t(y); break;
+        case 3: v = int32_t(x); break;
+        case 4: v = wabs(n.top); break;
+        case 5: v = wabs(n.left); break;
+        case 6: v = n.top; break;
+        case 7: v = n.left; break;
+        case 8: v = wsub(n.left, prev_p9); break;
+        case 9: v = p9; break;
+        case 10: v = wsub(n.left, n.topleft); break;
+        case 11: v = wsub(n.topleft, n.top); break;
+        case 12: v = wsub(n.top, n.topright); break;
+        case 13: v = wsub(n.top, n.toptop); break;
+        case 14: v = wsub(n.left, n.leftleft); break;
+        default: v = wp_prop; break;
+      }
+      prev_p9 = p9;
+      const int32_t clamped = v < kLutMin ? kLutMin : (v > kLutMax ? kLutMax : v);
+      const TreeNode* nd = nodes + lut[size_t(clamped - kLutMin)];
+      const int64_t guess = (kWp && nd->left == kWeighted ? wp_pred : predict_one(nd->left, n, wp_pred)) + int64_t(nd->val);
+      const int32_t val =
+          int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
+      if (kWp) wp.update(val, x, y);
+      row[x] = val;
+    };
+    size_t x = 0;
+    if (y >= 2 && w > 4) {
+      for (; x < 2; x++) pixel(x, get_neigh(row, top_row, toptop_row, x, y, w));
+      for (; x + 2 < w; x++) pixel(x, get_neigh_interior(row, top_row, toptop_row, x));
+    }
+    for (; x < w; x++) pixel(x, get_neigh(row, top_row, toptop_row, x, y, w));
+  }
+  io = rd;
+}
+
 // Runs `f(reader)` with the register-resident reader when the code allows it (no LZ77), else with the member one.
 template <class F>
 static void with_reader(SymbolReader& reader, BitReader& br, F&& f) {
@@ -578,9 +678,23 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
     // Properties 0..15 evaluated on demand; the weighted predictor runs only if the subtree uses it (as property
     // 15 or as a leaf predictor).
     const uint8_t* cmap = tree.code.context_map.data();
+    // one dynamic property only -> table walk
+    int single_prop = -1;
+    std::vector<uint32_t> lut;
+    const uint32_t dyn_mask = used_mask & ~3u;
+    if (w * h >= 1024 && dyn_mask != 0 && (dyn_mask & (dyn_mask - 1)) == 0 && (used_mask & 3u) == 0) {
+      single_prop = __builtin_ctz(dyn_mask);
+      if (!make_prop_lut(nodes, root, lut)) single_prop = -1;
+    }
     with_reader(reader, br, [&](auto& rd) {
-      if (sub_wp) decode_lazy_props<true>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
-      else decode_lazy_props<false>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
+      if (single_prop >= 0) {
+        if (sub_wp) decode_prop_lut<true>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
+        else decode_prop_lut<false>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
+      } else if (sub_wp) {
+        decode_lazy_props<true>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
+      } else {
+        decode_lazy_props<false>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
+      }
     });
     br.check();
     return;
