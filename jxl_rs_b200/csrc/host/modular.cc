@@ -185,8 +185,9 @@ void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t top
   p = bsel(std::llabs(te_n) > std::llabs(p), te_n, p);
   p = bsel(std::llabs(te_nw) > std::llabs(p), te_nw, p);
   p = bsel(std::llabs(te_ne) > std::llabs(p), te_ne, p);
-  int64_t n = int64_t(top) << 3, w = int64_t(left) << 3, ne = int64_t(topright) << 3, nw = int64_t(topleft) << 3,
-          nn = int64_t(toptop) << 3;
+  // add_bits (predict.rs): value * 8 (a multiplication: << on a negative value is undefined before C++20)
+  int64_t n = int64_t(top) * 8, w = int64_t(left) * 8, ne = int64_t(topright) * 8, nw = int64_t(topleft) * 8,
+          nn = int64_t(toptop) * 8;
   int64_t p0 = w + ne - n;
   int64_t p1 = n - (((sum_wn + te_ne) * int64_t(hdr.p1c)) >> 5);
   int64_t p2 = w - (((sum_wn + te_nw) * int64_t(hdr.p2c)) >> 5);
@@ -216,7 +217,7 @@ void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t top
 
 void WpState::update(int32_t val, size_t x, size_t y) {
   size_t cur_row = (y & 1) ? 0 : xsize + 1, prev_row = (y & 1) ? xsize + 1 : 0;
-  int64_t v = int64_t(val) << 3;
+  int64_t v = int64_t(val) * 8;
   error[cur_row + x + 1] = int32_t(pred - v);
   uint32_t* cur = &pred_errors[(cur_row + x) * 4];
   uint32_t* prev = &pred_errors[(prev_row + x + 1) * 4];
