@@ -224,7 +224,8 @@ def main():
     # timed steps alternate between them, so that consecutive steps overlap on the device (entropy decode of
     # one batch is latency-bound and leaves issue slots to the transforms/filters of the other).
     with ThreadPoolExecutor(max_workers=min(n, rank_cores())) as ex:
-        frames = list(ex.map(j.ParsedFrame, files))
+        per_file = max(1, rank_cores() // max(1, len(files)))  # one large image: LF groups in parallel
+        frames = list(ex.map(lambda f: j.ParsedFrame(f, per_file), files))
     depth = max(1, args.inflight)
     ctxs = [ctx] + [j.JxgContext(local_rank) for _ in range(depth - 1)]
     dev_out = [[torch.empty((fr.height, fr.width, 3), dtype=torch.uint8, device=f"cuda:{local_rank}") for fr in frames]

@@ -193,6 +193,10 @@ typedef struct JxgImageInfo {
 } JxgImageInfo;
 
 int jxg_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info);
+/* Same, decoding the frame's LF groups (independent TOC sections, frame/decode.rs:429 decode_lf_group) on `threads`
+ * host threads, the fan-out jxl-rs does over its parallel runner (api/inner/codestream_parser/frame_info.rs:505-520):
+ * the latency path for one large image. The parsed state does not depend on `threads`. */
+int jxg_parse_file_mt(const uint8_t* data, size_t size, int threads, void** parsed, JxgImageInfo* info);
 void jxg_parsed_free(void* parsed);
 /* Adds a parsed frame to a batch with the given output. */
 int jxg_batch_add_parsed(void* batch, void* parsed, uint32_t output_format, void* out, size_t out_row_stride,

@@ -633,9 +633,13 @@ int jxg_batch_read_xyb(void* bp, uint32_t f, int stage, float* out, size_t out_l
 // ---------------- host front-end convenience ----------------
 
 int jxg_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info) {
+  return jxg_parse_file_mt(data, size, 1, parsed, info);
+}
+
+int jxg_parse_file_mt(const uint8_t* data, size_t size, int threads, void** parsed, JxgImageInfo* info) {
   if (!data || !parsed) return JXG_ERR_ARGUMENT;
   try {
-    std::unique_ptr<jxg::FrameState> fs = jxg::parse_vardct_file(data, size);
+    std::unique_ptr<jxg::FrameState> fs = jxg::parse_vardct_file(data, size, threads);
     if (info) {
       info->width = fs->header.xsize();
       info->height = fs->header.ysize();

@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "quant.h"
 
@@ -420,7 +422,7 @@ void recycle_frame_state(FrameState* fs) {
   }  // else: b is freed on return
 }
 
-std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) {
+std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, int threads) {
   auto fsp = std::make_unique<FrameState>();
   FrameState& fs = *fsp;
   take_buffers(fs);
@@ -447,10 +449,12 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) 
   fs.xb = h.xsize_blocks();
   fs.yb = h.ysize_blocks();
   size_t nb = size_t(fs.xb) * fs.yb;
-  for (auto& p : fs.lf) p.assign(nb, 0.0f);
+  // LF samples, raw quant and EPF sharpness of every block are written by its LF group (a stream that leaves a block
+  // uncovered is rejected below), so pooled buffers are only resized; the transform map is the coverage marker.
+  for (auto& p : fs.lf) p.resize(nb);
   fs.transform_map.assign(nb, 27);
-  fs.raw_quant_map.assign(nb, 0);
-  fs.epf_map.assign(nb, 0);
+  fs.raw_quant_map.resize(nb);
+  fs.epf_map.resize(nb);
   fs.quant_lf_map.assign(nb, 0);
   size_t ncm = size_t((fs.xb + 7) / 8) * ((fs.yb + 7) / 8);
   fs.ytox_map.assign(ncm, 0);
@@ -475,9 +479,47 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size) 
       BitReader sbr(base + fs.toc.offsets[0], fs.toc.lengths[0]);
       decode_lf_global(fs, sbr);
     }
-    for (uint32_t g = 0; g < h.num_lf_groups(); g++) {
-      BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
-      decode_lf_group(fs, g, sbr);
+    const uint32_t nlf = h.num_lf_groups();
+    const uint32_t nthreads = std::min<uint32_t>(nlf, uint32_t(std::max(1, threads)));
+    if (nthreads <= 1) {
+      for (uint32_t g = 0; g < nlf; g++) {
+        BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
+        decode_lf_group(fs, g, sbr);
+      }
+    } else {
+      // LF groups are independent sections writing disjoint rectangles of the planes; the error of the lowest
+      // failing group is reported, like the serial loop would.
+      std::atomic<uint32_t> next{0};
+      std::mutex err_mutex;
+      uint32_t err_group = UINT32_MAX;
+      std::unique_ptr<Error> err;
+      auto work = [&] {
+        for (;;) {
+          const uint32_t g = next.fetch_add(1);
+          if (g >= nlf) return;
+          try {
+            BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
+            decode_lf_group(fs, g, sbr);
+          } catch (Error& e) {
+            std::lock_guard<std::mutex> lock(err_mutex);
+            if (g < err_group) {
+              err_group = g;
+              err = std::make_unique<Error>(e);
+            }
+          } catch (std::exception& e) {
+            std::lock_guard<std::mutex> lock(err_mutex);
+            if (g < err_group) {
+              err_group = g;
+              err = std::make_unique<Error>(kErrBitstream, e.what());
+            }
+          }
+        }
+      };
+      std::vector<std::thread> pool;
+      for (uint32_t t = 1; t < nthreads; t++) pool.emplace_back(work);
+      work();
+      for (auto& t : pool) t.join();
+      if (err) throw *err;
     }
     {
       size_t s = 1 + h.num_lf_groups();

@@ -86,7 +86,11 @@ void adaptive_lf_smoothing(FrameState& fs);
 
 // Parses a complete file up to (not including) the HF groups of its first
 // displayed VarDCT frame. Throws jxg::Error.
-std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size);
+// `threads` > 1 decodes the LF groups of the frame (LF image + HF metadata, independent TOC sections,
+// frame/decode.rs:429) on that many host threads: the latency path for one large image (a 16384x16384 frame has 64
+// LF groups and ~45 M Modular symbols); batches of many frames keep 1 and parallelise over frames instead. The
+// parsed state does not depend on `threads`.
+std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, int threads = 1);
 
 // Destroys a FrameState but keeps its large buffers (codestream copy, LF planes, per-block maps; ~4 MB for a 4K
 // frame) in a bounded process-wide pool that parse_vardct_file draws from: a steady-state decode loop then does no

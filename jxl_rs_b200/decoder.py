@@ -33,11 +33,14 @@ class ParsedFrame:
     groups, HfGlobal): what a Rust host has in `Frame` when it reaches
     decode_and_render_hf_groups (frame/render.rs:143)."""
 
-    def __init__(self, data: bytes):
+    def __init__(self, data: bytes, threads: int = 1):
+        """threads > 1: the frame's LF groups are decoded on that many host threads (one large image); batches of
+        many frames keep 1 and parse frames in parallel instead."""
         self._lib = abi.load_library()
         self._h = C.c_void_p()
         self.info = abi.JxgImageInfo()
-        abi.check(self._lib, self._lib.jxg_parse_file(data, len(data), C.byref(self._h), C.byref(self.info)))
+        abi.check(self._lib, self._lib.jxg_parse_file_mt(data, len(data), int(threads), C.byref(self._h),
+                                                          C.byref(self.info)))
 
     @property
     def width(self):
@@ -164,7 +167,14 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
     (H x W x C). Host results land in pinned memory (JxlOutputBuffer analogue)."""
     import torch
     fmt = pixel_format.abi_format()
-    frames = [ParsedFrame(f) for f in files]
+    cpus = effective_cpus()
+    per_file = max(1, cpus // max(1, len(files)))
+    if len(files) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(cpus, len(files))) as ex:
+            frames = list(ex.map(lambda f: ParsedFrame(f, per_file), files))
+    else:
+        frames = [ParsedFrame(f, per_file) for f in files]
     batch = Batch(ctx, len(frames))
     outs = []
     for fr in frames:
@@ -223,7 +233,8 @@ class PipelinedDecoder:
         self.ctxs = [JxgContext(device) for _ in range(depth)]
         self.depth = depth
         self.staging_threads = staging_threads
-        self.pool = ThreadPoolExecutor(max_workers=workers or min(64, effective_cpus()))
+        self.workers = workers or min(64, effective_cpus())
+        self.pool = ThreadPoolExecutor(max_workers=self.workers)
         self.inflight = deque()
         self.k = 0
         self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0, "kernel_launches": 0}
@@ -293,7 +304,9 @@ class PipelinedDecoder:
         """files: list of .jxl byte strings; outs: list of (data_ptr, row_stride). Returns once the batch is
         queued; its outputs are complete after drain() (or once `depth` later batches have been launched)."""
         self._ahead.acquire()
-        futs = [self.pool.submit(ParsedFrame, f) for f in files]
+        # fewer files than workers (one large image): the spare workers decode LF groups inside each file
+        per_file = max(1, self.workers // max(1, len(files)))
+        futs = [self.pool.submit(ParsedFrame, f, per_file) for f in files]
         self._jobs.put((futs, list(outs), fmt, out_is_device))
 
     def drain(self):

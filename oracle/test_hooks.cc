@@ -153,4 +153,30 @@ void jxo_t_adaptive_lf_smoothing(uint32_t xs, uint32_t ys, uint32_t global_scale
   adaptive_lf_smoothing(fs);
   for (int c = 0; c < 3; c++) std::copy(fs.lf[c].begin(), fs.lf[c].end(), planes + size_t(c) * xs * ys);
 }
+
+// FNV-1a digest over everything the front-end hands to the hot path (planes, maps, section table), for tests that
+// compare parses (e.g. serial vs multi-threaded LF groups). Returns 0 on a parse error.
+uint64_t jxo_t_parse_digest(const uint8_t* data, size_t size, int threads) {
+  try {
+    auto fs = parse_vardct_file(data, size, threads);
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t n) {
+      const uint8_t* b = static_cast<const uint8_t*>(p);
+      for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    for (int c = 0; c < 3; c++) mix(fs->lf[c].data(), fs->lf[c].size() * 4);
+    mix(fs->transform_map.data(), fs->transform_map.size());
+    mix(fs->raw_quant_map.data(), fs->raw_quant_map.size() * 4);
+    mix(fs->epf_map.data(), fs->epf_map.size());
+    mix(fs->quant_lf_map.data(), fs->quant_lf_map.size());
+    mix(fs->ytox_map.data(), fs->ytox_map.size());
+    mix(fs->ytob_map.data(), fs->ytob_map.size());
+    mix(fs->hf_off.data(), fs->hf_off.size() * 8);
+    mix(fs->hf_len.data(), fs->hf_len.size() * 4);
+    recycle_frame_state(fs.release());
+    return h ? h : 1;
+  } catch (Error&) {
+    return 0;
+  }
+}
 }

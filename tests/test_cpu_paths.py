@@ -174,3 +174,26 @@ def test_specialised_modular_walks_match_the_generic_loop():
         finally:
             lib.jxo_t_force_generic_walk(0)
         assert np.array_equal(a, b) and np.array_equal(a, synth.modular_source(700, 530, 11))
+
+
+def test_multithreaded_lf_groups_give_the_same_parse():
+    """jxg_parse_file_mt: the LF groups of one frame decoded on several threads (frame_info.rs:505-520) must hand the
+    hot path exactly the state the serial parse does — also when buffers come back from the pool with stale contents
+    (the parses below recycle each other's planes), and a corrupt LF group must still be reported."""
+    import synth
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    lib.jxo_t_parse_digest.restype = C.c_uint64
+    lib.jxo_t_parse_digest.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+    f = synth.encode_synthetic(4200, 2100, 99, 0.7, 2, 1, 1)  # 3 x 2 LF groups
+    g = synth.encode_synthetic(4200, 2100, 100, 0.7, 2, 1, 1)
+    ref_f, ref_g = lib.jxo_t_parse_digest(f, len(f), 1), lib.jxo_t_parse_digest(g, len(g), 1)
+    assert ref_f != 0 and ref_g != 0 and ref_f != ref_g
+    for threads in (2, 3, 8):
+        assert lib.jxo_t_parse_digest(f, len(f), threads) == ref_f
+        assert lib.jxo_t_parse_digest(g, len(g), threads) == ref_g
+    assert lib.jxo_t_parse_digest(f, len(f), 1) == ref_f
+    bad = bytearray(f)
+    bad[len(f) // 40] ^= 0x55  # inside the LF-group sections (they come first and are ~5 % of the file)
+    bad = bytes(bad)
+    assert lib.jxo_t_parse_digest(bad, len(bad), 4) in (0, lib.jxo_t_parse_digest(bad, len(bad), 1))
