@@ -300,9 +300,11 @@ void decode_hf_global(FrameState& fs, BitReader& br) {
 // order as compute_pixel_channel (:20-41): results are bit-identical to the scalar definition.
 #pragma GCC push_options
 #pragma GCC optimize("fp-contract=off")
-void adaptive_lf_smoothing(FrameState& fs) {
-  const size_t xs = fs.xb, ys = fs.yb;
-  if (xs <= 2 || ys <= 2) return;
+// Rows [y_begin, y_end) of the smoothing, in place. `top0[c]` is the original row y_begin - 1 and `bot_last[c]` the
+// original row y_end (both saved by the caller before any band runs, because neighbouring bands overwrite them).
+static void smooth_band(FrameState& fs, size_t y_begin, size_t y_end, const float* const top0[3],
+                        const float* const bot_last[3]) {
+  const size_t xs = fs.xb;
   const float inv_quant_lf = (65536.0f / float(fs.global_scale)) / float(fs.quant_lf);
   const float lf_factors[3] = {inv_quant_lf * fs.lf_quant[0], inv_quant_lf * fs.lf_quant[1],
                                inv_quant_lf * fs.lf_quant[2]};
@@ -317,16 +319,16 @@ void adaptive_lf_smoothing(FrameState& fs) {
   for (int c = 0; c < 3; c++) {
     prev[c] = &saved[size_t(2 * c) * xs];
     cur[c] = &saved[size_t(2 * c + 1) * xs];
-    memcpy(prev[c], &fs.lf[c][0], xs * sizeof(float));
+    memcpy(prev[c], top0[c], xs * sizeof(float));
   }
   const __m256 vside = _mm256_set1_ps(kSide), vcorner = _mm256_set1_ps(kCorner), vcenter = _mm256_set1_ps(kCenter);
   const __m256 vabs = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
-  for (size_t y = 1; y + 1 < ys; y++) {
+  for (size_t y = y_begin; y < y_end; y++) {
     float* outp[3];
     const float* bot[3];
     for (int c = 0; c < 3; c++) {
       outp[c] = &fs.lf[c][y * xs];
-      bot[c] = &fs.lf[c][(y + 1) * xs];
+      bot[c] = y + 1 == y_end ? bot_last[c] : &fs.lf[c][(y + 1) * xs];
       memcpy(cur[c], outp[c], xs * sizeof(float));
     }
     size_t x = 1;
@@ -368,6 +370,35 @@ void adaptive_lf_smoothing(FrameState& fs) {
     }
     for (int c = 0; c < 3; c++) std::swap(prev[c], cur[c]);
   }
+}
+
+void adaptive_lf_smoothing(FrameState& fs, int threads) {
+  const size_t xs = fs.xb, ys = fs.yb;
+  if (xs <= 2 || ys <= 2) return;
+  // rows 1 .. ys-2 in bands of whole rows, one per thread (at least 64 rows each)
+  const size_t rows = ys - 2;
+  const size_t nb = std::max<size_t>(1, std::min<size_t>(size_t(std::max(1, threads)), rows / 64));
+  std::vector<float> edge(nb * 6 * xs);  // per band: original rows (begin - 1) and (end), 3 channels each
+  std::vector<size_t> begin(nb + 1);
+  for (size_t b = 0; b <= nb; b++) begin[b] = 1 + rows * b / nb;
+  for (size_t b = 0; b < nb; b++)
+    for (int c = 0; c < 3; c++) {
+      memcpy(&edge[(b * 6 + c) * xs], &fs.lf[c][(begin[b] - 1) * xs], xs * sizeof(float));
+      memcpy(&edge[(b * 6 + 3 + c) * xs], &fs.lf[c][begin[b + 1] * xs], xs * sizeof(float));
+    }
+  auto run = [&](size_t b) {
+    const float* top0[3];
+    const float* bot_last[3];
+    for (int c = 0; c < 3; c++) {
+      top0[c] = &edge[(b * 6 + c) * xs];
+      bot_last[c] = &edge[(b * 6 + 3 + c) * xs];
+    }
+    smooth_band(fs, begin[b], begin[b + 1], top0, bot_last);
+  };
+  std::vector<std::thread> pool;
+  for (size_t b = 1; b < nb; b++) pool.emplace_back(run, b);
+  run(0);
+  for (auto& t : pool) t.join();
 }
 #pragma GCC pop_options
 
@@ -535,7 +566,7 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
   }
   for (uint8_t t : fs.transform_map)
     if (t == 27) fail("VarDCT transform map has uncovered blocks");
-  if (h.adaptive_lf_smoothing()) adaptive_lf_smoothing(fs);
+  if (h.adaptive_lf_smoothing()) adaptive_lf_smoothing(fs, threads);
   return fsp;
 }
 

@@ -82,7 +82,7 @@ struct FrameState {
 };
 
 // frame/adaptive_lf_smoothing.rs:44 on fs.lf (uses xb, yb, global_scale, quant_lf, lf_quant). Exposed for the tests.
-void adaptive_lf_smoothing(FrameState& fs);
+void adaptive_lf_smoothing(FrameState& fs, int threads = 1);
 
 // Parses a complete file up to (not including) the HF groups of its first
 // displayed VarDCT frame. Throws jxg::Error.

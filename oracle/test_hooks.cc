@@ -140,7 +140,7 @@ void jxo_t_force_generic_walk(int on) { set_force_generic_walk(on != 0); }
 
 // frame/adaptive_lf_smoothing.rs on caller planes (3 x ys x xs f32, in place), for the known-answer test.
 void jxo_t_adaptive_lf_smoothing(uint32_t xs, uint32_t ys, uint32_t global_scale, uint32_t quant_lf,
-                                 const float* lf_quant, float* planes) {
+                                 const float* lf_quant, float* planes, int threads) {
   FrameState fs;
   fs.xb = xs;
   fs.yb = ys;
@@ -150,7 +150,7 @@ void jxo_t_adaptive_lf_smoothing(uint32_t xs, uint32_t ys, uint32_t global_scale
     fs.lf_quant[c] = lf_quant[c];
     fs.lf[c].assign(planes + size_t(c) * xs * ys, planes + size_t(c + 1) * xs * ys);
   }
-  adaptive_lf_smoothing(fs);
+  adaptive_lf_smoothing(fs, threads);
   for (int c = 0; c < 3; c++) std::copy(fs.lf[c].begin(), fs.lf[c].end(), planes + size_t(c) * xs * ys);
 }
 

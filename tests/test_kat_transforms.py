@@ -151,8 +151,10 @@ def test_adaptive_lf_smoothing_matches_the_scalar_definition(oracle, xs, ys):
     factor = np.maximum(f(3.0) - f(4.0) * gap, f(0.0))
     for c in range(3):
         want[c, 1:-1, 1:-1] = (sm[c] - mc[c]) * factor + mc[c]
-    got = lf.copy()
-    oracle.jxo_t_adaptive_lf_smoothing(xs, ys, gs, qlf, lf_quant.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p))
     if xs * ys > 100:
         assert (factor == 0).any() and (factor > 0).any()
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    for threads in (1, 3):  # 3: row bands on separate threads (only the 270-row case is tall enough to split)
+        got = lf.copy()
+        oracle.jxo_t_adaptive_lf_smoothing(xs, ys, gs, qlf, lf_quant.ctypes.data_as(C.c_void_p),
+                                           got.ctypes.data_as(C.c_void_p), threads)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
