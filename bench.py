@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--distance", type=float, default=0.5, help="synthetic quantiser knob (0.5 ~ 1.2 bpp)")
     ap.add_argument("--profile", type=int, default=1, help="transform mix of the synthetic writer")
     ap.add_argument("--epf", type=int, default=2)
+    ap.add_argument("--lf-tree", type=int, default=0, choices=[0, 1],
+                    help="coding of the LF image in the synthetic frames: 0 = one Gradient leaf per channel (default "
+                         "workload), 1 = libjxl-like weighted-predictor tree (3x the host front-end work per frame)")
     ap.add_argument("--unique", type=int, default=0, help="encode only this many distinct frames and repeat them (0 = all distinct)")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
     ap.add_argument("--inflight", type=int, default=2, help="resident batches alternated by the device-resident loop")
@@ -82,7 +85,8 @@ def make_frames(args, rank):
     seeds = frame_seeds(n, rank)[:uniq]
     workers = max(1, min(uniq, rank_cores()))
     with ThreadPoolExecutor(max_workers=workers) as ex:
-        files = list(ex.map(lambda s: synth.encode_synthetic(args.width, args.height, s, args.distance, args.epf, 1, args.profile), seeds))
+        files = list(ex.map(lambda s: synth.encode_synthetic(args.width, args.height, s, args.distance, args.epf, 1, args.profile,
+                                                             getattr(args, "lf_tree", 0)), seeds))
     return [files[i % uniq] for i in range(n)]
 
 
@@ -332,7 +336,8 @@ def main():
             "config": {
                 "workload": f"batch of {n} synthetic {args.width}x{args.height} VarDCT frames per GPU (BASELINE config 2), "
                             f"distance {args.distance} (~{sum(i.hf_bytes for i in infos) * 8 / (args.width * args.height * n):.2f} bpp HF), "
-                            f"transform profile {args.profile}, Gaborish on, EPF iters {args.epf}, RGB u8 out",
+                            f"transform profile {args.profile}, Gaborish on, EPF iters {args.epf}, RGB u8 out, LF image coded with "
+                            + ("a libjxl-like weighted-predictor tree" if args.lf_tree else "one Gradient leaf per channel"),
                 "frames_per_gpu": n, "unique_frames": args.unique or n,
                 "l2_policy": "working set per step (coefficients + XYB planes, >10 GB) far exceeds the 126 MB L2; no explicit flush",
                 "sharding": "frames partitioned by rank, no data-path collective",

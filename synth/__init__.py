@@ -26,9 +26,11 @@ def _lib():
     return _LIB
 
 
-def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, profile=1) -> bytes:
+def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, profile=1, lf_tree=0) -> bytes:
     """One synthetic VarDCT frame. profile 0: DCT8x8 only; 1: mixed transforms up to 32x32;
-    2: also 64x64 / 64x32 / 32x64."""
+    2: also 64x64 / 64x32 / 32x64. lf_tree 0: LF image coded with one Gradient leaf per channel; 1: like libjxl
+    (channel prefix, then a subtree on the weighted-predictor property with Weighted-predictor leaves)."""
+    profile = (profile & 0xff) | ((lf_tree & 1) << 8)
     lib = _lib()
     cap = max(1 << 16, width * height * 2)
     buf = C.create_string_buffer(cap)

@@ -38,7 +38,8 @@ struct Params {
   uint32_t epf_iters;  // 0..3
   uint32_t gab;        // 0/1
   uint32_t profile;    // 0 = DCT8x8 only, 1 = mixed <= 32x32 (+4x8/8x4/4x4), 2 = + 64x64 family
-  uint32_t num_threads_unused;
+  uint32_t lf_tree;    // coding of the LF image: 0 = one Gradient leaf per channel, 1 = libjxl-like (channel prefix,
+                       // then a subtree on the weighted-predictor property 15 with Weighted leaves)
 };
 
 // ---------------------------------------------------------------------------
@@ -364,7 +365,46 @@ static inline int64_t clamped_gradient(int64_t l, int64_t t, int64_t tl) {
   int64_t mn = std::min(l, t), mx = std::max(l, t), g = l + t - tl;
   return tl < mn ? mx : (tl > mx ? mn : g);
 }
-static void write_modular(BitWriter& bw, const std::vector<Chan>& ch, uint32_t predictor) {
+// MA tree in the bitstream's order (tree.rs:284-340: breadth first, children appended to the pending queue).
+struct TNode {
+  int property = -1;  // -1: leaf
+  int32_t splitval = 0;
+  uint32_t left = 0, right = 0;  // property > splitval -> left
+  uint32_t predictor = 5, ctx = 0;
+};
+struct TDesc {  // nested description; left / right index into the description vector
+  int property;
+  int32_t splitval;
+  uint32_t predictor;
+  int left, right;
+};
+static std::vector<TNode> flatten_tree(const std::vector<TDesc>& d, int root) {
+  std::vector<TNode> out;
+  std::vector<int> q{root};
+  for (size_t qi = 0; qi < q.size(); qi++) {
+    const TDesc& t = d[q[qi]];
+    TNode n;
+    if (t.property >= 0) {
+      n.property = t.property;
+      n.splitval = t.splitval;
+      n.left = uint32_t(q.size());
+      n.right = n.left + 1;
+      q.push_back(t.left);
+      q.push_back(t.right);
+    } else {
+      n.predictor = t.predictor;
+    }
+    out.push_back(n);
+  }
+  uint32_t leaf = 0;
+  for (auto& n : out)
+    if (n.property < 0) n.ctx = leaf++;
+  return out;
+}
+
+// lf_tree: false = one leaf (`predictor`) per channel; true = libjxl-like: the same channel prefix, then per channel
+// a subtree that splits on the weighted-predictor property (15) and predicts with the weighted predictor (6).
+static void write_modular(BitWriter& bw, const std::vector<Chan>& ch, uint32_t predictor, bool wp_tree = false) {
   bool empty = true;
   for (auto& c : ch)
     if (c.w && c.h) empty = false;
@@ -373,24 +413,38 @@ static void write_modular(BitWriter& bw, const std::vector<Chan>& ch, uint32_t p
   bw.write(1, 1);  // WeightedHeader all_default
   bw.write(0, 2);  // no transforms
   const size_t n = ch.size();
-  // tree: chain of splits on property 0 (channel), emitted in BFS order (tree.rs:284-340)
-  std::vector<Token> tt;
-  auto leaf = [&] {
-    tt.push_back(Token{1, 0});
-    tt.push_back(Token{2, predictor});
-    tt.push_back(Token{3, 0});
-    tt.push_back(Token{4, 0});
-    tt.push_back(Token{5, 0});
+  std::vector<TDesc> d;
+  auto leaf = [&](uint32_t pred) {
+    d.push_back(TDesc{-1, 0, pred, -1, -1});
+    return int(d.size() - 1);
   };
-  if (n == 1) {
-    leaf();
-  } else {
-    for (size_t i = 0; i + 1 < n; i++) {
-      tt.push_back(Token{1, 1});                                     // property 0 (+1)
-      tt.push_back(Token{0, pack_signed(int32_t(n - 2 - i))});       // channel > val -> left
-      leaf();                                                        // left child: channel n-1-i
+  auto split = [&](int prop, int32_t val, int l, int r) {
+    d.push_back(TDesc{prop, val, 0, l, r});
+    return int(d.size() - 1);
+  };
+  auto channel_subtree = [&]() {
+    if (!wp_tree) return leaf(predictor);
+    // contexts by the signed maximum neighbouring error of the weighted predictor (in 1/8 sample units)
+    static const int32_t kThr[6] = {96, 24, 5, -6, -25, -97};
+    int t = leaf(6);
+    for (int i = 5; i >= 0; i--) t = split(15, kThr[i], leaf(6), t);
+    return t;
+  };
+  int root = channel_subtree();  // channel 0
+  for (size_t c = 1; c < n; c++) root = split(0, int32_t(c) - 1, channel_subtree(), root);  // channel > c-1 -> c..
+  const std::vector<TNode> tree = flatten_tree(d, root);
+  std::vector<Token> tt;
+  for (const TNode& nd : tree) {
+    if (nd.property >= 0) {
+      tt.push_back(Token{1, uint32_t(nd.property + 1)});
+      tt.push_back(Token{0, pack_signed(nd.splitval)});
+    } else {
+      tt.push_back(Token{1, 0});
+      tt.push_back(Token{2, nd.predictor});
+      tt.push_back(Token{3, 0});
+      tt.push_back(Token{4, 0});
+      tt.push_back(Token{5, 0});
     }
-    leaf();  // channel 0
   }
   {
     uint32_t nc;
@@ -400,26 +454,43 @@ static void write_modular(BitWriter& bw, const std::vector<Chan>& ch, uint32_t p
     write_code(bw, code);
     write_tokens(bw, code, tt);
   }
-  // data: context of channel c is leaf id n-1-c
+  const size_t num_leaves = (tree.size() + 1) / 2;
   std::vector<Token> dt;
+  const jxg::WeightedHeader wph;
   for (size_t c = 0; c < n; c++) {
     const Chan& k = ch[c];
-    uint32_t ctx = uint32_t(n - 1 - c);
+    if (!k.w || !k.h) continue;
+    jxg::WpState wp(wph, wp_tree ? k.w : 0);
     for (uint32_t y = 0; y < k.h; y++)
       for (uint32_t x = 0; x < k.w; x++) {
         const int32_t* row = &k.d[size_t(y) * k.w];
         const int32_t* top = y ? row - k.w : row;
-        int64_t left = x ? row[x - 1] : (y ? top[0] : 0);
-        int64_t t = y ? top[x] : left;
-        int64_t tl = (x && y) ? top[x - 1] : left;
-        int64_t pred = predictor == 5 ? clamped_gradient(left, t, tl) : predictor == 1 ? left : 0;
-        dt.push_back(Token{ctx, pack_signed(int32_t(int64_t(row[x]) - pred))});
+        const int32_t* toptop = y > 1 ? top - k.w : top;
+        const int32_t left = x ? row[x - 1] : (y ? top[0] : 0);
+        const int32_t t = y ? top[x] : left;
+        const int32_t tl = (x && y) ? top[x - 1] : left;
+        const int32_t tr = (x + 1 < k.w && y) ? top[x + 1] : t;
+        const int32_t tt2 = y > 1 ? toptop[x] : t;
+        int64_t wp_pred = 0;
+        int32_t wp_prop = 0;
+        if (wp_tree) wp.predict(x, y, t, left, tr, tl, tt2, wp_pred, wp_prop);
+        const TNode* nd = &tree[0];
+        while (nd->property >= 0) {
+          const int32_t v = nd->property == 0 ? int32_t(c) : wp_prop;
+          nd = &tree[v > nd->splitval ? nd->left : nd->right];
+        }
+        const int64_t pred = nd->predictor == 6   ? wp_pred
+                             : nd->predictor == 5 ? clamped_gradient(left, t, tl)
+                             : nd->predictor == 1 ? int64_t(left)
+                                                  : 0;
+        dt.push_back(Token{nd->ctx, pack_signed(int32_t(int64_t(row[x]) - pred))});
+        if (wp_tree) wp.update(row[x], x, y);
       }
   }
   uint32_t nc;
   HybridCfg cfg;
-  std::vector<uint8_t> map = cluster_contexts(n, {&dt}, 8, nc, cfg);
-  AnsCode code = build_code(n, map, nc, {&dt});
+  std::vector<uint8_t> map = cluster_contexts(num_leaves, {&dt}, 8, nc, cfg);
+  AnsCode code = build_code(num_leaves, map, nc, {&dt});
   write_code(bw, code);
   write_tokens(bw, code, dt);
 }
@@ -656,7 +727,7 @@ std::vector<uint8_t> encode(const Params& p) {
       for (uint32_t y = 0; y < h; y++)
         for (uint32_t x = 0; x < w; x++) ch[i].d[size_t(y) * w + x] = f.lfq[order[i]][size_t(y0 + y) * f.xb + x0 + x];
     }
-    write_modular(bw, ch, 5);
+    write_modular(bw, ch, 5, f.p.lf_tree != 0);
     // HF metadata (modular/mod.rs:984-1080)
     std::vector<int32_t> types, quants;
     for (uint32_t y = 0; y < h; y++)
@@ -798,7 +869,8 @@ const char* jxs_last_error() { return g_err.c_str(); }
 int64_t jxs_encode_synthetic(uint32_t width, uint32_t height, uint64_t seed, float distance, uint32_t epf_iters,
                              uint32_t gab, uint32_t profile, uint8_t* out, size_t cap) {
   try {
-    jxs::Params p{width, height, seed, distance, epf_iters, gab, profile, 0};
+    // profile: bits 0..7 transform mix, bit 8: libjxl-like LF tree (weighted predictor)
+    jxs::Params p{width, height, seed, distance, epf_iters, gab, profile & 0xff, (profile >> 8) & 1};
     std::vector<uint8_t> b = jxs::encode(p);
     if (b.size() <= cap && out) memcpy(out, b.data(), b.size());
     return int64_t(b.size());

@@ -164,6 +164,17 @@ def test_specialised_modular_walks_match_the_generic_loop():
         lib.jxo_t_force_generic_walk(0)
     assert np.array_equal(taps_fast["coeffs"], taps_slow["coeffs"])
     assert np.array_equal(fast, slow)
+    # the same frame with the LF image coded like libjxl does (channel prefix + weighted-predictor subtree: the
+    # single-property table walk): same LF samples, so the same pixels, through both walks
+    fw = synth.encode_synthetic(2304 + 40, 1024 + 24, 4242, 0.5, 2, 1, 1, lf_tree=1)
+    assert fw != f
+    try:
+        fast_w, _ = ob.decode_file(fw, abi.FORMAT_RGB_F32)
+        lib.jxo_t_force_generic_walk(1)
+        slow_w, _ = ob.decode_file(fw, abi.FORMAT_RGB_F32)
+    finally:
+        lib.jxo_t_force_generic_walk(0)
+    assert np.array_equal(fast_w, fast) and np.array_equal(slow_w, fast)
     # Modular frames: group streams of 65 536 samples per channel through the same walks
     for tk in (0, 1):
         m = synth.encode_modular(700, 530, 11, 6, 0, tk)

@@ -11,7 +11,8 @@
 #   stages     per-stage device times of one resident batch (tools/stage_times.py)
 #   e2e        host-side timeline of PipelinedDecoder (tools/e2e_profile4.py)
 #   hostprobe  CPU quota and front-end parse throughput of the box (tools/host_probe.py)
-#   sweeps     resident batches 1/2/3, batch of 128 frames, 1080p frames (config 3 shape), one 16384^2 EPF-3 frame (config 4)
+#   sweeps     resident batches 1/2/3, batch of 128 frames, 1080p frames (config 3 shape), libjxl-like LF coding,
+#              one 16384^2 EPF-3 frame (config 4)
 #   modular    config 5 (tools/bench_modular.py)
 #   launches   ncu launch list of a short bench run (per-launch times; shares, not absolutes)
 #   ncu_full   ncu --set full of the entropy, transform and filter kernels on a small batch (+ raw CSV pages)
@@ -51,6 +52,7 @@ if want sweeps; then
   step sweep_inflight3 300 python bench.py --steps 6 --warmup 3 --inflight 3
   step sweep_frames128 500 python bench.py --steps 4 --warmup 3 --frames 128
   step sweep_1080p 400 python bench.py --steps 6 --warmup 3 --frames 64 --width 1920 --height 1080
+  step sweep_lf_wp_tree 400 python bench.py --steps 6 --warmup 3 --lf-tree 1
   step sweep_16k_epf3 600 python bench.py --steps 3 --warmup 3 --frames 1 --width 16384 --height 16384 --epf 3 --cpu-sample-frames 0
 fi
 if want modular; then
