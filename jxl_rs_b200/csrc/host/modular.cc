@@ -158,8 +158,15 @@ WpState::WpState(const WeightedHeader& h, size_t xs) : xsize(xs), hdr(h) {
   error.assign(n, 0);
 }
 
-void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t topright, int32_t topleft,
-                      int32_t toptop, int64_t& pred_out, int32_t& prop_out) {
+// Force-inlined bodies: the per-pixel loops call these directly (a call per pixel with nine arguments and results
+// through memory costs ~15 % of the weighted-predictor path); WpState::predict / update are the out-of-line entry points.
+__attribute__((always_inline)) static inline void wp_predict(WpState& S, size_t x, size_t y, int32_t top, int32_t left,
+                                                             int32_t topright, int32_t topleft, int32_t toptop,
+                                                             int64_t& pred_out, int32_t& prop_out) {
+  const size_t xsize = S.xsize;
+  const WeightedHeader& hdr = S.hdr;
+  const uint32_t* pred_errors = S.pred_errors.data();
+  const int32_t* error = S.error.data();
   size_t cur_row = (y & 1) ? 0 : xsize + 1, prev_row = (y & 1) ? xsize + 1 : 0;
   size_t pos_ne = x + 1 < xsize ? x + 1 : x;
   size_t pos_nw = x > 0 ? x - 1 : 0;
@@ -206,16 +213,21 @@ void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t top
     const int64_t clamped = bsel(mn3 > lo, mn3, lo);     // max(mn, min(mx, pr))
     pr = bsel(((te_n ^ te_w) | (te_n ^ te_nw)) <= 0, clamped, pr);
   }
-  prediction[0] = p0;
-  prediction[1] = p1;
-  prediction[2] = p2;
-  prediction[3] = p3;
-  pred = pr;
+  S.prediction[0] = p0;
+  S.prediction[1] = p1;
+  S.prediction[2] = p2;
+  S.prediction[3] = p3;
+  S.pred = pr;
   pred_out = (pr + 3) >> 3;
   prop_out = int32_t(p);
 }
 
-void WpState::update(int32_t val, size_t x, size_t y) {
+__attribute__((always_inline)) static inline void wp_update(WpState& S, int32_t val, size_t x, size_t y) {
+  const size_t xsize = S.xsize;
+  uint32_t* pred_errors = S.pred_errors.data();
+  int32_t* error = S.error.data();
+  const int64_t pred = S.pred;
+  const int64_t* prediction = S.prediction;
   size_t cur_row = (y & 1) ? 0 : xsize + 1, prev_row = (y & 1) ? xsize + 1 : 0;
   int64_t v = int64_t(val) * 8;
   error[cur_row + x + 1] = int32_t(pred - v);
@@ -227,6 +239,13 @@ void WpState::update(int32_t val, size_t x, size_t y) {
     prev[i] += e;
   }
 }
+
+void WpState::predict(size_t x, size_t y, int32_t top, int32_t left, int32_t topright, int32_t topleft,
+                      int32_t toptop, int64_t& pred_out, int32_t& prop_out) {
+  wp_predict(*this, x, y, top, left, topright, topleft, toptop, pred_out, prop_out);
+}
+
+void WpState::update(int32_t val, size_t x, size_t y) { wp_update(*this, val, x, y); }
 
 // ---------------------------------------------------------------------------
 // Headers / tree
@@ -484,7 +503,7 @@ static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, c
       const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
       int64_t wp_pred = 0;
       int32_t wp_prop = 0;
-      if (kWp) wp.predict(x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
+      if (kWp) wp_predict(wp, x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
       const TreeNode* nd = root;
       while (nd->property >= 0) {
         int32_t v;
@@ -512,7 +531,7 @@ static void decode_lazy_props(ModularChannel& ch, size_t ci, size_t stream_id, c
       const int64_t guess = predict_one(nd->left, n, wp_pred) + int64_t(nd->val);
       const int32_t val =
           int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
-      if (kWp) wp.update(val, x, y);
+      if (kWp) wp_update(wp, val, x, y);
       row[x] = val;
     }
   }
@@ -546,7 +565,8 @@ static bool make_prop_lut(const TreeNode* nodes, const TreeNode* root, std::vect
   return true;
 }
 
-template <bool kWp, class R>
+// kProp15: the table is over the weighted-predictor property (the libjxl LF case), which removes the property switch.
+template <bool kWp, bool kProp15, class R>
 static void decode_prop_lut(ModularChannel& ch, const TreeNode* nodes, int prop, const uint32_t* lut,
                             const uint8_t* cmap, const WeightedHeader& wph, R& io) {
   R rd = io;
@@ -557,43 +577,46 @@ static void decode_prop_lut(ModularChannel& ch, const TreeNode* nodes, int prop,
     const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
     const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
     int32_t prev_p9 = 0;
-    auto pixel = [&](size_t x, const Neigh& n) {
-      const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
+    const size_t interior_end = (y >= 2 && w > 4) ? w - 2 : 0;  // 2 <= x < w - 2: every neighbour exists
+    // one loop body (a single copy of the predictor + reader code keeps its state in registers)
+    for (size_t x = 0; x < w; x++) {
+      const Neigh n = (x >= 2 && x < interior_end) ? get_neigh_interior(row, top_row, toptop_row, x)
+                                                   : get_neigh(row, top_row, toptop_row, x, y, w);
       int64_t wp_pred = 0;
       int32_t wp_prop = 0;
-      if (kWp) wp.predict(x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
+      if (kWp) wp_predict(wp, x, y, n.top, n.left, n.topright, n.topleft, n.toptop, wp_pred, wp_prop);
       int32_t v;
-      switch (prop) {  // loop invariant
-        case 2: v = int32_t(y); break;
-        case 3: v = int32_t(x); break;
-        case 4: v = wabs(n.top); break;
-        case 5: v = wabs(n.left); break;
-        case 6: v = n.top; break;
-        case 7: v = n.left; break;
-        case 8: v = wsub(n.left, prev_p9); break;
-        case 9: v = p9; break;
-        case 10: v = wsub(n.left, n.topleft); break;
-        case 11: v = wsub(n.topleft, n.top); break;
-        case 12: v = wsub(n.top, n.topright); break;
-        case 13: v = wsub(n.top, n.toptop); break;
-        case 14: v = wsub(n.left, n.leftleft); break;
-        default: v = wp_prop; break;
+      if (kProp15) {
+        v = wp_prop;
+      } else {
+        const int32_t p9 = wsub(wadd(n.left, n.top), n.topleft);
+        switch (prop) {  // loop invariant
+          case 2: v = int32_t(y); break;
+          case 3: v = int32_t(x); break;
+          case 4: v = wabs(n.top); break;
+          case 5: v = wabs(n.left); break;
+          case 6: v = n.top; break;
+          case 7: v = n.left; break;
+          case 8: v = wsub(n.left, prev_p9); break;
+          case 9: v = p9; break;
+          case 10: v = wsub(n.left, n.topleft); break;
+          case 11: v = wsub(n.topleft, n.top); break;
+          case 12: v = wsub(n.top, n.topright); break;
+          case 13: v = wsub(n.top, n.toptop); break;
+          case 14: v = wsub(n.left, n.leftleft); break;
+          default: v = wp_prop; break;
+        }
+        prev_p9 = p9;
       }
-      prev_p9 = p9;
       const int32_t clamped = v < kLutMin ? kLutMin : (v > kLutMax ? kLutMax : v);
       const TreeNode* nd = nodes + lut[size_t(clamped - kLutMin)];
-      const int64_t guess = (kWp && nd->left == kWeighted ? wp_pred : predict_one(nd->left, n, wp_pred)) + int64_t(nd->val);
+      const int64_t guess =
+          (kWp && nd->left == kWeighted ? wp_pred : predict_one(nd->left, n, wp_pred)) + int64_t(nd->val);
       const int32_t val =
           int32_t(guess + int64_t(nd->right) * int64_t(unpack_signed(rd.read_clustered(cmap[nd->ctx]))));
-      if (kWp) wp.update(val, x, y);
+      if (kWp) wp_update(wp, val, x, y);
       row[x] = val;
-    };
-    size_t x = 0;
-    if (y >= 2 && w > 4) {
-      for (; x < 2; x++) pixel(x, get_neigh(row, top_row, toptop_row, x, y, w));
-      for (; x + 2 < w; x++) pixel(x, get_neigh_interior(row, top_row, toptop_row, x));
     }
-    for (; x < w; x++) pixel(x, get_neigh(row, top_row, toptop_row, x, y, w));
   }
   io = rd;
 }
@@ -688,9 +711,11 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
       if (!make_prop_lut(nodes, root, lut)) single_prop = -1;
     }
     with_reader(reader, br, [&](auto& rd) {
-      if (single_prop >= 0) {
-        if (sub_wp) decode_prop_lut<true>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
-        else decode_prop_lut<false>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
+      if (single_prop == 15) {
+        decode_prop_lut<true, true>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
+      } else if (single_prop >= 0) {
+        if (sub_wp) decode_prop_lut<true, false>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
+        else decode_prop_lut<false, false>(ch, nodes, single_prop, lut.data(), cmap, header.wp, rd);
       } else if (sub_wp) {
         decode_lazy_props<true>(ch, ci, stream_id, nodes, root, cmap, header.wp, rd);
       } else {
