@@ -208,3 +208,68 @@ def test_multithreaded_lf_groups_give_the_same_parse():
     bad[len(f) // 40] ^= 0x55  # inside the LF-group sections (they come first and are ~5 % of the file)
     bad = bytes(bad)
     assert lib.jxo_t_parse_digest(bad, len(bad), 4) in (0, lib.jxo_t_parse_digest(bad, len(bad), 1))
+
+
+def test_pipelined_decoder_host_logic_with_a_fake_device(monkeypatch):
+    """The host side of PipelinedDecoder (worker pool, parse-ahead, dispatcher thread, per-file LF-group threads for
+    single large images, error propagation) with the device context and batch replaced by recorders: no GPU needed."""
+    import synth
+    from jxl_rs_b200 import decoder
+
+    calls = []
+
+    class FakeCtx:
+        def __init__(self, device):
+            self.device = device
+
+        def close(self):
+            pass
+
+    class FakeBatch:
+        def __init__(self, ctx, n, staging_threads=0):
+            self.frames = []
+
+        def add(self, fr, ptr, stride, fmt, out_is_device):
+            self.frames.append((fr.width, fr.height, ptr, stride))
+
+        def run(self, stream_ptr=0):
+            calls.append(list(self.frames))
+
+        def wait(self):
+            pass
+
+        def stats(self):
+            return {"h2d_bytes": 1, "d2h_bytes": 2, "kernel_launches": 3}
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(decoder, "JxgContext", FakeCtx)
+    monkeypatch.setattr(decoder, "Batch", FakeBatch)
+    seen_threads = []
+    real_parsed = decoder.ParsedFrame
+
+    class SpyParsed(real_parsed):
+        def __init__(self, data, threads=1):
+            seen_threads.append(threads)
+            super().__init__(data, threads)
+
+    monkeypatch.setattr(decoder, "ParsedFrame", SpyParsed)
+    files = [synth.encode_synthetic(64 + 8 * i, 48, 10 + i, 1.0, 2, 1, 0) for i in range(3)]
+    dec = decoder.PipelinedDecoder(0, depth=2, workers=6)
+    try:
+        for _ in range(4):
+            dec.submit(files, [(100 + i, 7) for i in range(3)])
+        dec.drain()
+        assert len(calls) == 4 and all(len(c) == 3 for c in calls)
+        assert calls[0][1][:2] == (72, 48) and calls[0][2][2:] == (102, 7)
+        assert set(seen_threads) == {2}  # 6 workers / 3 files
+        dec.decode(files[:1], [(5, 5)])
+        assert seen_threads[-1] == 6 and dec.last_stats["kernel_launches"] == 3
+        # a corrupt file surfaces at drain() as the front-end's error, and the decoder stays usable
+        dec.submit([files[0][:40]], [(1, 1)])
+        with pytest.raises(abi.JxgError):
+            dec.drain()
+        dec.decode(files[:2], [(1, 1), (2, 2)])
+    finally:
+        dec.close()
