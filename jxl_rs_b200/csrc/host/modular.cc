@@ -396,15 +396,19 @@ struct DirectReader {
 static void build_direct_tables(const EntropyCode& code, uint32_t cluster, uint32_t* tab, uint64_t* tok_tab) {
   const uint32_t log_bucket = kAnsLogSumProbs - code.log_alpha_size;
   const AnsBucket* buckets = code.ans_buckets.data() + (size_t(cluster) << code.log_alpha_size);
-  for (uint32_t idx = 0; idx < 4096; idx++) {
-    const uint32_t i = idx >> log_bucket, pos = idx & ((1u << log_bucket) - 1);
+  // per bucket: positions below the cut-off keep the bucket's own symbol, the rest go to its alias; inside each run
+  // only the offset changes (by one per position), so both runs are plain counting loops.
+  // build_alias_map guarantees 1 <= dist <= 4096 and offset < dist for every slot.
+  const uint32_t bucket_size = 1u << log_bucket;
+  for (uint32_t i = 0; i < (1u << code.log_alpha_size); i++) {
     const AnsBucket& b = buckets[i];
-    const bool alias = pos >= b.alias_cutoff;
-    const uint32_t offset = (alias ? b.alias_offset : 0) + pos;
-    const uint32_t dist = uint32_t(b.dist) ^ (alias ? b.alias_dist_xor : 0);
-    const uint32_t symbol = alias ? b.alias_symbol : i;
-    // build_alias_map guarantees 1 <= dist <= 4096 and offset < dist for every slot.
-    tab[idx] = (symbol & 0xff) | ((offset & 0xfff) << 8) | (((dist - 1) & 0xfff) << 20);
+    uint32_t* t = tab + (size_t(i) << log_bucket);
+    const uint32_t cutoff = std::min<uint32_t>(b.alias_cutoff, bucket_size);
+    const uint32_t own = (i & 0xff) | (((uint32_t(b.dist) - 1) & 0xfff) << 20);
+    for (uint32_t pos = 0; pos < cutoff; pos++) t[pos] = own | ((pos & 0xfff) << 8);
+    const uint32_t alias_dist = uint32_t(b.dist) ^ uint32_t(b.alias_dist_xor);
+    const uint32_t alias = uint32_t(b.alias_symbol) | (((alias_dist - 1) & 0xfff) << 20);
+    for (uint32_t pos = cutoff; pos < bucket_size; pos++) t[pos] = alias | (((uint32_t(b.alias_offset) + pos) & 0xfff) << 8);
   }
   const HybridUint& u = code.uint_configs[cluster];
   for (uint32_t tok = 0; tok < 256; tok++) {
