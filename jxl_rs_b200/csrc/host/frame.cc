@@ -31,6 +31,78 @@ std::vector<uint8_t> repack_bits(const uint8_t* data, size_t size, size_t bit_po
   return out;
 }
 
+bool ec_is_meta(const ModularChannel& c) { return c.hshift < 0 || c.vshift < 0; }
+
+// The part of coded channel `c` one (LF) group of side `dim` carries (modular/mod.rs:150-190).
+ModularChannel ec_group_rect(const ModularChannel& c, uint32_t dim, uint32_t gx, uint32_t gy) {
+  const uint32_t gw = dim >> c.hshift, gh = dim >> c.vshift;
+  const uint64_t bx = uint64_t(gx) * gw, by = uint64_t(gy) * gh;
+  if (gw == 0 || gh == 0 || bx >= c.w || by >= c.h) return ModularChannel(0, 0, c.hshift, c.vshift);
+  return ModularChannel(std::min<uint32_t>(c.w - uint32_t(bx), gw), std::min<uint32_t>(c.h - uint32_t(by), gh), c.hshift,
+                        c.vshift);
+}
+
+// FullModularImage::read + read_section0 (modular/mod.rs:258-365, 405-470) for the extra channels of a VarDCT frame:
+// decoded and dropped (see FrameState::ec). Needed in full because a single-section frame has LfGroup / HfGlobal /
+// the HF group right behind this data in the same bit stream.
+void skip_extra_channels_global(FrameState& fs, BitReader& br) {
+  const FrameHeader& h = fs.header;
+  for (uint32_t i = 0; i < h.num_extra_channels; i++) {
+    const uint32_t ecups = h.ec_upsampling[i];
+    if (ecups == 0 || (ecups & (ecups - 1))) fail("invalid extra-channel upsampling");
+    const int32_t shift = int32_t(floor_log2(ecups));  // colour upsampling is 1 here (checked by the caller)
+    ModularChannel c;
+    c.w = (h.width + ecups - 1) / ecups;
+    c.h = (h.height + ecups - 1) / ecups;
+    c.hshift = c.vshift = shift;
+    fs.ec.coded.push_back(c);
+  }
+  fs.ec.header = GroupHeader::read(br);
+  fs.ec.nb_meta = 0;
+  meta_apply_transforms(fs.ec.coded, fs.ec.nb_meta, fs.ec.header, /*allocate=*/false);
+  const uint32_t gd = h.group_dim();
+  size_t n0 = 0;
+  while (n0 < fs.ec.coded.size() &&
+         (ec_is_meta(fs.ec.coded[n0]) || (fs.ec.coded[n0].w <= gd && fs.ec.coded[n0].h <= gd)))
+    n0++;
+  fs.ec.n0 = n0;
+  std::vector<ModularChannel> scratch;
+  bool empty = true;
+  for (size_t i = 0; i < n0; i++) {
+    const ModularChannel& c = fs.ec.coded[i];
+    scratch.emplace_back(c.w, c.h, c.hshift, c.vshift);
+    if (c.w && c.h) empty = false;
+  }
+  if (empty) return;
+  ModularTree local;
+  const ModularTree* tree = &fs.global_tree;
+  if (!fs.ec.header.use_global_tree) {
+    size_t samples = 0;
+    for (const ModularChannel& c : scratch) samples += size_t(c.w) * c.h;
+    local = ModularTree::read(br, std::min<size_t>(1024 + samples, size_t(1) << 20));
+    tree = &local;
+  } else if (!fs.has_global_tree) {
+    fail("no global MA tree");
+  }
+  std::vector<ModularChannel*> ptrs;
+  for (ModularChannel& c : scratch) ptrs.push_back(&c);
+  decode_modular_channels(ptrs, 0, fs.ec.header, *tree, br);
+}
+
+// The ModularLF stream of LF group `g` (modular/mod.rs:367-400: channels with min(hshift, vshift) >= 3): decoded and
+// dropped. Empty for full-resolution extra channels without Squeeze.
+void skip_extra_channels_lf_group(FrameState& fs, uint32_t g, BitReader& br) {
+  const FrameHeader& h = fs.header;
+  std::vector<ModularChannel> ch;
+  const uint32_t xlg = h.xsize_lf_groups();
+  for (size_t c = fs.ec.n0; c < fs.ec.coded.size(); c++) {
+    const ModularChannel& cc = fs.ec.coded[c];
+    if (ec_is_meta(cc) || std::min(cc.hshift, cc.vshift) < 3) continue;
+    ch.push_back(ec_group_rect(cc, h.group_dim() * 8, g % xlg, g / xlg));
+  }
+  decode_modular_subbitstream(ch, 1 + size_t(h.num_lf_groups()) + g, fs.has_global_tree ? &fs.global_tree : nullptr, br);
+}
+
 // frame/decode.rs:307-427
 void decode_lf_global(FrameState& fs, BitReader& br) {
   const FrameHeader& h = fs.header;
@@ -114,11 +186,12 @@ void decode_lf_global(FrameState& fs, BitReader& br) {
   }
   // global MA tree (frame/decode.rs:380-391)
   if (br.read_bool()) {
-    size_t limit = std::min<size_t>(1024 + size_t(h.width) * h.height * 3 / 16, size_t(1) << 22);
+    size_t limit = std::min<size_t>(1024 + size_t(h.width) * h.height * (3 + h.num_extra_channels) / 16, size_t(1) << 22);
     fs.global_tree = ModularTree::read(br, limit);
     fs.has_global_tree = true;
   }
   // FullModularImage::read: zero channels for VarDCT without extra channels (modular/mod.rs:303-321).
+  if (h.num_extra_channels) skip_extra_channels_global(fs, br);
   br.check();
 }
 
@@ -169,6 +242,7 @@ void decode_lf_group(FrameState& fs, uint32_t g, BitReader& br) {
     }
   }
   // ModularLF stream: no channels in a VarDCT frame without extra channels.
+  if (h.num_extra_channels) skip_extra_channels_lf_group(fs, g, br);
   // ---- HF metadata (decode_hf_metadata) ----
   {
     uint32_t count = uint32_t(br.read(ceil_log2(uint64_t(w) * hh))) + 1;
@@ -466,7 +540,6 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
   if (h.encoding != 0) fail("not a VarDCT frame (Modular frames use the Modular path)", kErrUnsupported);
   if (h.frame_type != 0) fail("only regular frames are in scope", kErrUnsupported);
   if (!fs.file.xyb_encoded || h.do_ycbcr) fail("non-XYB VarDCT (JPEG recompression) is outside the scope", kErrUnsupported);
-  if (h.num_extra_channels) fail("extra channels are outside the hot-path scope", kErrUnsupported);
   if (h.upsampling != 1) fail("upsampling is outside the hot-path scope", kErrUnsupported);
   if (h.has_lf_frame()) fail("LF frames are outside the hot-path scope", kErrUnsupported);
   if (h.have_crop || h.blending.mode != 0) fail("cropped/blended frames are outside the hot-path scope", kErrUnsupported);

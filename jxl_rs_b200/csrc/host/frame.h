@@ -60,6 +60,19 @@ struct FrameState {
   bool has_global_tree = false;
   ModularTree global_tree;
 
+  // Extra channels (alpha, depth, ...) of a VarDCT frame are Modular-coded next to the colour data
+  // (FullModularImage::read, modular/mod.rs:258-330). The hot path decodes the colour channels only — the
+  // reference API's "extra channel not requested" case, JxlPixelFormat::extra_channel_format = None
+  // (api/data_types.rs:154) — so the front-end just steps over their sub-bitstreams: the global header and the
+  // "meta or small" channels in LfGlobal, the shift >= 3 channels in every LfGroup section; the ModularHF streams
+  // sit behind the AC coefficients of their HF section and are never reached.
+  struct ExtraChannelImage {
+    std::vector<ModularChannel> coded;  // channel shapes after the global meta-apply (no sample planes)
+    GroupHeader header;
+    uint32_t nb_meta = 0;
+    size_t n0 = 0;  // leading channels coded in LfGlobal
+  } ec;
+
   // planes (xb x yb)
   uint32_t xb = 0, yb = 0;
   std::vector<float> lf[3];

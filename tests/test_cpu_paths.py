@@ -26,6 +26,26 @@ def test_oracle_self_verifies_on_reference_fixtures(golden_dir, name):
     assert out.shape[2] == 3 and np.isfinite(taps["xyb_filtered"]).all()
 
 
+ALPHA = ["3x3a_srgb_lossy.jxl", "alpha_premultiplied.jxl", "dice.jxl", "squeeze_alpha.jxl", "upsampled_alpha.jxl"]
+
+
+@pytest.mark.parametrize("name", ALPHA)
+def test_vardct_frames_with_extra_channels_decode_their_colour(golden_dir, name):
+    """Extra channels (alpha) are Modular sub-bitstreams around the colour data (modular/mod.rs:258-400); the front-end
+    steps over them (LfGlobal section 0, ModularLF per LF group) and the hot path decodes the colour channels — the
+    reference's "extra channel not requested" output. Everything behind a skipped stream (HF metadata, HfGlobal, the
+    AC streams) only self-verifies if the skip ended on the right bit."""
+    from tests import oracle_binding as ob
+    data = open(os.path.join(golden_dir, "jxl", name), "rb").read()
+    out, taps = ob.decode_file(data, abi.FORMAT_RGB_U8, taps=True, threads=4)
+    assert out.shape[2] == 3 and np.isfinite(taps["xyb_filtered"]).all()
+    if name == "3x3a_srgb_lossy.jxl":  # the same nine pixels as the file without alpha
+        plain = open(os.path.join(golden_dir, "jxl", "3x3_srgb_lossy.jxl"), "rb").read()
+        assert np.array_equal(out, ob.decode_file(plain, abi.FORMAT_RGB_U8)[0])
+    # truncating inside the skipped data must be reported, not read past
+    assert ob.load().jxo_t_parse_ok(data[: len(data) // 3], len(data) // 3) != 0
+
+
 def test_oracle_detects_corruption(golden_dir):
     from tests import oracle_binding as ob
     data = bytearray(open(os.path.join(golden_dir, "jxl", "green_queen_vardct_e3.jxl"), "rb").read())
@@ -130,14 +150,16 @@ def test_front_end_survives_corrupt_files(golden_dir):
     assert errors > 0 and parsed >= 0
 
 
-@pytest.mark.parametrize("name", REAL + ["green_queen_modular_e3.jxl", "lz77_flower.jxl", "tree_max_property_20.jxl", "grayscale_public_university.jxl"])
+@pytest.mark.parametrize("name", REAL + ["green_queen_modular_e3.jxl", "lz77_flower.jxl", "tree_max_property_20.jxl", "grayscale_public_university.jxl",
+                                         "alpha_premultiplied.jxl", "dice.jxl", "squeeze_alpha.jxl", "upsampled_alpha.jxl"])
 def test_specialised_walks_match_the_generic_loop_on_reference_fixtures(golden_dir, name):
     """Same differential check on the reference's real files (libjxl trees: property walks, prefix codes, LZ77,
     weighted predictor), VarDCT front-end and Modular frames."""
     from tests import oracle_binding as ob
     lib = ob.load()
     data = open(os.path.join(golden_dir, "jxl", name), "rb").read()
-    dec = ob.decode_modular_file if name not in REAL else (lambda d: ob.decode_file(d, abi.FORMAT_RGB_U8)[0])
+    vardct = name in REAL or "alpha" in name or name == "dice.jxl"
+    dec = (lambda d: ob.decode_file(d, abi.FORMAT_RGB_U8)[0]) if vardct else ob.decode_modular_file
     try:
         fast = dec(data)
         lib.jxo_t_force_generic_walk(1)

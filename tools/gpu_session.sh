@@ -37,7 +37,11 @@ nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,clocks_even
 python __graft_entry__.py > "$OUT/build.log" 2>&1 || echo "build failed" | tee -a "$OUT/session.log"
 
 TESTS_RC=0
-if want tests; then step tests 900 python -m pytest tests -m gpu -x -q; TESTS_RC=$?; fi
+if want tests; then
+  step tests 900 python -m pytest tests -m gpu -x -q; TESTS_RC=$?
+  # tests of features written without a device at hand (kept out of the default run until they have passed once)
+  step tests_experimental 300 env JXG_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_zz_extra_channels.py -m gpu -q
+fi
 if want bench; then
   step bench_reference 400 python bench.py --impl reference --steps 2 --warmup 1
   step bench 600 python bench.py --steps 8 --warmup 4
