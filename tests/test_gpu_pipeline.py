@@ -69,6 +69,11 @@ def test_device_survives_corrupt_streams(golden_dir):
     import synth
     from tests.fuzz_util import mutants
     paths = sorted(glob.glob(os.path.join(golden_dir, "jxl", "*.jxl")))
+    if os.environ.get("JXG_TEST_EXPERIMENTAL") != "1":
+        # fixtures added with the extra-channel support (see test_gpu_zz_extra_channels.py) join the mutation set once
+        # that support has had its first run on a device
+        new = {"3x3a_srgb_lossy.jxl", "alpha_premultiplied.jxl", "dice.jxl", "squeeze_alpha.jxl", "upsampled_alpha.jxl"}
+        paths = [p for p in paths if os.path.basename(p) not in new]
     ctx = j.JxgContext(0)
     decoded = failed = 0
     for _, data in mutants(paths, seed=99, count=220):
