@@ -14,6 +14,8 @@
 
 namespace jxg {
 
+static std::atomic<bool> g_pair_lf_groups{true};
+
 namespace {
 
 // Re-packs the bits of `data` starting at bit `bit_pos` into a fresh byte
@@ -195,117 +197,171 @@ void decode_lf_global(FrameState& fs, BitReader& br) {
   br.check();
 }
 
-// modular/mod.rs:837-1080
-void decode_lf_group(FrameState& fs, uint32_t g, BitReader& br) {
-  const FrameHeader& h = fs.header;
-  const uint32_t gd = h.group_dim();  // LF group = group_dim blocks
-  uint32_t gx = g % h.xsize_lf_groups(), gy = g / h.xsize_lf_groups();
-  uint32_t x0 = gx * gd, y0 = gy * gd;
-  uint32_t w = std::min(gd, fs.xb - x0), hh = std::min(gd, fs.yb - y0);
-  const ModularTree* gt = fs.has_global_tree ? &fs.global_tree : nullptr;
+// modular/mod.rs:837-1080: one LF group (LF image, ModularLF stream of extra channels, HF metadata), in phases so
+// that two groups can run their Modular sub-bitstreams in lockstep (decode_substreams_paired):
+//   begin_lf -> [LF image channels] -> finish_lf_begin_meta -> [HF metadata channels] -> finish_meta
+struct LfGroupJob {
+  FrameState& fs;
+  const uint32_t g;
+  BitReader br;
+  uint32_t x0, y0, w, hh;
+  float mul = 1.0f;
+  uint32_t count = 0, cw = 0, chh = 0;
+  std::vector<ModularChannel> ch;
+  std::unique_ptr<SubStream> ss;
+
+  LfGroupJob(FrameState& f, uint32_t group, const uint8_t* data, size_t size) : fs(f), g(group), br(data, size) {
+    const FrameHeader& h = fs.header;
+    const uint32_t gd = h.group_dim();  // LF group = group_dim blocks
+    const uint32_t gx = g % h.xsize_lf_groups(), gy = g / h.xsize_lf_groups();
+    x0 = gx * gd;
+    y0 = gy * gd;
+    w = std::min(gd, fs.xb - x0);
+    hh = std::min(gd, fs.yb - y0);
+  }
+  const ModularTree* global_tree() const { return fs.has_global_tree ? &fs.global_tree : nullptr; }
+
   // ---- LF coefficients (decode_vardct_lf) ----
-  uint32_t extra_precision = uint32_t(br.read(2));
-  float mul = 1.0f / float(1u << extra_precision);
-  {
-    std::vector<ModularChannel> ch;
+  void begin_lf() {
+    const uint32_t extra_precision = uint32_t(br.read(2));
+    mul = 1.0f / float(1u << extra_precision);
     for (int c = 0; c < 3; c++) ch.emplace_back(w, hh);
-    decode_modular_subbitstream(ch, 1 + g, gt, br);
-    // dequant_lf (444): channel 0 = Y, 1 = X, 2 = B
-    float inv_quant_lf = 65536.0f / (float(fs.global_scale) * float(fs.quant_lf));
-    float fac_x = fs.lf_quant[0] * inv_quant_lf * mul;
-    float fac_y = fs.lf_quant[1] * inv_quant_lf * mul;
-    float fac_b = fs.lf_quant[2] * inv_quant_lf * mul;
-    float cfl_x = fs.base_correlation_x + float(fs.ytox_lf) / float(fs.color_factor);
-    float cfl_b = fs.base_correlation_b + float(fs.ytob_lf) / float(fs.color_factor);
-    for (uint32_t y = 0; y < hh; y++) {
-      const int32_t *qy = ch[0].row(y), *qx = ch[1].row(y), *qb = ch[2].row(y);
-      size_t o = size_t(y0 + y) * fs.xb + x0;
-      for (uint32_t x = 0; x < w; x++) {
-        float in_x = float(qx[x]) * fac_x, in_y = float(qy[x]) * fac_y, in_b = float(qb[x]) * fac_b;
-        fs.lf[1][o + x] = in_y;
-        fs.lf[0][o + x] = in_y * cfl_x + in_x;
-        fs.lf[2][o + x] = in_y * cfl_b + in_b;
-      }
-      if (fs.num_lf_contexts > 1) {
+    ss = std::make_unique<SubStream>();
+    substream_begin(*ss, ch, 1 + g, global_tree(), br);
+  }
+
+  // call after the LF sub-bitstream has been finished
+  void finish_lf_begin_meta() {
+    const FrameHeader& h = fs.header;
+    {
+      // dequant_lf (444): channel 0 = Y, 1 = X, 2 = B
+      float inv_quant_lf = 65536.0f / (float(fs.global_scale) * float(fs.quant_lf));
+      float fac_x = fs.lf_quant[0] * inv_quant_lf * mul;
+      float fac_y = fs.lf_quant[1] * inv_quant_lf * mul;
+      float fac_b = fs.lf_quant[2] * inv_quant_lf * mul;
+      float cfl_x = fs.base_correlation_x + float(fs.ytox_lf) / float(fs.color_factor);
+      float cfl_b = fs.base_correlation_b + float(fs.ytob_lf) / float(fs.color_factor);
+      for (uint32_t y = 0; y < hh; y++) {
+        const int32_t *qy = ch[0].row(y), *qx = ch[1].row(y), *qb = ch[2].row(y);
+        size_t o = size_t(y0 + y) * fs.xb + x0;
         for (uint32_t x = 0; x < w; x++) {
-          auto bucket = [](const std::vector<int32_t>& thr, int32_t v) {
-            uint32_t n = 0;
-            for (int32_t t : thr) n += v > t;
-            return n;
-          };
-          uint32_t b = bucket(fs.lf_thresholds[0], qx[x]);
-          b = b * uint32_t(fs.lf_thresholds[2].size() + 1) + bucket(fs.lf_thresholds[2], qb[x]);
-          b = b * uint32_t(fs.lf_thresholds[1].size() + 1) + bucket(fs.lf_thresholds[1], qy[x]);
-          fs.quant_lf_map[o + x] = uint8_t(b);
+          float in_x = float(qx[x]) * fac_x, in_y = float(qy[x]) * fac_y, in_b = float(qb[x]) * fac_b;
+          fs.lf[1][o + x] = in_y;
+          fs.lf[0][o + x] = in_y * cfl_x + in_x;
+          fs.lf[2][o + x] = in_y * cfl_b + in_b;
+        }
+        if (fs.num_lf_contexts > 1) {
+          for (uint32_t x = 0; x < w; x++) {
+            auto bucket = [](const std::vector<int32_t>& thr, int32_t v) {
+              uint32_t n = 0;
+              for (int32_t t : thr) n += v > t;
+              return n;
+            };
+            uint32_t b = bucket(fs.lf_thresholds[0], qx[x]);
+            b = b * uint32_t(fs.lf_thresholds[2].size() + 1) + bucket(fs.lf_thresholds[2], qb[x]);
+            b = b * uint32_t(fs.lf_thresholds[1].size() + 1) + bucket(fs.lf_thresholds[1], qy[x]);
+            fs.quant_lf_map[o + x] = uint8_t(b);
+          }
         }
       }
     }
-  }
-  // ModularLF stream: no channels in a VarDCT frame without extra channels.
-  if (h.num_extra_channels) skip_extra_channels_lf_group(fs, g, br);
-  // ---- HF metadata (decode_hf_metadata) ----
-  {
-    uint32_t count = uint32_t(br.read(ceil_log2(uint64_t(w) * hh))) + 1;
-    uint32_t cw = (w + 7) / 8, chh = (hh + 7) / 8;
-    std::vector<ModularChannel> ch;
+    ss.reset();
+    ch.clear();
+    // ModularLF stream: no channels in a VarDCT frame without extra channels.
+    if (h.num_extra_channels) skip_extra_channels_lf_group(fs, g, br);
+    // ---- HF metadata (decode_hf_metadata) ----
+    count = uint32_t(br.read(ceil_log2(uint64_t(w) * hh))) + 1;
+    cw = (w + 7) / 8;
+    chh = (hh + 7) / 8;
     ch.emplace_back(cw, chh, 3, 3);
     ch.emplace_back(cw, chh, 3, 3);
     ch.emplace_back(count, 2);
     ch.emplace_back(w, hh);
-    size_t stream_id = 1 + 2 * size_t(h.num_lf_groups()) + g;
-    decode_modular_subbitstream(ch, stream_id, gt, br);
-    uint32_t cxb = (fs.xb + 7) / 8;
-    for (uint32_t y = 0; y < chh; y++)
-      for (uint32_t x = 0; x < cw; x++) {
-        size_t o = size_t(y0 / 8 + y) * cxb + x0 / 8 + x;
-        fs.ytox_map[o] = int8_t(std::clamp(ch[0].row(y)[x], -128, 127));
-        fs.ytob_map[o] = int8_t(std::clamp(ch[1].row(y)[x], -128, 127));
-      }
-    // EPF sharpness: one pass per row (range check folded into an OR so that the loop vectorises)
-    for (uint32_t y = 0; y < hh; y++) {
-      const int32_t* e = ch[3].row(y);
-      uint8_t* eo = &fs.epf_map[size_t(y0 + y) * fs.xb + x0];
-      int32_t seen = 0;
-      for (uint32_t x = 0; x < w; x++) {
-        seen |= e[x];
-        eo[x] = uint8_t(e[x]);
-      }
-      if (seen & ~7) fail("invalid EPF sharpness value");
-    }
-    // Varblocks in raster order at the first uncovered block (modular/mod.rs:1040-1075)
-    uint32_t num = 0;
-    const int32_t *raw_transforms = ch[2].row(0), *raw_quants = ch[2].row(1);
-    for (uint32_t y = 0; y < hh; y++) {
-      uint8_t* tm = &fs.transform_map[size_t(y0 + y) * fs.xb + x0];
-      int32_t* rq = &fs.raw_quant_map[size_t(y0 + y) * fs.xb + x0];
-      const uint32_t ngy = std::min(hh, (y / 32 + 1) * 32);
-      for (uint32_t x = 0; x < w;) {
-        if (tm[x] != 27) {  // already covered by an earlier varblock
-          x++;
-          continue;
-        }
-        if (num >= count) fail("invalid VarDCT transform map");
-        const int32_t raw_transform = raw_transforms[num];
-        const int32_t raw_quant = 1 + std::clamp(raw_quants[num], 0, 255);
-        if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
-        const uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
-        const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
-        if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
-        num++;
-        for (uint32_t iy = 0; iy < cy; iy++) {
-          uint8_t* t = tm + size_t(iy) * fs.xb + x;
-          int32_t* q = rq + size_t(iy) * fs.xb + x;
-          for (uint32_t ix = 0; ix < cx; ix++) {  // a block covered earlier is overwritten, like mod.rs:1066-1075
-            t[ix] = uint8_t(raw_transform);
-            q[ix] = raw_quant;
-          }
-        }
-        tm[x] |= 128;  // first block of the varblock
-        x += cx;
-      }
-    }
+    ss = std::make_unique<SubStream>();
+    substream_begin(*ss, ch, 1 + 2 * size_t(h.num_lf_groups()) + g, global_tree(), br);
   }
-  br.check();
+
+  // call after the HF-metadata sub-bitstream has been finished
+  void finish_meta() {
+    {
+      uint32_t cxb = (fs.xb + 7) / 8;
+      for (uint32_t y = 0; y < chh; y++)
+        for (uint32_t x = 0; x < cw; x++) {
+          size_t o = size_t(y0 / 8 + y) * cxb + x0 / 8 + x;
+          fs.ytox_map[o] = int8_t(std::clamp(ch[0].row(y)[x], -128, 127));
+          fs.ytob_map[o] = int8_t(std::clamp(ch[1].row(y)[x], -128, 127));
+        }
+      // EPF sharpness: one pass per row (range check folded into an OR so that the loop vectorises)
+      for (uint32_t y = 0; y < hh; y++) {
+        const int32_t* e = ch[3].row(y);
+        uint8_t* eo = &fs.epf_map[size_t(y0 + y) * fs.xb + x0];
+        int32_t seen = 0;
+        for (uint32_t x = 0; x < w; x++) {
+          seen |= e[x];
+          eo[x] = uint8_t(e[x]);
+        }
+        if (seen & ~7) fail("invalid EPF sharpness value");
+      }
+      // Varblocks in raster order at the first uncovered block (modular/mod.rs:1040-1075)
+      uint32_t num = 0;
+      const int32_t *raw_transforms = ch[2].row(0), *raw_quants = ch[2].row(1);
+      for (uint32_t y = 0; y < hh; y++) {
+        uint8_t* tm = &fs.transform_map[size_t(y0 + y) * fs.xb + x0];
+        int32_t* rq = &fs.raw_quant_map[size_t(y0 + y) * fs.xb + x0];
+        const uint32_t ngy = std::min(hh, (y / 32 + 1) * 32);
+        for (uint32_t x = 0; x < w;) {
+          if (tm[x] != 27) {  // already covered by an earlier varblock
+            x++;
+            continue;
+          }
+          if (num >= count) fail("invalid VarDCT transform map");
+          const int32_t raw_transform = raw_transforms[num];
+          const int32_t raw_quant = 1 + std::clamp(raw_quants[num], 0, 255);
+          if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
+          const uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
+          const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
+          if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
+          num++;
+          for (uint32_t iy = 0; iy < cy; iy++) {
+            uint8_t* t = tm + size_t(iy) * fs.xb + x;
+            int32_t* q = rq + size_t(iy) * fs.xb + x;
+            for (uint32_t ix = 0; ix < cx; ix++) {  // a block covered earlier is overwritten, like mod.rs:1066-1075
+              t[ix] = uint8_t(raw_transform);
+              q[ix] = raw_quant;
+            }
+          }
+          tm[x] |= 128;  // first block of the varblock
+          x += cx;
+        }
+      }
+    }
+    ss.reset();
+    br.check();
+  }
+};
+
+// One LF group on its own.
+void decode_lf_group(FrameState& fs, uint32_t g, const uint8_t* data, size_t size) {
+  LfGroupJob job(fs, g, data, size);
+  job.begin_lf();
+  substream_finish(*job.ss);
+  job.finish_lf_begin_meta();
+  substream_finish(*job.ss);
+  job.finish_meta();
+}
+
+// Two LF groups with their sub-bitstreams in lockstep (same results as two decode_lf_group calls).
+void decode_lf_group_pair(FrameState& fs, uint32_t ga, const uint8_t* da, size_t sa, uint32_t gb, const uint8_t* db,
+                          size_t sb) {
+  LfGroupJob a(fs, ga, da, sa), b(fs, gb, db, sb);
+  a.begin_lf();
+  b.begin_lf();
+  decode_substreams_paired(*a.ss, *b.ss);
+  a.finish_lf_begin_meta();
+  b.finish_lf_begin_meta();
+  decode_substreams_paired(*a.ss, *b.ss);
+  a.finish_meta();
+  b.finish_meta();
 }
 
 // frame/decode.rs:506-566
@@ -476,6 +532,8 @@ void adaptive_lf_smoothing(FrameState& fs, int threads) {
 }
 #pragma GCC pop_options
 
+void set_pair_lf_groups(bool on) { g_pair_lf_groups.store(on); }
+
 namespace {
 
 // Pool of the large FrameState buffers (see recycle_frame_state in frame.h).
@@ -571,7 +629,18 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
   if (fs.toc.offsets.size() == 1) {
     BitReader sbr(base + fs.toc.offsets[0], fs.toc.lengths[0]);
     decode_lf_global(fs, sbr);
-    decode_lf_group(fs, 0, sbr);
+    // single-section frames (frame_info.rs:414-450) share one bit stream: the LF group continues where LfGlobal
+    // stopped and HfGlobal continues where the LF group stops
+    {
+      LfGroupJob job(fs, 0, base + fs.toc.offsets[0], fs.toc.lengths[0]);
+      job.br.skip_bits(sbr.total_bits_read());
+      job.begin_lf();
+      substream_finish(*job.ss);
+      job.finish_lf_begin_meta();
+      substream_finish(*job.ss);
+      job.finish_meta();
+      sbr.skip_bits(job.br.total_bits_read() - sbr.total_bits_read());
+    }
     decode_hf_global(fs, sbr);
     // The single HF group follows without alignment: re-pack it byte aligned at the end of the codestream buffer.
     std::vector<uint8_t> packed = repack_bits(base + fs.toc.offsets[0], fs.toc.lengths[0], sbr.total_bits_read());
@@ -586,10 +655,12 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
     const uint32_t nlf = h.num_lf_groups();
     const uint32_t nthreads = std::min<uint32_t>(nlf, uint32_t(std::max(1, threads)));
     if (nthreads <= 1) {
-      for (uint32_t g = 0; g < nlf; g++) {
-        BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
-        decode_lf_group(fs, g, sbr);
-      }
+      // two groups at a time: their Modular sub-bitstreams advance in lockstep (decode_substreams_paired)
+      uint32_t g = 0;
+      for (; g + 1 < nlf && g_pair_lf_groups.load(std::memory_order_relaxed); g += 2)
+        decode_lf_group_pair(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g], g + 1,
+                             base + fs.toc.offsets[2 + g], fs.toc.lengths[2 + g]);
+      for (; g < nlf; g++) decode_lf_group(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
     } else {
       // LF groups are independent sections writing disjoint rectangles of the planes; the error of the lowest
       // failing group is reported, like the serial loop would.
@@ -602,8 +673,7 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
           const uint32_t g = next.fetch_add(1);
           if (g >= nlf) return;
           try {
-            BitReader sbr(base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
-            decode_lf_group(fs, g, sbr);
+            decode_lf_group(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
           } catch (Error& e) {
             std::lock_guard<std::mutex> lock(err_mutex);
             if (g < err_group) {

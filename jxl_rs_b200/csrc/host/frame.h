@@ -105,6 +105,9 @@ void adaptive_lf_smoothing(FrameState& fs, int threads = 1);
 // parsed state does not depend on `threads`.
 std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, int threads = 1);
 
+// Test hook: decode the LF groups of serial parses one at a time instead of in lockstep pairs.
+void set_pair_lf_groups(bool on);
+
 // Destroys a FrameState but keeps its large buffers (codestream copy, LF planes, per-block maps; ~4 MB for a 4K
 // frame) in a bounded process-wide pool that parse_vardct_file draws from: a steady-state decode loop then does no
 // large malloc / free, i.e. no mmap, page-fault and munmap (TLB shoot-down) traffic between the parse threads.

@@ -371,7 +371,7 @@ struct DirectReader {
   // `nsym` more symbols of <= 47 bits can be read with unchecked 8-byte loads.
   inline bool room(size_t nsym) const { return (bitpos >> 3) + nsym * 6 + 16 <= size; }
   template <bool kUnchecked = false>
-  inline uint32_t read_clustered(uint32_t /*cluster*/) {
+  __attribute__((always_inline)) inline uint32_t read_clustered(uint32_t /*cluster*/) {
     uint64_t w;
     const size_t byte = bitpos >> 3;
     if (kUnchecked || byte + 8 <= size) {
@@ -425,6 +425,44 @@ static void build_direct_tables(const EntropyCode& code, uint32_t cluster, uint3
   }
 }
 
+// Row segments shared by the single-stream and the paired static-leaf decoders. `kU`: refills without the
+// end-of-data test (the caller checked room() for the segment).
+struct GradState {
+  __m128i left, topleft;
+};
+
+// Gradient predictor, y > 0, columns [x0, x1) of one row; same arithmetic as decode_static_leaf's gradient_row.
+template <bool kU, class R>
+__attribute__((always_inline)) inline void grad_segment(R& rd, uint32_t cluster, uint32_t uoff, uint32_t umul,
+                                                        int32_t* row, const int32_t* top_row, size_t x0, size_t x1,
+                                                        GradState& s) {
+  for (size_t x = x0; x < x1; x++) {
+    const __m128i top = _mm_cvtsi32_si128(top_row[x]);
+    const uint32_t res = uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
+    const __m128i add = _mm_cvtsi32_si128(int32_t(uoff + umul * res));
+    const __m128i mn = _mm_min_epi32(s.left, top), mx = _mm_max_epi32(s.left, top);
+    __m128i g = _mm_sub_epi32(_mm_add_epi32(s.left, top), s.topleft);
+    g = _mm_blendv_epi8(g, mx, _mm_cmpgt_epi32(mn, s.topleft));
+    g = _mm_blendv_epi8(g, mn, _mm_cmpgt_epi32(s.topleft, mx));
+    s.left = _mm_add_epi32(g, add);
+    row[x] = _mm_cvtsi128_si32(s.left);
+    s.topleft = top;
+  }
+}
+
+// Zero / West predictor (and Gradient on the first row): value = (left & keep) + offset + mul * residual.
+template <bool kU, class R>
+__attribute__((always_inline)) inline void west_segment(R& rd, uint32_t cluster, uint32_t uoff, uint32_t umul,
+                                                        uint32_t keep, int32_t* row, size_t x0, size_t x1,
+                                                        uint32_t& left) {
+  for (size_t x = x0; x < x1; x++) {
+    left = (left & keep) + uoff + umul * uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
+    row[x] = int32_t(left);
+  }
+}
+
+constexpr size_t kRowChunk = 512;  // room() is decided per chunk of columns, so long rows need no whole-row slack
+
 // Only channel / stream id are tested by the tree: one leaf (predictor, offset, multiplier, cluster) for the
 // whole channel, so the symbol chain is independent of the sample values.
 template <class R>
@@ -434,51 +472,33 @@ static void decode_static_leaf(ModularChannel& ch, const TreeNode* nd, uint32_t 
   const uint32_t pred = nd->left;
   const int64_t offset = nd->val, mul = nd->right;
   const uint32_t uoff = uint32_t(offset), umul = uint32_t(mul);
-  // One row of the Gradient predictor, y > 0. `unchecked` rows (all but the last few of a section) refill the bit
-  // window without the end-of-data test, which keeps the byte-wise tail path out of the loop body.
-  // clamped_gradient runs on xmm scalars: its selects depend only on i32 comparisons of left / top / topleft, and
-  // left + top - topleft is exact in wrapping i32 whenever it is the selected value (it then lies between left and
-  // top). That keeps the serial left -> left chain free of (unpredictable) branches and out of the general-purpose
-  // registers the symbol reader needs.
-  auto gradient_row = [&](auto unchecked, int32_t* row, const int32_t* top_row) {
-    constexpr bool kU = decltype(unchecked)::value;
-    __m128i left = _mm_cvtsi32_si128(top_row[0]), topleft = left;  // x = 0: left = topleft = top_row[0]
-    for (size_t x = 0; x < w; x++) {
-      const __m128i top = _mm_cvtsi32_si128(top_row[x]);
-      const uint32_t res = uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
-      const __m128i add = _mm_cvtsi32_si128(int32_t(uoff + umul * res));
-      const __m128i mn = _mm_min_epi32(left, top), mx = _mm_max_epi32(left, top);
-      __m128i g = _mm_sub_epi32(_mm_add_epi32(left, top), topleft);
-      g = _mm_blendv_epi8(g, mx, _mm_cmpgt_epi32(mn, topleft));  // topleft < min -> max
-      g = _mm_blendv_epi8(g, mn, _mm_cmpgt_epi32(topleft, mx));  // topleft > max -> min
-      left = _mm_add_epi32(g, add);
-      row[x] = _mm_cvtsi128_si32(left);
-      topleft = top;
-    }
-  };
-  // One row of a predictor that only looks at the left neighbour (West; also Gradient on the first row, where
-  // top = topleft = left, predict.rs:64-103) or at nothing (Zero).
-  auto west_row = [&](auto unchecked, int32_t* row, uint32_t left, uint32_t keep) {
-    constexpr bool kU = decltype(unchecked)::value;
-    for (size_t x = 0; x < w; x++) {
-      left = (left & keep) + uoff + umul * uint32_t(unpack_signed(rd.template read_clustered<kU>(cluster)));
-      row[x] = int32_t(left);
-    }
-  };
   auto next_signed = [&]() { return int64_t(unpack_signed(rd.read_clustered(cluster))); };
   for (size_t y = 0; y < h; y++) {
     int32_t* row = ch.row(uint32_t(y));
     const int32_t* top_row = y > 0 ? ch.row(uint32_t(y - 1)) : row;
     const int32_t* toptop_row = y > 1 ? ch.row(uint32_t(y - 2)) : top_row;
-    const bool fast = rd.room(w);
     if (pred == kZero || pred == kWest || (pred == kGradient && y == 0)) {
+      // predictors that only look at the left neighbour (West; Gradient on the first row, where top = topleft =
+      // left, predict.rs:64-103) or at nothing (Zero)
       const uint32_t keep = pred == kZero ? 0u : ~0u;
-      const uint32_t left0 = y > 0 ? uint32_t(top_row[0]) : 0u;  // x = 0: left = top_row[0], or 0 at the origin
-      if (fast) west_row(std::true_type(), row, left0, keep);
-      else west_row(std::false_type(), row, left0, keep);
+      uint32_t left = y > 0 ? uint32_t(top_row[0]) : 0u;  // x = 0: left = top_row[0], or 0 at the origin
+      for (size_t c0 = 0; c0 < w; c0 += kRowChunk) {
+        const size_t c1 = std::min(w, c0 + kRowChunk);
+        if (rd.room(c1 - c0)) west_segment<true>(rd, cluster, uoff, umul, keep, row, c0, c1, left);
+        else west_segment<false>(rd, cluster, uoff, umul, keep, row, c0, c1, left);
+      }
     } else if (pred == kGradient) {
-      if (fast) gradient_row(std::true_type(), row, top_row);
-      else gradient_row(std::false_type(), row, top_row);
+      // clamped_gradient on xmm scalars: its selects depend only on i32 comparisons of left / top / topleft, and
+      // left + top - topleft is exact in wrapping i32 whenever it is the selected value (it then lies between left
+      // and top): the serial left -> left chain has no (unpredictable) branches and stays out of the general-purpose
+      // registers the symbol reader needs.
+      GradState gs;
+      gs.left = gs.topleft = _mm_cvtsi32_si128(top_row[0]);  // x = 0: left = topleft = top_row[0]
+      for (size_t c0 = 0; c0 < w; c0 += kRowChunk) {
+        const size_t c1 = std::min(w, c0 + kRowChunk);
+        if (rd.room(c1 - c0)) grad_segment<true>(rd, cluster, uoff, umul, row, top_row, c0, c1, gs);
+        else grad_segment<false>(rd, cluster, uoff, umul, row, top_row, c0, c1, gs);
+      }
     } else {
       for (size_t x = 0; x < w; x++) {
         Neigh n = get_neigh(row, top_row, toptop_row, x, y, w);
@@ -645,6 +665,46 @@ static void with_reader(SymbolReader& reader, BitReader& br, F&& f) {
 static std::atomic<bool> g_force_generic_walk{false};
 void set_force_generic_walk(bool on) { g_force_generic_walk.store(on); }
 
+// Where the per-pixel walk of one channel starts and what it needs.
+struct ChannelPlan {
+  const TreeNode* root;
+  uint32_t used_mask;  // properties 0..15 tested below root
+  bool wide_props, sub_wp;
+};
+static ChannelPlan plan_channel(const ModularTree& tree, size_t ci, size_t stream_id) {
+  const TreeNode* nodes = tree.nodes.data();
+  // Static prefix: nodes that split on the channel index / stream id have one outcome for the whole channel
+  // (libjxl's global trees start with such a chain), so the walk can start below them.
+  const TreeNode* root = nodes;
+  while (root->property == 0 || root->property == 1) {
+    const int32_t v = root->property == 0 ? int32_t(ci) : int32_t(stream_id);
+    root = nodes + (v > root->val ? root->left : root->right);
+  }
+  // Which properties and predictors does the subtree under `root` use?
+  ChannelPlan p{root, 0, false, false};
+  std::vector<const TreeNode*> stack{root};
+  while (!stack.empty()) {
+    const TreeNode* nd = stack.back();
+    stack.pop_back();
+    if (nd->property < 0) {
+      if (nd->left == kWeighted) p.sub_wp = true;
+      continue;
+    }
+    if (nd->property < 16) p.used_mask |= 1u << nd->property;
+    else p.wide_props = true;
+    if (nd->property == 15) p.sub_wp = true;
+    stack.push_back(nodes + nd->left);
+    stack.push_back(nodes + nd->right);
+  }
+  return p;
+}
+
+// A channel the direct-table reader takes: one leaf, one ANS cluster, big enough to pay for the table.
+static bool direct_eligible(const ChannelPlan& plan, const SymbolReader& reader, const ModularChannel& ch) {
+  return !g_force_generic_walk.load(std::memory_order_relaxed) && plan.root->property < 0 && !plan.sub_wp &&
+         reader.can_localise() && !reader.uses_prefix() && size_t(ch.w) * ch.h >= 8192;
+}
+
 static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_t stream_id, const GroupHeader& header,
                            const ModularTree& tree, SymbolReader& reader, BitReader& br) {
   ModularChannel& ch = *chans[ci];
@@ -658,35 +718,15 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
   const TreeNode* nodes = tree.nodes.data();
   // ---- specialised walks (same semantics as the generic loop below; the reference keeps a family of these in
   // decode/specialized_trees.rs).
-  // Static prefix: nodes that split on the channel index / stream id have one outcome for the whole channel
-  // (libjxl's global trees start with such a chain), so the walk can start below them.
-  const TreeNode* root = nodes;
-  while (root->property == 0 || root->property == 1)
-    root = nodes + (props[root->property] > root->val ? root->left : root->right);
-  // Which properties and predictors does the subtree under `root` use?
-  uint32_t used_mask = 0;
-  bool wide_props = false, sub_wp = false;
-  {
-    std::vector<const TreeNode*> stack{root};
-    while (!stack.empty()) {
-      const TreeNode* nd = stack.back();
-      stack.pop_back();
-      if (nd->property < 0) {
-        if (nd->left == kWeighted) sub_wp = true;
-        continue;
-      }
-      if (nd->property < 16) used_mask |= 1u << nd->property;
-      else wide_props = true;
-      if (nd->property == 15) sub_wp = true;
-      stack.push_back(nodes + nd->left);
-      stack.push_back(nodes + nd->right);
-    }
-  }
+  const ChannelPlan plan = plan_channel(tree, ci, stream_id);
+  const TreeNode* root = plan.root;
+  const uint32_t used_mask = plan.used_mask;
+  const bool wide_props = plan.wide_props, sub_wp = plan.sub_wp;
   const bool specialise = !g_force_generic_walk.load(std::memory_order_relaxed);
   if (specialise && root->property < 0 && !sub_wp) {
     const TreeNode* nd = root;
     const uint32_t cluster = tree.code.context_map[nd->ctx];  // one leaf -> one cluster for the whole channel
-    if (reader.can_localise() && !reader.uses_prefix() && w * h >= 8192) {
+    if (direct_eligible(plan, reader, ch)) {
       // big channel, one ANS cluster: direct table (its 4096-entry build is < 1 % of the channel)
       uint32_t tab[4096];
       uint64_t tok_tab[256];
@@ -790,6 +830,203 @@ static void decode_channel(std::vector<ModularChannel*>& chans, size_t ci, size_
     }
   }
   br.check();
+}
+
+// ---------------------------------------------------------------------------
+// Two static-leaf channels of two independent sub-bitstreams in lockstep
+// ---------------------------------------------------------------------------
+
+namespace {
+
+struct LeafChannel {  // one static-leaf channel being decoded by decode_static_leaf_pair
+  ModularChannel* ch;
+  uint32_t pred, uoff, umul;
+  // row kind: 0 = west-like (Zero, West, Gradient on row 0), 1 = Gradient with a row above
+  int kind(size_t y) const { return (pred == kGradient && y > 0) ? 1 : 0; }
+  uint32_t keep() const { return pred == kZero ? 0u : ~0u; }
+};
+
+}  // namespace
+
+// Both channels are direct-table channels with predictor Zero, West or Gradient. Rows advance in lockstep; where both
+// rows are of the same kind and far enough from the end of their sections for unchecked refills, the two symbol
+// chains share one loop body (the second stream costs ~6 instead of ~19 cycles per symbol); everything else — row
+// tails, rows of different kinds, the last rows of a section — takes the single-stream segments.
+__attribute__((noinline)) static void decode_static_leaf_pair(const LeafChannel& A, DirectReader& ioA, const LeafChannel& B,
+                                                            DirectReader& ioB) {
+  DirectReader ra = ioA, rb = ioB;  // true locals: both readers stay in registers
+  const size_t wA = A.ch->w, hA = A.ch->h, wB = B.ch->w, hB = B.ch->h;
+  auto single_row = [&](const LeafChannel& L, DirectReader& rd, size_t y) __attribute__((always_inline)) {
+    const size_t w = L.ch->w;
+    int32_t* row = L.ch->row(uint32_t(y));
+    const int32_t* top_row = y > 0 ? L.ch->row(uint32_t(y - 1)) : row;
+    GradState s;
+    s.left = s.topleft = _mm_cvtsi32_si128(top_row[0]);
+    uint32_t left = y > 0 ? uint32_t(top_row[0]) : 0u;
+    for (size_t c0 = 0; c0 < w; c0 += kRowChunk) {
+      const size_t c1 = std::min(w, c0 + kRowChunk);
+      const bool fast = rd.room(c1 - c0);
+      if (L.kind(y) == 1) {
+        if (fast) grad_segment<true>(rd, 0, L.uoff, L.umul, row, top_row, c0, c1, s);
+        else grad_segment<false>(rd, 0, L.uoff, L.umul, row, top_row, c0, c1, s);
+      } else {
+        if (fast) west_segment<true>(rd, 0, L.uoff, L.umul, L.keep(), row, c0, c1, left);
+        else west_segment<false>(rd, 0, L.uoff, L.umul, L.keep(), row, c0, c1, left);
+      }
+    }
+  };
+  // Rows are walked in chunks of kChunk columns: "enough input left for unchecked refills" is decided per chunk, so a
+  // very long row (the 2 x count channel of the HF metadata) does not need its whole length of slack.
+  constexpr size_t kChunk = kRowChunk;
+  const size_t hmax = std::max(hA, hB);
+  for (size_t y = 0; y < hmax; y++) {
+    const bool inA = y < hA, inB = y < hB;
+    if (inA && inB && A.kind(y) == B.kind(y)) {
+      int32_t* rowA = A.ch->row(uint32_t(y));
+      int32_t* rowB = B.ch->row(uint32_t(y));
+      const int32_t* topA = y > 0 ? A.ch->row(uint32_t(y - 1)) : rowA;
+      const int32_t* topB = y > 0 ? B.ch->row(uint32_t(y - 1)) : rowB;
+      const size_t n = std::min(wA, wB);
+      const bool grad = A.kind(y) == 1;
+      GradState sa, sb;
+      sa.left = sa.topleft = _mm_cvtsi32_si128(topA[0]);
+      sb.left = sb.topleft = _mm_cvtsi32_si128(topB[0]);
+      uint32_t la = y > 0 ? uint32_t(topA[0]) : 0u, lb = y > 0 ? uint32_t(topB[0]) : 0u;
+      const uint32_t ka = A.keep(), kb = B.keep();
+      // columns [x0, x1) of stream L alone
+      auto alone = [&](const LeafChannel& L, DirectReader& rd, int32_t* row, const int32_t* top, size_t x0, size_t x1,
+                       GradState& gs, uint32_t& left, uint32_t keep) __attribute__((always_inline)) {
+        for (size_t c0 = x0; c0 < x1; c0 += kChunk) {
+          const size_t c1 = std::min(x1, c0 + kChunk);
+          const bool fast = rd.room(c1 - c0);
+          if (grad) {
+            if (fast) grad_segment<true>(rd, 0, L.uoff, L.umul, row, top, c0, c1, gs);
+            else grad_segment<false>(rd, 0, L.uoff, L.umul, row, top, c0, c1, gs);
+          } else {
+            if (fast) west_segment<true>(rd, 0, L.uoff, L.umul, keep, row, c0, c1, left);
+            else west_segment<false>(rd, 0, L.uoff, L.umul, keep, row, c0, c1, left);
+          }
+        }
+      };
+      for (size_t c0 = 0; c0 < n; c0 += kChunk) {
+        const size_t c1 = std::min(n, c0 + kChunk);
+        if (ra.room(c1 - c0) && rb.room(c1 - c0)) {
+          if (grad) {
+            for (size_t x = c0; x < c1; x++) {  // one body, two independent chains
+              grad_segment<true>(ra, 0, A.uoff, A.umul, rowA, topA, x, x + 1, sa);
+              grad_segment<true>(rb, 0, B.uoff, B.umul, rowB, topB, x, x + 1, sb);
+            }
+          } else {
+            for (size_t x = c0; x < c1; x++) {
+              west_segment<true>(ra, 0, A.uoff, A.umul, ka, rowA, x, x + 1, la);
+              west_segment<true>(rb, 0, B.uoff, B.umul, kb, rowB, x, x + 1, lb);
+            }
+          }
+        } else {
+          alone(A, ra, rowA, topA, c0, c1, sa, la, ka);
+          alone(B, rb, rowB, topB, c0, c1, sb, lb, kb);
+        }
+      }
+      alone(A, ra, rowA, topA, n, wA, sa, la, ka);
+      alone(B, rb, rowB, topB, n, wB, sb, lb, kb);
+    } else {
+      if (inA) single_row(A, ra, y);
+      if (inB) single_row(B, rb, y);
+    }
+  }
+  ioA = ra;
+  ioB = rb;
+}
+
+SubStream::~SubStream() { delete reader; }
+
+void substream_begin(SubStream& s, std::vector<ModularChannel>& channels, size_t stream_id,
+                     const ModularTree* global_tree, BitReader& br) {
+  s.channels = &channels;
+  s.stream_id = stream_id;
+  s.br = &br;
+  s.empty = true;
+  for (auto& c : channels)
+    if (c.w && c.h) s.empty = false;
+  if (s.empty) return;
+  s.header = GroupHeader::read(br);
+  uint32_t nb_meta = 0;
+  meta_apply_transforms(channels, nb_meta, s.header);
+  s.tree = global_tree;
+  if (!s.header.use_global_tree) {
+    size_t samples = 0;
+    for (auto& c : channels) samples += size_t(c.w) * c.h;
+    s.local = ModularTree::read(br, std::min<size_t>(1024 + samples, 1u << 20));
+    s.tree = &s.local;
+  } else if (!global_tree) {
+    fail("no global MA tree");
+  }
+  for (auto& c : channels) s.ptrs.push_back(&c);
+  size_t image_width = 0;
+  for (auto* c : s.ptrs) image_width = std::max<size_t>(image_width, c->w);
+  s.reader = new SymbolReader(s.tree->code, br, image_width);
+  s.next = 0;
+}
+
+// Skips empty channels; false when none is left.
+static bool substream_has_channel(SubStream& s) {
+  if (s.empty) return false;
+  while (s.next < s.ptrs.size() && (s.ptrs[s.next]->w == 0 || s.ptrs[s.next]->h == 0)) s.next++;
+  return s.next < s.ptrs.size();
+}
+
+static void substream_decode_next(SubStream& s) {
+  decode_channel(s.ptrs, s.next, s.stream_id, s.header, *s.tree, *s.reader, *s.br);
+  s.next++;
+}
+
+void substream_finish(SubStream& s) {
+  if (s.empty) return;
+  while (substream_has_channel(s)) substream_decode_next(s);
+  s.reader->check_final_state(*s.br);
+  undo_transforms(*s.channels, s.header, 8);
+}
+
+void decode_substreams_paired(SubStream& a, SubStream& b) {
+  for (;;) {
+    const bool ha = substream_has_channel(a), hb = substream_has_channel(b);
+    if (!ha || !hb) break;
+    ModularChannel& ca = *a.ptrs[a.next];
+    ModularChannel& cb = *b.ptrs[b.next];
+    const ChannelPlan pa = plan_channel(*a.tree, a.next, a.stream_id), pb = plan_channel(*b.tree, b.next, b.stream_id);
+    auto pairable = [](const ChannelPlan& p, const SymbolReader& r, const ModularChannel& c) {
+      return direct_eligible(p, r, c) && (p.root->left == kZero || p.root->left == kWest || p.root->left == kGradient);
+    };
+    const bool ea = pairable(pa, *a.reader, ca), eb = pairable(pb, *b.reader, cb);
+    if (ea && eb) {
+      uint32_t tab_a[4096], tab_b[4096];
+      uint64_t tok_a[256], tok_b[256];
+      const uint32_t cla = a.tree->code.context_map[pa.root->ctx], clb = b.tree->code.context_map[pb.root->ctx];
+      build_direct_tables(a.tree->code, cla, tab_a, tok_a);
+      build_direct_tables(b.tree->code, clb, tab_b, tok_b);
+      DirectReader da{a.br->data(), a.br->size_bytes(), a.br->bit_pos(), a.reader->ans_state(), tab_a, tok_a,
+                      a.tree->code.uint_configs[cla].lsb};
+      DirectReader db{b.br->data(), b.br->size_bytes(), b.br->bit_pos(), b.reader->ans_state(), tab_b, tok_b,
+                      b.tree->code.uint_configs[clb].lsb};
+      const LeafChannel la{&ca, pa.root->left, uint32_t(pa.root->val), pa.root->right};
+      const LeafChannel lb{&cb, pb.root->left, uint32_t(pb.root->val), pb.root->right};
+      decode_static_leaf_pair(la, da, lb, db);
+      a.reader->set_ans_state(da.state);
+      a.br->seek_bits(da.bitpos);
+      b.reader->set_ans_state(db.state);
+      b.br->seek_bits(db.bitpos);
+      a.br->check();
+      b.br->check();
+      a.next++;
+      b.next++;
+    } else {
+      // not a pair: let the stream(s) with an ordinary channel catch up, then look again
+      if (!ea) substream_decode_next(a);
+      if (!eb) substream_decode_next(b);
+    }
+  }
+  substream_finish(a);
+  substream_finish(b);
 }
 
 void decode_modular_channels(std::vector<ModularChannel*>& channels, size_t stream_id, const GroupHeader& header,
@@ -1106,27 +1343,9 @@ void undo_transforms(std::vector<ModularChannel>& ch, const GroupHeader& header,
 
 void decode_modular_subbitstream(std::vector<ModularChannel>& channels, size_t stream_id,
                                  const ModularTree* global_tree, BitReader& br) {
-  bool empty = true;
-  for (auto& c : channels)
-    if (c.w && c.h) empty = false;
-  if (empty) return;
-  GroupHeader header = GroupHeader::read(br);
-  uint32_t nb_meta = 0;
-  meta_apply_transforms(channels, nb_meta, header);
-  ModularTree local;
-  const ModularTree* tree = global_tree;
-  if (!header.use_global_tree) {
-    size_t samples = 0;
-    for (auto& c : channels) samples += size_t(c.w) * c.h;
-    local = ModularTree::read(br, std::min<size_t>(1024 + samples, 1u << 20));
-    tree = &local;
-  } else if (!global_tree) {
-    fail("no global MA tree");
-  }
-  std::vector<ModularChannel*> ptrs;
-  for (auto& c : channels) ptrs.push_back(&c);
-  decode_modular_channels(ptrs, stream_id, header, *tree, br);
-  undo_transforms(channels, header, 8);
+  SubStream s;
+  substream_begin(s, channels, stream_id, global_tree, br);
+  substream_finish(s);
 }
 
 }  // namespace jxg

@@ -108,6 +108,32 @@ struct WpState {
 void decode_modular_subbitstream(std::vector<ModularChannel>& channels, size_t stream_id,
                                  const ModularTree* global_tree, BitReader& br);
 
+// One sub-bitstream decoded channel by channel, so that two independent sub-bitstreams (the LF image or the HF
+// metadata of two LF groups) can advance in lockstep: a big static-leaf ANS channel is one serial dependency chain per
+// stream, and a core has issue slots for two of them (decode_substreams_paired). begin + finish is
+// decode_modular_subbitstream. A SubStream must stay where it is between begin and finish.
+class SymbolReader;
+struct SubStream {
+  SubStream() = default;
+  SubStream(const SubStream&) = delete;
+  SubStream& operator=(const SubStream&) = delete;
+  ~SubStream();
+  std::vector<ModularChannel>* channels = nullptr;
+  size_t stream_id = 0;
+  BitReader* br = nullptr;
+  bool empty = true;
+  GroupHeader header;
+  ModularTree local;
+  const ModularTree* tree = nullptr;
+  SymbolReader* reader = nullptr;  // owned
+  std::vector<ModularChannel*> ptrs;
+  size_t next = 0;  // next channel to decode
+};
+void substream_begin(SubStream& s, std::vector<ModularChannel>& channels, size_t stream_id,
+                     const ModularTree* global_tree, BitReader& br);
+void substream_finish(SubStream& s);  // remaining channels, final-state check, inverse local transforms
+void decode_substreams_paired(SubStream& a, SubStream& b);  // all remaining channels of both
+
 // Pieces used by the Modular-frame path (global image split over groups).
 // allocate = false: only channel shapes are tracked (planes stay empty; Modular-frame front end).
 void meta_apply_transforms(std::vector<ModularChannel>& channels, uint32_t& nb_meta, GroupHeader& header,

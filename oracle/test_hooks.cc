@@ -179,4 +179,7 @@ uint64_t jxo_t_parse_digest(const uint8_t* data, size_t size, int threads) {
     return 0;
   }
 }
+
+// 0: serial parses decode their LF groups one at a time instead of in lockstep pairs (differential tests).
+void jxo_t_pair_lf_groups(int on) { set_pair_lf_groups(on != 0); }
 }

@@ -226,6 +226,21 @@ def test_multithreaded_lf_groups_give_the_same_parse():
         assert lib.jxo_t_parse_digest(f, len(f), threads) == ref_f
         assert lib.jxo_t_parse_digest(g, len(g), threads) == ref_g
     assert lib.jxo_t_parse_digest(f, len(f), 1) == ref_f
+    # serial parses pair LF groups (two sub-bitstreams in lockstep through the direct-table reader): the same state as
+    # one group at a time, for plain and for libjxl-like (weighted-predictor, i.e. unpairable) LF coding, and for a
+    # frame whose paired groups have different widths and heights
+    for data in (f, g, synth.encode_synthetic(4200, 2100, 99, 0.7, 2, 1, 1, lf_tree=1),
+                 synth.encode_synthetic(2048 + 8 * 9, 2048 + 8 * 3, 7, 0.7, 2, 1, 0)):
+        paired = lib.jxo_t_parse_digest(data, len(data), 1)
+        try:
+            lib.jxo_t_pair_lf_groups(0)
+            single = lib.jxo_t_parse_digest(data, len(data), 1)
+            lib.jxo_t_force_generic_walk(1)
+            generic = lib.jxo_t_parse_digest(data, len(data), 1)
+        finally:
+            lib.jxo_t_pair_lf_groups(1)
+            lib.jxo_t_force_generic_walk(0)
+        assert paired != 0 and paired == single == generic
     bad = bytearray(f)
     bad[len(f) // 40] ^= 0x55  # inside the LF-group sections (they come first and are ~5 % of the file)
     bad = bytes(bad)
