@@ -669,11 +669,16 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
       uint32_t err_group = UINT32_MAX;
       std::unique_ptr<Error> err;
       auto work = [&] {
+        const bool pair = g_pair_lf_groups.load(std::memory_order_relaxed) && nlf >= 4 * nthreads;
         for (;;) {
-          const uint32_t g = next.fetch_add(1);
+          const uint32_t g = next.fetch_add(pair ? 2 : 1);
           if (g >= nlf) return;
           try {
-            decode_lf_group(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
+            if (pair && g + 1 < nlf)
+              decode_lf_group_pair(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g], g + 1,
+                                   base + fs.toc.offsets[2 + g], fs.toc.lengths[2 + g]);
+            else
+              decode_lf_group(fs, g, base + fs.toc.offsets[1 + g], fs.toc.lengths[1 + g]);
           } catch (Error& e) {
             std::lock_guard<std::mutex> lock(err_mutex);
             if (g < err_group) {

@@ -241,6 +241,9 @@ def test_multithreaded_lf_groups_give_the_same_parse():
             lib.jxo_t_pair_lf_groups(1)
             lib.jxo_t_force_generic_walk(0)
         assert paired != 0 and paired == single == generic
+    # many LF groups per thread: the worker threads take them in lockstep pairs too (10 groups, 2 threads)
+    wide = synth.encode_synthetic(8200, 2056, 3, 1.5, 2, 1, 0)
+    assert lib.jxo_t_parse_digest(wide, len(wide), 2) == lib.jxo_t_parse_digest(wide, len(wide), 1) != 0
     bad = bytearray(f)
     bad[len(f) // 40] ^= 0x55  # inside the LF-group sections (they come first and are ~5 % of the file)
     bad = bytes(bad)
