@@ -322,6 +322,12 @@ struct LfGroupJob {
           const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
           if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
           num++;
+          if ((cx | cy) == 1) {  // the 8x8-class transforms (most varblocks): no loops with data-dependent trip counts
+            tm[x] = uint8_t(raw_transform) | 128;
+            rq[x] = raw_quant;
+            x++;
+            continue;
+          }
           for (uint32_t iy = 0; iy < cy; iy++) {
             uint8_t* t = tm + size_t(iy) * fs.xb + x;
             int32_t* q = rq + size_t(iy) * fs.xb + x;
