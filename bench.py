@@ -290,24 +290,40 @@ def main():
     outs = [[(o.data_ptr(), fr.width * 3) for o, fr in zip(ho, frames)] for ho in host_out]
     del frames
     ctx.close()
-    dec = j.PipelinedDecoder(local_rank, depth=2, workers=min(64, rank_cores()), staging_threads=max(2, min(4, rank_cores() // 4)))
-    for i in range(max(3, min(args.warmup, 3))):
-        dec.submit(files, outs[i % 2], abi.FORMAT_RGB_U8)
-    dec.drain()
+    # A failure of the end-to-end leg must not lose the device-resident measurement (nor dead-lock the other ranks at
+    # a barrier): it is reported as e2e.value = null with the error text.
+    e2e_err, dec, e2e_sec, h2d, d2h = None, None, float("nan"), 0, 0
+    try:
+        dec = j.PipelinedDecoder(local_rank, depth=2, workers=min(64, rank_cores()), staging_threads=max(2, min(4, rank_cores() // 4)))
+        for i in range(max(3, min(args.warmup, 3))):
+            dec.submit(files, outs[i % 2], abi.FORMAT_RGB_U8)
+        dec.drain()
+    except Exception as e:  # noqa: BLE001
+        e2e_err = e
     barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        dec.submit(files, outs[i % 2], abi.FORMAT_RGB_U8)
-    dec.drain()
-    torch.cuda.synchronize()
-    e2e_sec = time.perf_counter() - t0
-    h2d, d2h = dec.last_stats["h2d_bytes"], dec.last_stats["d2h_bytes"]
+    if e2e_err is None:
+        try:
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                dec.submit(files, outs[i % 2], abi.FORMAT_RGB_U8)
+            dec.drain()
+            torch.cuda.synchronize()
+            e2e_sec = time.perf_counter() - t0
+            h2d, d2h = dec.last_stats["h2d_bytes"], dec.last_stats["d2h_bytes"]
+        except Exception as e:  # noqa: BLE001
+            e2e_err = e
     barrier()
-    t = torch.tensor([e2e_sec], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t = torch.tensor([0.0 if e2e_err is not None else e2e_sec, 1.0 if e2e_err is not None else 0.0], dtype=torch.float64,
+                     device=f"cuda:{local_rank}")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sec_max = float(t.item())
-    dec.close()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank; and "did any rank fail"
+    e2e_sec_max, any_failed = float(t[0].item()), float(t[1].item()) > 0
+    if dec is not None:
+        try:
+            dec.close()
+        except Exception as e:  # noqa: BLE001
+            e2e_err = e2e_err or e
+    e2e_ok = not any_failed and e2e_sec_max > 0
 
     if rank == 0:
         peaks = {}
@@ -352,8 +368,10 @@ def main():
                          "kernel_ms": dom_ms},
             "cpu_baseline": {"value": cpu_v, "unit": "MP/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} frames of {args.width}x{args.height}, oracle port, {cpu_sec:.1f} s"},
-            "e2e": {"value": mp_per_step * world * args.steps / e2e_sec_max, "unit": "MP/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec_max / args.steps * 1e3},
+            "e2e": ({"value": mp_per_step * world * args.steps / e2e_sec_max, "unit": "MP/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec_max / args.steps * 1e3} if e2e_ok else
+                    {"value": None, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "error": repr(e2e_err) if e2e_err else "end-to-end leg failed on another rank"}),
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }
