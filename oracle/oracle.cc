@@ -732,59 +732,65 @@ void epf(int stage, const JxgFrameDesc& d, const Geometry& geo, const std::vecto
   // reference sums the 5 plus-shaped positions top, left, centre, right, bottom.
   static const int kPlusOrder[5][2] = {{0, -1}, {-1, 0}, {0, 0}, {1, 0}, {0, 1}};
   (void)kPlus;
+  // One pixel; `at(c, x, y)` reads the input with whole-image mirroring (SimpleRenderPipeline semantics) or, for
+  // pixels whose 7x7 neighbourhood lies inside the image, directly — the arithmetic and its order are the same.
+  auto pixel = [&](ptrdiff_t x, ptrdiff_t y, auto&& at) __attribute__((always_inline)) {
+    float inv_sigma_px = sigma[size_t(y / 8) * geo.xb + size_t(x / 8)];
+    if (inv_sigma_px < kMinSigma) {
+      for (int c = 0; c < 3; c++) out.p[c][size_t(y) * out.stride + size_t(x)] = at(c, x, y);
+      return;
+    }
+    bool border = (y % 8 == 0 || y % 8 == 7) || (x % 8 == 0 || x % 8 == 7);
+    float inv_s = inv_sigma_px * (border ? bsm : sm);
+    if (stage == 2) {  // epf2.rs:53-125
+      float cc[3] = {at(0, x, y), at(1, x, y), at(2, x, y)};
+      float wacc = 1.0f, acc[3] = {cc[0], cc[1], cc[2]};
+      for (auto& o : kOff1) {
+        float nb[3] = {at(0, x + o[0], y + o[1]), at(1, x + o[0], y + o[1]), at(2, x + o[0], y + o[1])};
+        float sad = std::fmaf(std::fabs(nb[0] - cc[0]), d.epf_channel_scale[0],
+                              std::fmaf(std::fabs(nb[1] - cc[1]), d.epf_channel_scale[1],
+                                        std::fabs(nb[2] - cc[2]) * d.epf_channel_scale[2]));
+        float wt = std::max(std::fmaf(sad, inv_s, 1.0f), 0.0f);
+        wacc += wt;
+        for (int c = 0; c < 3; c++) acc[c] = std::fmaf(wt, nb[c], acc[c]);
+      }
+      float inv_w = 1.0f / wacc;
+      for (int c = 0; c < 3; c++) out.p[c][size_t(y) * out.stride + size_t(x)] = acc[c] * inv_w;
+      return;
+    }
+    const int n = stage == 0 ? 12 : 4;
+    const int(*off)[2] = stage == 0 ? kOff0 : kOff1;
+    float sads[12];
+    for (int k = 0; k < n; k++) sads[k] = 0.0f;
+    for (int c = 0; c < 3; c++) {
+      float scale = d.epf_channel_scale[c];
+      for (int k = 0; k < n; k++) {
+        float s = 0.0f;
+        for (auto& pl : kPlusOrder)
+          s += std::fabs(at(c, x + pl[0], y + pl[1]) - at(c, x + pl[0] + off[k][0], y + pl[1] + off[k][1]));
+        sads[k] = std::fmaf(scale, s, sads[k]);
+      }
+    }
+    float wsum = 1.0f;
+    for (int k = 0; k < n; k++) {
+      sads[k] = std::max(std::fmaf(sads[k], inv_s, 1.0f), 0.0f);
+      wsum += sads[k];
+    }
+    float inv_w = 1.0f / wsum;
+    for (int c = 0; c < 3; c++) {
+      float o = at(c, x, y);
+      for (int k = n - 1; k >= 0; k--) o = std::fmaf(at(c, x + off[k][0], y + off[k][1]), sads[k], o);
+      out.p[c][size_t(y) * out.stride + size_t(x)] = o * inv_w;
+    }
+  };
+  auto at_mirror = [&](int c, ptrdiff_t xx, ptrdiff_t yy) { return in.p[c][mirror(yy, h) * in.stride + mirror(xx, w)]; };
+  auto at_direct = [&](int c, ptrdiff_t xx, ptrdiff_t yy) { return in.p[c][size_t(yy) * in.stride + size_t(xx)]; };
   parallel_for(int(h), num_threads, [&](int yi) {
     const ptrdiff_t y = yi;
+    const bool row_inside = y >= 3 && y + 3 < ptrdiff_t(h);
     for (ptrdiff_t x = 0; x < ptrdiff_t(w); x++) {
-      float inv_sigma_px = sigma[size_t(y / 8) * geo.xb + size_t(x / 8)];
-      auto at = [&](int c, ptrdiff_t xx, ptrdiff_t yy) {
-        return in.p[c][mirror(yy, h) * in.stride + mirror(xx, w)];
-      };
-      if (inv_sigma_px < kMinSigma) {
-        for (int c = 0; c < 3; c++) out.p[c][size_t(y) * out.stride + size_t(x)] = at(c, x, y);
-        continue;
-      }
-      bool border = (y % 8 == 0 || y % 8 == 7) || (x % 8 == 0 || x % 8 == 7);
-      float inv_s = inv_sigma_px * (border ? bsm : sm);
-      if (stage == 2) {  // epf2.rs:53-125
-        float cc[3] = {at(0, x, y), at(1, x, y), at(2, x, y)};
-        float wacc = 1.0f, acc[3] = {cc[0], cc[1], cc[2]};
-        for (auto& o : kOff1) {
-          float nb[3] = {at(0, x + o[0], y + o[1]), at(1, x + o[0], y + o[1]), at(2, x + o[0], y + o[1])};
-          float sad = std::fmaf(std::fabs(nb[0] - cc[0]), d.epf_channel_scale[0],
-                                std::fmaf(std::fabs(nb[1] - cc[1]), d.epf_channel_scale[1],
-                                          std::fabs(nb[2] - cc[2]) * d.epf_channel_scale[2]));
-          float wt = std::max(std::fmaf(sad, inv_s, 1.0f), 0.0f);
-          wacc += wt;
-          for (int c = 0; c < 3; c++) acc[c] = std::fmaf(wt, nb[c], acc[c]);
-        }
-        float inv_w = 1.0f / wacc;
-        for (int c = 0; c < 3; c++) out.p[c][size_t(y) * out.stride + size_t(x)] = acc[c] * inv_w;
-        continue;
-      }
-      const int n = stage == 0 ? 12 : 4;
-      const int(*off)[2] = stage == 0 ? kOff0 : kOff1;
-      float sads[12];
-      for (int k = 0; k < n; k++) sads[k] = 0.0f;
-      for (int c = 0; c < 3; c++) {
-        float scale = d.epf_channel_scale[c];
-        for (int k = 0; k < n; k++) {
-          float s = 0.0f;
-          for (auto& pl : kPlusOrder)
-            s += std::fabs(at(c, x + pl[0], y + pl[1]) - at(c, x + pl[0] + off[k][0], y + pl[1] + off[k][1]));
-          sads[k] = std::fmaf(scale, s, sads[k]);
-        }
-      }
-      float wsum = 1.0f;
-      for (int k = 0; k < n; k++) {
-        sads[k] = std::max(std::fmaf(sads[k], inv_s, 1.0f), 0.0f);
-        wsum += sads[k];
-      }
-      float inv_w = 1.0f / wsum;
-      for (int c = 0; c < 3; c++) {
-        float o = at(c, x, y);
-        for (int k = n - 1; k >= 0; k--) o = std::fmaf(at(c, x + off[k][0], y + off[k][1]), sads[k], o);
-        out.p[c][size_t(y) * out.stride + size_t(x)] = o * inv_w;
-      }
+      if (row_inside && x >= 3 && x + 3 < ptrdiff_t(w)) pixel(x, y, at_direct);
+      else pixel(x, y, at_mirror);
     }
   });
 }
