@@ -9,91 +9,12 @@ import types
 import pytest
 
 
-class _FakeEvent:
-    def __init__(self, enable_timing=False):
-        pass
-
-    def record(self, stream=None):
-        pass
-
-    def elapsed_time(self, other):
-        return 1.0
-
-
-class _FakeStream:
-    cuda_stream = 0
-
-    def __init__(self, device=None):
-        pass
-
-
-def _install_fakes(monkeypatch, fail_e2e=False):
-    import torch
-    import bench
-    from jxl_rs_b200 import decoder
-    import jxl_rs_b200 as j
-
-    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
-    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
-    real_empty, real_tensor = torch.empty, torch.tensor
-    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
-    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-
-    class FakeCtx:
-        def __init__(self, device=0):
-            self.device = device
-
-        def close(self):
-            pass
-
-    class FakeBatch:
-        runs = 0
-
-        def __init__(self, ctx, n=0, staging_threads=0):
-            self.n = 0
-
-        def add(self, fr, ptr, stride, fmt, out_is_device):
-            assert fr.width > 0 and ptr != 0 and stride >= fr.width * 3
-            self.n += 1
-
-        def set_profile(self, on):
-            pass
-
-        def run(self, stream_ptr=0):
-            FakeBatch.runs += 1
-            if fail_e2e and FakeBatch.runs > 4:
-                raise RuntimeError("injected failure of the end-to-end leg")
-
-        def rerun_device(self, stream_ptr=0):
-            pass
-
-        def wait(self):
-            pass
-
-        def stage_times(self):
-            return {"memset": 0.1, "entropy": 3.0, "dequant_idct": 1.0, "epf2": 1.2}
-
-        def stats(self):
-            return {"h2d_bytes": 1000, "d2h_bytes": 2000, "kernel_launches": 7, "device_ms": 5.5}
-
-        def close(self):
-            pass
-
-    for mod in (decoder, j):
-        monkeypatch.setattr(mod, "JxgContext", FakeCtx)
-        monkeypatch.setattr(mod, "Batch", FakeBatch)
-    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
-    return bench
+from tests import bench_fakes
 
 
 @pytest.mark.parametrize("fail_e2e", [False, True])
 def test_bench_main_control_flow(monkeypatch, capsys, fail_e2e):
-    bench = _install_fakes(monkeypatch, fail_e2e)
+    bench = bench_fakes.install(monkeypatch.setattr, fail_e2e)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "1", "--steps", "3", "--warmup", "3", "--frames", "3",
                                       "--width", "320", "--height", "200", "--cpu-sample-frames", "1", "--lf-tree", "1"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
@@ -115,3 +36,32 @@ def test_bench_main_control_flow(monkeypatch, capsys, fail_e2e):
         assert line["value"] > 0  # the device-resident measurement survives
     else:
         assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 1000
+
+
+def test_bench_two_ranks_over_gloo(tmp_path):
+    """The multi-rank control flow (per-rank frame seeds and host-thread share, barriers, max-over-ranks reductions, rank
+    0 printing the line) with two CPU processes launched the way the driver launches them."""
+    import os
+    import socket
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    driver = tmp_path / "drive.py"
+    driver.write_text(
+        "import sys\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from tests import bench_fakes\n"
+        "bench = bench_fakes.install(setattr, gloo=True)\n"
+        "sys.argv = ['bench.py', '--gpus', '2', '--steps', '2', '--warmup', '3', '--frames', '2', '--width', '200',\n"
+        "            '--height', '120', '--cpu-sample-frames', '1']\n"
+        "bench.main()\n")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(driver)],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["e2e"]["value"] > 0 and line["value"] > 0
