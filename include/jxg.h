@@ -185,7 +185,10 @@ int jxg_batch_stats(void* batch, uint64_t* kernel_launches, uint64_t* h2d_bytes,
  * Parses complete .jxl files (container or bare codestream) on the host with
  * the in-tree C++ front-end (the stand-in for the Rust host: headers, TOC,
  * LfGlobal, LfGroups, HfGlobal), then feeds the batch API above. Mirrors
- * JxlDecoder::process for whole files (jxl/src/api/decoder.rs:258). */
+ * JxlDecoder::process for whole files (jxl/src/api/decoder.rs:258).
+ * Frames with extra channels (alpha ...) are accepted and decode to their colour channels — the output of the
+ * reference when JxlPixelFormat::extra_channel_format holds None (api/data_types.rs:154); patches, splines,
+ * upsampling, non-regular / blended frames and JPEG recompression return JXG_ERR_UNSUPPORTED. */
 typedef struct JxgImageInfo {
   uint32_t width, height, num_groups, num_passes;
   uint32_t encoding;      /* 0 VarDCT, 1 Modular */
