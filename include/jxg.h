@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JXG_ABI_VERSION 1
+#define JXG_ABI_VERSION 2
 
 /* Error codes; names mirror jxl/src/error.rs variants raised on this path. */
 enum {
@@ -62,7 +62,14 @@ enum {
 };
 
 /* Output transfer function (render/stages/from_linear.rs). */
-enum { JXG_TF_LINEAR = 0, JXG_TF_SRGB = 1 };
+enum {
+  JXG_TF_LINEAR = 0, /* no curve (the reference adds no stage for a linear output, frame/render.rs:761)      */
+  JXG_TF_SRGB = 1,   /* color/tf.rs:13-44                                                                     */
+  JXG_TF_GAMMA = 2,  /* |v|^output_gamma, sign kept (from_linear.rs:97-109; DCI is gamma 1/2.6)               */
+  JXG_TF_BT709 = 3,  /* color/tf.rs:114-150                                                                   */
+  JXG_TF_PQ = 4,     /* color/tf.rs:261-304, 1.0 = intensity_target nits                                      */
+  JXG_TF_HLG = 5     /* inverse OOTF with output_luminances, then the HLG OETF (color/tf.rs:458-470, 481-497) */
+};
 
 /* One entropy-coded histogram set + coefficient orders, per pass
  * (HfGlobalState.passes[i], jxl/src/frame/decode.rs:519-545). */
@@ -127,6 +134,14 @@ typedef struct JxgFrameDesc {
   float opsin_inverse_matrix[9]; float opsin_biases[3]; float intensity_target;
   uint32_t output_tf;             /* JXG_TF_*                                         */
   uint32_t output_format;         /* JXG_FORMAT_*                                     */
+  /* ImageMetadata.orientation 1..8 (headers/image_metadata.rs:41-50), applied by the store as the reference's save stage
+   * does (render/save.rs, api/options.rs:39 adjust_orientation = true): the output buffer holds the image in display
+   * orientation, i.e. height x width swap for values 5..8. The XYB debug tap ignores it. */
+  uint32_t orientation;
+  /* Output encoding as OutputColorInfo::from_header derives it (render/stages/xyb.rs:65-140): opsin_inverse_matrix above
+   * is already re-targeted to the output primaries / white point (grey: three luminance rows). */
+  float output_gamma;             /* JXG_TF_GAMMA exponent                             */
+  float output_luminances[3];     /* Y row of the output primaries (JXG_TF_HLG)        */
 } JxgFrameDesc;
 
 /* Context: one per device/rank. Owns streams, pinned staging and device pools. */
@@ -190,9 +205,12 @@ int jxg_batch_stats(void* batch, uint64_t* kernel_launches, uint64_t* h2d_bytes,
  * reference when JxlPixelFormat::extra_channel_format holds None (api/data_types.rs:154); patches, splines,
  * upsampling, non-regular / blended frames and JPEG recompression return JXG_ERR_UNSUPPORTED. */
 typedef struct JxgImageInfo {
-  uint32_t width, height, num_groups, num_passes;
+  uint32_t width, height; /* size of the OUTPUT (display orientation): what the caller allocates */
+  uint32_t num_groups, num_passes;
   uint32_t encoding;      /* 0 VarDCT, 1 Modular */
   uint64_t hf_bytes;      /* sum of HF section sizes */
+  uint32_t coded_width, coded_height; /* frame size as coded (swapped against width/height for orientation 5..8) */
+  uint32_t orientation;   /* 1..8 */
 } JxgImageInfo;
 
 int jxg_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info);

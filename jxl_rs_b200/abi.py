@@ -6,7 +6,7 @@ package touches raw pointers.
 import ctypes as C
 import os
 
-JXG_ABI_VERSION = 1
+JXG_ABI_VERSION = 2
 
 # error codes (include/jxg.h)
 JXG_OK = 0
@@ -52,13 +52,15 @@ class JxgFrameDesc(C.Structure):
         ("epf_quant_mul", C.c_float), ("epf_pass0_sigma_scale", C.c_float),
         ("epf_pass2_sigma_scale", C.c_float), ("epf_border_sad_mul", C.c_float),
         ("opsin_inverse_matrix", C.c_float * 9), ("opsin_biases", C.c_float * 3), ("intensity_target", C.c_float),
-        ("output_tf", C.c_uint32), ("output_format", C.c_uint32),
+        ("output_tf", C.c_uint32), ("output_format", C.c_uint32), ("orientation", C.c_uint32),
+        ("output_gamma", C.c_float), ("output_luminances", C.c_float * 3),
     ]
 
 
 class JxgImageInfo(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("num_groups", C.c_uint32),
-                ("num_passes", C.c_uint32), ("encoding", C.c_uint32), ("hf_bytes", C.c_uint64)]
+                ("num_passes", C.c_uint32), ("encoding", C.c_uint32), ("hf_bytes", C.c_uint64),
+                ("coded_width", C.c_uint32), ("coded_height", C.c_uint32), ("orientation", C.c_uint32)]
 
 
 # every symbol include/jxg.h declares (tests check the .so exports all of them)

@@ -32,9 +32,13 @@ namespace {
 
 struct FrameOut {
   void* user_ptr;
-  size_t row_stride, rows, bytes;
+  size_t row_stride, rows, bytes;  // bytes: rows * row_stride (device staging), copy_bytes: what the user buffer must hold
   bool is_device;
   size_t dev_off;  // offset in d_out when !is_device
+  size_t copy_bytes;
+  // orientation != 1: the kernels store the coded image tightly into d_orient, k_orient writes the final place
+  uint32_t orientation, coded_w, coded_h, bpp;
+  size_t stage_off, stage_stride;
 };
 
 struct Batch {
@@ -55,7 +59,7 @@ struct Batch {
   std::vector<uint32_t> tile_prefix{0};
   std::vector<uint32_t> fused_prefix{0};
   std::vector<FrameOut> outs;
-  uint64_t total_groups = 0, total_blocks = 0, total_plane_floats = 0, nz_bytes = 0, out_bytes = 0;
+  uint64_t total_groups = 0, total_blocks = 0, total_plane_floats = 0, nz_bytes = 0, out_bytes = 0, orient_bytes = 0;
   uint32_t max_epf = 0;
   uint32_t filter_cfg_mask = 0;  // bit (gab * 4 + min(epf_iters, 3))
   bool any_gab = false;
@@ -73,6 +77,76 @@ struct Batch {
   uint64_t launches = 0, h2d = 0, d2h = 0;
   float last_ms = 0;
 };
+
+// The kernels index device tables with fields of the descriptor and never bounds-check them, so everything a
+// foreign host could get wrong is checked here (the in-tree front-end guarantees all of it by construction).
+static int validate_desc(const JxgFrameDesc* d, const uint32_t* sec_len, uint32_t n_sections) {
+  auto bad = [](const char* what) { return set_error(JXG_ERR_ARGUMENT, std::string("frame descriptor: ") + what); };
+  static const uint8_t kCovX[27] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
+  static const uint8_t kCovY[27] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
+  static const uint32_t kShapeCoeffs[13] = {64, 64, 256, 1024, 128, 256, 512, 4096, 2048, 16384, 8192, 65536, 32768};
+  if (!d->width || !d->height || d->width > (1u << 30) || d->height > (1u << 30)) return bad("bad dimensions");
+  if (!d->global_scale || !d->color_factor || !(d->intensity_target > 0.0f)) return bad("zero global_scale / color_factor / intensity_target");
+  if (!d->block_ctx_map || !d->passes || !d->transform_map || !d->raw_quant_map || !d->epf_map || !d->quant_lf || !d->ytox_map ||
+      !d->ytob_map || !d->lf[0] || !d->lf[1] || !d->lf[2])
+    return bad("null table pointer");
+  if (d->num_qf_thresholds > 15 || !d->num_lf_contexts || d->num_lf_contexts > 64) return bad("bad qf / lf context counts");
+  if (!d->num_block_contexts || d->num_block_contexts > 16) return bad("num_block_contexts must be 1..16");
+  if (d->block_ctx_map_len != 39u * (d->num_qf_thresholds + 1) * d->num_lf_contexts) return bad("block_ctx_map_len");
+  for (uint32_t i = 0; i < d->block_ctx_map_len; i++)
+    if (d->block_ctx_map[i] >= d->num_block_contexts) return bad("block_ctx_map entry >= num_block_contexts");
+  if (!d->num_histograms || d->num_histograms > 4096) return bad("num_histograms");
+  if (d->output_tf > JXG_TF_HLG) return bad("unknown output_tf");
+  if (d->output_tf == JXG_TF_GAMMA && !(d->output_gamma > 0.0f && d->output_gamma <= 1.0f)) return bad("output_gamma must be in (0, 1]");
+  const uint64_t need_ctx = uint64_t(d->num_histograms) * d->num_block_contexts * 495;
+  for (uint32_t p = 0; p < d->num_passes; p++) {
+    const JxgPassDesc& s = d->passes[p];
+    if (!s.context_map || !s.uint_configs) return bad("null pass table");
+    if (!s.num_clusters || s.num_clusters > 256) return bad("num_clusters must be 1..256");
+    if (s.num_contexts < need_ctx) return bad("context map shorter than num_histograms * num_block_contexts * 495");
+    for (uint32_t i = 0; i < s.num_contexts; i++)
+      if (s.context_map[i] >= s.num_clusters) return bad("context_map entry >= num_clusters");
+    if (s.shift > 31) return bad("pass shift");
+    if (s.use_prefix) {
+      if (!s.huff_entries || !s.huff_offset) return bad("null prefix tables");
+      for (uint32_t c = 0; c < s.num_clusters; c++) {
+        const uint64_t o = s.huff_offset[c];
+        if (o + 256 > s.huff_entries_len) return bad("prefix LUT root outside huff_entries");
+        for (uint32_t r = 0; r < 256; r++) {  // 2nd-level reach of every root entry (huffman.rs:446-457)
+          const uint32_t e = s.huff_entries[o + r], nb = e & 0xff;
+          if (nb > 8 && (nb > 15 || o + r + (e >> 16) + (1u << (nb - 8)) > s.huff_entries_len)) return bad("prefix LUT 2nd level outside huff_entries");
+        }
+      }
+    } else {
+      if (!s.ans_buckets) return bad("null ANS table");
+      if (s.log_alpha_size < 5 || s.log_alpha_size > 8) return bad("log_alpha_size must be 5..8");
+    }
+    if (s.coeff_order) {
+      for (int i = 0; i < 39; i++) {
+        const uint64_t o = s.coeff_order_offset[i], n = kShapeCoeffs[i / 3];
+        if (o + n > s.coeff_order_len) return bad("coefficient order outside coeff_order");
+        for (uint64_t k = 0; k < n; k++)
+          if (s.coeff_order[o + k] >= n) return bad("coefficient order entry out of range");
+      }
+    }
+  }
+  const uint32_t xb = (d->width + 7) / 8, yb = (d->height + 7) / 8;
+  for (uint32_t by = 0; by < yb; by++)
+    for (uint32_t bx = 0; bx < xb; bx++) {
+      const size_t i = size_t(by) * xb + bx;
+      if (d->quant_lf[i] >= d->num_lf_contexts) return bad("quant_lf entry >= num_lf_contexts");
+      if (d->epf_map[i] > 7) return bad("epf sharpness > 7");
+      const uint32_t t = d->transform_map[i];
+      if (t < 128) continue;
+      if ((t & 127) >= 27) return bad("unknown transform type");
+      const uint32_t cx = kCovX[t & 127], cy = kCovY[t & 127];
+      if ((bx & 31) + cx > 32 || (by & 31) + cy > 32 || bx + cx > xb || by + cy > yb) return bad("varblock crosses its group or the frame");
+      if (d->raw_quant_map[i] < 1) return bad("raw_quant < 1");
+    }
+  for (uint32_t i = 0; i < n_sections; i++)
+    if (sec_len[i] > (1u << 30)) return bad("HF section too large");
+  return 0;
+}
 
 }  // namespace
 
@@ -153,10 +227,13 @@ int jxg_batch_begin(void* c, uint32_t n_frames_hint, void** out_batch) {
   cx->blob.size = 0;
   cx->blob.pending.clear();
   cx->blob.deferred_threads = 0;
-  cx->batch_live = true;
   b->frames.reserve(n_frames_hint);
   CUDA_TRY(cudaEventCreate(&b->ev0));
-  CUDA_TRY(cudaEventCreate(&b->ev1));
+  if (cudaError_t e = cudaEventCreate(&b->ev1); e != cudaSuccess) {
+    cudaEventDestroy(b->ev0);
+    return set_error(JXG_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+  }
+  cx->batch_live = true;  // only once nothing can fail any more
   *out_batch = b.release();
   return JXG_OK;
 }
@@ -235,8 +312,13 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   F.plane_rows = F.yb * 8;
   F.cxb = (F.xb + 7) / 8;
   const size_t nb = size_t(F.xb) * F.yb, ncm = size_t(F.cxb) * ((F.yb + 7) / 8);
+  if (d->output_format > JXG_FORMAT_XYB_F32_PLANAR) return set_error(JXG_ERR_ARGUMENT, "unknown output format");
   size_t bpp = d->output_format == JXG_FORMAT_RGB_U8 ? 3 : d->output_format == JXG_FORMAT_RGBA_U8 ? 4 : d->output_format == JXG_FORMAT_RGB_F32 ? 12 : 4;
-  if (out_row_stride < size_t(F.width) * bpp) return set_error(JXG_ERR_INVALID_OUTPUT, "output row stride too small");
+  if (d->orientation > 8) return set_error(JXG_ERR_ARGUMENT, "orientation must be 1..8");
+  const uint32_t orientation = (d->orientation == 0 || d->output_format == JXG_FORMAT_XYB_F32_PLANAR) ? 1u : d->orientation;
+  const uint32_t disp_w = orientation >= 5 ? F.height : F.width, disp_h = orientation >= 5 ? F.width : F.height;
+  if (out_row_stride < size_t(disp_w) * bpp) return set_error(JXG_ERR_INVALID_OUTPUT, "output row stride too small");
+  if (int r = validate_desc(d, sec_len, n_sections)) return r;
   F.num_histograms = d->num_histograms;
   F.num_block_contexts = d->num_block_contexts;
   F.num_lf_contexts = d->num_lf_contexts;
@@ -332,11 +414,27 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   F.plane_base = b->total_plane_floats;
   b->total_plane_floats += 3 * F.plane_size;
   F.out_row_stride = out_row_stride;
-  size_t rows = d->output_format == JXG_FORMAT_XYB_F32_PLANAR ? size_t(F.height) * 3 : F.height;
-  FrameOut fo{out, out_row_stride, rows, rows * out_row_stride, out_is_device != 0, 0};
+  size_t rows = d->output_format == JXG_FORMAT_XYB_F32_PLANAR ? size_t(F.height) * 3 : disp_h;
+  FrameOut fo{};
+  fo.user_ptr = out;
+  fo.row_stride = out_row_stride;
+  fo.rows = rows;
+  fo.bytes = rows * out_row_stride;
+  fo.copy_bytes = (rows - 1) * out_row_stride + size_t(disp_w) * bpp;  // the last row of a user buffer may be unpadded
+  fo.is_device = out_is_device != 0;
+  fo.orientation = orientation;
+  fo.coded_w = F.width;
+  fo.coded_h = F.height;
+  fo.bpp = uint32_t(bpp);
   if (!fo.is_device) {
     fo.dev_off = (b->out_bytes + 255) / 256 * 256;
     b->out_bytes = fo.dev_off + fo.bytes;
+  }
+  if (orientation != 1) {  // coded image, tight rows (16-byte multiples: the vector store path stays usable)
+    fo.stage_stride = (size_t(F.width) * bpp + 15) / 16 * 16;
+    fo.stage_off = (b->orient_bytes + 255) / 256 * 256;
+    b->orient_bytes = fo.stage_off + fo.stage_stride * F.height;
+    F.out_row_stride = fo.stage_stride;
   }
   b->outs.push_back(fo);
   F.gab = d->gab;
@@ -362,6 +460,14 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
   }
   F.output_tf = d->output_tf;
   F.output_format = d->output_format;
+  F.tf_gamma = d->output_gamma;
+  memcpy(F.tf_lum, d->output_luminances, sizeof(F.tf_lum));
+  {  // color/tf.rs:458-470 hlg_display_to_scene: exponent of the inverse OOTF; |exp| < 0.1 skips it (tf.rs:381-383)
+    const float system_gamma = 1.2f * std::pow(1.111f, std::log2(d->intensity_target / 1e3f));
+    const float e = (1.0f - system_gamma) / system_gamma;
+    F.tf_hlg_exp = std::fabs(e) < 0.1f ? 0.0f : e;
+  }
+  F.tf_pq_mul = d->intensity_target * (1.0f / 10000.0f);
   b->max_epf = std::max(b->max_epf, d->epf_iters);
   b->any_gab = b->any_gab || d->gab;
   b->filter_cfg_mask |= 1u << ((d->gab ? 4 : 0) + std::min<uint32_t>(d->epf_iters, 3));
@@ -485,14 +591,22 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
       const uint32_t f0 = uint32_t(uint64_t(nf) * r / nr), f1 = uint32_t(uint64_t(nf) * (r + 1) / nr);
       const uint32_t t0 = b->fused_prefix[f0], t1 = b->fused_prefix[f1];
       b->launches += uint64_t(launch_filter_range(B, fp, t0, t1 - t0, b->filter_cfg_mask, s));
+      for (uint32_t f = f0; f < f1; f++) {  // orientation post-pass (rare): staging image -> final place
+        const FrameOut& fo = b->outs[f];
+        if (fo.orientation == 1) continue;
+        void* dst = fo.is_device ? fo.user_ptr : static_cast<void*>(static_cast<uint8_t*>(b->d_out.p) + fo.dev_off);
+        launch_orient(static_cast<uint8_t*>(cx->d_orient.p) + fo.stage_off, fo.stage_stride, dst, fo.row_stride, fo.coded_w,
+                      fo.coded_h, fo.bpp, fo.orientation, s);
+        b->launches++;
+      }
       if (copy_to_host) {
         CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
         CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->range_done[r], 0));
         for (uint32_t f = f0; f < f1; f++) {
           const FrameOut& fo = b->outs[f];
           if (fo.is_device) continue;
-          CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.bytes, cudaMemcpyDeviceToHost, cx->copy_stream));
-          b->d2h += fo.bytes;
+          CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.copy_bytes, cudaMemcpyDeviceToHost, cx->copy_stream));
+          b->d2h += fo.copy_bytes;
         }
       }
     }
@@ -532,8 +646,12 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
   if (int r = b->ctx->d_lean_desc.ensure(std::max<size_t>(b->streams_lean.size() * 1024 * 16, 16))) return r;
   if (int r = b->ctx->d_lean_nblk.ensure(std::max<size_t>(b->streams_lean.size() * 4, 16))) return r;
-  for (size_t f = 0; f < b->frames.size(); f++)
-    b->frames[f].out_ptr = b->outs[f].is_device ? b->outs[f].user_ptr : static_cast<uint8_t*>(b->d_out.p) + b->outs[f].dev_off;
+  if (int r = b->ctx->d_orient.ensure(std::max<size_t>(b->orient_bytes, 16))) return r;
+  for (size_t f = 0; f < b->frames.size(); f++) {
+    const FrameOut& fo = b->outs[f];
+    if (fo.orientation != 1) b->frames[f].out_ptr = static_cast<uint8_t*>(b->ctx->d_orient.p) + fo.stage_off;
+    else b->frames[f].out_ptr = fo.is_device ? fo.user_ptr : static_cast<uint8_t*>(b->d_out.p) + fo.dev_off;
+  }
   b->status_n = b->streams.size();
   if (b->status_n > b->ctx->status_cap) {
     if (b->ctx->status_host) cudaFreeHost(b->ctx->status_host);
@@ -641,8 +759,11 @@ int jxg_parse_file_mt(const uint8_t* data, size_t size, int threads, void** pars
   try {
     std::unique_ptr<jxg::FrameState> fs = jxg::parse_vardct_file(data, size, threads);
     if (info) {
-      info->width = fs->header.xsize();
-      info->height = fs->header.ysize();
+      info->coded_width = fs->header.xsize();
+      info->coded_height = fs->header.ysize();
+      info->orientation = fs->file.orientation;
+      info->width = fs->file.orientation >= 5 ? info->coded_height : info->coded_width;
+      info->height = fs->file.orientation >= 5 ? info->coded_width : info->coded_height;
       info->num_groups = fs->header.num_groups();
       info->num_passes = fs->header.passes.num_passes;
       info->encoding = 0;

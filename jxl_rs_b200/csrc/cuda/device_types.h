@@ -63,6 +63,10 @@ struct FrameDev {
   float quant_scale;  // 1 / inv_global_scale (features/epf.rs:55)
   float opsin[9], bias_cbrt[3], scaled_bias[3], intensity_scale;
   uint32_t output_tf, output_format;
+  float tf_gamma;        // JXG_TF_GAMMA exponent
+  float tf_lum[3];       // JXG_TF_HLG: luminances of the output primaries
+  float tf_hlg_exp;      // JXG_TF_HLG: (1 - system_gamma) / system_gamma (color/tf.rs:458-470), 0 = OOTF skipped
+  float tf_pq_mul;       // JXG_TF_PQ: intensity_target / 10000
 };
 
 struct SectionDev {

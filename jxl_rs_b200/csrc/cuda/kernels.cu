@@ -2133,6 +2133,69 @@ __device__ __forceinline__ float linear_to_srgb(float v) {
   return copysignf(r, v);
 }
 
+// render/stages/from_linear.rs:56-112: the output transfer function on display-referred linear RGB. The sRGB curve is
+// handled by the callers (their hot path); this is the rare-encoding switch, written from color/tf.rs with the device's
+// exp2f / log2f where the reference uses its own rational fast_powf (max relative error 3e-5 there).
+__device__ __noinline__ void from_linear_other(const FrameDev& F, float (&v)[3]) {
+  auto rat5 = [](float x, const float* p, const float* q) {
+    float yp = p[4], yq = q[4];
+#pragma unroll
+    for (int i = 3; i >= 0; i--) {
+      yp = fmaf(yp, x, p[i]);
+      yq = fmaf(yq, x, q[i]);
+    }
+    return yp / yq;
+  };
+  switch (F.output_tf) {
+    case JXG_TF_GAMMA:
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float a = fabsf(v[c]);
+        v[c] = copysignf(a > 0.0f ? exp2f(F.tf_gamma * log2f(a)) : 0.0f, v[c]);
+      }
+      break;
+    case JXG_TF_BT709: {  // tf.rs:114-150
+      const float P[5] = {-9.625309705734253e-2f, -2.2635456919670105e-1f, 1.935774803161621e1f, 5.897886276245117e1f, 2.3947298049926758e1f};
+      const float Q[5] = {1.0f, 1.877663230895996e1f, 5.5292449951171875e1f, 2.6565317153930664e1f, 3.269049823284149e-1f};
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float a = fabsf(v[c]);
+        v[c] = copysignf(a < 0.018f ? a * 4.5f : rat5(sqrtf(a), P, Q), v[c]);
+      }
+      break;
+    }
+    case JXG_TF_PQ: {  // tf.rs:236-283
+      const float P[5] = {1.351392e-2f, -1.095778f, 5.522776e1f, 1.492516e2f, 4.838434e1f};
+      const float Q[5] = {1.012416f, 2.016708e1f, 9.26371e1f, 1.120607e2f, 2.590418e1f};
+      const float PS[5] = {9.863406e-6f, 3.881234e-1f, 1.352821e2f, 6.889862e4f, -2.864824e5f};
+      const float QS[5] = {3.371868e1f, 1.477719e3f, 1.608477e4f, -4.389884e4f, -2.072546e5f};
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float a = fabsf(v[c]);
+        const float a14 = sqrtf(sqrtf(a * F.tf_pq_mul));
+        v[c] = copysignf(a < 1e-4f ? rat5(a14, PS, QS) : rat5(a14, P, Q), v[c]);
+      }
+      break;
+    }
+    case JXG_TF_HLG: {  // tf.rs:381-395 (inverse OOTF), 481-497 (OETF)
+      if (F.tf_hlg_exp != 0.0f) {
+        const float mixed = fmaf(v[0], F.tf_lum[0], fmaf(v[1], F.tf_lum[1], v[2] * F.tf_lum[2]));
+        const float mult = exp2f(F.tf_hlg_exp * log2f(mixed));
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[c] *= mult;
+      }
+      const float kA = 0.17883277f, kB = 1.0f - 4.0f * 0.17883277f, kC = 0.5599107295f;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float a = fabsf(v[c]);
+        v[c] = copysignf(a <= 1.0f / 12.0f ? sqrtf(3.0f * a) : kA * 0.69314718056f * log2f(12.0f * a - kB) + kC, v[c]);
+      }
+      break;
+    }
+    default: break;  // JXG_TF_LINEAR
+  }
+}
+
 // xyb.rs:197-241 + from_linear + convert.rs:574-598 + save (interleave)
 __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileDev T, const float* src) {
   uint32_t f;
@@ -2162,6 +2225,8 @@ __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileD
   if (F.output_tf == JXG_TF_SRGB) {
 #pragma unroll
     for (int c = 0; c < 3; c++) v[c] = linear_to_srgb(v[c]);
+  } else if (F.output_tf != JXG_TF_LINEAR) {
+    from_linear_other(F, v);
   }
   if (F.output_format == JXG_FORMAT_RGB_F32) {
     float* dst = reinterpret_cast<float*>(row) + size_t(x) * 3;
@@ -2465,6 +2530,8 @@ __device__ __forceinline__ void filter_tile(const BatchDev& B, const FrameDev& F
     if (F.output_tf == JXG_TF_SRGB) {
 #pragma unroll
       for (int c = 0; c < 3; c++) v[c] = linear_to_srgb(v[c]);
+    } else if (F.output_tf != JXG_TF_LINEAR) {
+      from_linear_other(F, v);
     }
     if (bpp == 12) {
       float* d = reinterpret_cast<float*>(stage_u8) + (ly * kTW + lx) * 3;
@@ -2746,6 +2813,8 @@ __device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev
         if (F.output_tf == JXG_TF_SRGB) {
 #pragma unroll
           for (int c = 0; c < 3; c++) rgb[i][c] = linear_to_srgb_fast(rgb[i][c]);
+        } else if (F.output_tf != JXG_TF_LINEAR) {
+          from_linear_other(F, rgb[i]);
         }
       }
       (void)w;
@@ -2817,6 +2886,36 @@ template <bool GAB, int EPF>
 static cudaError_t configure_filters() {
   return cudaFuncSetAttribute(k_filters_store<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               int(FCfg<GAB, EPF>::kSmemBytes));
+}
+
+// ---------------------------------------------------------------------------
+// Orientation post-pass (headers/image_metadata.rs:85-96 display_pixel, applied by the reference's save stage,
+// render/save.rs): pixel (x, y) of the coded w x h image goes to display_pixel(x, y). Only frames whose
+// ImageMetadata.orientation != 1 take it: they are filtered / stored into a tight staging image first.
+// One thread per pixel; threads of a warp read consecutive source pixels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_orient(const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride,
+                                                uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation) {
+  const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  uint32_t dx, dy;
+  switch (orientation) {
+    case 2: dx = w - 1 - x; dy = y; break;          // FlipHorizontal
+    case 3: dx = w - 1 - x; dy = h - 1 - y; break;  // Rotate180
+    case 4: dx = x; dy = h - 1 - y; break;          // FlipVertical
+    case 5: dx = y; dy = x; break;                  // Transpose
+    case 6: dx = h - 1 - y; dy = x; break;          // Rotate90Cw
+    case 7: dx = h - 1 - y; dy = w - 1 - x; break;  // AntiTranspose
+    case 8: dx = y; dy = w - 1 - x; break;          // Rotate90Ccw
+    default: dx = x; dy = y; break;
+  }
+  const uint8_t* s = src + size_t(y) * src_stride + size_t(x) * bpp;
+  uint8_t* d = dst + size_t(dy) * dst_stride + size_t(dx) * bpp;
+  if ((bpp & 3) == 0) {
+    for (uint32_t i = 0; i < bpp; i += 4) *reinterpret_cast<uint32_t*>(d + i) = *reinterpret_cast<const uint32_t*>(s + i);
+  } else {
+    for (uint32_t i = 0; i < bpp; i++) d[i] = s[i];
+  }
 }
 
 // ===========================================================================
@@ -2955,6 +3054,12 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(8);
   if (final_planes) *final_planes = cur;
   return launches;
+}
+
+void launch_orient(const void* src, size_t src_stride, void* dst, size_t dst_stride, uint32_t w, uint32_t h, uint32_t bpp,
+                   uint32_t orientation, cudaStream_t stream) {
+  k_orient<<<dim3((w + 31) / 32, (h + 7) / 8), 256, 0, stream>>>(static_cast<const uint8_t*>(src), src_stride,
+                                                                 static_cast<uint8_t*>(dst), dst_stride, w, h, bpp, orientation);
 }
 
 // Fused filter/colour/store kernel over tiles [tile_begin, tile_begin + tile_count): one launch per filter

@@ -112,7 +112,8 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
   f.out_stride = stride;
   f.out_is_device = is_device;
   const uint32_t W = ms->header.xsize(), H = ms->header.ysize();
-  if (stride < size_t(W) * 3) throw jxg::Error(JXG_ERR_INVALID_OUTPUT, "output row stride too small");
+  const uint32_t orient = ms->file.orientation;  // applied by the store kernel (render/save.rs)
+  if (stride < size_t(orient >= 5 ? H : W) * 3) throw jxg::Error(JXG_ERR_INVALID_OUTPUT, "output row stride too small");
   // ---- plane arena: host-decoded coded channels first (one contiguous upload), then the rest ----
   f.arena_base = b->arena_elems;
   f.buf_off.assign(ms->bufs.size(), 0);
@@ -239,6 +240,7 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
   sj.c = f.buf_off[ms->out_buf[nc > 2 ? 2 : 0]];
   sj.w = W;
   sj.h = H;
+  sj.op = orient;
   for (uint32_t c = 0; c < nc; c++)
     if (ms->bufs[ms->out_buf[c]].w != W || ms->bufs[ms->out_buf[c]].h != H)
       throw jxg::Error(jxg::kErrBitstream, "unexpected output channel size");
@@ -299,7 +301,8 @@ int launch_all(ModularBatch* b, cudaStream_t s, bool copy_to_host) {
   if (copy_to_host) {
     for (const MFrame& f : b->frames)
       if (!f.out_is_device) {
-        const uint32_t W = f.ms->header.xsize(), H = f.ms->header.ysize();
+        const bool tr = f.ms->file.orientation >= 5;  // display size
+        const uint32_t W = tr ? f.ms->header.ysize() : f.ms->header.xsize(), H = tr ? f.ms->header.xsize() : f.ms->header.ysize();
         CUDA_TRY(cudaMemcpy2DAsync(f.out, f.out_stride, static_cast<uint8_t*>(cx->d_out.p) + f.dev_out_off, size_t(W) * 3,
                                    size_t(W) * 3, H, cudaMemcpyDeviceToHost, s));
         b->d2h += size_t(W) * 3 * H;
@@ -320,8 +323,11 @@ int jxg_modular_parse_file(const uint8_t* data, size_t size, void** parsed, JxgI
     auto ms = jxg::parse_modular_file(data, size);
     if (info) {
       memset(info, 0, sizeof(*info));
-      info->width = ms->header.xsize();
-      info->height = ms->header.ysize();
+      info->coded_width = ms->header.xsize();
+      info->coded_height = ms->header.ysize();
+      info->orientation = ms->file.orientation;
+      info->width = ms->file.orientation >= 5 ? info->coded_height : info->coded_width;
+      info->height = ms->file.orientation >= 5 ? info->coded_width : info->coded_height;
       info->num_groups = ms->header.num_groups();
       info->num_passes = 1;
       info->encoding = 1;
@@ -394,7 +400,8 @@ int jxg_modular_batch_run(void* bp, void* cuda_stream) {
   for (size_t i = 0; i < b->frames.size(); i++) {
     MFrame& f = b->frames[i];
     b->store_jobs[i].out = f.out_is_device ? f.out : static_cast<uint8_t*>(cx->d_out.p) + f.dev_out_off;
-    b->store_jobs[i].out_stride = f.out_is_device ? f.out_stride : size_t(f.ms->header.xsize()) * 3;
+    b->store_jobs[i].out_stride =
+        f.out_is_device ? f.out_stride : size_t(f.ms->file.orientation >= 5 ? f.ms->header.ysize() : f.ms->header.xsize()) * 3;
   }
   if (b->streams.size() > cx->status_cap) {
     if (cx->status_host) cudaFreeHost(cx->status_host);

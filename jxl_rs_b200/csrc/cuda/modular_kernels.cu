@@ -511,13 +511,24 @@ __global__ void __launch_bounds__(128) k_unsqueeze_v(const MJobDev* jobs, int32_
   if (oh & 1) o[size_t(oh - 1) * w] = a[size_t(ah - 1) * w];
 }
 
-// i32 planes -> interleaved RGB u8, clamped (convert.rs:675-680). job: a, b, c = R, G, B planes (w x h).
+// i32 planes -> interleaved RGB u8, clamped (convert.rs:675-680). job: a, b, c = R, G, B planes (w x h), op = orientation.
 __global__ void __launch_bounds__(256) k_modular_store(const MJobDev* jobs, const int32_t* planes) {
   const MJobDev j = jobs[blockIdx.y];
   const size_t n = size_t(j.w) * j.h;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     const uint32_t y = uint32_t(i / j.w), x = uint32_t(i - size_t(y) * j.w);
-    uint8_t* d = static_cast<uint8_t*>(j.out) + size_t(y) * j.out_stride + size_t(x) * 3;
+    uint32_t dx = x, dy = y;
+    switch (j.op) {  // ImageMetadata.orientation (headers/image_metadata.rs:85-96 display_pixel); 1 = identity
+      case 2: dx = j.w - 1 - x; break;
+      case 3: dx = j.w - 1 - x; dy = j.h - 1 - y; break;
+      case 4: dy = j.h - 1 - y; break;
+      case 5: dx = y; dy = x; break;
+      case 6: dx = j.h - 1 - y; dy = x; break;
+      case 7: dx = j.h - 1 - y; dy = j.w - 1 - x; break;
+      case 8: dx = y; dy = j.w - 1 - x; break;
+      default: break;
+    }
+    uint8_t* d = static_cast<uint8_t*>(j.out) + size_t(dy) * j.out_stride + size_t(dx) * 3;
     d[0] = uint8_t(min(max(planes[j.a + i], 0), 255));
     d[1] = uint8_t(min(max(planes[j.b + i], 0), 255));
     d[2] = uint8_t(min(max(planes[j.c + i], 0), 255));

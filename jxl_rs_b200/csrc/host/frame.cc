@@ -110,8 +110,9 @@ void decode_lf_global(FrameState& fs, BitReader& br) {
   const FrameHeader& h = fs.header;
   if (h.has_patches()) fail("patches are outside the hot-path scope", kErrUnsupported);
   if (h.has_splines()) fail("splines are outside the hot-path scope", kErrUnsupported);
-  if (h.has_noise())
-    for (int i = 0; i < 8; i++) br.read(10);  // features/noise.rs:14 (parsed, not rendered)
+  // features/noise.rs:14 + render/stages/noise.rs: noise synthesis is not rendered by this path, and dropping it would
+  // silently differ from the reference's pixels, so the frame is refused.
+  if (h.has_noise()) fail("noise synthesis is outside the hot-path scope", kErrUnsupported);
   // LfQuantFactors (quantizer.rs:28-52)
   if (!br.read_bool()) {
     for (float& q : fs.lf_quant) {
@@ -607,6 +608,8 @@ std::unique_ptr<FrameState> parse_vardct_file(const uint8_t* data, size_t size, 
   if (h.upsampling != 1) fail("upsampling is outside the hot-path scope", kErrUnsupported);
   if (h.has_lf_frame()) fail("LF frames are outside the hot-path scope", kErrUnsupported);
   if (h.have_crop || h.blending.mode != 0) fail("cropped/blended frames are outside the hot-path scope", kErrUnsupported);
+  check_single_still_frame(fs.file, h);
+  resolve_output_colour(fs.file);  // refuses the colour encodings this path cannot reproduce
   fs.toc = read_toc(br, h.num_toc_entries());
   fs.sections_base = br.byte_pos();
   const uint8_t* base = fs.codestream.data() + fs.sections_base;
@@ -790,13 +793,19 @@ void FrameState::fill_desc(JxgFrameDesc* d, uint32_t output_format) {
   d->epf_pass0_sigma_scale = rf.epf_pass0_sigma_scale;
   d->epf_pass2_sigma_scale = rf.epf_pass2_sigma_scale;
   d->epf_border_sad_mul = rf.epf_border_sad_mul;
-  memcpy(d->opsin_inverse_matrix, file.opsin.inverse_matrix, sizeof(d->opsin_inverse_matrix));
   memcpy(d->opsin_biases, file.opsin.opsin_biases, sizeof(d->opsin_biases));
   d->intensity_target = file.intensity_target;
   d->output_format = output_format;
-  // api/inner/codestream_parser/image_info.rs:204-237: integer outputs get the
-  // image's transfer function (sRGB here), f32 output stays linear.
-  d->output_tf = (output_format == JXG_FORMAT_RGB_F32 || output_format == JXG_FORMAT_XYB_F32_PLANAR) ? JXG_TF_LINEAR : JXG_TF_SRGB;
+  d->orientation = file.orientation;
+  // api/inner/codestream_parser/image_info.rs:204-237 + render/stages/xyb.rs:65-140: a non-ICC embedded encoding is the
+  // output encoding for every sample format; an ICC profile cannot be output to, so integer formats get sRGB and
+  // float formats linear sRGB.
+  const bool is_float = output_format == JXG_FORMAT_RGB_F32 || output_format == JXG_FORMAT_XYB_F32_PLANAR;
+  const OutputColour oc = resolve_output_colour(file);
+  d->output_tf = oc.from_icc ? uint32_t(is_float ? JXG_TF_LINEAR : JXG_TF_SRGB) : oc.tf;
+  d->output_gamma = oc.gamma;
+  memcpy(d->output_luminances, oc.luminances, sizeof(d->output_luminances));
+  memcpy(d->opsin_inverse_matrix, oc.matrix, sizeof(d->opsin_inverse_matrix));
 }
 
 }  // namespace jxg

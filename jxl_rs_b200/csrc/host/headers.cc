@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "entropy.h"
 
@@ -69,8 +70,11 @@ void read_preview(BitReader& br) {  // size.rs:49-66
   }
 }
 
-void read_custom_xy(BitReader& br) {
-  for (int i = 0; i < 2; i++) u2s(br, B(19), B(19, 524288), B(20, 1048576), B(21, 2097152));
+void read_custom_xy(BitReader& br, int32_t* xy) {  // color_encoding.rs:91-100: u2S then unpack_signed (encodings.rs:99-108)
+  for (int i = 0; i < 2; i++) {
+    const uint32_t u = u2s(br, B(19), B(19, 524288), B(20, 1048576), B(21, 2097152));
+    xy[i] = int32_t((u >> 1) ^ (((~u) & 1u) - 1u));
+  }
 }
 
 ColorEncoding read_color_encoding(BitReader& br) {  // color_encoding.rs:166-196
@@ -82,12 +86,12 @@ ColorEncoding read_color_encoding(BitReader& br) {  // color_encoding.rs:166-196
   bool not_xyb = c.color_space != ColorSpace::XYB;
   if (!c.want_icc && not_xyb) {
     c.white_point = read_enum(br);
-    if (c.white_point == 2) read_custom_xy(br);
+    if (c.white_point == 2) read_custom_xy(br, c.white_xy);
   }
   if (!c.want_icc && not_xyb && c.color_space != ColorSpace::Gray) {
     c.primaries = read_enum(br);
     if (c.primaries == 2)
-      for (int i = 0; i < 3; i++) read_custom_xy(br);
+      for (int i = 0; i < 3; i++) read_custom_xy(br, c.primaries_xy[i]);
   }
   if (!c.want_icc) {
     if (not_xyb) c.have_gamma = br.read_bool();
@@ -430,6 +434,154 @@ Toc read_toc(BitReader& br, uint32_t num_entries) {
     toc.lengths[i] = toc.sizes[src];
   }
   return toc;
+}
+
+void check_single_still_frame(const FileHeader& fh, const FrameHeader& h) {
+  if (fh.have_animation) fail("animations are outside the hot-path scope", kErrUnsupported);
+  if (!h.is_last) fail("multi-frame (layered) files are outside the hot-path scope", kErrUnsupported);
+  if (h.duration != 0 || h.save_as_reference != 0) fail("frames with a duration / reference slot are outside the hot-path scope", kErrUnsupported);
+  if (fh.orientation < 1 || fh.orientation > 8) fail("bad orientation");
+}
+
+namespace {
+// util/linalg.rs:29-110 and api/color.rs:124-275, in double precision like the reference.
+struct M3 {
+  double m[3][3];
+};
+M3 mul(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+  return r;
+}
+void mulv(const M3& a, const double* v, double* out) {
+  for (int i = 0; i < 3; i++) out[i] = a.m[i][0] * v[0] + a.m[i][1] * v[1] + a.m[i][2] * v[2];
+}
+M3 inverse(const M3& a) {
+  const double (*m)[3] = a.m;
+  const double det = m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                     m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  if (!(std::fabs(det) > 1e-10)) fail("singular colour matrix");
+  const double id = 1.0 / det;
+  M3 r;
+  r.m[0][0] = (m[1][1] * m[2][2] - m[2][1] * m[1][2]) * id;
+  r.m[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id;
+  r.m[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+  r.m[1][0] = (m[1][2] * m[2][0] - m[1][0] * m[2][2]) * id;
+  r.m[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id;
+  r.m[1][2] = (m[1][0] * m[0][2] - m[0][0] * m[1][2]) * id;
+  r.m[2][0] = (m[1][0] * m[2][1] - m[2][0] * m[1][1]) * id;
+  r.m[2][1] = (m[2][0] * m[0][1] - m[0][0] * m[2][1]) * id;
+  r.m[2][2] = (m[0][0] * m[1][1] - m[1][0] * m[0][1]) * id;
+  return r;
+}
+void check_white(float wx, float wy) {
+  if (!(wx >= 0.0f && wx <= 1.0f && wy > 0.0f && wy <= 1.0f)) fail("white point out of range");
+}
+// api/color.rs:124-190: RGB -> XYZ relative to the encoding's own white point.
+M3 primaries_to_xyz(const float (*p)[2], float wx, float wy) {
+  check_white(wx, wy);
+  M3 pm;
+  for (int i = 0; i < 3; i++) {
+    pm.m[0][i] = double(p[i][0]);
+    pm.m[1][i] = double(p[i][1]);
+    pm.m[2][i] = 1.0 - double(p[i][0]) - double(p[i][1]);
+  }
+  const M3 pinv = inverse(pm);
+  const double w[3] = {double(wx) / double(wy), 1.0, (1.0 - double(wx) - double(wy)) / double(wy)};
+  double sv[3];
+  mulv(pinv, w, sv);
+  M3 sd{{{sv[0], 0, 0}, {0, sv[1], 0}, {0, 0, sv[2]}}};
+  return mul(pm, sd);
+}
+// api/color.rs:193-252: Bradford adaptation of the white point to D50.
+M3 adapt_to_xyz_d50(float wx, float wy) {
+  check_white(wx, wy);
+  static const M3 kBradford{{{0.8951, 0.2664, -0.1614}, {-0.7502, 1.7135, 0.0367}, {0.0389, -0.0685, 1.0296}}};
+  static const M3 kBradfordInv{{{0.9869929, -0.1470543, 0.1599627}, {0.4323053, 0.5183603, 0.0492912}, {-0.0085287, 0.0400428, 0.9684867}}};
+  const double w[3] = {double(wx) / double(wy), 1.0, (1.0 - double(wx) - double(wy)) / double(wy)};
+  const double w50[3] = {0.96422, 1.0, 0.82521};
+  double ls[3], l50[3];
+  mulv(kBradford, w, ls);
+  mulv(kBradford, w50, l50);
+  M3 a{{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}};
+  for (int i = 0; i < 3; i++) {
+    if (ls[i] == 0.0) fail("white point with a zero LMS component");
+    a.m[i][i] = l50[i] / ls[i];
+  }
+  return mul(kBradfordInv, mul(a, kBradford));
+}
+}  // namespace
+
+OutputColour resolve_output_colour(const FileHeader& fh) {
+  const ColorEncoding& c = fh.color_encoding;
+  OutputColour oc;
+  memcpy(oc.matrix, fh.opsin.inverse_matrix, sizeof(oc.matrix));
+  if (c.want_icc) {
+    oc.from_icc = true;
+    return oc;
+  }
+  if (c.all_default) return oc;  // RGB, D65, sRGB primaries, sRGB curve
+  if (c.color_space == ColorSpace::XYB || c.color_space == ColorSpace::Unknown)
+    fail("XYB / unknown colour spaces have no simple output profile (outside the hot-path scope)", kErrUnsupported);
+  // api/color.rs:319-326, 363-393 (the sRGB primaries are libjxl's rounded-through-f32 values)
+  static const float kSrgbPrim[3][2] = {{0.6399987f, 0.33001015f}, {0.3000038f, 0.60000336f}, {0.15000205f, 0.059997204f}};
+  static const float kBt2100Prim[3][2] = {{0.708f, 0.292f}, {0.170f, 0.797f}, {0.131f, 0.046f}};
+  static const float kP3Prim[3][2] = {{0.680f, 0.320f}, {0.265f, 0.690f}, {0.150f, 0.060f}};
+  float wx = 0.3127f, wy = 0.3290f;
+  switch (c.white_point) {
+    case 1: break;
+    case 2: wx = float(c.white_xy[0]) / 1000000.0f; wy = float(c.white_xy[1]) / 1000000.0f; break;
+    case 10: wx = wy = 1.0f / 3.0f; break;
+    case 11: wx = 0.314f; wy = 0.351f; break;
+    default: fail("unknown white point");
+  }
+  M3 inv;
+  for (int i = 0; i < 9; i++) inv.m[i / 3][i % 3] = double(fh.opsin.inverse_matrix[i]);
+  if (c.color_space == ColorSpace::Gray) {
+    if (c.white_point != 1) fail("grey with a non-D65 white point needs a CMS (outside the hot-path scope)", kErrUnsupported);
+    M3 lum;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) lum.m[i][j] = double(oc.luminances[j]);
+    inv = mul(lum, inv);
+  } else {
+    float prim[3][2];
+    switch (c.primaries) {
+      case 1: memcpy(prim, kSrgbPrim, sizeof(prim)); break;
+      case 2:
+        for (int i = 0; i < 3; i++)
+          for (int k = 0; k < 2; k++) prim[i][k] = float(c.primaries_xy[i][k]) / 1000000.0f;
+        break;
+      case 9: memcpy(prim, kBt2100Prim, sizeof(prim)); break;
+      case 11: memcpy(prim, kP3Prim, sizeof(prim)); break;
+      default: fail("unknown primaries");
+    }
+    if (c.primaries != 1 || c.white_point != 1) {  // xyb.rs:92-107
+      const M3 srgb_to_xyzd50 = mul(adapt_to_xyz_d50(0.3127f, 0.3290f), primaries_to_xyz(kSrgbPrim, 0.3127f, 0.3290f));
+      const M3 original_to_xyz = primaries_to_xyz(prim, wx, wy);
+      for (int j = 0; j < 3; j++) oc.luminances[j] = float(original_to_xyz.m[1][j]);
+      const M3 original_to_xyzd50 = mul(adapt_to_xyz_d50(wx, wy), original_to_xyz);
+      const M3 srgb_to_original = mul(inverse(original_to_xyzd50), srgb_to_xyzd50);
+      inv = mul(srgb_to_original, inv);
+    }
+  }
+  for (int i = 0; i < 9; i++) oc.matrix[i] = float(inv.m[i / 3][i % 3]);
+  if (c.have_gamma) {  // color_encoding.rs:145-158
+    oc.tf = 2;
+    oc.gamma = float(c.gamma) * 0.0000001f;
+    if (oc.gamma > 1.0f || oc.gamma * 8192.0f < 1.0f) fail("invalid gamma");
+    return oc;
+  }
+  switch (c.tf) {  // xyb.rs:122-133
+    case TransferFunction::SRGB: oc.tf = 1; break;
+    case TransferFunction::Linear: oc.tf = 0; break;  // Gamma(1.0): the reference skips the stage (frame/render.rs:761)
+    case TransferFunction::BT709: oc.tf = 3; break;
+    case TransferFunction::PQ: oc.tf = 4; break;
+    case TransferFunction::HLG: oc.tf = 5; break;
+    case TransferFunction::DCI: oc.tf = 2; oc.gamma = 1.0f / 2.6f; break;
+    default: fail("unknown transfer function");
+  }
+  return oc;
 }
 
 }  // namespace jxg

@@ -34,8 +34,10 @@ struct ColorEncoding {
   bool all_default = true;
   bool want_icc = false;
   ColorSpace color_space = ColorSpace::RGB;
-  uint32_t white_point = 1;  // D65
-  uint32_t primaries = 1;    // sRGB
+  uint32_t white_point = 1;  // D65 = 1, Custom = 2, E = 10, DCI = 11
+  uint32_t primaries = 1;    // sRGB = 1, Custom = 2, BT2100 = 9, P3 = 11
+  int32_t white_xy[2] = {0, 0};        // CustomXY, in 1e-6 units (color_encoding.rs:91-106)
+  int32_t primaries_xy[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   bool have_gamma = false;
   uint32_t gamma = 0;
   TransferFunction tf = TransferFunction::SRGB;
@@ -169,6 +171,26 @@ FrameHeader read_frame_header(BitReader& br, const FileHeader& fh);
 
 // toc.rs:20-32 + frame/decode.rs:263-285 (sections(): permutation applied).
 Toc read_toc(BitReader& br, uint32_t num_entries);
+
+// Scope guard shared by the VarDCT and the Modular front-ends: one still frame. Layered / animated files
+// (FrameHeader.is_last == false, ImageMetadata.have_animation, a duration) would need blending of several frames
+// (frame/render.rs:503); decoding only the first frame would silently differ from the reference, so these are refused
+// with kErrUnsupported. (Orientation is applied by the store, as the reference's save stage does.)
+void check_single_still_frame(const FileHeader& fh, const FrameHeader& h);
+
+// Output colour of an XYB image: render/stages/xyb.rs:65-140 OutputColorInfo::from_header (opsin matrix re-targeted to
+// the embedded primaries / white point, grey luminances folded in, embedded transfer function) plus the profile
+// choice of api/inner/codestream_parser/image_info.rs:204-237 (an ICC-tagged image cannot be output to: integer
+// samples get sRGB, float samples linear sRGB -> from_icc). Grey with a non-D65 white point and the XYB colour space
+// (no simple output profile, color.rs:1287-1300) are refused with kErrUnsupported.
+struct OutputColour {
+  bool from_icc = false;
+  uint32_t tf = 1;         // JXG_TF_* of the embedded encoding (ignored when from_icc)
+  float gamma = 1.0f;      // exponent of JXG_TF_GAMMA
+  float matrix[9];         // opsin inverse matrix, re-targeted
+  float luminances[3] = {0.2126f, 0.7152f, 0.0722f};  // Y row of the output primaries (HLG OOTF)
+};
+OutputColour resolve_output_colour(const FileHeader& fh);
 
 float f16_bits_to_float(uint16_t h);
 float read_f16(BitReader& br);  // encodings.rs:59-74 (rejects NaN/Inf)

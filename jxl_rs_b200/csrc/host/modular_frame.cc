@@ -50,8 +50,7 @@ void decode_lf_global_modular(ModularFrameState& ms, BitReader& br) {
   const FrameHeader& h = ms.header;
   if (h.has_patches()) fail("patches are outside the hot-path scope", kErrUnsupported);
   if (h.has_splines()) fail("splines are outside the hot-path scope", kErrUnsupported);
-  if (h.has_noise())
-    for (int i = 0; i < 8; i++) br.read(10);
+  if (h.has_noise()) fail("noise synthesis is outside the hot-path scope", kErrUnsupported);
   if (!br.read_bool())  // LfQuantFactors (quantizer.rs:28-52): present but unused by Modular frames
     for (int i = 0; i < 3; i++) read_f16(br);
   if (br.read_bool()) {
@@ -225,6 +224,7 @@ std::unique_ptr<ModularFrameState> parse_modular_file(const uint8_t* data, size_
   if (h.has_lf_frame()) fail("LF frames are outside the hot-path scope", kErrUnsupported);
   if (h.have_crop || h.blending.mode != 0) fail("cropped/blended frames are outside the hot-path scope", kErrUnsupported);
   if (h.passes.num_passes != 1) fail("multi-pass Modular frames are outside the scope", kErrUnsupported);
+  check_single_still_frame(ms.file, h);
   if (ms.file.bit_depth.floating_point || ms.file.bit_depth.bits_per_sample != 8)
     fail("only 8-bit integer samples are in scope", kErrUnsupported);
   ms.num_color_channels = ms.file.color_encoding.color_space == ColorSpace::Gray ? 1 : 3;

@@ -44,6 +44,7 @@ class ParsedFrame:
 
     @property
     def width(self):
+        """Output (display-orientation) width: what the caller's buffer must hold."""
         return self.info.width
 
     @property
@@ -143,7 +144,7 @@ class Batch:
         return out.reshape(self.frames[f].info.num_groups, 3, 65536)
 
     def read_xyb(self, f: int, stage: int):
-        w, h = self.frames[f].width, self.frames[f].height
+        w, h = self.frames[f].info.coded_width, self.frames[f].info.coded_height
         ps, pr = (w + 7) // 8 * 8, (h + 7) // 8 * 8
         out = np.empty(3 * ps * pr, np.float32)
         abi.check(self._lib, self._lib.jxg_batch_read_xyb(self._h, f, stage, out.ctypes.data_as(C.c_void_p), out.size))
@@ -393,7 +394,7 @@ class ModularBatch:
     def read_planes(self, f: int):
         import numpy as np
         fr = self.frames[f]
-        out = np.zeros((3, fr.height, fr.width), np.int32)
+        out = np.zeros((3, fr.info.coded_height, fr.info.coded_width), np.int32)
         abi.check(self._lib, self._lib.jxg_modular_batch_read_planes(self._h, f, out.ctypes.data, out.size))
         return out
 

@@ -57,8 +57,9 @@ int jxo_modular_info(const uint8_t* data, size_t size, uint32_t* width, uint32_t
                      uint32_t* num_groups) {
   try {
     auto ms = jxg::parse_modular_file(data, size);
-    *width = ms->header.xsize();
-    *height = ms->header.ysize();
+    const bool tr = ms->file.orientation >= 5;  // display size (render/save.rs)
+    *width = tr ? ms->header.ysize() : ms->header.xsize();
+    *height = tr ? ms->header.xsize() : ms->header.ysize();
     *channels = ms->num_color_channels;
     *num_groups = ms->header.num_groups();
     return 0;
@@ -68,12 +69,30 @@ int jxo_modular_info(const uint8_t* data, size_t size, uint32_t* width, uint32_t
   }
 }
 
+// ImageMetadata.orientation of the file (1..8), or 1 when it does not parse.
+int jxo_modular_orientation(const uint8_t* data, size_t size) {
+  try {
+    return int(jxg::parse_modular_file(data, size)->file.orientation);
+  } catch (jxg::Error&) {
+    return 1;
+  }
+}
+
 // out: interleaved RGB u8 (grey is replicated); planes (optional): 3 full-size i32 planes before the u8 conversion.
 int jxo_decode_modular_file(const uint8_t* data, size_t size, uint8_t* out, size_t out_row_stride, int32_t* planes) {
   try {
     auto ms = jxg::parse_modular_file(data, size);
     std::vector<jxg::ModularChannel> ch = decode_modular_frame_cpu(*ms);
     const uint32_t w = ms->header.xsize(), h = ms->header.ysize();
+    const uint32_t orientation = ms->file.orientation;
+    std::vector<uint8_t> staging;
+    uint8_t* const user_out = out;
+    const size_t user_stride = out_row_stride;
+    if (orientation != 1) {
+      staging.resize(size_t(w) * h * 3);
+      out = staging.data();
+      out_row_stride = size_t(w) * 3;
+    }
     for (uint32_t c = 0; c < 3; c++) {
       const jxg::ModularChannel& src = ch[std::min<size_t>(c, ch.size() - 1)];
       if (src.w != w || src.h != h) throw jxg::Error(jxg::kErrBitstream, "unexpected output channel size");
@@ -84,6 +103,7 @@ int jxo_decode_modular_file(const uint8_t* data, size_t size, uint8_t* out, size
         for (uint32_t x = 0; x < w; x++) o[size_t(x) * 3] = uint8_t(std::min(std::max(r[x], 0), 255));  // convert.rs:675-680
       }
     }
+    if (orientation != 1) jxo_orient_image(staging.data(), w, h, 3, orientation, user_out, user_stride);
     return 0;
   } catch (jxg::Error& e) {
     g_jxo_modular_error = e.what();

@@ -826,6 +826,99 @@ inline float linear_to_srgb(float v) {
   }
   return std::copysign(r, v);
 }
+// util/rational_poly.rs:20-35 (SIMD form: mul_add chains)
+inline float rational_poly5(float x, const float* p, const float* q) {
+  float yp = p[4], yq = q[4];
+  for (int i = 3; i >= 0; i--) {
+    yp = std::fmaf(yp, x, p[i]);
+    yq = std::fmaf(yq, x, q[i]);
+  }
+  return yp / yq;
+}
+// util/fast_math.rs:98-114 (fast_pow2f_simd), :140-149 (fast_log2f_simd), :158-160
+inline float fast_pow2f(float x) {
+  const float kNum[3] = {1.01749063e1f, 4.88687798e1f, 9.85506591e1f};
+  const float kDen[4] = {2.10242958e-1f, -2.22328856e-2f, -1.94414990e1f, 9.85506633e1f};
+  const float x_floor = std::floor(x);
+  const uint32_t ebits = uint32_t(int32_t(x_floor) + 127) << 23;
+  float exp;
+  memcpy(&exp, &ebits, 4);
+  const float frac = x - x_floor;
+  float num = frac + kNum[0];
+  num = std::fmaf(num, frac, kNum[1]);
+  num = std::fmaf(num, frac, kNum[2]);
+  num = num * exp;
+  float den = std::fmaf(kDen[0], frac, kDen[1]);
+  den = std::fmaf(den, frac, kDen[2]);
+  den = std::fmaf(den, frac, kDen[3]);
+  return num / den;
+}
+inline float fast_log2f(float x) {
+  const float kP[3] = {-1.8503833400518310e-6f, 1.4287160470083755f, 7.4245873327820566e-1f};
+  const float kQ[3] = {9.9032814277590719e-1f, 1.0096718572241148f, 1.7409343003366853e-1f};
+  int32_t x_bits;
+  memcpy(&x_bits, &x, 4);
+  const int32_t exp_bits = int32_t(uint32_t(x_bits) - 0x3f2aaaabu);
+  const int32_t exp_shifted = exp_bits >> 23;
+  const uint32_t mbits = uint32_t(x_bits) - (uint32_t(exp_shifted) << 23);
+  float mantissa;
+  memcpy(&mantissa, &mbits, 4);
+  const float m1 = mantissa - 1.0f;
+  const float yp = std::fmaf(std::fmaf(kP[2], m1, kP[1]), m1, kP[0]);
+  const float yq = std::fmaf(std::fmaf(kQ[2], m1, kQ[1]), m1, kQ[0]);
+  return yp / yq + float(exp_shifted);
+}
+inline float fast_powf(float base, float e) { return fast_pow2f(fast_log2f(base) * e); }
+
+// a16 (other encodings). render/stages/from_linear.rs:56-112 on one RGB triple.
+inline void from_linear_other(const JxgFrameDesc& d, float* v) {
+  switch (d.output_tf) {
+    case JXG_TF_GAMMA:  // from_linear.rs:97-109
+      for (int c = 0; c < 3; c++) v[c] = std::copysign(fast_powf(std::fabs(v[c]), d.output_gamma), v[c]);
+      break;
+    case JXG_TF_BT709: {  // color/tf.rs:114-150
+      const float P[5] = {-9.625309705734253e-2f, -2.2635456919670105e-1f, 1.935774803161621e1f, 5.897886276245117e1f, 2.3947298049926758e1f};
+      const float Q[5] = {1.0f, 1.877663230895996e1f, 5.5292449951171875e1f, 2.6565317153930664e1f, 3.269049823284149e-1f};
+      for (int c = 0; c < 3; c++) {
+        const float a = std::fabs(v[c]);
+        v[c] = std::copysign(0.018f > a ? a * 4.5f : rational_poly5(std::sqrt(a), P, Q), v[c]);
+      }
+      break;
+    }
+    case JXG_TF_PQ: {  // color/tf.rs:236-304
+      const float P[5] = {1.351392e-2f, -1.095778f, 5.522776e1f, 1.492516e2f, 4.838434e1f};
+      const float Q[5] = {1.012416f, 2.016708e1f, 9.26371e1f, 1.120607e2f, 2.590418e1f};
+      const float PS[5] = {9.863406e-6f, 3.881234e-1f, 1.352821e2f, 6.889862e4f, -2.864824e5f};
+      const float QS[5] = {3.371868e1f, 1.477719e3f, 1.608477e4f, -4.389884e4f, -2.072546e5f};
+      const float y_mult = d.intensity_target * (1.0f / 10000.0f);
+      for (int c = 0; c < 3; c++) {
+        const float a = std::fabs(v[c]);
+        const float a14 = std::sqrt(std::sqrt(a * y_mult));
+        v[c] = std::copysign(1e-4f > a ? rational_poly5(a14, PS, QS) : rational_poly5(a14, P, Q), v[c]);
+      }
+      break;
+    }
+    case JXG_TF_HLG: {  // color/tf.rs:381-395, 458-470, 481-497
+      const float system_gamma = 1.2f * std::pow(1.111f, std::log2(d.intensity_target / 1e3f));
+      const float e = (1.0f - system_gamma) / system_gamma;
+      if (!(std::fabs(e) < 0.1f)) {
+        const float mixed = std::fmaf(v[0], d.output_luminances[0], std::fmaf(v[1], d.output_luminances[1], v[2] * d.output_luminances[2]));
+        const float mult = fast_powf(mixed, e);
+        for (int c = 0; c < 3; c++) v[c] *= mult;
+      }
+      const double kA = 0.17883277, kB = 1.0 - 4.0 * kA, kC = 0.5599107295;
+      for (int c = 0; c < 3; c++) {
+        const float a = std::fabs(v[c]);
+        float y;
+        if (a <= 1.0f / 12.0f) y = std::sqrt(3.0f * a);
+        else y = float(kA * 0.693147180559945309417) * fast_log2f(12.0f * a - float(kB)) + float(kC);
+        v[c] = std::copysign(y, v[c]);
+      }
+      break;
+    }
+    default: break;  // JXG_TF_LINEAR: no stage (frame/render.rs:761)
+  }
+}
 const float kDither[32 * 32] = {
 #include "dither_table.inc"
 };
@@ -917,14 +1010,28 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
     bias_cbrt[i] = std::cbrt(d.opsin_biases[i]);
     scaled_bias[i] = d.opsin_biases[i] * intensity_scale;
   }
+  // Orientation (render/save.rs + headers/image_metadata.rs:85-96): the coded image is produced into a tight staging
+  // image first and every pixel moved to display_pixel(x, y) afterwards.
+  const uint32_t orientation = d.orientation == 0 ? 1u : d.orientation;
+  const size_t obpp = d.output_format == JXG_FORMAT_RGB_F32 ? 12 : (d.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 3);
+  std::vector<uint8_t> staging;
+  uint8_t* obase = static_cast<uint8_t*>(out);
+  size_t ostride = out_row_stride;
+  if (orientation != 1) {
+    staging.resize(geo.width * geo.height * obpp);
+    obase = staging.data();
+    ostride = geo.width * obpp;
+  }
   parallel_for(int(geo.height), num_threads, [&](int yi) {
     size_t y = size_t(yi);
-    uint8_t* row = static_cast<uint8_t*>(out) + y * out_row_stride;
+    uint8_t* row = obase + y * ostride;
     for (size_t x = 0; x < geo.width; x++) {
       float v[3] = {cur.p[0][y * pstride + x], cur.p[1][y * pstride + x], cur.p[2][y * pstride + x]};
       xyb_to_linear_px(v[0], v[1], v[2], d.opsin_inverse_matrix, bias_cbrt, scaled_bias, intensity_scale);
       if (d.output_tf == JXG_TF_SRGB)
         for (float& f : v) f = linear_to_srgb(f);
+      else
+        from_linear_other(d, v);
       if (d.output_format == JXG_FORMAT_RGB_F32) {
         memcpy(row + x * 12, v, 12);
       } else {
@@ -939,14 +1046,19 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
       }
     }
   });
+  if (orientation != 1)
+    jxo_orient_image(staging.data(), geo.width, geo.height, obpp, orientation, static_cast<uint8_t*>(out), out_row_stride);
   return 0;
 }
 
 int jxo_file_info(const uint8_t* data, size_t size, JxgImageInfo* info) {
   try {
     auto fs = jxg::parse_vardct_file(data, size);
-    info->width = fs->header.xsize();
-    info->height = fs->header.ysize();
+    info->coded_width = fs->header.xsize();
+    info->coded_height = fs->header.ysize();
+    info->orientation = fs->file.orientation;
+    info->width = fs->file.orientation >= 5 ? info->coded_height : info->coded_width;
+    info->height = fs->file.orientation >= 5 ? info->coded_width : info->coded_height;
     info->num_groups = fs->header.num_groups();
     info->num_passes = fs->header.passes.num_passes;
     info->encoding = 0;
@@ -976,6 +1088,24 @@ int jxo_decode_file(const uint8_t* data, size_t size, uint32_t output_format, vo
   }
 }
 
+void jxo_orient_image(const uint8_t* src, size_t w, size_t h, size_t bpp, uint32_t orientation, uint8_t* dst, size_t dst_stride) {
+  for (size_t y = 0; y < h; y++)
+    for (size_t x = 0; x < w; x++) {
+      size_t dx = x, dy = y;
+      switch (orientation) {
+        case 2: dx = w - 1 - x; break;                  // FlipHorizontal
+        case 3: dx = w - 1 - x; dy = h - 1 - y; break;  // Rotate180
+        case 4: dy = h - 1 - y; break;                  // FlipVertical
+        case 5: dx = y; dy = x; break;                  // Transpose
+        case 6: dx = h - 1 - y; dy = x; break;          // Rotate90Cw
+        case 7: dx = h - 1 - y; dy = w - 1 - x; break;  // AntiTranspose
+        case 8: dx = y; dy = w - 1 - x; break;          // Rotate90Ccw
+        default: break;
+      }
+      memcpy(dst + dy * dst_stride + dx * bpp, src + (y * w + x) * bpp, bpp);
+    }
+}
+
 void jxo_idct2d(int rows, int cols, float* block) { idct2d(rows, cols, block); }
 void jxo_reinterpreting_dct2d(int rows, int cols, const float* in, float* out, int out_stride) {
   reinterpreting_dct2d(rows, cols, in, out, out_stride);
@@ -992,6 +1122,21 @@ void jxo_xyb_to_linear(int n, float* x, float* y, float* b, const float* opsin_m
     scaled_bias[i] = opsin_biases[i] * is;
   }
   for (int i = 0; i < n; i++) xyb_to_linear_px(x[i], y[i], b[i], opsin_matrix, bias_cbrt, scaled_bias, is);
+}
+// from_linear stage of the oracle on n RGB triples (interleaved), for the known-answer tests of the other encodings.
+void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const float* luminances, int n, float* rgb) {
+  JxgFrameDesc d;
+  memset(&d, 0, sizeof(d));
+  d.output_tf = tf;
+  d.output_gamma = gamma;
+  d.intensity_target = intensity_target;
+  memcpy(d.output_luminances, luminances, 12);
+  for (int i = 0; i < n; i++) {
+    if (tf == JXG_TF_SRGB)
+      for (int c = 0; c < 3; c++) rgb[3 * i + c] = linear_to_srgb(rgb[3 * i + c]);
+    else
+      from_linear_other(d, rgb + 3 * i);
+  }
 }
 void jxo_linear_to_srgb(int n, float* v) {
   for (int i = 0; i < n; i++) v[i] = linear_to_srgb(v[i]);

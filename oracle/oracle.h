@@ -58,6 +58,10 @@ void jxo_gaborish(int w, int h, const float* in, float* out, float w1, float w2)
 void jxo_xyb_to_linear(int n, float* x, float* y, float* b, const float* opsin_matrix, const float* opsin_biases,
                        float intensity_target);
 void jxo_linear_to_srgb(int n, float* v);
+void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const float* luminances, int n, float* rgb);
+/* ImageMetadata.orientation (headers/image_metadata.rs:85-96 display_pixel): pixel (x, y) of the tight w x h source goes
+ * to display_pixel(x, y) of `dst` (row stride dst_stride; h x w for orientations 5..8). */
+void jxo_orient_image(const uint8_t* src, size_t w, size_t h, size_t bpp, uint32_t orientation, uint8_t* dst, size_t dst_stride);
 
 #ifdef __cplusplus
 }

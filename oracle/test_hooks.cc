@@ -182,4 +182,32 @@ uint64_t jxo_t_parse_digest(const uint8_t* data, size_t size, int threads) {
 
 // 0: serial parses decode their LF groups one at a time instead of in lockstep pairs (differential tests).
 void jxo_t_pair_lf_groups(int on) { set_pair_lf_groups(on != 0); }
+
+// Output colour derivation of the host front-end (headers.cc resolve_output_colour <- render/stages/xyb.rs:65-140) for
+// a non-ICC colour encoding given by its header fields; the opsin inverse matrix is the default one. Returns the error
+// code on refusal. out: 9 matrix entries, 3 luminances, tf, gamma.
+int jxo_t_output_colour(uint32_t color_space, uint32_t white_point, const int32_t* white_xy, uint32_t primaries,
+                        const int32_t* prim_xy, int have_gamma, uint32_t gamma, uint32_t tf, float* out) {
+  try {
+    FileHeader fh;
+    ColorEncoding& c = fh.color_encoding;
+    c.all_default = false;
+    c.color_space = ColorSpace(color_space);
+    c.white_point = white_point;
+    c.primaries = primaries;
+    if (white_xy) memcpy(c.white_xy, white_xy, sizeof(c.white_xy));
+    if (prim_xy) memcpy(c.primaries_xy, prim_xy, sizeof(c.primaries_xy));
+    c.have_gamma = have_gamma != 0;
+    c.gamma = gamma;
+    c.tf = TransferFunction(tf);
+    const OutputColour oc = resolve_output_colour(fh);
+    memcpy(out, oc.matrix, 36);
+    memcpy(out + 9, oc.luminances, 12);
+    out[12] = float(oc.tf);
+    out[13] = oc.gamma;
+    return 0;
+  } catch (Error& e) {
+    return e.code;
+  }
+}
 }

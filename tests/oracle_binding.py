@@ -52,23 +52,24 @@ def decode_file(data: bytes, fmt=abi.FORMAT_RGB_U8, taps=False, threads=0):
     """Returns (pixels, taps dict). pixels: HxWx3 u8 / HxWx4 u8 / HxWx3 f32."""
     lib = load()
     info = file_info(data)
-    w, h = info.width, info.height
+    w, h = info.width, info.height              # display orientation
+    cw, ch = info.coded_width, info.coded_height  # as coded: parity taps and the XYB debug format
     if fmt == abi.FORMAT_RGB_F32:
         out = np.zeros((h, w, 3), np.float32)
     elif fmt == abi.FORMAT_RGBA_U8:
         out = np.zeros((h, w, 4), np.uint8)
     elif fmt == abi.FORMAT_XYB_F32_PLANAR:
-        out = np.zeros((3, h, w), np.float32)
+        out = np.zeros((3, ch, cw), np.float32)
     else:
         out = np.zeros((h, w, 3), np.uint8)
     stride = out.strides[0] if fmt != abi.FORMAT_XYB_F32_PLANAR else out.strides[1]
     t = None
     tap_arrays = {}
     if taps:
-        ps, pr = (w + 7) // 8 * 8, (h + 7) // 8 * 8
+        ps, pr = (cw + 7) // 8 * 8, (ch + 7) // 8 * 8
         tap_arrays["coeffs"] = np.zeros((info.num_groups, 3, 65536), np.int32)
         tap_arrays["xyb_idct"] = np.zeros((3, pr, ps), np.float32)
-        tap_arrays["xyb_filtered"] = np.zeros((3, h, w), np.float32)
+        tap_arrays["xyb_filtered"] = np.zeros((3, ch, cw), np.float32)
         t = JxoTaps(tap_arrays["coeffs"].ctypes.data, tap_arrays["xyb_idct"].ctypes.data, tap_arrays["xyb_filtered"].ctypes.data)
     r = lib.jxo_decode_file(data, len(data), fmt, out.ctypes.data, stride, C.byref(t) if t else None, threads)
     if r != 0:
@@ -81,6 +82,7 @@ def _load_modular():
     if not getattr(lib, "_modular_ready", False):
         lib.jxo_modular_last_error.restype = C.c_char_p
         lib.jxo_modular_info.argtypes = [C.c_char_p, C.c_size_t] + [C.POINTER(C.c_uint32)] * 4
+        lib.jxo_modular_orientation.argtypes = [C.c_char_p, C.c_size_t]
         lib.jxo_decode_modular_file.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         lib._modular_ready = True
     return lib
@@ -101,7 +103,8 @@ def decode_modular_file(data: bytes, planes=False):
     lib = _load_modular()
     w, h, _, _ = modular_info(data)
     out = np.zeros((h, w, 3), np.uint8)
-    pl = np.zeros((3, h, w), np.int32) if planes else None
+    transposed = lib.jxo_modular_orientation(data, len(data)) >= 5
+    pl = (np.zeros((3, w, h), np.int32) if transposed else np.zeros((3, h, w), np.int32)) if planes else None  # as coded
     r = lib.jxo_decode_modular_file(data, len(data), out.ctypes.data, out.strides[0], pl.ctypes.data if planes else None)
     if r != 0:
         raise abi.JxgError(r, lib.jxo_modular_last_error().decode())
