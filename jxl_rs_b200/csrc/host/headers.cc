@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "entropy.h"
@@ -437,6 +438,12 @@ Toc read_toc(BitReader& br, uint32_t num_entries) {
 }
 
 void check_single_still_frame(const FileHeader& fh, const FrameHeader& h) {
+  // A few header bytes can announce 2^30 x 2^30 pixels; refuse before any plane is sized from them. JXG_MAX_PIXELS
+  // (default 2^29, twice BASELINE config 4) is the knob for hosts with the memory for more.
+  uint64_t max_pixels = uint64_t(1) << 29;
+  if (const char* e = getenv("JXG_MAX_PIXELS")) max_pixels = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  if (uint64_t(h.xsize()) * h.ysize() > max_pixels || uint64_t(fh.xsize) * fh.ysize > max_pixels)
+    fail("image larger than JXG_MAX_PIXELS", kErrUnsupported);
   if (fh.have_animation) fail("animations are outside the hot-path scope", kErrUnsupported);
   if (!h.is_last) fail("multi-frame (layered) files are outside the hot-path scope", kErrUnsupported);
   if (h.duration != 0 || h.save_as_reference != 0) fail("frames with a duration / reference slot are outside the hot-path scope", kErrUnsupported);

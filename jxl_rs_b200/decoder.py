@@ -178,18 +178,20 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
         frames = [ParsedFrame(f, per_file) for f in files]
     batch = Batch(ctx, len(frames))
     outs = []
-    for fr in frames:
-        ch = 4 if fmt == abi.FORMAT_RGBA_U8 else 3
-        dt = torch.float32 if fmt == abi.FORMAT_RGB_F32 else torch.uint8
-        if to_host:
-            t = torch.empty((fr.height, fr.width, ch), dtype=dt).pin_memory()
-        else:
-            t = torch.empty((fr.height, fr.width, ch), dtype=dt, device=f"cuda:{ctx.device}")
-        outs.append(t)
-        batch.add(fr, t.data_ptr(), fr.width * ch * t.element_size(), fmt, not to_host)
-    batch.run()
-    batch.wait()
-    batch.close()
+    try:  # a corrupt frame must not leave the context with a live batch
+        for fr in frames:
+            ch = 4 if fmt == abi.FORMAT_RGBA_U8 else 3
+            dt = torch.float32 if fmt == abi.FORMAT_RGB_F32 else torch.uint8
+            if to_host:
+                t = torch.empty((fr.height, fr.width, ch), dtype=dt).pin_memory()
+            else:
+                t = torch.empty((fr.height, fr.width, ch), dtype=dt, device=f"cuda:{ctx.device}")
+            outs.append(t)
+            batch.add(fr, t.data_ptr(), fr.width * ch * t.element_size(), fmt, not to_host)
+        batch.run()
+        batch.wait()
+    finally:
+        batch.close()
     return outs
 
 

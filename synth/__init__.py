@@ -18,6 +18,7 @@ def _lib():
         _LIB.jxs_encode_synthetic.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_float, C.c_uint32, C.c_uint32,
                                               C.c_uint32, C.c_void_p, C.c_size_t]
         _LIB.jxs_last_error.restype = C.c_char_p
+        _LIB.jxs_set_threads.argtypes = [C.c_int]
         _LIB.jxs_encode_modular.restype = C.c_int64
         _LIB.jxs_encode_modular.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.c_void_p, C.c_void_p, C.c_size_t]
@@ -26,11 +27,16 @@ def _lib():
     return _LIB
 
 
-def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, profile=1, lf_tree=0) -> bytes:
+def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, profile=1, lf_tree=0, entropy=0, orientation=1,
+                     colour=0) -> bytes:
     """One synthetic VarDCT frame. profile 0: DCT8x8 only; 1: mixed transforms up to 32x32;
-    2: also 64x64 / 64x32 / 32x64. lf_tree 0: LF image coded with one Gradient leaf per channel; 1: like libjxl
-    (channel prefix, then a subtree on the weighted-predictor property with Weighted-predictor leaves)."""
-    profile = (profile & 0xff) | ((lf_tree & 1) << 8)
+    2: also 64x64 / 64x32 / 32x64; 3: also the 128 / 256 families (DCT128X128 ... DCT256X256, transform types 21..26).
+    lf_tree 0: LF image coded with one Gradient leaf per channel; 1: like libjxl (channel prefix, then a subtree on the
+    weighted-predictor property with Weighted-predictor leaves). entropy 0: ANS-coded AC streams; 1: prefix codes.
+    orientation: ImageMetadata.orientation 1..8. colour: embedded colour encoding (0 sRGB, 1 linear, 2 gamma 0.45455,
+    3 P3 + PQ, 4 BT2100 + HLG, 5 custom primaries + DCI white + BT709, 6 grey, 7 E white + DCI curve)."""
+    profile = ((profile & 0xff) | ((lf_tree & 1) << 8) | ((entropy & 3) << 9) | (((orientation - 1) & 7) << 12)
+               | ((colour & 15) << 16))
     lib = _lib()
     cap = max(1 << 16, width * height * 2)
     buf = C.create_string_buffer(cap)
@@ -41,6 +47,12 @@ def encode_synthetic(width, height, seed, distance=1.0, epf_iters=2, gab=1, prof
         buf = C.create_string_buffer(n)
         n = lib.jxs_encode_synthetic(width, height, seed, distance, epf_iters, gab, profile, buf, n)
     return buf.raw[:n]
+
+
+def set_threads(n: int):
+    """Worker threads inside each following encode_synthetic call (one large image); the bitstream does not depend
+    on it. Batches of many frames keep 1 and encode frames in parallel instead."""
+    _lib().jxs_set_threads(int(n))
 
 
 def modular_source(width, height, seed):

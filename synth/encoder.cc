@@ -6,6 +6,10 @@
 //
 // Test-data tooling, not part of the product path.
 #include <algorithm>
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -37,10 +41,49 @@ struct Params {
   float distance;      // ~ butteraugli-style quality knob: larger = coarser quantisation
   uint32_t epf_iters;  // 0..3
   uint32_t gab;        // 0/1
-  uint32_t profile;    // 0 = DCT8x8 only, 1 = mixed <= 32x32 (+4x8/8x4/4x4), 2 = + 64x64 family
+  uint32_t profile;    // 0 = DCT8x8 only, 1 = mixed <= 32x32 (+4x8/8x4/4x4), 2 = + 64x64 family, 3 = + 128 / 256 families
   uint32_t lf_tree;    // coding of the LF image: 0 = one Gradient leaf per channel, 1 = libjxl-like (channel prefix,
                        // then a subtree on the weighted-predictor property 15 with Weighted leaves)
+  uint32_t entropy;    // AC coefficient streams: 0 = ANS, 1 = prefix codes (entropy_coding/huffman.rs)
+  uint32_t orientation = 1;  // ImageMetadata.orientation 1..8
+  // colour encoding written into ImageMetadata (the pixels are always produced from sRGB-primaries XYB; the variants
+  // exist to exercise the decoder's output-colour derivation): 0 default sRGB, 1 linear, 2 gamma 0.45455,
+  // 3 P3 / D65 / PQ at 1000 nits, 4 BT2100 / D65 / HLG at 1000 nits, 5 custom primaries / DCI white / BT709, 6 grey sRGB,
+  // 7 DCI transfer function with the E white point
+  uint32_t colour = 0;
 };
+
+// Worker threads inside one encode (jxs_set_threads): only loops whose result does not depend on the order of
+// evaluation are split, so the bitstream of a (size, seed, parameters) tuple is the same for every thread count.
+static std::atomic<int> g_threads{1};
+template <typename F>
+static void parallel_for(size_t n, F&& fn) {
+  const size_t nt = std::min<size_t>(size_t(std::max(1, g_threads.load())), n);
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::exception_ptr err;
+  std::mutex mu;
+  auto work = [&] {
+    try {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= n) return;
+        fn(i);
+      }
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(mu);
+      err = std::current_exception();
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
 
 // ---------------------------------------------------------------------------
 // synthetic source image (linear RGB in [0,1])
@@ -73,7 +116,8 @@ static void make_image(const Params& p, std::vector<float> (&rgb)[3]) {
         g[1][i] = 0.8f * g[0][i] + 0.2f * g[1][i];
         g[2][i] = 0.7f * g[0][i] + 0.3f * g[2][i];
       }
-    for (uint32_t y = 0; y < H; y++) {
+    parallel_for(H, [&](size_t yi) {
+      const uint32_t y = uint32_t(yi);
       uint32_t gy = y / cell;
       float fy = float(y % cell) / float(cell);
       for (uint32_t x = 0; x < W; x++) {
@@ -85,10 +129,11 @@ static void make_image(const Params& p, std::vector<float> (&rgb)[3]) {
           rgb[c][size_t(y) * W + x] += amp * v;
         }
       }
-    }
+    });
   };
   float base[3] = {0.35f + 0.2f * float(rng.uniform()), 0.35f + 0.2f * float(rng.uniform()), 0.3f + 0.2f * float(rng.uniform())};
-  for (uint32_t y = 0; y < H; y++)
+  parallel_for(H, [&](size_t yi) {
+    const uint32_t y = uint32_t(yi);
     for (uint32_t x = 0; x < W; x++) {
       for (int c = 0; c < 3; c++) {
         float v = base[c] + 0.1f * float(x) / float(W) - 0.08f * float(y) / float(H);
@@ -96,6 +141,7 @@ static void make_image(const Params& p, std::vector<float> (&rgb)[3]) {
         rgb[c][size_t(y) * W + x] = v;
       }
     }
+  });
   grid_noise(64, 0.25f, 1);
   grid_noise(16, 0.12f, 1);
   grid_noise(4, 0.09f, 1);
@@ -140,7 +186,9 @@ static void to_xyb(std::vector<float> (&rgb)[3], const jxg::OpsinInverseMatrix& 
   double bias[3] = {op.opsin_biases[0], op.opsin_biases[1], op.opsin_biases[2]};
   double cb[3] = {std::cbrt(bias[0]), std::cbrt(bias[1]), std::cbrt(bias[2])};
   size_t n = rgb[0].size();
-  for (size_t i = 0; i < n; i++) {
+  const size_t chunk = 1 << 16;
+  parallel_for((n + chunk - 1) / chunk, [&](size_t ci) {
+  for (size_t i = ci * chunk; i < std::min(n, (ci + 1) * chunk); i++) {
     double r = rgb[0][i], g = rgb[1][i], b = rgb[2][i];
     double l = inv[0] * r + inv[1] * g + inv[2] * b, mm = inv[3] * r + inv[4] * g + inv[5] * b, s = inv[6] * r + inv[7] * g + inv[8] * b;
     double lg = std::cbrt(l - bias[0]) + cb[0], mg = std::cbrt(mm - bias[1]) + cb[1], sg = std::cbrt(s - bias[2]) + cb[2];
@@ -148,6 +196,7 @@ static void to_xyb(std::vector<float> (&rgb)[3], const jxg::OpsinInverseMatrix& 
     rgb[1][i] = float((lg + mg) * 0.5);
     rgb[2][i] = float(sg);
   }
+  });
 }
 
 // ---------------------------------------------------------------------------
@@ -240,6 +289,24 @@ static void plan_transforms(Frame& f) {
     return true;
   };
   if (f.p.profile >= 1) {
+    // profile 3 first drops the largest transforms on 32x32-block (group) and 16x16-block cells:
+    // DCT256X256 (24), 256X128 (25), 128X256 (26), 128X128 (21), 128X64 (22), 64X128 (23)
+    if (f.p.profile >= 3) {
+      for (uint32_t by = 0; by < f.yb; by += 32)
+        for (uint32_t bx = 0; bx < f.xb; bx += 32) {
+          const uint32_t r = rng.below(100);
+          if (r < 15 && place(bx, by, 24)) continue;
+          if (r < 25 && place(bx, by, 25)) { place(bx + 16, by, 25); continue; }   // 256 rows x 128 cols, twice
+          if (r < 35 && place(bx, by, 26)) { place(bx, by + 16, 26); continue; }   // 128 rows x 256 cols, twice
+          for (uint32_t qy = 0; qy < 32; qy += 16)
+            for (uint32_t qx = 0; qx < 32; qx += 16) {
+              const uint32_t q = rng.below(100), x = bx + qx, y = by + qy;
+              if (q < 25) place(x, y, 21);
+              else if (q < 40) { place(x, y, 22); place(x + 8, y, 22); }           // 128 rows x 64 cols
+              else if (q < 55) { place(x, y, 23); place(x, y + 8, 23); }           // 64 rows x 128 cols
+            }
+        }
+    }
     // 4x4-block cells (32x32 px); profile 2 first drops some 8x8-block (64x64 px) transforms
     if (f.p.profile >= 2) {
       for (uint32_t by = 0; by + 8 <= f.yb; by += 8)
@@ -586,8 +653,8 @@ std::vector<uint8_t> encode(const Params& p) {
   f.coeffs.resize(f.blocks.size());
   const float inv_quant_lf = 65536.0f / (float(f.global_scale) * float(f.quant_lf));
   const float lf_fac[3] = {(1.0f / 4096.0f) * inv_quant_lf, (1.0f / 512.0f) * inv_quant_lf, (1.0f / 256.0f) * inv_quant_lf};
-  std::vector<float> co[3], lf[3];
-  for (size_t bi = 0; bi < f.blocks.size(); bi++) {
+  parallel_for(f.blocks.size(), [&](size_t bi) {
+    std::vector<float> co[3], lf[3];
     const Varblock& vb = f.blocks[bi];
     const int t = vb.t;
     const uint32_t cx = kCoveredBlocksX[t], cy = kCoveredBlocksY[t];
@@ -631,7 +698,7 @@ std::vector<uint8_t> encode(const Params& p) {
       q[k] = quant((co[0][k] - x_cc * dy) / (mat[k] * sx));
       q[2 * num_coeffs + k] = quant((co[2][k] - b_cc * dy) / (mat[2 * num_coeffs + k] * sb));
     }
-  }
+  });
   for (auto& pl : xyb) {
     pl.clear();
     pl.shrink_to_fit();
@@ -644,7 +711,8 @@ std::vector<uint8_t> encode(const Params& p) {
     for (size_t bi = 0; bi < f.blocks.size(); bi++) block_index[size_t(f.blocks[bi].by) * f.xb + f.blocks[bi].bx] = uint32_t(bi);
     std::vector<std::vector<uint32_t>> orders(13);
     for (int s = 0; s < 13; s++) orders[s] = jxg::natural_coeff_order(s);
-    for (uint32_t g = 0; g < f.num_groups; g++) {
+    parallel_for(f.num_groups, [&](size_t gi) {
+      const uint32_t g = uint32_t(gi);
       uint32_t bx0 = (g % f.xg) * 32, by0 = (g / f.xg) * 32;
       uint32_t gw = std::min(32u, f.xb - bx0), gh = std::min(32u, f.yb - by0);
       uint32_t nz[3][1024];
@@ -687,7 +755,7 @@ std::vector<uint8_t> encode(const Params& p) {
             }
           }
         }
-    }
+    });
   }
   const size_t num_ac_ctx = 15 * (37 + 458);
   std::vector<const std::vector<Token>*> ac_ptrs;
@@ -695,7 +763,7 @@ std::vector<uint8_t> encode(const Params& p) {
   uint32_t ac_clusters;
   HybridCfg cfg;
   std::vector<uint8_t> ac_map = cluster_contexts(num_ac_ctx, ac_ptrs, 48, ac_clusters, cfg);
-  AnsCode ac_code = build_code(num_ac_ctx, ac_map, ac_clusters, ac_ptrs, 6);
+  AnsCode ac_code = build_code(num_ac_ctx, ac_map, ac_clusters, ac_ptrs, 6, p.entropy == 1);
 
   // ---- sections ----
   BitWriter lf_global;
@@ -770,10 +838,10 @@ std::vector<uint8_t> encode(const Params& p) {
   write_code(hf_global, ac_code);
 
   std::vector<BitWriter> hf_groups(f.num_groups);
-  for (uint32_t g = 0; g < f.num_groups; g++) {
+  parallel_for(f.num_groups, [&](size_t g) {
     // histogram_index: ceil_log2(num_histograms = 1) = 0 bits
     write_tokens(hf_groups[g], ac_code, ac[g]);
-  }
+  });
 
   // ---- file assembly ----
   BitWriter out;
@@ -791,7 +859,84 @@ std::vector<uint8_t> encode(const Params& p) {
   write_dim(H);
   out.write(0, 3);  // ratio 0: explicit xsize
   write_dim(W);
-  out.write(1, 1);  // ImageMetadata all_default
+  if (p.orientation == 1 && p.colour == 0) {
+    out.write(1, 1);  // ImageMetadata all_default
+  } else {  // headers/image_metadata.rs:197-236
+    auto write_enum = [&](uint32_t v) {  // jxl_macros default enum coder: u2S(0, 1, Bits(4) + 2, Bits(6) + 18)
+      if (v == 0) out.u2s_sel(0);
+      else if (v == 1) out.u2s_sel(1);
+      else if (v < 18) out.u2s_sel(2, v - 2, 4);
+      else out.u2s_sel(3, v - 18, 6);
+    };
+    auto write_f16 = [&](float v) {  // exactly representable positive values only (headers/encodings.rs:59-74)
+      int e = 0;
+      float m = std::frexp(v, &e);  // v = m * 2^e, m in [0.5, 1)
+      const uint32_t mant = uint32_t(std::lround((m * 2.0f - 1.0f) * 1024.0f));
+      out.write(v == 0.0f ? 0u : (uint32_t(e - 1 + 15) << 10) | mant, 16);
+    };
+    auto write_xy = [&](double x, double y) {  // CustomXY: pack_signed(round(v * 1e6)) through u2S (color_encoding.rs:91-100)
+      for (double v : {x, y}) {
+        const uint32_t u = pack_signed(int32_t(std::lround(v * 1e6)));
+        if (u < (1u << 19)) out.u2s_sel(0, u, 19);
+        else if (u < 524288u + (1u << 19)) out.u2s_sel(1, u - 524288u, 19);
+        else if (u < 1048576u + (1u << 20)) out.u2s_sel(2, u - 1048576u, 20);
+        else out.u2s_sel(3, u - 2097152u, 21);
+      }
+    };
+    out.write(0, 1);                    // all_default
+    out.write(1, 1);                    // extra_fields
+    out.write(p.orientation - 1, 3);
+    out.write(0, 1);                    // have_intrinsic_size
+    out.write(0, 1);                    // have_preview
+    out.write(0, 1);                    // have_animation
+    out.write(0, 1);                    // BitDepth: integer samples
+    out.u2s_sel(0);                     //           8 bits
+    out.write(1, 1);                    // modular_16bit_sufficient
+    out.u2s_sel(0);                     // no extra channels
+    out.write(1, 1);                    // xyb_encoded
+    bool hdr = false;
+    if (p.colour == 0) {
+      out.write(1, 1);                  // ColorEncoding all_default
+    } else {  // headers/color_encoding.rs:166-196
+      out.write(0, 1);
+      out.write(0, 1);                  // want_icc
+      write_enum(p.colour == 6 ? 1 : 0);  // colour space RGB / Gray
+      uint32_t wp = 1, prim = 1, tf = 13;  // D65, sRGB primaries, sRGB curve
+      bool gamma = false;
+      switch (p.colour) {
+        case 1: tf = 8; break;
+        case 2: gamma = true; break;
+        case 3: prim = 11; tf = 16; hdr = true; break;
+        case 4: prim = 9; tf = 18; hdr = true; break;
+        case 5: wp = 11; prim = 2; tf = 1; break;
+        case 6: break;
+        default: wp = 10; tf = 17; break;
+      }
+      write_enum(wp);
+      if (p.colour != 6) {
+        write_enum(prim);
+        if (prim == 2) {
+          write_xy(0.66, 0.31);
+          write_xy(0.28, 0.62);
+          write_xy(0.14, 0.07);
+        }
+      }
+      out.write(gamma ? 1 : 0, 1);      // have_gamma
+      if (gamma) out.write(4545455, 24);
+      else write_enum(tf);
+      write_enum(1);                    // rendering intent: relative
+    }
+    if (hdr) {  // ToneMapping (image_metadata.rs:156-167)
+      out.write(0, 1);
+      write_f16(1000.0f);               // intensity_target
+      write_f16(0.0f);                  // min_nits
+      out.write(0, 1);                  // relative_to_max_display
+      write_f16(0.0f);                  // linear_below
+    } else {
+      out.write(1, 1);                  // ToneMapping all_default
+    }
+    out.write_u64(0);                   // extensions
+  }
   out.write(1, 1);  // CustomTransformData all_default
   out.zero_pad_to_byte();
   // FrameHeader (frame_header.rs:267-444)
@@ -849,7 +994,7 @@ std::vector<uint8_t> encode(const Params& p) {
 
 // 8-bit RGB rendering of the same procedural image (source of the synthetic Modular frames).
 void make_image_u8(uint32_t width, uint32_t height, uint64_t seed, std::vector<uint8_t>& rgb) {
-  Params p{width, height, seed, 1.0f, 0, 0, 0, 0};
+  Params p{width, height, seed, 1.0f, 0, 0, 0, 0, 0};
   std::vector<float> img[3];
   make_image(p, img);
   rgb.resize(size_t(width) * height * 3);
@@ -863,14 +1008,18 @@ extern "C" {
 
 static thread_local std::string g_err;
 const char* jxs_last_error() { return g_err.c_str(); }
+// Worker threads used inside each following encode (process-wide; 1 = serial). The output does not depend on it.
+void jxs_set_threads(int n) { jxs::g_threads.store(n < 1 ? 1 : n); }
 
 // Encodes one synthetic frame. Returns the number of bytes written (or the
 // needed size when `cap` is too small), negative on error.
 int64_t jxs_encode_synthetic(uint32_t width, uint32_t height, uint64_t seed, float distance, uint32_t epf_iters,
                              uint32_t gab, uint32_t profile, uint8_t* out, size_t cap) {
   try {
-    // profile: bits 0..7 transform mix, bit 8: libjxl-like LF tree (weighted predictor)
-    jxs::Params p{width, height, seed, distance, epf_iters, gab, profile & 0xff, (profile >> 8) & 1};
+    // profile: bits 0..7 transform mix, bit 8: libjxl-like LF tree (weighted predictor), bits 9..10: AC entropy coder
+    // bits 12..15: orientation - 1, bits 16..19: colour encoding variant
+    jxs::Params p{width, height, seed, distance, epf_iters, gab, profile & 0xff, (profile >> 8) & 1, (profile >> 9) & 3,
+                  ((profile >> 12) & 7) + 1, (profile >> 16) & 15};
     std::vector<uint8_t> b = jxs::encode(p);
     if (b.size() <= cap && out) memcpy(out, b.data(), b.size());
     return int64_t(b.size());

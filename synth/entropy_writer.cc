@@ -159,6 +159,126 @@ void write_histogram(BitWriter& bw, const std::vector<uint16_t>& freq, uint32_t 
   }
 }
 
+// ---- prefix codes (entropy_coding/huffman.rs) ----
+
+// Huffman code lengths limited to `limit` bits: plain Huffman, and while the tree is too deep the small counts are
+// raised (flattening the distribution) and the tree rebuilt. >= 2 used symbols.
+std::vector<uint8_t> limited_code_lengths(std::vector<uint64_t> counts, unsigned limit) {
+  const size_t n = counts.size();
+  std::vector<uint8_t> len(n, 0);
+  for (uint64_t floor = 1;; floor *= 2) {
+    struct Node {
+      uint64_t w;
+      int l, r;
+    };
+    std::vector<Node> nodes;
+    std::vector<int> live;
+    for (size_t i = 0; i < n; i++)
+      if (counts[i]) {
+        nodes.push_back(Node{std::max(counts[i], floor), -1 - int(i), 0});
+        live.push_back(int(nodes.size()) - 1);
+      }
+    while (live.size() > 1) {
+      std::sort(live.begin(), live.end(), [&](int a, int b) { return nodes[a].w > nodes[b].w || (nodes[a].w == nodes[b].w && a > b); });
+      int a = live.back();
+      live.pop_back();
+      int b = live.back();
+      live.pop_back();
+      nodes.push_back(Node{nodes[a].w + nodes[b].w, a, b});
+      live.push_back(int(nodes.size()) - 1);
+    }
+    std::fill(len.begin(), len.end(), 0);
+    unsigned deepest = 0;
+    std::vector<std::pair<int, unsigned>> stack{{live[0], 0}};
+    while (!stack.empty()) {
+      auto [id, d] = stack.back();
+      stack.pop_back();
+      if (nodes[id].l < 0) {
+        len[size_t(-1 - nodes[id].l)] = uint8_t(std::max(d, 1u));
+        deepest = std::max(deepest, d);
+      } else {
+        stack.push_back({nodes[id].l, d + 1});
+        stack.push_back({nodes[id].r, d + 1});
+      }
+    }
+    if (deepest <= limit) return len;
+  }
+}
+
+// Canonical codes in the decoder's order (huffman.rs:276-400): symbols sorted by (length, symbol) take consecutive
+// codes; the table is indexed by the bit-reversed code, i.e. the pattern is written LSB first.
+std::vector<uint16_t> canonical_bits(const std::vector<uint8_t>& len) {
+  std::vector<uint16_t> bits(len.size(), 0);
+  uint32_t code = 0;
+  for (unsigned l = 1; l <= 15; l++) {
+    for (size_t s = 0; s < len.size(); s++)
+      if (len[s] == l) {
+        uint32_t rev = 0;
+        for (unsigned b = 0; b < l; b++)
+          if (code & (1u << b)) rev |= 1u << (l - 1 - b);
+        bits[s] = uint16_t(rev);
+        code++;
+      }
+    code <<= 1;
+  }
+  return bits;
+}
+
+void write_varint16(BitWriter& bw, uint32_t v) {  // inverse of decode.rs:18-29
+  if (v == 0) {
+    bw.write(0, 1);
+    return;
+  }
+  bw.write(1, 1);
+  uint32_t n = floor_log2(v);
+  bw.write(n, 4);
+  bw.write(v - (1u << n), n);
+}
+
+// One prefix code in the format Table::decode reads (huffman.rs:404-443). `len` covers the announced alphabet.
+void write_prefix_code(BitWriter& bw, const std::vector<uint8_t>& len) {
+  const size_t al = len.size();
+  if (al == 1) return;
+  std::vector<uint32_t> used;
+  for (size_t i = 0; i < al; i++)
+    if (len[i]) used.push_back(uint32_t(i));
+  const unsigned max_bits = ceil_log2(al);
+  if (used.size() <= 2) {  // simple code (huffman.rs:73-205): 1 symbol (0 bits) or 2 symbols (1 bit each)
+    bw.write(1, 2);
+    bw.write(uint32_t(used.size()) - 1, 2);
+    for (uint32_t sym : used) bw.write(sym, max_bits);
+    return;
+  }
+  bw.write(0, 2);  // complex code, no skipped code-length-code entries
+  // the lengths are sent literally (no repeat codes 16 / 17) up to the last used symbol: the decoder stops when the
+  // Kraft sum is complete (huffman.rs:222)
+  std::vector<uint64_t> cl_counts(18, 0);
+  for (size_t i = 0; i <= used.back(); i++) cl_counts[len[i]]++;
+  size_t distinct = 0;
+  for (auto c : cl_counts) distinct += c != 0;
+  static const uint8_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+  static const uint8_t kStaticBits[6] = {0b00, 0b0111, 0b011, 0b10, 0b01, 0b1111};  // value -> pattern (LSB first)
+  static const uint8_t kStaticLen[6] = {2, 4, 3, 2, 2, 4};
+  std::vector<uint8_t> cl_len(18, 0);
+  if (distinct == 1) {  // a single code-length symbol: zero bits per length (num_codes == 1 is accepted, huffman.rs:430)
+    for (int i = 0; i < 18; i++)
+      if (cl_counts[i]) cl_len[i] = 1;
+  } else {
+    cl_len = limited_code_lengths(cl_counts, 5);
+  }
+  int space = 32;
+  for (int i = 0; i < 18 && space > 0; i++) {
+    const uint8_t v = cl_len[kOrder[i]];
+    bw.write(kStaticBits[v], kStaticLen[v]);
+    if (v) space -= 32 >> v;
+  }
+  if (distinct != 1 && space != 0) throw std::runtime_error("code-length code is not complete");
+  if (distinct == 1) return;  // every length costs zero bits
+  // the code-length code itself is canonical over symbols 0..17 with a 5-bit root table (huffman.rs:213)
+  const std::vector<uint16_t> cl_bits = canonical_bits(cl_len);
+  for (size_t i = 0; i <= used.back(); i++) bw.write(cl_bits[len[i]], cl_len[len[i]]);
+}
+
 }  // namespace
 
 std::vector<uint16_t> normalize_counts(const std::vector<uint64_t>& counts, size_t alphabet) {
@@ -254,8 +374,9 @@ std::vector<uint8_t> cluster_contexts(size_t num_contexts, const std::vector<con
 }
 
 AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
-                   const std::vector<const std::vector<Token>*>& streams, uint32_t min_log_alpha) {
+                   const std::vector<const std::vector<Token>*>& streams, uint32_t min_log_alpha, bool use_prefix) {
   AnsCode code;
+  code.use_prefix = use_prefix;
   code.num_contexts = uint32_t(num_contexts);
   code.context_map = cluster_of_ctx;
   code.num_clusters = num_clusters;
@@ -269,6 +390,38 @@ AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_c
       counts[cluster_of_ctx[t.ctx]][tok]++;
       max_token = std::max(max_token, tok);
     }
+  if (use_prefix) {
+    code.log_alpha_size = 15;  // HUFFMAN_MAX_BITS (decode.rs:509-513): only sizes the hybrid-uint configuration
+    code.plen.resize(num_clusters);
+    code.pbits.resize(num_clusters);
+    for (uint32_t c = 0; c < num_clusters; c++) {
+      size_t used = 0, last = 0;
+      for (size_t i = 0; i < 256; i++)
+        if (counts[c][i]) {
+          used++;
+          last = i;
+        }
+      std::vector<uint64_t> cc(counts[c].begin(), counts[c].begin() + last + 1);
+      if (used == 0) cc[0] = 1, used = 1;  // unused cluster: one symbol, zero bits
+      std::vector<uint8_t> len(cc.size(), 0);
+      if (used == 1) len[last] = 0;  // single symbol: simple code, 0 bits (the decoder's table reads nothing)
+      else if (used == 2) {
+        for (size_t i = 0; i < cc.size(); i++)
+          if (cc[i]) len[i] = 1;
+      } else {
+        len = limited_code_lengths(cc, 15);
+      }
+      if (used == 1) {
+        code.plen[c].assign(cc.size(), 0);
+        code.pbits[c].assign(cc.size(), 0);
+        code.plen[c][last] = 0;
+      } else {
+        code.plen[c] = len;
+        code.pbits[c] = canonical_bits(len);
+      }
+    }
+    return code;
+  }
   code.log_alpha_size = std::max<uint32_t>(min_log_alpha, std::max<uint32_t>(5, ceil_log2(uint64_t(max_token) + 1)));
   if (code.log_alpha_size > 8) throw std::runtime_error("alphabet too large");
   // split_exponent must be <= log_alpha_size; 4 always is.
@@ -325,6 +478,27 @@ void write_code(BitWriter& bw, const AnsCode& code) {
       write_tokens(bw, sub, toks);
     }
   }
+  if (code.use_prefix) {  // decode.rs:509-524, huffman.rs:466-480
+    bw.write(1, 1);
+    for (uint32_t c = 0; c < code.num_clusters; c++) write_hybrid_cfg(bw, code.cfg, 15);
+    for (uint32_t c = 0; c < code.num_clusters; c++) write_varint16(bw, uint32_t(code.plen[c].size()) - 1);
+    for (uint32_t c = 0; c < code.num_clusters; c++) {
+      // a one-symbol code whose symbol is not 0 still needs the simple-code header; plen alone cannot say which
+      // symbol, so that case is written here
+      size_t used = 0, last = 0;
+      for (size_t i = 0; i < code.plen[c].size(); i++)
+        if (code.plen[c][i]) used++, last = i;
+      if (used == 0 && code.plen[c].size() > 1) {  // single symbol = the last of the announced alphabet
+        bw.write(1, 2);
+        bw.write(0, 2);
+        bw.write(uint32_t(code.plen[c].size() - 1), ceil_log2(code.plen[c].size()));
+        continue;
+      }
+      (void)last;
+      write_prefix_code(bw, code.plen[c]);
+    }
+    return;
+  }
   bw.write(0, 1);  // use_prefix_code = 0
   bw.write(code.log_alpha_size - 5, 2);
   for (uint32_t c = 0; c < code.num_clusters; c++) write_hybrid_cfg(bw, code.cfg, code.log_alpha_size);
@@ -332,6 +506,17 @@ void write_code(BitWriter& bw, const AnsCode& code) {
 }
 
 void write_tokens(BitWriter& bw, const AnsCode& code, const std::vector<Token>& tokens) {
+  if (code.use_prefix) {  // no initial state; token pattern then the hybrid-uint extra bits (decode.rs:286-330)
+    for (const Token& t : tokens) {
+      uint32_t tok, nb, bits;
+      code.cfg.encode(t.value, tok, nb, bits);
+      const uint32_t c = code.context_map[t.ctx];
+      if (tok >= code.plen[c].size()) throw std::runtime_error("token outside the prefix alphabet");
+      bw.write(code.pbits[c][tok], code.plen[c][tok]);
+      bw.write(bits, nb);
+    }
+    return;
+  }
   const size_t n = tokens.size();
   std::vector<uint8_t> has_chunk(n, 0);
   std::vector<uint16_t> chunk(n, 0);

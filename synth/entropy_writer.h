@@ -110,13 +110,18 @@ struct AnsCode {
   std::vector<std::vector<uint16_t>> freqs;       // [cluster][alphabet] sums to 4096
   std::vector<std::vector<uint16_t>> inv;         // [cluster] start index per symbol into slots
   std::vector<std::vector<uint16_t>> slots;       // [cluster] concatenated idx lists per symbol (offset -> idx)
+  // Prefix-code variant (entropy_coding/huffman.rs): per cluster canonical code lengths (<= 15) and the bit patterns
+  // as the decoder's table expects them (first bit read = LSB).
+  bool use_prefix = false;
+  std::vector<std::vector<uint8_t>> plen;         // [cluster][alphabet]
+  std::vector<std::vector<uint16_t>> pbits;       // [cluster][alphabet]
 };
 
 // Normalises counts to sum 4096 with every used symbol >= 1.
 std::vector<uint16_t> normalize_counts(const std::vector<uint64_t>& counts, size_t alphabet);
 // Builds a code from tokens: `cluster_of_ctx` (size num_contexts, values < num_clusters) given by the caller.
 AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
-                   const std::vector<const std::vector<Token>*>& streams, uint32_t min_log_alpha = 5);
+                   const std::vector<const std::vector<Token>*>& streams, uint32_t min_log_alpha = 5, bool use_prefix = false);
 // Convenience: one cluster per context when num_contexts <= 8, else quantile clustering into <= max_clusters.
 std::vector<uint8_t> cluster_contexts(size_t num_contexts, const std::vector<const std::vector<Token>*>& streams,
                                       uint32_t max_clusters, uint32_t& num_clusters, const HybridCfg& cfg);

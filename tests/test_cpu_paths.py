@@ -54,18 +54,93 @@ def test_oracle_detects_corruption(golden_dir):
         ob.decode_file(bytes(data))
 
 
-@pytest.mark.parametrize("case", [(8, 8, 1, 1.0, 2, 1, 0), (256, 256, 1000, 0.5, 2, 1, 1), (300, 200, 7, 0.5, 3, 0, 2), (640, 480, 9, 0.3, 0, 1, 1)])
+def _srgb_exact(x):
+    return np.where(x < 0.0031308, 12.92 * x, 1.055 * np.power(np.maximum(x, 1e-9), 1 / 2.4) - 0.055)
+
+
+@pytest.mark.parametrize("case", [(8, 8, 1, 1.0, 2, 1, 0, 0), (256, 256, 1000, 0.5, 2, 1, 1, 0), (300, 200, 7, 0.5, 3, 0, 2, 0),
+                                  (640, 480, 9, 0.3, 0, 1, 1, 0), (512, 512, 77, 0.5, 0, 0, 3, 0), (600, 520, 78, 0.5, 2, 1, 3, 1),
+                                  (400, 300, 79, 0.5, 2, 1, 1, 1)])
 def test_synthetic_writer_round_trip(case):
     """The writer's forward transforms / entropy coder and the oracle's decoder were written independently:
     a decode that reproduces the source image (PSNR) pins the transform conventions end to end."""
     import synth
     from tests import oracle_binding as ob
-    w, h, seed, dist, epf, gab, prof = case
-    data = synth.encode_synthetic(w, h, seed, dist, epf, gab, prof)
+    w, h, seed, dist, epf, gab, prof, ent = case
+    data = synth.encode_synthetic(w, h, seed, dist, epf, gab, prof, 0, ent)
     out, _ = ob.decode_file(data, abi.FORMAT_RGB_F32, threads=4)
     assert out.shape == (h, w, 3) and np.isfinite(out).all()
     assert 0.0 < out.mean() < 1.0 and out.std() > 0.01
     assert ob.file_info(data).width == w
+    # the source picture of the writer (linear RGB, 8-bit rendering) against the decode (sRGB-encoded float)
+    src = _srgb_exact(synth.modular_source(w, h, seed) / 255.0)
+    mse = float(np.mean((out.astype(np.float64) - src) ** 2))
+    assert 10 * np.log10(1.0 / mse) > (24.0 if w <= 8 else 30.0), f"PSNR {10 * np.log10(1.0 / mse):.1f} dB"
+
+
+def test_orientation_is_applied_like_the_reference_save_stage():
+    """headers/image_metadata.rs:85-96 display_pixel, written here as numpy flips / transposes of the identity decode."""
+    import synth
+    from tests import oracle_binding as ob
+    base, _ = ob.decode_file(synth.encode_synthetic(200, 120, 5, 0.5, 2, 1, 1), abi.FORMAT_RGB_U8)
+    want = {1: base, 2: base[:, ::-1], 3: base[::-1, ::-1], 4: base[::-1], 5: base.transpose(1, 0, 2),
+            6: np.rot90(base, k=-1), 7: base.transpose(1, 0, 2)[::-1, ::-1], 8: np.rot90(base, k=1)}
+    for o in range(1, 9):
+        data = synth.encode_synthetic(200, 120, 5, 0.5, 2, 1, 1, orientation=o)
+        info = ob.file_info(data)
+        assert (info.coded_width, info.coded_height, info.orientation) == (200, 120, o)
+        assert (info.width, info.height) == ((120, 200) if o >= 5 else (200, 120))
+        out, _ = ob.decode_file(data, abi.FORMAT_RGB_U8)
+        assert np.array_equal(out, want[o]), f"orientation {o}"
+
+
+def test_scope_guards_refuse_what_the_path_cannot_reproduce(golden_dir):
+    """A frame the path cannot render like the reference must be refused (JXG_ERR_UNSUPPORTED), never decoded to
+    different pixels: noise synthesis (render/stages/noise.rs), multi-frame files, absurd dimensions."""
+    from tests import oracle_binding as ob
+    lib = abi.load_library()
+    data = open(os.path.join(golden_dir, "jxl", "noise.jxl"), "rb").read()
+    h, info = C.c_void_p(), abi.JxgImageInfo()
+    assert lib.jxg_parse_file(data, len(data), C.byref(h), C.byref(info)) == -2
+    assert b"noise" in lib.jxg_last_error()
+    with pytest.raises(abi.JxgError) as e:
+        ob.decode_file(data)
+    assert e.value.code == -2
+
+
+def _frame_census(data):
+    """Transform types used by first blocks and the entropy code of pass 0, from the descriptor the front-end hands
+    to the hot path (no GPU involved)."""
+    import jxl_rs_b200 as j
+    fr = j.ParsedFrame(data)
+    d, _, _, _, _ = fr.desc(abi.FORMAT_RGB_U8)
+    nb = ((fr.info.coded_width + 7) // 8) * ((fr.info.coded_height + 7) // 8)
+    tm = np.ctypeslib.as_array(C.cast(d.transform_map, C.POINTER(C.c_uint8)), (nb,)).copy()
+    types = np.bincount(tm[tm >= 128] & 127, minlength=27)
+    p0 = d.passes[0]
+    census = {"types": types, "use_prefix": int(p0.use_prefix), "clusters": int(p0.num_clusters), "max_code_bits": 0}
+    if p0.use_prefix:
+        e = np.ctypeslib.as_array(C.cast(p0.huff_entries, C.POINTER(C.c_uint32)), (p0.huff_entries_len,)).copy()
+        off = np.ctypeslib.as_array(C.cast(p0.huff_offset, C.POINTER(C.c_uint32)), (p0.num_clusters,)).copy()
+        roots = np.concatenate([e[o:o + 256] for o in off])
+        census["second_level_roots"] = int(((roots & 0xff) > 8).sum())
+    return census
+
+
+def test_profile_3_places_the_128_and_256_transform_families():
+    """DCT128X128 ... DCT256X256 (types 21..26) must all occur in the frame the parity tests use."""
+    import synth
+    c = _frame_census(synth.encode_synthetic(1024, 768, 31, 0.5, 2, 1, 3))
+    assert all(c["types"][t] > 0 for t in range(21, 27)), c["types"]
+    assert c["types"][18] > 0 and c["types"][5] > 0 and c["types"][0] > 0  # and the smaller families around them
+
+
+def test_prefix_variant_exercises_the_second_level_tables():
+    """prefix-coded AC streams with codes longer than the 8-bit root table (huffman.rs:446-457) and many
+    clusters — not the 1x1 / one-cluster prefix files of the reference's fixture set."""
+    import synth
+    c = _frame_census(synth.encode_synthetic(1024, 768, 32, 0.5, 2, 1, 1, 0, 1))
+    assert c["use_prefix"] == 1 and c["clusters"] >= 16 and c["second_level_roots"] > 0, c
 
 
 def test_c_abi_exports_every_declared_symbol():

@@ -1,8 +1,6 @@
 """GPU parity on VarDCT frames that carry extra channels (alpha): the device path decodes their colour channels
 (the extra channels' Modular streams are stepped over by the front-end; in the HF sections they sit behind the AC
-coefficients the entropy kernel reads). Runs last (file name) and only when JXG_TEST_EXPERIMENTAL=1: the
-front-end support was written after the round's GPU budget was spent, so the first run on a device is a deliberate
-one (tools/gpu_session.sh sets the variable)."""
+coefficients the entropy kernel reads)."""
 import os
 
 import numpy as np
@@ -10,8 +8,7 @@ import pytest
 
 from jxl_rs_b200 import abi
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("JXG_TEST_EXPERIMENTAL") != "1", reason="set JXG_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 FILES = ["3x3a_srgb_lossy.jxl", "alpha_premultiplied.jxl", "dice.jxl", "squeeze_alpha.jxl", "upsampled_alpha.jxl"]
 
