@@ -144,6 +144,10 @@ typedef struct JxgFrameDesc {
   float output_luminances[3];     /* Y row of the output primaries (JXG_TF_HLG)        */
 } JxgFrameDesc;
 
+/* PCI bus id of a CUDA device in the spelling of /sys/bus/pci/devices ("0000:1b:00.0"): lets the host bind its
+ * threads and pinned allocations to the GPU's NUMA node before jxg_init. buf: >= 16 bytes. */
+int jxg_device_pci_bus_id(int device, char* buf, int len);
+
 /* Context: one per device/rank. Owns streams, pinned staging and device pools. */
 int jxg_init(int device, void** ctx);
 void jxg_shutdown(void* ctx);

@@ -72,6 +72,7 @@ struct Batch {
   int32_t* status_host = nullptr;  // pinned (context-owned): a D2H copy into pageable memory would block jxg_batch_run
   size_t status_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t last_stream = nullptr;  // stream of the last run / rerun (the context's or the caller's)
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
   uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -153,6 +154,16 @@ static int validate_desc(const JxgFrameDesc* d, const uint32_t* sec_len, uint32_
 extern "C" {
 
 const char* jxg_last_error(void) { return g_error.c_str(); }
+
+// PCI bus id of a CUDA device ("0000:1b:00.0", lower case, as under /sys/bus/pci/devices), so that a host can find the
+// NUMA node the GPU hangs off and keep its threads and pinned buffers there. No context is created.
+int jxg_device_pci_bus_id(int device, char* buf, int len) {
+  if (!buf || len < 16) return JXG_ERR_ARGUMENT;
+  CUDA_TRY(cudaDeviceGetPCIBusId(buf, len, device));
+  for (char* p = buf; *p; p++)
+    if (*p >= 'A' && *p <= 'Z') *p = char(*p - 'A' + 'a');
+  return JXG_OK;
+}
 
 int jxg_init(int device, void** out_ctx) {
   if (!out_ctx) return JXG_ERR_ARGUMENT;
@@ -264,7 +275,7 @@ int jxg_batch_set_profile(void* bp, int on) {
 int jxg_batch_stage_times(void* bp, float* ms, int n) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b || !ms || n < kNumStages || !b->profile) return JXG_ERR_ARGUMENT;
-  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->last_stream ? b->last_stream : b->ctx->stream));
   for (int i = 0; i < kNumStages; i++) {
     ms[i] = 0.0f;
     if (cudaEventElapsedTime(&ms[i], b->stage_ev[i], b->stage_ev[i + 1]) != cudaSuccess) ms[i] = 0.0f;
@@ -633,6 +644,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (!b || b->frames.empty()) return JXG_ERR_ARGUMENT;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  b->last_stream = s;
   b->h2d = b->d2h = 0;
   schedule_lean(b);
   // device allocations
@@ -687,6 +699,7 @@ int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
   if (!b || !b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch was never submitted");
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  b->last_stream = s;
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   if (int r = launch(b, s, false)) return r;
   CUDA_TRY(cudaEventRecord(b->ev1, s));
@@ -699,7 +712,7 @@ int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_grou
   if (!b) return JXG_ERR_ARGUMENT;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   CUDA_TRY(cudaEventSynchronize(b->ev1));
-  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->last_stream ? b->last_stream : b->ctx->stream));  // the status words follow ev1
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
   for (size_t i = 0; i < b->status_n; i++)

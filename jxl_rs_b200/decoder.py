@@ -195,6 +195,53 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
     return outs
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(device: int, sysfs: str = "/sys"):
+    """(numa_node, set of CPUs) of the NUMA node the GPU's PCIe root hangs off, or (None, None) when the platform does
+    not say (single-node hosts report -1)."""
+    import os
+    lib = abi.load_library()
+    buf = C.create_string_buffer(32)
+    if lib.jxg_device_pci_bus_id(device, buf, 32) != 0:
+        return None, None
+    try:
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", buf.value.decode(), "numa_node")).read())
+        if node < 0:
+            return None, None
+        return node, _parse_cpulist(open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")).read())
+    except (OSError, ValueError):
+        return None, None
+
+
+def bind_to_gpu_numa_node(device: int):
+    """Restricts the calling thread (and every thread it starts afterwards: worker pools, the dispatcher) to the
+    CPUs of the GPU's NUMA node. Call it before the pools and the pinned buffers are created: pinned pages are
+    allocated on the node of the thread that asks for them, and H2D / D2H copies through a remote node cross the
+    inter-socket link (the end-to-end scaling collapse of round 1 at 8 GPUs). Returns a description for logs."""
+    import os
+    node, cpus = gpu_numa_cpus(device)
+    if not cpus:
+        return {"numa_node": None, "bound": False}
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+            return {"numa_node": node, "bound": True, "cpus": len(want)}
+    except (AttributeError, OSError):
+        pass
+    return {"numa_node": node, "bound": False}
+
+
 def effective_cpus() -> int:
     """Host threads this process can really run at once: min(cpu_count, affinity mask, cgroup v2/v1 CPU quota)."""
     import math
