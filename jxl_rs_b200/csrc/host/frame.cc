@@ -198,6 +198,44 @@ void decode_lf_global(FrameState& fs, BitReader& br) {
   br.check();
 }
 
+// modular/mod.rs:837-929 dequant_lf for a 4:4:4 frame: quantised LF integers of a w x h rect (row stride qstride) ->
+// dequantised X / Y / B LF samples with the LF chroma-from-luma, and the LF context bucket of every block, written at
+// element offset `o0` (row stride fs.xb) of fs.lf[] / fs.quant_lf_map.
+}  // namespace
+void dequant_lf_rect(FrameState& fs, const int32_t* qy_p, const int32_t* qx_p, const int32_t* qb_p, size_t qstride, uint32_t w,
+                     uint32_t hh, float mul, size_t o0) {
+  float inv_quant_lf = 65536.0f / (float(fs.global_scale) * float(fs.quant_lf));
+  float fac_x = fs.lf_quant[0] * inv_quant_lf * mul;
+  float fac_y = fs.lf_quant[1] * inv_quant_lf * mul;
+  float fac_b = fs.lf_quant[2] * inv_quant_lf * mul;
+  float cfl_x = fs.base_correlation_x + float(fs.ytox_lf) / float(fs.color_factor);
+  float cfl_b = fs.base_correlation_b + float(fs.ytob_lf) / float(fs.color_factor);
+  for (uint32_t y = 0; y < hh; y++) {
+    const int32_t *qy = qy_p + size_t(y) * qstride, *qx = qx_p + size_t(y) * qstride, *qb = qb_p + size_t(y) * qstride;
+    size_t o = o0 + size_t(y) * fs.xb;
+    for (uint32_t x = 0; x < w; x++) {
+      float in_x = float(qx[x]) * fac_x, in_y = float(qy[x]) * fac_y, in_b = float(qb[x]) * fac_b;
+      fs.lf[1][o + x] = in_y;
+      fs.lf[0][o + x] = in_y * cfl_x + in_x;
+      fs.lf[2][o + x] = in_y * cfl_b + in_b;
+    }
+    if (fs.num_lf_contexts > 1) {
+      for (uint32_t x = 0; x < w; x++) {
+        auto bucket = [](const std::vector<int32_t>& thr, int32_t v) {
+          uint32_t n = 0;
+          for (int32_t t : thr) n += v > t;
+          return n;
+        };
+        uint32_t b = bucket(fs.lf_thresholds[0], qx[x]);
+        b = b * uint32_t(fs.lf_thresholds[2].size() + 1) + bucket(fs.lf_thresholds[2], qb[x]);
+        b = b * uint32_t(fs.lf_thresholds[1].size() + 1) + bucket(fs.lf_thresholds[1], qy[x]);
+        fs.quant_lf_map[o + x] = uint8_t(b);
+      }
+    }
+  }
+}
+
+namespace {
 // modular/mod.rs:837-1080: one LF group (LF image, ModularLF stream of extra channels, HF metadata), in phases so
 // that two groups can run their Modular sub-bitstreams in lockstep (decode_substreams_paired):
 //   begin_lf -> [LF image channels] -> finish_lf_begin_meta -> [HF metadata channels] -> finish_meta
@@ -234,38 +272,8 @@ struct LfGroupJob {
   // call after the LF sub-bitstream has been finished
   void finish_lf_begin_meta() {
     const FrameHeader& h = fs.header;
-    {
-      // dequant_lf (444): channel 0 = Y, 1 = X, 2 = B
-      float inv_quant_lf = 65536.0f / (float(fs.global_scale) * float(fs.quant_lf));
-      float fac_x = fs.lf_quant[0] * inv_quant_lf * mul;
-      float fac_y = fs.lf_quant[1] * inv_quant_lf * mul;
-      float fac_b = fs.lf_quant[2] * inv_quant_lf * mul;
-      float cfl_x = fs.base_correlation_x + float(fs.ytox_lf) / float(fs.color_factor);
-      float cfl_b = fs.base_correlation_b + float(fs.ytob_lf) / float(fs.color_factor);
-      for (uint32_t y = 0; y < hh; y++) {
-        const int32_t *qy = ch[0].row(y), *qx = ch[1].row(y), *qb = ch[2].row(y);
-        size_t o = size_t(y0 + y) * fs.xb + x0;
-        for (uint32_t x = 0; x < w; x++) {
-          float in_x = float(qx[x]) * fac_x, in_y = float(qy[x]) * fac_y, in_b = float(qb[x]) * fac_b;
-          fs.lf[1][o + x] = in_y;
-          fs.lf[0][o + x] = in_y * cfl_x + in_x;
-          fs.lf[2][o + x] = in_y * cfl_b + in_b;
-        }
-        if (fs.num_lf_contexts > 1) {
-          for (uint32_t x = 0; x < w; x++) {
-            auto bucket = [](const std::vector<int32_t>& thr, int32_t v) {
-              uint32_t n = 0;
-              for (int32_t t : thr) n += v > t;
-              return n;
-            };
-            uint32_t b = bucket(fs.lf_thresholds[0], qx[x]);
-            b = b * uint32_t(fs.lf_thresholds[2].size() + 1) + bucket(fs.lf_thresholds[2], qb[x]);
-            b = b * uint32_t(fs.lf_thresholds[1].size() + 1) + bucket(fs.lf_thresholds[1], qy[x]);
-            fs.quant_lf_map[o + x] = uint8_t(b);
-          }
-        }
-      }
-    }
+    // dequant_lf (444): channel 0 = Y, 1 = X, 2 = B
+    dequant_lf_rect(fs, ch[0].row(0), ch[1].row(0), ch[2].row(0), ch[0].w, w, hh, mul, size_t(y0) * fs.xb + x0);
     ss.reset();
     ch.clear();
     // ModularLF stream: no channels in a VarDCT frame without extra channels.

@@ -94,6 +94,10 @@ struct FrameState {
   void fill_desc(JxgFrameDesc* d, uint32_t output_format);
 };
 
+// modular/mod.rs:837-929 dequant_lf (4:4:4) on a w x h rect of quantised LF integers; exposed for the tests.
+void dequant_lf_rect(FrameState& fs, const int32_t* qy, const int32_t* qx, const int32_t* qb, size_t qstride, uint32_t w, uint32_t h,
+                     float mul, size_t o0);
+
 // frame/adaptive_lf_smoothing.rs:44 on fs.lf (uses xb, yb, global_scale, quant_lf, lf_quant). Exposed for the tests.
 void adaptive_lf_smoothing(FrameState& fs, int threads = 1);
 

@@ -538,6 +538,24 @@ const float* dequant_table(const JxgFrameDesc& d, int idx) {
   return jxg::library_dequant_table(idx).data();  // host-side table construction (not on the hot path)
 }
 
+// a9. group.rs:85-177: adjust_quant_bias, dequantisation with the per-block scale and the table weight, chroma from
+// luma (X and B get x_cc / b_cc times the dequantised Y coefficient through mul_add).
+inline void dequant_block(size_t num_coeffs, const int32_t* qx, const int32_t* qy, const int32_t* qb, const float* mat, float sx,
+                          float sy, float sb, float x_cc, float b_cc, const float* bias, float* ox, float* oy, float* ob) {
+  auto adj = [&](int c, int32_t q) {
+    float qf = float(q);
+    return std::abs(q) < 2 ? qf * bias[c] : qf - bias[3] / qf;
+  };
+  for (size_t k = 0; k < num_coeffs; k++) {
+    float dy = adj(1, qy[k]) * (mat[num_coeffs + k] * sy);
+    float dxc = adj(0, qx[k]) * (mat[k] * sx);
+    float dbc = adj(2, qb[k]) * (mat[2 * num_coeffs + k] * sb);
+    oy[k] = dy;
+    ox[k] = std::fmaf(x_cc, dy, dxc);
+    ob[k] = std::fmaf(b_cc, dy, dbc);
+  }
+}
+
 // a2, a3, a8, a9: one HF group — jxl/src/frame/group.rs:383-632
 int decode_group(const JxgFrameDesc& d, const Geometry& geo, uint32_t g, const uint8_t* hf, const uint64_t* sec_off,
                  const uint32_t* sec_len, int32_t* coeffs /* [3][65536] */, float* planes[3], size_t plane_stride) {
@@ -636,20 +654,8 @@ int decode_group(const JxgFrameDesc& d, const Geometry& geo, uint32_t g, const u
         const float b_cc = d.base_correlation_b + float(d.ytob_map[size_t((by0 + by) / 8) * cxb + (bx0 + bx) / 8]) / float(d.color_factor);
         const float sy = inv_global_scale / float(raw_quant), sx = sy * x_dm, sb = sy * b_dm;
         const float* mat = dequant_table(d, kQuantTable[t]);
-        const float* bias = d.quant_biases;
-        auto adj = [&](int c, int32_t q) {
-          float qf = float(q);
-          return std::abs(q) < 2 ? qf * bias[c] : qf - bias[3] / qf;
-        };
         const int32_t *qx = coeffs + coeffs_offset, *qy = coeffs + 65536 + coeffs_offset, *qb = coeffs + 2 * 65536 + coeffs_offset;
-        for (size_t k = 0; k < num_coeffs; k++) {
-          float dy = adj(1, qy[k]) * (mat[num_coeffs + k] * sy);
-          float dxc = adj(0, qx[k]) * (mat[k] * sx);
-          float dbc = adj(2, qb[k]) * (mat[2 * num_coeffs + k] * sb);
-          tbuf[1][k] = dy;
-          tbuf[0][k] = std::fmaf(x_cc, dy, dxc);
-          tbuf[2][k] = std::fmaf(b_cc, dy, dbc);
-        }
+        dequant_block(num_coeffs, qx, qy, qb, mat, sx, sy, sb, x_cc, b_cc, d.quant_biases, tbuf[0].data(), tbuf[1].data(), tbuf[2].data());
         for (int c : {1, 0, 2}) {
           for (uint32_t y = 0; y < cy; y++)
             for (uint32_t x = 0; x < cx; x++) lfbuf[y * cx + x] = d.lf[c][size_t(by0 + by + y) * geo.xb + bx0 + bx + x];
@@ -1122,6 +1128,46 @@ void jxo_xyb_to_linear(int n, float* x, float* y, float* b, const float* opsin_m
     scaled_bias[i] = opsin_biases[i] * is;
   }
   for (int i = 0; i < n; i++) xyb_to_linear_px(x[i], y[i], b[i], opsin_matrix, bias_cbrt, scaled_bias, is);
+}
+// Float stages on caller-supplied data, for the independent float64 restatements of tests/test_kat_float_stages.py.
+void jxo_dequant_block(uint32_t num_coeffs, const int32_t* qx, const int32_t* qy, const int32_t* qb, const float* mat, float sx,
+                       float sy, float sb, float x_cc, float b_cc, const float* bias, float* out3) {
+  dequant_block(num_coeffs, qx, qy, qb, mat, sx, sy, sb, x_cc, b_cc, bias, out3, out3 + num_coeffs, out3 + 2 * size_t(num_coeffs));
+}
+// inv-sigma image (features/epf.rs:35-86) of an xb x yb block grid.
+void jxo_sigma_image(uint32_t xb, uint32_t yb, uint32_t global_scale, const int32_t* raw_quant, const uint8_t* sharpness,
+                     float quant_mul, const float* sharp_lut, float* out) {
+  JxgFrameDesc d;
+  memset(&d, 0, sizeof(d));
+  d.global_scale = global_scale;
+  d.raw_quant_map = raw_quant;
+  d.epf_map = sharpness;
+  d.epf_quant_mul = quant_mul;
+  memcpy(d.epf_sharp_lut, sharp_lut, sizeof(d.epf_sharp_lut));
+  d.width = xb * 8;
+  d.height = yb * 8;
+  Geometry geo(d);
+  std::vector<float> s = sigma_image(d, geo);
+  memcpy(out, s.data(), s.size() * 4);
+}
+// One EPF stage (0, 1, 2) over a w x h image of 3 planes (tight rows) with whole-image mirroring; inv_sigma: one value per
+// 8x8 block (ceil(w/8) x ceil(h/8)).
+void jxo_epf_stage(int stage, uint32_t w, uint32_t h, const float* in3, float* out3, const float* inv_sigma, const float* channel_scale,
+                   float pass0_sigma_scale, float pass2_sigma_scale, float border_sad_mul, int threads) {
+  JxgFrameDesc d;
+  memset(&d, 0, sizeof(d));
+  memcpy(d.epf_channel_scale, channel_scale, 12);
+  d.epf_pass0_sigma_scale = pass0_sigma_scale;
+  d.epf_pass2_sigma_scale = pass2_sigma_scale;
+  d.epf_border_sad_mul = border_sad_mul;
+  d.width = w;
+  d.height = h;
+  Geometry geo(d);
+  std::vector<float> sigma(inv_sigma, inv_sigma + size_t(geo.xb) * geo.yb);
+  const size_t n = size_t(w) * h;
+  Planes in{{const_cast<float*>(in3), const_cast<float*>(in3) + n, const_cast<float*>(in3) + 2 * n}, w};
+  Planes out{{out3, out3 + n, out3 + 2 * n}, w};
+  epf(stage, d, geo, sigma, in, out, threads);
 }
 // from_linear stage of the oracle on n RGB triples (interleaved), for the known-answer tests of the other encodings.
 void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const float* luminances, int n, float* rgb) {

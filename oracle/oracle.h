@@ -58,6 +58,12 @@ void jxo_gaborish(int w, int h, const float* in, float* out, float w1, float w2)
 void jxo_xyb_to_linear(int n, float* x, float* y, float* b, const float* opsin_matrix, const float* opsin_biases,
                        float intensity_target);
 void jxo_linear_to_srgb(int n, float* v);
+void jxo_dequant_block(uint32_t num_coeffs, const int32_t* qx, const int32_t* qy, const int32_t* qb, const float* mat, float sx,
+                       float sy, float sb, float x_cc, float b_cc, const float* bias, float* out3);
+void jxo_sigma_image(uint32_t xb, uint32_t yb, uint32_t global_scale, const int32_t* raw_quant, const uint8_t* sharpness,
+                     float quant_mul, const float* sharp_lut, float* out);
+void jxo_epf_stage(int stage, uint32_t w, uint32_t h, const float* in3, float* out3, const float* inv_sigma, const float* channel_scale,
+                   float pass0_sigma_scale, float pass2_sigma_scale, float border_sad_mul, int threads);
 void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const float* luminances, int n, float* rgb);
 /* ImageMetadata.orientation (headers/image_metadata.rs:85-96 display_pixel): pixel (x, y) of the tight w x h source goes
  * to display_pixel(x, y) of `dst` (row stride dst_stride; h x w for orientations 5..8). */

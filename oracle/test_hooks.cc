@@ -210,4 +210,34 @@ int jxo_t_output_colour(uint32_t color_space, uint32_t white_point, const int32_
     return e.code;
   }
 }
+
+// modular/mod.rs:837-929 dequant_lf through the front-end's dequant_lf_rect on caller data: q = 3 planes (Y, X, B order of
+// the coded channels) of w x h quantised LF integers; out: X, Y, B f32 planes; qlf: context buckets.
+void jxo_t_dequant_lf(uint32_t w, uint32_t h, const int32_t* q, uint32_t global_scale, uint32_t quant_lf, const float* lf_quant,
+                      uint32_t extra_precision, float base_x, float base_b, int32_t ytox_lf, int32_t ytob_lf, uint32_t color_factor,
+                      const int32_t* thr, const uint32_t* nthr, float* out, uint8_t* qlf) {
+  FrameState fs;
+  fs.xb = w;
+  fs.yb = h;
+  fs.global_scale = global_scale;
+  fs.quant_lf = quant_lf;
+  for (int c = 0; c < 3; c++) fs.lf_quant[c] = lf_quant[c];
+  fs.base_correlation_x = base_x;
+  fs.base_correlation_b = base_b;
+  fs.ytox_lf = ytox_lf;
+  fs.ytob_lf = ytob_lf;
+  fs.color_factor = color_factor;
+  fs.num_lf_contexts = 1;
+  for (int c = 0; c < 3; c++) {
+    fs.lf_thresholds[c].assign(thr, thr + nthr[c]);
+    thr += nthr[c];
+    fs.num_lf_contexts *= nthr[c] + 1;
+    fs.lf[c].assign(size_t(w) * h, 0.0f);
+  }
+  fs.quant_lf_map.assign(size_t(w) * h, 0);
+  const size_t n = size_t(w) * h;
+  dequant_lf_rect(fs, q, q + n, q + 2 * n, w, w, h, 1.0f / float(1u << extra_precision), 0);
+  for (int c = 0; c < 3; c++) memcpy(out + size_t(c) * n, fs.lf[c].data(), n * 4);
+  memcpy(qlf, fs.quant_lf_map.data(), n);
+}
 }
