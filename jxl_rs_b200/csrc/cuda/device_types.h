@@ -47,6 +47,7 @@ struct FrameDev {
   uint32_t first_stream;      // index of group 0 in the batch stream list
   // persistent entropy lanes (k_entropy_lean): this frame's range in streams_lean (longest first) and its CTAs
   uint32_t lean_first, lean_count, lean_cta_first, lean_ctas;
+  uint32_t lean_lanes;        // lanes of this frame that start with a stream of their own; the rest is queued
   // device-only buffers (element offsets)
   uint64_t coeff_group_base;  // group index base into coeffs
   uint64_t block_base;        // block index base into block_off
@@ -98,6 +99,7 @@ struct BatchDev {
   int32_t* status;      // per stream
   uint32_t* queue;      // [frames] work-queue cursors of the persistent entropy kernel
   const uint32_t* lean_cta_first;  // [frames] first CTA of each frame in k_entropy_lean's grid
+  const uint2* lean_warp;          // [lean CTAs * 4] per warp: first stream (relative to the frame's list), lanes
   uint4* lean_desc;      // [num_lean][1024] varblock descriptors written by k_block_plan
   uint32_t* lean_nblk;   // [num_lean] varblocks per stream (0xffffffff: invalid transform id)
   // context-wide tables

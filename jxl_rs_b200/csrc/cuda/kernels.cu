@@ -758,10 +758,14 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   const uint32_t nz2_s = uint32_t(__cvta_generic_to_shared(s_nz2)), fr2_s = uint32_t(__cvta_generic_to_shared(s_fr2));
   auto ctx_cluster = [&](uint32_t ctx) { return CTXS ? spec_lds_u8(ctxmap_s + ctx) : spec_ld_u8(ctxmap_g + ctx); };
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t lane_in_frame = ((blockIdx.x - F.lean_cta_first) * 4 + (threadIdx.x >> 5)) * S + lane;
-  const uint32_t frame_lanes = F.lean_ctas * 4 * S;
-  uint32_t qpos = lane_in_frame;  // position in this frame's (longest first) stream list
-  bool done = !(lane < S && qpos < F.lean_count);
+  // Warp schedule written by the host (batch.cc schedule_lean): the first stream of this warp in the frame's
+  // longest-first list and its number of lanes (<= S). The longest streams of a frame sit alone in their warp — the
+  // kernel ends when the longest stream ends, and a lane that shares its warp pays for the divergent set-up paths of
+  // its neighbours — the shorter ones are packed 2 or S to a warp.
+  const uint2 wsched = B.lean_warp[blockIdx.x * 4 + (threadIdx.x >> 5)];
+  const uint32_t frame_lanes = F.lean_lanes;
+  uint32_t qpos = wsched.x + lane;  // position in this frame's (longest first) stream list
+  bool done = !(lane < wsched.y && qpos < F.lean_count);
   uint8_t* const nz = s_nzcol[(threadIdx.x >> 5) * S + (lane < S ? lane : 0)];
   // ---- per-frame constants ----
   const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);

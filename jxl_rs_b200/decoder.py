@@ -274,7 +274,7 @@ class PipelinedDecoder:
     front-end work of batch k+1 therefore overlaps the kernels and the D2H copies of batch k.
     This is the serving-shaped entry point (many independent images in flight)."""
 
-    def __init__(self, device: int = 0, depth: int = 2, workers: int = 0, staging_threads: int = 4, parse_ahead: int = 2):
+    def __init__(self, device: int = 0, depth: int = 3, workers: int = 0, staging_threads: int = 4, parse_ahead: int = 2):
         import os
         import queue
         import threading

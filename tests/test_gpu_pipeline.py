@@ -104,3 +104,60 @@ def test_device_survives_corrupt_streams(golden_dir):
     (o,) = j.decode_files(ctx, [good])
     assert o.shape == (200, 300, 3)
     ctx.close()
+
+
+def test_c_abi_rejects_inconsistent_descriptors():
+    """jxg_batch_add_frame is the boundary a foreign host (the Rust shim) calls: every index-bearing field of the
+    descriptor is checked on the host before a kernel can dereference it; a descriptor of the in-tree front-end passes."""
+    import ctypes as C
+    import torch
+    import jxl_rs_b200 as j
+    import synth
+    data = synth.encode_synthetic(300, 200, 9, 0.5, 2, 1, 1)
+    fr = j.ParsedFrame(data)
+    ctx = j.JxgContext(0)
+    out = torch.empty((200, 300, 3), dtype=torch.uint8, device="cuda:0")
+
+    def try_add(mutate):
+        d, hf, off, ln, n = fr.desc(abi.FORMAT_RGB_U8)
+        keep = mutate(d)  # noqa: F841 - keeps replacement buffers alive
+        b = j.Batch(ctx, 1)
+        try:
+            b.add_desc(d, hf, off, ln, n, out.data_ptr(), 300 * 3, True)
+            return 0
+        except abi.JxgError as e:
+            return e.code
+        finally:
+            b.close()
+
+    assert try_add(lambda d: None) == 0
+
+    def bad_context_map(d):
+        p = d.passes[0]
+        buf = (C.c_uint8 * p.num_contexts).from_buffer_copy(C.string_at(p.context_map, p.num_contexts))
+        buf[5] = 255
+        p.context_map = C.cast(buf, C.c_void_p)
+        return buf
+
+    def bad_transform(d):
+        nb = ((300 + 7) // 8) * ((200 + 7) // 8)
+        buf = (C.c_uint8 * nb).from_buffer_copy(C.string_at(d.transform_map, nb))
+        buf[nb - 1] = 128 | 24  # a 256x256 varblock starting in the last block: crosses the frame
+        d.transform_map = C.cast(buf, C.c_void_p)
+        return buf
+
+    def bad_quant_lf(d):
+        nb = ((300 + 7) // 8) * ((200 + 7) // 8)
+        buf = (C.c_uint8 * nb)(*([200] * nb))
+        d.quant_lf = C.cast(buf, C.c_void_p)
+        return buf
+
+    def setter(name, value):
+        def f(d):
+            setattr(d, name, value)
+        return f
+
+    for mutate in (bad_context_map, bad_transform, bad_quant_lf, setter("block_ctx_map_len", 7), setter("num_block_contexts", 200),
+                   setter("orientation", 9), setter("output_tf", 77), setter("global_scale", 0)):
+        assert try_add(mutate) == -22, mutate  # JXG_ERR_ARGUMENT
+    ctx.close()

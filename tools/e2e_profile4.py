@@ -8,17 +8,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 args = types.SimpleNamespace(frames=n, unique=0, width=3840, height=2160, distance=0.5, epf=2, profile=1)
 files = bench.make_frames(args, 0)
-host_out = [[torch.empty((2160, 3840, 3), dtype=torch.uint8).pin_memory() for _ in range(n)] for _ in range(2)]
+depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+j.bind_to_gpu_numa_node(0)
+host_out = [[torch.empty((2160, 3840, 3), dtype=torch.uint8).pin_memory() for _ in range(n)] for _ in range(depth)]
 outs = [[(o.data_ptr(), 3840 * 3) for o in ho] for ho in host_out]
-for st in (8, 16):
-    dec = j.PipelinedDecoder(0, depth=2, staging_threads=st)
+for st in (4, 8):
+    dec = j.PipelinedDecoder(0, depth=depth, staging_threads=st)
     for i in range(3):
-        dec.submit(files, outs[i % 2])
+        dec.submit(files, outs[i % depth])
     dec.drain()
     dec.trace = []
     t0 = time.perf_counter()
     for i in range(steps):
-        dec.submit(files, outs[i % 2])
+        dec.submit(files, outs[i % depth])
     dec.drain()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
