@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -500,13 +501,14 @@ int jxg_batch_add_frame(void* bp, const JxgFrameDesc* d, const uint8_t* hf_bytes
 }
 
 // Schedule of the persistent entropy lanes (k_entropy_lean). A stream's cost is proportional to its section length
-// and a stream is one serial chain, so the kernel cannot end before the longest stream of any frame does; what the
-// schedule controls is how fast that stream runs and how many warps the rest occupies. Each frame's streams are
-// ordered longest first; streams longer than `solo` x the longest get a warp of their own (a lone lane does not pay
-// for the divergent set-up paths of neighbours: ~510 against ~830 cycles per symbol at 1 against 4 lanes per warp,
-// profiles/r01_ncu_summary.md), those above `duo` x the longest share a warp in pairs, the rest is packed S to a warp;
-// the shortest streams are not assigned at all but queued, and pulled by whichever lane finishes first
-// (longest-processing-time rule). All CTAs of one frame stay on that frame so that its tables stay in L1 / shared memory.
+// and a stream is one serial chain; each frame's streams are ordered longest first and handed to the frame's lanes in
+// that order (longest-processing-time rule), streams beyond the initial assignment are queued and pulled by whichever
+// lane finishes first. All CTAs of one frame stay on that frame so that its tables stay in L1 / shared memory.
+// Measured on B200 (64 x 4K, profiles/r02_entropy_schedule.md): every stream on a lane of its own from the start, four
+// lanes to a warp, is the fastest (33.1 ms); giving the longest streams warps of their own (`solo` / `duo` thresholds
+// as fractions of the frame's longest stream) is slower (38.6 - 41.4 ms) because a lone lane still costs a full warp's
+// issue slots, and so are fewer lanes with queued streams (43.9 ms at 2.5 streams per lane) and 8 lanes per warp (40.2).
+// The thresholds stay as experiment knobs (JXG_ENTROPY_SOLO / _DUO / _PER_LANE / _S).
 static void schedule_lean(Batch* b) {
   if (b->streams_lean.empty() || b->lean_ctas) return;
   auto len_of = [&](const StreamDev& sd) { return b->sections[b->frames[sd.frame].section_base + sd.group].len; };
@@ -517,9 +519,9 @@ static void schedule_lean(Batch* b) {
     const char* e = getenv(name);
     return e ? float(atof(e)) : dflt;
   };
-  float solo = knob("JXG_ENTROPY_SOLO", 0.62f), duo = knob("JXG_ENTROPY_DUO", 0.45f);
+  float solo = knob("JXG_ENTROPY_SOLO", 1.1f), duo = knob("JXG_ENTROPY_DUO", 1.1f);
   // streams per packed lane (initial stream + queued ones): 1 = every stream starts at once
-  float per_lane = std::max(1.0f, knob("JXG_ENTROPY_PER_LANE", 1.6f));
+  float per_lane = std::max(1.0f, knob("JXG_ENTROPY_PER_LANE", 1.0f));
   const size_t nf = b->frames.size();
   for (auto& F : b->frames) F.lean_first = F.lean_count = F.lean_cta_first = F.lean_ctas = F.lean_lanes = 0;
   for (size_t i = 0; i < b->streams_lean.size();) {
@@ -585,7 +587,7 @@ static void schedule_lean(Batch* b) {
   for (size_t f = 0; f < nf; f++) b->lean_cta_first[f] = b->frames[f].lean_cta_first;
 }
 
-static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
+static BatchDev make_batch_dev(Batch* b) {
   BatchDev B;
   memset(&B, 0, sizeof(B));
   B.blob = static_cast<const uint8_t*>(b->d_blob.p);
@@ -601,7 +603,8 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   B.num_fast = uint32_t(b->streams_fast.size());
   B.num_slow = uint32_t(b->streams_slow.size());
   B.reg_idct32 = (getenv("JXG_REG_IDCT32") && atoi(getenv("JXG_REG_IDCT32"))) ? 1u : 0u;
-  B.coeffs = static_cast<int32_t*>(b->d_coeffs.p);
+  B.nzlist = static_cast<uint32_t*>(b->d_coeffs.p);  // the pool that held the dense coefficients now holds the lists
+  B.big = static_cast<BigTable*>(b->ctx->d_big.p);
   B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
   B.nz = static_cast<uint8_t*>(b->d_nz.p);
   B.nz_base = static_cast<uint64_t*>(b->d_nz_base.p);
@@ -611,13 +614,18 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   B.queue = reinterpret_cast<uint32_t*>(B.status + b->streams.size());
   B.lean_cta_first = static_cast<const uint32_t*>(b->d_lean_cta.p);
   B.lean_warp = static_cast<const uint2*>(b->ctx->d_lean_warp.p);
-  B.lean_desc = static_cast<uint4*>(b->ctx->d_lean_desc.p);
-  B.lean_nblk = static_cast<uint32_t*>(b->ctx->d_lean_nblk.p);
+  B.desc = static_cast<uint4*>(b->ctx->d_lean_desc.p);
+  B.nblk = static_cast<uint32_t*>(b->ctx->d_lean_nblk.p);
   B.dequant_default = static_cast<const float*>(b->ctx->dequant_default.p);
   B.dequant_default_off = static_cast<const uint32_t*>(b->ctx->dequant_default_off.p);
   B.natural_orders = static_cast<const uint32_t*>(b->ctx->natural_orders.p);
   B.natural_order_off = static_cast<const uint32_t*>(b->ctx->natural_order_off.p);
-  size_t coeff_bytes = size_t(b->total_groups) * 3 * kGroupCoeffs * 4;
+  return B;
+}
+
+static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
+  const BatchDev B = make_batch_dev(b);
+  size_t coeff_bytes = 0;
   cudaEvent_t* ev = b->profile ? b->stage_ev : nullptr;
   b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
@@ -675,9 +683,29 @@ static int copy_status(Batch* b, cudaStream_t s) {
   return 0;
 }
 
+// JXG_TRACE_RUN=1: host-side phase times of jxg_batch_run on stderr (which call blocks, and for how long).
+struct RunTrace {
+  bool on = getenv("JXG_TRACE_RUN") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+  std::string line;
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[64];
+    snprintf(buf, sizeof(buf), " %s %.1f", what, std::chrono::duration<double, std::milli>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  ~RunTrace() {
+    if (on) fprintf(stderr, "[jxg_batch_run]%s | total %.1f ms\n", line.c_str(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 int jxg_batch_run(void* bp, void* cuda_stream) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b || b->frames.empty()) return JXG_ERR_ARGUMENT;
+  RunTrace trace;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
   b->last_stream = s;
@@ -685,15 +713,17 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   schedule_lean(b);
   // device allocations
   if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
-  if (int r = b->d_coeffs.ensure(size_t(b->total_groups) * 3 * kGroupCoeffs * 4)) return r;
+  // one coefficient list per HF section (pass x group), worst-case capacity (every coefficient non-zero)
+  if (int r = b->d_coeffs.ensure(b->sections.size() * size_t(kListStride) * 4)) return r;
+  if (int r = b->ctx->d_big.ensure(std::max<size_t>(b->sections.size() * sizeof(BigTable), 16))) return r;
   if (int r = b->d_block_off.ensure(b->total_blocks * 4)) return r;
   if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
   if (int r = b->d_planes_a.ensure(b->total_plane_floats * 4)) return r;
   if (int r = b->d_planes_b.ensure(b->total_plane_floats * 4)) return r;
   if (int r = b->d_status.ensure((b->streams.size() + b->frames.size() + 4) * 4)) return r;
   if (int r = b->d_out.ensure(std::max<size_t>(b->out_bytes, 16))) return r;
-  if (int r = b->ctx->d_lean_desc.ensure(std::max<size_t>(b->streams_lean.size() * 1024 * 16, 16))) return r;
-  if (int r = b->ctx->d_lean_nblk.ensure(std::max<size_t>(b->streams_lean.size() * 4, 16))) return r;
+  if (int r = b->ctx->d_lean_desc.ensure(std::max<size_t>(b->streams.size() * 1024 * 16, 16))) return r;
+  if (int r = b->ctx->d_lean_nblk.ensure(std::max<size_t>(b->streams.size() * 4, 16))) return r;
   if (int r = b->ctx->d_orient.ensure(std::max<size_t>(b->orient_bytes, 16))) return r;
   for (size_t f = 0; f < b->frames.size(); f++) {
     const FrameOut& fo = b->outs[f];
@@ -709,9 +739,12 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   }
   b->status_host = b->ctx->status_host;
   memset(b->status_host, 0, b->status_n * 4);
+  trace.mark("alloc");
   b->blob.flush();
+  trace.mark("flush");
   CUDA_TRY(cudaEventRecord(b->ev0, s));
   CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
+  trace.mark("blob_h2d");
   b->h2d += b->blob.size;
   if (int r = upload(b->d_frames, b->frames, s, &b->h2d)) return r;
   if (int r = upload(b->d_sections, b->sections, s, &b->h2d)) return r;
@@ -725,9 +758,12 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
   if (int r = upload(b->d_ftiles, b->fused_prefix, s, &b->h2d)) return r;
   b->uploaded = true;
+  trace.mark("uploads");
   if (int r = launch(b, s, true)) return r;
+  trace.mark("launch");
   if (int r = copy_status(b, s)) return r;
   CUDA_TRY(cudaEventRecord(b->ev1, s));
+  trace.mark("status");
   return JXG_OK;
 }
 
@@ -779,8 +815,15 @@ int jxg_batch_read_coeffs(void* bp, uint32_t f, int32_t* out, size_t out_len) {
   size_t n = size_t(F.num_groups) * 3 * kGroupCoeffs;
   if (out_len < n) return JXG_ERR_ARGUMENT;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
-  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
-  CUDA_TRY(cudaMemcpy(out, static_cast<int32_t*>(b->d_coeffs.p) + F.coeff_group_base * 3 * kGroupCoeffs, n * 4, cudaMemcpyDeviceToHost));
+  cudaStream_t s = b->last_stream ? b->last_stream : b->ctx->stream;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  // The device holds lists of non-zero coefficients; the tap expands them into the reference's dense layout.
+  DevBuf dense;
+  if (int r = dense.ensure(n * 4)) return r;
+  CUDA_TRY(cudaMemsetAsync(dense.p, 0, n * 4, s));
+  launch_expand_coeffs(make_batch_dev(b), f, F.num_groups, static_cast<int32_t*>(dense.p), s);
+  CUDA_TRY(cudaMemcpyAsync(out, dense.p, n * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
   return JXG_OK;
 }
 

@@ -11,6 +11,26 @@ namespace jxgpu {
 constexpr int kMaxPasses = 11;
 constexpr uint32_t kGroupCoeffs = 65536;  // per channel per group (group.rs:53-55)
 
+// Coefficients travel from the entropy kernels to the transform kernels as one list of NON-ZERO entries per
+// (pass, group) stream, in decode order (varblocks in raster order, channels Y, X, B inside a varblock, coefficient
+// order inside a channel): entry = position in the varblock's storage layout (16 bits) | value << 16 (i16). A value
+// outside i16 leaves the marker 0x8000 in the entry and goes to the list's side table. Behind the entries sit the
+// offset words: offw[seq * 3 + ci] = index of the first entry of channel ci (0 = Y, 1 = X, 2 = B) of the seq-th
+// varblock, offw[nblk * 3] = total. The dense [groups][3][65536] i32 array of round 1 (12 B/px written once, read
+// once, >= 90 % zeros, plus a memset) is gone; a list is written and read sequentially.
+constexpr uint32_t kListCap = 3 * kGroupCoeffs;        // entries: every coefficient of the group non-zero
+constexpr uint32_t kOffWords = 3 * 1024 + 4;           // offsets of <= 1024 varblocks x 3 channels + end, 16-byte multiple
+constexpr uint32_t kListStride = kListCap + kOffWords;  // u32 words per list
+constexpr uint32_t kBigCap = 255;
+struct BigTable {  // values beyond i16, in entry order (2048 bytes per list)
+  uint32_t count, pad;
+  struct {
+    uint32_t entry;
+    int32_t value;
+  } e[kBigCap];
+};
+constexpr uint32_t kBigMarker = 0x8000u;
+
 struct PassDev {
   uint32_t shift, use_prefix, log_alpha_size, num_clusters;
   uint32_t lz77_enabled, lz77_min_symbol, lz77_min_length, lz77_length_uint, lz_dist_cluster;
@@ -90,8 +110,9 @@ struct BatchDev {
   const StreamDev* streams_slow;  // multi-pass frames: k_entropy
   uint32_t num_frames, num_streams, num_lean, num_fast, num_slow;
   uint32_t reg_idct32;  // 1: rows of 32 coefficients also go through the register path (experiment knob)
-  int32_t* coeffs;      // [groups][3][65536]
-  uint32_t* block_off;  // per 8x8 block: coefficient offset of the varblock starting there
+  uint32_t* nzlist;     // [sections][kListStride]: list of section (pass * num_groups + group) of a frame, see above
+  BigTable* big;        // [sections]
+  uint32_t* block_off;  // per 8x8 block: ordinal (raster order) of the varblock starting there within its group
   uint8_t* nz;          // [streams][passes][3][1024]
   uint64_t* nz_base;    // per stream offset into nz (bytes)
   float* planes_a;
@@ -100,8 +121,8 @@ struct BatchDev {
   uint32_t* queue;      // [frames] work-queue cursors of the persistent entropy kernel
   const uint32_t* lean_cta_first;  // [frames] first CTA of each frame in k_entropy_lean's grid
   const uint2* lean_warp;          // [lean CTAs * 4] per warp: first stream (relative to the frame's list), lanes
-  uint4* lean_desc;      // [num_lean][1024] varblock descriptors written by k_block_plan
-  uint32_t* lean_nblk;   // [num_lean] varblocks per stream (0xffffffff: invalid transform id)
+  uint4* desc;           // [num_streams][1024] varblock descriptors written by k_block_plan
+  uint32_t* nblk;        // [num_streams] varblocks per stream (0xffffffff: invalid transform id)
   // context-wide tables
   const float* dequant_default;       // 17 tables concatenated
   const uint32_t* dequant_default_off;  // [17] float offsets

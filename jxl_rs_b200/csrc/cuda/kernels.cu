@@ -165,15 +165,80 @@ __device__ __forceinline__ uint32_t read_symbol(const PassTables& T, PassState& 
 
 __device__ __forceinline__ int32_t unpack_signed(uint32_t u) { return int32_t((u >> 1) ^ (((~u) & 1u) - 1u)); }
 
+// One coefficient list (device_types.h): base of the entries, offset words behind them.
+__device__ __forceinline__ uint32_t* list_base(const BatchDev& B, uint32_t section) { return B.nzlist + size_t(section) * kListStride; }
+// Entry of a non-zero coefficient; values beyond i16 go to the side table (false: table full).
+__device__ __forceinline__ bool list_put(const BatchDev& B, uint32_t section, uint32_t* base, uint32_t& n, uint32_t pos, int32_t v) {
+  uint32_t e = pos | (uint32_t(v) << 16);
+  bool ok = true;
+  if (v < -32767 || v > 32767) {
+    BigTable& T = B.big[section];
+    const uint32_t j = T.count;
+    if (j < kBigCap) {
+      T.e[j].entry = n;
+      T.e[j].value = v;
+      T.count = j + 1;
+    } else {
+      ok = false;
+    }
+    e = pos | (kBigMarker << 16);
+  }
+  if (n < kListCap) base[n++] = e;
+  return ok;
+}
+// Value of entry i (reader side).
+__device__ __forceinline__ int32_t list_value(const BatchDev& B, uint32_t section, uint32_t i, uint32_t e) {
+  const uint32_t hi = e >> 16;
+  if (hi != kBigMarker) return int32_t(int16_t(hi));
+  const BigTable& T = B.big[section];
+  uint32_t lo = 0, n = min(T.count, kBigCap);
+  while (lo < n) {  // entries are in increasing order
+    const uint32_t mid = (lo + n) >> 1;
+    if (T.e[mid].entry < i) lo = mid + 1;
+    else n = mid;
+  }
+  return (lo < min(T.count, kBigCap) && T.e[lo].entry == i) ? T.e[lo].value : 0;
+}
+
+// Builds the dense coefficient tile of one varblock in shared memory from the coefficient lists: `nl` lanes (rank r,
+// all lanes of `gmask` call this together) zero tile[3][NC], then add the entries of every pass (the sum of the passes
+// is the coefficient, group.rs:556-567). Entries come in the order Y, X, B; the tile is indexed X, Y, B like the
+// dequant tables. Positions beyond NC (corrupt stream) are dropped.
+__device__ __forceinline__ void gather_block_tile(const BatchDev& B, const FrameDev& F, uint32_t g, uint32_t seq, int32_t* tile,
+                                                  uint32_t NC, uint32_t r, uint32_t nl, uint32_t gmask, bool valid) {
+  int4* t4 = reinterpret_cast<int4*>(tile);
+  __syncwarp(gmask);  // the previous varblock of this lane group has been read completely
+  for (uint32_t i = r; i < 3 * NC / 4; i += nl) t4[i] = make_int4(0, 0, 0, 0);
+  __syncwarp(gmask);
+  for (uint32_t p = 0; p < F.num_passes; p++) {
+    const uint32_t section = F.section_base + p * F.num_groups + g;
+    const uint32_t* base = list_base(B, section);
+    if (valid) {
+      const uint32_t* ow = base + kListCap + seq * 3;
+      const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
+      uint32_t o3 = __ldg(ow + 3);
+      o3 = min(o3, kListCap);
+      for (uint32_t i = o0 + r; i < o3; i += nl) {
+        const uint32_t e = __ldg(base + i);
+        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
+        const uint32_t pos = e & 0xffffu;
+        if (pos < NC) tile[c * NC + pos] += list_value(B, section, i, e);
+      }
+    }
+    if (p + 1 < F.num_passes) __syncwarp(gmask);
+  }
+  __syncwarp(gmask);
+}
+
 struct BlockInfo {
   uint32_t bx, by, cx, cy, shape, raw_quant, quant_lf, num_blocks, num_coeffs, log_num_blocks;
 };
 
 // One varblock, one pass: the three channels in Y, X, B order (group.rs:509-577).
 __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameDev& F, const PassDev& P,
-                                                 const PassTables& T, PassState& s, uint32_t pass, const BlockInfo& bi,
-                                                 uint8_t* nz_pass /* [3][1024] */, int32_t* group_coeffs,
-                                                 uint32_t coeffs_offset) {
+                                                 const PassTables& T, PassState& s, const BlockInfo& bi,
+                                                 uint8_t* nz_pass /* [3][1024] */, uint32_t section, uint32_t* list, uint32_t& nlist,
+                                                 uint32_t bseq) {
   const uint32_t num_ac_contexts = F.num_block_contexts * (37 + 458);
   const uint32_t context_offset = s.hist_idx * num_ac_contexts;
   const uint8_t* bcm = B.blob + F.block_ctx_map_off;
@@ -203,7 +268,7 @@ __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameD
     const uint32_t* order = P.custom_orders
                                 ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[bi.shape * 3 + c]
                                 : B.natural_orders + B.natural_order_off[bi.shape];
-    int32_t* cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+    list[kListCap + bseq * 3 + ci] = nlist;  // first entry of channel ci (Y, X, B) of this varblock in this pass
     const uint32_t lnb = bi.log_num_blocks, rnd = bi.num_blocks - 1;
 #pragma unroll 1
     for (uint32_t k = bi.num_blocks; k < bi.num_coeffs && nonzeros != 0; k++) {
@@ -212,11 +277,7 @@ __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameD
       int32_t coeff = int32_t(uint32_t(unpack_signed(u)) << P.shift);
       prev = coeff != 0;
       nonzeros -= prev;
-      if (coeff != 0) {
-        uint32_t pos = __ldg(order + k);
-        if (pass == 0) cur[pos] = coeff;
-        else cur[pos] += coeff;
-      }
+      if (coeff != 0 && !list_put(B, section, list, nlist, __ldg(order + k), coeff)) return JXG_ERR_UNSUPPORTED;
     }
     if (nonzeros != 0) return JXG_ERR_RESIDUAL_NONZEROS;
   }
@@ -266,66 +327,50 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
   const uint32_t gx = g % F.xg, gy = g / F.xg;
   const uint32_t bx0 = gx * 32, by0 = gy * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
-  int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
   uint8_t* nz = B.nz + B.nz_base[stream];
   const uint8_t* tmap = B.blob + F.transform_off;
   const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const uint8_t* qlf = B.blob + F.quant_lf_off;
-  uint32_t* block_off = B.block_off + F.block_base;
   const uint32_t np = F.num_passes;
   int err = 0;
-  uint32_t coeffs_offset = 0;
-
-  if (np == 1) {
-    PassState s;
-    err = init_pass(B, F, 0, g, s);
-    const PassTables T = make_tables(B, F.passes[0]);
-    for (uint32_t by = 0; by < gh && !err; by++) {
-      for (uint32_t bx = 0; bx < gw && !err; bx++) {
-        const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
-        uint32_t raw_t = tmap[bidx];
-        if (raw_t < 128) continue;
-        uint32_t t = raw_t & 127;
-        if (t >= 27) { err = JXG_ERR_INVALID_TRANSFORM; break; }
-        BlockInfo bi;
-        bi.bx = bx; bi.by = by; bi.cx = c_cov_x[t]; bi.cy = c_cov_y[t]; bi.shape = c_shape[t];
-        bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
-        bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
-        bi.log_num_blocks = 31 - __clz(bi.num_blocks);
-        if (coeffs_offset + bi.num_coeffs > kGroupCoeffs) { err = JXG_ERR_INVALID_TRANSFORM; break; }  // overlapping varblocks
-        block_off[bidx] = coeffs_offset;
-        err = decode_block_pass(B, F, F.passes[0], T, s, 0, bi, nz, group_coeffs, coeffs_offset);
-        coeffs_offset += bi.num_coeffs;
+  uint32_t coeffs_offset = 0, bseq = 0;
+  // one coefficient list per pass (section = pass * num_groups + group); the transform kernels add the passes up
+  PassState st[kMaxPasses];
+  uint32_t nlist[kMaxPasses];
+  for (uint32_t p = 0; p < np; p++) {
+    nlist[p] = 0;
+    B.big[F.section_base + p * F.num_groups + g].count = 0;
+  }
+  for (uint32_t p = 0; p < np && !err; p++) err = init_pass(B, F, p, g, st[p]);
+  for (uint32_t by = 0; by < gh && !err; by++) {
+    for (uint32_t bx = 0; bx < gw && !err; bx++) {
+      const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
+      uint32_t raw_t = tmap[bidx];
+      if (raw_t < 128) continue;
+      uint32_t t = raw_t & 127;
+      if (t >= 27) { err = JXG_ERR_INVALID_TRANSFORM; break; }
+      BlockInfo bi;
+      bi.bx = bx; bi.by = by; bi.cx = c_cov_x[t]; bi.cy = c_cov_y[t]; bi.shape = c_shape[t];
+      bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
+      bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
+      bi.log_num_blocks = 31 - __clz(bi.num_blocks);
+      if (coeffs_offset + bi.num_coeffs > kGroupCoeffs || bseq >= 1024) { err = JXG_ERR_INVALID_TRANSFORM; break; }  // overlapping varblocks
+      for (uint32_t p = 0; p < np && !err; p++) {
+        PassState s = st[p];
+        const PassTables T = make_tables(B, F.passes[p]);
+        const uint32_t section = F.section_base + p * F.num_groups + g;
+        uint32_t n = nlist[p];
+        err = decode_block_pass(B, F, F.passes[p], T, s, bi, nz + p * 3072, section, list_base(B, section), n, bseq);
+        nlist[p] = n;
+        st[p] = s;
       }
+      coeffs_offset += bi.num_coeffs;
+      bseq++;
     }
-    if (!err) err = finish_pass(B, F, 0, g, s);
-  } else {
-    PassState st[kMaxPasses];
-    for (uint32_t p = 0; p < np && !err; p++) err = init_pass(B, F, p, g, st[p]);
-    for (uint32_t by = 0; by < gh && !err; by++) {
-      for (uint32_t bx = 0; bx < gw && !err; bx++) {
-        const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
-        uint32_t raw_t = tmap[bidx];
-        if (raw_t < 128) continue;
-        uint32_t t = raw_t & 127;
-        if (t >= 27) { err = JXG_ERR_INVALID_TRANSFORM; break; }
-        BlockInfo bi;
-        bi.bx = bx; bi.by = by; bi.cx = c_cov_x[t]; bi.cy = c_cov_y[t]; bi.shape = c_shape[t];
-        bi.raw_quant = uint32_t(rq[bidx]); bi.quant_lf = qlf[bidx];
-        bi.num_blocks = bi.cx * bi.cy; bi.num_coeffs = bi.num_blocks * 64;
-        bi.log_num_blocks = 31 - __clz(bi.num_blocks);
-        if (coeffs_offset + bi.num_coeffs > kGroupCoeffs) { err = JXG_ERR_INVALID_TRANSFORM; break; }  // overlapping varblocks
-        block_off[bidx] = coeffs_offset;
-        for (uint32_t p = 0; p < np && !err; p++) {
-          PassState s = st[p];
-          const PassTables T = make_tables(B, F.passes[p]);
-          err = decode_block_pass(B, F, F.passes[p], T, s, p, bi, nz + p * 3072, group_coeffs, coeffs_offset);
-          st[p] = s;
-        }
-        coeffs_offset += bi.num_coeffs;
-      }
-    }
-    for (uint32_t p = 0; p < np && !err; p++) err = finish_pass(B, F, p, g, st[p]);
+  }
+  for (uint32_t p = 0; p < np && !err; p++) {
+    list_base(B, F.section_base + p * F.num_groups + g)[kListCap + bseq * 3] = nlist[p];
+    err = finish_pass(B, F, p, g, st[p]);
   }
   B.status[stream] = err;
 }
@@ -406,13 +451,14 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
   const uint32_t gsid = F.first_stream + g;
   const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0), gn = gw * gh;
-  int32_t* const group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
+  const uint32_t lsec = F.section_base + g;  // single pass: list of section `group`
+  uint32_t* const list = list_base(B, lsec);
+  uint32_t nlist = 0, bseq = 0;
   uint8_t* const nz = B.nz + B.nz_base[gsid];
   const uint8_t* const tmap = B.blob + F.transform_off;
   const int32_t* const rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const uint8_t* const qlf = B.blob + F.quant_lf_off;
   const uint8_t* const bcm = B.blob + F.block_ctx_map_off;
-  uint32_t* const block_off = B.block_off + F.block_base;
   const PassDev& P = F.passes[0];
   const uint8_t* const ctxmap = B.blob + P.context_map_off;
   const uint32_t* const ucfg = reinterpret_cast<const uint32_t*>(B.blob + P.uint_configs_off);
@@ -429,6 +475,7 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
   uint32_t ans_state = 0x130000u, context_offset = 0;
   if (!done) {
     const SectionDev sec = B.sections[F.section_base + g];
+    B.big[lsec].count = 0;
     br.init(B.blob + sec.off, sec.len);
     uint32_t nb = 0;
     while ((1u << nb) < F.num_histograms) nb++;
@@ -454,7 +501,6 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
   uint32_t bx = 0, by = 0, cx = 1, cy = 1, shape = 0, qf_idx = 0, quant_lf = 0, num_blocks = 1, num_coeffs = 64, lnb = 0;
   uint32_t ci = 0, k = 0, nonzeros = 0, prev = 0, histo_offset = 0;
   const uint32_t* order = B.natural_orders;
-  int32_t* cur = group_coeffs;
 
   for (;;) {
     if (!__any_sync(0xffffffffu, !done)) break;
@@ -472,6 +518,7 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
         if (br.bitpos > sec.len * 8u) err = JXG_ERR_OUT_OF_BOUNDS;
         else if (!use_prefix && ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
         B.status[gsid] = err;
+        list[kListCap + bseq * 3] = nlist;
         done = true;
       } else {
         const uint32_t t = raw_t & 127;
@@ -490,11 +537,10 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
           num_blocks = cx * cy;
           num_coeffs = num_blocks * 64;
           lnb = 31 - __clz(num_blocks);
-          if (coeffs_offset + num_coeffs > kGroupCoeffs) {  // overlapping varblocks: the group's coefficient area would overflow
+          if (coeffs_offset + num_coeffs > kGroupCoeffs || bseq >= 1024) {  // overlapping varblocks: the group's coefficient area would overflow
             B.status[gsid] = JXG_ERR_INVALID_TRANSFORM;
             done = true;
           } else {
-            block_off[bidx] = coeffs_offset;
             ci = 0;
             phase = PH_NNZ;
           }
@@ -571,13 +617,17 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
                               : B.natural_orders + B.natural_order_off[shape];
-      cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+      list[kListCap + bseq * 3 + ci] = nlist;
       if (nonzeros == 0) next_channel = true;
       else phase = PH_COEF;
     } else {
       const int32_t coeff = int32_t(uint32_t(unpack_signed(value)) << shift);
       if (coeff != 0) {
-        cur[__ldg(order + k)] = coeff;
+        if (!list_put(B, lsec, list, nlist, __ldg(order + k), coeff)) {
+          B.status[gsid] = JXG_ERR_UNSUPPORTED;
+          done = true;
+          continue;
+        }
         prev = 1;
         nonzeros--;
       } else {
@@ -596,6 +646,7 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
       phase = PH_NNZ;
       if (ci == 3) {
         coeffs_offset += num_coeffs;
+        bseq++;
         pos++;
         phase = PH_SCAN;
       }
@@ -622,14 +673,14 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
 // in raster order and writes, for every varblock, a 16-byte descriptor
 //   x: bx | by << 5 | cx << 10 | cy << 16 | shape << 22 | log2(cx * cy) << 26
 //   y: block contexts of Y, X, B (block_context_map.rs:128-150), one byte each
-//   z: offset of the block's coefficients inside the group (group.rs:455)
-// plus the block count and block_off[] (read by the transform kernels). This is everything the serial decode lanes
+//   z: offset of the block's coefficients inside the group's dense decode-order array (group.rs:455; parity tap only)
+// plus the block count and block_off[] = the varblock's ordinal (read by the transform kernels to find its entries). This is everything the serial decode lanes
 // needed several dependent loads and a scan loop for, computed here fully in parallel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_block_plan(const BatchDev B) {
   const uint32_t sidx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (sidx >= B.num_lean) return;
-  const StreamDev sd = B.streams_lean[sidx];
+  if (sidx >= B.num_streams) return;
+  const StreamDev sd = B.streams[sidx];  // ordered by frame then group: sidx == F.first_stream + group
   const FrameDev& F = B.frames[sd.frame];
   const uint32_t g = sd.group;
   const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
@@ -640,7 +691,7 @@ __global__ void __launch_bounds__(128) k_block_plan(const BatchDev B) {
   const uint8_t* qlf = B.blob + F.quant_lf_off + goff;
   const uint8_t* bcm = B.blob + F.block_ctx_map_off;
   uint32_t* block_off = B.block_off + F.block_base + goff;
-  uint4* desc = B.lean_desc + size_t(sidx) * 1024;
+  uint4* desc = B.desc + size_t(sidx) * 1024;
   uint32_t seq = 0, coeffs_offset = 0;
   bool bad = false;
   for (uint32_t by = 0; by < gh; by++) {
@@ -680,13 +731,13 @@ __global__ void __launch_bounds__(128) k_block_plan(const BatchDev B) {
       d.z = off;
       d.w = 0;
       desc[seq + rank] = d;
-      block_off[bidx] = off;
+      block_off[bidx] = seq + rank;
     }
     seq += __popc(mask);
     coeffs_offset += row_total;
   }
   bad = __any_sync(0xffffffffu, bad);
-  if (lane == 0) B.lean_nblk[sidx] = bad ? 0xffffffffu : seq;
+  if (lane == 0) B.nblk[sidx] = bad ? 0xffffffffu : seq;
 }
 
 // Loads the compiler must not sink below the token computation (it would re-serialise the chain).
@@ -773,8 +824,9 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   const uint32_t log_alpha = P.log_alpha_size, log_bucket = 12 - P.log_alpha_size, bucket_mask = (1u << (12 - P.log_alpha_size)) - 1;
   // ---- per-stream state (re-initialised by the set-up path when a lane takes a new stream) ----
   uint32_t gsid = 0, nblk = 0, bi = 0;
-  const uint4* desc = B.lean_desc;
-  int32_t* group_coeffs = B.coeffs;
+  const uint4* desc = B.desc;
+  uint32_t* list = B.nzlist;  // this stream's coefficient list (pass 0), entries written so far, its section index
+  uint32_t nlist = 0, lsec = 0;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(B.blob);
   uint32_t sec_bits = 0, wlimit = 0;
   uint32_t bitpos = 0, ans_state = 0x130000u, context_offset = 0;
@@ -789,7 +841,6 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   uint32_t block_context = 0, cluster = 0;
   uint32_t k = 0, nonzeros = 0, histo_offset = 0;
   const uint32_t* order = B.natural_orders;
-  int32_t* cur = group_coeffs;
 
   for (;;) {
     if (!__any_sync(0xffffffffu, !done)) break;
@@ -800,9 +851,12 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           const uint32_t lidx = F.lean_first + qpos;
           const uint32_t g = B.streams_lean[lidx].group;
           gsid = F.first_stream + g;
-          group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
-          desc = B.lean_desc + size_t(lidx) * 1024;
-          nblk = B.lean_nblk[lidx];
+          lsec = F.section_base + g;
+          list = list_base(B, lsec);
+          nlist = 0;
+          B.big[lsec].count = 0;
+          desc = B.desc + size_t(gsid) * 1024;
+          nblk = B.nblk[gsid];
           bi = 0;
           const SectionDev sec = B.sections[F.section_base + g];
           words = reinterpret_cast<const uint32_t*>(B.blob + sec.off);
@@ -837,6 +891,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
             if (bitpos > sec_bits) err = JXG_ERR_OUT_OF_BOUNDS;
             else if (ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
             B.status[gsid] = err;
+            list[kListCap + nblk * 3] = nlist;  // end of the last varblock's entries
           }
           qpos = atomicAdd(B.queue + fidx, 1u) + frame_lanes;
           if (qpos >= F.lean_count) {
@@ -948,7 +1003,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
                               : B.natural_orders + s_order_off[shape];
-      cur = group_coeffs + c * kGroupCoeffs + coeffs_offset;
+      list[kListCap + (bi - 1) * 3 + ci] = nlist;  // first entry of this varblock's channel ci (Y, X, B)
       mode_nnz = false;
       if (nonzeros == 0) {
         need_setup = true;
@@ -959,7 +1014,16 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
                               uint32_t(s_fr2[(k >> lnb) & 63]) + prev);
       }
     } else {
-      if (nonzero) cur[__ldg(order + k)] = unpack_signed(value);  // lean streams have shift == 0 (host routing)
+      if (nonzero) {  // lean streams have shift == 0 (host routing)
+        if (!list_put(B, lsec, list, nlist, __ldg(order + k), unpack_signed(value))) {
+          B.status[gsid] = JXG_ERR_UNSUPPORTED;  // more than kBigCap coefficients beyond 16 bits in one group
+          failed = true;
+          bi = nblk;
+          ci = 3;
+          need_setup = true;
+          continue;
+        }
+      }
       nonzeros -= nonzero;
       cluster = cluster_next;
       k++;
@@ -1131,14 +1195,15 @@ struct DequantCtx {
   const float* mat;
   uint32_t num_coeffs;
   float sx, sy, sb, x_cc, b_cc, bias0, bias1, bias2, bias3;
-  __device__ __forceinline__ void get(uint32_t k, float& vx, float& vy, float& vb) const {
-    float dy = adjust_quant_bias(qy[k], bias1, bias3) * (__ldg(mat + num_coeffs + k) * sy);
-    float dxc = adjust_quant_bias(qx[k], bias0, bias3) * (__ldg(mat + k) * sx);
-    float dbc = adjust_quant_bias(qb[k], bias2, bias3) * (__ldg(mat + 2 * num_coeffs + k) * sb);
+  __device__ __forceinline__ void get_q(uint32_t k, int32_t qxv, int32_t qyv, int32_t qbv, float& vx, float& vy, float& vb) const {
+    float dy = adjust_quant_bias(qyv, bias1, bias3) * (__ldg(mat + num_coeffs + k) * sy);
+    float dxc = adjust_quant_bias(qxv, bias0, bias3) * (__ldg(mat + k) * sx);
+    float dbc = adjust_quant_bias(qbv, bias2, bias3) * (__ldg(mat + 2 * num_coeffs + k) * sb);
     vy = dy;
     vx = fmaf(x_cc, dy, dxc);
     vb = fmaf(b_cc, dy, dbc);
   }
+  __device__ __forceinline__ void get(uint32_t k, float& vx, float& vy, float& vb) const { get_q(k, qx[k], qy[k], qb[k], vx, vy, vb); }
 };
 
 // ---- special 8x8 transforms, one lane per channel, serial (transform.rs:306-661) ----
@@ -1313,7 +1378,9 @@ __device__ __forceinline__ bool is_small_reg_type(int t, bool reg32) {
   return (t == 0) || (t >= 3 && t <= 13 && (reg32 || !(t == 5 || (t >= 8 && t <= 11))));
 }
 
-constexpr int kIdctWarps = 8;
+constexpr int kIdctWarps = 4;   // per warp: float work tiles 3 x kWarpBuf + the varblock's coefficient tile 3 x 1024 i32
+constexpr int kWarpInts = 3 * 1024;
+constexpr size_t kLargeSmemBytes = size_t(kIdctWarps) * (3 * (32 * 33) + kWarpInts) * sizeof(float);
 constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
 
 // Global in-place 1-D passes for varblocks with a dimension >= 64.
@@ -1391,7 +1458,6 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
   const uint32_t gx = g % F.xg, gy = g / F.xg;
   const uint32_t bx0 = gx * 32, by0 = gy * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
-  const int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
   const uint8_t* tmap = B.blob + F.transform_off;
   const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
@@ -1403,21 +1469,20 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
                          reinterpret_cast<const float*>(B.blob + F.lf_off[1]),
                          reinterpret_cast<const float*>(B.blob + F.lf_off[2])};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* wbuf = smem + warp * 3 * kWarpBuf;
+  float* wbuf = smem + warp * (3 * kWarpBuf + kWarpInts);
+  int32_t* itile = reinterpret_cast<int32_t*>(wbuf + 3 * kWarpBuf);
   if (threadIdx.x == 0) {
     s_next = 0;
     s_nbig = 0;
   }
   __syncthreads();
 
+  // everything of the dequantisation context but the coefficient pointers (set by the callers)
   auto setup = [&](uint32_t bx, uint32_t by, int t, DequantCtx& dq) {
     const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
-    const uint32_t off = block_off[bidx];
     const uint32_t cx = c_cov_x[t], cy = c_cov_y[t];
     dq.num_coeffs = cx * cy * 64;
-    dq.qx = group_coeffs + off;
-    dq.qy = group_coeffs + kGroupCoeffs + off;
-    dq.qb = group_coeffs + 2 * kGroupCoeffs + off;
+    dq.qx = dq.qy = dq.qb = nullptr;
     int qt = c_qtable[t];
     dq.mat = F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt])
                                     : B.dequant_default + B.dequant_default_off[qt];
@@ -1455,6 +1520,11 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     }
     DequantCtx dq;
     setup(bx, by, t, dq);
+    // the varblock's coefficients: list entries -> dense tile in shared memory (X, Y, B at stride num_coeffs)
+    gather_block_tile(B, F, g, block_off[bidx], itile, dq.num_coeffs, uint32_t(lane), 32, 0xffffffffu, true);
+    dq.qx = itile;
+    dq.qy = itile + dq.num_coeffs;
+    dq.qb = itile + 2 * dq.num_coeffs;
     const int R = 8 * cy, C = 8 * cx;
     const bool is_dct = (t == 0) || (t >= 4 && t <= 11);
     float* ch0 = wbuf;
@@ -1555,12 +1625,38 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     setup(bx, by, t, dq);
     const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
     const bool wide = R < C;
+    // The varblock's own pixel area doubles as its dense coefficient array (i32 view, coefficient k at the place the
+    // dequantised value goes): zero, add the list entries of every pass, then dequantise in place.
+    auto place = [&](uint32_t k) {
+      const int vf = wide ? int(k) / C : int(k) % R, hf = wide ? int(k) % C : int(k) / R;
+      return px0 + size_t(vf) * F.plane_stride + hf;
+    };
+    int32_t* ip[3] = {reinterpret_cast<int32_t*>(planes[0]), reinterpret_cast<int32_t*>(planes[1]), reinterpret_cast<int32_t*>(planes[2])};
     for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
+      const size_t o = place(k);
+      ip[0][o] = 0;
+      ip[1][o] = 0;
+      ip[2][o] = 0;
+    }
+    __syncthreads();
+    const uint32_t seq = block_off[bidx];
+    for (uint32_t p = 0; p < F.num_passes; p++) {
+      const uint32_t section = F.section_base + p * F.num_groups + g;
+      const uint32_t* base = list_base(B, section);
+      const uint32_t* ow = base + kListCap + seq * 3;
+      const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2), o3 = min(__ldg(ow + 3), kListCap);
+      for (uint32_t i = o0 + threadIdx.x; i < o3; i += blockDim.x) {
+        const uint32_t e = __ldg(base + i);
+        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);  // entries come as Y, X, B
+        const uint32_t cpos = e & 0xffffu;
+        if (cpos < dq.num_coeffs) ip[c][place(cpos)] += list_value(B, section, i, e);
+      }
+      __syncthreads();
+    }
+    for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
+      const size_t o = place(k);
       float vx, vy, vb;
-      dq.get(k, vx, vy, vb);
-      int vf = wide ? int(k) / C : int(k) % R;
-      int hf = wide ? int(k) % C : int(k) / R;
-      size_t o = px0 + size_t(vf) * F.plane_stride + hf;
+      dq.get_q(k, ip[0][o], ip[1][o], ip[2][o], vx, vy, vb);
       planes[0][o] = vx;
       planes[1][o] = vy;
       planes[2][o] = vb;
@@ -1633,7 +1729,8 @@ __device__ __forceinline__ void transposeN(float* v, uint32_t r, uint32_t gmask)
 }
 
 struct RegBlockCtx {
-  const int32_t* coeffs;  // group coefficient base (channel 0) + block offset
+  const int32_t* coeffs;  // the varblock's coefficient tile in shared memory: channel c at coeffs + c * cstride
+  uint32_t cstride;
   const float* mat;       // dequant matrix of the block's table (channel 0)
   float* plane;           // plane set base (channel 0) + pixel offset of the block
   const float* lf;        // LF plane set base handled by caller
@@ -1653,8 +1750,8 @@ __device__ __forceinline__ void reg_dct_block(const RegBlockCtx& X, const float*
   for (int c = 0; c < 3; c++) {
     float w[L];
     {
-      const int4* qc = reinterpret_cast<const int4*>(X.coeffs + size_t(c) * kGroupCoeffs + r * L);
-      const int4* qy = reinterpret_cast<const int4*>(X.coeffs + kGroupCoeffs + r * L);
+      const int4* qc = reinterpret_cast<const int4*>(X.coeffs + c * X.cstride + r * L);
+      const int4* qy = reinterpret_cast<const int4*>(X.coeffs + X.cstride + r * L);
       const float4* mc = reinterpret_cast<const float4*>(X.mat + size_t(c) * X.num_coeffs + r * L);
       const float4* my = reinterpret_cast<const float4*>(X.mat + X.num_coeffs + r * L);
       const float sc = c == 0 ? X.sx : (c == 1 ? X.sy : X.sb);
@@ -1742,8 +1839,17 @@ __device__ __forceinline__ int reg_kind(int t) {
   }
 }
 
+// Shared memory for the coefficient tiles of the lane groups of one CTA: every class of a KIND needs 32 x 8 lanes x 3 x NC
+// words with NC = 64 / 128 / 256 coefficients per channel (the 16- and 32-lane classes hold 2x / 4x the coefficients in
+// half / a quarter of the groups).
+template <int KIND>
+constexpr size_t small_tile_bytes() {
+  return size_t(kSmallThreads / 8) * 3 * (KIND == 0 ? 64 : (KIND == 1 ? 128 : 256)) * sizeof(int32_t);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small(const BatchDev B) {
+  extern __shared__ __align__(16) int32_t s_tiles[];
   __shared__ uint16_t s_list[1024];
   __shared__ uint32_t s_cnt[28], s_start[28], s_fill[28];
   const uint32_t stream = blockIdx.x;
@@ -1780,19 +1886,18 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
   }
   __syncthreads();
   const uint32_t begin8 = 0, begin16 = s_start[4], begin32 = s_start[5], end_all = s_start[5] + s_cnt[5];
-  const int32_t* group_coeffs = B.coeffs + (F.coeff_group_base + g) * (3ull * kGroupCoeffs);
   const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
   const int8_t* ytob = reinterpret_cast<const int8_t*>(B.blob + F.ytob_off);
   const uint32_t* block_off = B.block_off + F.block_base;
   const float bias0 = F.quant_biases[0], bias1 = F.quant_biases[1], bias2 = F.quant_biases[2], bias3 = F.quant_biases[3];
 
-  auto setup_ctx = [&](uint32_t e, RegBlockCtx& X, const float* (&lfp)[3], int& t) {
+  auto setup_ctx = [&](uint32_t e, RegBlockCtx& X, const float* (&lfp)[3], int& t, uint32_t& seq) {
     const uint32_t bx = e & 31, by = e >> 5;
     const size_t bidx = size_t(by0 + by) * F.xb + bx0 + bx;
     t = tmap[bidx] & 127;
     const int qt = c_qtable[t];
-    X.coeffs = group_coeffs + block_off[bidx];
+    seq = block_off[bidx];
     X.mat = F.dequant_off[qt] >= 0 ? reinterpret_cast<const float*>(B.blob + F.dequant_off[qt]) : B.dequant_default + B.dequant_default_off[qt];
     X.num_coeffs = uint32_t(c_cov_x[t]) * c_cov_y[t] * 64;
     const size_t cidx = size_t((by0 + by) >> 3) * F.cxb + ((bx0 + bx) >> 3);
@@ -1820,7 +1925,13 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       RegBlockCtx X;
       const float* lfp[3];
       int t;
-      setup_ctx(s_list[begin8 + (valid ? li : 0)], X, lfp, t);
+      uint32_t seq;
+      setup_ctx(s_list[begin8 + (valid ? li : 0)], X, lfp, t, seq);
+      constexpr uint32_t NC = KIND == 0 ? 64 : (KIND == 1 ? 128 : 256);
+      int32_t* tile = s_tiles + (threadIdx.x >> 3) * 3 * NC;
+      gather_block_tile(B, F, g, seq, tile, NC, r, 8, gmask, valid);
+      X.coeffs = tile;
+      X.cstride = NC;
       if constexpr (KIND == 1) {
         if (t == 6) reg_dct_block<8, 16, true>(X, lfp, F.xb, r, gmask, valid);
         else reg_dct_block<8, 16, false>(X, lfp, F.xb, r, gmask, valid);
@@ -1837,7 +1948,7 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
           float m[3][8];
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            const int4* qp = reinterpret_cast<const int4*>(X.coeffs + size_t(c) * kGroupCoeffs + r * 8);
+            const int4* qp = reinterpret_cast<const int4*>(X.coeffs + c * X.cstride + r * 8);
             const int4 a = qp[0], b = qp[1];
             q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
             q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
@@ -1933,7 +2044,15 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       RegBlockCtx X;
       const float* lfp[3];
       int t;
-      setup_ctx(s_list[begin16 + (valid ? li : 0)], X, lfp, t);
+      uint32_t seq;
+      setup_ctx(s_list[begin16 + (valid ? li : 0)], X, lfp, t, seq);
+      constexpr uint32_t NC = KIND == 1 ? 256 : 512;
+      if constexpr (KIND >= 1) {
+        int32_t* tile = s_tiles + (threadIdx.x >> 4) * 3 * NC;
+        gather_block_tile(B, F, g, seq, tile, NC, r, 16, gmask, valid);
+        X.coeffs = tile;
+        X.cstride = NC;
+      }
       if constexpr (KIND == 1) {
         reg_dct_block<16, 16, true>(X, lfp, F.xb, r, gmask, valid);
       } else if constexpr (KIND == 2) {
@@ -1953,8 +2072,15 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       RegBlockCtx X;
       const float* lfp[3];
       int t;
-      setup_ctx(s_list[begin32 + (valid ? li : 0)], X, lfp, t);
-      if constexpr (KIND == 2) reg_dct_block<32, 32, true>(X, lfp, F.xb, r, 0xffffffffu, valid);
+      uint32_t seq;
+      setup_ctx(s_list[begin32 + (valid ? li : 0)], X, lfp, t, seq);
+      if constexpr (KIND == 2) {
+        int32_t* tile = s_tiles + (threadIdx.x >> 5) * 3 * 1024;
+        gather_block_tile(B, F, g, seq, tile, 1024, r, 32, 0xffffffffu, valid);
+        X.coeffs = tile;
+        X.cstride = 1024;
+        reg_dct_block<32, 32, true>(X, lfp, F.xb, r, 0xffffffffu, valid);
+      }
     }
   }
 }
@@ -2948,8 +3074,10 @@ cudaError_t configure_kernels() {
   if ((e = configure_filters<true, 1>()) != cudaSuccess) return e;
   if ((e = configure_filters<true, 2>()) != cudaSuccess) return e;
   if ((e = configure_filters<true, 3>()) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(kIdctWarps * 3 * kWarpBuf * sizeof(float)));
+  if ((e = cudaFuncSetAttribute(k_idct_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<0>()))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_idct_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<1>()))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_idct_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<2>()))) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLargeSmemBytes));
 }
 
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
@@ -2963,13 +3091,13 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
     if (ev) cudaEventRecord(ev[i], stream);
   };
   mark(0);
-  cudaMemsetAsync(B.coeffs, 0, coeff_bytes, stream);
+  (void)coeff_bytes;  // no dense coefficient array any more: nothing to clear
   mark(1);
+  k_block_plan<<<(B.num_streams + 3) / 4, 128, 0, stream>>>(B);
+  launches++;
   if (B.num_lean) {
     // Persistent lanes, scheduled per frame by the host (batch.cc schedule_lean): S lanes per warp, lean_ctas CTAs.
     cudaMemsetAsync(B.queue, 0, sizeof(uint32_t) * B.num_frames, stream);
-    k_block_plan<<<(B.num_lean + 3) / 4, 128, 0, stream>>>(B);
-    launches++;
     const uint32_t S = lean_S, grid = lean_ctas;
     const int smem = lean_ctx_smem ? int(kLeanCtxSmem) : 0;
 #define JXG_LEAN(SV, KV, CV) k_entropy_lean<SV, KV, CV><<<grid, 128, smem, stream>>>(B)
@@ -3008,11 +3136,11 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
-  k_idct_small<0><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
-  k_idct_small<1><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
-  if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, 0, stream>>>(B);
+  k_idct_small<0><<<B.num_streams, kSmallThreads, small_tile_bytes<0>(), stream>>>(B);
+  k_idct_small<1><<<B.num_streams, kSmallThreads, small_tile_bytes<1>(), stream>>>(B);
+  if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, small_tile_bytes<2>(), stream>>>(B);
   launches += B.reg_idct32 ? 3 : 2;
-  k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kIdctWarps * 3 * kWarpBuf * sizeof(float), stream>>>(B);
+  k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kLargeSmemBytes, stream>>>(B);
   launches++;
   mark(3);
   if (debug_stop == 2) return launches;
@@ -3058,6 +3186,38 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(8);
   if (final_planes) *final_planes = cur;
   return launches;
+}
+
+// Parity tap: the coefficient lists of one frame expanded into the reference's dense decode-order layout
+// [groups][3][65536] (group.rs:53-55), all passes added up. One CTA per group; `dense` must be zeroed by the caller.
+__global__ void __launch_bounds__(256) k_expand_coeffs(const BatchDev B, uint32_t frame, int32_t* dense) {
+  const FrameDev& F = B.frames[frame];
+  const uint32_t g = blockIdx.x, gsid = F.first_stream + g;
+  const uint32_t nblk = B.nblk[gsid];
+  if (nblk == 0xffffffffu) return;
+  const uint4* desc = B.desc + size_t(gsid) * 1024;
+  int32_t* out = dense + size_t(g) * 3 * kGroupCoeffs;
+  for (uint32_t p = 0; p < F.num_passes; p++) {
+    const uint32_t section = F.section_base + p * F.num_groups + g;
+    const uint32_t* base = list_base(B, section);
+    const uint32_t* ow = base + kListCap;
+    for (uint32_t bi = threadIdx.x >> 5; bi < nblk; bi += blockDim.x >> 5) {  // one warp per varblock
+      const uint4 d = desc[bi];
+      const uint32_t nc = ((d.x >> 10) & 63) * ((d.x >> 16) & 63) * 64;
+      const uint32_t o0 = ow[bi * 3], o1 = ow[bi * 3 + 1], o2 = ow[bi * 3 + 2], o3 = min(ow[bi * 3 + 3], kListCap);
+      for (uint32_t i = o0 + (threadIdx.x & 31); i < o3; i += 32) {
+        const uint32_t e = base[i];
+        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
+        const uint32_t pos = e & 0xffffu;
+        if (pos < nc) out[c * kGroupCoeffs + d.z + pos] += list_value(B, section, i, e);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+void launch_expand_coeffs(const BatchDev& B, uint32_t frame, uint32_t num_groups, int32_t* dense, cudaStream_t stream) {
+  k_expand_coeffs<<<num_groups, 256, 0, stream>>>(B, frame, dense);
 }
 
 void launch_orient(const void* src, size_t src_stride, void* dst, size_t dst_stride, uint32_t w, uint32_t h, uint32_t bpp,

@@ -15,6 +15,8 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
 constexpr int kFusedTileW = 64, kFusedTileH = 32;
 int launch_filter_range(const BatchDev& B, const uint32_t* fused_prefix, uint32_t tile_begin, uint32_t tile_count,
                         uint32_t filter_cfg_mask, cudaStream_t stream);
+// Parity tap (jxg_batch_read_coeffs): lists of one frame -> dense [groups][3][65536] i32 (zeroed by the caller).
+void launch_expand_coeffs(const BatchDev& B, uint32_t frame, uint32_t num_groups, int32_t* dense, cudaStream_t stream);
 // Orientation post-pass of one frame: coded w x h image at `src` (row stride src_stride) -> display orientation at `dst`.
 void launch_orient(const void* src, size_t src_stride, void* dst, size_t dst_stride, uint32_t w, uint32_t h, uint32_t bpp,
                    uint32_t orientation, cudaStream_t stream);
