@@ -1,19 +1,16 @@
 #!/usr/bin/env bash
-# Short GPU session: a subset of the GPU tests, one bench line, the end-to-end timeline and sweeps of the entropy
-# schedule knobs. Usage: gpurun --timeout 900 -- 'bash tools/gpu_quick.sh <tag>'
+# Short GPU session: GPU tests, stage times, one bench line, the end-to-end timeline with the host-side phase trace of
+# jxg_batch_run. Usage: gpurun --timeout 1200 -- 'bash tools/gpu_quick.sh <tag>'   (TESTS="..." selects test files)
 set -u
 TAG="${1:-quick}"
 OUT="gpurun_out/quick_${TAG}"
 mkdir -p "$OUT"
-step() { local name="$1" limit="$2"; shift 2; echo "=== $name ($(date +%T))" | tee -a "$OUT/session.log"; timeout "$limit" "$@" > "$OUT/$name.log" 2>&1; echo "    exit $?" | tee -a "$OUT/session.log"; tail -n 3 "$OUT/$name.log" >> "$OUT/session.log"; }
-step tests 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_synthetic.py tests/test_gpu_pipeline.py -m gpu -q -x -k "not config4"
-step stages_default 200 python tools/stage_times.py 64
-for solo in 0.5 0.75 1.1; do
-  step "stages_solo_${solo}" 200 env JXG_ENTROPY_SOLO=$solo python tools/stage_times.py 64
-done
-step stages_solo_off_perlane1 200 env JXG_ENTROPY_SOLO=1.1 JXG_ENTROPY_DUO=1.1 JXG_ENTROPY_PER_LANE=1.0 python tools/stage_times.py 64
-step stages_perlane_2.5 200 env JXG_ENTROPY_PER_LANE=2.5 python tools/stage_times.py 64
-step stages_S8 200 env JXG_ENTROPY_S=8 python tools/stage_times.py 64
+step() { local name="$1" limit="$2"; shift 2; echo "=== $name ($(date +%T))" | tee -a "$OUT/session.log"; timeout "$limit" "$@" > "$OUT/$name.log" 2>&1; echo "    exit $?" | tee -a "$OUT/session.log"; tail -n 4 "$OUT/$name.log" >> "$OUT/session.log"; }
+step tests 900 python -m pytest ${TESTS:-tests} -m gpu -q -x --durations=5
+step stages 200 python tools/stage_times.py 64
 step bench 400 python bench.py --steps 8 --warmup 4
-step e2e 300 python tools/e2e_profile4.py 64 8 3
+step e2e 300 env JXG_TRACE_RUN=1 python tools/e2e_profile4.py 64 6 3
+if [[ "${LAUNCHES:-0}" == 1 ]]; then
+  step launches 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file "$OUT/launches.csv" python tools/stage_times.py 64
+fi
 echo "=== done ($(date +%T))" | tee -a "$OUT/session.log"
