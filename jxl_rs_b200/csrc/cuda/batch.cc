@@ -70,6 +70,13 @@ struct Batch {
   DevBuf &d_blob, &d_frames, &d_sections, &d_streams, &d_streams_lean, &d_lean_cta, &d_streams_fast, &d_streams_slow, &d_nz_base, &d_tiles, &d_ftiles, &d_coeffs, &d_block_off, &d_nz, &d_planes_a,
       &d_planes_b, &d_status, &d_out;
   bool uploaded = false;
+  // byte offsets of the batch tables inside the blob (they ride on the one pinned H2D copy: a cudaMemcpyAsync from
+  // pageable std::vector storage blocks the calling thread until earlier device work drains — 100+ ms with other
+  // batches in flight, profiles/r02c_e2e_trace.log)
+  struct {
+    uint64_t frames = 0, sections = 0, streams = 0, lean_cta = 0, lean_warp = 0, streams_lean = 0, streams_fast = 0, streams_slow = 0,
+             nz_base = 0, tiles = 0, ftiles = 0;
+  } tab;
   const float* final_planes = nullptr;
   int32_t* status_host = nullptr;  // pinned (context-owned): a D2H copy into pageable memory would block jxg_batch_run
   size_t status_n = 0;
@@ -591,29 +598,29 @@ static BatchDev make_batch_dev(Batch* b) {
   BatchDev B;
   memset(&B, 0, sizeof(B));
   B.blob = static_cast<const uint8_t*>(b->d_blob.p);
-  B.frames = static_cast<const FrameDev*>(b->d_frames.p);
-  B.sections = static_cast<const SectionDev*>(b->d_sections.p);
-  B.streams = static_cast<const StreamDev*>(b->d_streams.p);
+  auto tab = [&](uint64_t off) { return static_cast<const uint8_t*>(b->d_blob.p) + off; };
+  B.frames = reinterpret_cast<const FrameDev*>(tab(b->tab.frames));
+  B.sections = reinterpret_cast<const SectionDev*>(tab(b->tab.sections));
+  B.streams = reinterpret_cast<const StreamDev*>(tab(b->tab.streams));
   B.num_frames = uint32_t(b->frames.size());
   B.num_streams = uint32_t(b->streams.size());
-  B.streams_lean = static_cast<const StreamDev*>(b->d_streams_lean.p);
+  B.streams_lean = reinterpret_cast<const StreamDev*>(tab(b->tab.streams_lean));
   B.num_lean = uint32_t(b->streams_lean.size());
-  B.streams_fast = static_cast<const StreamDev*>(b->d_streams_fast.p);
-  B.streams_slow = static_cast<const StreamDev*>(b->d_streams_slow.p);
+  B.streams_fast = reinterpret_cast<const StreamDev*>(tab(b->tab.streams_fast));
+  B.streams_slow = reinterpret_cast<const StreamDev*>(tab(b->tab.streams_slow));
   B.num_fast = uint32_t(b->streams_fast.size());
   B.num_slow = uint32_t(b->streams_slow.size());
   B.reg_idct32 = (getenv("JXG_REG_IDCT32") && atoi(getenv("JXG_REG_IDCT32"))) ? 1u : 0u;
   B.nzlist = static_cast<uint32_t*>(b->d_coeffs.p);  // the pool that held the dense coefficients now holds the lists
-  B.big = static_cast<BigTable*>(b->ctx->d_big.p);
   B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
   B.nz = static_cast<uint8_t*>(b->d_nz.p);
-  B.nz_base = static_cast<uint64_t*>(b->d_nz_base.p);
+  B.nz_base = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(tab(b->tab.nz_base)));
   B.planes_a = static_cast<float*>(b->d_planes_a.p);
   B.planes_b = static_cast<float*>(b->d_planes_b.p);
   B.status = static_cast<int32_t*>(b->d_status.p);
   B.queue = reinterpret_cast<uint32_t*>(B.status + b->streams.size());
-  B.lean_cta_first = static_cast<const uint32_t*>(b->d_lean_cta.p);
-  B.lean_warp = static_cast<const uint2*>(b->ctx->d_lean_warp.p);
+  B.lean_cta_first = reinterpret_cast<const uint32_t*>(tab(b->tab.lean_cta));
+  B.lean_warp = reinterpret_cast<const uint2*>(tab(b->tab.lean_warp));
   B.desc = static_cast<uint4*>(b->ctx->d_lean_desc.p);
   B.nblk = static_cast<uint32_t*>(b->ctx->d_lean_nblk.p);
   B.dequant_default = static_cast<const float*>(b->ctx->dequant_default.p);
@@ -625,11 +632,12 @@ static BatchDev make_batch_dev(Batch* b) {
 
 static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
   const BatchDev B = make_batch_dev(b);
+  auto tab = [&](uint64_t off) { return static_cast<const uint8_t*>(b->d_blob.p) + off; };
   size_t coeff_bytes = 0;
   cudaEvent_t* ev = b->profile ? b->stage_ev : nullptr;
-  b->launches = uint64_t(launch_pipeline(B, static_cast<const uint32_t*>(b->d_tiles.p), b->tile_prefix.back(), b->max_epf,
+  b->launches = uint64_t(launch_pipeline(B, reinterpret_cast<const uint32_t*>(tab(b->tab.tiles)), b->tile_prefix.back(), b->max_epf,
                                          b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
-                                         static_cast<const uint32_t*>(b->d_ftiles.p), b->fused_prefix.back(),
+                                         reinterpret_cast<const uint32_t*>(tab(b->tab.ftiles)), b->fused_prefix.back(),
                                          b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas,
                                          b->lean_ctx_smem && !(getenv("JXG_LEAN_CTX_SMEM") && atoi(getenv("JXG_LEAN_CTX_SMEM")) == 0)));
   if (b->debug_stop == 0) {
@@ -638,7 +646,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
     Context* cx = b->ctx;
     const uint32_t nf = uint32_t(b->frames.size());
     const uint32_t nr = copy_to_host ? std::min<uint32_t>(Context::kMaxRanges, nf) : 1;
-    const uint32_t* fp = static_cast<const uint32_t*>(b->d_ftiles.p);
+    const uint32_t* fp = reinterpret_cast<const uint32_t*>(tab(b->tab.ftiles));
     if (ev) {
       for (int i = 4; i <= 6; i++) cudaEventRecord(ev[i], s);
     }
@@ -712,10 +720,8 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   b->h2d = b->d2h = 0;
   schedule_lean(b);
   // device allocations
-  if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
   // one coefficient list per HF section (pass x group), worst-case capacity (every coefficient non-zero)
   if (int r = b->d_coeffs.ensure(b->sections.size() * size_t(kListStride) * 4)) return r;
-  if (int r = b->ctx->d_big.ensure(std::max<size_t>(b->sections.size() * sizeof(BigTable), 16))) return r;
   if (int r = b->d_block_off.ensure(b->total_blocks * 4)) return r;
   if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
   if (int r = b->d_planes_a.ensure(b->total_plane_floats * 4)) return r;
@@ -739,6 +745,27 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   }
   b->status_host = b->ctx->status_host;
   memset(b->status_host, 0, b->status_n * 4);
+  {  // batch tables behind the frames' data in the pinned blob: they travel with the one H2D copy below
+    auto put = [&](const void* p, size_t bytes, uint64_t& off) {
+      const int64_t o = b->blob.append(bytes ? p : nullptr, bytes, 16, 16);
+      if (o < 0) return false;
+      off = uint64_t(o);
+      return true;
+    };
+    bool ok = put(b->frames.data(), b->frames.size() * sizeof(FrameDev), b->tab.frames) &&
+              put(b->sections.data(), b->sections.size() * sizeof(SectionDev), b->tab.sections) &&
+              put(b->streams.data(), b->streams.size() * sizeof(StreamDev), b->tab.streams) &&
+              put(b->lean_cta_first.data(), b->lean_cta_first.size() * 4, b->tab.lean_cta) &&
+              put(b->lean_warps.data(), b->lean_warps.size() * sizeof(uint2), b->tab.lean_warp) &&
+              put(b->streams_lean.data(), b->streams_lean.size() * sizeof(StreamDev), b->tab.streams_lean) &&
+              put(b->streams_fast.data(), b->streams_fast.size() * sizeof(StreamDev), b->tab.streams_fast) &&
+              put(b->streams_slow.data(), b->streams_slow.size() * sizeof(StreamDev), b->tab.streams_slow) &&
+              put(b->nz_base.data(), b->nz_base.size() * 8, b->tab.nz_base) &&
+              put(b->tile_prefix.data(), b->tile_prefix.size() * 4, b->tab.tiles) &&
+              put(b->fused_prefix.data(), b->fused_prefix.size() * 4, b->tab.ftiles);
+    if (!ok) return set_error(JXG_ERR_CUDA, "pinned staging allocation failed");
+  }
+  if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
   trace.mark("alloc");
   b->blob.flush();
   trace.mark("flush");
@@ -746,17 +773,6 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
   trace.mark("blob_h2d");
   b->h2d += b->blob.size;
-  if (int r = upload(b->d_frames, b->frames, s, &b->h2d)) return r;
-  if (int r = upload(b->d_sections, b->sections, s, &b->h2d)) return r;
-  if (int r = upload(b->d_streams, b->streams, s, &b->h2d)) return r;
-  if (int r = upload(b->d_lean_cta, b->lean_cta_first, s, &b->h2d)) return r;
-  if (int r = upload(b->ctx->d_lean_warp, b->lean_warps, s, &b->h2d)) return r;
-  if (int r = upload(b->d_streams_lean, b->streams_lean, s, &b->h2d)) return r;
-  if (int r = upload(b->d_streams_fast, b->streams_fast, s, &b->h2d)) return r;
-  if (int r = upload(b->d_streams_slow, b->streams_slow, s, &b->h2d)) return r;
-  if (int r = upload(b->d_nz_base, b->nz_base, s, &b->h2d)) return r;
-  if (int r = upload(b->d_tiles, b->tile_prefix, s, &b->h2d)) return r;
-  if (int r = upload(b->d_ftiles, b->fused_prefix, s, &b->h2d)) return r;
   b->uploaded = true;
   trace.mark("uploads");
   if (int r = launch(b, s, true)) return r;

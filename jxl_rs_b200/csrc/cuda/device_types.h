@@ -13,23 +13,20 @@ constexpr uint32_t kGroupCoeffs = 65536;  // per channel per group (group.rs:53-
 
 // Coefficients travel from the entropy kernels to the transform kernels as one list of NON-ZERO entries per
 // (pass, group) stream, in decode order (varblocks in raster order, channels Y, X, B inside a varblock, coefficient
-// order inside a channel): entry = position in the varblock's storage layout (16 bits) | value << 16 (i16). A value
-// outside i16 leaves the marker 0x8000 in the entry and goes to the list's side table. Behind the entries sit the
-// offset words: offw[seq * 3 + ci] = index of the first entry of channel ci (0 = Y, 1 = X, 2 = B) of the seq-th
-// varblock, offw[nblk * 3] = total. The dense [groups][3][65536] i32 array of round 1 (12 B/px written once, read
-// once, >= 90 % zeros, plus a memset) is gone; a list is written and read sequentially.
+// order inside a channel). Entry of a varblock with 2^n coefficients per channel (n = 6 .. 16):
+//     position in the storage layout (low n bits) | value << n (two's complement in the remaining 32 - n bits),
+// i.e. +-2^25 for an 8x8 block down to +-2^15 for DCT256X256. A value outside that range is refused
+// (JXG_ERR_UNSUPPORTED for the stream): quantised coefficients of that size do not occur in real streams, and refusing
+// keeps both sides branch-free. Behind the entries (and 4 words of padding: the writer stores every decoded coefficient
+// at the cursor and only advances it for non-zero ones) sit the offset words: offw[seq * 3 + ci] = index of the first
+// entry of channel ci (0 = Y, 1 = X, 2 = B) of the seq-th varblock, offw[nblk * 3] = total. The dense
+// [groups][3][65536] i32 array of round 1 (12 B/px written once, read once, >= 90 % zeros, plus a memset) is gone;
+// a list is written and read sequentially.
 constexpr uint32_t kListCap = 3 * kGroupCoeffs;        // entries: every coefficient of the group non-zero
+constexpr uint32_t kListPad = 4;
+constexpr uint32_t kOffBase = kListCap + kListPad;     // first offset word
 constexpr uint32_t kOffWords = 3 * 1024 + 4;           // offsets of <= 1024 varblocks x 3 channels + end, 16-byte multiple
-constexpr uint32_t kListStride = kListCap + kOffWords;  // u32 words per list
-constexpr uint32_t kBigCap = 255;
-struct BigTable {  // values beyond i16, in entry order (2048 bytes per list)
-  uint32_t count, pad;
-  struct {
-    uint32_t entry;
-    int32_t value;
-  } e[kBigCap];
-};
-constexpr uint32_t kBigMarker = 0x8000u;
+constexpr uint32_t kListStride = kOffBase + kOffWords;  // u32 words per list
 
 struct PassDev {
   uint32_t shift, use_prefix, log_alpha_size, num_clusters;
@@ -111,7 +108,6 @@ struct BatchDev {
   uint32_t num_frames, num_streams, num_lean, num_fast, num_slow;
   uint32_t reg_idct32;  // 1: rows of 32 coefficients also go through the register path (experiment knob)
   uint32_t* nzlist;     // [sections][kListStride]: list of section (pass * num_groups + group) of a frame, see above
-  BigTable* big;        // [sections]
   uint32_t* block_off;  // per 8x8 block: ordinal (raster order) of the varblock starting there within its group
   uint8_t* nz;          // [streams][passes][3][1024]
   uint64_t* nz_base;    // per stream offset into nz (bytes)

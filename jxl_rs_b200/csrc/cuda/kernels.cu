@@ -167,45 +167,58 @@ __device__ __forceinline__ int32_t unpack_signed(uint32_t u) { return int32_t((u
 
 // One coefficient list (device_types.h): base of the entries, offset words behind them.
 __device__ __forceinline__ uint32_t* list_base(const BatchDev& B, uint32_t section) { return B.nzlist + size_t(section) * kListStride; }
-// Entry of a non-zero coefficient; values beyond i16 go to the side table (false: table full).
-__device__ __forceinline__ bool list_put(const BatchDev& B, uint32_t section, uint32_t* base, uint32_t& n, uint32_t pos, int32_t v) {
-  uint32_t e = pos | (uint32_t(v) << 16);
-  bool ok = true;
-  if (v < -32767 || v > 32767) {
-    BigTable& T = B.big[section];
-    const uint32_t j = T.count;
-    if (j < kBigCap) {
-      T.e[j].entry = n;
-      T.e[j].value = v;
-      T.count = j + 1;
-    } else {
-      ok = false;
-    }
-    e = pos | (kBigMarker << 16);
-  }
-  if (n < kListCap) base[n++] = e;
-  return ok;
+// Writer side: the entry of coefficient value v at position pos of a varblock with 2^lnc coefficients per channel is
+// stored at the cursor whatever v is; the cursor only moves for v != 0 (branch-free; a zero is overwritten by the next
+// entry or stays behind the end of the channel). `ovf` collects values that do not fit the entry.
+__device__ __forceinline__ void list_put(uint32_t* base, uint32_t& n, uint32_t pos, int32_t v, uint32_t lnc, uint32_t& ovf) {
+  const int32_t sv = int32_t(uint32_t(v) << lnc);
+  ovf |= uint32_t((sv >> lnc) ^ v);
+  base[n] = pos | uint32_t(sv);
+  n += v != 0 ? 1u : 0u;
 }
-// Value of entry i (reader side).
-__device__ __forceinline__ int32_t list_value(const BatchDev& B, uint32_t section, uint32_t i, uint32_t e) {
-  const uint32_t hi = e >> 16;
-  if (hi != kBigMarker) return int32_t(int16_t(hi));
-  const BigTable& T = B.big[section];
-  uint32_t lo = 0, n = min(T.count, kBigCap);
-  while (lo < n) {  // entries are in increasing order
-    const uint32_t mid = (lo + n) >> 1;
-    if (T.e[mid].entry < i) lo = mid + 1;
-    else n = mid;
-  }
-  return (lo < min(T.count, kBigCap) && T.e[lo].entry == i) ? T.e[lo].value : 0;
+__device__ __forceinline__ uint32_t entry_pos(uint32_t e, uint32_t lnc) { return e & ((1u << lnc) - 1u); }
+__device__ __forceinline__ int32_t entry_value(uint32_t e, uint32_t lnc) { return int32_t(e) >> lnc; }
+
+// ---- bulk asynchronous copies (TMA engine, 1-D form) + mbarrier: global -> shared without passing through registers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// One thread: announce `bytes` of asynchronous traffic on the barrier, then start the copy that will deliver them.
+// src, dst and bytes are multiples of 16.
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+// Prefix of a stream's pass-0 coefficient list staged in shared memory by bulk copies (k_idct_small): the offset words
+// of all varblocks and the first `staged` entries; entries beyond that, and other passes, are read from global memory.
+struct ListStage {
+  const uint32_t* off;  // nullptr: nothing staged
+  const uint32_t* ent;
+  uint32_t staged;
+};
 
 // Builds the dense coefficient tile of one varblock in shared memory from the coefficient lists: `nl` lanes (rank r,
 // all lanes of `gmask` call this together) zero tile[3][NC], then add the entries of every pass (the sum of the passes
 // is the coefficient, group.rs:556-567). Entries come in the order Y, X, B; the tile is indexed X, Y, B like the
-// dequant tables. Positions beyond NC (corrupt stream) are dropped.
+// dequant tables. NC is the varblock's own coefficient count, so every decoded position lies inside the tile.
 __device__ __forceinline__ void gather_block_tile(const BatchDev& B, const FrameDev& F, uint32_t g, uint32_t seq, int32_t* tile,
-                                                  uint32_t NC, uint32_t r, uint32_t nl, uint32_t gmask, bool valid) {
+                                                  uint32_t NC, uint32_t r, uint32_t nl, uint32_t gmask, bool valid,
+                                                  const ListStage& st = ListStage{nullptr, nullptr, 0}) {
+  const uint32_t lnc = 31 - __clz(NC);  // NC = the varblock's coefficients per channel (a power of two)
   int4* t4 = reinterpret_cast<int4*>(tile);
   __syncwarp(gmask);  // the previous varblock of this lane group has been read completely
   for (uint32_t i = r; i < 3 * NC / 4; i += nl) t4[i] = make_int4(0, 0, 0, 0);
@@ -214,15 +227,16 @@ __device__ __forceinline__ void gather_block_tile(const BatchDev& B, const Frame
     const uint32_t section = F.section_base + p * F.num_groups + g;
     const uint32_t* base = list_base(B, section);
     if (valid) {
-      const uint32_t* ow = base + kListCap + seq * 3;
-      const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
-      uint32_t o3 = __ldg(ow + 3);
+      const bool from_stage = p == 0 && st.off != nullptr;
+      const uint32_t* ow = from_stage ? st.off + seq * 3 : base + kOffBase + seq * 3;
+      const uint32_t o0 = ow[0], o1 = ow[1], o2 = ow[2];
+      uint32_t o3 = ow[3];
       o3 = min(o3, kListCap);
+      const uint32_t staged = from_stage ? st.staged : 0u;
       for (uint32_t i = o0 + r; i < o3; i += nl) {
-        const uint32_t e = __ldg(base + i);
+        const uint32_t e = i < staged ? st.ent[i] : __ldg(base + i);
         const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
-        const uint32_t pos = e & 0xffffu;
-        if (pos < NC) tile[c * NC + pos] += list_value(B, section, i, e);
+        tile[c * NC + entry_pos(e, lnc)] += entry_value(e, lnc);
       }
     }
     if (p + 1 < F.num_passes) __syncwarp(gmask);
@@ -237,8 +251,8 @@ struct BlockInfo {
 // One varblock, one pass: the three channels in Y, X, B order (group.rs:509-577).
 __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameDev& F, const PassDev& P,
                                                  const PassTables& T, PassState& s, const BlockInfo& bi,
-                                                 uint8_t* nz_pass /* [3][1024] */, uint32_t section, uint32_t* list, uint32_t& nlist,
-                                                 uint32_t bseq) {
+                                                 uint8_t* nz_pass /* [3][1024] */, uint32_t* list, uint32_t& nlist, uint32_t bseq,
+                                                 uint32_t& ovf) {
   const uint32_t num_ac_contexts = F.num_block_contexts * (37 + 458);
   const uint32_t context_offset = s.hist_idx * num_ac_contexts;
   const uint8_t* bcm = B.blob + F.block_ctx_map_off;
@@ -268,7 +282,7 @@ __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameD
     const uint32_t* order = P.custom_orders
                                 ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[bi.shape * 3 + c]
                                 : B.natural_orders + B.natural_order_off[bi.shape];
-    list[kListCap + bseq * 3 + ci] = nlist;  // first entry of channel ci (Y, X, B) of this varblock in this pass
+    list[kOffBase + bseq * 3 + ci] = nlist;  // first entry of channel ci (Y, X, B) of this varblock in this pass
     const uint32_t lnb = bi.log_num_blocks, rnd = bi.num_blocks - 1;
 #pragma unroll 1
     for (uint32_t k = bi.num_blocks; k < bi.num_coeffs && nonzeros != 0; k++) {
@@ -277,7 +291,7 @@ __device__ __forceinline__ int decode_block_pass(const BatchDev& B, const FrameD
       int32_t coeff = int32_t(uint32_t(unpack_signed(u)) << P.shift);
       prev = coeff != 0;
       nonzeros -= prev;
-      if (coeff != 0 && !list_put(B, section, list, nlist, __ldg(order + k), coeff)) return JXG_ERR_UNSUPPORTED;
+      list_put(list, nlist, __ldg(order + k), coeff, bi.log_num_blocks + 6, ovf);
     }
     if (nonzeros != 0) return JXG_ERR_RESIDUAL_NONZEROS;
   }
@@ -337,10 +351,8 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
   // one coefficient list per pass (section = pass * num_groups + group); the transform kernels add the passes up
   PassState st[kMaxPasses];
   uint32_t nlist[kMaxPasses];
-  for (uint32_t p = 0; p < np; p++) {
-    nlist[p] = 0;
-    B.big[F.section_base + p * F.num_groups + g].count = 0;
-  }
+  for (uint32_t p = 0; p < np; p++) nlist[p] = 0;
+  uint32_t ovf = 0;
   for (uint32_t p = 0; p < np && !err; p++) err = init_pass(B, F, p, g, st[p]);
   for (uint32_t by = 0; by < gh && !err; by++) {
     for (uint32_t bx = 0; bx < gw && !err; bx++) {
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
         const PassTables T = make_tables(B, F.passes[p]);
         const uint32_t section = F.section_base + p * F.num_groups + g;
         uint32_t n = nlist[p];
-        err = decode_block_pass(B, F, F.passes[p], T, s, bi, nz + p * 3072, section, list_base(B, section), n, bseq);
+        err = decode_block_pass(B, F, F.passes[p], T, s, bi, nz + p * 3072, list_base(B, section), n, bseq, ovf);
         nlist[p] = n;
         st[p] = s;
       }
@@ -369,9 +381,10 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) k_entropy(const BatchDev B
     }
   }
   for (uint32_t p = 0; p < np && !err; p++) {
-    list_base(B, F.section_base + p * F.num_groups + g)[kListCap + bseq * 3] = nlist[p];
+    list_base(B, F.section_base + p * F.num_groups + g)[kOffBase + bseq * 3] = nlist[p];
     err = finish_pass(B, F, p, g, st[p]);
   }
+  if (!err && ovf) err = JXG_ERR_UNSUPPORTED;  // a coefficient beyond the entry width (device_types.h)
   B.status[stream] = err;
 }
 
@@ -453,7 +466,7 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0), gn = gw * gh;
   const uint32_t lsec = F.section_base + g;  // single pass: list of section `group`
   uint32_t* const list = list_base(B, lsec);
-  uint32_t nlist = 0, bseq = 0;
+  uint32_t nlist = 0, bseq = 0, ovf = 0;
   uint8_t* const nz = B.nz + B.nz_base[gsid];
   const uint8_t* const tmap = B.blob + F.transform_off;
   const int32_t* const rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
@@ -475,7 +488,6 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
   uint32_t ans_state = 0x130000u, context_offset = 0;
   if (!done) {
     const SectionDev sec = B.sections[F.section_base + g];
-    B.big[lsec].count = 0;
     br.init(B.blob + sec.off, sec.len);
     uint32_t nb = 0;
     while ((1u << nb) < F.num_histograms) nb++;
@@ -517,8 +529,9 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
         const SectionDev sec = B.sections[F.section_base + g];
         if (br.bitpos > sec.len * 8u) err = JXG_ERR_OUT_OF_BOUNDS;
         else if (!use_prefix && ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
+        else if (ovf) err = JXG_ERR_UNSUPPORTED;  // a coefficient beyond the entry width (device_types.h)
         B.status[gsid] = err;
-        list[kListCap + bseq * 3] = nlist;
+        list[kOffBase + bseq * 3] = nlist;
         done = true;
       } else {
         const uint32_t t = raw_t & 127;
@@ -617,17 +630,13 @@ __global__ void __launch_bounds__(128, 8) k_entropy_fast(const BatchDev B) {
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
                               : B.natural_orders + B.natural_order_off[shape];
-      list[kListCap + bseq * 3 + ci] = nlist;
+      list[kOffBase + bseq * 3 + ci] = nlist;
       if (nonzeros == 0) next_channel = true;
       else phase = PH_COEF;
     } else {
       const int32_t coeff = int32_t(uint32_t(unpack_signed(value)) << shift);
+      list_put(list, nlist, __ldg(order + k), coeff, lnb + 6, ovf);
       if (coeff != 0) {
-        if (!list_put(B, lsec, list, nlist, __ldg(order + k), coeff)) {
-          B.status[gsid] = JXG_ERR_UNSUPPORTED;
-          done = true;
-          continue;
-        }
         prev = 1;
         nonzeros--;
       } else {
@@ -805,8 +814,11 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   }
   __syncthreads();
   const uint8_t* const ctxmap_g = B.blob + P.context_map_off;
-  const uint32_t ctxmap_s = uint32_t(__cvta_generic_to_shared(s_ctxmap));
-  const uint32_t nz2_s = uint32_t(__cvta_generic_to_shared(s_nz2)), fr2_s = uint32_t(__cvta_generic_to_shared(s_fr2));
+  // Shared-window addresses of the three look-up tables, made opaque so that they stay in registers: left to itself the
+  // compiler rematerialises them inside the per-symbol loop (S2R SR_CgaCtaId + LEA + adds, ~8 of the ~92 instructions).
+  uint32_t ctxmap_s = uint32_t(__cvta_generic_to_shared(s_ctxmap));
+  uint32_t nz2_s = uint32_t(__cvta_generic_to_shared(s_nz2)), fr2_s = uint32_t(__cvta_generic_to_shared(s_fr2));
+  asm volatile("" : "+r"(ctxmap_s), "+r"(nz2_s), "+r"(fr2_s));
   auto ctx_cluster = [&](uint32_t ctx) { return CTXS ? spec_lds_u8(ctxmap_s + ctx) : spec_ld_u8(ctxmap_g + ctx); };
   const uint32_t lane = threadIdx.x & 31;
   // Warp schedule written by the host (batch.cc schedule_lean): the first stream of this warp in the frame's
@@ -826,7 +838,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   uint32_t gsid = 0, nblk = 0, bi = 0;
   const uint4* desc = B.desc;
   uint32_t* list = B.nzlist;  // this stream's coefficient list (pass 0), entries written so far, its section index
-  uint32_t nlist = 0, lsec = 0;
+  uint32_t nlist = 0, ovf = 0;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(B.blob);
   uint32_t sec_bits = 0, wlimit = 0;
   uint32_t bitpos = 0, ans_state = 0x130000u, context_offset = 0;
@@ -851,10 +863,9 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
           const uint32_t lidx = F.lean_first + qpos;
           const uint32_t g = B.streams_lean[lidx].group;
           gsid = F.first_stream + g;
-          lsec = F.section_base + g;
-          list = list_base(B, lsec);
+          list = list_base(B, F.section_base + g);
           nlist = 0;
-          B.big[lsec].count = 0;
+          ovf = 0;
           desc = B.desc + size_t(gsid) * 1024;
           nblk = B.nblk[gsid];
           bi = 0;
@@ -890,8 +901,9 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
             int err = 0;
             if (bitpos > sec_bits) err = JXG_ERR_OUT_OF_BOUNDS;
             else if (ans_state != 0x130000u) err = JXG_ERR_ANS_CHECKSUM;
+            else if (ovf) err = JXG_ERR_UNSUPPORTED;  // a coefficient beyond the entry width (device_types.h)
             B.status[gsid] = err;
-            list[kListCap + nblk * 3] = nlist;  // end of the last varblock's entries
+            list[kOffBase + nblk * 3] = nlist;  // end of the last varblock's entries
           }
           qpos = atomicAdd(B.queue + fidx, 1u) + frame_lanes;
           if (qpos >= F.lean_count) {
@@ -1003,7 +1015,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
       k = num_blocks;
       order = P.custom_orders ? reinterpret_cast<const uint32_t*>(B.blob + P.order_off) + P.order_offset[shape * 3 + c]
                               : B.natural_orders + s_order_off[shape];
-      list[kListCap + (bi - 1) * 3 + ci] = nlist;  // first entry of this varblock's channel ci (Y, X, B)
+      list[kOffBase + (bi - 1) * 3 + ci] = nlist;  // first entry of this varblock's channel ci (Y, X, B)
       mode_nnz = false;
       if (nonzeros == 0) {
         need_setup = true;
@@ -1014,16 +1026,7 @@ __global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
                               uint32_t(s_fr2[(k >> lnb) & 63]) + prev);
       }
     } else {
-      if (nonzero) {  // lean streams have shift == 0 (host routing)
-        if (!list_put(B, lsec, list, nlist, __ldg(order + k), unpack_signed(value))) {
-          B.status[gsid] = JXG_ERR_UNSUPPORTED;  // more than kBigCap coefficients beyond 16 bits in one group
-          failed = true;
-          bi = nblk;
-          ci = 3;
-          need_setup = true;
-          continue;
-        }
-      }
+      list_put(list, nlist, __ldg(order + k), unpack_signed(value), lnb + 6, ovf);  // lean streams have shift == 0 (host routing)
       nonzeros -= nonzero;
       cluster = cluster_next;
       k++;
@@ -1639,17 +1642,16 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
       ip[2][o] = 0;
     }
     __syncthreads();
-    const uint32_t seq = block_off[bidx];
+    const uint32_t seq = block_off[bidx], lnc = 31 - __clz(dq.num_coeffs);
     for (uint32_t p = 0; p < F.num_passes; p++) {
       const uint32_t section = F.section_base + p * F.num_groups + g;
       const uint32_t* base = list_base(B, section);
-      const uint32_t* ow = base + kListCap + seq * 3;
+      const uint32_t* ow = base + kOffBase + seq * 3;
       const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2), o3 = min(__ldg(ow + 3), kListCap);
       for (uint32_t i = o0 + threadIdx.x; i < o3; i += blockDim.x) {
         const uint32_t e = __ldg(base + i);
         const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);  // entries come as Y, X, B
-        const uint32_t cpos = e & 0xffffu;
-        if (cpos < dq.num_coeffs) ip[c][place(cpos)] += list_value(B, section, i, e);
+        ip[c][place(entry_pos(e, lnc))] += entry_value(e, lnc);
       }
       __syncthreads();
     }
@@ -1843,8 +1845,15 @@ __device__ __forceinline__ int reg_kind(int t) {
 // words with NC = 64 / 128 / 256 coefficients per channel (the 16- and 32-lane classes hold 2x / 4x the coefficients in
 // half / a quarter of the groups).
 template <int KIND>
-constexpr size_t small_tile_bytes() {
+__host__ __device__ constexpr size_t small_tile_bytes() {
   return size_t(kSmallThreads / 8) * 3 * (KIND == 0 ? 64 : (KIND == 1 ? 128 : 256)) * sizeof(int32_t);
+}
+// Behind the tiles: the staged offset words (kOffWords) and the first kStageEntries entries of the group's list,
+// delivered by two bulk copies issued by thread 0 before the CTA sorts its varblocks.
+constexpr uint32_t kStageEntries = 8192;
+template <int KIND>
+constexpr size_t small_smem_bytes() {
+  return small_tile_bytes<KIND>() + size_t(kOffWords + kStageEntries) * sizeof(uint32_t);
 }
 
 template <int KIND>
@@ -1852,11 +1861,24 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
   extern __shared__ __align__(16) int32_t s_tiles[];
   __shared__ uint16_t s_list[1024];
   __shared__ uint32_t s_cnt[28], s_start[28], s_fill[28];
+  __shared__ __align__(8) uint64_t s_bar[2];
   const uint32_t stream = blockIdx.x;
   if (B.status[stream] != 0) return;
   const StreamDev sd = B.streams[stream];
   const FrameDev& F = B.frames[sd.frame];
   const uint32_t g = sd.group;
+  uint32_t* const s_off = reinterpret_cast<uint32_t*>(s_tiles) + small_tile_bytes<KIND>() / 4;
+  uint32_t* const s_ent = s_off + kOffWords;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    // pass-0 list of this group: offset words, and the head of the entries (whatever lies behind the last entry is
+    // copied too and never looked at)
+    const uint32_t* base = list_base(B, F.section_base + g);
+    bulk_load(s_off, base + kOffBase, kOffWords * 4, &s_bar[0]);
+    bulk_load(s_ent, base, kStageEntries * 4, &s_bar[1]);
+  }
   const uint32_t bx0 = (g % F.xg) * 32, by0 = (g / F.xg) * 32;
   const uint32_t gw = min(32u, F.xb - bx0), gh = min(32u, F.yb - by0);
   const uint8_t* tmap = B.blob + F.transform_off;
@@ -1886,6 +1908,10 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
   }
   __syncthreads();
   const uint32_t begin8 = 0, begin16 = s_start[4], begin32 = s_start[5], end_all = s_start[5] + s_cnt[5];
+  // the staged list has landed (the sort above ran while the copies were in flight)
+  mbar_wait(&s_bar[0], 0);
+  mbar_wait(&s_bar[1], 0);
+  const ListStage stage{s_off, s_ent, kStageEntries};
   const int32_t* rq = reinterpret_cast<const int32_t*>(B.blob + F.raw_quant_off);
   const int8_t* ytox = reinterpret_cast<const int8_t*>(B.blob + F.ytox_off);
   const int8_t* ytob = reinterpret_cast<const int8_t*>(B.blob + F.ytob_off);
@@ -1929,7 +1955,7 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       setup_ctx(s_list[begin8 + (valid ? li : 0)], X, lfp, t, seq);
       constexpr uint32_t NC = KIND == 0 ? 64 : (KIND == 1 ? 128 : 256);
       int32_t* tile = s_tiles + (threadIdx.x >> 3) * 3 * NC;
-      gather_block_tile(B, F, g, seq, tile, NC, r, 8, gmask, valid);
+      gather_block_tile(B, F, g, seq, tile, NC, r, 8, gmask, valid, stage);
       X.coeffs = tile;
       X.cstride = NC;
       if constexpr (KIND == 1) {
@@ -2049,7 +2075,7 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       constexpr uint32_t NC = KIND == 1 ? 256 : 512;
       if constexpr (KIND >= 1) {
         int32_t* tile = s_tiles + (threadIdx.x >> 4) * 3 * NC;
-        gather_block_tile(B, F, g, seq, tile, NC, r, 16, gmask, valid);
+        gather_block_tile(B, F, g, seq, tile, NC, r, 16, gmask, valid, stage);
         X.coeffs = tile;
         X.cstride = NC;
       }
@@ -2076,7 +2102,7 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       setup_ctx(s_list[begin32 + (valid ? li : 0)], X, lfp, t, seq);
       if constexpr (KIND == 2) {
         int32_t* tile = s_tiles + (threadIdx.x >> 5) * 3 * 1024;
-        gather_block_tile(B, F, g, seq, tile, 1024, r, 32, 0xffffffffu, valid);
+        gather_block_tile(B, F, g, seq, tile, 1024, r, 32, 0xffffffffu, valid, stage);
         X.coeffs = tile;
         X.cstride = 1024;
         reg_dct_block<32, 32, true>(X, lfp, F.xb, r, 0xffffffffu, valid);
@@ -3074,9 +3100,9 @@ cudaError_t configure_kernels() {
   if ((e = configure_filters<true, 1>()) != cudaSuccess) return e;
   if ((e = configure_filters<true, 2>()) != cudaSuccess) return e;
   if ((e = configure_filters<true, 3>()) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_idct_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<0>()))) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_idct_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<1>()))) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_idct_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_tile_bytes<2>()))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_idct_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<0>()))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_idct_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<1>()))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_idct_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<2>()))) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLargeSmemBytes));
 }
 
@@ -3136,9 +3162,9 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
-  k_idct_small<0><<<B.num_streams, kSmallThreads, small_tile_bytes<0>(), stream>>>(B);
-  k_idct_small<1><<<B.num_streams, kSmallThreads, small_tile_bytes<1>(), stream>>>(B);
-  if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, small_tile_bytes<2>(), stream>>>(B);
+  k_idct_small<0><<<B.num_streams, kSmallThreads, small_smem_bytes<0>(), stream>>>(B);
+  k_idct_small<1><<<B.num_streams, kSmallThreads, small_smem_bytes<1>(), stream>>>(B);
+  if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, small_smem_bytes<2>(), stream>>>(B);
   launches += B.reg_idct32 ? 3 : 2;
   k_dequant_idct<<<B.num_streams, kIdctWarps * 32, kLargeSmemBytes, stream>>>(B);
   launches++;
@@ -3203,13 +3229,12 @@ __global__ void __launch_bounds__(256) k_expand_coeffs(const BatchDev B, uint32_
     const uint32_t* ow = base + kListCap;
     for (uint32_t bi = threadIdx.x >> 5; bi < nblk; bi += blockDim.x >> 5) {  // one warp per varblock
       const uint4 d = desc[bi];
-      const uint32_t nc = ((d.x >> 10) & 63) * ((d.x >> 16) & 63) * 64;
+      const uint32_t lnc = (d.x >> 26) + 6;  // log2 of the varblock's coefficients per channel
       const uint32_t o0 = ow[bi * 3], o1 = ow[bi * 3 + 1], o2 = ow[bi * 3 + 2], o3 = min(ow[bi * 3 + 3], kListCap);
       for (uint32_t i = o0 + (threadIdx.x & 31); i < o3; i += 32) {
         const uint32_t e = base[i];
         const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
-        const uint32_t pos = e & 0xffffu;
-        if (pos < nc) out[c * kGroupCoeffs + d.z + pos] += list_value(B, section, i, e);
+        out[c * kGroupCoeffs + d.z + entry_pos(e, lnc)] += entry_value(e, lnc);
       }
     }
     __syncthreads();
