@@ -62,6 +62,7 @@ struct Batch {
   std::vector<uint32_t> fused_prefix{0};
   std::vector<FrameOut> outs;
   uint64_t total_groups = 0, total_blocks = 0, total_plane_floats = 0, nz_bytes = 0, out_bytes = 0, orient_bytes = 0;
+  uint32_t lz_windows = 0;
   uint32_t max_epf = 0;
   uint32_t filter_cfg_mask = 0;  // bit (gab * 4 + min(epf_iters, 3))
   bool any_gab = false;
@@ -117,6 +118,7 @@ static int validate_desc(const JxgFrameDesc* d, const uint32_t* sec_len, uint32_
     for (uint32_t i = 0; i < s.num_contexts; i++)
       if (s.context_map[i] >= s.num_clusters) return bad("context_map entry >= num_clusters");
     if (s.shift > 31) return bad("pass shift");
+    if (s.lz77_enabled && s.lz_dist_cluster >= s.num_clusters) return bad("lz_dist_cluster >= num_clusters");
     if (s.use_prefix) {
       if (!s.huff_entries || !s.huff_offset) return bad("null prefix tables");
       for (uint32_t c = 0; c < s.num_clusters; c++) {
@@ -358,8 +360,12 @@ static int add_frame_impl(void* bp, const JxgFrameDesc* d, const uint8_t* hf_byt
   for (uint32_t p = 0; p < d->num_passes; p++) {
     const JxgPassDesc& s = d->passes[p];
     PassDev& P = F.passes[p];
-    if (s.lz77_enabled)
-      return set_error(JXG_ERR_UNSUPPORTED, "LZ77 in HF coefficient streams is not implemented on the device path");
+    if (s.lz77_enabled) F.has_lz = 1;  // routed to the one-lane-per-warp kernel, which carries the LZ77 window
+    P.lz77_enabled = s.lz77_enabled;
+    P.lz77_min_symbol = s.lz77_min_symbol;
+    P.lz77_min_length = s.lz77_min_length;
+    P.lz77_length_uint = s.lz77_length_uint;
+    P.lz_dist_cluster = s.lz_dist_cluster;
     P.shift = s.shift;
     P.use_prefix = s.use_prefix;
     P.log_alpha_size = s.log_alpha_size;
@@ -416,16 +422,20 @@ static int add_frame_impl(void* bp, const JxgFrameDesc* d, const uint8_t* hf_byt
     b->sections.push_back(sd);
   }
 #undef APPEND
-  if (F.num_passes == 1 && !F.passes[0].use_prefix && F.passes[0].shift == 0 &&
+  if (F.has_lz) {
+    F.lz_win_base = b->lz_windows;
+    b->lz_windows += F.num_passes * F.num_groups;
+  }
+  if (F.num_passes == 1 && !F.has_lz && !F.passes[0].use_prefix && F.passes[0].shift == 0 &&
       size_t(F.num_histograms) * F.num_block_contexts * 495 + 64 > 16384)
     b->lean_ctx_smem = false;
-  if (F.num_passes == 1 && !F.passes[0].use_prefix)
+  if (F.num_passes == 1 && !F.has_lz && !F.passes[0].use_prefix)
     for (uint32_t c = 0; c < d->passes[0].num_clusters; c++)
       if (d->passes[0].uint_configs[c] != (4u | (2u << 8))) b->lean_all_420 = false;
   F.first_stream = uint32_t(b->streams.size());
   for (uint32_t g = 0; g < F.num_groups; g++) {
     b->streams.push_back(StreamDev{uint32_t(b->frames.size()), g});
-    (F.num_passes != 1 ? b->streams_slow : ((F.passes[0].use_prefix || F.passes[0].shift != 0) ? b->streams_fast : b->streams_lean)).push_back(StreamDev{uint32_t(b->frames.size()), g});
+    ((F.num_passes != 1 || F.has_lz) ? b->streams_slow : ((F.passes[0].use_prefix || F.passes[0].shift != 0) ? b->streams_fast : b->streams_lean)).push_back(StreamDev{uint32_t(b->frames.size()), g});
     b->nz_base.push_back(b->nz_bytes);
     b->nz_bytes += size_t(F.num_passes) * 3072;
   }
@@ -613,6 +623,7 @@ static BatchDev make_batch_dev(Batch* b) {
   B.reg_idct32 = (getenv("JXG_REG_IDCT32") && atoi(getenv("JXG_REG_IDCT32"))) ? 1u : 0u;
   B.nzlist = static_cast<uint32_t*>(b->d_coeffs.p);  // the pool that held the dense coefficients now holds the lists
   B.block_off = static_cast<uint32_t*>(b->d_block_off.p);
+  B.lzwin = static_cast<uint32_t*>(b->ctx->d_lzwin.p);
   B.nz = static_cast<uint8_t*>(b->d_nz.p);
   B.nz_base = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(tab(b->tab.nz_base)));
   B.planes_a = static_cast<float*>(b->d_planes_a.p);
@@ -723,6 +734,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   // one coefficient list per HF section (pass x group), worst-case capacity (every coefficient non-zero)
   if (int r = b->d_coeffs.ensure(b->sections.size() * size_t(kListStride) * 4)) return r;
   if (int r = b->d_block_off.ensure(b->total_blocks * 4)) return r;
+  if (int r = b->ctx->d_lzwin.ensure(std::max<size_t>(size_t(b->lz_windows) * kLzWindow * 4, 16))) return r;
   if (int r = b->d_nz.ensure(b->nz_bytes)) return r;
   if (int r = b->d_planes_a.ensure(b->total_plane_floats * 4)) return r;
   if (int r = b->d_planes_b.ensure(b->total_plane_floats * 4)) return r;

@@ -120,7 +120,7 @@ struct Context {
   // steady-state decode loop does no cudaMalloc / cudaHostAlloc.
   PinnedArena blob;
   DevBuf d_blob, d_frames, d_sections, d_streams, d_streams_lean, d_lean_cta, d_streams_fast, d_streams_slow, d_nz_base, d_tiles, d_ftiles, d_coeffs, d_block_off, d_nz, d_planes_a,
-      d_planes_b, d_status, d_out, d_lean_desc, d_lean_nblk, d_orient, d_lean_warp, d_big;
+      d_planes_b, d_status, d_out, d_lean_desc, d_lean_nblk, d_orient, d_lean_warp, d_big, d_lzwin;
   bool batch_live = false;
   // pinned status readback buffer, owned by the context: cudaHostAlloc / cudaFreeHost synchronise the whole
   // device, so they must not happen per batch when batches of several contexts are in flight

@@ -22,6 +22,9 @@ constexpr uint32_t kGroupCoeffs = 65536;  // per channel per group (group.rs:53-
 // entry of channel ci (0 = Y, 1 = X, 2 = B) of the seq-th varblock, offw[nblk * 3] = total. The dense
 // [groups][3][65536] i32 array of round 1 (12 B/px written once, read once, >= 90 % zeros, plus a memset) is gone;
 // a list is written and read sequentially.
+// A pass of one group decodes at most 3 x 1024 non-zero counts + 3 x 65536 coefficients, fewer than the reference's
+// 2^20-symbol LZ77 window: the window never wraps and is addressed linearly.
+constexpr uint32_t kLzWindow = 3 * kGroupCoeffs + 3 * 1024;
 constexpr uint32_t kListCap = 3 * kGroupCoeffs;        // entries: every coefficient of the group non-zero
 constexpr uint32_t kListPad = 4;
 constexpr uint32_t kOffBase = kListCap + kListPad;     // first offset word
@@ -65,6 +68,9 @@ struct FrameDev {
   // persistent entropy lanes (k_entropy_lean): this frame's range in streams_lean (longest first) and its CTAs
   uint32_t lean_first, lean_count, lean_cta_first, lean_ctas;
   uint32_t lean_lanes;        // lanes of this frame that start with a stream of their own; the rest is queued
+  // LZ77 inside the HF streams (entropy_coding/decode.rs:286-330): such frames take the one-lane-per-warp kernel and own
+  // one window of decoded symbols per section in BatchDev::lzwin
+  uint32_t has_lz, lz_win_base;
   // device-only buffers (element offsets)
   uint64_t coeff_group_base;  // group index base into coeffs
   uint64_t block_base;        // block index base into block_off
@@ -108,6 +114,7 @@ struct BatchDev {
   uint32_t num_frames, num_streams, num_lean, num_fast, num_slow;
   uint32_t reg_idct32;  // 1: rows of 32 coefficients also go through the register path (experiment knob)
   uint32_t* nzlist;     // [sections][kListStride]: list of section (pass * num_groups + group) of a frame, see above
+  uint32_t* lzwin;      // [lz sections][kLzWindow] LZ77 windows (decode.rs:86-146), frames with has_lz only
   uint32_t* block_off;  // per 8x8 block: ordinal (raster order) of the varblock starting there within its group
   uint8_t* nz;          // [streams][passes][3][1024]
   uint64_t* nz_base;    // per stream offset into nz (bytes)

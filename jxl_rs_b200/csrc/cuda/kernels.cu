@@ -95,6 +95,9 @@ struct PassState {
   DevBr br;
   uint32_t ans_state;
   uint32_t hist_idx;
+  // LZ77 (decode.rs:86-146): window of the symbols decoded so far (linear, see kLzWindow), pending copy
+  uint32_t* lz_win;
+  uint32_t lz_to_copy, lz_copy_pos, lz_decoded, lz_err;
 };
 
 // hybrid_uint.rs:87-102
@@ -118,6 +121,7 @@ struct PassTables {
   const uint32_t* huff;
   const uint32_t* huff_offset;
   uint32_t use_prefix, log_alpha_size;
+  uint32_t lz_enabled, lz_min_symbol, lz_min_length, lz_len_cfg, lz_dist_cluster;
 };
 
 // ans.rs:356-393 / huffman.rs:446-457
@@ -157,7 +161,39 @@ __device__ __forceinline__ uint32_t read_token(const PassTables& T, PassState& s
   return symbol;
 }
 
+// decode.rs:286-330 with dist_multiplier == 0 (HF streams create their reader without an image width, group.rs:345-349).
+__device__ __noinline__ uint32_t read_symbol_lz77(const PassTables& T, PassState& s, uint32_t ctx) {
+  auto push = [&](uint32_t sym) {
+    s.lz_win[min(s.lz_decoded, kLzWindow - 1)] = sym;
+    s.lz_decoded++;
+    return sym;
+  };
+  if (s.lz_to_copy) {  // pull_symbol
+    s.lz_to_copy--;
+    return push(s.lz_win[min(s.lz_copy_pos++, kLzWindow - 1)]);
+  }
+  const uint32_t cluster = __ldg(T.context_map + ctx);
+  const uint32_t tok = read_token(T, s, cluster);
+  if (tok < T.lz_min_symbol) return push(hybrid_uint(__ldg(T.uint_configs + cluster), tok, s.br));
+  if (s.lz_decoded == 0) {  // a copy before anything was decoded (errors.lz77_repeat)
+    s.lz_err = 1;
+    return 0;
+  }
+  const uint32_t n = hybrid_uint(T.lz_len_cfg, tok - T.lz_min_symbol, s.br);
+  if (n > 0xffffffffu - T.lz_min_length) {
+    s.lz_err = 1;
+    return 0;
+  }
+  const uint32_t dtok = read_token(T, s, T.lz_dist_cluster);
+  const uint32_t dsym = hybrid_uint(__ldg(T.uint_configs + T.lz_dist_cluster), dtok, s.br);
+  const uint32_t distance = min(min(dsym, (1u << 20) - 1u) + 1u, s.lz_decoded);  // apply_copy, decode.rs:111-124
+  s.lz_copy_pos = s.lz_decoded - distance;
+  s.lz_to_copy = n + T.lz_min_length - 1;  // the first copied symbol is returned right away
+  return push(s.lz_win[min(s.lz_copy_pos++, kLzWindow - 1)]);
+}
+
 __device__ __forceinline__ uint32_t read_symbol(const PassTables& T, PassState& s, uint32_t ctx) {
+  if (T.lz_enabled) return read_symbol_lz77(T, s, ctx);
   uint32_t cluster = __ldg(T.context_map + ctx);
   uint32_t tok = read_token(T, s, cluster);
   return hybrid_uint(__ldg(T.uint_configs + cluster), tok, s.br);
@@ -307,6 +343,11 @@ __device__ __forceinline__ PassTables make_tables(const BatchDev& B, const PassD
   T.huff_offset = reinterpret_cast<const uint32_t*>(B.blob + P.huff_offset_off);
   T.use_prefix = P.use_prefix;
   T.log_alpha_size = P.log_alpha_size;
+  T.lz_enabled = P.lz77_enabled;
+  T.lz_min_symbol = P.lz77_min_symbol;
+  T.lz_min_length = P.lz77_min_length;
+  T.lz_len_cfg = P.lz77_length_uint;
+  T.lz_dist_cluster = P.lz_dist_cluster;
   return T;
 }
 
@@ -319,11 +360,14 @@ __device__ __forceinline__ int init_pass(const BatchDev& B, const FrameDev& F, u
   if (s.hist_idx >= F.num_histograms) return JXG_ERR_INVALID_HISTOGRAM_INDEX;
   s.ans_state = 0x130000u;
   if (!F.passes[pass].use_prefix) s.ans_state = s.br.read(32);  // ans.rs:431
+  s.lz_win = F.has_lz ? B.lzwin + size_t(F.lz_win_base + pass * F.num_groups + g) * kLzWindow : nullptr;
+  s.lz_to_copy = s.lz_copy_pos = s.lz_decoded = s.lz_err = 0;
   return 0;
 }
 
 __device__ __forceinline__ int finish_pass(const BatchDev& B, const FrameDev& F, uint32_t pass, uint32_t g, const PassState& s) {
   const SectionDev sec = B.sections[F.section_base + pass * F.num_groups + g];
+  if (s.lz_err) return JXG_ERR_LZ77;
   if (s.br.total > sec.len * 8u) return JXG_ERR_OUT_OF_BOUNDS;                          // bit_reader.rs:109
   if (!F.passes[pass].use_prefix && s.ans_state != 0x130000u) return JXG_ERR_ANS_CHECKSUM;  // ans.rs:441
   return 0;

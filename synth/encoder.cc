@@ -763,7 +763,24 @@ std::vector<uint8_t> encode(const Params& p) {
   uint32_t ac_clusters;
   HybridCfg cfg;
   std::vector<uint8_t> ac_map = cluster_contexts(num_ac_ctx, ac_ptrs, 48, ac_clusters, cfg);
-  AnsCode ac_code = build_code(num_ac_ctx, ac_map, ac_clusters, ac_ptrs, 6, p.entropy == 1);
+  // entropy 0 / 1: ANS / prefix codes; 2 / 3: the same with LZ77 copies (runs of equal coefficients, mostly zeros)
+  const bool use_lz = p.entropy >= 2, use_prefix = (p.entropy & 1) != 0;
+  std::vector<std::vector<Sym>> ac_syms;
+  AnsCode ac_code;
+  if (use_lz) {
+    Lz77 lz;
+    lz.enabled = true;
+    const HybridCfg len_cfg{0, 0, 0};
+    ac_syms.resize(ac.size());
+    parallel_for(ac.size(), [&](size_t g) { ac_syms[g] = lz77_symbols(ac[g], cfg, lz, len_cfg, uint32_t(num_ac_ctx)); });
+    ac_map.push_back(uint8_t(ac_clusters));  // the distance context gets a cluster of its own
+    std::vector<const std::vector<Sym>*> sp;
+    for (auto& v : ac_syms) sp.push_back(&v);
+    ac_code = build_code_lz77(num_ac_ctx + 1, ac_map, ac_clusters + 1, sp, lz, use_prefix);
+    ac_code.lz_len_cfg = len_cfg;
+  } else {
+    ac_code = build_code(num_ac_ctx, ac_map, ac_clusters, ac_ptrs, 6, use_prefix);
+  }
 
   // ---- sections ----
   BitWriter lf_global;
@@ -840,7 +857,8 @@ std::vector<uint8_t> encode(const Params& p) {
   std::vector<BitWriter> hf_groups(f.num_groups);
   parallel_for(f.num_groups, [&](size_t g) {
     // histogram_index: ceil_log2(num_histograms = 1) = 0 bits
-    write_tokens(hf_groups[g], ac_code, ac[g]);
+    if (use_lz) write_symbols(hf_groups[g], ac_code, ac_syms[g]);
+    else write_tokens(hf_groups[g], ac_code, ac[g]);
   });
 
   // ---- file assembly ----

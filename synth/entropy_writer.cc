@@ -373,8 +373,72 @@ std::vector<uint8_t> cluster_contexts(size_t num_contexts, const std::vector<con
   return map;
 }
 
+static std::vector<Sym> plain_symbols(const std::vector<Token>& tokens, const HybridCfg& cfg) {
+  std::vector<Sym> out;
+  out.reserve(tokens.size());
+  for (const Token& t : tokens) {
+    Sym s{t.ctx, 0, 0, 0};
+    cfg.encode(t.value, s.tok, s.nbits, s.bits);
+    out.push_back(s);
+  }
+  return out;
+}
+
+std::vector<Sym> lz77_symbols(const std::vector<Token>& tokens, const HybridCfg& cfg, const Lz77& lz, const HybridCfg& len_cfg,
+                              uint32_t dist_ctx) {
+  std::vector<Sym> out;
+  out.reserve(tokens.size());
+  static const uint32_t kDist[6] = {1, 2, 3, 4, 8, 64};
+  for (size_t i = 0; i < tokens.size();) {
+    size_t best_len = 0, best_dist = 0;
+    for (uint32_t d : kDist) {
+      if (d > i) break;
+      size_t l = 0;
+      while (i + l < tokens.size() && l < 4000 && tokens[i + l].value == tokens[i + l - d].value) l++;
+      if (l > best_len) best_len = l, best_dist = d;
+    }
+    if (best_len >= std::max<size_t>(lz.min_length, 4)) {
+      Sym len{tokens[i].ctx, 0, 0, 0};  // the copy is announced in the context of the symbol it replaces
+      len_cfg.encode(uint32_t(best_len - lz.min_length), len.tok, len.nbits, len.bits);
+      len.tok += lz.min_symbol;
+      out.push_back(len);
+      Sym dist{dist_ctx, 0, 0, 0};
+      cfg.encode(uint32_t(best_dist - 1), dist.tok, dist.nbits, dist.bits);
+      out.push_back(dist);
+      i += best_len;
+    } else {
+      Sym s{tokens[i].ctx, 0, 0, 0};
+      cfg.encode(tokens[i].value, s.tok, s.nbits, s.bits);
+      if (s.tok >= lz.min_symbol) throw std::runtime_error("literal token collides with the LZ77 range");
+      out.push_back(s);
+      i++;
+    }
+  }
+  return out;
+}
+
+static AnsCode build_code_syms(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
+                               const std::vector<const std::vector<Sym>*>& streams, uint32_t min_log_alpha, bool use_prefix);
+
 AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
                    const std::vector<const std::vector<Token>*>& streams, uint32_t min_log_alpha, bool use_prefix) {
+  HybridCfg cfg;
+  std::vector<std::vector<Sym>> syms;
+  for (auto* s : streams) syms.push_back(plain_symbols(*s, cfg));
+  std::vector<const std::vector<Sym>*> ptrs;
+  for (auto& v : syms) ptrs.push_back(&v);
+  return build_code_syms(num_contexts, cluster_of_ctx, num_clusters, ptrs, min_log_alpha, use_prefix);
+}
+
+AnsCode build_code_lz77(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
+                        const std::vector<const std::vector<Sym>*>& streams, const Lz77& lz, bool use_prefix) {
+  AnsCode code = build_code_syms(num_contexts, cluster_of_ctx, num_clusters, streams, 8, use_prefix);
+  code.lz = lz;
+  return code;
+}
+
+static AnsCode build_code_syms(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
+                               const std::vector<const std::vector<Sym>*>& streams, uint32_t min_log_alpha, bool use_prefix) {
   AnsCode code;
   code.use_prefix = use_prefix;
   code.num_contexts = uint32_t(num_contexts);
@@ -383,9 +447,8 @@ AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_c
   std::vector<std::vector<uint64_t>> counts(num_clusters, std::vector<uint64_t>(256, 0));
   uint32_t max_token = 0;
   for (auto* s : streams)
-    for (const Token& t : *s) {
-      uint32_t tok, nb, bits;
-      code.cfg.encode(t.value, tok, nb, bits);
+    for (const Sym& t : *s) {
+      const uint32_t tok = t.tok;
       if (tok >= 256) throw std::runtime_error("token too large for ANS alphabet");
       counts[cluster_of_ctx[t.ctx]][tok]++;
       max_token = std::max(max_token, tok);
@@ -457,7 +520,15 @@ AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_c
 }
 
 void write_code(BitWriter& bw, const AnsCode& code) {
-  bw.write(0, 1);  // lz77 disabled
+  if (code.lz.enabled) {  // decode.rs:36-44 + :489-498
+    bw.write(1, 1);
+    if (code.lz.min_symbol != 224 || code.lz.min_length != 3) throw std::runtime_error("only min_symbol 224 / min_length 3 are written");
+    bw.u2s_sel(0);  // min_symbol 224
+    bw.u2s_sel(0);  // min_length 3
+    write_hybrid_cfg(bw, code.lz_len_cfg, 8);
+  } else {
+    bw.write(0, 1);
+  }
   if (code.num_contexts > 1) {
     // context map (context_map.rs:43-76)
     uint32_t bits_needed = ceil_log2(code.num_clusters);
@@ -506,14 +577,16 @@ void write_code(BitWriter& bw, const AnsCode& code) {
 }
 
 void write_tokens(BitWriter& bw, const AnsCode& code, const std::vector<Token>& tokens) {
+  write_symbols(bw, code, plain_symbols(tokens, code.cfg));
+}
+
+void write_symbols(BitWriter& bw, const AnsCode& code, const std::vector<Sym>& tokens) {
   if (code.use_prefix) {  // no initial state; token pattern then the hybrid-uint extra bits (decode.rs:286-330)
-    for (const Token& t : tokens) {
-      uint32_t tok, nb, bits;
-      code.cfg.encode(t.value, tok, nb, bits);
+    for (const Sym& t : tokens) {
       const uint32_t c = code.context_map[t.ctx];
-      if (tok >= code.plen[c].size()) throw std::runtime_error("token outside the prefix alphabet");
-      bw.write(code.pbits[c][tok], code.plen[c][tok]);
-      bw.write(bits, nb);
+      if (t.tok >= code.plen[c].size()) throw std::runtime_error("token outside the prefix alphabet");
+      bw.write(code.pbits[c][t.tok], code.plen[c][t.tok]);
+      bw.write(t.bits, t.nbits);
     }
     return;
   }
@@ -522,9 +595,8 @@ void write_tokens(BitWriter& bw, const AnsCode& code, const std::vector<Token>& 
   std::vector<uint16_t> chunk(n, 0);
   uint32_t state = 0x130000;
   for (size_t i = n; i-- > 0;) {
-    const Token& t = tokens[i];
-    uint32_t tok, nb, bits;
-    code.cfg.encode(t.value, tok, nb, bits);
+    const Sym& t = tokens[i];
+    const uint32_t tok = t.tok;
     uint32_t c = code.context_map[t.ctx];
     uint32_t f = code.freqs[c][tok];
     if (f == 0) throw std::runtime_error("token with zero frequency");
@@ -538,11 +610,8 @@ void write_tokens(BitWriter& bw, const AnsCode& code, const std::vector<Token>& 
   }
   bw.write(state, 32);
   for (size_t i = 0; i < n; i++) {
-    const Token& t = tokens[i];
-    uint32_t tok, nb, bits;
-    code.cfg.encode(t.value, tok, nb, bits);
     if (has_chunk[i]) bw.write(chunk[i], 16);
-    bw.write(bits, nb);
+    bw.write(tokens[i].bits, tokens[i].nbits);
   }
 }
 

@@ -100,6 +100,19 @@ struct HybridCfg {
   }
 };
 
+// LZ77 layer of a code (entropy_coding/decode.rs:36-44, 286-330): tokens >= min_symbol announce a copy of
+// hybrid(length_cfg, token - min_symbol) + min_length earlier symbols, followed by the distance - 1 coded in the extra
+// context behind the regular ones (dist_multiplier 0: plain distances).
+struct Lz77 {
+  bool enabled = false;
+  uint32_t min_symbol = 224, min_length = 3;
+};
+// One coded symbol: context (index into the context map; the distance context is num_contexts - 1 of an LZ77 code),
+// entropy-coded token, raw bits behind it.
+struct Sym {
+  uint32_t ctx, tok, nbits, bits;
+};
+
 // One clustered ANS code (all clusters), ready to serialise and to encode with.
 struct AnsCode {
   uint32_t num_contexts = 0;
@@ -112,6 +125,8 @@ struct AnsCode {
   std::vector<std::vector<uint16_t>> slots;       // [cluster] concatenated idx lists per symbol (offset -> idx)
   // Prefix-code variant (entropy_coding/huffman.rs): per cluster canonical code lengths (<= 15) and the bit patterns
   // as the decoder's table expects them (first bit read = LSB).
+  Lz77 lz;
+  HybridCfg lz_len_cfg{0, 0, 0};  // hybrid-uint configuration of the copy lengths (8-bit alphabet form, decode.rs:493)
   bool use_prefix = false;
   std::vector<std::vector<uint8_t>> plen;         // [cluster][alphabet]
   std::vector<std::vector<uint16_t>> pbits;       // [cluster][alphabet]
@@ -125,9 +140,17 @@ AnsCode build_code(size_t num_contexts, const std::vector<uint8_t>& cluster_of_c
 // Convenience: one cluster per context when num_contexts <= 8, else quantile clustering into <= max_clusters.
 std::vector<uint8_t> cluster_contexts(size_t num_contexts, const std::vector<const std::vector<Token>*>& streams,
                                       uint32_t max_clusters, uint32_t& num_clusters, const HybridCfg& cfg);
-// Serialises lz77=off, context map, ANS flag, log_alpha, uint configs, histograms (decode.rs:487-545).
+// Serialises the LZ77 parameters, context map, ANS flag, log_alpha, uint configs, histograms (decode.rs:487-545).
 void write_code(BitWriter& bw, const AnsCode& code);
 // Writes initial state + symbols so that decoding ends in 0x130000.
 void write_tokens(BitWriter& bw, const AnsCode& code, const std::vector<Token>& tokens);
+
+// LZ77 variant: tokens -> coded symbols with greedy copies (runs and short-distance repeats), then a code built from
+// the symbols of all streams (num_contexts counts the distance context), and the symbol writer.
+std::vector<Sym> lz77_symbols(const std::vector<Token>& tokens, const HybridCfg& cfg, const Lz77& lz, const HybridCfg& len_cfg,
+                              uint32_t dist_ctx);
+AnsCode build_code_lz77(size_t num_contexts, const std::vector<uint8_t>& cluster_of_ctx, uint32_t num_clusters,
+                        const std::vector<const std::vector<Sym>*>& streams, const Lz77& lz, bool use_prefix);
+void write_symbols(BitWriter& bw, const AnsCode& code, const std::vector<Sym>& syms);
 
 }  // namespace jxs

@@ -108,6 +108,17 @@ def test_scope_guards_refuse_what_the_path_cannot_reproduce(golden_dir):
     assert e.value.code == -2
 
 
+def test_entropy_variants_of_the_writer_decode_identically():
+    """The same quantised frame coded four ways — ANS, prefix codes, and both with LZ77 copies — is the same picture."""
+    import synth
+    from tests import oracle_binding as ob
+    outs = [ob.decode_file(synth.encode_synthetic(600, 400, 5, 0.5, 2, 1, 1, 0, ent), abi.FORMAT_RGB_U8)[0] for ent in range(4)]
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    lz = _frame_census(synth.encode_synthetic(600, 400, 5, 0.5, 2, 1, 1, 0, 2))
+    assert lz["lz77"] == 1
+
+
 def _frame_census(data):
     """Transform types used by first blocks and the entropy code of pass 0, from the descriptor the front-end hands
     to the hot path (no GPU involved)."""
@@ -118,7 +129,7 @@ def _frame_census(data):
     tm = np.ctypeslib.as_array(C.cast(d.transform_map, C.POINTER(C.c_uint8)), (nb,)).copy()
     types = np.bincount(tm[tm >= 128] & 127, minlength=27)
     p0 = d.passes[0]
-    census = {"types": types, "use_prefix": int(p0.use_prefix), "clusters": int(p0.num_clusters), "max_code_bits": 0}
+    census = {"types": types, "use_prefix": int(p0.use_prefix), "clusters": int(p0.num_clusters), "lz77": int(p0.lz77_enabled)}
     if p0.use_prefix:
         e = np.ctypeslib.as_array(C.cast(p0.huff_entries, C.POINTER(C.c_uint32)), (p0.huff_entries_len,)).copy()
         off = np.ctypeslib.as_array(C.cast(p0.huff_offset, C.POINTER(C.c_uint32)), (p0.num_clusters,)).copy()

@@ -8,7 +8,7 @@ from jxl_rs_b200 import abi
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # w, h, seed, distance, epf, gab, profile, entropy (0 ANS, 1 prefix codes)
+    # w, h, seed, distance, epf, gab, profile, entropy (0 ANS, 1 prefix codes, 2 ANS + LZ77, 3 prefix codes + LZ77)
     (256, 256, 1000, 0.5, 2, 1, 1, 0),     # BASELINE config 1 geometry: one group, single TOC entry
     (8, 8, 1, 1.0, 2, 1, 0, 0),
     (263, 131, 2, 0.7, 1, 0, 1, 0),        # ragged edges
@@ -22,6 +22,9 @@ CASES = [
     (1024, 768, 32, 0.5, 2, 1, 1, 1),
     (777, 513, 34, 0.3, 1, 1, 3, 1),       # prefix codes + every transform family
     (256, 256, 35, 0.5, 2, 1, 0, 1),       # single-section frame, prefix codes
+    # LZ77 inside the HF streams (entropy_coding/decode.rs:286-330), ANS and prefix coded
+    (1024, 768, 36, 0.5, 2, 1, 1, 2),
+    (777, 513, 37, 0.5, 1, 1, 2, 3),
 ]
 
 
