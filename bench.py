@@ -500,6 +500,26 @@ def main():
             h2d, d2h = dec.last_stats["h2d_bytes"], dec.last_stats["d2h_bytes"]
         except Exception as e:  # noqa: BLE001
             e2e_err = e
+    # The host link itself: one plain pinned D2H / H2D copy of a batch's worth of bytes, all ranks at once (they share the
+    # host's root complexes and memory). The end-to-end leg cannot be faster than its D2H bytes over this rate.
+    link = {"d2h_gbs": None, "h2d_gbs": None}
+    try:
+        nbytes = sum(o.numel() for o in host_out[0])
+        dev_buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        host_buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        for name, dst, src in (("d2h_gbs", host_buf, dev_buf), ("h2d_gbs", dev_buf, host_buf)):
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            link[name] = 3 * nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+        del dev_buf, host_buf
+    except Exception as e:  # noqa: BLE001
+        link["error"] = repr(e)
     barrier()
     t = torch.tensor([0.0 if e2e_err is not None else e2e_sec, 1.0 if e2e_err is not None else 0.0], dtype=torch.float64,
                      device=f"cuda:{local_rank}")
@@ -557,7 +577,10 @@ def main():
                              "sample": f"{sample} frames of {args.width}x{args.height}, oracle port, {cpu_sec:.1f} s"},
             "e2e": ({"value": mp_per_step * world * args.steps / e2e_sec_max, "unit": "MP/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec_max / args.steps * 1e3,
-                     "frac_of_device_resident": (mp_per_step * world * args.steps / e2e_sec_max) / value} if e2e_ok else
+                     "frac_of_device_resident": (mp_per_step * world * args.steps / e2e_sec_max) / value,
+                     "host_link_gbs_rank0": link,
+                     "link_bound_mp_per_s": (link["d2h_gbs"] * 1e9 / (d2h / mp_per_step / 1e6) / 1e6 * world
+                                             if link.get("d2h_gbs") and d2h else None)} if e2e_ok else
                     {"value": None, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "error": repr(e2e_err) if e2e_err else "end-to-end leg failed on another rank"}),
             "gpu_launches": int(launches_per_step * args.steps),

@@ -3270,7 +3270,7 @@ __global__ void __launch_bounds__(256) k_expand_coeffs(const BatchDev B, uint32_
   for (uint32_t p = 0; p < F.num_passes; p++) {
     const uint32_t section = F.section_base + p * F.num_groups + g;
     const uint32_t* base = list_base(B, section);
-    const uint32_t* ow = base + kListCap;
+    const uint32_t* ow = base + kOffBase;
     for (uint32_t bi = threadIdx.x >> 5; bi < nblk; bi += blockDim.x >> 5) {  // one warp per varblock
       const uint4 d = desc[bi];
       const uint32_t lnc = (d.x >> 26) + 6;  // log2 of the varblock's coefficients per channel
