@@ -480,7 +480,11 @@ def main():
     # A failure of the end-to-end leg must not lose the device-resident measurement (nor dead-lock the other ranks at
     # a barrier): it is reported as e2e.value = null with the error text.
     e2e_err, dec, e2e_sec, h2d, d2h = None, None, float("nan"), 0, 0
+    if os.environ.get("JXG_BENCH_SKIP_E2E"):  # sweeps of the device-resident leg only (tools/gpu_sweep.sh)
+        e2e_err = RuntimeError("end-to-end leg skipped (JXG_BENCH_SKIP_E2E)")
     try:
+        if e2e_err is not None:
+            raise e2e_err
         dec = j.PipelinedDecoder(local_rank, depth=e2e_depth, workers=min(64, rank_cores()),
                                  staging_threads=max(2, min(4, rank_cores() // 4)))
         for i in range(max(3, min(args.warmup, 3))):
