@@ -656,7 +656,14 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
     // on the copy stream while the next range is being filtered.
     Context* cx = b->ctx;
     const uint32_t nf = uint32_t(b->frames.size());
-    const uint32_t nr = copy_to_host ? std::min<uint32_t>(Context::kMaxRanges, nf) : 1;
+    // D2H of host outputs: JXG_D2H_RANGES = r > 0 copies each of r frame ranges on the copy stream as soon as its filter
+    // launch ends (lowest latency for one batch alone); 0 = one filter launch, then all copies on the launching stream
+    // (no cross-stream events: with several batches in flight on several contexts the copies of batch k overlap the
+    // kernels of batch k + 1 anyway).
+    static const int d2h_ranges = getenv("JXG_D2H_RANGES") ? atoi(getenv("JXG_D2H_RANGES")) : int(Context::kMaxRanges);
+    const bool same_stream = copy_to_host && d2h_ranges <= 0;
+    const uint32_t nr = (copy_to_host && !same_stream) ? std::min<uint32_t>(std::min<uint32_t>(uint32_t(d2h_ranges), Context::kMaxRanges), nf) : 1;
+    cudaStream_t cs = same_stream ? s : cx->copy_stream;
     const uint32_t* fp = reinterpret_cast<const uint32_t*>(tab(b->tab.ftiles));
     if (ev) {
       for (int i = 4; i <= 6; i++) cudaEventRecord(ev[i], s);
@@ -674,12 +681,14 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
         b->launches++;
       }
       if (copy_to_host) {
-        CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
-        CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->range_done[r], 0));
+        if (!same_stream) {
+          CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
+          CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->range_done[r], 0));
+        }
         for (uint32_t f = f0; f < f1; f++) {
           const FrameOut& fo = b->outs[f];
           if (fo.is_device) continue;
-          CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.copy_bytes, cudaMemcpyDeviceToHost, cx->copy_stream));
+          CUDA_TRY(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.copy_bytes, cudaMemcpyDeviceToHost, cs));
           b->d2h += fo.copy_bytes;
         }
       }
@@ -688,7 +697,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
       cudaEventRecord(ev[7], s);
       cudaEventRecord(ev[8], s);
     }
-    if (copy_to_host) {  // the launching stream joins the copy stream so that ev1 / stream sync cover the copies
+    if (copy_to_host && !same_stream) {  // the launching stream joins the copy stream so that ev1 / stream sync cover the copies
       CUDA_TRY(cudaEventRecord(cx->copy_done, cx->copy_stream));
       CUDA_TRY(cudaStreamWaitEvent(s, cx->copy_done, 0));
     }

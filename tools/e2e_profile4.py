@@ -12,7 +12,7 @@ depth = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 j.bind_to_gpu_numa_node(0)
 host_out = [[torch.empty((2160, 3840, 3), dtype=torch.uint8).pin_memory() for _ in range(n)] for _ in range(depth)]
 outs = [[(o.data_ptr(), 3840 * 3) for o in ho] for ho in host_out]
-for st in (4, 8):
+for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     dec = j.PipelinedDecoder(0, depth=depth, staging_threads=st)
     for i in range(3):
         dec.submit(files, outs[i % depth])
