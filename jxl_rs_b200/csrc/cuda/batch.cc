@@ -549,12 +549,14 @@ static void schedule_lean(Batch* b) {
     b->frames[f].lean_count = uint32_t(j - i);
     i = j;
   }
-  // The kernel keeps 6 CTAs per SM resident (register bound); a grid beyond one resident wave would start its last
-  // CTAs only when the first ones end, so the packing is made denser until the grid fits.
-  const uint32_t max_ctas = 148 * 6;
+  // The kernel keeps 8 CTAs per SM resident (64 registers per thread); a grid beyond one resident wave would start its
+  // last CTAs only when the first ones end, so the packing is made denser until the grid fits.
+  const uint32_t max_ctas = 148 * 8;
   uint32_t S = 4;
   if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
   S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
+  // lanes actually used per packed warp (<= S, the kernel's compile-time capacity): 3 is a legal in-between
+  uint32_t L = std::min<uint32_t>(S, std::max<uint32_t>(1, uint32_t(knob("JXG_ENTROPY_LANES", float(S)))));
   std::vector<uint2> warps;
   for (int attempt = 0; attempt < 12; attempt++) {
     warps.clear();
@@ -575,13 +577,13 @@ static void schedule_lean(Batch* b) {
       n_duo &= ~1u;
       const uint32_t rest = F.lean_count - n_solo - n_duo;
       uint32_t packed = uint32_t(std::ceil(float(rest) / per_lane));  // lanes of the S-wide warps
-      packed = std::min(rest, (packed + S - 1) / S * S);
+      packed = std::min(rest, (packed + L - 1) / L * L);
       const size_t w0 = warps.size();
       uint32_t pos = 0;
       for (uint32_t i = 0; i < n_solo; i++) warps.push_back(make_uint2(pos++, 1));
       for (uint32_t i = 0; i < n_duo; i += 2, pos += 2) warps.push_back(make_uint2(pos, 2));
-      for (uint32_t i = 0; i < packed; i += S) {
-        const uint32_t n = std::min(S, packed - i);
+      for (uint32_t i = 0; i < packed; i += L) {
+        const uint32_t n = std::min(L, packed - i);
         warps.push_back(make_uint2(pos, n));
         pos += n;
       }
@@ -595,7 +597,8 @@ static void schedule_lean(Batch* b) {
     // denser: first fewer privileged warps, then more streams per packed lane, then wider warps
     if (solo < 0.95f) solo = std::min(0.95f, solo + 0.1f), duo = std::min(0.9f, duo + 0.1f);
     else if (per_lane < 4.0f) per_lane *= 1.3f;
-    else if (S < 8) S = 8, per_lane = 1.6f;
+    else if (L < S) L = S;
+    else if (S < 8) S = L = 8, per_lane = 1.6f;
     else per_lane *= 1.3f;
   }
   b->lean_S = S;
