@@ -247,39 +247,6 @@ struct ListStage {
   uint32_t staged;
 };
 
-// Builds the dense coefficient tile of one varblock in shared memory from the coefficient lists: `nl` lanes (rank r,
-// all lanes of `gmask` call this together) zero tile[3][NC], then add the entries of every pass (the sum of the passes
-// is the coefficient, group.rs:556-567). Entries come in the order Y, X, B; the tile is indexed X, Y, B like the
-// dequant tables. NC is the varblock's own coefficient count, so every decoded position lies inside the tile.
-__device__ __forceinline__ void gather_block_tile(const BatchDev& B, const FrameDev& F, uint32_t g, uint32_t seq, int32_t* tile,
-                                                  uint32_t NC, uint32_t r, uint32_t nl, uint32_t gmask, bool valid,
-                                                  const ListStage& st = ListStage{nullptr, nullptr, 0}) {
-  const uint32_t lnc = 31 - __clz(NC);  // NC = the varblock's coefficients per channel (a power of two)
-  int4* t4 = reinterpret_cast<int4*>(tile);
-  __syncwarp(gmask);  // the previous varblock of this lane group has been read completely
-  for (uint32_t i = r; i < 3 * NC / 4; i += nl) t4[i] = make_int4(0, 0, 0, 0);
-  __syncwarp(gmask);
-  for (uint32_t p = 0; p < F.num_passes; p++) {
-    const uint32_t section = F.section_base + p * F.num_groups + g;
-    const uint32_t* base = list_base(B, section);
-    if (valid) {
-      const bool from_stage = p == 0 && st.off != nullptr;
-      const uint32_t* ow = from_stage ? st.off + seq * 3 : base + kOffBase + seq * 3;
-      const uint32_t o0 = ow[0], o1 = ow[1], o2 = ow[2];
-      uint32_t o3 = ow[3];
-      o3 = min(o3, kListCap);
-      const uint32_t staged = from_stage ? st.staged : 0u;
-      for (uint32_t i = o0 + r; i < o3; i += nl) {
-        const uint32_t e = i < staged ? st.ent[i] : __ldg(base + i);
-        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
-        tile[c * NC + entry_pos(e, lnc)] += entry_value(e, lnc);
-      }
-    }
-    if (p + 1 < F.num_passes) __syncwarp(gmask);
-  }
-  __syncwarp(gmask);
-}
-
 struct BlockInfo {
   uint32_t bx, by, cx, cy, shape, raw_quant, quant_lf, num_blocks, num_coeffs, log_num_blocks;
 };
@@ -1240,6 +1207,92 @@ __device__ __forceinline__ float adjust_quant_bias(int32_t q, float bias_c, floa
   return (q > -2 && q < 2) ? qf * bias_c : qf - bias3 / qf;
 }
 
+// Dequantisation constants of one varblock (group.rs:137-177).
+struct DeqParams {
+  const float* mat;  // dequant weights of the block's table: channel c at mat + c * ncoef
+  uint32_t ncoef;
+  float sx, sy, sb, x_cc, b_cc, bias0, bias1, bias2, bias3;
+};
+
+// Coefficient lists -> DEQUANTISED coefficient tile of one varblock in shared memory (three channels at stride
+// `cstride` floats, element of position pos at idx(pos)). Only the non-zero entries are touched: the tile is zeroed, the
+// Y entries write dy and seed X / B with cc * dy, then the X / B entries write mul_add(cc, dy, d) — exactly
+// group.rs:100-133 evaluated at every position (a zero quantised value dequantises to 0, and mul_add(cc, dy, 0) is the
+// rounded product), at a tenth of the arithmetic since >= 90 % of the coefficients are zero. `nl` lanes of rank r work
+// together and separate the phases with sync(). Frames with several passes add the passes up as integers first
+// (group.rs:556-567: the sum is the coefficient) and convert in place.
+template <typename Sync, typename Idx>
+__device__ __forceinline__ void gather_dequant_tile(const BatchDev& B, const FrameDev& F, uint32_t g, uint32_t seq, float* tile,
+                                                    uint32_t cstride, uint32_t zero_floats, const DeqParams& D, uint32_t r, uint32_t nl,
+                                                    bool valid, const ListStage& st, Sync sync, Idx idx) {
+  const uint32_t lnc = 31 - __clz(D.ncoef);
+  sync();  // the previous varblock of this lane group has been read completely
+  for (uint32_t c = 0; c < 3; c++) {
+    float4* t4 = reinterpret_cast<float4*>(tile + c * cstride);
+    for (uint32_t i = r; i < zero_floats / 4; i += nl) t4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  sync();
+  if (F.num_passes == 1) {
+    const uint32_t* base = list_base(B, F.section_base + g);
+    const bool from_stage = st.off != nullptr;
+    const uint32_t* ow = from_stage ? st.off + seq * 3 : base + kOffBase + seq * 3;
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    if (valid) {
+      o0 = ow[0];
+      o1 = ow[1];
+      o2 = ow[2];
+      o3 = min(ow[3], kListCap);
+    }
+    const uint32_t staged = from_stage ? st.staged : 0u;
+    for (uint32_t i = o0 + r; i < o1; i += nl) {  // Y
+      const uint32_t e = i < staged ? st.ent[i] : __ldg(base + i);
+      const uint32_t pos = entry_pos(e, lnc), j = idx(pos);
+      const float dy = adjust_quant_bias(entry_value(e, lnc), D.bias1, D.bias3) * (__ldg(D.mat + D.ncoef + pos) * D.sy);
+      tile[cstride + j] = dy;
+      tile[j] = D.x_cc * dy;
+      tile[2 * cstride + j] = D.b_cc * dy;
+    }
+    sync();
+    for (uint32_t i = o1 + r; i < o3; i += nl) {  // X, then B
+      const uint32_t e = i < staged ? st.ent[i] : __ldg(base + i);
+      const uint32_t pos = entry_pos(e, lnc), j = idx(pos);
+      const bool is_x = i < o2;
+      const uint32_t c = is_x ? 0u : 2u;
+      const float d = adjust_quant_bias(entry_value(e, lnc), is_x ? D.bias0 : D.bias2, D.bias3) *
+                      (__ldg(D.mat + c * D.ncoef + pos) * (is_x ? D.sx : D.sb));
+      tile[c * cstride + j] = fmaf(is_x ? D.x_cc : D.b_cc, tile[cstride + j], d);
+    }
+    sync();
+    return;
+  }
+  int32_t* it = reinterpret_cast<int32_t*>(tile);
+  for (uint32_t p = 0; p < F.num_passes; p++) {
+    const uint32_t* base = list_base(B, F.section_base + p * F.num_groups + g);
+    const uint32_t* ow = base + kOffBase + seq * 3;
+    if (valid) {
+      const uint32_t o0 = ow[0], o1 = ow[1], o2 = ow[2], o3 = min(ow[3], kListCap);
+      for (uint32_t i = o0 + r; i < o3; i += nl) {
+        const uint32_t e = __ldg(base + i);
+        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);
+        it[c * cstride + idx(entry_pos(e, lnc))] += entry_value(e, lnc);
+      }
+    }
+    sync();
+  }
+  if (valid) {
+    for (uint32_t k = r; k < D.ncoef; k += nl) {
+      const uint32_t j = idx(k);
+      const float dy = adjust_quant_bias(it[cstride + j], D.bias1, D.bias3) * (__ldg(D.mat + D.ncoef + k) * D.sy);
+      const float dxc = adjust_quant_bias(it[j], D.bias0, D.bias3) * (__ldg(D.mat + k) * D.sx);
+      const float dbc = adjust_quant_bias(it[2 * cstride + j], D.bias2, D.bias3) * (__ldg(D.mat + 2 * D.ncoef + k) * D.sb);
+      tile[cstride + j] = dy;
+      tile[j] = fmaf(D.x_cc, dy, dxc);
+      tile[2 * cstride + j] = fmaf(D.b_cc, dy, dbc);
+    }
+  }
+  sync();
+}
+
 struct DequantCtx {
   const int32_t* qx;
   const int32_t* qy;
@@ -1430,9 +1483,8 @@ __device__ __forceinline__ bool is_small_reg_type(int t, bool reg32) {
   return (t == 0) || (t >= 3 && t <= 13 && (reg32 || !(t == 5 || (t >= 8 && t <= 11))));
 }
 
-constexpr int kIdctWarps = 4;   // per warp: float work tiles 3 x kWarpBuf + the varblock's coefficient tile 3 x 1024 i32
-constexpr int kWarpInts = 3 * 1024;
-constexpr size_t kLargeSmemBytes = size_t(kIdctWarps) * (3 * (32 * 33) + kWarpInts) * sizeof(float);
+constexpr int kIdctWarps = 8;   // per warp: dequantised work tiles 3 x kWarpBuf floats
+constexpr size_t kLargeSmemBytes = size_t(kIdctWarps) * (3 * (32 * 33)) * sizeof(float);
 constexpr int kWarpBuf = 32 * 33;  // floats per channel per warp
 
 // Global in-place 1-D passes for varblocks with a dimension >= 64.
@@ -1457,25 +1509,10 @@ __device__ __forceinline__ void big_line_dispatch(int n, float* base, size_t ele
 
 // Shared-memory warp path of one plain-DCT varblock with compile-time shape (index arithmetic becomes shifts).
 template <int R, int C>
-__device__ __forceinline__ void warp_dct_block(const DequantCtx& dq, float* wbuf, int lane, const float* const* lfp,
-                                               size_t lf_index, uint32_t lf_stride, float* const* planes, size_t px0,
-                                               uint32_t plane_stride) {
+__device__ __forceinline__ void warp_dct_block(float* wbuf, int lane, const float* const* lfp, size_t lf_index,
+                                               uint32_t lf_stride, float* const* planes, size_t px0, uint32_t plane_stride) {
+  // wbuf: the three dequantised channels, coefficient (vf, hf) at [vf * (C + 1) + hf] (gather_dequant_tile)
   constexpr int stride = C + 1, cx = C / 8, cy = R / 8;
-  constexpr bool wide = R < C;
-  float* ch0 = wbuf;
-  float* ch1 = wbuf + kWarpBuf;
-  float* ch2 = wbuf + 2 * kWarpBuf;
-#pragma unroll 4
-  for (int k = lane; k < R * C; k += 32) {
-    float vx, vy, vb;
-    dq.get(uint32_t(k), vx, vy, vb);
-    const int vf = wide ? k / C : k % R;
-    const int hf = wide ? k % C : k / R;
-    ch0[vf * stride + hf] = vx;
-    ch1[vf * stride + hf] = vy;
-    ch2[vf * stride + hf] = vb;
-  }
-  __syncwarp();
   if (lane < 3) {  // LLF (group.rs:227-236)
     float* ch = wbuf + lane * kWarpBuf;
     llf_small(lfp[lane] + lf_index, lf_stride, cy, cx, [&](int vf, int hf, float v) { ch[vf * stride + hf] = v; });
@@ -1521,8 +1558,7 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
                          reinterpret_cast<const float*>(B.blob + F.lf_off[1]),
                          reinterpret_cast<const float*>(B.blob + F.lf_off[2])};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* wbuf = smem + warp * (3 * kWarpBuf + kWarpInts);
-  int32_t* itile = reinterpret_cast<int32_t*>(wbuf + 3 * kWarpBuf);
+  float* wbuf = smem + warp * (3 * kWarpBuf);
   if (threadIdx.x == 0) {
     s_next = 0;
     s_nbig = 0;
@@ -1572,41 +1608,36 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     }
     DequantCtx dq;
     setup(bx, by, t, dq);
-    // the varblock's coefficients: list entries -> dense tile in shared memory (X, Y, B at stride num_coeffs)
-    gather_block_tile(B, F, g, block_off[bidx], itile, dq.num_coeffs, uint32_t(lane), 32, 0xffffffffu, true);
-    dq.qx = itile;
-    dq.qy = itile + dq.num_coeffs;
-    dq.qb = itile + 2 * dq.num_coeffs;
     const int R = 8 * cy, C = 8 * cx;
     const bool is_dct = (t == 0) || (t >= 4 && t <= 11);
-    float* ch0 = wbuf;
-    float* ch1 = wbuf + kWarpBuf;
-    float* ch2 = wbuf + 2 * kWarpBuf;
+    {  // the varblock's coefficients: list entries -> dequantised work tiles (wbuf, channels at stride kWarpBuf); plain DCTs
+       // in [vf][hf] order with row stride C + 1, the 8x8 specials in storage order
+      const uint32_t lR = 31 - __clz(uint32_t(R)), lC = 31 - __clz(uint32_t(C));
+      const bool wide_l = R < C;
+      const DeqParams D{dq.mat, dq.num_coeffs, dq.sx, dq.sy, dq.sb, dq.x_cc, dq.b_cc, dq.bias0, dq.bias1, dq.bias2, dq.bias3};
+      const uint32_t zero_floats = is_dct ? uint32_t((R * (C + 1) + 3) & ~3) : 64u;
+      gather_dequant_tile(B, F, g, block_off[bidx], wbuf, uint32_t(kWarpBuf), zero_floats, D, uint32_t(lane), 32, true,
+                          ListStage{nullptr, nullptr, 0}, [] { __syncwarp(); },
+                          [=](uint32_t k) {
+                            if (!is_dct) return k;
+                            const uint32_t vf = wide_l ? k >> lC : k & (uint32_t(R) - 1), hf = wide_l ? k & (uint32_t(C) - 1) : k >> lR;
+                            return vf * uint32_t(C + 1) + hf;
+                          });
+    }
     const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
     const size_t lf_index = size_t(by0 + by) * F.xb + bx0 + bx;
     if (is_dct && R == 32 && C == 32) {
-      warp_dct_block<32, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+      warp_dct_block<32, 32>(wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
     } else if (is_dct && R == 32 && C == 16) {
-      warp_dct_block<32, 16>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+      warp_dct_block<32, 16>(wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
     } else if (is_dct && R == 16 && C == 32) {
-      warp_dct_block<16, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+      warp_dct_block<16, 32>(wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
     } else if (is_dct && R == 32 && C == 8) {
-      warp_dct_block<32, 8>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+      warp_dct_block<32, 8>(wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
     } else if (is_dct && R == 8 && C == 32) {
-      warp_dct_block<8, 32>(dq, wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
+      warp_dct_block<8, 32>(wbuf, lane, lfp, lf_index, F.xb, planes, px0, F.plane_stride);
     } else if (is_dct) {
       const int stride = C + 1;
-      const bool wide = R < C;
-      for (uint32_t k = lane; k < dq.num_coeffs; k += 32) {
-        float vx, vy, vb;
-        dq.get(k, vx, vy, vb);
-        int vf = wide ? int(k) / C : int(k) % R;
-        int hf = wide ? int(k) % C : int(k) / R;
-        ch0[vf * stride + hf] = vx;
-        ch1[vf * stride + hf] = vy;
-        ch2[vf * stride + hf] = vb;
-      }
-      __syncwarp();
       if (lane < 3) {  // LLF (group.rs:227-236, transform.rs:387-...)
         float* ch = wbuf + lane * kWarpBuf;
         const float* lf = lfp[lane] + size_t(by0 + by) * F.xb + bx0 + bx;
@@ -1639,14 +1670,6 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
       }
     } else {
       // special transforms work on the storage layout (64 coefficients, stride 8)
-      for (uint32_t k = lane; k < 64; k += 32) {
-        float vx, vy, vb;
-        dq.get(k, vx, vy, vb);
-        ch0[k] = vx;
-        ch1[k] = vy;
-        ch2[k] = vb;
-      }
-      __syncwarp();
       if (lane < 3) {
         float* ch = wbuf + lane * kWarpBuf;
         ch[0] = lfp[lane][size_t(by0 + by) * F.xb + bx0 + bx];
@@ -1677,42 +1700,68 @@ __global__ void __launch_bounds__(kIdctWarps * 32) k_dequant_idct(const BatchDev
     setup(bx, by, t, dq);
     const size_t px0 = (size_t(by0 + by) * 8) * F.plane_stride + size_t(bx0 + bx) * 8;
     const bool wide = R < C;
-    // The varblock's own pixel area doubles as its dense coefficient array (i32 view, coefficient k at the place the
-    // dequantised value goes): zero, add the list entries of every pass, then dequantise in place.
+    // The varblock's own pixel area is its coefficient array (coefficient k at the place its dequantised value goes):
+    // zero it, then write the non-zero entries dequantised — Y first (seeding X / B with cc * dy), then X and B with
+    // mul_add(cc, dy, d), group.rs:100-133 at every position. Frames with several passes add the passes up as integers
+    // in the same place first and convert afterwards.
     auto place = [&](uint32_t k) {
       const int vf = wide ? int(k) / C : int(k) % R, hf = wide ? int(k) % C : int(k) / R;
       return px0 + size_t(vf) * F.plane_stride + hf;
     };
-    int32_t* ip[3] = {reinterpret_cast<int32_t*>(planes[0]), reinterpret_cast<int32_t*>(planes[1]), reinterpret_cast<int32_t*>(planes[2])};
     for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
       const size_t o = place(k);
-      ip[0][o] = 0;
-      ip[1][o] = 0;
-      ip[2][o] = 0;
+      planes[0][o] = 0.0f;
+      planes[1][o] = 0.0f;
+      planes[2][o] = 0.0f;
     }
     __syncthreads();
     const uint32_t seq = block_off[bidx], lnc = 31 - __clz(dq.num_coeffs);
-    for (uint32_t p = 0; p < F.num_passes; p++) {
-      const uint32_t section = F.section_base + p * F.num_groups + g;
-      const uint32_t* base = list_base(B, section);
+    if (F.num_passes == 1) {
+      const uint32_t* base = list_base(B, F.section_base + g);
       const uint32_t* ow = base + kOffBase + seq * 3;
       const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2), o3 = min(__ldg(ow + 3), kListCap);
-      for (uint32_t i = o0 + threadIdx.x; i < o3; i += blockDim.x) {
-        const uint32_t e = __ldg(base + i);
-        const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);  // entries come as Y, X, B
-        ip[c][place(entry_pos(e, lnc))] += entry_value(e, lnc);
+      for (uint32_t i = o0 + threadIdx.x; i < o1; i += blockDim.x) {  // Y
+        const uint32_t e = __ldg(base + i), cpos = entry_pos(e, lnc);
+        const size_t o = place(cpos);
+        const float dy = adjust_quant_bias(entry_value(e, lnc), dq.bias1, dq.bias3) * (__ldg(dq.mat + dq.num_coeffs + cpos) * dq.sy);
+        planes[1][o] = dy;
+        planes[0][o] = dq.x_cc * dy;
+        planes[2][o] = dq.b_cc * dy;
+      }
+      __syncthreads();
+      for (uint32_t i = o1 + threadIdx.x; i < o3; i += blockDim.x) {  // X, then B
+        const uint32_t e = __ldg(base + i), cpos = entry_pos(e, lnc);
+        const size_t o = place(cpos);
+        const bool is_x = i < o2;
+        const uint32_t c = is_x ? 0u : 2u;
+        const float d = adjust_quant_bias(entry_value(e, lnc), is_x ? dq.bias0 : dq.bias2, dq.bias3) *
+                        (__ldg(dq.mat + c * dq.num_coeffs + cpos) * (is_x ? dq.sx : dq.sb));
+        planes[c][o] = fmaf(is_x ? dq.x_cc : dq.b_cc, planes[1][o], d);
+      }
+      __syncthreads();
+    } else {
+      int32_t* ip[3] = {reinterpret_cast<int32_t*>(planes[0]), reinterpret_cast<int32_t*>(planes[1]), reinterpret_cast<int32_t*>(planes[2])};
+      for (uint32_t p = 0; p < F.num_passes; p++) {
+        const uint32_t* base = list_base(B, F.section_base + p * F.num_groups + g);
+        const uint32_t* ow = base + kOffBase + seq * 3;
+        const uint32_t o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2), o3 = min(__ldg(ow + 3), kListCap);
+        for (uint32_t i = o0 + threadIdx.x; i < o3; i += blockDim.x) {
+          const uint32_t e = __ldg(base + i);
+          const uint32_t c = i < o1 ? 1u : (i < o2 ? 0u : 2u);  // entries come as Y, X, B
+          ip[c][place(entry_pos(e, lnc))] += entry_value(e, lnc);
+        }
+        __syncthreads();
+      }
+      for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
+        const size_t o = place(k);
+        float vx, vy, vb;
+        dq.get_q(k, ip[0][o], ip[1][o], ip[2][o], vx, vy, vb);
+        planes[0][o] = vx;
+        planes[1][o] = vy;
+        planes[2][o] = vb;
       }
       __syncthreads();
     }
-    for (uint32_t k = threadIdx.x; k < dq.num_coeffs; k += blockDim.x) {
-      const size_t o = place(k);
-      float vx, vy, vb;
-      dq.get_q(k, ip[0][o], ip[1][o], ip[2][o], vx, vy, vb);
-      planes[0][o] = vx;
-      planes[1][o] = vy;
-      planes[2][o] = vb;
-    }
-    __syncthreads();
     // LLF: rows then columns of the cy x cx LF samples, staged in shared memory.
     float* llf = smem;  // 3 * 32 * 33
     for (int r = threadIdx.x; r < 3 * cy; r += blockDim.x) {
@@ -1780,7 +1829,7 @@ __device__ __forceinline__ void transposeN(float* v, uint32_t r, uint32_t gmask)
 }
 
 struct RegBlockCtx {
-  const int32_t* coeffs;  // the varblock's coefficient tile in shared memory: channel c at coeffs + c * cstride
+  const float* coeffs;  // the varblock's dequantised coefficient tile in shared memory: channel c at coeffs + c * cstride
   uint32_t cstride;
   const float* mat;       // dequant matrix of the block's table (channel 0)
   float* plane;           // plane set base (channel 0) + pixel offset of the block
@@ -1789,6 +1838,10 @@ struct RegBlockCtx {
   uint32_t num_coeffs;
   float sx, sy, sb, x_cc, b_cc, bias0, bias1, bias2, bias3;
 };
+
+__device__ __forceinline__ DeqParams deq_of(const RegBlockCtx& X) {
+  return DeqParams{X.mat, X.num_coeffs, X.sx, X.sy, X.sb, X.x_cc, X.b_cc, X.bias0, X.bias1, X.bias2, X.bias3};
+}
 
 // One plain-DCT varblock of min(R,C) = NT storage rows x max(R,C) = L entries, NT threads (lanes r = 0..NT-1 of
 // an aligned lane group). TALL: rows >= cols, storage [hf][vf]; else storage [vf][hf] (tests.rs:123-136).
@@ -1801,31 +1854,14 @@ __device__ __forceinline__ void reg_dct_block(const RegBlockCtx& X, const float*
   for (int c = 0; c < 3; c++) {
     float w[L];
     {
-      const int4* qc = reinterpret_cast<const int4*>(X.coeffs + c * X.cstride + r * L);
-      const int4* qy = reinterpret_cast<const int4*>(X.coeffs + X.cstride + r * L);
-      const float4* mc = reinterpret_cast<const float4*>(X.mat + size_t(c) * X.num_coeffs + r * L);
-      const float4* my = reinterpret_cast<const float4*>(X.mat + X.num_coeffs + r * L);
-      const float sc = c == 0 ? X.sx : (c == 1 ? X.sy : X.sb);
-      const float bc = c == 0 ? X.bias0 : (c == 1 ? X.bias1 : X.bias2);
-      const float cc = c == 0 ? X.x_cc : (c == 1 ? 0.0f : X.b_cc);
+      const float4* tc = reinterpret_cast<const float4*>(X.coeffs + c * X.cstride + r * L);  // storage row r of channel c
 #pragma unroll
       for (int j4 = 0; j4 < L / 4; j4++) {
-        const int4 q = qc[j4];
-        const float4 m = __ldg(mc + j4);
-        float d0 = adjust_quant_bias(q.x, bc, X.bias3) * (m.x * sc), d1 = adjust_quant_bias(q.y, bc, X.bias3) * (m.y * sc);
-        float d2 = adjust_quant_bias(q.z, bc, X.bias3) * (m.z * sc), d3 = adjust_quant_bias(q.w, bc, X.bias3) * (m.w * sc);
-        if (c != 1) {  // chroma from luma: recompute the dequantised Y coefficient (group.rs:128-130)
-          const int4 y = qy[j4];
-          const float4 n = __ldg(my + j4);
-          d0 = fmaf(cc, adjust_quant_bias(y.x, X.bias1, X.bias3) * (n.x * X.sy), d0);
-          d1 = fmaf(cc, adjust_quant_bias(y.y, X.bias1, X.bias3) * (n.y * X.sy), d1);
-          d2 = fmaf(cc, adjust_quant_bias(y.z, X.bias1, X.bias3) * (n.z * X.sy), d2);
-          d3 = fmaf(cc, adjust_quant_bias(y.w, X.bias1, X.bias3) * (n.w * X.sy), d3);
-        }
-        w[4 * j4] = d0;
-        w[4 * j4 + 1] = d1;
-        w[4 * j4 + 2] = d2;
-        w[4 * j4 + 3] = d3;
+        const float4 t = tc[j4];
+        w[4 * j4] = t.x;
+        w[4 * j4 + 1] = t.y;
+        w[4 * j4 + 2] = t.z;
+        w[4 * j4 + 3] = t.w;
       }
     }
     // LLF: rows < (TALL ? CX : CY), entries < (TALL ? CY : CX)
@@ -1907,7 +1943,7 @@ constexpr size_t small_smem_bytes() {
 
 template <int KIND>
 __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small(const BatchDev B) {
-  extern __shared__ __align__(16) int32_t s_tiles[];
+  extern __shared__ __align__(16) float s_tiles[];
   __shared__ uint16_t s_list[1024];
   __shared__ uint32_t s_cnt[28], s_start[28], s_fill[28];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -1916,7 +1952,7 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
   const StreamDev sd = B.streams[stream];
   const FrameDev& F = B.frames[sd.frame];
   const uint32_t g = sd.group;
-  uint32_t* const s_off = reinterpret_cast<uint32_t*>(s_tiles) + small_tile_bytes<KIND>() / 4;
+  uint32_t* const s_off = reinterpret_cast<uint32_t*>(s_tiles + small_tile_bytes<KIND>() / 4);
   uint32_t* const s_ent = s_off + kOffWords;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar[0], 1);
@@ -2003,8 +2039,9 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       uint32_t seq;
       setup_ctx(s_list[begin8 + (valid ? li : 0)], X, lfp, t, seq);
       constexpr uint32_t NC = KIND == 0 ? 64 : (KIND == 1 ? 128 : 256);
-      int32_t* tile = s_tiles + (threadIdx.x >> 3) * 3 * NC;
-      gather_block_tile(B, F, g, seq, tile, NC, r, 8, gmask, valid, stage);
+      float* tile = s_tiles + (threadIdx.x >> 3) * 3 * NC;
+      gather_dequant_tile(B, F, g, seq, tile, NC, NC, deq_of(X), r, 8, valid, stage, [&] { __syncwarp(gmask); },
+                          [](uint32_t pos) { return pos; });
       X.coeffs = tile;
       X.cstride = NC;
       if constexpr (KIND == 1) {
@@ -2018,29 +2055,12 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       } else {
         // DCT4x4 / DCT4x8 / DCT8x4: all three channels at once (64 coefficients each)
         float v[3][8];
-        {
-          int q[3][8];
-          float m[3][8];
 #pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const int4* qp = reinterpret_cast<const int4*>(X.coeffs + c * X.cstride + r * 8);
-            const int4 a = qp[0], b = qp[1];
-            q[c][0] = a.x; q[c][1] = a.y; q[c][2] = a.z; q[c][3] = a.w;
-            q[c][4] = b.x; q[c][5] = b.y; q[c][6] = b.z; q[c][7] = b.w;
-            const float4* mp = reinterpret_cast<const float4*>(X.mat + c * 64 + r * 8);
-            const float4 ma = __ldg(mp), mb = __ldg(mp + 1);
-            m[c][0] = ma.x; m[c][1] = ma.y; m[c][2] = ma.z; m[c][3] = ma.w;
-            m[c][4] = mb.x; m[c][5] = mb.y; m[c][6] = mb.z; m[c][7] = mb.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; j++) {  // group.rs:100-133
-            const float dy = adjust_quant_bias(q[1][j], bias1, bias3) * (m[1][j] * X.sy);
-            const float dxc = adjust_quant_bias(q[0][j], bias0, bias3) * (m[0][j] * X.sx);
-            const float dbc = adjust_quant_bias(q[2][j], bias2, bias3) * (m[2][j] * X.sb);
-            v[1][j] = dy;
-            v[0][j] = fmaf(X.x_cc, dy, dxc);
-            v[2][j] = fmaf(X.b_cc, dy, dbc);
-          }
+        for (int c = 0; c < 3; c++) {  // storage row r of the dequantised tile
+          const float4* tp = reinterpret_cast<const float4*>(X.coeffs + c * X.cstride + r * 8);
+          const float4 a = tp[0], b = tp[1];
+          v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+          v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -2123,8 +2143,9 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       setup_ctx(s_list[begin16 + (valid ? li : 0)], X, lfp, t, seq);
       constexpr uint32_t NC = KIND == 1 ? 256 : 512;
       if constexpr (KIND >= 1) {
-        int32_t* tile = s_tiles + (threadIdx.x >> 4) * 3 * NC;
-        gather_block_tile(B, F, g, seq, tile, NC, r, 16, gmask, valid, stage);
+        float* tile = s_tiles + (threadIdx.x >> 4) * 3 * NC;
+        gather_dequant_tile(B, F, g, seq, tile, NC, NC, deq_of(X), r, 16, valid, stage, [&] { __syncwarp(gmask); },
+                            [](uint32_t pos) { return pos; });
         X.coeffs = tile;
         X.cstride = NC;
       }
@@ -2150,8 +2171,9 @@ __global__ void __launch_bounds__(kSmallThreads, KIND == 0 ? 3 : 2) k_idct_small
       uint32_t seq;
       setup_ctx(s_list[begin32 + (valid ? li : 0)], X, lfp, t, seq);
       if constexpr (KIND == 2) {
-        int32_t* tile = s_tiles + (threadIdx.x >> 5) * 3 * 1024;
-        gather_block_tile(B, F, g, seq, tile, 1024, r, 32, 0xffffffffu, valid, stage);
+        float* tile = s_tiles + (threadIdx.x >> 5) * 3 * 1024;
+        gather_dequant_tile(B, F, g, seq, tile, 1024, 1024, deq_of(X), r, 32, valid, stage, [&] { __syncwarp(); },
+                            [](uint32_t pos) { return pos; });
         X.coeffs = tile;
         X.cstride = 1024;
         reg_dct_block<32, 32, true>(X, lfp, F.xb, r, 0xffffffffu, valid);
