@@ -148,6 +148,11 @@ typedef struct JxgFrameDesc {
  * threads and pinned allocations to the GPU's NUMA node before jxg_init. buf: >= 16 bytes. */
 int jxg_device_pci_bus_id(int device, char* buf, int len);
 
+/* Batches run without an explicit stream are pipelined over two streams shared by all contexts of the device: upload +
+ * entropy decode of batch k + 1 on the first, transforms + filters + stores of batch k on the second (one kernel of each
+ * kind at a time, sharing every SM). This returns them, e.g. to record timing events around a sequence of batches. */
+int jxg_device_streams(int device, void** entropy_stream, void** post_stream);
+
 /* Context: one per device/rank. Owns streams, pinned staging and device pools. */
 int jxg_init(int device, void** ctx);
 void jxg_shutdown(void* ctx);

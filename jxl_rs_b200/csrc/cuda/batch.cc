@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,20 @@ using namespace jxgpu;
 namespace jxgpu {
 namespace detail {
 thread_local std::string g_error;
+DeviceStreams device_streams(int device) {
+  static std::mutex mu;
+  static DeviceStreams table[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64) return DeviceStreams{};
+  DeviceStreams& d = table[device];
+  if (!d.entropy) {
+    cudaSetDevice(device);
+    if (cudaStreamCreateWithFlags(&d.entropy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d.post, cudaStreamNonBlocking) != cudaSuccess)
+      d = DeviceStreams{};
+  }
+  return d;
+}
 }
 }  // namespace jxgpu
 using namespace jxgpu::detail;
@@ -81,7 +96,8 @@ struct Batch {
   const float* final_planes = nullptr;
   int32_t* status_host = nullptr;  // pinned (context-owned): a D2H copy into pageable memory would block jxg_batch_run
   size_t status_n = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_handoff = nullptr;
+  bool copies_on_copy_stream = false;  // last run: the D2H copies went to the context's copy stream
   cudaStream_t last_stream = nullptr;  // stream of the last run / rerun (the context's or the caller's)
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
@@ -176,6 +192,15 @@ int jxg_device_pci_bus_id(int device, char* buf, int len) {
   return JXG_OK;
 }
 
+// The device's stage streams (see DeviceStreams), for hosts that want to bracket batches with their own events.
+int jxg_device_streams(int device, void** entropy_stream, void** post_stream) {
+  const DeviceStreams ds = device_streams(device);
+  if (!ds.entropy) return set_error(JXG_ERR_CUDA, "cannot create the device's stage streams");
+  if (entropy_stream) *entropy_stream = ds.entropy;
+  if (post_stream) *post_stream = ds.post;
+  return JXG_OK;
+}
+
 int jxg_init(int device, void** out_ctx) {
   if (!out_ctx) return JXG_ERR_ARGUMENT;
   int n = 0;
@@ -255,6 +280,11 @@ int jxg_batch_begin(void* c, uint32_t n_frames_hint, void** out_batch) {
     cudaEventDestroy(b->ev0);
     return set_error(JXG_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
   }
+  if (cudaError_t e = cudaEventCreateWithFlags(&b->ev_handoff, cudaEventDisableTiming); e != cudaSuccess) {
+    cudaEventDestroy(b->ev0);
+    cudaEventDestroy(b->ev1);
+    return set_error(JXG_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+  }
   cx->batch_live = true;  // only once nothing can fail any more
   *out_batch = b.release();
   return JXG_OK;
@@ -264,9 +294,10 @@ void jxg_batch_end(void* bp) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b) return;
   cudaSetDevice(b->ctx->device);
-  cudaStreamSynchronize(b->ctx->stream);
+  if (b->uploaded && b->ev1) cudaEventSynchronize(b->ev1);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev_handoff) cudaEventDestroy(b->ev_handoff);
   for (auto& e : b->stage_ev)
     if (e) cudaEventDestroy(e);
   b->ctx->batch_live = false;
@@ -286,7 +317,7 @@ int jxg_batch_set_profile(void* bp, int on) {
 int jxg_batch_stage_times(void* bp, float* ms, int n) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b || !ms || n < kNumStages || !b->profile) return JXG_ERR_ARGUMENT;
-  CUDA_TRY(cudaStreamSynchronize(b->last_stream ? b->last_stream : b->ctx->stream));
+  CUDA_TRY(cudaEventSynchronize(b->ev1));
   for (int i = 0; i < kNumStages; i++) {
     ms[i] = 0.0f;
     if (cudaEventElapsedTime(&ms[i], b->stage_ev[i], b->stage_ev[i + 1]) != cudaSuccess) ms[i] = 0.0f;
@@ -644,16 +675,23 @@ static BatchDev make_batch_dev(Batch* b) {
   return B;
 }
 
-static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
+// se: stream of the upload, block plan and entropy kernels; s: stream of everything after them (== se when the caller
+// brought its own stream).
+static int launch(Batch* b, cudaStream_t se, cudaStream_t s, bool copy_to_host) {
   const BatchDev B = make_batch_dev(b);
   auto tab = [&](uint64_t off) { return static_cast<const uint8_t*>(b->d_blob.p) + off; };
   size_t coeff_bytes = 0;
   cudaEvent_t* ev = b->profile ? b->stage_ev : nullptr;
   b->launches = uint64_t(launch_pipeline(B, reinterpret_cast<const uint32_t*>(tab(b->tab.tiles)), b->tile_prefix.back(), b->max_epf,
-                                         b->any_gab, s, coeff_bytes, &b->final_planes, b->debug_stop, ev,
+                                         b->any_gab, se, coeff_bytes, &b->final_planes, b->debug_stop, ev,
                                          reinterpret_cast<const uint32_t*>(tab(b->tab.ftiles)), b->fused_prefix.back(),
                                          b->filter_cfg_mask, b->lean_all_420, b->lean_S, b->lean_ctas,
-                                         b->lean_ctx_smem && !(getenv("JXG_LEAN_CTX_SMEM") && atoi(getenv("JXG_LEAN_CTX_SMEM")) == 0)));
+                                         b->lean_ctx_smem && !(getenv("JXG_LEAN_CTX_SMEM") && atoi(getenv("JXG_LEAN_CTX_SMEM")) == 0),
+                                         s, b->ev_handoff));
+  if (b->debug_stop == 1 && s != se) {  // stopped after the entropy stage: the post stream still has to cover it
+    cudaEventRecord(b->ev_handoff, se);
+    cudaStreamWaitEvent(s, b->ev_handoff, 0);
+  }
   if (b->debug_stop == 0) {
     // Fused filter + colour + store, launched per range of frames; each finished range is copied to the host
     // on the copy stream while the next range is being filtered.
@@ -700,10 +738,7 @@ static int launch(Batch* b, cudaStream_t s, bool copy_to_host) {
       cudaEventRecord(ev[7], s);
       cudaEventRecord(ev[8], s);
     }
-    if (copy_to_host && !same_stream) {  // the launching stream joins the copy stream so that ev1 / stream sync cover the copies
-      CUDA_TRY(cudaEventRecord(cx->copy_done, cx->copy_stream));
-      CUDA_TRY(cudaStreamWaitEvent(s, cx->copy_done, 0));
-    }
+    b->copies_on_copy_stream = copy_to_host && !same_stream;
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -738,7 +773,12 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (!b || b->frames.empty()) return JXG_ERR_ARGUMENT;
   RunTrace trace;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  // the caller's stream for everything, or the device's stage streams (see DeviceStreams)
+  const DeviceStreams ds = device_streams(b->ctx->device);
+  static const bool staged = !(getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) == 0);
+  const bool use_pair = !cuda_stream && staged && ds.entropy;
+  cudaStream_t se = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : (use_pair ? ds.entropy : b->ctx->stream);
+  cudaStream_t s = cuda_stream ? se : (use_pair ? ds.post : b->ctx->stream);
   b->last_stream = s;
   b->h2d = b->d2h = 0;
   schedule_lean(b);
@@ -793,16 +833,35 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   trace.mark("alloc");
   b->blob.flush();
   trace.mark("flush");
-  CUDA_TRY(cudaEventRecord(b->ev0, s));
-  CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, s));
+  if (use_pair) {
+    // the upload rides on the context's own stream so that it overlaps the entropy kernel of the batch before;
+    // the entropy stream picks it up through the hand-off event (free again once launch() re-records it)
+    CUDA_TRY(cudaEventRecord(b->ev0, b->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, b->ctx->stream));
+    CUDA_TRY(cudaEventRecord(b->ev_handoff, b->ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(se, b->ev_handoff, 0));
+  } else {
+    CUDA_TRY(cudaEventRecord(b->ev0, se));
+    CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, se));
+  }
   trace.mark("blob_h2d");
   b->h2d += b->blob.size;
   b->uploaded = true;
   trace.mark("uploads");
-  if (int r = launch(b, s, true)) return r;
+  b->copies_on_copy_stream = false;
+  if (int r = launch(b, se, s, true)) return r;
   trace.mark("launch");
   if (int r = copy_status(b, s)) return r;
-  CUDA_TRY(cudaEventRecord(b->ev1, s));
+  // ev1 = everything of this batch done. The copy stream joins the post stream and carries ev1 when it holds the D2H
+  // copies: the post stream itself must not wait for them (the next batch's transforms follow on it).
+  if (b->copies_on_copy_stream) {
+    Context* cx = b->ctx;
+    CUDA_TRY(cudaEventRecord(cx->copy_done, s));
+    CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->copy_done, 0));
+    CUDA_TRY(cudaEventRecord(b->ev1, cx->copy_stream));
+  } else {
+    CUDA_TRY(cudaEventRecord(b->ev1, s));
+  }
   trace.mark("status");
   return JXG_OK;
 }
@@ -811,12 +870,17 @@ int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b || !b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch was never submitted");
   CUDA_TRY(cudaSetDevice(b->ctx->device));
-  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->ctx->stream;
+  const DeviceStreams ds = device_streams(b->ctx->device);
+  static const bool staged = !(getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) == 0);
+  const bool use_pair = !cuda_stream && staged && ds.entropy;
+  cudaStream_t se = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : (use_pair ? ds.entropy : b->ctx->stream);
+  cudaStream_t s = cuda_stream ? se : (use_pair ? ds.post : b->ctx->stream);
   b->last_stream = s;
-  CUDA_TRY(cudaEventRecord(b->ev0, s));
-  if (int r = launch(b, s, false)) return r;
-  CUDA_TRY(cudaEventRecord(b->ev1, s));
+  CUDA_TRY(cudaStreamWaitEvent(se, b->ev1, 0));  // the previous run of this batch still owns its device buffers
+  CUDA_TRY(cudaEventRecord(b->ev0, se));
+  if (int r = launch(b, se, s, false)) return r;
   CUDA_TRY(cudaMemcpyAsync(b->status_host, b->d_status.p, b->status_n * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(b->ev1, s));
   return JXG_OK;
 }
 
@@ -824,8 +888,8 @@ int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_grou
   Batch* b = static_cast<Batch*>(bp);
   if (!b) return JXG_ERR_ARGUMENT;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
-  CUDA_TRY(cudaEventSynchronize(b->ev1));
-  CUDA_TRY(cudaStreamSynchronize(b->last_stream ? b->last_stream : b->ctx->stream));  // the status words follow ev1
+  CUDA_TRY(cudaEventSynchronize(b->ev1));  // recorded behind the status words and the D2H copies; no stream-wide wait:
+                                           // the stage streams carry later batches too
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
   for (size_t i = 0; i < b->status_n; i++)

@@ -108,6 +108,17 @@ struct PinnedArena {
   }
 };
 
+// Two streams per DEVICE shared by all its contexts: every batch runs its upload, block plan and entropy kernels on the
+// entropy stream and its transforms, filters and stores on the post stream. Entropy decode is a latency-bound one-wave
+// kernel that leaves ~60 % of the issue slots and half the registers of every SM idle; the filters are throughput work.
+// With one stream per batch, two entropy kernels of different batches end up co-resident and lock the filters of a
+// third out of the register file (profiles/r02g_e2e_variants.log); with the stage streams at most one kernel of each
+// kind runs at a time and they share every SM: steady-state step = max(entropy, transforms + filters), not their sum.
+struct DeviceStreams {
+  cudaStream_t entropy = nullptr, post = nullptr;
+};
+DeviceStreams device_streams(int device);  // created on first use
+
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;

@@ -3180,7 +3180,8 @@ cudaError_t configure_kernels() {
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
                     bool any_gab, cudaStream_t stream, size_t coeff_bytes, const float** final_planes, int debug_stop,
                     cudaEvent_t* ev, const uint32_t* fused_prefix, uint32_t fused_tiles, uint32_t filter_cfg_mask,
-                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas, bool lean_ctx_smem) {
+                    bool lean_all_420, uint32_t lean_S, uint32_t lean_ctas, bool lean_ctx_smem, cudaStream_t post_stream,
+                    cudaEvent_t handoff) {
   // ev (optional, kNumStages + 1 events): ev[i] is recorded before stage i, ev[i+1] after it; stages that do not
   // run record nothing (the host pairs consecutive recorded events).
   int launches = 0;
@@ -3233,6 +3234,11 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   mark(2);
   if (final_planes) *final_planes = B.planes_a;
   if (debug_stop == 1) return launches;
+  if (post_stream != stream) {  // two-stage pipeline: the transforms and filters of this batch continue on the post stream
+    cudaEventRecord(handoff, stream);
+    cudaStreamWaitEvent(post_stream, handoff, 0);
+    stream = post_stream;
+  }
   k_idct_small<0><<<B.num_streams, kSmallThreads, small_smem_bytes<0>(), stream>>>(B);
   k_idct_small<1><<<B.num_streams, kSmallThreads, small_smem_bytes<1>(), stream>>>(B);
   if (B.reg_idct32) k_idct_small<2><<<B.num_streams, kSmallThreads, small_smem_bytes<2>(), stream>>>(B);

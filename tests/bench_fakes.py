@@ -29,6 +29,9 @@ def install(setattr_fn, fail_e2e=False, gloo=False):
     setattr_fn(torch.cuda, "synchronize", lambda *a, **k: None)
     setattr_fn(torch.cuda, "Stream", _FakeStream)
     setattr_fn(torch.cuda, "Event", _FakeEvent)
+    setattr_fn(torch.cuda, "ExternalStream", lambda ptr, *a, **k: _FakeStream())
+    for mod in (decoder, j):
+        setattr_fn(mod, "device_streams", lambda device=0: (1, 2))
     setattr_fn(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
     real_empty, real_tensor = torch.empty, torch.tensor
     setattr_fn(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
