@@ -49,7 +49,7 @@ def parse_args():
                          "workload), 1 = libjxl-like weighted-predictor tree (3x the host front-end work per frame)")
     ap.add_argument("--unique", type=int, default=0, help="encode only this many distinct frames and repeat them (0 = all distinct)")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
-    ap.add_argument("--inflight", type=int, default=2, help="resident batches alternated by the device-resident loop")
+    ap.add_argument("--inflight", type=int, default=3, help="resident batches alternated by the device-resident loop")
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the pipelined end-to-end decode")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -427,32 +427,41 @@ def main():
         b.wait()
         batches.append(b)
     batch = batches[0]
-    # The resident batches run through the library's two stage streams (entropy decode of batch k + 1 next to the transforms
-    # and filters of batch k); the timing events are recorded on those streams.
-    e_ptr, p_ptr = j.device_streams(local_rank)
-    es, ps = torch.cuda.ExternalStream(e_ptr), torch.cuda.ExternalStream(p_ptr)
+    # Every resident batch runs on its own torch stream (JXG_STAGE_STREAMS=1: on the library's two stage streams), so that
+    # torch events bracket the kernels on the launching streams.
+    staged = os.environ.get("JXG_STAGE_STREAMS", "0") not in ("", "0")
+    if staged:
+        e_ptr, p_ptr = j.device_streams(local_rank)
+        first_stream, last_streams = torch.cuda.ExternalStream(e_ptr), [torch.cuda.ExternalStream(p_ptr)]
+        sptrs = [0] * depth
+    else:
+        streams = [torch.cuda.Stream(device=local_rank) for _ in range(depth)]
+        first_stream, last_streams = streams[0], streams
+        sptrs = [st_.cuda_stream for st_ in streams]
     for i in range(args.warmup):
-        batches[i % depth].rerun_device()
+        batches[i % depth].rerun_device(sptrs[i % depth])
     for b in batches:
         b.wait()
-    # per-stage times of one batch running alone (CUDA events on the launching streams)
-    batch.rerun_device()
+    # per-stage times of one batch running alone (CUDA events on the launching stream)
+    batch.rerun_device(sptrs[0])
     batch.wait()
     stage_acc = batch.stage_times()
     single_ms = batch.stats()["device_ms"]
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev_end = [torch.cuda.Event(enable_timing=True) for _ in last_streams]
     torch.cuda.synchronize()
-    ev0.record(es)  # the device is idle: this is the start of all K steps
+    ev0.record(first_stream)  # the device is idle: this is the start of all K steps
     for i in range(args.steps):
-        batches[i % depth].rerun_device()
-    ev_end.record(ps)  # behind the stores of the last step (the post stream is in order)
+        batches[i % depth].rerun_device(sptrs[i % depth])
+    for e, st_ in zip(ev_end, last_streams):
+        e.record(st_)
     for b in batches:
         b.wait()
     torch.cuda.synchronize()
-    dev_ms = ev0.elapsed_time(ev_end)  # first launch to the last kernel of the last step, device clock
+    dev_ms = max(ev0.elapsed_time(e) for e in ev_end)  # first launch to the last kernel of the last step, device clock
     clocks = sampler.stop()
     st = batch.stats()
     launches_per_step = st["kernel_launches"]

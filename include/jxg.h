@@ -200,6 +200,9 @@ int jxg_batch_set_debug_stop(void* batch, int stage);
  * stages = memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store. */
 int jxg_batch_set_profile(void* batch, int on);
 int jxg_batch_stage_times(void* batch, float* ms, int n);
+/* Absolute device times (ms since a process-wide reference event set at the first call) of the 9 stage events of the
+ * last run: the timeline of several batches in flight. */
+int jxg_batch_stage_marks(void* batch, float* ms, int n);
 
 /* Counters for bench.py (kernels launched by the last run, bytes moved). */
 int jxg_batch_stats(void* batch, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes,

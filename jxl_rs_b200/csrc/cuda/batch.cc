@@ -326,6 +326,25 @@ int jxg_batch_stage_times(void* bp, float* ms, int n) {
   return JXG_OK;
 }
 
+// Absolute device times of the stage events of the last run, in ms since a process-wide reference event (recorded at the
+// first call): ms[i] = time of event i (before stage i; ms[kNumStages] = end), 0 for events that were not recorded.
+// Lets a host draw the timeline of several batches in flight (tools/e2e_profile4.py).
+int jxg_batch_stage_marks(void* bp, float* ms, int n) {
+  Batch* b = static_cast<Batch*>(bp);
+  if (!b || !ms || n < kNumStages + 1 || !b->profile) return JXG_ERR_ARGUMENT;
+  static cudaEvent_t ref = nullptr;
+  if (!ref) {
+    CUDA_TRY(cudaEventCreate(&ref));
+    CUDA_TRY(cudaEventRecord(ref, 0));
+    CUDA_TRY(cudaEventSynchronize(ref));
+  }
+  CUDA_TRY(cudaEventSynchronize(b->ev1));
+  for (int i = 0; i <= kNumStages; i++)
+    if (cudaEventElapsedTime(&ms[i], ref, b->stage_ev[i]) != cudaSuccess) ms[i] = 0.0f;
+  cudaGetLastError();
+  return JXG_OK;
+}
+
 // Opt-in: copies of large inputs (LF planes, maps, HF sections) into the pinned staging blob are postponed to
 // jxg_batch_run and spread over `threads` host threads. Every pointer handed to jxg_batch_add_frame /
 // jxg_batch_add_parsed must then stay valid until jxg_batch_run returns.
@@ -580,9 +599,9 @@ static void schedule_lean(Batch* b) {
     b->frames[f].lean_count = uint32_t(j - i);
     i = j;
   }
-  // The kernel keeps 8 CTAs per SM resident (64 registers per thread); a grid beyond one resident wave would start its
-  // last CTAs only when the first ones end, so the packing is made denser until the grid fits.
-  const uint32_t max_ctas = 148 * 8;
+  // The kernel keeps 6 CTAs per SM resident (register bound); a grid beyond one resident wave would start its last
+  // CTAs only when the first ones end, so the packing is made denser until the grid fits.
+  const uint32_t max_ctas = 148 * 6;
   uint32_t S = 4;
   if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
   S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
@@ -775,7 +794,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   // the caller's stream for everything, or the device's stage streams (see DeviceStreams)
   const DeviceStreams ds = device_streams(b->ctx->device);
-  static const bool staged = !(getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) == 0);
+  static const bool staged = getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) != 0;
   const bool use_pair = !cuda_stream && staged && ds.entropy;
   cudaStream_t se = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : (use_pair ? ds.entropy : b->ctx->stream);
   cudaStream_t s = cuda_stream ? se : (use_pair ? ds.post : b->ctx->stream);
@@ -871,7 +890,7 @@ int jxg_batch_rerun_device(void* bp, void* cuda_stream) {
   if (!b || !b->uploaded) return set_error(JXG_ERR_ARGUMENT, "batch was never submitted");
   CUDA_TRY(cudaSetDevice(b->ctx->device));
   const DeviceStreams ds = device_streams(b->ctx->device);
-  static const bool staged = !(getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) == 0);
+  static const bool staged = getenv("JXG_STAGE_STREAMS") && atoi(getenv("JXG_STAGE_STREAMS")) != 0;
   const bool use_pair = !cuda_stream && staged && ds.entropy;
   cudaStream_t se = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : (use_pair ? ds.entropy : b->ctx->stream);
   cudaStream_t s = cuda_stream ? se : (use_pair ? ds.post : b->ctx->stream);

@@ -108,12 +108,12 @@ struct PinnedArena {
   }
 };
 
-// Two streams per DEVICE shared by all its contexts: every batch runs its upload, block plan and entropy kernels on the
-// entropy stream and its transforms, filters and stores on the post stream. Entropy decode is a latency-bound one-wave
-// kernel that leaves ~60 % of the issue slots and half the registers of every SM idle; the filters are throughput work.
-// With one stream per batch, two entropy kernels of different batches end up co-resident and lock the filters of a
-// third out of the register file (profiles/r02g_e2e_variants.log); with the stage streams at most one kernel of each
-// kind runs at a time and they share every SM: steady-state step = max(entropy, transforms + filters), not their sum.
+// Optional (JXG_STAGE_STREAMS=1): two streams per DEVICE shared by all its contexts — every batch runs its block plan and
+// entropy kernels on the entropy stream and its transforms, filters and stores on the post stream, so that at most one
+// kernel of each kind runs at a time. Measured slower than one stream per batch on B200 (53 - 56 against 44 - 50 ms per
+// 64-frame step, profiles/r02h_stage_stream_sweep.log): the entropy kernel parks ~30 K of an SM's 64 K registers for its
+// whole duration, so the transforms / filters beside it run at one CTA per SM, and nothing is gained over letting
+// batches overlap in the entropy kernel's tail. The default is one stream per batch.
 struct DeviceStreams {
   cudaStream_t entropy = nullptr, post = nullptr;
 };

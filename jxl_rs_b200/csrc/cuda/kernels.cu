@@ -786,13 +786,11 @@ __device__ __forceinline__ uint32_t spec_lds_u16(uint32_t addr) {
 }
 
 // CTXS: the frame's context map fits the shared-memory staging area (host decision for the whole batch).
-// 64 registers per thread (launch bound 8 CTAs / SM, no spills): a 64-frame batch occupies ~3.7 CTAs = 30 K of an SM's
-// 64 K registers for the whole duration of its serial chains, which leaves room for a filter CTA (512 threads x 60
-// registers) or transform CTAs of ANOTHER batch on the same SM. With the 78 registers the compiler takes when left alone
-// the filter kernel does not fit next to it and batches in flight only overlap in this kernel's tail
-// (profiles/r02f_inflight_sweep.log).
+// Launch bound 6 CTAs / SM (<= 85 registers; the compiler takes 71 - 78). A 64-register build (bound 8) is 3 ms slower
+// per 64-frame batch (35.2 against 32.1 ms) and did not buy co-residency with the filters of other batches: measured in
+// profiles/r02h_stage_stream_sweep.log.
 template <int S, bool K420, bool CTXS>
-__global__ void __launch_bounds__(128, 8) k_entropy_lean(const BatchDev B) {
+__global__ void __launch_bounds__(128, 6) k_entropy_lean(const BatchDev B) {
   // context LUTs, pre-multiplied by 2 (block_context_map.rs:34-46), natural-order table offsets
   __shared__ uint16_t s_nz2[64], s_fr2[64];
   __shared__ uint32_t s_order_off[13];

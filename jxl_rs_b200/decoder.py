@@ -122,6 +122,12 @@ class Batch:
         abi.check(self._lib, self._lib.jxg_batch_stage_times(self._h, ms, 8))
         return dict(zip(self.STAGES, [float(v) for v in ms]))
 
+    def stage_marks(self):
+        """Absolute device times (ms) of the 9 stage events of the last run (jxg_batch_stage_marks)."""
+        ms = (C.c_float * 9)()
+        abi.check(self._lib, self._lib.jxg_batch_stage_marks(self._h, ms, 9))
+        return [float(v) for v in ms]
+
     def run(self, stream_ptr: int = 0):
         abi.check(self._lib, self._lib.jxg_batch_run(self._h, C.c_void_p(stream_ptr)))
 
@@ -301,6 +307,7 @@ class PipelinedDecoder:
         self._ahead = threading.Semaphore(depth + parse_ahead)  # bounds parsed-but-not-yet-launched batches
         self._error = None
         self.trace = None  # set to [] to record the dispatcher timeline
+        self.marks = None  # set to [] to record the device timeline of every batch (stage event times)
         self._thread = threading.Thread(target=self._dispatch, daemon=True)
         self._thread.start()
 
@@ -309,6 +316,8 @@ class PipelinedDecoder:
         try:
             b.wait()
             self.last_stats = b.stats()
+            if self.marks is not None:
+                self.marks.append(b.stage_marks())
         finally:
             b.close()
 
@@ -321,6 +330,8 @@ class PipelinedDecoder:
         ctx = self.ctxs[self.k % self.depth]
         self.k += 1
         b = Batch(ctx, len(futs), self.staging_threads)
+        if self.marks is not None:
+            b.set_profile(True)
         try:
             frames = [fut.result() for fut in futs]
             t2 = time.perf_counter()

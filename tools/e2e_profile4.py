@@ -18,6 +18,7 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
         dec.submit(files, outs[i % depth])
     dec.drain()
     dec.trace = []
+    dec.marks = [] if os.environ.get("E2E_MARKS") else None
     t0 = time.perf_counter()
     for i in range(steps):
         dec.submit(files, outs[i % depth])
@@ -27,4 +28,9 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     print(f"staging_threads={st}: {dt/steps*1e3:.1f} ms/step, {n*3840*2160/1e6*steps/dt:.0f} MP/s")
     for (ts, ret, pw, add, run) in dec.trace:
         print(f"  t={1e3*(ts-t0):7.1f}  retire {ret*1e3:6.1f}  parsewait {pw*1e3:6.1f}  add {add*1e3:6.1f}  run {run*1e3:6.1f}")
+    if dec.marks:
+        base = min(m[0] for m in dec.marks if m[0] > 0)
+        print("  device timeline (ms): start | entropy begin..end | transforms end | filters+D2H launches end")
+        for m in dec.marks:
+            print("   ", " ".join(f"{(v - base):8.1f}" if v > 0 else "       -" for v in m))
     dec.close()
