@@ -3172,7 +3172,46 @@ cudaError_t configure_kernels() {
   if ((e = cudaFuncSetAttribute(k_idct_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<0>()))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_idct_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<1>()))) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_idct_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem_bytes<2>()))) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLargeSmemBytes));
+  if ((e = cudaFuncSetAttribute(k_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLargeSmemBytes))) != cudaSuccess) return e;
+  // One shared-memory carve-out for every kernel of the pipeline. An SM can only change its L1 / shared-memory split when
+  // it is empty, so a filter CTA (92 KB) or transform CTA (68 - 101 KB) of one batch cannot join an SM that still holds
+  // entropy CTAs of another batch launched with a small carve-out: kernels of different streams then only overlap in the
+  // entropy kernel's tail. JXG_CARVEOUT = percentage of the unified memory given to shared memory (default 100 = max shared, -1 =
+  // leave the driver's per-kernel choice).
+  int pct = 100;
+  if (const char* env = getenv("JXG_CARVEOUT")) pct = atoi(env);
+  if (pct >= 0) {
+#define JXG_CARVE(k) \
+  if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+#define JXG_CARVE_LEAN(SV)                 \
+  JXG_CARVE((k_entropy_lean<SV, true, true>))   \
+  JXG_CARVE((k_entropy_lean<SV, true, false>))  \
+  JXG_CARVE((k_entropy_lean<SV, false, true>))  \
+  JXG_CARVE((k_entropy_lean<SV, false, false>)) \
+  JXG_CARVE((k_entropy_fast<SV>))
+    JXG_CARVE_LEAN(1)
+    JXG_CARVE_LEAN(2)
+    JXG_CARVE_LEAN(4)
+    JXG_CARVE_LEAN(8)
+    JXG_CARVE(k_entropy)
+    JXG_CARVE(k_block_plan)
+    JXG_CARVE((k_idct_small<0>))
+    JXG_CARVE((k_idct_small<1>))
+    JXG_CARVE((k_idct_small<2>))
+    JXG_CARVE(k_dequant_idct)
+    JXG_CARVE((k_filters_store<false, 0>))
+    JXG_CARVE((k_filters_store<false, 1>))
+    JXG_CARVE((k_filters_store<false, 2>))
+    JXG_CARVE((k_filters_store<false, 3>))
+    JXG_CARVE((k_filters_store<true, 0>))
+    JXG_CARVE((k_filters_store<true, 1>))
+    JXG_CARVE((k_filters_store<true, 2>))
+    JXG_CARVE((k_filters_store<true, 3>))
+    JXG_CARVE(k_orient)
+#undef JXG_CARVE_LEAN
+#undef JXG_CARVE
+  }
+  return cudaSuccess;
 }
 
 int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t total_tiles, uint32_t max_epf_iters,
