@@ -201,7 +201,8 @@ int jxg_batch_set_debug_stop(void* batch, int stage);
 int jxg_batch_set_profile(void* batch, int on);
 int jxg_batch_stage_times(void* batch, float* ms, int n);
 /* Absolute device times (ms since a process-wide reference event set at the first call) of the 9 stage events of the
- * last run: the timeline of several batches in flight. */
+ * last run: the timeline of several batches in flight. With n >= 11, ms[9] and ms[10] are the run's first event (before
+ * the H2D copy of the staging blob) and its last one (behind the D2H copies of the outputs). */
 int jxg_batch_stage_marks(void* batch, float* ms, int n);
 
 /* Counters for bench.py (kernels launched by the last run, bytes moved). */

@@ -341,6 +341,10 @@ int jxg_batch_stage_marks(void* bp, float* ms, int n) {
   CUDA_TRY(cudaEventSynchronize(b->ev1));
   for (int i = 0; i <= kNumStages; i++)
     if (cudaEventElapsedTime(&ms[i], ref, b->stage_ev[i]) != cudaSuccess) ms[i] = 0.0f;
+  if (n >= kNumStages + 3) {  // + the run's first event (before the H2D copy) and its last (behind the D2H copies)
+    if (cudaEventElapsedTime(&ms[kNumStages + 1], ref, b->ev0) != cudaSuccess) ms[kNumStages + 1] = 0.0f;
+    if (cudaEventElapsedTime(&ms[kNumStages + 2], ref, b->ev1) != cudaSuccess) ms[kNumStages + 2] = 0.0f;
+  }
   cudaGetLastError();
   return JXG_OK;
 }
@@ -604,7 +608,7 @@ static void schedule_lean(Batch* b) {
   const uint32_t max_ctas = 148 * 6;
   uint32_t S = 4;
   if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
-  S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : 8));
+  S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32))));
   // lanes actually used per packed warp (<= S, the kernel's compile-time capacity): 3 is a legal in-between
   uint32_t L = std::min<uint32_t>(S, std::max<uint32_t>(1, uint32_t(knob("JXG_ENTROPY_LANES", float(S)))));
   std::vector<uint2> warps;
@@ -907,8 +911,16 @@ int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_grou
   Batch* b = static_cast<Batch*>(bp);
   if (!b) return JXG_ERR_ARGUMENT;
   CUDA_TRY(cudaSetDevice(b->ctx->device));
-  CUDA_TRY(cudaEventSynchronize(b->ev1));  // recorded behind the status words and the D2H copies; no stream-wide wait:
-                                           // the stage streams carry later batches too
+  {
+    static const bool traced = getenv("JXG_TRACE_RUN") && atoi(getenv("JXG_TRACE_RUN")) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool was_done = traced && cudaEventQuery(b->ev1) == cudaSuccess;
+    CUDA_TRY(cudaEventSynchronize(b->ev1));  // recorded behind the status words and the D2H copies; no stream-wide wait:
+                                             // the stage streams carry later batches too
+    if (traced)
+      fprintf(stderr, "[jxg_batch_wait] done on entry %d, event wait %.1f ms\n", int(was_done),
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
   CUDA_TRY(cudaGetLastError());
   cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1);
   for (size_t i = 0; i < b->status_n; i++)

@@ -2497,6 +2497,7 @@ struct FusedTiles {
   uint32_t num_frames;
   uint32_t tile_begin;          // first tile of this launch (frame ranges are launched separately so that the
                                 // D2H copy of finished frames overlaps the filtering of the next ones)
+  uint32_t tile_end;            // one past the last tile of this launch (the persistent kernel strides up to it)
 };
 
 template <bool GAB, int EPF>
@@ -2841,26 +2842,11 @@ __device__ __forceinline__ void epf_maps_v4(const float* src, float* maps, int r
   }
 }
 
-__device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev& F, const float* src_planes, float* smem,
-                                               int x0, int y0) {
-  using C = FCfg<true, 2>;
-  constexpr int H = 4, WW = C::WW, WH = C::WH, NC = C::NC, QW = WW / 4;
-  static_assert(C::H == H && WW == 72 && WH == 40, "vector path is written for the halo-4 configuration");
-  float* bufA = smem;
-  float* bufB = smem + 3 * NC;
-  float* maps = smem + 6 * NC;
-  float* sig = maps + C::NMAPS * NC;
-  const int wx0 = x0 - H, wy0 = y0 - H;
-  // ---- load ----
-  for (int q = threadIdx.x; q < QW * WH; q += blockDim.x) {
-    const int ly = q / QW, o = ly * WW + (q % QW) * 4;
-    const float* g = src_planes + F.plane_base + size_t(wy0 + ly) * F.plane_stride + wx0 + (q % QW) * 4;
-#pragma unroll
-    for (int c = 0; c < 3; c++) st4(bufA + c * NC + o, __ldg(reinterpret_cast<const float4*>(g + c * F.plane_size)));
-  }
-  const int sbx0 = wx0 >> 3, sby0 = wy0 >> 3;
-  for (int idx = threadIdx.x; idx < C::SBW * C::SBH; idx += blockDim.x) {  // features/epf.rs:54-79
-    const int bx = sbx0 + idx % C::SBW, by = sby0 + idx / C::SBW;
+// Sigma of every 8x8 block touched by a tile's window (features/epf.rs:54-79).
+template <int SBW, int SBH>
+__device__ __forceinline__ void tile_sigma(const BatchDev& B, const FrameDev& F, float* sig, int sbx0, int sby0, int t0, int nt) {
+  for (int idx = t0; idx < SBW * SBH; idx += nt) {
+    const int bx = sbx0 + idx % SBW, by = sby0 + idx / SBW;
     float v = 0.0f;
     if (bx < int(F.xb) && by < int(F.yb)) {
       const size_t bidx = size_t(by) * F.xb + bx;
@@ -2871,7 +2857,54 @@ __device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev
     }
     sig[idx] = v;
   }
-  __syncthreads();
+}
+
+// A tile of the persistent kernel's walk: its frame, origin and whether the vector path takes it.
+struct TileRef {
+  const FrameDev* F;
+  int x0, y0;
+  bool mine;  // the frame has this kernel's filter configuration
+  bool vec;   // interior tile with an aligned output row: vector path (and asynchronous prefetch)
+};
+
+constexpr int kV4Rows = 3 * (kTH + 8);       // window rows of the three planes: one bulk copy each
+constexpr uint32_t kV4RowBytes = (kTW + 8) * 4;
+
+// Window of the vector path fetched by the asynchronous copy engine: one cp.async.bulk per window row and plane
+// (288 bytes, 16-byte aligned on both sides), all completing on one mbarrier. Called by the first kV4Rows threads.
+__device__ __forceinline__ void v4_prefetch(const FrameDev& F, const float* src_planes, float* buf, int x0, int y0, uint64_t* bar) {
+  constexpr int WW = kTW + 8, WH = kTH + 8, NC = WW * WH;
+  const int r = threadIdx.x;
+  if (r >= kV4Rows) return;
+  const int c = r / WH, ly = r % WH;
+  const float* g = src_planes + F.plane_base + size_t(c) * F.plane_size + size_t(y0 - 4 + ly) * F.plane_stride + (x0 - 4);
+  bulk_load(buf + c * NC + ly * WW, g, kV4RowBytes, bar);
+}
+
+// X holds (or receives) the tile's window, Y is the second plane buffer. After EPF stage 1 the Y buffer is dead, so
+// the window of the CTA's next tile is fetched into it while stage 2, the colour conversion and the store run.
+__device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev& F, const float* src_planes, float* bufA,
+                                               float* bufB, float* maps, float* sig, float* sig_next, int x0, int y0,
+                                               bool prefetched, uint64_t* bar, uint32_t& bar_parity, const TileRef& next) {
+  using C = FCfg<true, 2>;
+  constexpr int H = 4, WW = C::WW, WH = C::WH, NC = C::NC, QW = WW / 4;
+  static_assert(C::H == H && WW == 72 && WH == 40, "vector path is written for the halo-4 configuration");
+  const int wx0 = x0 - H, wy0 = y0 - H;
+  const int sbx0 = wx0 >> 3, sby0 = wy0 >> 3;
+  if (prefetched) {
+    mbar_wait(bar, bar_parity);  // the copies were started during the previous tile; sig was filled then as well
+    bar_parity ^= 1;
+  } else {
+    // ---- load ----
+    for (int q = threadIdx.x; q < QW * WH; q += blockDim.x) {
+      const int ly = q / QW, o = ly * WW + (q % QW) * 4;
+      const float* g = src_planes + F.plane_base + size_t(wy0 + ly) * F.plane_stride + wx0 + (q % QW) * 4;
+#pragma unroll
+      for (int c = 0; c < 3; c++) st4(bufA + c * NC + o, __ldg(reinterpret_cast<const float4*>(g + c * F.plane_size)));
+    }
+    tile_sigma<C::SBW, C::SBH>(B, F, sig, sbx0, sby0, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
   // ---- Gaborish (gaborish.rs:40-88): rows 1..38, bufA -> bufB ----
   for (int q = threadIdx.x; q < QW * (WH - 2); q += blockDim.x) {
     const int ly = 1 + q / QW, o = ly * WW + (q % QW) * 4;
@@ -2966,6 +2999,15 @@ __device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev
     }
   }
   __syncthreads();
+  if (next.vec) {
+    // bufB is dead from here on: fetch the next tile's window into it (the generic-proxy reads of stage 1 are ordered
+    // before the asynchronous writes by the barrier above plus the proxy fence), and its sigma blocks on idle threads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    v4_prefetch(*next.F, src_planes, bufB, next.x0, next.y0, bar);
+    if (int(threadIdx.x) >= kV4Rows)
+      tile_sigma<C::SBW, C::SBH>(B, *next.F, sig_next, (next.x0 - H) >> 3, (next.y0 - H) >> 3, int(threadIdx.x) - kV4Rows,
+                                 int(blockDim.x) - kV4Rows);
+  }
   // ---- EPF stage 2 (epf2.rs) on the 64x32 core + colour + store ----
   epf_maps_v4<WW, NC>(bufA, maps, 3, WH - 3, cs0, cs1, cs2);
   __syncthreads();
@@ -3076,10 +3118,13 @@ __device__ __forceinline__ void filter_tile_v4(const BatchDev& B, const FrameDev
 }
 
 template <bool GAB, int EPF>
-__global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+__device__ __forceinline__ TileRef locate_tile(const BatchDev& B, const FusedTiles& T, uint32_t tile_id) {
   using C = FCfg<GAB, EPF>;
-  extern __shared__ float smem[];
-  const uint32_t tile_id = blockIdx.x + T.tile_begin;
+  TileRef r;
+  r.F = nullptr;
+  r.x0 = r.y0 = 0;
+  r.mine = r.vec = false;
+  if (tile_id >= T.tile_end) return r;
   uint32_t lo = 0, hi = T.num_frames;
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
@@ -3087,28 +3132,119 @@ __global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev
     else hi = mid;
   }
   const FrameDev& F = B.frames[lo];
-  if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return;  // another instantiation handles this frame
+  r.F = &F;
+  if ((F.gab != 0) != GAB || int(min(F.epf_iters, 3u)) != EPF) return r;  // another instantiation handles this frame
+  r.mine = true;
   const uint32_t local = tile_id - T.tile_prefix[lo];
   const uint32_t tiles_x = (F.width + kTW - 1) / kTW;
-  const int x0 = int(local % tiles_x) * kTW, y0 = int(local / tiles_x) * kTH;
-  const bool interior = x0 - C::H >= 0 && y0 - C::H >= 0 && x0 + kTW + C::H <= int(F.width) && y0 + kTH + C::H <= int(F.height);
-  if (interior) {
-    // 16-byte accesses need an aligned output row (RGB8: stride and base multiples of 4, f32 / RGBA: of 16)
-    const uintptr_t oa = reinterpret_cast<uintptr_t>(F.out_ptr) | uintptr_t(F.out_row_stride);
-    const bool aligned = F.output_format == JXG_FORMAT_RGB_U8 ? (oa & 3) == 0 : (oa & 15) == 0;
-    if (GAB && EPF == 2 && aligned) filter_tile_v4(B, F, src_planes, smem, x0, y0);
-    else filter_tile<GAB, EPF, true>(B, F, src_planes, smem, x0, y0);
+  r.x0 = int(local % tiles_x) * kTW;
+  r.y0 = int(local / tiles_x) * kTH;
+  const bool interior = r.x0 - C::H >= 0 && r.y0 - C::H >= 0 && r.x0 + kTW + C::H <= int(F.width) && r.y0 + kTH + C::H <= int(F.height);
+  // 16-byte accesses need an aligned output row (RGB8: stride and base multiples of 4, f32 / RGBA: of 16)
+  const uintptr_t oa = reinterpret_cast<uintptr_t>(F.out_ptr) | uintptr_t(F.out_row_stride);
+  const bool aligned = F.output_format == JXG_FORMAT_RGB_U8 ? (oa & 3) == 0 : (oa & 15) == 0;
+  r.vec = GAB && EPF == 2 && interior && aligned;
+  return r;
+}
+
+template <bool GAB, int EPF>
+__global__ void __launch_bounds__(kFilterThreads) k_filters_store(const BatchDev B, const FusedTiles T, const float* src_planes) {
+  using C = FCfg<GAB, EPF>;
+  extern __shared__ float smem[];
+  const TileRef r = locate_tile<GAB, EPF>(B, T, blockIdx.x + T.tile_begin);
+  if (!r.mine) return;
+  const FrameDev& F = *r.F;
+  const bool interior = r.x0 - C::H >= 0 && r.y0 - C::H >= 0 && r.x0 + kTW + C::H <= int(F.width) && r.y0 + kTH + C::H <= int(F.height);
+  if (GAB && EPF == 2 && r.vec) {
+    __shared__ float s_sig[FCfg<true, 2>::SBW * FCfg<true, 2>::SBH];
+    uint32_t parity = 0;
+    TileRef none;
+    none.F = nullptr;
+    none.x0 = none.y0 = 0;
+    none.mine = none.vec = false;
+    filter_tile_v4(B, F, src_planes, smem, smem + 3 * FCfg<true, 2>::NC, smem + 6 * FCfg<true, 2>::NC, s_sig, s_sig, r.x0, r.y0, false,
+                   nullptr, parity, none);
+  } else if (interior) {
+    filter_tile<GAB, EPF, true>(B, F, src_planes, smem, r.x0, r.y0);
   } else {
-    filter_tile<GAB, EPF, false>(B, F, src_planes, smem, x0, y0);
+    filter_tile<GAB, EPF, false>(B, F, src_planes, smem, r.x0, r.y0);
   }
+}
+
+// Gaborish + EPF iters 2 can also run persistently (JXG_FILTERS_PERSISTENT=1): 2 CTAs per SM stride over the launch's tiles,
+// interior tiles take the vector path with their window prefetched by bulk copies during the previous tile's last
+// phase; edge tiles (and frames with unaligned output rows) take the generic path in the same shared memory.
+__global__ void __launch_bounds__(kFilterThreads, 2) k_filters_v4(const BatchDev B, const FusedTiles T, const float* src_planes) {
+  using C = FCfg<true, 2>;
+  extern __shared__ float smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ float s_sig[2][C::SBW * C::SBH];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, kV4Rows);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  float* bufX = smem;               // holds the current tile's window
+  float* bufY = smem + 3 * C::NC;
+  float* maps = smem + 6 * C::NC;
+  uint32_t parity = 0, cur = 0;
+  bool prefetched = false;
+  uint32_t tile = T.tile_begin + blockIdx.x;
+  TileRef r = locate_tile<true, 2>(B, T, tile);
+  while (tile < T.tile_end) {
+    const TileRef next = locate_tile<true, 2>(B, T, tile + gridDim.x);
+    if (r.mine) {
+      if (r.vec) {
+        filter_tile_v4(B, *r.F, src_planes, bufX, bufY, maps, s_sig[cur], s_sig[cur ^ 1], r.x0, r.y0, prefetched, &s_bar, parity, next);
+        prefetched = next.vec;
+        if (prefetched) {  // the next window is arriving in bufY
+          float* t = bufX; bufX = bufY; bufY = t;
+          cur ^= 1;
+        }
+      } else {
+        const FrameDev& F = *r.F;
+        const bool interior = r.x0 - C::H >= 0 && r.y0 - C::H >= 0 && r.x0 + kTW + C::H <= int(F.width) && r.y0 + kTH + C::H <= int(F.height);
+        if (interior) filter_tile<true, 2, true>(B, F, src_planes, smem, r.x0, r.y0);
+        else filter_tile<true, 2, false>(B, F, src_planes, smem, r.x0, r.y0);
+      }
+      __syncthreads();  // every reader of this tile's buffers is done before the next tile writes them
+    }
+    r = next;
+    tile += gridDim.x;
+  }
+}
+
+// Experiment knobs (read once): JXG_FILTER_THREADS = threads per filter CTA (multiple of 32, 128..512; the kernels stride
+// by blockDim.x), JXG_FILTERS_PERSISTENT = 1 selects the persistent prefetching kernel for Gaborish + EPF 2.
+static int filter_threads() {
+  static const int n = [] {
+    const char* e = getenv("JXG_FILTER_THREADS");
+    int v = e ? atoi(e) : kFilterThreads;
+    v = (v / 32) * 32;
+    return v < 128 ? 128 : (v > kFilterThreads ? kFilterThreads : v);
+  }();
+  return n;
+}
+static bool filters_persistent() {
+  static const bool on = getenv("JXG_FILTERS_PERSISTENT") && atoi(getenv("JXG_FILTERS_PERSISTENT")) != 0;
+  return on;
 }
 
 template <bool GAB, int EPF>
 static void launch_filters(const BatchDev& B, const FusedTiles& FT, uint32_t tiles, cudaStream_t stream) {
-  k_filters_store<GAB, EPF><<<tiles, kFilterThreads, FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
+  if (GAB && EPF == 2 && filters_persistent()) {
+    const uint32_t grid = tiles < 2 * 148 ? tiles : 2 * 148;
+    k_filters_v4<<<grid, filter_threads(), FCfg<true, 2>::kSmemBytes, stream>>>(B, FT, B.planes_a);
+    return;
+  }
+  k_filters_store<GAB, EPF><<<tiles, filter_threads(), FCfg<GAB, EPF>::kSmemBytes, stream>>>(B, FT, B.planes_a);
 }
 template <bool GAB, int EPF>
 static cudaError_t configure_filters() {
+  if (GAB && EPF == 2) {
+    cudaError_t e = cudaFuncSetAttribute(k_filters_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(FCfg<true, 2>::kSmemBytes));
+    if (e != cudaSuccess) return e;
+  }
   return cudaFuncSetAttribute(k_filters_store<GAB, EPF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               int(FCfg<GAB, EPF>::kSmemBytes));
 }
@@ -3176,9 +3312,10 @@ cudaError_t configure_kernels() {
   // One shared-memory carve-out for every kernel of the pipeline. An SM can only change its L1 / shared-memory split when
   // it is empty, so a filter CTA (92 KB) or transform CTA (68 - 101 KB) of one batch cannot join an SM that still holds
   // entropy CTAs of another batch launched with a small carve-out: kernels of different streams then only overlap in the
-  // entropy kernel's tail. JXG_CARVEOUT = percentage of the unified memory given to shared memory (default 100 = max shared, -1 =
-  // leave the driver's per-kernel choice).
-  int pct = 100;
+  // entropy kernel's tail. JXG_CARVEOUT = percentage of the unified memory given to shared memory (-1, the default, leaves the
+  // driver's per-kernel choice). Measured (profiles/r02j_carveout.log): 100 costs the entropy kernel its L1 (32.3 -> 42.8 ms
+  // alone) and gains nothing at 3 resident batches (40.6 against 39.3 ms per step); 75 is within noise of the default.
+  int pct = -1;
   if (const char* env = getenv("JXG_CARVEOUT")) pct = atoi(env);
   if (pct >= 0) {
 #define JXG_CARVE(k) \
@@ -3189,16 +3326,24 @@ cudaError_t configure_kernels() {
   JXG_CARVE((k_entropy_lean<SV, false, true>))  \
   JXG_CARVE((k_entropy_lean<SV, false, false>)) \
   JXG_CARVE((k_entropy_fast<SV>))
+#define JXG_CARVE_WIDE(SV)                 \
+  JXG_CARVE((k_entropy_lean<SV, true, true>))   \
+  JXG_CARVE((k_entropy_lean<SV, true, false>))  \
+  JXG_CARVE((k_entropy_lean<SV, false, true>))  \
+  JXG_CARVE((k_entropy_lean<SV, false, false>))
     JXG_CARVE_LEAN(1)
     JXG_CARVE_LEAN(2)
     JXG_CARVE_LEAN(4)
     JXG_CARVE_LEAN(8)
+    JXG_CARVE_WIDE(16)
+    JXG_CARVE_WIDE(32)
     JXG_CARVE(k_entropy)
     JXG_CARVE(k_block_plan)
     JXG_CARVE((k_idct_small<0>))
     JXG_CARVE((k_idct_small<1>))
     JXG_CARVE((k_idct_small<2>))
     JXG_CARVE(k_dequant_idct)
+    JXG_CARVE(k_filters_v4)
     JXG_CARVE((k_filters_store<false, 0>))
     JXG_CARVE((k_filters_store<false, 1>))
     JXG_CARVE((k_filters_store<false, 2>))
@@ -3209,6 +3354,7 @@ cudaError_t configure_kernels() {
     JXG_CARVE((k_filters_store<true, 3>))
     JXG_CARVE(k_orient)
 #undef JXG_CARVE_LEAN
+#undef JXG_CARVE_WIDE
 #undef JXG_CARVE
   }
   return cudaSuccess;
@@ -3241,7 +3387,9 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
     if (S == 1) JXG_LEAN(1, KV, CV);                          \
     else if (S == 2) JXG_LEAN(2, KV, CV);                     \
     else if (S == 4) JXG_LEAN(4, KV, CV);                     \
-    else JXG_LEAN(8, KV, CV);                                 \
+    else if (S == 8) JXG_LEAN(8, KV, CV);                     \
+    else if (S == 16) JXG_LEAN(16, KV, CV);                   \
+    else JXG_LEAN(32, KV, CV);                                \
   } while (0)
     if (lean_all_420) {
       if (lean_ctx_smem) JXG_LEAN_S(true, true);
@@ -3371,7 +3519,7 @@ int launch_filter_range(const BatchDev& B, const uint32_t* fused_prefix, uint32_
                         uint32_t filter_cfg_mask, cudaStream_t stream) {
   int launches = 0;
   if (!tile_count) return 0;
-  FusedTiles FT{fused_prefix, B.num_frames, tile_begin};
+  FusedTiles FT{fused_prefix, B.num_frames, tile_begin, tile_begin + tile_count};
   for (int cfg = 0; cfg < 8; cfg++) {
     if (!(filter_cfg_mask & (1u << cfg))) continue;
     switch (cfg) {

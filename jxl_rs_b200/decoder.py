@@ -123,9 +123,10 @@ class Batch:
         return dict(zip(self.STAGES, [float(v) for v in ms]))
 
     def stage_marks(self):
-        """Absolute device times (ms) of the 9 stage events of the last run (jxg_batch_stage_marks)."""
-        ms = (C.c_float * 9)()
-        abi.check(self._lib, self._lib.jxg_batch_stage_marks(self._h, ms, 9))
+        """Absolute device times (ms) of the 9 stage events of the last run, then of the run's first event (before the
+        H2D copy) and its last one (behind the D2H copies) (jxg_batch_stage_marks)."""
+        ms = (C.c_float * 11)()
+        abi.check(self._lib, self._lib.jxg_batch_stage_marks(self._h, ms, 11))
         return [float(v) for v in ms]
 
     def run(self, stream_ptr: int = 0):
@@ -307,19 +308,26 @@ class PipelinedDecoder:
         self._ahead = threading.Semaphore(depth + parse_ahead)  # bounds parsed-but-not-yet-launched batches
         self._error = None
         self.trace = None  # set to [] to record the dispatcher timeline
+        self.retire_trace = []  # with trace on: (start, seconds in wait / stats / close) of every retired batch
         self.marks = None  # set to [] to record the device timeline of every batch (stage event times)
         self._thread = threading.Thread(target=self._dispatch, daemon=True)
         self._thread.start()
 
     def _retire(self):
+        import time
         b = self.inflight.popleft()
+        t0 = time.perf_counter()
         try:
             b.wait()
+            t1 = time.perf_counter()
             self.last_stats = b.stats()
             if self.marks is not None:
                 self.marks.append(b.stage_marks())
         finally:
+            t2 = time.perf_counter()
             b.close()
+        if self.trace is not None:  # ("retire", start, event wait, stats + marks, close)
+            self.retire_trace.append((t0, t1 - t0, t2 - t1, time.perf_counter() - t2))
 
     def _launch(self, futs, outs, fmt, out_is_device):
         import time
