@@ -35,7 +35,8 @@ DeviceStreams device_streams(int device) {
   if (!d.entropy) {
     cudaSetDevice(device);
     if (cudaStreamCreateWithFlags(&d.entropy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&d.post, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&d.post, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d.d2h, cudaStreamNonBlocking) != cudaSuccess)
       d = DeviceStreams{};
   }
   return d;
@@ -97,7 +98,8 @@ struct Batch {
   int32_t* status_host = nullptr;  // pinned (context-owned): a D2H copy into pageable memory would block jxg_batch_run
   size_t status_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_handoff = nullptr;
-  bool copies_on_copy_stream = false;  // last run: the D2H copies went to the context's copy stream
+  bool copies_on_copy_stream = false;  // last run: the D2H copies went to a copy stream (`copy_stream`), not the launching one
+  cudaStream_t copy_stream = nullptr;  // the device's shared D2H stream (default) or the context's own (JXG_D2H_SHARED=0)
   cudaStream_t last_stream = nullptr;  // stream of the last run / rerun (the context's or the caller's)
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
@@ -607,7 +609,8 @@ static void schedule_lean(Batch* b) {
   // CTAs only when the first ones end, so the packing is made denser until the grid fits.
   const uint32_t max_ctas = 148 * 6;
   uint32_t S = 4;
-  if (const char* e = getenv("JXG_ENTROPY_S")) S = uint32_t(atoi(e));
+  const char* s_env = getenv("JXG_ENTROPY_S");  // pins the lanes per warp (experiments)
+  if (s_env) S = uint32_t(atoi(s_env));
   S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32))));
   // lanes actually used per packed warp (<= S, the kernel's compile-time capacity): 3 is a legal in-between
   uint32_t L = std::min<uint32_t>(S, std::max<uint32_t>(1, uint32_t(knob("JXG_ENTROPY_LANES", float(S)))));
@@ -648,11 +651,13 @@ static void schedule_lean(Batch* b) {
     }
     b->lean_ctas = ctas;
     if (ctas <= max_ctas) break;
-    // denser: first fewer privileged warps, then more streams per packed lane, then wider warps
+    // denser: first fewer privileged warps, then 8 lanes per warp, then more streams per packed lane. A batch that does
+    // not fit one resident wave at 4 lanes per warp is a throughput job: 8 lanes halve the kernel's warp-instructions,
+    // which is what counts once several batches share the SMs (64 x 4K: alone 57.2 against 52.3 ms, three resident batches
+    // 37.1 against 40.5 ms per batch, five 35.1 against 38.0; 16 and 32 lanes lose again: profiles/r02k_entropy_lanes.log).
     if (solo < 0.95f) solo = std::min(0.95f, solo + 0.1f), duo = std::min(0.9f, duo + 0.1f);
-    else if (per_lane < 4.0f) per_lane *= 1.3f;
     else if (L < S) L = S;
-    else if (S < 8) S = L = 8, per_lane = 1.6f;
+    else if (S < 8 && !s_env) S = L = 8;
     else per_lane *= 1.3f;
   }
   b->lean_S = S;
@@ -727,7 +732,10 @@ static int launch(Batch* b, cudaStream_t se, cudaStream_t s, bool copy_to_host) 
     static const int d2h_ranges = getenv("JXG_D2H_RANGES") ? atoi(getenv("JXG_D2H_RANGES")) : int(Context::kMaxRanges);
     const bool same_stream = copy_to_host && d2h_ranges <= 0;
     const uint32_t nr = (copy_to_host && !same_stream) ? std::min<uint32_t>(std::min<uint32_t>(uint32_t(d2h_ranges), Context::kMaxRanges), nf) : 1;
-    cudaStream_t cs = same_stream ? s : cx->copy_stream;
+    static const bool shared_d2h = !(getenv("JXG_D2H_SHARED") && atoi(getenv("JXG_D2H_SHARED")) == 0);
+    const DeviceStreams ds = device_streams(cx->device);
+    b->copy_stream = (shared_d2h && ds.d2h) ? ds.d2h : cx->copy_stream;
+    cudaStream_t cs = same_stream ? s : b->copy_stream;
     const uint32_t* fp = reinterpret_cast<const uint32_t*>(tab(b->tab.ftiles));
     if (ev) {
       for (int i = 4; i <= 6; i++) cudaEventRecord(ev[i], s);
@@ -747,7 +755,7 @@ static int launch(Batch* b, cudaStream_t se, cudaStream_t s, bool copy_to_host) 
       if (copy_to_host) {
         if (!same_stream) {
           CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
-          CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->range_done[r], 0));
+          CUDA_TRY(cudaStreamWaitEvent(cs, cx->range_done[r], 0));
         }
         for (uint32_t f = f0; f < f1; f++) {
           const FrameOut& fo = b->outs[f];
@@ -852,6 +860,7 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
               put(b->fused_prefix.data(), b->fused_prefix.size() * 4, b->tab.ftiles);
     if (!ok) return set_error(JXG_ERR_CUDA, "pinned staging allocation failed");
   }
+  if (!b->blob.reserve(b->blob.size + 16)) return set_error(JXG_ERR_CUDA, "pinned staging allocation failed");  // k_upload reads whole 16-byte words
   if (int r = b->d_blob.ensure(b->blob.size + 64)) return r;
   trace.mark("alloc");
   b->blob.flush();
@@ -865,7 +874,13 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
     CUDA_TRY(cudaStreamWaitEvent(se, b->ev_handoff, 0));
   } else {
     CUDA_TRY(cudaEventRecord(b->ev0, se));
-    CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, se));
+    // JXG_UPLOAD_KERNEL=1: the SMs fetch the blob from pinned host memory instead of a copy engine. With several batches
+    // in flight the copy engine's queue holds the D2H copies of older batches, and an H2D cudaMemcpyAsync submitted behind
+    // them does not start until that queue runs dry (profiles/r02m_e2e_fifo.log: the first event of a batch's stream is
+    // stamped when the D2H of the batch three launches earlier ends) - the new batch's kernels wait with it.
+    static const bool upload_kernel = getenv("JXG_UPLOAD_KERNEL") && atoi(getenv("JXG_UPLOAD_KERNEL")) != 0;
+    if (upload_kernel) launch_upload(b->blob.p, b->d_blob.p, b->blob.size, se);
+    else CUDA_TRY(cudaMemcpyAsync(b->d_blob.p, b->blob.p, b->blob.size, cudaMemcpyHostToDevice, se));
   }
   trace.mark("blob_h2d");
   b->h2d += b->blob.size;
@@ -880,8 +895,8 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (b->copies_on_copy_stream) {
     Context* cx = b->ctx;
     CUDA_TRY(cudaEventRecord(cx->copy_done, s));
-    CUDA_TRY(cudaStreamWaitEvent(cx->copy_stream, cx->copy_done, 0));
-    CUDA_TRY(cudaEventRecord(b->ev1, cx->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, cx->copy_done, 0));
+    CUDA_TRY(cudaEventRecord(b->ev1, b->copy_stream));
   } else {
     CUDA_TRY(cudaEventRecord(b->ev1, s));
   }

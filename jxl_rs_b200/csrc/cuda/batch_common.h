@@ -116,6 +116,11 @@ struct PinnedArena {
 // batches overlap in the entropy kernel's tail. The default is one stream per batch.
 struct DeviceStreams {
   cudaStream_t entropy = nullptr, post = nullptr;
+  // One D2H stream for all contexts of the device: output copies leave in launch order. With a copy stream per context
+  // the copies of all batches in flight share the host link evenly, so they all end together, all contexts come free
+  // together and the next batches start together: a convoy that leaves the SMs idle for the length of the D2H tail
+  // (profiles/r02l_e2e_convoy.log). First in, first out retires the oldest batch early and keeps the launches staggered.
+  cudaStream_t d2h = nullptr;
 };
 DeviceStreams device_streams(int device);  // created on first use
 

@@ -3476,6 +3476,27 @@ int launch_pipeline(const BatchDev& B, const uint32_t* tile_prefix, uint32_t tot
   return launches;
 }
 
+// Upload of the staging blob by the SMs: 16-byte loads from the pinned host arena (the device reaches it through UVA),
+// 16-byte stores to the device copy. Used instead of cudaMemcpyAsync when copy-engine work of other batches (the D2H
+// copies of finished frames) would sit in front of this batch's H2D copy: see batch.cc jxg_batch_run.
+__global__ void __launch_bounds__(256) k_upload(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {  // four loads in flight per thread: the host link's latency is microseconds
+    const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = src[i];
+}
+
+void launch_upload(const void* host_pinned, void* dev, size_t bytes, cudaStream_t stream) {
+  const size_t n16 = (bytes + 15) / 16;  // both buffers are allocated in 16-byte multiples and 16-byte aligned
+  k_upload<<<64, 256, 0, stream>>>(static_cast<const uint4*>(host_pinned), static_cast<uint4*>(dev), n16);
+}
+
 // Parity tap: the coefficient lists of one frame expanded into the reference's dense decode-order layout
 // [groups][3][65536] (group.rs:53-55), all passes added up. One CTA per group; `dense` must be zeroed by the caller.
 __global__ void __launch_bounds__(256) k_expand_coeffs(const BatchDev B, uint32_t frame, int32_t* dense) {

@@ -22,5 +22,7 @@ void launch_expand_coeffs(const BatchDev& B, uint32_t frame, uint32_t num_groups
 // Orientation post-pass of one frame: coded w x h image at `src` (row stride src_stride) -> display orientation at `dst`.
 void launch_orient(const void* src, size_t src_stride, void* dst, size_t dst_stride, uint32_t w, uint32_t h, uint32_t bpp,
                    uint32_t orientation, cudaStream_t stream);
+// The staging blob copied by a kernel (host_pinned must be device-accessible pinned memory, sizes padded to 16 bytes).
+void launch_upload(const void* host_pinned, void* dev, size_t bytes, cudaStream_t stream);
 constexpr int kNumStages = 8;  // memset, entropy, dequant_idct, gaborish, epf0, epf1, epf2, xyb_store
 }  // namespace jxgpu

@@ -8,6 +8,8 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../../include/jxg.h"
@@ -101,9 +103,98 @@ uint64_t add_tree(ModularBatch* b, const jxg::ModularTree& t) {
   return blob_append(b, nodes.data(), nodes.size() * 4, 16);
 }
 
+// Table form of a channel's tree walk (see modular_device.h). Returns false when the channel needs the generic walk.
+// `root`: first node whose decision is not on the channel index / stream id. Keys of the cache: (tree, root).
+struct WalkKey {
+  uint64_t tree_off;
+  uint32_t root, ci;
+  uint64_t stream_id;
+  bool operator<(const WalkKey& o) const {
+    return std::tie(tree_off, root, ci, stream_id) < std::tie(o.tree_off, o.root, o.ci, o.stream_id);
+  }
+};
+
+// Does the tree decide on the channel index / stream id (properties 0 / 1) below a split on another property?
+bool has_inner_static(const jxg::ModularTree& t) {
+  std::vector<std::pair<uint32_t, bool>> stack{{0u, false}};
+  while (!stack.empty()) {
+    auto [n, below] = stack.back();
+    stack.pop_back();
+    const jxg::TreeNode& nd = t.nodes[n];
+    if (nd.property < 0) continue;
+    const bool is_static = nd.property == 0 || nd.property == 1;
+    if (is_static && below) return true;
+    stack.push_back({nd.left, below || !is_static});
+    stack.push_back({nd.right, below || !is_static});
+  }
+  return false;
+}
+struct WalkInfo {
+  uint32_t walk;
+  uint64_t lut_off;
+};
+
+uint32_t static_root(const jxg::ModularTree& t, uint32_t ci, uint64_t stream_id) {
+  uint32_t n = 0;
+  while (t.nodes[n].property == 0 || t.nodes[n].property == 1) {
+    const int64_t v = t.nodes[n].property == 0 ? int64_t(ci) : int64_t(int32_t(uint32_t(stream_id)));
+    n = v > int64_t(t.nodes[n].val) ? t.nodes[n].left : t.nodes[n].right;
+  }
+  return n;
+}
+
+bool build_walk_table(const jxg::ModularTree& t, uint32_t root, uint32_t ci, uint64_t stream_id, std::vector<uint32_t>& lut,
+                      uint32_t& prop, uint32_t& single) {
+  struct Item {
+    int32_t lo, hi;  // [lo, hi)
+    uint32_t node;
+  };
+  auto entry = [&](uint32_t node, uint32_t& e) {
+    const jxg::TreeNode& n = t.nodes[node];
+    if (node >= (1u << 16) || n.ctx >= t.code.context_map.size()) return false;
+    const uint32_t cluster = t.code.context_map[n.ctx];
+    const bool plain = n.val == 0 && n.right == 1;
+    e = (n.left & 15u) | (cluster << 4) | (plain ? 1u << 12 : 0u) | (node << 16);
+    return true;
+  };
+  prop = kLutNoProperty;
+  lut.assign(kLutSize, 0);
+  std::vector<Item> stack{Item{kLutMin, kLutMin + kLutSize, root}};
+  bool any_split = false;
+  while (!stack.empty()) {
+    Item it = stack.back();
+    stack.pop_back();
+    uint32_t node = it.node;
+    // decisions on the channel / stream below other splits are still constant
+    while (t.nodes[node].property == 0 || t.nodes[node].property == 1) {
+      const int64_t v = t.nodes[node].property == 0 ? int64_t(ci) : int64_t(int32_t(uint32_t(stream_id)));
+      node = v > int64_t(t.nodes[node].val) ? t.nodes[node].left : t.nodes[node].right;
+    }
+    const jxg::TreeNode& n = t.nodes[node];
+    if (n.property < 0) {
+      uint32_t e;
+      if (!entry(node, e)) return false;
+      for (int32_t v = it.lo; v < it.hi; v++) lut[size_t(v - kLutMin)] = e;
+      single = e;
+      continue;
+    }
+    if (n.property < 2 || n.property > 15) return false;  // properties of previous channels: generic walk
+    if (prop == kLutNoProperty) prop = uint32_t(n.property);
+    else if (prop != uint32_t(n.property)) return false;
+    // values beyond the table are clamped to its ends: the decision must not change there
+    if (n.val < kLutMin || n.val > kLutMin + kLutSize - 2) return false;
+    any_split = true;
+    const int32_t first_left = n.val + 1;  // v > val -> left child
+    if (first_left < it.hi) stack.push_back(Item{std::max(first_left, it.lo), it.hi, n.left});
+    if (first_left > it.lo) stack.push_back(Item{it.lo, std::min(first_left, it.hi), n.right});
+  }
+  if (!any_split) prop = kLutNoProperty;
+  return true;
+}
+
 void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t stride, bool is_device) {
-  for (const auto& t : ms->global_header.transforms)
-    if (t.id == 1) throw jxg::Error(JXG_ERR_UNSUPPORTED, "palette transforms are not implemented on the device path");
+  if (!ms->device_plan_ok)
+    throw jxg::Error(JXG_ERR_UNSUPPORTED, "palette transforms with delta entries or a predictor are not implemented on the device path");
   if (ms->toc.offsets.size() == 1 && !ms->hf[0].empty)
     throw jxg::Error(JXG_ERR_UNSUPPORTED, "single-section Modular frames with a coded group are not on the device path");
   MFrame f;
@@ -141,6 +232,9 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
   uint32_t global_code = 0;
   uint64_t global_tree = 0;
   bool have_global = false;
+  static const bool walk_tables = !(getenv("JXG_MODULAR_WALK_TABLES") && atoi(getenv("JXG_MODULAR_WALK_TABLES")) == 0);
+  std::map<WalkKey, WalkInfo> walk_cache;
+  std::map<uint64_t, bool> inner_static;
   f.first_stream = uint32_t(b->streams.size());
   for (const jxg::ModularGroupStream& st : ms->hf) {
     if (st.empty) continue;
@@ -179,7 +273,28 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
       rd.base = f.buf_off[r.chan] + uint64_t(r.y0) * rd.stride + r.x0;
       rd.w = r.w;
       rd.h = r.h;
-      rd.pad = 0;
+      rd.walk = kWalkGeneric;
+      rd.lut_off = 0;
+      if (walk_tables && r.w && r.h) {
+        const uint32_t root = static_root(*tree, uint32_t(ri), st.stream_id);
+        // channel / stream decisions below another split make the table specific to this channel of this stream
+        auto is_it = inner_static.find(d.tree_off);
+        if (is_it == inner_static.end()) is_it = inner_static.emplace(d.tree_off, has_inner_static(*tree)).first;
+        const WalkKey key{d.tree_off, root, is_it->second ? uint32_t(ri) : ~0u, is_it->second ? st.stream_id : ~uint64_t(0)};
+        auto it = walk_cache.find(key);
+        if (it == walk_cache.end()) {
+          std::vector<uint32_t> lut;
+          uint32_t prop = kLutNoProperty, single = 0;
+          WalkInfo wi{kWalkGeneric, 0};
+          if (build_walk_table(*tree, root, uint32_t(ri), st.stream_id, lut, prop, single)) {
+            wi.walk = kWalkLut | (prop << 8);
+            wi.lut_off = prop == kLutNoProperty ? uint64_t(single) : blob_append(b, lut.data(), lut.size() * 4, 16);
+          }
+          it = walk_cache.emplace(key, wi).first;
+        }
+        rd.walk = it->second.walk;
+        rd.lut_off = it->second.lut_off;
+      }
       // reference channels: earlier channels of the stream with the same shape, nearest first (common.rs:52-60)
       rd.ref_first = uint32_t(b->refs.size());
       if (tree->num_properties > 16)
@@ -228,6 +343,17 @@ void add_frame(ModularBatch* b, jxg::ModularFrameState* ms, void* out, size_t st
     j.h = ms->bufs[s.a].h;
     j.rw = s.kind == 1 ? ms->bufs[s.b].w : (s.kind == 2 ? ms->bufs[s.b].h : 0);
     j.op = s.rct_op;
+    if (s.kind == 3) {  // one job per colour channel: a index plane, b palette plane (row c = component c), c output
+      if (ms->bufs[s.b].h < s.n || ms->bufs[s.b].w < s.num_colors) throw jxg::Error(jxg::kErrBitstream, "palette channel smaller than its header says");
+      for (uint32_t c = 0; c < s.n; c++) {
+        j.c = f.buf_off[s.c + c];
+        j.rw = s.num_colors;
+        j.op = c;
+        j.out_stride = ms->bufs[s.b].w;  // palette row stride
+        b->levels[si].push_back(j);
+      }
+      continue;
+    }
     b->levels[si].push_back(j);
   }
   if (ms->steps.size() < b->levels.size() && !b->frames.empty())
@@ -284,7 +410,7 @@ int launch_all(ModularBatch* b, cudaStream_t s, bool copy_to_host) {
       mw = std::max(mw, j.w);
       mh = std::max(mh, j.h);
     }
-    launch_modular_jobs(b->level_kind[l], jobs + job_cursor, uint32_t(b->levels[l].size()), mw, mh, B.planes, s);
+    launch_modular_jobs(b->level_kind[l] == 3 ? 4 : b->level_kind[l], jobs + job_cursor, uint32_t(b->levels[l].size()), mw, mh, B.planes, s);
     job_cursor += b->levels[l].size();
     launches++;
   }

@@ -29,11 +29,23 @@ struct MStreamDev {  // one ModularHF(group) section
   uint32_t first_rct, num_rct;
 };
 
+// Channel walk. The decisions of the MA tree on the channel index and the stream id are constant for a channel; when
+// what is left of the tree splits on ONE property (or is a single leaf) the host turns it into a table over that
+// property's value clamped to [-1024, 1023] - the device form of the reference's single-property specialisations
+// (frame/modular/decode/specialized_trees.rs:197-372: make_lut, GradientOnly, WpOnly, SingleGradientOnly), widened to any
+// of the per-pixel properties 2..15 and to arbitrary leaves.
+constexpr uint32_t kWalkGeneric = 0, kWalkLut = 1;
+constexpr uint32_t kLutNoProperty = 0xff;   // single leaf: `lut_off` holds the entry itself
+constexpr int32_t kLutMin = -1024, kLutSize = 2048;
+// Table entry: predictor | cluster << 4 | plain << 12 | leaf node index << 16 (plain: offset 0, multiplier 1).
+
 struct MRectDev {
   uint64_t base;  // element index of the rect origin in the plane arena
   uint32_t stride, w, h;
   uint32_t ref_first;  // into MBatchDev::refs: rects usable as reference channels (same shape, nearest first)
-  uint32_t ref_count, pad;
+  uint32_t ref_count;
+  uint32_t walk;       // kWalkGeneric | kWalkLut | property << 8
+  uint64_t lut_off;    // blob offset of u32[kLutSize] (kWalkLut with a property), or the single entry itself
 };
 
 struct MRctDev {
@@ -64,7 +76,7 @@ struct MBatchDev {
 };
 
 int launch_modular_decode(const MBatchDev& B, uint32_t lanes_per_warp, uint32_t num_rct_streams, cudaStream_t stream);
-// kind: 0 RCT, 1 horizontal unsqueeze, 2 vertical unsqueeze, 3 store
+// kind: 0 RCT, 1 horizontal unsqueeze, 2 vertical unsqueeze, 3 store, 4 palette look-up
 void launch_modular_jobs(int kind, const MJobDev* jobs, uint32_t num_jobs, uint32_t max_w, uint32_t max_h, int32_t* planes,
                          cudaStream_t stream);
 

@@ -78,8 +78,7 @@ struct MSym {  // symbol reader state of one stream (decode.rs:177-405 without L
   uint32_t use_prefix, log_alpha;
 };
 
-__device__ __forceinline__ uint32_t m_read_unsigned(MSym& s, uint32_t ctx) {
-  const uint32_t cluster = __ldg(s.cmap + ctx);
+__device__ __forceinline__ uint32_t m_read_clustered(MSym& s, uint32_t cluster) {
   uint32_t token;
   if (s.use_prefix) {  // huffman.rs:446-457
     const uint32_t* t = s.huff + __ldg(s.huff_offset + cluster);
@@ -120,6 +119,8 @@ __device__ __forceinline__ uint32_t m_read_unsigned(MSym& s, uint32_t ctx) {
   const uint32_t hi = ((token >> lsb) & ((1u << msb) - 1)) | (1u << msb);
   return (((hi << nbits) | bits) << lsb) | low;
 }
+
+__device__ __forceinline__ uint32_t m_read_unsigned(MSym& s, uint32_t ctx) { return m_read_clustered(s, __ldg(s.cmap + ctx)); }
 
 __device__ __forceinline__ int32_t m_unpack_signed(uint32_t u) { return int32_t((u >> 1) ^ (((~u) & 1u) - 1u)); }
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return int32_t(uint32_t(a) + uint32_t(b)); }
@@ -210,6 +211,107 @@ struct MWp {
   }
 };
 
+// predict.rs:148-194. nee is only read by predictor 13.
+__device__ __forceinline__ int64_t m_predict(uint32_t predictor, int64_t L, int64_t T, int64_t TL, int64_t TR, int32_t ww, int32_t nn,
+                                            int32_t nee, int64_t wp_pred) {
+  switch (predictor) {
+    case 0: return 0;
+    case 1: return L;
+    case 2: return T;
+    case 3: return (T + L) / 2;
+    case 4: {
+      const int64_t pp = L + T - TL;
+      return labs64(pp - L) < labs64(pp - T) ? L : T;
+    }
+    case 5: return clamped_gradient(L, T, TL);
+    case 6: return wp_pred;
+    case 7: return TR;
+    case 8: return TL;
+    case 9: return ww;
+    case 10: return (L + TL) / 2;
+    case 11: return (T + TL) / 2;
+    case 12: return (T + TR) / 2;
+    default: return (6 * T - 2 * int64_t(nn) + 7 * L + int64_t(ww) + int64_t(nee) + 3 * TR + 8) / 16;
+  }
+}
+
+// One channel whose tree walk is a table over one property (MRectDev::walk == kWalkLut): per pixel the property, one
+// table load (predictor, cluster, leaf), the predictor and the symbol. specialized_trees.rs:197-372 is the CPU form.
+template <bool WP>
+__device__ __forceinline__ void m_channel_lut(const MBatchDev& B, const MRectDev& rc, MSym& sym, MWp& wp, const int4* nodes) {
+  const uint32_t w = rc.w, h = rc.h, prop = rc.walk >> 8;
+  int32_t* const base = B.planes + rc.base;
+  const uint32_t* const lut = reinterpret_cast<const uint32_t*>(B.blob + rc.lut_off);
+  const uint32_t single = uint32_t(rc.lut_off);
+  for (uint32_t y = 0; y < h; y++) {
+    int32_t* const row = base + size_t(y) * rc.stride;
+    const int32_t* const top = y > 0 ? row - rc.stride : row;
+    const int32_t* const toptop = y > 1 ? top - rc.stride : top;
+    int32_t prev_p9 = 0;
+    const bool has_top = y > 0, has_tt = y > 1;
+    int32_t v_prev = 0, v_prev2 = 0;
+    int32_t t_prev = 0;
+    int32_t t_cur = has_top ? top[0] : 0;
+    int32_t t_next = (has_top && w > 1) ? top[1] : 0;
+    int32_t tt_cur = has_tt ? toptop[0] : 0;
+    const int32_t top0 = t_cur;
+    for (uint32_t x = 0; x < w; x++) {
+      const int32_t t_next2 = (has_top && x + 2 < w) ? top[x + 2] : 0;
+      const int32_t tt_next = (has_tt && x + 1 < w) ? toptop[x + 1] : 0;
+      const int32_t left = x > 0 ? v_prev : (has_top ? top0 : 0);
+      const int32_t n = has_top ? t_cur : left;
+      const int32_t nw = (x > 0 && has_top) ? t_prev : left;
+      const int32_t ne = (x + 1 < w && has_top) ? t_next : n;
+      const int32_t ww = x > 1 ? v_prev2 : left;
+      const int32_t nn = has_tt ? tt_cur : n;
+      int64_t wp_pred = 0;
+      int32_t wp_prop = 0;
+      if (WP) wp.predict(x, y, n, left, ne, nw, nn, wp_pred, wp_prop);
+      const int32_t p9 = wsub(wadd(left, n), nw);
+      uint32_t e = single;
+      if (prop != kLutNoProperty) {
+        int32_t v;
+        switch (prop) {  // tree.rs:189-280
+          case 2: v = int32_t(y); break;
+          case 3: v = int32_t(x); break;
+          case 4: v = wabs(n); break;
+          case 5: v = wabs(left); break;
+          case 6: v = n; break;
+          case 7: v = left; break;
+          case 8: v = wsub(left, prev_p9); break;
+          case 9: v = p9; break;
+          case 10: v = wsub(left, nw); break;
+          case 11: v = wsub(nw, n); break;
+          case 12: v = wsub(n, ne); break;
+          case 13: v = wsub(n, nn); break;
+          case 14: v = wsub(left, ww); break;
+          default: v = wp_prop; break;
+        }
+        e = __ldg(lut + uint32_t(min(max(v, kLutMin), kLutMin + kLutSize - 1) - kLutMin));
+      }
+      prev_p9 = p9;
+      const int32_t nee = (x + 2 < w && has_top) ? t_next2 : ne;
+      int64_t guess = m_predict(e & 15u, left, n, nw, ne, ww, nn, nee, wp_pred);
+      const int32_t dec = m_unpack_signed(m_read_clustered(sym, (e >> 4) & 255u));
+      int32_t val;
+      if (e & (1u << 12)) {
+        val = int32_t(guess + int64_t(dec));
+      } else {
+        const int4 leaf = __ldg(nodes + (e >> 16));
+        val = int32_t(guess + int64_t(leaf.y) + int64_t(uint32_t(leaf.w)) * int64_t(dec));  // decode/common.rs:85
+      }
+      if (WP) wp.update(val, x, y);
+      row[x] = val;
+      v_prev2 = v_prev;
+      v_prev = val;
+      t_prev = t_cur;
+      t_cur = t_next;
+      t_next = t_next2;
+      tt_cur = tt_next;
+    }
+  }
+}
+
 }  // namespace
 
 // One lane per stream; lanes >= S of a warp idle. Persistent: finished lanes pull the next stream from B.queue.
@@ -262,6 +364,11 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
         wp.err = reinterpret_cast<int32_t*>(wp.perr + size_t(w + 1) * 8);
         for (uint32_t i = 0; i < (w + 1) * 8; i++) wp.perr[i] = 0;
         for (uint32_t i = 0; i < (w + 1) * 2; i++) wp.err[i] = 0;
+      }
+      if ((rc.walk & 0xff) == kWalkLut) {
+        if (use_wp) m_channel_lut<true>(B, rc, sym, wp, nodes);
+        else m_channel_lut<false>(B, rc, sym, wp, nodes);
+        continue;
       }
       for (uint32_t y = 0; y < h; y++) {
         int32_t* const row = base + size_t(y) * rc.stride;
@@ -558,6 +665,60 @@ int launch_modular_decode(const MBatchDev& B, uint32_t lanes_per_warp, uint32_t 
   return launches;
 }
 
+// transforms/palette.rs:17-163 get_palette_value for 8-bit samples: explicit entries, the implicit 4x4x4 and 5x5x5
+// colour cubes behind them, the 72-entry delta table for negative indices.
+__constant__ int16_t c_palette_delta[72][3] = {
+    {0, 0, 0},       {4, 4, 4},       {11, 0, 0},      {0, 0, -13},     {0, -12, 0},     {-10, -10, -10},
+    {-18, -18, -18}, {-27, -27, -27}, {-18, -18, 0},   {0, 0, -32},     {-32, 0, 0},     {-37, -37, -37},
+    {0, -32, -32},   {24, 24, 45},    {50, 50, 50},    {-45, -24, -24}, {-24, -45, -45}, {0, -24, -24},
+    {-34, -34, 0},   {-24, 0, -24},   {-45, -45, -24}, {64, 64, 64},    {-32, 0, -32},   {0, -32, 0},
+    {-32, 0, 32},    {-24, -45, -24}, {45, 24, 45},    {24, -24, -45},  {-45, -24, 24},  {80, 80, 80},
+    {64, 0, 0},      {0, 0, -64},     {0, -64, -64},   {-24, -24, 45},  {96, 96, 96},    {64, 64, 0},
+    {45, -24, -24},  {34, -34, 0},    {112, 112, 112}, {24, -45, -45},  {45, 45, -24},   {0, -32, 32},
+    {24, -24, 45},   {0, 96, 96},     {45, -24, 24},   {24, -45, -24},  {-24, -45, 24},  {0, -64, 0},
+    {96, 0, 0},      {128, 128, 128}, {64, 0, 64},     {144, 144, 144}, {96, 96, 0},     {-36, -36, 36},
+    {45, -24, -45},  {45, -45, -24},  {0, 0, -96},     {0, 128, 128},   {0, 96, 0},      {45, 24, -45},
+    {-128, 0, 0},    {24, -45, 24},   {-45, 24, -45},  {64, 0, -64},    {64, -64, -64},  {96, 0, 96},
+    {45, -45, 24},   {24, 45, -45},   {64, 64, -64},   {128, 128, 0},   {0, 0, -128},    {-24, 45, -45},
+};
+
+__device__ __forceinline__ int32_t palette_value8(const int32_t* pal, uint32_t pal_stride, int32_t index, uint32_t c, uint32_t palette_size) {
+  if (index < 0) {
+    if (c >= 3) return 0;
+    uint32_t idx = uint32_t(-(int64_t(index) + 1));
+    idx %= 1 + 2 * (72 - 1);
+    const int32_t d = c_palette_delta[(idx + 1) >> 1][c];
+    return (idx & 1) ? d : -d;
+  }
+  uint32_t idx = uint32_t(index);
+  if (idx >= palette_size && idx < palette_size + 64) {  // small cube
+    if (c >= 3) return 0;
+    idx -= palette_size;
+    idx >>= c * 2;
+    return int32_t(((idx % 4) * 255u) >> 2) + 32;
+  }
+  if (idx >= palette_size + 64) {  // large cube
+    if (c >= 3) return 0;
+    idx -= palette_size + 64;
+    if (c == 1) idx /= 5;
+    if (c == 2) idx /= 25;
+    return int32_t(((idx % 5) * 255u) >> 2);
+  }
+  return pal[size_t(c) * pal_stride + idx];
+}
+
+// Inverse palette without delta entries (palette.rs:165-199): out[c][p] = palette_value(index[p], c). One job per colour
+// channel (blockIdx.y), grid-stride over the pixels.
+__global__ void __launch_bounds__(256) k_modular_palette(const MJobDev* jobs, int32_t* planes) {
+  const MJobDev j = jobs[blockIdx.y];
+  const size_t n = size_t(j.w) * j.h;
+  const int32_t* index = planes + j.a;
+  const int32_t* pal = planes + j.b;
+  int32_t* out = planes + j.c;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    out[i] = palette_value8(pal, uint32_t(j.out_stride), index[i], j.op, j.rw);
+}
+
 void launch_modular_jobs(int kind, const MJobDev* jobs, uint32_t num_jobs, uint32_t max_w, uint32_t max_h, int32_t* planes,
                          cudaStream_t stream) {
   if (!num_jobs) return;
@@ -568,6 +729,9 @@ void launch_modular_jobs(int kind, const MJobDev* jobs, uint32_t num_jobs, uint3
     k_unsqueeze_h<<<dim3((max_h + 127) / 128, num_jobs), 128, 0, stream>>>(jobs, planes);
   } else if (kind == 2) {
     k_unsqueeze_v<<<dim3((max_w + 127) / 128, num_jobs), 128, 0, stream>>>(jobs, planes);
+  } else if (kind == 4) {
+    const uint32_t gx = uint32_t(min((size_t(max_w) * max_h + 255) / 256, size_t(148 * 16)));
+    k_modular_palette<<<dim3(max(gx, 1u), num_jobs), 256, 0, stream>>>(jobs, planes);
   } else {
     const uint32_t gx = uint32_t(min((size_t(max_w) * max_h + 255) / 256, size_t(148 * 16)));
     k_modular_store<<<dim3(max(gx, 1u), num_jobs), 256, 0, stream>>>(jobs, planes);

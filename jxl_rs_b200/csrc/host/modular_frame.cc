@@ -179,7 +179,25 @@ void build_inverse_plan(ModularFrameState& ms) {
       cur[b + (perm + 1 + perm / 3) % 3] = ids[1];
       cur[b + (perm + 2 - perm / 3) % 3] = ids[2];
     } else if (t.id == 1) {
-      return;  // palette: no device plan (device_unsupported is set by the caller)
+      // transforms/palette.rs:165-199 (num_deltas == 0 and the Zero predictor: a per-pixel look-up). Delta entries predict
+      // from already reconstructed neighbours, a raster-order chain over the whole image: no device form.
+      const size_t bi = size_t(t.begin_channel) + 1;
+      if (t.num_deltas != 0 || t.predictor_id != 0 || bi >= cur.size() || t.num_channels == 0) {
+        ms.device_plan_ok = false;
+        return;
+      }
+      ModularStep s;
+      s.kind = 3;
+      s.a = cur[bi];
+      s.b = cur[0];
+      s.c = uint32_t(ms.bufs.size());
+      s.n = t.num_channels;
+      s.num_colors = t.num_colors;
+      for (uint32_t c = 0; c < t.num_channels; c++) ms.bufs.push_back(ModularBuf{ms.bufs[s.a].w, ms.bufs[s.a].h});
+      ms.steps.push_back(s);
+      cur.erase(cur.begin() + bi);
+      for (uint32_t c = 0; c < t.num_channels; c++) cur.insert(cur.begin() + bi + c, s.c + c);
+      cur.erase(cur.begin());
     } else {
       for (size_t si = t.squeezes.size(); si-- > 0;) {
         const SqueezeParams& sq = t.squeezes[si];

@@ -39,12 +39,15 @@ struct ModularBuf {
   uint32_t w = 0, h = 0;
 };
 struct ModularStep {
-  uint32_t kind = 0;  // 0 RCT (in place on a,b,c), 1 horizontal unsqueeze (a avg, b residual -> c), 2 vertical
+  uint32_t kind = 0;  // 0 RCT (in place on a,b,c), 1 horizontal unsqueeze (a avg, b residual -> c), 2 vertical,
+                      // 3 palette without delta entries (a index channel, b palette, c .. c + n - 1 the colour channels)
   uint32_t a = 0, b = 0, c = 0;
   uint32_t rct_op = 0;
+  uint32_t n = 0, num_colors = 0;  // palette: colour channels, explicit palette entries
 };
 
 struct ModularFrameState {
+  bool device_plan_ok = true;  // false: a global transform has no device form (delta palettes): the device path refuses the frame
   FileHeader file;
   FrameHeader header;
   Toc toc;

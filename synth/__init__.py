@@ -23,6 +23,10 @@ def _lib():
         _LIB.jxs_encode_modular.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.c_void_p, C.c_void_p, C.c_size_t]
         _LIB.jxs_modular_source.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+        _LIB.jxs_modular_source_ex.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
+        _LIB.jxs_encode_modular_ex.restype = C.c_int64
+        _LIB.jxs_encode_modular_ex.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.c_void_p, C.c_void_p, C.c_size_t]
         _LIB.jxs_modular_last_error.restype = C.c_char_p
     return _LIB
 
@@ -55,20 +59,22 @@ def set_threads(n: int):
     _lib().jxs_set_threads(int(n))
 
 
-def modular_source(width, height, seed):
-    """The 8-bit RGB image (H x W x 3 numpy array) the synthetic Modular frame of `seed` encodes losslessly."""
+def modular_source(width, height, seed, palette=0):
+    """The 8-bit RGB image (H x W x 3 numpy array) the synthetic Modular frame of `seed` encodes losslessly
+    (palette=1: the picture snapped to palette colours that encode_modular(..., palette=1) carries)."""
     import numpy as np
     lib = _lib()
     out = np.zeros((height, width, 3), np.uint8)
-    if lib.jxs_modular_source(width, height, seed, out.ctypes.data) != 0:
+    if lib.jxs_modular_source_ex(width, height, seed, palette, out.ctypes.data) != 0:
         raise RuntimeError("synthetic source failed: " + lib.jxs_modular_last_error().decode())
     return out
 
 
-def encode_modular(width, height, seed, rct=6, squeeze=0, tree_kind=1, source=None) -> bytes:
+def encode_modular(width, height, seed, rct=6, squeeze=0, tree_kind=1, source=None, palette=0) -> bytes:
     """One synthetic lossless Modular frame (8-bit RGB, group size 256). rct: 0 or 6 (YCoCg); squeeze: default
     Squeeze transform on/off; tree_kind: 0 single Gradient leaf, 1 property tree, 2 weighted-predictor tree,
-    3 tree on properties of the previous channel (17, 19).
+    3 tree on properties of the previous channel (17, 19); palette: 1 = global palette transform over the colour
+    channels (explicit entries + both implicit colour cubes, no delta entries; rct and squeeze must be 0).
     source: optional H x W x 3 uint8 array to encode instead of the procedural image."""
     lib = _lib()
     src = None
@@ -79,10 +85,10 @@ def encode_modular(width, height, seed, rct=6, squeeze=0, tree_kind=1, source=No
         src = source.ctypes.data
     cap = max(1 << 16, width * height * 4)
     buf = C.create_string_buffer(cap)
-    n = lib.jxs_encode_modular(width, height, seed, rct, squeeze, tree_kind, src, buf, cap)
+    n = lib.jxs_encode_modular_ex(width, height, seed, rct, squeeze, tree_kind, palette, src, buf, cap)
     if n < 0:
         raise RuntimeError("synthetic Modular encode failed: " + lib.jxs_modular_last_error().decode())
     if n > cap:
         buf = C.create_string_buffer(n)
-        n = lib.jxs_encode_modular(width, height, seed, rct, squeeze, tree_kind, src, buf, n)
+        n = lib.jxs_encode_modular_ex(width, height, seed, rct, squeeze, tree_kind, palette, src, buf, n)
     return buf.raw[:n]

@@ -271,6 +271,20 @@ void write_group_header(BitWriter& bw, const std::vector<jxg::ModularTransform>&
       else if (t.rct_type < 4) { bw.write(1, 2); bw.write(t.rct_type, 2); }
       else if (t.rct_type < 18) { bw.write(2, 2); bw.write(t.rct_type - 2, 4); }
       else { bw.write(3, 2); bw.write(t.rct_type - 10, 6); }
+    } else if (t.id == 1) {  // headers/modular.rs:85-117
+      bw.write(0, 2);  // begin_channel selector 0: 3 bits
+      bw.write(t.begin_channel, 3);
+      if (t.num_channels == 1) bw.write(0, 2);
+      else if (t.num_channels == 3) bw.write(1, 2);
+      else if (t.num_channels == 4) bw.write(2, 2);
+      else { bw.write(3, 2); bw.write(t.num_channels - 1, 13); }
+      if (t.num_colors < 256) { bw.write(0, 2); bw.write(t.num_colors, 8); }
+      else if (t.num_colors < 1280) { bw.write(1, 2); bw.write(t.num_colors - 256, 10); }
+      else if (t.num_colors < 5376) { bw.write(2, 2); bw.write(t.num_colors - 1280, 12); }
+      else { bw.write(3, 2); bw.write(t.num_colors - 5376, 16); }
+      if (t.num_deltas != 0) throw std::runtime_error("the synthetic writer has no delta palettes");
+      bw.write(0, 2);  // num_deltas = 0
+      bw.write(t.predictor_id, 4);
     } else {
       bw.write(0, 2);  // Squeeze with default parameters (num_sq = 0)
     }
@@ -296,11 +310,24 @@ bool is_meta(const ModularChannel& c) { return c.hshift < 0 || c.vshift < 0; }
 
 }  // namespace
 
+// Snaps the picture to colours a palette transform without delta entries can carry three ways: the left quarter to the
+// implicit 4x4x4 cube (levels 32, 95, 159, 223), the rest to the levels of the implicit 5x5x5 cube (0, 63, 127, 191, 255).
+void snap_to_palette_colours(uint32_t W, uint32_t H, std::vector<uint8_t>& rgb) {
+  for (uint32_t y = 0; y < H; y++)
+    for (uint32_t x = 0; x < W; x++)
+      for (int c = 0; c < 3; c++) {
+        uint8_t& v = rgb[(size_t(y) * W + x) * 3 + c];
+        if (x < W / 4) v = uint8_t((((uint32_t(v) * 4) >> 8) * 255u >> 2) + 32);
+        else v = uint8_t((((uint32_t(v) * 5) >> 8) * 255u) >> 2);
+      }
+}
+
 std::vector<uint8_t> encode_modular(uint32_t W, uint32_t H, uint64_t seed, uint32_t rct_type, uint32_t squeeze,
-                                    uint32_t tree_kind, const uint8_t* source_rgb) {
+                                    uint32_t tree_kind, const uint8_t* source_rgb, uint32_t palette) {
   std::vector<uint8_t> rgb;
   if (source_rgb) rgb.assign(source_rgb, source_rgb + size_t(W) * H * 3);
   else make_image_u8(W, H, seed, rgb);
+  if (palette && !source_rgb) snap_to_palette_colours(W, H, rgb);
   const uint32_t group_dim = 256;
   const uint32_t xg = (W + group_dim - 1) / group_dim, yg = (H + group_dim - 1) / group_dim, num_groups = xg * yg;
   const uint32_t lf_dim = group_dim * 8;
@@ -314,6 +341,51 @@ std::vector<uint8_t> encode_modular(uint32_t W, uint32_t H, uint64_t seed, uint3
   }
   jxg::GroupHeader gh;
   gh.use_global_tree = true;
+  if (palette) {
+    // Forward palette over the three colour channels (meta_apply.rs:181-230 / palette.rs:165-199 inverted), no delta
+    // entries, Zero predictor. Colours on the 5x5x5 cube with an odd level sum and all colours on the 4x4x4 cube use
+    // the implicit entries behind the explicit ones; everything else gets an explicit entry.
+    if (rct_type || squeeze) throw std::runtime_error("the synthetic palette variant takes no other global transform");
+    auto cube5 = [](int32_t v) { return v == 0 ? 0 : v == 63 ? 1 : v == 127 ? 2 : v == 191 ? 3 : v == 255 ? 4 : -1; };
+    auto cube4 = [](int32_t v) { return v == 32 ? 0 : v == 95 ? 1 : v == 159 ? 2 : v == 223 ? 3 : -1; };
+    std::vector<uint32_t> colours;  // explicit entries, first appearance order
+    std::vector<int32_t> entry_of(1u << 24, -1);
+    std::vector<int32_t> pending(size_t(W) * H, 0);
+    for (size_t i = 0; i < size_t(W) * H; i++) {
+      const int32_t r = ch[0].data[i], g = ch[1].data[i], b = ch[2].data[i];
+      const int a5 = cube5(r), b5 = cube5(g), c5 = cube5(b), a4 = cube4(r), b4 = cube4(g), c4 = cube4(b);
+      if (a4 >= 0 && b4 >= 0 && c4 >= 0) pending[i] = -1 - (a4 | (b4 << 2) | (c4 << 4));            // small cube
+      else if (a5 >= 0 && b5 >= 0 && c5 >= 0 && ((a5 + b5 + c5) & 1)) pending[i] = -100 - (a5 + 5 * b5 + 25 * c5);  // large cube
+      else {
+        const uint32_t key = uint32_t(r) | (uint32_t(g) << 8) | (uint32_t(b) << 16);
+        if (entry_of[key] < 0) {
+          entry_of[key] = int32_t(colours.size());
+          colours.push_back(key);
+        }
+        pending[i] = entry_of[key];
+      }
+    }
+    if (colours.empty()) colours.push_back(0);
+    if (colours.size() > 5376) throw std::runtime_error("too many colours for the synthetic palette variant");
+    const uint32_t N = uint32_t(colours.size());
+    for (size_t i = 0; i < size_t(W) * H; i++) {
+      const int32_t p = pending[i];
+      ch[0].data[i] = p >= 0 ? p : (p > -100 ? int32_t(N) + (-1 - p) : int32_t(N) + 64 + (-100 - p));
+    }
+    ch.erase(ch.begin() + 1, ch.begin() + 3);
+    ModularChannel pal(N, 3, -1, -1);
+    for (uint32_t i = 0; i < N; i++)
+      for (int c = 0; c < 3; c++) pal.row(uint32_t(c))[i] = int32_t((colours[i] >> (8 * c)) & 0xff);
+    ch.insert(ch.begin(), std::move(pal));
+    jxg::ModularTransform t;
+    t.id = 1;
+    t.begin_channel = 0;
+    t.num_channels = 3;
+    t.num_colors = N;
+    t.num_deltas = 0;
+    t.predictor_id = 0;
+    gh.transforms.push_back(t);
+  }
   if (rct_type) {
     if (rct_type != 6) throw std::runtime_error("the synthetic writer only has the forward YCoCg RCT (type 6)");
     jxg::ModularTransform t;
@@ -526,6 +598,19 @@ static thread_local std::string g_merr;
 const char* jxs_modular_last_error() { return g_merr.c_str(); }
 
 // The 8-bit RGB source image of seed `seed` (interleaved), what a lossless decode must reproduce.
+int jxs_modular_source_ex(uint32_t width, uint32_t height, uint64_t seed, uint32_t palette, uint8_t* out_rgb) {
+  try {
+    std::vector<uint8_t> rgb;
+    jxs::make_image_u8(width, height, seed, rgb);
+    if (palette) jxs::snap_to_palette_colours(width, height, rgb);
+    memcpy(out_rgb, rgb.data(), rgb.size());
+    return 0;
+  } catch (std::exception& e) {
+    g_merr = e.what();
+    return -1;
+  }
+}
+
 int jxs_modular_source(uint32_t width, uint32_t height, uint64_t seed, uint8_t* out_rgb) {
   try {
     std::vector<uint8_t> rgb;
@@ -543,7 +628,21 @@ int jxs_modular_source(uint32_t width, uint32_t height, uint64_t seed, uint8_t* 
 int64_t jxs_encode_modular(uint32_t width, uint32_t height, uint64_t seed, uint32_t rct, uint32_t squeeze,
                            uint32_t tree_kind, const uint8_t* source_rgb, uint8_t* out, size_t cap) {
   try {
-    std::vector<uint8_t> b = jxs::encode_modular(width, height, seed, rct, squeeze, tree_kind, source_rgb);
+    std::vector<uint8_t> b = jxs::encode_modular(width, height, seed, rct, squeeze, tree_kind, source_rgb, 0);
+    if (b.size() <= cap && out) memcpy(out, b.data(), b.size());
+    return int64_t(b.size());
+  } catch (std::exception& e) {
+    g_merr = e.what();
+    return -1;
+  }
+}
+
+// palette: 1 = forward palette over the three colour channels (no delta entries); the picture is first snapped to
+// colours of the implicit cubes / a few hundred explicit entries (jxs_modular_source_ex returns that picture).
+int64_t jxs_encode_modular_ex(uint32_t width, uint32_t height, uint64_t seed, uint32_t rct, uint32_t squeeze,
+                              uint32_t tree_kind, uint32_t palette, const uint8_t* source_rgb, uint8_t* out, size_t cap) {
+  try {
+    std::vector<uint8_t> b = jxs::encode_modular(width, height, seed, rct, squeeze, tree_kind, source_rgb, palette);
     if (b.size() <= cap && out) memcpy(out, b.data(), b.size());
     return int64_t(b.size());
   } catch (std::exception& e) {

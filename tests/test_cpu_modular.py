@@ -47,6 +47,19 @@ def test_lossless_roundtrip(w, h, rct, sq, tk):
     assert np.array_equal(ob.decode_modular_file(data), synth.modular_source(w, h, 11))
 
 
+@pytest.mark.parametrize("w,h,tk", [(300, 260, 1), (64, 48, 0), (700, 530, 2), (1030, 600, 3)])
+def test_palette_roundtrip_uses_explicit_and_implicit_entries(w, h, tk):
+    """Writer's palette variant (explicit entries + the 4x4x4 and 5x5x5 implicit cubes, palette.rs:17-163) -> oracle ==
+    the snapped source picture; the index channel really holds indices of all three kinds."""
+    import synth
+    from tests import oracle_binding as ob
+    data = synth.encode_modular(w, h, 12, 0, 0, tk, palette=1)
+    src = synth.modular_source(w, h, 12, palette=1)
+    assert np.array_equal(ob.decode_modular_file(data), src)
+    left, right = src[:, :w // 4].reshape(-1), src[:, w // 4:].reshape(-1)
+    assert set(np.unique(left)) <= {32, 95, 159, 223} and set(np.unique(right)) <= {0, 63, 127, 191, 255}
+
+
 def test_roundtrip_of_extreme_values():
     """Caller-supplied image with saturated checkerboards and flat areas (largest residuals, zero residuals)."""
     import synth

@@ -61,6 +61,22 @@ def test_synthetic_modular_parity(ctx, case):
         assert np.array_equal(out, src)
 
 
+@pytest.mark.parametrize("case", [(300, 260, 21, 1), (700, 530, 22, 2), (1030, 770, 23, 0)])
+def test_palette_without_delta_entries_on_the_device(ctx, case):
+    """a19: the global palette transform as a device look-up (transforms/palette.rs:165-199): explicit entries and both
+    implicit colour cubes, index channel decoded by the group streams, palette meta channel by the host front-end."""
+    import synth
+    from tests import oracle_binding as ob
+    w, h, seed, tk = case
+    data = synth.encode_modular(w, h, seed, 0, 0, tk, palette=1)
+    src = synth.modular_source(w, h, seed, palette=1)
+    ref, ref_planes = ob.decode_modular_file(data, planes=True)
+    assert np.array_equal(ref, src)
+    (out,), (planes,) = gpu_decode(ctx, [data])
+    assert np.array_equal(planes, ref_planes)
+    assert np.array_equal(out, src)
+
+
 @pytest.mark.parametrize("name", ["green_queen_modular_e3.jxl", "grayscale_public_university.jxl", "issue865_large_toc.jxl",
                                   "3x3_srgb_lossless.jxl", "lz77_flower.jxl", "tree_max_property_20.jxl"])
 def test_real_modular_files(ctx, golden_dir, name):

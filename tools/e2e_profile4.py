@@ -34,10 +34,13 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     t0 = time.perf_counter()
     for i in range(steps):
         submit(dec, i)
+    t_sub = time.perf_counter()
     dec.drain()
+    t_drain = time.perf_counter()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"staging_threads={st}: {dt/steps*1e3:.1f} ms/step, {n*3840*2160/1e6*steps/dt:.0f} MP/s")
+    print(f"  main thread: submits done at {1e3*(t_sub-t0):.1f} ms, drain returned at {1e3*(t_drain-t0):.1f}, device idle at {1e3*dt:.1f}")
     for (ts, ret, pw, add, run) in dec.trace:
         print(f"  t={1e3*(ts-t0):7.1f}  retire {ret*1e3:6.1f}  parsewait {pw*1e3:6.1f}  add {add*1e3:6.1f}  run {run*1e3:6.1f}")
     for (ts, w, m, c) in dec.retire_trace:
