@@ -58,7 +58,11 @@ enum {
   JXG_FORMAT_RGB_U8 = 0,   /* interleaved sRGB-encoded u8, 3 B/px  (convert.rs:548) */
   JXG_FORMAT_RGBA_U8 = 1,  /* + opaque alpha 255 (fill_opaque_alpha, render.rs:858) */
   JXG_FORMAT_RGB_F32 = 2,  /* interleaved f32, 12 B/px; linear sRGB unless tf set   */
-  JXG_FORMAT_XYB_F32_PLANAR = 3 /* debug/parity tap: the 3 XYB planes after filters */
+  JXG_FORMAT_XYB_F32_PLANAR = 3, /* debug/parity tap: the 3 XYB planes after filters */
+  JXG_FORMAT_RGB_U16 = 4,  /* interleaved u16 (native endian), 6 B/px: clamp to [0,1], x 65535, round
+                              (ConvertF32ToU16Stage, convert.rs:717-786, bit_depth 16; no dither) */
+  JXG_FORMAT_RGB_F16 = 5   /* interleaved IEEE half, 6 B/px (ConvertF32ToF16Stage, convert.rs:789-857); PQ output
+                              is clamped to [0,1], HLG to [-0.074, 1.1] first (frame/render.rs:746-750) */
 };
 
 /* Output transfer function (render/stages/from_linear.rs). */

@@ -392,8 +392,11 @@ static int add_frame_impl(void* bp, const JxgFrameDesc* d, const uint8_t* hf_byt
   F.plane_rows = F.yb * 8;
   F.cxb = (F.xb + 7) / 8;
   const size_t nb = size_t(F.xb) * F.yb, ncm = size_t(F.cxb) * ((F.yb + 7) / 8);
-  if (d->output_format > JXG_FORMAT_XYB_F32_PLANAR) return set_error(JXG_ERR_ARGUMENT, "unknown output format");
-  size_t bpp = d->output_format == JXG_FORMAT_RGB_U8 ? 3 : d->output_format == JXG_FORMAT_RGBA_U8 ? 4 : d->output_format == JXG_FORMAT_RGB_F32 ? 12 : 4;
+  if (d->output_format > JXG_FORMAT_RGB_F16) return set_error(JXG_ERR_ARGUMENT, "unknown output format");
+  size_t bpp = d->output_format == JXG_FORMAT_RGB_U8 ? 3
+               : d->output_format == JXG_FORMAT_RGBA_U8 ? 4
+               : d->output_format == JXG_FORMAT_RGB_F32 ? 12
+               : (d->output_format == JXG_FORMAT_RGB_U16 || d->output_format == JXG_FORMAT_RGB_F16) ? 6 : 4;
   if (d->orientation > 8) return set_error(JXG_ERR_ARGUMENT, "orientation must be 1..8");
   const uint32_t orientation = (d->orientation == 0 || d->output_format == JXG_FORMAT_XYB_F32_PLANAR) ? 1u : d->orientation;
   const uint32_t disp_w = orientation >= 5 ? F.height : F.width, disp_h = orientation >= 5 ? F.width : F.height;

@@ -12,6 +12,7 @@
 //
 // No tensor cores: there is no dense contraction on this path; everything is
 // HBM / latency bound integer and f32 work.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -2422,6 +2423,25 @@ __device__ __noinline__ void from_linear_other(const FrameDev& F, float (&v)[3])
 }
 
 // xyb.rs:197-241 + from_linear + convert.rs:574-598 + save (interleave)
+// 16-bit stores of one colour sample. U16: ConvertF32ToU16Stage (convert.rs:739-762: clamp to [0, 1], scale by
+// 2^16 - 1, round to nearest, ties to even like the AVX2 store). F16: ConvertF32ToF16Stage (convert.rs:831-857) with the
+// clamp range frame/render.rs:746-750 gives PQ and HLG outputs.
+__device__ __forceinline__ uint16_t sample16(const FrameDev& F, float v) {
+  if (F.output_format == JXG_FORMAT_RGB_U16) return uint16_t(__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 65535.0f));
+  if (F.output_tf == JXG_TF_PQ) v = fminf(fmaxf(v, 0.0f), 1.0f);
+  else if (F.output_tf == JXG_TF_HLG) v = fminf(fmaxf(v, -0.074f), 1.1f);
+  // util/float16.rs:82-141: round to nearest even for normal halves, but the reference TRUNCATES into the subnormal range
+  // (and shifts one bit too far: 2^-15 becomes 2^-16 - reproduced, identical output is the contract)
+  const uint32_t bits = __float_as_uint(v), mag = bits & 0x7fffffffu;
+  if (mag < 0x38800000u) {  // |v| < 2^-14
+    const uint32_t sign = (bits >> 16) & 0x8000u;
+    const int unbiased = int(mag >> 23) - 127;
+    if ((mag >> 23) == 0 || unbiased < -24) return uint16_t(sign);
+    return uint16_t(sign | (((mag & 0x007fffffu) | 0x00800000u) >> (uint32_t(-14 - unbiased) + 14)));
+  }
+  return __half_as_ushort(__float2half_rn(v));
+}
+
 __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileDev T, const float* src) {
   uint32_t f;
   int x, y;
@@ -2458,6 +2478,12 @@ __global__ void __launch_bounds__(256) k_xyb_store(const BatchDev B, const TileD
     dst[0] = v[0];
     dst[1] = v[1];
     dst[2] = v[2];
+    return;
+  }
+  if (F.output_format == JXG_FORMAT_RGB_U16 || F.output_format == JXG_FORMAT_RGB_F16) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(row) + size_t(x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) dst[c] = sample16(F, v[c]);
     return;
   }
   uint8_t px[4];
@@ -2736,7 +2762,8 @@ __device__ __forceinline__ void filter_tile(const BatchDev& B, const FrameDev& F
     return;
   }
   uint8_t* stage_u8 = reinterpret_cast<uint8_t*>(nxt);  // free buffer: interleaved output staging (<= 24 KB)
-  const int bpp = F.output_format == JXG_FORMAT_RGB_U8 ? 3 : (F.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 12);
+  const bool fmt16 = F.output_format == JXG_FORMAT_RGB_U16 || F.output_format == JXG_FORMAT_RGB_F16;
+  const int bpp = F.output_format == JXG_FORMAT_RGB_U8 ? 3 : (F.output_format == JXG_FORMAT_RGBA_U8 ? 4 : (fmt16 ? 6 : 12));
   for (int idx = threadIdx.x; idx < kTW * th; idx += blockDim.x) {
     const int lx = idx % kTW, ly = idx / kTW;
     if (lx >= tw) continue;
@@ -2764,6 +2791,10 @@ __device__ __forceinline__ void filter_tile(const BatchDev& B, const FrameDev& F
       d[0] = v[0];
       d[1] = v[1];
       d[2] = v[2];
+    } else if (bpp == 6) {
+      uint16_t* d = reinterpret_cast<uint16_t*>(stage_u8) + (ly * kTW + lx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; c++) d[c] = sample16(F, v[c]);
     } else {
       uint8_t* d = stage_u8 + (ly * kTW + lx) * bpp;
 #pragma unroll
@@ -3143,7 +3174,8 @@ __device__ __forceinline__ TileRef locate_tile(const BatchDev& B, const FusedTil
   // 16-byte accesses need an aligned output row (RGB8: stride and base multiples of 4, f32 / RGBA: of 16)
   const uintptr_t oa = reinterpret_cast<uintptr_t>(F.out_ptr) | uintptr_t(F.out_row_stride);
   const bool aligned = F.output_format == JXG_FORMAT_RGB_U8 ? (oa & 3) == 0 : (oa & 15) == 0;
-  r.vec = GAB && EPF == 2 && interior && aligned;
+  const bool vec_format = F.output_format <= JXG_FORMAT_XYB_F32_PLANAR;  // the 16-bit stores take the generic path
+  r.vec = GAB && EPF == 2 && interior && aligned && vec_format;
   return r;
 }
 

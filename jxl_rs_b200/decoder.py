@@ -18,13 +18,13 @@ from . import abi
 class JxlPixelFormat:
     """jxl/src/api/data_types.rs:154 (colour part only)."""
     color_type: str = "RGB"          # "RGB" | "RGBA"
-    data_format: str = "U8"          # "U8" | "F32"
+    data_format: str = "U8"          # "U8" | "U16" | "F16" | "F32" (JxlDataFormat, 16-bit samples in native endianness)
 
     def abi_format(self):
         if self.data_format == "U8":
             return abi.FORMAT_RGBA_U8 if self.color_type == "RGBA" else abi.FORMAT_RGB_U8
-        if self.data_format == "F32" and self.color_type == "RGB":
-            return abi.FORMAT_RGB_F32
+        if self.color_type == "RGB" and self.data_format in ("F32", "U16", "F16"):
+            return {"F32": abi.FORMAT_RGB_F32, "U16": abi.FORMAT_RGB_U16, "F16": abi.FORMAT_RGB_F16}[self.data_format]
         raise ValueError(f"unsupported pixel format {self}")
 
 
@@ -188,7 +188,7 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
     try:  # a corrupt frame must not leave the context with a live batch
         for fr in frames:
             ch = 4 if fmt == abi.FORMAT_RGBA_U8 else 3
-            dt = torch.float32 if fmt == abi.FORMAT_RGB_F32 else torch.uint8
+            dt = {abi.FORMAT_RGB_F32: torch.float32, abi.FORMAT_RGB_U16: torch.uint16, abi.FORMAT_RGB_F16: torch.float16}.get(fmt, torch.uint8)
             if to_host:
                 t = torch.empty((fr.height, fr.width, ch), dtype=dt).pin_memory()
             else:

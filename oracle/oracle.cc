@@ -925,8 +925,32 @@ inline void from_linear_other(const JxgFrameDesc& d, float* v) {
     default: break;  // JXG_TF_LINEAR: no stage (frame/render.rs:761)
   }
 }
+// util/float16.rs:82-141 f16::from_f32: round to nearest even for normal halves, TRUNCATION into the subnormal range
+// (2^-24 <= |f| < 2^-14; the reference shifts one bit too far there, so those values also come out halved - kept),
+// zero below it and for f32 subnormals, infinity above 65504 + half an ulp.
+static uint16_t f32_to_f16_bits(float f) {
+  uint32_t bits;
+  memcpy(&bits, &f, 4);
+  const uint16_t sign = uint16_t((bits >> 31) & 1);
+  const int exp = int((bits >> 23) & 0xff);
+  const uint32_t mant = bits & 0x007fffffu;
+  if (exp == 0) return uint16_t(sign << 15);
+  if (exp == 255) return uint16_t((sign << 15) | (0x1f << 10) | (mant ? 0x0200 : 0));
+  const int unbiased = exp - 127;
+  if (unbiased < -24) return uint16_t(sign << 15);
+  if (unbiased < -14) return uint16_t((sign << 15) | uint16_t((mant | 0x00800000u) >> (uint32_t(-14 - unbiased) + 14)));
+  if (unbiased > 15) return uint16_t((sign << 15) | (0x1f << 10));
+  const uint16_t h_exp = uint16_t(unbiased + 15);
+  uint16_t h_mant = uint16_t(mant >> 13);
+  const uint32_t round_bit = (mant >> 12) & 1, sticky = mant & 0x0fff;
+  if (round_bit && (sticky || (h_mant & 1))) h_mant++;
+  if (h_mant > 0x3ff) return h_exp >= 30 ? uint16_t((sign << 15) | (0x1f << 10)) : uint16_t((sign << 15) | ((h_exp + 1) << 10));
+  return uint16_t((sign << 15) | (h_exp << 10) | h_mant);
+}
+
 const float kDither[32 * 32] = {
 #include "dither_table.inc"
+
 };
 
 }  // namespace
@@ -1019,7 +1043,8 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
   // Orientation (render/save.rs + headers/image_metadata.rs:85-96): the coded image is produced into a tight staging
   // image first and every pixel moved to display_pixel(x, y) afterwards.
   const uint32_t orientation = d.orientation == 0 ? 1u : d.orientation;
-  const size_t obpp = d.output_format == JXG_FORMAT_RGB_F32 ? 12 : (d.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 3);
+  const bool fmt16 = d.output_format == JXG_FORMAT_RGB_U16 || d.output_format == JXG_FORMAT_RGB_F16;
+  const size_t obpp = d.output_format == JXG_FORMAT_RGB_F32 ? 12 : (d.output_format == JXG_FORMAT_RGBA_U8 ? 4 : (fmt16 ? 6 : 3));
   std::vector<uint8_t> staging;
   uint8_t* obase = static_cast<uint8_t*>(out);
   size_t ostride = out_row_stride;
@@ -1040,6 +1065,19 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
         from_linear_other(d, v);
       if (d.output_format == JXG_FORMAT_RGB_F32) {
         memcpy(row + x * 12, v, 12);
+      } else if (d.output_format == JXG_FORMAT_RGB_U16) {  // convert.rs:739-762, bit depth 16
+        uint16_t px[3];
+        for (int c = 0; c < 3; c++) px[c] = uint16_t(std::nearbyint(std::min(std::max(v[c], 0.0f), 1.0f) * 65535.0f));
+        memcpy(row + x * 6, px, 6);
+      } else if (d.output_format == JXG_FORMAT_RGB_F16) {  // convert.rs:831-857; clamp ranges frame/render.rs:746-750
+        uint16_t px[3];
+        for (int c = 0; c < 3; c++) {
+          float f = v[c];
+          if (d.output_tf == JXG_TF_PQ) f = std::min(std::max(f, 0.0f), 1.0f);
+          else if (d.output_tf == JXG_TF_HLG) f = std::min(std::max(f, -0.074f), 1.1f);
+          px[c] = f32_to_f16_bits(f);
+        }
+        memcpy(row + x * 6, px, 6);
       } else {
         int nc = d.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 3;
         for (int c = 0; c < 3; c++) {
@@ -1183,6 +1221,10 @@ void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const flo
     else
       from_linear_other(d, rgb + 3 * i);
   }
+}
+// The oracle's f32 -> f16 conversion on n values (known-answer test of the F16 store).
+void jxo_f32_to_f16(int n, const float* v, uint16_t* out) {
+  for (int i = 0; i < n; i++) out[i] = f32_to_f16_bits(v[i]);
 }
 void jxo_linear_to_srgb(int n, float* v) {
   for (int i = 0; i < n; i++) v[i] = linear_to_srgb(v[i]);

@@ -49,7 +49,7 @@ def file_info(data: bytes):
 
 
 def decode_file(data: bytes, fmt=abi.FORMAT_RGB_U8, taps=False, threads=0):
-    """Returns (pixels, taps dict). pixels: HxWx3 u8 / HxWx4 u8 / HxWx3 f32."""
+    """Returns (pixels, taps dict). pixels: HxWx3 u8 / HxWx4 u8 / HxWx3 f32 / HxWx3 u16 / HxWx3 f16."""
     lib = load()
     info = file_info(data)
     w, h = info.width, info.height              # display orientation
@@ -60,6 +60,10 @@ def decode_file(data: bytes, fmt=abi.FORMAT_RGB_U8, taps=False, threads=0):
         out = np.zeros((h, w, 4), np.uint8)
     elif fmt == abi.FORMAT_XYB_F32_PLANAR:
         out = np.zeros((3, ch, cw), np.float32)
+    elif fmt == abi.FORMAT_RGB_U16:
+        out = np.zeros((h, w, 3), np.uint16)
+    elif fmt == abi.FORMAT_RGB_F16:
+        out = np.zeros((h, w, 3), np.float16)
     else:
         out = np.zeros((h, w, 3), np.uint8)
     stride = out.strides[0] if fmt != abi.FORMAT_XYB_F32_PLANAR else out.strides[1]

@@ -85,6 +85,37 @@ def test_orientation(ctx, orientation):
     assert np.abs(outf - reff).max() <= 1e-3
 
 
+@pytest.mark.parametrize("orientation,colour", [(1, 0), (6, 0), (1, 5), (1, 6)])
+def test_sixteen_bit_output_samples(ctx, orientation, colour):
+    """a17: U16 (convert.rs:717-786) and F16 (convert.rs:789-857, clamp ranges of PQ / HLG outputs frame/render.rs:746-750)
+    against the oracle: u16 within 1 LSB (= 1.5e-5), f16 within one half-precision step; interior vector tiles, edge tiles
+    and the orientation post-pass all carry 6-byte pixels."""
+    import synth
+    import torch
+    import jxl_rs_b200 as j
+    from tests import oracle_binding as ob
+    w, h = 333, 271
+    data = synth.encode_synthetic(w, h, 77, 0.5, 2, 1, 1, orientation=orientation, colour=colour)
+    fr = j.ParsedFrame(data)
+    for fmt, dt in ((abi.FORMAT_RGB_U16, torch.uint16), (abi.FORMAT_RGB_F16, torch.float16)):
+        ref, _ = ob.decode_file(data, fmt)
+        out = torch.empty((fr.height, fr.width, 3), dtype=dt).pin_memory()
+        b = j.Batch(ctx, 1)
+        b.add(fr, out.data_ptr(), fr.width * 6, fmt, False)
+        b.run()
+        b.wait()
+        b.close()
+        if fmt == abi.FORMAT_RGB_U16:
+            got = out.view(torch.int16).numpy().view(np.uint16).astype(np.int64)
+            assert np.abs(got - ref.astype(np.int64)).max() <= 64  # 1e-3 of full scale, the float tolerance of the stages before
+            assert np.mean(got == ref) > 0.5
+        else:
+            got = out.view(torch.int16).numpy().view(np.float16).astype(np.float64)
+            r = ref.astype(np.float64)
+            assert np.all(np.isfinite(got))
+            assert np.abs(got - r).max() <= 1e-3 * max(1.0, np.abs(r).max()) + 2 ** -11
+
+
 @pytest.mark.parametrize("colour", [1, 2, 3, 4, 5, 6, 7])
 def test_output_colour_encodings(ctx, colour):
     """linear, gamma, PQ (P3), HLG (BT2100), BT709 (custom primaries, DCI white), grey, DCI curve (E

@@ -167,3 +167,32 @@ def test_hlg_curve():
             want = np.sign(x) * np.where(a <= 1 / 12, np.sqrt(3 * a), A * np.log(np.maximum(12 * a - B, 1e-30)) + Cc)
         got = from_linear(abi_tf("HLG"), v, it=it, lum=lum)
         assert np.abs(got - want).max() <= 1e-4  # fast_powf in the OOTF (3e-5 relative), fast_log2f in the OETF (5e-7)
+
+
+def test_f16_store_matches_the_reference_conversion():
+    """util/float16.rs:82-141 restated with numpy: round to nearest even for normal halves, overflow to infinity, and
+    TRUNCATION (not rounding) into the subnormal range (with the reference's extra halving there), zero below 2^-24 —
+    the F16 output format's last step."""
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    rng = np.random.default_rng(9)
+    v = np.concatenate([rng.uniform(-2, 2, 20000), rng.uniform(-1e-4, 1e-4, 20000), rng.uniform(-1e-7, 1e-7, 2000),
+                        np.array([0.0, -0.0, 1.0, 65504.0, 65519.9, 65520.0, 1e6, -1e6, 2.0 ** -14, 2.0 ** -24, 2.0 ** -25,
+                                  0.5 + 2.0 ** -12, 0.5 + 3 * 2.0 ** -12, 1e-45])]).astype(np.float32)
+    out = np.zeros(v.shape, np.uint16)
+    lib.jxo_f32_to_f16.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    lib.jxo_f32_to_f16(len(v), v.ctypes.data, out.ctypes.data)
+    got = out.view(np.float16).astype(np.float64)
+    a = np.abs(v.astype(np.float64))
+    with np.errstate(over="ignore"):
+        rne = v.astype(np.float16).astype(np.float64)  # IEEE round to nearest even (numpy)
+    normal = a >= 2.0 ** -14
+    assert np.array_equal(got[normal], rne[normal])
+    sub = (a < 2.0 ** -14) & (a >= 2.0 ** -24)
+    # float16.rs:104-108 shifts the 24-bit significand by (-14 - e) + 14 bits, one more than the value needs: inputs in the
+    # subnormal range come out truncated AND halved (2^-15 -> 2^-16). Reproduced as is - identical output is the contract.
+    want = np.sign(v[sub]) * np.floor(a[sub] * 2.0 ** 23) * 2.0 ** -24
+    assert np.array_equal(got[sub], want)
+    tiny = a < 2.0 ** -24
+    assert np.all(got[tiny] == 0.0)
+    assert np.array_equal(np.signbit(got), np.signbit(v.astype(np.float64)))
