@@ -49,7 +49,8 @@ def parse_args():
                          "workload), 1 = libjxl-like weighted-predictor tree (3x the host front-end work per frame)")
     ap.add_argument("--unique", type=int, default=0, help="encode only this many distinct frames and repeat them (0 = all distinct)")
     ap.add_argument("--cpu-sample-frames", type=int, default=4)
-    ap.add_argument("--inflight", type=int, default=3, help="resident batches alternated by the device-resident loop")
+    ap.add_argument("--inflight", type=int, default=5, help="resident batches alternated by the device-resident loop")
+    ap.add_argument("--e2e-depth", type=int, default=5, help="contexts (batches in flight) of the end-to-end leg's PipelinedDecoder")
     ap.add_argument("--chunk", type=int, default=16, help="frames per chunk of the pipelined end-to-end decode")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -481,7 +482,7 @@ def main():
     # ---------------- end to end through the public API (host bytes -> host pixels) ----------------
     # K batches stream through PipelinedDecoder (2 contexts): parse + staging of batch k+1 overlap the kernels
     # and D2H copies of batch k; every batch's pixels are in pinned host memory before the clock stops.
-    e2e_depth = 3  # contexts of the pipelined decoder = host output sets (a set is rewritten only after its batch retired)
+    e2e_depth = max(1, args.e2e_depth)  # contexts of the pipelined decoder = host output sets (a set is rewritten only after its batch retired)
     host_out = [[torch.empty((fr.height, fr.width, 3), dtype=torch.uint8).pin_memory() for fr in frames] for _ in range(e2e_depth)]
     outs = [[(o.data_ptr(), fr.width * 3) for o, fr in zip(ho, frames)] for ho in host_out]
     del frames
@@ -495,8 +496,8 @@ def main():
         if e2e_err is not None:
             raise e2e_err
         dec = j.PipelinedDecoder(local_rank, depth=e2e_depth, workers=min(64, rank_cores()),
-                                 staging_threads=max(2, min(4, rank_cores() // 4)))
-        for i in range(max(3, min(args.warmup, 3))):
+                                 staging_threads=max(2, min(8, rank_cores() // 2)))
+        for i in range(e2e_depth + 1):  # every context has sized its pools and pinned arena before the clock starts
             dec.submit(files, outs[i % e2e_depth], abi.FORMAT_RGB_U8)
         dec.drain()
     except Exception as e:  # noqa: BLE001
@@ -578,7 +579,7 @@ def main():
                 "l2_policy": "working set per step (coefficients + XYB planes, >10 GB) far exceeds the 126 MB L2; no explicit flush",
                 "sharding": "frames partitioned by rank, no data-path collective",
                 "stage_ms_single_batch": stage_acc, "single_batch_ms": single_ms, "batches_in_flight": depth,
-                "e2e_pipeline": "whole batches on 3 contexts (host parse / staging of batch k+1 overlaps the kernels and D2H of batches k and k-1)",
+                "e2e_pipeline": f"whole batches on {e2e_depth} contexts (host parse / staging of later batches overlaps the kernels and the D2H copies of earlier ones; output copies leave on one first-in-first-out stream)",
                 "host_cores": cores, "host_cores_per_rank": rank_cores(), "numa": numa,
                 "pipeline_alg_gbs": pipeline_gbs,
                 "alg_bytes_per_step": alg_bytes,

@@ -211,35 +211,45 @@ struct MWp {
   }
 };
 
-// predict.rs:148-194. nee is only read by predictor 13.
-__device__ __forceinline__ int64_t m_predict(uint32_t predictor, int64_t L, int64_t T, int64_t TL, int64_t TR, int32_t ww, int32_t nn,
-                                            int32_t nee, int64_t wp_pred) {
+// predict.rs:148-194 in wrapping 32-bit arithmetic. The pixel is (guess + offset + multiplier * dec) truncated to i32
+// (decode/common.rs:85), so only the low 32 bits of the guess matter; the comparisons of Select and of the clamped
+// gradient are made on exact values (a difference of two i32 fits a u32; the clamped gradient lies between left and top).
+__device__ __forceinline__ int32_t m_predict32(uint32_t predictor, int32_t L, int32_t T, int32_t TL, int32_t TR, int32_t ww,
+                                               int32_t nn, int32_t nee, int64_t wp_pred) {
   switch (predictor) {
     case 0: return 0;
     case 1: return L;
     case 2: return T;
-    case 3: return (T + L) / 2;
     case 4: {
-      const int64_t pp = L + T - TL;
-      return labs64(pp - L) < labs64(pp - T) ? L : T;
+      const uint32_t dl = T > TL ? uint32_t(T) - uint32_t(TL) : uint32_t(TL) - uint32_t(T);  // |pp - L| = |T - TL|
+      const uint32_t dt = L > TL ? uint32_t(L) - uint32_t(TL) : uint32_t(TL) - uint32_t(L);  // |pp - T| = |L - TL|
+      return dl < dt ? L : T;
     }
-    case 5: return clamped_gradient(L, T, TL);
-    case 6: return wp_pred;
+    case 5: {
+      const int32_t mn = min(L, T), mx = max(L, T);
+      const int32_t grad = wsub(wadd(L, T), TL);  // exact whenever it is the result (then mn <= grad <= mx)
+      return TL < mn ? mx : (TL > mx ? mn : grad);
+    }
+    case 6: return int32_t(wp_pred);
     case 7: return TR;
     case 8: return TL;
     case 9: return ww;
-    case 10: return (L + TL) / 2;
-    case 11: return (T + TL) / 2;
-    case 12: return (T + TR) / 2;
-    default: return (6 * T - 2 * int64_t(nn) + 7 * L + int64_t(ww) + int64_t(nee) + 3 * TR + 8) / 16;
+    case 3: return int32_t((int64_t(T) + L) / 2);
+    case 10: return int32_t((int64_t(L) + TL) / 2);
+    case 11: return int32_t((int64_t(T) + TL) / 2);
+    case 12: return int32_t((int64_t(T) + TR) / 2);
+    default: return int32_t((6 * int64_t(T) - 2 * int64_t(nn) + 7 * int64_t(L) + int64_t(ww) + int64_t(nee) + 3 * int64_t(TR) + 8) / 16);
   }
 }
 
 // One channel whose tree walk is a table over one property (MRectDev::walk == kWalkLut): per pixel the property, one
 // table load (predictor, cluster, leaf), the predictor and the symbol. specialized_trees.rs:197-372 is the CPU form.
-template <bool WP>
+// PROP: the property (2..15), -1 = single leaf, -2 = read from the rect at run time. Pixels with all neighbours inside
+// the channel (y >= 2, 2 <= x < w - 2) skip the edge rules of predict.rs:64-103.
+template <bool WP, int PROP>
 __device__ __forceinline__ void m_channel_lut(const MBatchDev& B, const MRectDev& rc, MSym& sym, MWp& wp, const int4* nodes) {
-  const uint32_t w = rc.w, h = rc.h, prop = rc.walk >> 8;
+  const uint32_t w = rc.w, h = rc.h;
+  const int prop_rt = int(rc.walk >> 8);
   int32_t* const base = B.planes + rc.base;
   const uint32_t* const lut = reinterpret_cast<const uint32_t*>(B.blob + rc.lut_off);
   const uint32_t single = uint32_t(rc.lut_off);
@@ -248,30 +258,17 @@ __device__ __forceinline__ void m_channel_lut(const MBatchDev& B, const MRectDev
     const int32_t* const top = y > 0 ? row - rc.stride : row;
     const int32_t* const toptop = y > 1 ? top - rc.stride : top;
     int32_t prev_p9 = 0;
-    const bool has_top = y > 0, has_tt = y > 1;
-    int32_t v_prev = 0, v_prev2 = 0;
-    int32_t t_prev = 0;
-    int32_t t_cur = has_top ? top[0] : 0;
-    int32_t t_next = (has_top && w > 1) ? top[1] : 0;
-    int32_t tt_cur = has_tt ? toptop[0] : 0;
-    const int32_t top0 = t_cur;
-    for (uint32_t x = 0; x < w; x++) {
-      const int32_t t_next2 = (has_top && x + 2 < w) ? top[x + 2] : 0;
-      const int32_t tt_next = (has_tt && x + 1 < w) ? toptop[x + 1] : 0;
-      const int32_t left = x > 0 ? v_prev : (has_top ? top0 : 0);
-      const int32_t n = has_top ? t_cur : left;
-      const int32_t nw = (x > 0 && has_top) ? t_prev : left;
-      const int32_t ne = (x + 1 < w && has_top) ? t_next : n;
-      const int32_t ww = x > 1 ? v_prev2 : left;
-      const int32_t nn = has_tt ? tt_cur : n;
+    // one pixel: neighbours in, value out (and stored)
+    auto pixel = [&](uint32_t x, int32_t left, int32_t n, int32_t nw, int32_t ne, int32_t ww, int32_t nn, int32_t nee) -> int32_t {
       int64_t wp_pred = 0;
       int32_t wp_prop = 0;
       if (WP) wp.predict(x, y, n, left, ne, nw, nn, wp_pred, wp_prop);
       const int32_t p9 = wsub(wadd(left, n), nw);
       uint32_t e = single;
-      if (prop != kLutNoProperty) {
+      const int p = PROP == -2 ? (prop_rt == int(kLutNoProperty) ? -1 : prop_rt) : PROP;
+      if (p >= 0) {
         int32_t v;
-        switch (prop) {  // tree.rs:189-280
+        switch (p) {  // tree.rs:189-280
           case 2: v = int32_t(y); break;
           case 3: v = int32_t(x); break;
           case 4: v = wabs(n); break;
@@ -290,24 +287,58 @@ __device__ __forceinline__ void m_channel_lut(const MBatchDev& B, const MRectDev
         e = __ldg(lut + uint32_t(min(max(v, kLutMin), kLutMin + kLutSize - 1) - kLutMin));
       }
       prev_p9 = p9;
-      const int32_t nee = (x + 2 < w && has_top) ? t_next2 : ne;
-      int64_t guess = m_predict(e & 15u, left, n, nw, ne, ww, nn, nee, wp_pred);
+      const int32_t guess = m_predict32(e & 15u, left, n, nw, ne, ww, nn, nee, wp_pred);
       const int32_t dec = m_unpack_signed(m_read_clustered(sym, (e >> 4) & 255u));
       int32_t val;
       if (e & (1u << 12)) {
-        val = int32_t(guess + int64_t(dec));
+        val = wadd(guess, dec);
       } else {
         const int4 leaf = __ldg(nodes + (e >> 16));
-        val = int32_t(guess + int64_t(leaf.y) + int64_t(uint32_t(leaf.w)) * int64_t(dec));  // decode/common.rs:85
+        val = int32_t(uint32_t(guess) + uint32_t(leaf.y) + uint32_t(leaf.w) * uint32_t(dec));  // decode/common.rs:85, low 32 bits
       }
       if (WP) wp.update(val, x, y);
       row[x] = val;
-      v_prev2 = v_prev;
-      v_prev = val;
-      t_prev = t_cur;
-      t_cur = t_next;
-      t_next = t_next2;
-      tt_cur = tt_next;
+      return val;
+    };
+    // neighbours with the edge rules (predict.rs:64-103); v1 / v2: the two pixels to the left in this row
+    auto edge_pixel = [&](uint32_t x, int32_t v1, int32_t v2) -> int32_t {
+      const bool has_top = y > 0, has_tt = y > 1;
+      const int32_t left = x > 0 ? v1 : (has_top ? top[0] : 0);
+      const int32_t n = has_top ? top[x] : left;
+      const int32_t nw = (x > 0 && has_top) ? top[x - 1] : left;
+      const int32_t ne = (x + 1 < w && has_top) ? top[x + 1] : n;
+      const int32_t ww = x > 1 ? v2 : left;
+      const int32_t nn = has_tt ? toptop[x] : n;
+      const int32_t nee = (x + 2 < w && has_top) ? top[x + 2] : ne;
+      return pixel(x, left, n, nw, ne, ww, nn, nee);
+    };
+    int32_t v1 = 0, v2 = 0;  // row[x - 1], row[x - 2]
+    uint32_t x = 0;
+    const uint32_t x_in0 = min(2u, w), x_in1 = (y >= 2 && w > 4) ? w - 2 : x_in0;
+    for (; x < x_in0; x++) {
+      const int32_t v = edge_pixel(x, v1, v2);
+      v2 = v1;
+      v1 = v;
+    }
+    if (x_in1 > x_in0) {
+      // interior: sliding window over the two rows above, loaded ahead of their use
+      int32_t t_prev = top[x - 1], t_cur = top[x], t_next = top[x + 1], tt_cur = toptop[x];
+      for (; x < x_in1; x++) {
+        const int32_t t_next2 = top[x + 2];
+        const int32_t tt_next = toptop[x + 1];
+        const int32_t v = pixel(x, v1, t_cur, t_prev, t_next, v2, tt_cur, t_next2);
+        v2 = v1;
+        v1 = v;
+        t_prev = t_cur;
+        t_cur = t_next;
+        t_next = t_next2;
+        tt_cur = tt_next;
+      }
+    }
+    for (; x < w; x++) {
+      const int32_t v = edge_pixel(x, v1, v2);
+      v2 = v1;
+      v1 = v;
     }
   }
 }
@@ -366,8 +397,17 @@ __global__ void __launch_bounds__(128) k_modular_decode(const MBatchDev B, const
         for (uint32_t i = 0; i < (w + 1) * 2; i++) wp.err[i] = 0;
       }
       if ((rc.walk & 0xff) == kWalkLut) {
-        if (use_wp) m_channel_lut<true>(B, rc, sym, wp, nodes);
-        else m_channel_lut<false>(B, rc, sym, wp, nodes);
+        if (use_wp) {
+          m_channel_lut<true, -2>(B, rc, sym, wp, nodes);
+        } else {
+          switch (rc.walk >> 8) {  // the property is a compile-time constant of the channel loop
+            case 9: m_channel_lut<false, 9>(B, rc, sym, wp, nodes); break;
+            case 10: m_channel_lut<false, 10>(B, rc, sym, wp, nodes); break;
+            case 13: m_channel_lut<false, 13>(B, rc, sym, wp, nodes); break;
+            case kLutNoProperty: m_channel_lut<false, -1>(B, rc, sym, wp, nodes); break;
+            default: m_channel_lut<false, -2>(B, rc, sym, wp, nodes); break;
+          }
+        }
         continue;
       }
       for (uint32_t y = 0; y < h; y++) {

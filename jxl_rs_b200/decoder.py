@@ -310,6 +310,7 @@ class PipelinedDecoder:
         self.trace = None  # set to [] to record the dispatcher timeline
         self.retire_trace = []  # with trace on: (start, seconds in wait / stats / close) of every retired batch
         self.marks = None  # set to [] to record the device timeline of every batch (stage event times)
+        self.marks_ref_host = None  # time.perf_counter() at the device timeline's zero (set with the first marks)
         self._thread = threading.Thread(target=self._dispatch, daemon=True)
         self._thread.start()
 
@@ -322,7 +323,10 @@ class PipelinedDecoder:
             t1 = time.perf_counter()
             self.last_stats = b.stats()
             if self.marks is not None:
+                tcall = time.perf_counter()
                 self.marks.append(b.stage_marks())
+                if self.marks_ref_host is None:  # the library's reference event was recorded inside that first call
+                    self.marks_ref_host = tcall
         finally:
             t2 = time.perf_counter()
             b.close()

@@ -60,7 +60,7 @@ def install(setattr_fn, fail_e2e=False, gloo=False):
 
         def run(self, stream_ptr=0):
             FakeBatch.runs += 1
-            if fail_e2e and FakeBatch.runs > 4:
+            if fail_e2e and FakeBatch.runs > 6:  # the device-resident leg runs --inflight (5) batches once; later runs belong to the end-to-end leg
                 raise RuntimeError("injected failure of the end-to-end leg")
 
         def rerun_device(self, stream_ptr=0):

@@ -25,6 +25,8 @@ def submit(dec, i):
 
 for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     dec = j.PipelinedDecoder(0, depth=depth, staging_threads=st)
+    if os.environ.get("E2E_MARKS"):
+        dec.marks = []  # the warm-up batches set the zero of the device timeline (before the timed region)
     for i in range(depth + 1):  # every context has sized its pools before the clock starts
         submit(dec, i)
     dec.drain()
@@ -39,6 +41,9 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     t_drain = time.perf_counter()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_sync2 = time.perf_counter()
+    print(f"  second synchronize: {1e3*(t_sync2-t0-dt):.2f} ms")
     print(f"staging_threads={st}: {dt/steps*1e3:.1f} ms/step, {n*3840*2160/1e6*steps/dt:.0f} MP/s")
     print(f"  main thread: submits done at {1e3*(t_sub-t0):.1f} ms, drain returned at {1e3*(t_drain-t0):.1f}, device idle at {1e3*dt:.1f}")
     for (ts, ret, pw, add, run) in dec.trace:
@@ -46,8 +51,9 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     for (ts, w, m, c) in dec.retire_trace:
         print(f"  retire at t={1e3*(ts-t0):7.1f}: wait {w*1e3:6.1f}  stats+marks {m*1e3:6.1f}  close {c*1e3:6.1f}")
     if dec.marks:
-        base = min(m[0] for m in dec.marks if m[0] > 0)
+        # device times on the host clock of the lines above: zero of the device timeline = dec.marks_ref_host
+        base = -1e3 * (dec.marks_ref_host - t0)
         print("  device timeline (ms): start | entropy begin..end | transforms end | filters launches end | H2D start | D2H end")
         for m in dec.marks:
-            print("   ", " ".join(f"{(v - base):8.1f}" if v > 0 else "       -" for v in m))
+            print("   ", " ".join(f"{(v - base):8.1f}" if v != 0 else "       -" for v in m))
     dec.close()
