@@ -3,8 +3,12 @@
 // reference code it restates (paths relative to /root/reference).
 #include "oracle.h"
 
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -273,9 +277,80 @@ int ilog2(int n) {
   return l;
 }
 
+#ifdef __AVX2__
+// The same recursion with eight independent 1-D transforms per step (one per lane): lane i runs exactly the scalar
+// sequence of idct1d on its own data, so the results are bit-identical. Used by idct2d when the fast CPU forms are on
+// (jxo_set_fast_cpu): eight rows at a time in the horizontal pass, eight columns at a time in the vertical one.
+static std::atomic<int> g_fast_cpu{0};
+void idct1d_x8(__m256* v, int n, int log_n, __m256* scratch) {
+  if (n == 1) return;
+  if (n == 2) {
+    const __m256 a = v[0], b = v[1];
+    v[0] = _mm256_add_ps(a, b);
+    v[1] = _mm256_sub_ps(a, b);
+    return;
+  }
+  const int half = n / 2;
+  __m256 *first = scratch, *second = scratch + half;
+  for (int i = 0; i < half; i++) {
+    first[i] = v[2 * i];
+    second[i] = v[2 * i + 1];
+  }
+  idct1d_x8(first, half, log_n - 1, scratch + n);
+  for (int i = half - 1; i >= 1; i--) second[i] = _mm256_add_ps(second[i], second[i - 1]);
+  second[0] = _mm256_mul_ps(second[0], _mm256_set1_ps(float(M_SQRT2)));
+  idct1d_x8(second, half, log_n - 1, scratch + n);
+  const float* wc = kWc.w[log_n];
+  for (int i = 0; i < half; i++) {
+    const __m256 w = _mm256_set1_ps(wc[i]);
+    v[i] = _mm256_fmadd_ps(second[i], w, first[i]);
+    v[n - 1 - i] = _mm256_fnmadd_ps(second[i], w, first[i]);  // fma(-second, w, first)
+  }
+}
+
+// rows and cols multiples of 8, at most 256.
+void idct2d_x8(int rows, int cols, float* block) {
+  static thread_local std::vector<float> tmp;
+  alignas(32) static thread_local __m256 line[256], scratch[2 * 256 + 16];
+  tmp.resize(size_t(rows) * cols);
+  const bool wide = rows < cols;
+  alignas(32) float lanes[8];
+  // horizontal pass: rows vf .. vf + 7 in the eight lanes
+  for (int vf = 0; vf < rows; vf += 8) {
+    for (int hf = 0; hf < cols; hf++) {
+      if (wide) {
+        for (int i = 0; i < 8; i++) lanes[i] = block[(vf + i) * cols + hf];
+        line[size_t(hf)] = _mm256_load_ps(lanes);
+      } else {
+        line[size_t(hf)] = _mm256_loadu_ps(block + hf * rows + vf);
+      }
+    }
+    idct1d_x8(line, cols, ilog2(cols), scratch);
+    for (int x = 0; x < cols; x++) {
+      _mm256_store_ps(lanes, line[size_t(x)]);
+      for (int i = 0; i < 8; i++) tmp[size_t(vf + i) * cols + x] = lanes[i];
+    }
+  }
+  // vertical pass: columns x .. x + 7 in the eight lanes
+  for (int x = 0; x < cols; x += 8) {
+    for (int vf = 0; vf < rows; vf++) line[size_t(vf)] = _mm256_loadu_ps(tmp.data() + size_t(vf) * cols + x);
+    idct1d_x8(line, rows, ilog2(rows), scratch);
+    for (int y = 0; y < rows; y++) _mm256_storeu_ps(block + size_t(y) * cols + x, line[size_t(y)]);
+  }
+}
+#else
+static std::atomic<int> g_fast_cpu{0};
+#endif
+
 // 2-D IDCT, in place. Coefficient layout: rows < cols -> [vfreq][hfreq] with
 // stride cols; otherwise [hfreq][vfreq] with stride rows. Output: rows x cols.
 void idct2d(int rows, int cols, float* block) {
+#ifdef __AVX2__
+  if (g_fast_cpu.load(std::memory_order_relaxed) != 0 && rows % 8 == 0 && cols % 8 == 0) {
+    idct2d_x8(rows, cols, block);
+    return;
+  }
+#endif
   std::vector<float> tmp(size_t(rows) * cols), line(std::max(rows, cols)), scratch(2 * std::max(rows, cols) + 16);
   const bool wide = rows < cols;
   // horizontal pass (size cols) for every vertical frequency
@@ -676,6 +751,10 @@ int decode_group(const JxgFrameDesc& d, const Geometry& geo, uint32_t g, const u
   return 0;
 }
 
+// AVX2 forms of Gaborish, EPF 1 / 2 and the sRGB u8 store (8 pixels per step, the per-pixel arithmetic and its order
+// unchanged: outputs are bit-identical to the scalar definitions below, tests/test_cpu_paths.py checks that). Off by
+// default - the checker stays the plain restatement; bench.py's CPU arm turns them on (jxo_set_fast_cpu) so that the CPU
+// baseline is not handicapped by scalar filter loops the reference runs as SIMD (render/stages/epf/*.rs, gaborish.rs).
 inline size_t mirror(ptrdiff_t v, size_t s) {  // util/mirror.rs:8
   for (;;) {
     if (v < 0) v = -v - 1;
@@ -690,12 +769,36 @@ void gaborish(size_t w, size_t h, const float* in, size_t in_stride, float* out,
               int num_threads) {
   float total = 1.0f + w1 * 4.0f + w2 * 4.0f;
   float k0 = 1.0f / total, k1 = w1 / total, k2 = w2 / total;
+  const bool fast = g_fast_cpu.load() != 0;
   parallel_for(int(h), num_threads, [&](int yi) {
     size_t y = size_t(yi);
     const float* t = in + mirror(ptrdiff_t(y) - 1, h) * in_stride;
     const float* c = in + y * in_stride;
     const float* b = in + mirror(ptrdiff_t(y) + 1, h) * in_stride;
+    size_t x_vec0 = w, x_vec1 = w;  // [x_vec0, x_vec1): done 8 at a time below
+#ifdef __AVX2__
+    if (fast && w >= 18) {
+      x_vec0 = 1;
+      x_vec1 = 1 + (w - 2) / 8 * 8;
+      const __m256 vk0 = _mm256_set1_ps(k0), vk1 = _mm256_set1_ps(k1), vk2 = _mm256_set1_ps(k2);
+      for (size_t x = x_vec0; x < x_vec1; x += 8) {
+        const __m256 cc = _mm256_loadu_ps(c + x), cl = _mm256_loadu_ps(c + x - 1), cr = _mm256_loadu_ps(c + x + 1);
+        const __m256 tt = _mm256_loadu_ps(t + x), tl = _mm256_loadu_ps(t + x - 1), tr = _mm256_loadu_ps(t + x + 1);
+        const __m256 bb = _mm256_loadu_ps(b + x), bl = _mm256_loadu_ps(b + x - 1), br = _mm256_loadu_ps(b + x + 1);
+        __m256 sum = _mm256_mul_ps(cc, vk0);
+        sum = _mm256_fmadd_ps(vk1, _mm256_add_ps(_mm256_add_ps(_mm256_add_ps(tt, cl), bb), cr), sum);
+        sum = _mm256_fmadd_ps(vk2, _mm256_add_ps(_mm256_add_ps(_mm256_add_ps(tl, tr), bl), br), sum);
+        _mm256_storeu_ps(out + y * out_stride + x, sum);
+      }
+    }
+#else
+    (void)fast;
+#endif
     for (size_t x = 0; x < w; x++) {
+      if (x == x_vec0) {
+        x = x_vec1 - 1;
+        continue;
+      }
       size_t xl = mirror(ptrdiff_t(x) - 1, w), xr = mirror(ptrdiff_t(x) + 1, w);
       float sum = c[x] * k0;
       sum = std::fmaf(k1, t[x] + c[xl] + b[x] + c[xr], sum);
@@ -791,10 +894,75 @@ void epf(int stage, const JxgFrameDesc& d, const Geometry& geo, const std::vecto
   };
   auto at_mirror = [&](int c, ptrdiff_t xx, ptrdiff_t yy) { return in.p[c][mirror(yy, h) * in.stride + mirror(xx, w)]; };
   auto at_direct = [&](int c, ptrdiff_t xx, ptrdiff_t yy) { return in.p[c][size_t(yy) * in.stride + size_t(xx)]; };
+#ifdef __AVX2__
+  // Eight pixels of one 8x8 block row at a time (x0 a multiple of 8, neighbourhood inside the image): the sigma is one
+  // value for the chunk, the border rule a lane mask; every lane runs the scalar sequence above.
+  const bool fast = g_fast_cpu.load() != 0 && stage != 0;
+  const __m256 vabs = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+  auto chunk = [&](ptrdiff_t x0, ptrdiff_t y) {
+    const float inv_sigma_px = sigma[size_t(y / 8) * geo.xb + size_t(x0 / 8)];
+    if (inv_sigma_px < kMinSigma) {
+      for (int c = 0; c < 3; c++) _mm256_storeu_ps(out.p[c] + size_t(y) * out.stride + x0, _mm256_loadu_ps(in.p[c] + size_t(y) * in.stride + x0));
+      return;
+    }
+    const bool rowb = (y % 8 == 0 || y % 8 == 7);
+    const __m256 mul = rowb ? _mm256_set1_ps(bsm) : _mm256_setr_ps(bsm, sm, sm, sm, sm, sm, sm, bsm);
+    const __m256 inv_s = _mm256_mul_ps(_mm256_set1_ps(inv_sigma_px), mul);
+    auto ld = [&](int c, ptrdiff_t dx, ptrdiff_t dy) { return _mm256_loadu_ps(in.p[c] + size_t(y + dy) * in.stride + size_t(x0 + dx)); };
+    const __m256 one = _mm256_set1_ps(1.0f), zero = _mm256_setzero_ps();
+    if (stage == 2) {
+      const __m256 cc[3] = {ld(0, 0, 0), ld(1, 0, 0), ld(2, 0, 0)};
+      __m256 wacc = one, acc[3] = {cc[0], cc[1], cc[2]};
+      for (auto& o : kOff1) {
+        const __m256 nb[3] = {ld(0, o[0], o[1]), ld(1, o[0], o[1]), ld(2, o[0], o[1])};
+        const __m256 a0 = _mm256_and_ps(_mm256_sub_ps(nb[0], cc[0]), vabs), a1 = _mm256_and_ps(_mm256_sub_ps(nb[1], cc[1]), vabs),
+                     a2 = _mm256_and_ps(_mm256_sub_ps(nb[2], cc[2]), vabs);
+        const __m256 sad = _mm256_fmadd_ps(a0, _mm256_set1_ps(d.epf_channel_scale[0]),
+                                           _mm256_fmadd_ps(a1, _mm256_set1_ps(d.epf_channel_scale[1]),
+                                                           _mm256_mul_ps(a2, _mm256_set1_ps(d.epf_channel_scale[2]))));
+        const __m256 wt = _mm256_max_ps(_mm256_fmadd_ps(sad, inv_s, one), zero);
+        wacc = _mm256_add_ps(wacc, wt);
+        for (int c = 0; c < 3; c++) acc[c] = _mm256_fmadd_ps(wt, nb[c], acc[c]);
+      }
+      const __m256 inv_w = _mm256_div_ps(one, wacc);
+      for (int c = 0; c < 3; c++) _mm256_storeu_ps(out.p[c] + size_t(y) * out.stride + x0, _mm256_mul_ps(acc[c], inv_w));
+      return;
+    }
+    __m256 sads[4] = {zero, zero, zero, zero};
+    for (int c = 0; c < 3; c++) {
+      const __m256 scale = _mm256_set1_ps(d.epf_channel_scale[c]);
+      for (int k = 0; k < 4; k++) {
+        __m256 sacc = zero;
+        for (auto& pl : kPlusOrder)
+          sacc = _mm256_add_ps(sacc, _mm256_and_ps(_mm256_sub_ps(ld(c, pl[0], pl[1]), ld(c, pl[0] + kOff1[k][0], pl[1] + kOff1[k][1])), vabs));
+        sads[k] = _mm256_fmadd_ps(scale, sacc, sads[k]);
+      }
+    }
+    __m256 wsum = one;
+    for (int k = 0; k < 4; k++) {
+      sads[k] = _mm256_max_ps(_mm256_fmadd_ps(sads[k], inv_s, one), zero);
+      wsum = _mm256_add_ps(wsum, sads[k]);
+    }
+    const __m256 inv_w = _mm256_div_ps(one, wsum);
+    for (int c = 0; c < 3; c++) {
+      __m256 o = ld(c, 0, 0);
+      for (int k = 3; k >= 0; k--) o = _mm256_fmadd_ps(ld(c, kOff1[k][0], kOff1[k][1]), sads[k], o);
+      _mm256_storeu_ps(out.p[c] + size_t(y) * out.stride + x0, _mm256_mul_ps(o, inv_w));
+    }
+  };
+#else
+  const bool fast = false;
+  auto chunk = [&](ptrdiff_t, ptrdiff_t) {};
+#endif
   parallel_for(int(h), num_threads, [&](int yi) {
     const ptrdiff_t y = yi;
     const bool row_inside = y >= 3 && y + 3 < ptrdiff_t(h);
     for (ptrdiff_t x = 0; x < ptrdiff_t(w); x++) {
+      if (fast && row_inside && (x & 7) == 0 && x >= 8 && x + 8 + 3 <= ptrdiff_t(w)) {
+        chunk(x, y);
+        x += 7;
+        continue;
+      }
       if (row_inside && x >= 3 && x + 3 < ptrdiff_t(w)) pixel(x, y, at_direct);
       else pixel(x, y, at_mirror);
     }
@@ -969,6 +1137,15 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
   Geometry geo(d);
   if (n_sections != geo.num_groups * d.num_passes) return JXG_ERR_ARGUMENT;
   if (num_threads <= 0) num_threads = int(std::thread::hardware_concurrency());
+  static const bool timing = getenv("JXO_TIMING") != nullptr;  // stage split of the CPU port on stderr
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto t_begin = tnow();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t = tnow();
+    fprintf(stderr, "[oracle] %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_begin).count());
+    t_begin = t;
+  };
   const size_t pstride = size_t(geo.xb) * 8, prow = size_t(geo.yb) * 8;
   std::vector<float> plane_a[3], plane_b[3];
   for (int c = 0; c < 3; c++) plane_a[c].assign(pstride * prow, 0.0f);
@@ -997,6 +1174,7 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
     if (bad_group) *bad_group = errg.load();
     return err.load();
   }
+  lap("entropy + dequant + IDCT");
   if (taps && taps->xyb_idct)
     for (int c = 0; c < 3; c++) memcpy(taps->xyb_idct + size_t(c) * pstride * prow, planes[c], pstride * prow * sizeof(float));
 
@@ -1009,6 +1187,7 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
       gaborish(geo.width, geo.height, cur.p[c], pstride, nxt.p[c], pstride, d.gab_w1[c], d.gab_w2[c], num_threads);
     std::swap(cur, nxt);
   }
+  lap("gaborish");
   if (d.epf_iters > 0) {
     std::vector<float> sigma = sigma_image(d, geo);
     if (d.epf_iters >= 3) {
@@ -1022,6 +1201,7 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
       std::swap(cur, nxt);
     }
   }
+  lap("epf");
   if (taps && taps->xyb_filtered)
     for (int c = 0; c < 3; c++)
       for (size_t y = 0; y < geo.height; y++)
@@ -1053,10 +1233,66 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
     obase = staging.data();
     ostride = geo.width * obpp;
   }
+  const bool fast_store = g_fast_cpu.load() != 0 && d.output_tf == JXG_TF_SRGB &&
+                          (d.output_format == JXG_FORMAT_RGB_U8 || d.output_format == JXG_FORMAT_RGBA_U8);
   parallel_for(int(geo.height), num_threads, [&](int yi) {
     size_t y = size_t(yi);
     uint8_t* row = obase + y * ostride;
-    for (size_t x = 0; x < geo.width; x++) {
+    size_t x_begin = 0;
+#ifdef __AVX2__
+    if (fast_store) {  // eight pixels per step through the same per-pixel sequence (xyb.rs:197-241, tf.rs:13-44, convert.rs:574-598)
+      const int nc = d.output_format == JXG_FORMAT_RGBA_U8 ? 4 : 3;
+      const __m256 vabs = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff)), vsign = _mm256_castsi256_ps(_mm256_set1_epi32(int(0x80000000u)));
+      const float* m = d.opsin_inverse_matrix;
+      const __m256 is = _mm256_set1_ps(intensity_scale);
+      static const float P[5] = {-5.135152395e-4f, 5.287254571e-3f, 3.903842876e-1f, 1.474205315f, 7.352629620e-1f};
+      static const float Q[5] = {1.004519624e-2f, 3.036675394e-1f, 1.340816930f, 9.258482155e-1f, 2.424867759e-2f};
+      for (; x_begin + 8 <= geo.width; x_begin += 8) {
+        const size_t x = x_begin;
+        const __m256 vx = _mm256_loadu_ps(cur.p[0] + y * pstride + x), vy = _mm256_loadu_ps(cur.p[1] + y * pstride + x),
+                     vb = _mm256_loadu_ps(cur.p[2] + y * pstride + x);
+        __m256 l = _mm256_sub_ps(_mm256_add_ps(vy, vx), _mm256_set1_ps(bias_cbrt[0]));
+        __m256 mm = _mm256_sub_ps(_mm256_sub_ps(vy, vx), _mm256_set1_ps(bias_cbrt[1]));
+        __m256 sb = _mm256_sub_ps(vb, _mm256_set1_ps(bias_cbrt[2]));
+        const __m256 l2 = _mm256_mul_ps(l, l), m2 = _mm256_mul_ps(mm, mm), s2 = _mm256_mul_ps(sb, sb);
+        l = _mm256_fmadd_ps(l2, _mm256_mul_ps(l, is), _mm256_set1_ps(scaled_bias[0]));
+        mm = _mm256_fmadd_ps(m2, _mm256_mul_ps(mm, is), _mm256_set1_ps(scaled_bias[1]));
+        sb = _mm256_fmadd_ps(s2, _mm256_mul_ps(sb, is), _mm256_set1_ps(scaled_bias[2]));
+        __m256 rgb[3];
+        for (int c = 0; c < 3; c++)
+          rgb[c] = _mm256_fmadd_ps(_mm256_set1_ps(m[3 * c]), l,
+                                   _mm256_fmadd_ps(_mm256_set1_ps(m[3 * c + 1]), mm, _mm256_mul_ps(_mm256_set1_ps(m[3 * c + 2]), sb)));
+        alignas(32) float px[3][8];
+        for (int c = 0; c < 3; c++) {
+          const __m256 a = _mm256_and_ps(rgb[c], vabs);
+          const __m256 lin = _mm256_mul_ps(a, _mm256_set1_ps(12.92f));
+          const __m256 sq = _mm256_sqrt_ps(a);
+          __m256 yp = _mm256_set1_ps(P[4]), yq = _mm256_set1_ps(Q[4]);
+          for (int i = 3; i >= 0; i--) {
+            yp = _mm256_fmadd_ps(yp, sq, _mm256_set1_ps(P[i]));
+            yq = _mm256_fmadd_ps(yq, sq, _mm256_set1_ps(Q[i]));
+          }
+          __m256 r = _mm256_blendv_ps(_mm256_div_ps(yp, yq), lin, _mm256_cmp_ps(a, _mm256_set1_ps(0.0031308f), _CMP_LT_OQ));
+          r = _mm256_or_ps(r, _mm256_and_ps(rgb[c], vsign));  // copysign: r is non-negative
+          alignas(32) float dth[8];
+          for (int i = 0; i < 8; i++) dth[i] = kDither[((y + 13 * size_t(c)) % 32) * 32 + (x + size_t(i) + 23 * size_t(c)) % 32];
+          __m256 sc = _mm256_add_ps(_mm256_mul_ps(r, _mm256_set1_ps(255.0f)), _mm256_load_ps(dth));
+          sc = _mm256_min_ps(_mm256_max_ps(sc, _mm256_setzero_ps()), _mm256_set1_ps(255.0f));
+          _mm256_store_ps(px[c], _mm256_round_ps(sc, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+        }
+        for (int i = 0; i < 8; i++) {
+          uint8_t* o = row + (x + size_t(i)) * size_t(nc);
+          o[0] = uint8_t(px[0][i]);
+          o[1] = uint8_t(px[1][i]);
+          o[2] = uint8_t(px[2][i]);
+          if (nc == 4) o[3] = 255;
+        }
+      }
+    }
+#else
+    (void)fast_store;
+#endif
+    for (size_t x = x_begin; x < geo.width; x++) {
       float v[3] = {cur.p[0][y * pstride + x], cur.p[1][y * pstride + x], cur.p[2][y * pstride + x]};
       xyb_to_linear_px(v[0], v[1], v[2], d.opsin_inverse_matrix, bias_cbrt, scaled_bias, intensity_scale);
       if (d.output_tf == JXG_TF_SRGB)
@@ -1090,6 +1326,7 @@ int jxo_decode_frame(const JxgFrameDesc* desc, const uint8_t* hf_bytes, const ui
       }
     }
   });
+  lap("colour + store");
   if (orientation != 1)
     jxo_orient_image(staging.data(), geo.width, geo.height, obpp, orientation, static_cast<uint8_t*>(out), out_row_stride);
   return 0;
@@ -1222,6 +1459,8 @@ void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const flo
       from_linear_other(d, rgb + 3 * i);
   }
 }
+// 1: run Gaborish / EPF 1-2 / the sRGB u8 store through their AVX2 forms (same results, see g_fast_cpu). Process-wide.
+void jxo_set_fast_cpu(int on) { g_fast_cpu.store(on); }
 // The oracle's f32 -> f16 conversion on n values (known-answer test of the F16 store).
 void jxo_f32_to_f16(int n, const float* v, uint16_t* out) {
   for (int i = 0; i < n; i++) out[i] = f32_to_f16_bits(v[i]);

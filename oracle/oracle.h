@@ -64,6 +64,7 @@ void jxo_sigma_image(uint32_t xb, uint32_t yb, uint32_t global_scale, const int3
                      float quant_mul, const float* sharp_lut, float* out);
 void jxo_epf_stage(int stage, uint32_t w, uint32_t h, const float* in3, float* out3, const float* inv_sigma, const float* channel_scale,
                    float pass0_sigma_scale, float pass2_sigma_scale, float border_sad_mul, int threads);
+void jxo_set_fast_cpu(int on);
 void jxo_f32_to_f16(int n, const float* v, uint16_t* out);
 void jxo_from_linear(uint32_t tf, float gamma, float intensity_target, const float* luminances, int n, float* rgb);
 /* ImageMetadata.orientation (headers/image_metadata.rs:85-96 display_pixel): pixel (x, y) of the tight w x h source goes

@@ -398,3 +398,27 @@ def test_pipelined_decoder_host_logic_with_a_fake_device(monkeypatch):
         dec.decode(files[:2], [(1, 1), (2, 2)])
     finally:
         dec.close()
+
+
+@pytest.mark.parametrize("w,h,epf,profile,fmt", [(520, 300, 2, 1, 0), (333, 271, 1, 2, 1), (1024, 768, 2, 3, 0), (300, 200, 3, 1, 0),
+                                                 (64, 40, 2, 0, 0)])
+def test_fast_cpu_forms_are_bit_identical_to_the_scalar_oracle(w, h, epf, profile, fmt):
+    """The AVX2 forms the CPU baseline of bench.py runs (8-lane IDCTs, Gaborish, EPF 1 / 2, sRGB u8 store: every lane runs
+    the scalar sequence) against the plain restatement that serves as the checker: coefficients aside, every plane and
+    every output byte must be equal."""
+    import synth
+    from jxl_rs_b200 import abi
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    data = synth.encode_synthetic(w, h, 90 + w, 0.5, epf, 1, profile)
+    f = abi.FORMAT_RGBA_U8 if fmt else abi.FORMAT_RGB_U8
+    try:
+        lib.jxo_set_fast_cpu(0)
+        a, ta = ob.decode_file(data, f, taps=True, threads=2)
+        lib.jxo_set_fast_cpu(1)
+        b, tb = ob.decode_file(data, f, taps=True, threads=2)
+    finally:
+        lib.jxo_set_fast_cpu(0)
+    assert np.array_equal(ta["xyb_idct"], tb["xyb_idct"])
+    assert np.array_equal(ta["xyb_filtered"], tb["xyb_filtered"])
+    assert np.array_equal(a, b)
