@@ -281,7 +281,7 @@ def run_modular(args, rank, world, local_rank, numa):
         frames = list(ex.map(j.ModularParsedFrame, files))
     ctx = j.JxgContext(local_rank)
     dev_out = [torch.empty((H, W, 3), dtype=torch.uint8, device=f"cuda:{local_rank}") for _ in range(n)]
-    b = j.ModularBatch(ctx, 1)
+    b = j.ModularBatch(ctx, 2)  # two streams per warp: 7 % faster than one on this workload (profiles/r02q_modular_and_bench.log)
     for fr, o in zip(frames, dev_out):
         b.add(fr, o.data_ptr(), W * 3, True)
     b.run()
@@ -316,7 +316,7 @@ def run_modular(args, rank, world, local_rank, numa):
     def e2e_step():
         with ThreadPoolExecutor(max_workers=max(1, min(n, rank_cores()))) as ex:
             frs = list(ex.map(j.ModularParsedFrame, files))
-        mb = j.ModularBatch(ctx, 1)
+        mb = j.ModularBatch(ctx, 2)  # two streams per warp: 7 % faster than one on this workload (profiles/r02q_modular_and_bench.log)
         try:
             for fr, o in zip(frs, host_out):
                 mb.add(fr, o.data_ptr(), W * 3, False)
@@ -420,7 +420,12 @@ def main():
     with ThreadPoolExecutor(max_workers=min(n, rank_cores())) as ex:
         per_file = max(1, rank_cores() // max(1, len(files)))  # one large image: LF groups in parallel
         frames = list(ex.map(lambda f: j.ParsedFrame(f, per_file), files))
-    depth = max(1, args.inflight)
+    # resident batches: as asked, but never more than fit the device (pools per batch ~ 48 B per pixel: coefficient lists at
+    # worst-case capacity, two XYB plane sets, output, varblock descriptors); config 3 (1.06 GP per batch) gets 3, not 5
+    free_b, _total_b = torch.cuda.mem_get_info(local_rank)
+    per_batch = 48.0 * args.width * args.height * n + (1 << 30)
+    depth = max(1, min(args.inflight, int(0.8 * free_b / per_batch)))
+    e2e_cap = depth
     ctxs = [ctx] + [j.JxgContext(local_rank) for _ in range(depth - 1)]
     dev_out = [[torch.empty((fr.height, fr.width, 3), dtype=torch.uint8, device=f"cuda:{local_rank}") for fr in frames]
                for _ in range(depth)]
@@ -488,7 +493,7 @@ def main():
     # ---------------- end to end through the public API (host bytes -> host pixels) ----------------
     # K batches stream through PipelinedDecoder (2 contexts): parse + staging of batch k+1 overlap the kernels
     # and D2H copies of batch k; every batch's pixels are in pinned host memory before the clock stops.
-    e2e_depth = max(1, args.e2e_depth)  # contexts of the pipelined decoder = host output sets (a set is rewritten only after its batch retired)
+    e2e_depth = max(1, min(args.e2e_depth, e2e_cap))  # contexts of the pipelined decoder = host output sets (a set is rewritten only after its batch retired)
     host_out = [[torch.empty((fr.height, fr.width, 3), dtype=torch.uint8).pin_memory() for fr in frames] for _ in range(e2e_depth)]
     outs = [[(o.data_ptr(), fr.width * 3) for o, fr in zip(ho, frames)] for ho in host_out]
     del frames

@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,6 +29,8 @@ using namespace jxgpu;
 namespace jxgpu {
 namespace detail {
 thread_local std::string g_error;
+std::atomic<int> g_live_contexts[64];  // per device: contexts between jxg_init and jxg_shutdown
+
 DeviceStreams device_streams(int device) {
   static std::mutex mu;
   static DeviceStreams table[64];
@@ -46,6 +51,50 @@ DeviceStreams device_streams(int device) {
 using namespace jxgpu::detail;
 
 namespace {
+
+// Host-ordered output copies (JXG_D2H_HOST_ORDERED=1): one thread per process takes the batches in launch order, waits on
+// the HOST for each frame range's filter launch (cudaEventSynchronize on a blocking-sync event) and only then enqueues that
+// range's D2H copies on the device's first-in-first-out copy stream. The copy stream then never holds a semaphore wait: a
+// stream parked on cudaStreamWaitEvent for tens of milliseconds (the next batch's filters) keeps the GPU's channel
+// scheduler from starting newly submitted streams - the first event of a new batch's stream was stamped 60 - 80 ms after
+// its submission, exactly when the output copies of the batch three launches earlier ended
+// (profiles/r02r_e2e_host_clock.log).
+class Copier {
+ public:
+  static Copier& get() {
+    // never destroyed: its thread waits on the condition variable for the life of the process, and destroying a condition
+    // variable with a waiter blocks (glibc) - a static instance would hang every process at exit
+    static Copier* c = new Copier;
+    return *c;
+  }
+  void push(std::function<void()> job) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!started_) {
+      started_ = true;
+      std::thread([this] { run(); }).detach();
+    }
+    q_.push_back(std::move(job));
+    cv_.notify_one();
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !q_.empty(); });
+        job = std::move(q_.front());
+        q_.pop_front();
+      }
+      job();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  bool started_ = false;
+};
 
 struct FrameOut {
   void* user_ptr;
@@ -100,6 +149,17 @@ struct Batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_handoff = nullptr;
   bool copies_on_copy_stream = false;  // last run: the D2H copies went to a copy stream (`copy_stream`), not the launching one
   cudaStream_t copy_stream = nullptr;  // the device's shared D2H stream (default) or the context's own (JXG_D2H_SHARED=0)
+  // host-ordered copies: set by the copier thread once every copy and ev1 are enqueued (wait / end block on it first)
+  std::mutex copier_mu;
+  std::condition_variable copier_cv;
+  bool copier_pending = false;
+  bool host_ordered = false;  // this run's copies are enqueued by the copier thread
+  uint32_t host_ranges = 0;
+  int copier_error = 0;
+  void copier_wait() {
+    std::unique_lock<std::mutex> lk(copier_mu);
+    copier_cv.wait(lk, [&] { return !copier_pending; });
+  }
   cudaStream_t last_stream = nullptr;  // stream of the last run / rerun (the context's or the caller's)
   bool profile = false;
   cudaEvent_t stage_ev[kNumStages + 1] = {nullptr};
@@ -214,8 +274,8 @@ int jxg_init(int device, void** out_ctx) {
   ctx->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  for (auto& e : ctx->range_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+  for (auto& e : ctx->range_done) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming | cudaEventBlockingSync));
   // constant tables
   std::vector<float> wc(9 * 128, 0.0f), rs(6 * 32, 0.0f);
   for (int l = 1; l <= 8; l++) {
@@ -250,6 +310,7 @@ int jxg_init(int device, void** out_ctx) {
   if (int r = upload(ctx->natural_orders, no, ctx->stream, nullptr)) return r;
   if (int r = upload(ctx->natural_order_off, no_off, ctx->stream, nullptr)) return r;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  g_live_contexts[device & 63].fetch_add(1);
   *out_ctx = ctx.release();
   return JXG_OK;
 }
@@ -264,6 +325,7 @@ void jxg_shutdown(void* c) {
     if (e) cudaEventDestroy(e);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->status_host) cudaFreeHost(ctx->status_host);
+  g_live_contexts[ctx->device & 63].fetch_sub(1);
   delete ctx;
 }
 
@@ -296,6 +358,7 @@ void jxg_batch_end(void* bp) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b) return;
   cudaSetDevice(b->ctx->device);
+  b->copier_wait();
   if (b->uploaded && b->ev1) cudaEventSynchronize(b->ev1);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
@@ -319,6 +382,7 @@ int jxg_batch_set_profile(void* bp, int on) {
 int jxg_batch_stage_times(void* bp, float* ms, int n) {
   Batch* b = static_cast<Batch*>(bp);
   if (!b || !ms || n < kNumStages || !b->profile) return JXG_ERR_ARGUMENT;
+  b->copier_wait();
   CUDA_TRY(cudaEventSynchronize(b->ev1));
   for (int i = 0; i < kNumStages; i++) {
     ms[i] = 0.0f;
@@ -340,6 +404,7 @@ int jxg_batch_stage_marks(void* bp, float* ms, int n) {
     CUDA_TRY(cudaEventRecord(ref, 0));
     CUDA_TRY(cudaEventSynchronize(ref));
   }
+  b->copier_wait();
   CUDA_TRY(cudaEventSynchronize(b->ev1));
   for (int i = 0; i <= kNumStages; i++)
     if (cudaEventElapsedTime(&ms[i], ref, b->stage_ev[i]) != cudaSuccess) ms[i] = 0.0f;
@@ -611,7 +676,12 @@ static void schedule_lean(Batch* b) {
   // The kernel keeps 6 CTAs per SM resident (register bound); a grid beyond one resident wave would start its last
   // CTAs only when the first ones end, so the packing is made denser until the grid fits.
   const uint32_t max_ctas = 148 * 6;
+  // 4 lanes per warp are the fastest schedule for a batch that has the device to itself; 8 lanes halve the kernel's
+  // warp-instructions, which is what counts once several batches share the SMs (64 x 4K: alone 57.2 against 52.3 ms, three
+  // resident batches 37.1 against 40.5 ms per batch, five 35.1 against 38.0; 16 and 32 lanes lose again:
+  // profiles/r02k_entropy_lanes.log). Three or more live contexts on the device are taken as "batches share the SMs".
   uint32_t S = 4;
+  if (g_live_contexts[b->ctx->device & 63].load() >= 3 && b->streams_lean.size() >= 2048) S = 8;
   const char* s_env = getenv("JXG_ENTROPY_S");  // pins the lanes per warp (experiments)
   if (s_env) S = uint32_t(atoi(s_env));
   S = S <= 1 ? 1 : (S <= 2 ? 2 : (S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32))));
@@ -654,10 +724,7 @@ static void schedule_lean(Batch* b) {
     }
     b->lean_ctas = ctas;
     if (ctas <= max_ctas) break;
-    // denser: first fewer privileged warps, then 8 lanes per warp, then more streams per packed lane. A batch that does
-    // not fit one resident wave at 4 lanes per warp is a throughput job: 8 lanes halve the kernel's warp-instructions,
-    // which is what counts once several batches share the SMs (64 x 4K: alone 57.2 against 52.3 ms, three resident batches
-    // 37.1 against 40.5 ms per batch, five 35.1 against 38.0; 16 and 32 lanes lose again: profiles/r02k_entropy_lanes.log).
+    // denser: first fewer privileged warps, then 8 lanes per warp, then more streams per packed lane
     if (solo < 0.95f) solo = std::min(0.95f, solo + 0.1f), duo = std::min(0.9f, duo + 0.1f);
     else if (L < S) L = S;
     else if (S < 8 && !s_env) S = L = 8;
@@ -736,6 +803,9 @@ static int launch(Batch* b, cudaStream_t se, cudaStream_t s, bool copy_to_host) 
     const bool same_stream = copy_to_host && d2h_ranges <= 0;
     const uint32_t nr = (copy_to_host && !same_stream) ? std::min<uint32_t>(std::min<uint32_t>(uint32_t(d2h_ranges), Context::kMaxRanges), nf) : 1;
     static const bool shared_d2h = !(getenv("JXG_D2H_SHARED") && atoi(getenv("JXG_D2H_SHARED")) == 0);
+    static const bool host_ordered_env = getenv("JXG_D2H_HOST_ORDERED") && atoi(getenv("JXG_D2H_HOST_ORDERED")) != 0;
+    b->host_ordered = host_ordered_env && copy_to_host && !same_stream;
+    b->host_ranges = nr;
     const DeviceStreams ds = device_streams(cx->device);
     b->copy_stream = (shared_d2h && ds.d2h) ? ds.d2h : cx->copy_stream;
     cudaStream_t cs = same_stream ? s : b->copy_stream;
@@ -758,6 +828,7 @@ static int launch(Batch* b, cudaStream_t se, cudaStream_t s, bool copy_to_host) 
       if (copy_to_host) {
         if (!same_stream) {
           CUDA_TRY(cudaEventRecord(cx->range_done[r], s));
+          if (b->host_ordered) continue;  // the copier thread waits for the event and enqueues this range's copies
           CUDA_TRY(cudaStreamWaitEvent(cs, cx->range_done[r], 0));
         }
         for (uint32_t f = f0; f < f1; f++) {
@@ -895,7 +966,42 @@ int jxg_batch_run(void* bp, void* cuda_stream) {
   if (int r = copy_status(b, s)) return r;
   // ev1 = everything of this batch done. The copy stream joins the post stream and carries ev1 when it holds the D2H
   // copies: the post stream itself must not wait for them (the next batch's transforms follow on it).
-  if (b->copies_on_copy_stream) {
+  if (b->copies_on_copy_stream && b->host_ordered) {
+    Context* cx = b->ctx;
+    CUDA_TRY(cudaEventRecord(cx->copy_done, s));  // behind the status words
+    {
+      std::lock_guard<std::mutex> lk(b->copier_mu);
+      b->copier_pending = true;
+      b->copier_error = 0;
+    }
+    Copier::get().push([b] {
+      Context* cx = b->ctx;
+      int err = 0;
+      auto chk = [&](cudaError_t e) {
+        if (e != cudaSuccess && !err) err = int(e);
+      };
+      chk(cudaSetDevice(cx->device));
+      const uint32_t nf = uint32_t(b->frames.size()), nr = b->host_ranges;
+      for (uint32_t r = 0; r < nr && !err; r++) {
+        chk(cudaEventSynchronize(cx->range_done[r]));  // host-side wait: nothing parks on the copy stream
+        const uint32_t f0 = uint32_t(uint64_t(nf) * r / nr), f1 = uint32_t(uint64_t(nf) * (r + 1) / nr);
+        for (uint32_t f = f0; f < f1 && !err; f++) {
+          const FrameOut& fo = b->outs[f];
+          if (fo.is_device) continue;
+          chk(cudaMemcpyAsync(fo.user_ptr, static_cast<uint8_t*>(b->d_out.p) + fo.dev_off, fo.copy_bytes, cudaMemcpyDeviceToHost,
+                              b->copy_stream));
+        }
+      }
+      chk(cudaEventSynchronize(cx->copy_done));
+      chk(cudaEventRecord(b->ev1, b->copy_stream));
+      std::lock_guard<std::mutex> lk(b->copier_mu);
+      b->copier_error = err;
+      b->copier_pending = false;
+      b->copier_cv.notify_all();
+    });
+    for (const FrameOut& fo : b->outs)
+      if (!fo.is_device) b->d2h += fo.copy_bytes;
+  } else if (b->copies_on_copy_stream) {
     Context* cx = b->ctx;
     CUDA_TRY(cudaEventRecord(cx->copy_done, s));
     CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, cx->copy_done, 0));
@@ -932,6 +1038,8 @@ int jxg_batch_wait(void* bp, uint32_t* first_bad_frame, uint32_t* first_bad_grou
   {
     static const bool traced = getenv("JXG_TRACE_RUN") && atoi(getenv("JXG_TRACE_RUN")) != 0;
     const auto t0 = std::chrono::steady_clock::now();
+    b->copier_wait();  // host-ordered copies: ev1 exists only once the copier has enqueued everything
+    if (b->copier_error) return set_error(JXG_ERR_CUDA, std::string("output copy failed: ") + cudaGetErrorString(cudaError_t(b->copier_error)));
     const bool was_done = traced && cudaEventQuery(b->ev1) == cudaSuccess;
     CUDA_TRY(cudaEventSynchronize(b->ev1));  // recorded behind the status words and the D2H copies; no stream-wide wait:
                                              // the stage streams carry later batches too

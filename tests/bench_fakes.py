@@ -33,6 +33,7 @@ def install(setattr_fn, fail_e2e=False, gloo=False):
     for mod in (decoder, j):
         setattr_fn(mod, "device_streams", lambda device=0: (1, 2))
     setattr_fn(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
+    setattr_fn(torch.cuda, "mem_get_info", lambda *a, **k: (150 << 30, 180 << 30))
     real_empty, real_tensor = torch.empty, torch.tensor
     setattr_fn(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
     setattr_fn(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
