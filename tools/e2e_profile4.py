@@ -30,6 +30,11 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     for i in range(depth + 1):  # every context has sized its pools before the clock starts
         submit(dec, i)
     dec.drain()
+    # reference copy of the last rows of the last frame (from the warm-up), then poison those rows in every output set:
+    # after drain() they must hold the picture again - i.e. drain() really returns with the pixels in host memory
+    ref_rows = host_out[0][n - 1][-64:].clone()
+    for ho in host_out:
+        ho[n - 1][-64:].zero_()
     dec.trace = []
     dec.retire_trace = []
     dec.marks = [] if os.environ.get("E2E_MARKS") else None
@@ -39,13 +44,15 @@ for st in [int(x) for x in os.environ.get('E2E_STAGING', '4,8').split(',')]:
     t_sub = time.perf_counter()
     dec.drain()
     t_drain = time.perf_counter()
+    complete = bool(torch.equal(host_out[(steps - 1) % sets][n - 1][-64:], ref_rows))  # before any device-wide wait
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     torch.cuda.synchronize()
     t_sync2 = time.perf_counter()
     print(f"  second synchronize: {1e3*(t_sync2-t0-dt):.2f} ms")
     print(f"staging_threads={st}: {dt/steps*1e3:.1f} ms/step, {n*3840*2160/1e6*steps/dt:.0f} MP/s")
-    print(f"  main thread: submits done at {1e3*(t_sub-t0):.1f} ms, drain returned at {1e3*(t_drain-t0):.1f}, device idle at {1e3*dt:.1f}")
+    print(f"  main thread: submits done at {1e3*(t_sub-t0):.1f} ms, drain returned at {1e3*(t_drain-t0):.1f} "
+          f"(last rows of the last frame in host memory: {complete}), device idle at {1e3*dt:.1f}")
     for (ts, ret, pw, add, run) in dec.trace:
         print(f"  t={1e3*(ts-t0):7.1f}  retire {ret*1e3:6.1f}  parsewait {pw*1e3:6.1f}  add {add*1e3:6.1f}  run {run*1e3:6.1f}")
     for (ts, w, m, c) in dec.retire_trace:
