@@ -268,6 +268,15 @@ int jxg_modular_batch_read_planes(void* batch, uint32_t f, int32_t* out, size_t 
 /* ms[0]: whole batch on the device, ms[1]: group-stream decode kernel (+ local RCT). */
 int jxg_modular_batch_stats(void* batch, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* kernel_launches, float* ms);
 void jxg_modular_batch_end(void* batch);
+/* Parity tap (no device needed): the table form of one channel's MA-tree walk as the Modular path builds it - the device
+ * counterpart of the single-property specialisations of frame/modular/decode/specialized_trees.rs:197-372.
+ * nodes: n_nodes x 5 ints {property (< 0: leaf), split value | offset, left child | predictor, right child | multiplier,
+ * leaf context}; context_map: leaf context -> cluster. Returns 1 and fills lut[2048] (index = property value clamped to
+ * [-1024, 1023] + 1024; entry = predictor | cluster << 4 | plain << 12 | leaf node << 16) and *property (0xff: single leaf,
+ * every entry equal) when the tree left after the channel / stream decisions has a table form, 0 when the channel needs
+ * the generic walk, JXG_ERR_ARGUMENT on malformed input. */
+int jxg_modular_walk_table(const int32_t* nodes, uint32_t n_nodes, const uint8_t* context_map, uint32_t n_contexts,
+                           uint32_t channel, uint32_t stream_id, uint32_t* lut, uint32_t* property);
 
 const char* jxg_last_error(void);
 

@@ -617,6 +617,32 @@ int jxg_modular_batch_stats(void* bp, uint64_t* h2d, uint64_t* d2h, uint64_t* la
   return JXG_OK;
 }
 
+int jxg_modular_walk_table(const int32_t* nodes, uint32_t n_nodes, const uint8_t* context_map, uint32_t n_contexts,
+                           uint32_t channel, uint32_t stream_id, uint32_t* lut_out, uint32_t* property) {
+  if (!nodes || !n_nodes || !context_map || !lut_out || !property) return JXG_ERR_ARGUMENT;
+  jxg::ModularTree t;
+  t.nodes.resize(n_nodes);
+  for (uint32_t i = 0; i < n_nodes; i++) {
+    jxg::TreeNode& n = t.nodes[i];
+    n.property = nodes[i * 5];
+    n.val = nodes[i * 5 + 1];
+    n.left = uint32_t(nodes[i * 5 + 2]);
+    n.right = uint32_t(nodes[i * 5 + 3]);
+    n.ctx = uint32_t(nodes[i * 5 + 4]);
+    // children must lie behind their parent (no cycles) and inside the array
+    if (n.property >= 0 && (n.left <= i || n.right <= i || n.left >= n_nodes || n.right >= n_nodes)) return JXG_ERR_ARGUMENT;
+    if (n.property < 0 && n.ctx >= n_contexts) return JXG_ERR_ARGUMENT;
+  }
+  t.code.context_map.assign(context_map, context_map + n_contexts);
+  std::vector<uint32_t> lut;
+  uint32_t prop = kLutNoProperty, single = 0;
+  const uint32_t root = static_root(t, channel, stream_id);
+  if (!build_walk_table(t, root, channel, stream_id, lut, prop, single)) return 0;
+  *property = prop;
+  for (int i = 0; i < kLutSize; i++) lut_out[i] = prop == kLutNoProperty ? single : lut[size_t(i)];
+  return 1;
+}
+
 void jxg_modular_batch_end(void* bp) {
   ModularBatch* b = static_cast<ModularBatch*>(bp);
   if (!b) return;
