@@ -1,7 +1,7 @@
 // Dev tool: mutation fuzzing of the host front-end under AddressSanitizer / UBSan.
 //   H=jxl_rs_b200/csrc/host
 //   g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=undefined -march=x86-64-v3 \
-//       -ffp-contract=off -Ioracle -o /tmp/fuzz_frontend tools/fuzz_frontend.cc oracle/modular_oracle.cc \
+//       -ffp-contract=off -Ioracle -o /tmp/fuzz_frontend tools/fuzz_frontend.cc oracle/modular_oracle.cc oracle/oracle.cc \
 //       $H/entropy.cc $H/headers.cc $H/modular.cc $H/quant.cc $H/frame.cc $H/modular_frame.cc -pthread
 //   /tmp/fuzz_frontend 1000 tests/golden/jxl/*.jxl
 // Every input is mutated `iters` times (bit flips, random bytes, 0xff bytes, truncation; a third of the mutations land
