@@ -416,9 +416,11 @@ def test_fast_cpu_forms_are_bit_identical_to_the_scalar_oracle(w, h, epf, profil
         lib.jxo_set_fast_cpu(0)
         a, ta = ob.decode_file(data, f, taps=True, threads=2)
         lib.jxo_set_fast_cpu(1)
-        b, tb = ob.decode_file(data, f, taps=True, threads=2)
+        ob.decode_file(synth.encode_synthetic(w + 72, h + 40, 3, 0.5, 2, 1, 1), f, threads=1)  # stale pixels of a larger frame
+        b, tb = ob.decode_file(data, f, taps=True, threads=1)                                    # in this thread's plane pool
+        b2, _ = ob.decode_file(data, f, threads=2)
     finally:
         lib.jxo_set_fast_cpu(0)
     assert np.array_equal(ta["xyb_idct"], tb["xyb_idct"])
     assert np.array_equal(ta["xyb_filtered"], tb["xyb_filtered"])
-    assert np.array_equal(a, b)
+    assert np.array_equal(a, b) and np.array_equal(a, b2)
