@@ -235,6 +235,49 @@ void dequant_lf_rect(FrameState& fs, const int32_t* qy_p, const int32_t* qx_p, c
   }
 }
 
+// Varblocks of one LF group's rect (w x hh blocks, maps with row stride `stride`, every entry 27 = INVALID_TRANSFORM on
+// entry) in raster order at the first uncovered block (modular/mod.rs:1040-1075): block `num` of the HF-metadata channel
+// {raw_transforms, raw_quants} lands there; its first block carries bit 7.
+void place_varblocks(uint32_t w, uint32_t hh, size_t stride, uint32_t count, const int32_t* raw_transforms, const int32_t* raw_quants,
+                     uint8_t* transform_map, int32_t* raw_quant_map) {
+  uint32_t num = 0;
+  for (uint32_t y = 0; y < hh; y++) {
+    uint8_t* tm = transform_map + size_t(y) * stride;
+    int32_t* rq = raw_quant_map + size_t(y) * stride;
+    const uint32_t ngy = std::min(hh, (y / 32 + 1) * 32);
+    for (uint32_t x = 0; x < w;) {
+      if (tm[x] != 27) {  // already covered by an earlier varblock
+        x++;
+        continue;
+      }
+      if (num >= count) fail("invalid VarDCT transform map");
+      const int32_t raw_transform = raw_transforms[num];
+      const int32_t raw_quant = 1 + std::clamp(raw_quants[num], 0, 255);
+      if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
+      const uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
+      const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
+      if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
+      num++;
+      if ((cx | cy) == 1) {  // the 8x8-class transforms (most varblocks): no loops with data-dependent trip counts
+        tm[x] = uint8_t(raw_transform) | 128;
+        rq[x] = raw_quant;
+        x++;
+        continue;
+      }
+      for (uint32_t iy = 0; iy < cy; iy++) {
+        uint8_t* t = tm + size_t(iy) * stride + x;
+        int32_t* q = rq + size_t(iy) * stride + x;
+        for (uint32_t ix = 0; ix < cx; ix++) {  // a block covered earlier is overwritten, like mod.rs:1066-1075
+          t[ix] = uint8_t(raw_transform);
+          q[ix] = raw_quant;
+        }
+      }
+      tm[x] |= 128;  // first block of the varblock
+      x += cx;
+    }
+  }
+}
+
 namespace {
 // modular/mod.rs:837-1080: one LF group (LF image, ModularLF stream of extra channels, HF metadata), in phases so
 // that two groups can run their Modular sub-bitstreams in lockstep (decode_substreams_paired):
@@ -311,44 +354,8 @@ struct LfGroupJob {
         }
         if (seen & ~7) fail("invalid EPF sharpness value");
       }
-      // Varblocks in raster order at the first uncovered block (modular/mod.rs:1040-1075)
-      uint32_t num = 0;
-      const int32_t *raw_transforms = ch[2].row(0), *raw_quants = ch[2].row(1);
-      for (uint32_t y = 0; y < hh; y++) {
-        uint8_t* tm = &fs.transform_map[size_t(y0 + y) * fs.xb + x0];
-        int32_t* rq = &fs.raw_quant_map[size_t(y0 + y) * fs.xb + x0];
-        const uint32_t ngy = std::min(hh, (y / 32 + 1) * 32);
-        for (uint32_t x = 0; x < w;) {
-          if (tm[x] != 27) {  // already covered by an earlier varblock
-            x++;
-            continue;
-          }
-          if (num >= count) fail("invalid VarDCT transform map");
-          const int32_t raw_transform = raw_transforms[num];
-          const int32_t raw_quant = 1 + std::clamp(raw_quants[num], 0, 255);
-          if (raw_transform < 0 || raw_transform >= 27) fail("invalid VarDCT transform");
-          const uint32_t cx = kCoveredBlocksX[raw_transform], cy = kCoveredBlocksY[raw_transform];
-          const uint32_t ngx = std::min(w, (x / 32 + 1) * 32);
-          if (x + cx > ngx || y + cy > ngy) fail("HF block out of bounds");
-          num++;
-          if ((cx | cy) == 1) {  // the 8x8-class transforms (most varblocks): no loops with data-dependent trip counts
-            tm[x] = uint8_t(raw_transform) | 128;
-            rq[x] = raw_quant;
-            x++;
-            continue;
-          }
-          for (uint32_t iy = 0; iy < cy; iy++) {
-            uint8_t* t = tm + size_t(iy) * fs.xb + x;
-            int32_t* q = rq + size_t(iy) * fs.xb + x;
-            for (uint32_t ix = 0; ix < cx; ix++) {  // a block covered earlier is overwritten, like mod.rs:1066-1075
-              t[ix] = uint8_t(raw_transform);
-              q[ix] = raw_quant;
-            }
-          }
-          tm[x] |= 128;  // first block of the varblock
-          x += cx;
-        }
-      }
+      place_varblocks(w, hh, fs.xb, count, ch[2].row(0), ch[2].row(1), &fs.transform_map[size_t(y0) * fs.xb + x0],
+                      &fs.raw_quant_map[size_t(y0) * fs.xb + x0]);
     }
     ss.reset();
     br.check();

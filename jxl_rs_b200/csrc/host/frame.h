@@ -95,6 +95,9 @@ struct FrameState {
 };
 
 // modular/mod.rs:837-929 dequant_lf (4:4:4) on a w x h rect of quantised LF integers; exposed for the tests.
+// HF-metadata placement of one LF group (modular/mod.rs:1040-1075), see frame.cc.
+void place_varblocks(uint32_t w, uint32_t hh, size_t stride, uint32_t count, const int32_t* raw_transforms, const int32_t* raw_quants,
+                     uint8_t* transform_map, int32_t* raw_quant_map);
 void dequant_lf_rect(FrameState& fs, const int32_t* qy, const int32_t* qx, const int32_t* qb, size_t qstride, uint32_t w, uint32_t h,
                      float mul, size_t o0);
 

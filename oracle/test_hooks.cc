@@ -240,4 +240,20 @@ void jxo_t_dequant_lf(uint32_t w, uint32_t h, const int32_t* q, uint32_t global_
   for (int c = 0; c < 3; c++) memcpy(out + size_t(c) * n, fs.lf[c].data(), n * 4);
   memcpy(qlf, fs.quant_lf_map.data(), n);
 }
+
+// The front-end's varblock placement of one LF-group rect (frame.cc place_varblocks): maps come back w x h with 27 =
+// uncovered; returns 0 or the front-end's error code for an invalid block list.
+int jxo_t_place_varblocks(uint32_t w, uint32_t h, uint32_t count, const int32_t* raw_transforms, const int32_t* raw_quants,
+                          uint8_t* transform_map, int32_t* raw_quant_map) {
+  for (size_t i = 0; i < size_t(w) * h; i++) {
+    transform_map[i] = 27;
+    raw_quant_map[i] = 0;
+  }
+  try {
+    jxg::place_varblocks(w, h, w, count, raw_transforms, raw_quants, transform_map, raw_quant_map);
+    return 0;
+  } catch (jxg::Error& e) {
+    return e.code ? e.code : -1;
+  }
+}
 }

@@ -160,3 +160,89 @@ def test_dequant_lf_against_f64_restatement(extra_precision):
     by = (q[0][..., None] > thr[1]).sum(-1)
     bb = (q[2][..., None] > thr[2]).sum(-1)
     assert np.array_equal(qlf, ((bx * (len(thr[2]) + 1) + bb) * (len(thr[1]) + 1) + by).astype(np.uint8))
+
+
+# ---- HF-metadata placement (integer; lives here with the other independent restatements of the front-end) ----
+_COV_X = [1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32]
+_COV_Y = [1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16]
+
+
+def _place_reference(w, h, count, raw_t, raw_q):
+    """modular/mod.rs:1032-1078 written out as the reference writes it: every block position in raster order; a position
+    already covered is skipped; the next entry of the block list is placed there (bounds: the LF-group rect and the 32x32
+    block group); covered positions are overwritten, the first one carries bit 7. covered_blocks_x/y: transform_map.rs."""
+    tm = np.full((h, w), 27, np.uint8)
+    rq = np.zeros((h, w), np.int32)
+    num = 0
+    for y in range(h):
+        for x in range(w):
+            if tm[y, x] != 27:
+                continue
+            if num >= count:
+                return None
+            t = int(raw_t[num])
+            q = 1 + min(max(int(raw_q[num]), 0), 255)
+            if not 0 <= t < 27:
+                return None
+            cx, cy = _COV_X[t], _COV_Y[t]
+            if x + cx > min(w, (x // 32 + 1) * 32) or y + cy > min(h, (y // 32 + 1) * 32):
+                return None
+            num += 1
+            for iy in range(cy):
+                for ix in range(cx):
+                    tm[y + iy, x + ix] = t | (128 if (ix == 0 and iy == 0) else 0)
+                    rq[y + iy, x + ix] = q
+    return tm, rq
+
+
+def test_varblock_placement_against_the_reference_loop():
+    """The front-end's placement loop (skips covered runs, 8x8 fast path, row pointers) against the reference's plain double
+    loop, on random block lists: valid tilings with all 27 transform types, lists that run out, blocks that cross a 32x32
+    group or the rect, out-of-range transform ids, quantiser values outside 0..255."""
+    from tests import oracle_binding as ob
+    lib = ob.load()
+    lib.jxo_t_place_varblocks.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(77)
+    ok = bad = 0
+    for trial in range(300):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        # build a list by simulating the placement with random transform choices that fit (or, sometimes, any choice)
+        sloppy = trial % 6 == 5
+        poison = trial % 9 == 8  # one out-of-range transform id somewhere in the list
+        cover = np.zeros((h, w), bool)
+        ts, qs = [], []
+        for y in range(h):
+            for x in range(w):
+                if cover[y, x]:
+                    continue
+                cands = list(range(27))
+                rng.shuffle(cands)
+                t = None
+                for c in cands:
+                    cx, cy = _COV_X[c], _COV_Y[c]
+                    if sloppy or (x + cx <= min(w, (x // 32 + 1) * 32) and y + cy <= min(h, (y // 32 + 1) * 32)
+                                  and not cover[y:y + cy, x:x + cx].any()):
+                        t = c
+                        break
+                if t is None:
+                    t = 0
+                cx, cy = _COV_X[t], _COV_Y[t]
+                cover[y:min(h, y + cy), x:min(w, x + cx)] = True
+                ts.append(t)
+                qs.append(int(rng.integers(-20, 300)))
+        if poison:
+            ts[int(rng.integers(0, len(ts)))] = int(rng.choice([-1, 27, 31, 200]))
+        if trial % 11 == 10 and len(ts) > 1:
+            ts, qs = ts[:-1], qs[:-1]  # list runs out
+        raw_t, raw_q = np.array(ts, np.int32), np.array(qs, np.int32)
+        want = _place_reference(w, h, len(ts), raw_t, raw_q)
+        tm, rq = np.zeros((h, w), np.uint8), np.zeros((h, w), np.int32)
+        r = lib.jxo_t_place_varblocks(w, h, len(ts), raw_t.ctypes.data, raw_q.ctypes.data, tm.ctypes.data, rq.ctypes.data)
+        if want is None:
+            assert r != 0, trial
+            bad += 1
+        else:
+            assert r == 0, trial
+            assert np.array_equal(tm, want[0]) and np.array_equal(rq, want[1]), trial
+            ok += 1
+    assert ok > 150 and bad > 40, (ok, bad)
