@@ -168,6 +168,22 @@ def test_c_abi_exports_every_declared_symbol():
         assert b"no CPU fallback" in lib.jxg_last_error()
 
 
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/jxg.h is the boundary a Rust / C host binds: it must compile as C99 (no C++ in the signatures) and a C program
+    must link against libjxgpu.so and reach an entry point (jxg_init without a GPU returns JXG_ERR_NO_DEVICE)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "jxg.h"\n'
+                   'int main(void) { void* ctx = 0; int r = jxg_init(0, &ctx); printf("%d %d\\n", JXG_ABI_VERSION, r);'
+                   ' if (r == 0) jxg_shutdown(ctx); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(abi.library_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-ljxgpu", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == abi.JXG_ABI_VERSION
+    assert int(out[1]) == (0 if os.path.exists("/dev/nvidia0") else -21)
+
+
 def test_product_does_not_touch_the_oracle():
     """Nothing under jxl_rs_b200/ may import, link or execute oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "jxl_rs_b200")):
