@@ -751,7 +751,7 @@ int decode_group(const JxgFrameDesc& d, const Geometry& geo, uint32_t g, const u
   return 0;
 }
 
-// AVX2 forms of Gaborish, EPF 1 / 2 and the sRGB u8 store (8 pixels per step, the per-pixel arithmetic and its order
+// AVX2 forms of Gaborish, EPF 0 / 1 / 2 and the sRGB u8 store (8 pixels per step, the per-pixel arithmetic and its order
 // unchanged: outputs are bit-identical to the scalar definitions below, tests/test_cpu_paths.py checks that). Off by
 // default - the checker stays the plain restatement; bench.py's CPU arm turns them on (jxo_set_fast_cpu) so that the CPU
 // baseline is not handicapped by scalar filter loops the reference runs as SIMD (render/stages/epf/*.rs, gaborish.rs).
@@ -897,7 +897,7 @@ void epf(int stage, const JxgFrameDesc& d, const Geometry& geo, const std::vecto
 #ifdef __AVX2__
   // Eight pixels of one 8x8 block row at a time (x0 a multiple of 8, neighbourhood inside the image): the sigma is one
   // value for the chunk, the border rule a lane mask; every lane runs the scalar sequence above.
-  const bool fast = g_fast_cpu.load() != 0 && stage != 0;
+  const bool fast = g_fast_cpu.load() != 0;
   const __m256 vabs = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
   auto chunk = [&](ptrdiff_t x0, ptrdiff_t y) {
     const float inv_sigma_px = sigma[size_t(y / 8) * geo.xb + size_t(x0 / 8)];
@@ -928,25 +928,28 @@ void epf(int stage, const JxgFrameDesc& d, const Geometry& geo, const std::vecto
       for (int c = 0; c < 3; c++) _mm256_storeu_ps(out.p[c] + size_t(y) * out.stride + x0, _mm256_mul_ps(acc[c], inv_w));
       return;
     }
-    __m256 sads[4] = {zero, zero, zero, zero};
+    const int nn = stage == 0 ? 12 : 4;  // stage 0: the 12 neighbours of epf0.rs:182-195, same sequence as the scalar form
+    const int(*offv)[2] = stage == 0 ? kOff0 : kOff1;
+    __m256 sads[12];
+    for (int k = 0; k < nn; k++) sads[k] = zero;
     for (int c = 0; c < 3; c++) {
       const __m256 scale = _mm256_set1_ps(d.epf_channel_scale[c]);
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < nn; k++) {
         __m256 sacc = zero;
         for (auto& pl : kPlusOrder)
-          sacc = _mm256_add_ps(sacc, _mm256_and_ps(_mm256_sub_ps(ld(c, pl[0], pl[1]), ld(c, pl[0] + kOff1[k][0], pl[1] + kOff1[k][1])), vabs));
+          sacc = _mm256_add_ps(sacc, _mm256_and_ps(_mm256_sub_ps(ld(c, pl[0], pl[1]), ld(c, pl[0] + offv[k][0], pl[1] + offv[k][1])), vabs));
         sads[k] = _mm256_fmadd_ps(scale, sacc, sads[k]);
       }
     }
     __m256 wsum = one;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < nn; k++) {
       sads[k] = _mm256_max_ps(_mm256_fmadd_ps(sads[k], inv_s, one), zero);
       wsum = _mm256_add_ps(wsum, sads[k]);
     }
     const __m256 inv_w = _mm256_div_ps(one, wsum);
     for (int c = 0; c < 3; c++) {
       __m256 o = ld(c, 0, 0);
-      for (int k = 3; k >= 0; k--) o = _mm256_fmadd_ps(ld(c, kOff1[k][0], kOff1[k][1]), sads[k], o);
+      for (int k = nn - 1; k >= 0; k--) o = _mm256_fmadd_ps(ld(c, offv[k][0], offv[k][1]), sads[k], o);
       _mm256_storeu_ps(out.p[c] + size_t(y) * out.stride + x0, _mm256_mul_ps(o, inv_w));
     }
   };
