@@ -152,9 +152,9 @@ typedef struct JxgFrameDesc {
  * threads and pinned allocations to the GPU's NUMA node before jxg_init. buf: >= 16 bytes. */
 int jxg_device_pci_bus_id(int device, char* buf, int len);
 
-/* Batches run without an explicit stream are pipelined over two streams shared by all contexts of the device: upload +
- * entropy decode of batch k + 1 on the first, transforms + filters + stores of batch k on the second (one kernel of each
- * kind at a time, sharing every SM). This returns them, e.g. to record timing events around a sequence of batches. */
+/* The device's two optional stage streams (JXG_STAGE_STREAMS=1: block plan + entropy decode of every batch on the first,
+ * transforms + filters + stores on the second). Off by default - every batch runs on its context's own stream, which
+ * measured faster; returned so that a host that turns them on can record events on them. */
 int jxg_device_streams(int device, void** entropy_stream, void** post_stream);
 
 /* Context: one per device/rank. Owns streams, pinned staging and device pools. */
@@ -251,7 +251,8 @@ int jxg_parsed_desc(void* parsed, uint32_t output_format, JxgFrameDesc* desc, co
  * section 0, ModularLF streams, group headers / local trees) is jxg_modular_parse_file; a Rust host would hand over
  * the same state from Frame::decode_lf_global / decode_lf_group (frame/decode.rs:307-497).
  * Device scope: 8-bit RGB / grey, one pass, global transforms RCT and Squeeze, group-local RCT, ANS or prefix codes,
- * all 14 predictors incl. the weighted one, all properties incl. those of reference channels. Palette and LZ77 return
+ * all 14 predictors incl. the weighted one, all properties incl. those of reference channels, the global palette
+ * transform without delta entries (transforms/palette.rs:165-199). Delta palettes and LZ77 in group streams return
  * JXG_ERR_UNSUPPORTED (no CPU fallback). Output: interleaved RGB u8 (grey replicated). */
 int jxg_modular_parse_file(const uint8_t* data, size_t size, void** parsed, JxgImageInfo* info);
 void jxg_modular_parsed_free(void* parsed);
