@@ -203,8 +203,8 @@ def decode_files(ctx: JxgContext, files, pixel_format: JxlPixelFormat = JxlPixel
 
 
 def device_streams(device: int = 0):
-    """(entropy stream, post stream) of the device as raw cudaStream_t values (jxg_device_streams): batches run without
-    an explicit stream are pipelined over these two."""
+    """(entropy stream, post stream) of the device as raw cudaStream_t values (jxg_device_streams): the optional stage
+    streams (JXG_STAGE_STREAMS=1); by default every batch runs on its context's own stream."""
     lib = abi.load_library()
     e, p = C.c_void_p(), C.c_void_p()
     abi.check(lib, lib.jxg_device_streams(device, C.byref(e), C.byref(p)))
@@ -285,10 +285,11 @@ def effective_cpus() -> int:
 class PipelinedDecoder:
     """Streaming decode of many batches. `submit()` only queues a batch: its files start parsing on the worker
     pool at once (so parsing of batch k+1.. overlaps everything else) and a dispatcher thread stages each batch
-    (parallel copies into the pinned blob), launches it on one of `depth` contexts (own CUDA streams, staging
+    (parallel copies into the pinned blob), launches it on one of `depth` contexts (own CUDA stream, staging
     arena and device pools, used round-robin) and retires the oldest one when all contexts are busy. Host
-    front-end work of batch k+1 therefore overlaps the kernels and the D2H copies of batch k.
-    This is the serving-shaped entry point (many independent images in flight)."""
+    front-end work of batch k+1 therefore overlaps the kernels and the D2H copies of batch k; the output copies of
+    all contexts leave on the device's one first-in-first-out D2H stream, so batches retire in launch order.
+    This is the serving-shaped entry point (many independent images in flight). bench.py runs it with depth 5."""
 
     def __init__(self, device: int = 0, depth: int = 3, workers: int = 0, staging_threads: int = 4, parse_ahead: int = 2):
         import os
