@@ -184,6 +184,19 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     assert int(out[1]) == (0 if os.path.exists("/dev/nvidia0") else -21)
 
 
+def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path, golden_dir):
+    """examples/decode_files.c (the C host of the file front-end) compiles as pedantic C99, links, and on a box without a
+    GPU stops at jxg_init with the library's own message - there is no CPU decode behind the ABI."""
+    exe = tmp_path / "decode_files"
+    libdir = os.path.dirname(abi.library_path())
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "decode_files.c"), "-o", str(exe), "-L", libdir, "-ljxgpu",
+                    "-Wl,-rpath," + libdir], check=True)
+    if not os.path.exists("/dev/nvidia0"):
+        r = subprocess.run([str(exe), os.path.join(golden_dir, "jxl", "3x3_srgb_lossy.jxl")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
 def test_product_does_not_touch_the_oracle():
     """Nothing under jxl_rs_b200/ may import, link or execute oracle/."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "jxl_rs_b200")):
